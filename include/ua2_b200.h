@@ -1,0 +1,155 @@
+/*
+ * ua2_b200.h - C ABI of the B200-native (sm_100a) UniAudio2 inference hot path.
+ *
+ * The reference (yangdongchao/UniAudio2) is 100% Python/PyTorch and has NO FFI for this path
+ * (SURVEY.md section 0 / 8b), so there is no existing binding to mirror.  Each entry point below names
+ * the reference Python interface it replaces (paths relative to the reference root).  The Python host
+ * side (uniaudio2_b200/llm_models/model_new.py etc.) binds these with ctypes and re-exposes the
+ * reference's class / method names.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success, <0 on error; ua2_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - a handle is thread-compatible (one stream at a time), not thread-safe - same contract as the
+ *     reference's nn.Module with persistent KV caches (lit_model.py:814-860);
+ *   - no host allocation / cudaMalloc happens after ua2_llm_setup_caches() returns.
+ */
+#ifndef UA2_B200_H
+#define UA2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UA2_OK 0
+#define UA2_ERR_INVALID (-1)
+#define UA2_ERR_CUDA (-2)
+#define UA2_ERR_STATE (-3)
+
+const char* ua2_last_error(void);
+/* library / device probe: returns the SM count of the current device (e.g. 148), <0 on error */
+int ua2_device_sm_count(void);
+const char* ua2_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * AR decode: llm_models/model_new.py::Model_stage3 over llm_models/lit_model.py::GPT
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One litgpt GPT stack (llm_models/config.py:785-899, the Llama-3.2 entries). */
+typedef struct ua2_gpt_cfg {
+  int32_t n_layer;
+  int32_t n_embd;
+  int32_t n_head;
+  int32_t n_query_groups;
+  int32_t head_size;          /* 64 or 128 (32 accepted for test configs) */
+  int32_t intermediate_size;
+  float norm_eps;             /* config.py:38, 1e-5 */
+} ua2_gpt_cfg;
+
+/* Model_stage3.__init__ (model_new.py:340-355). */
+typedef struct ua2_llm_cfg {
+  ua2_gpt_cfg backbone;       /* llm_name, e.g. Llama-3.2-3B */
+  ua2_gpt_cfg decoder;        /* decoder_name / local_model, e.g. Llama-3.2-300M */
+  ua2_gpt_cfg understanding;  /* hard-wired 'Llama-3.2-Understanding' (model_new.py:351) */
+  ua2_gpt_cfg generation;     /* hard-wired 'Llama-3.2-Generation'   (model_new.py:354) */
+  int32_t text_vocab;         /* backbone padded_vocab_size (128256) */
+  int32_t audio_vocab;        /* audio_semantic_vocab_size + audio_reason_vocab_size */
+  int32_t num_codebooks;      /* audio_num_codebooks (8) */
+  int32_t max_seq_length;     /* KV slots of the three global stacks (2048, model_new.py:560-565) */
+} ua2_llm_cfg;
+
+typedef struct ua2_llm ua2_llm;
+
+/* Model_stage3(config) - model_new.py:340.  Allocates nothing on the device yet. */
+int ua2_llm_create(const ua2_llm_cfg* cfg, ua2_llm** out);
+int ua2_llm_destroy(ua2_llm* h);
+
+/* load_state_dict / resume_for_inference (llm_utils/train_utils.py:159-177): register one fp32
+ * parameter by its reference state-dict key ("backbone.transformer.h.3.attn.qkv.weight",
+ * "audio_embeddings.weight", "projection.weight", "audio_head", ...).  The tensor must stay alive
+ * and unchanged for the life of the handle, EXCEPT "audio_head" (num_codebooks, d, V_a), which is
+ * repacked into the library's own (num_codebooks, V_a, d) layout at ua2_llm_setup_caches() time.
+ * `rope_cos` / `rope_sin` tables are registered the same way under the pseudo keys
+ * "<stack>.rope_cos" / "<stack>.rope_sin" with shape (max_positions, head_size) - they are the
+ * output of lit_model.py:634-706 build_rope_cache, computed by the host side. */
+int ua2_llm_load_weight(ua2_llm* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+
+/* Model_stage3.setup_caches(max_batch_size) - model_new.py:554-565.  Allocates KV caches
+ * (B, n_query_groups, max_seq, head_size) fp32 per layer, workspaces, and validates that every
+ * parameter has been registered.  max_prefill_rows bounds the rows processed per prefill chunk. */
+int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream);
+
+/* Model_stage3.reset_caches() - model_new.py:647-651 (zero-fills every KV buffer). */
+int ua2_llm_reset_caches(ua2_llm* h, void* stream);
+
+/* Model_stage3.forward_prefix - model_new.py:456-507, KV-cache side effect only (every caller
+ * discards the returned logits, e.g. evaluation/tts_task.py:244).
+ *   tokens   (B, T, num_codebooks+1) int64   audio streams in cols 0..nq-1, text in col nq
+ *   mask     (B, T, num_codebooks+1) uint8   already sliced to the T processed rows
+ *   pos      (B, T) int64                    cache slot / RoPE position of each row
+ *   max_pos  host copy of max(pos) (bounds the attention span like input_pos_maxp1); -1 = unknown */
+int ua2_llm_prefill(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, const int64_t* pos, int B, int T,
+                    int64_t max_pos, void* stream);
+
+/* Model_stage3.generate_frame - model_new.py:568-645.
+ *   tokens (B,1,nq+1) int64, mask (B,1,nq+1) uint8, input_pos scalar (the reference passes a
+ *   1-element tensor shared by all rows, tts_task.py:245), temperature > 0, topk >= 1,
+ *   forbid_prefix >= 0, cfg_scale (CFG active iff cfg_scale > 1 and B > 1, model_new.py:618).
+ *   noise: nullable.  If non-null: Exp(1) draws, laid out [R x text_vocab | nq x (R x audio_vocab)]
+ *   with R = sampled rows (B, or 1 under CFG) - the draws the reference would take from
+ *   torch.empty_like(probs).exponential_(1) (model_new.py:141-143).  If null the library draws
+ *   Exp(1) itself from Philox4x32-10 keyed by (seed, frame counter).
+ *   out (B, 1+nq) int32: col 0 text token, cols 1.. audio tokens (merged id space).
+ * Error behaviour mirrors model_new.py:165-180 (ValueError cases -> UA2_ERR_INVALID). */
+int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, int B, int64_t input_pos,
+                           float temperature, int topk, int forbid_prefix, float cfg_scale, const float* noise,
+                           uint64_t seed, int32_t* out, void* stream);
+
+/* Introspection for parity tests: device pointers of internal buffers (valid until destroy).
+ * which: 0 backbone, 1 decoder, 2 understanding, 3 generation. */
+int ua2_llm_get_kv(ua2_llm* h, int which, int layer, float** k, float** v);
+/* name: "h_final" (B x n_embd), "text_logits" (B x text_vocab), "audio_logits" (nq x B x audio_vocab) */
+int ua2_llm_get_buffer(ua2_llm* h, const char* name, float** ptr, int64_t* numel);
+/* knobs: "graph" (0/1, default 1: replay the frame as a CUDA graph), "pdl" (0/1) */
+int ua2_llm_set_option(ua2_llm* h, const char* name, int value);
+/* number of kernels launched (or graph kernel nodes replayed) by the last prefill / generate_frame */
+int ua2_llm_last_launch_count(ua2_llm* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone operators (unit-parity surface; the handle API above is built from these kernels)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y[m, n] = sum_k f(x)[m,k] * W[n,k]    (lit_model.py:424/511/592-595 F.linear, bias-free)
+ *   norm_w != NULL : f = RMSNorm(x; norm_w, eps) (lit_model.py:883-890) fused in front
+ *   residual != NULL : y += residual (Block.forward residual adds, lit_model.py:344-349)        */
+int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float eps, const float* residual, float* y,
+                   int M, int N, int K, void* stream);
+/* y[m, n] = silu(sum_k f(x) W1[n,k]) * (sum_k f(x) W2[n,k])   (LLaMAMLP fc_1/fc_2, lit_model.py:591-594) */
+int ua2_swiglu_f32(const float* x, const float* W1, const float* W2, const float* norm_w, float eps, float* y, int M,
+                   int N, int K, void* stream);
+/* fused RMSNorm -> QKV linear -> half-split RoPE -> KV-cache append (lit_model.py:424-467).
+ *   pos (M) int32 cache slot per row, bidx (M) int32 batch row in the cache;
+ *   q_out (M, n_head*hs); k_cache/v_cache (B, G, S_max, hs); cos/sin (>=max pos, hs). */
+int ua2_qkv_rope_f32(const float* x, const float* Wqkv, const float* norm_w, float eps, const int32_t* pos,
+                     const int32_t* bidx, const float* cos, const float* sin, float* q_out, float* k_cache,
+                     float* v_cache, int M, int K, int n_head, int n_groups, int hs, int S_max, void* stream);
+/* causal GQA attention of M query rows against the cache: softmax(q k^T / sqrt(hs)) v over slots
+ * 0..pos[m] (lit_model.py:468-532).  y (M, n_head*hs).  workspace: see ua2_attn_workspace_floats. */
+int ua2_attn_f32(const float* q, const float* k_cache, const float* v_cache, const int32_t* pos, const int32_t* bidx,
+                 float* y, float* workspace, int M, int n_head, int n_groups, int hs, int S_max, void* stream);
+int64_t ua2_attn_workspace_floats(int M, int n_head, int hs, int S_max);
+/* sample_topk / audio_sample_topk (model_new.py:146-187) on R rows of V logits.
+ *   cfg_scale > 1: logits has 2R rows (cond rows first R? no: row 0 = cond, row 1 = uncond, R must be 1)
+ *   noise nullable (R x V Exp(1) draws); out (R) int32. */
+int ua2_sample_topk_f32(const float* logits, int R, int V, float temperature, int topk, int forbid_prefix,
+                        float cfg_scale, const float* noise, uint64_t seed, uint64_t offset, int32_t* out,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UA2_B200_H */

@@ -1,0 +1,107 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/ua2_b200.h declares, and its argument
+validation (the reference's ValueError paths) works without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from uniaudio2_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        from uniaudio2_b200.build import build
+
+        build()
+    return _lib.lib()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ua2_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ua2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(L):
+    from uniaudio2_b200 import _lib
+
+    declared = _declared_symbols()
+    assert declared, "no symbols parsed from the header"
+    assert sorted(_lib.SYMBOLS.keys()) == declared
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/ua2_b200.h but not exported by the .so"
+
+
+def test_version_and_error_string(L):
+    assert b"sm_100a" in L.ua2_version()
+    assert isinstance(L.ua2_last_error(), bytes)
+
+
+def test_create_validates_config(L):
+    from uniaudio2_b200 import _lib
+
+    good = _lib.GptCfg(2, 256, 4, 2, 64, 512, 1e-5)
+    bad_hs = _lib.GptCfg(2, 256, 4, 2, 48, 512, 1e-5)
+    h = C.c_void_p()
+    cfg = _lib.LlmCfg(good, good, good, good, 1024, 128, 8, 64)
+    assert L.ua2_llm_create(C.byref(cfg), C.byref(h)) == 0
+    # setup before weights are registered must fail loudly, not crash
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_llm_setup_caches(h, 1, None))
+    # unknown key
+    shape = (C.c_int64 * 2)(4, 4)
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_llm_load_weight(h, b"no.such.weight", C.c_void_p(16), shape, 2))
+    # wrong shape for a known key
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_llm_load_weight(h, b"backbone.transformer.h.0.attn.qkv.weight", C.c_void_p(16), shape, 2))
+    assert L.ua2_llm_destroy(h) == 0
+    cfg2 = _lib.LlmCfg(bad_hs, good, good, good, 1024, 128, 8, 64)
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_llm_create(C.byref(cfg2), C.byref(h)))
+    assert b"head_size" in L.ua2_last_error()
+
+
+def test_sampler_argument_errors_without_gpu(L):
+    """model_new.py:165-180 error cases are rejected before any CUDA call."""
+    from uniaudio2_b200 import _lib
+
+    p = C.c_void_p(16)
+    for (temp, topk, forbid) in ((0.0, 1, 0), (1.0, 1, -1), (1.0, 1, 64), (1.0, 0, 0), (1.0, 33, 32)):
+        with pytest.raises(ValueError):
+            _lib.check(L.ua2_sample_topk_f32(p, 1, 64, temp, topk, forbid, 1.0, None, 0, 0, p, None))
+
+
+def test_product_has_no_cpu_fallback():
+    import torch
+
+    from uniaudio2_b200 import _lib
+    from uniaudio2_b200.llm_models import config as pc
+    from uniaudio2_b200.llm_models.model_new import Model_stage3, ModelArgs
+
+    pc.name_to_config["t-bb"] = dict(name="t-bb", n_layer=1, n_embd=128, n_head=2, n_query_groups=1, intermediate_size=256, padded_vocab_size=64)
+    saved = {k: pc.name_to_config[k] for k in ("Llama-3.2-Understanding", "Llama-3.2-Generation")}
+    pc.name_to_config["Llama-3.2-Understanding"] = dict(pc.name_to_config["t-bb"])
+    pc.name_to_config["Llama-3.2-Generation"] = dict(pc.name_to_config["t-bb"])
+    try:
+        m = Model_stage3(ModelArgs("t-bb", "t-bb", "", "", "", 30, 2, 8))
+    finally:
+        pc.name_to_config.update(saved)
+    with pytest.raises(_lib.Ua2Error):
+        m.setup_caches(1)  # parameters on the CPU -> refuse
+    with pytest.raises(TypeError):
+        m.reset_caches()  # lit_model.py:134-135 'You need to call set_kv_cache'
+
+
+def test_product_does_not_import_oracle():
+    """The product package must not reference oracle/ (parity would be void)."""
+    pkg = os.path.join(ROOT, "uniaudio2_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"

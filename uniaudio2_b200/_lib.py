@@ -1,0 +1,92 @@
+"""ctypes binding of libua2_b200.so (the C ABI declared in include/ua2_b200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libua2_b200.so")
+
+_lib = None
+
+
+class Ua2Error(RuntimeError):
+    pass
+
+
+class GptCfg(C.Structure):
+    _fields_ = [("n_layer", C.c_int32), ("n_embd", C.c_int32), ("n_head", C.c_int32), ("n_query_groups", C.c_int32),
+                ("head_size", C.c_int32), ("intermediate_size", C.c_int32), ("norm_eps", C.c_float)]
+
+
+class LlmCfg(C.Structure):
+    _fields_ = [("backbone", GptCfg), ("decoder", GptCfg), ("understanding", GptCfg), ("generation", GptCfg),
+                ("text_vocab", C.c_int32), ("audio_vocab", C.c_int32), ("num_codebooks", C.c_int32),
+                ("max_seq_length", C.c_int32)]
+
+
+# every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "ua2_last_error": (C.c_char_p, []),
+    "ua2_device_sm_count": (C.c_int, []),
+    "ua2_version": (C.c_char_p, []),
+    "ua2_llm_create": (C.c_int, [C.POINTER(LlmCfg), C.POINTER(_P)]),
+    "ua2_llm_destroy": (C.c_int, [_P]),
+    "ua2_llm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_llm_setup_caches": (C.c_int, [_P, C.c_int, _P]),
+    "ua2_llm_reset_caches": (C.c_int, [_P, _P]),
+    "ua2_llm_prefill": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, _P]),
+    "ua2_llm_generate_frame": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_float, _P,
+                                         C.c_uint64, _P, _P]),
+    "ua2_llm_get_kv": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "ua2_llm_get_buffer": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "ua2_llm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "ua2_llm_last_launch_count": (C.c_int, [_P]),
+    "ua2_linear_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_swiglu_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_qkv_rope_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_attn_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_attn_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ua2_sample_topk_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, _P, C.c_uint64,
+                                      C.c_uint64, _P, _P]),
+}
+
+
+def lib():
+    """Load (once) and return the ctypes library with typed signatures."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Ua2Error(f"{LIB_PATH} not found - build it with `python -m uniaudio2_b200.build` "
+                           "(there is no CPU fallback for this path)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().ua2_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}" if what else msg)  # mirrors the reference's ValueError cases
+        if rc == -3:
+            raise TypeError(f"{what}: {msg}" if what else msg)  # lit_model.py:134-135 'You need to call set_kv_cache'
+        raise Ua2Error(f"{what}: {msg}" if what else msg)
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor as c_void_p; None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

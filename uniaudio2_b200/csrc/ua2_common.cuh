@@ -1,0 +1,84 @@
+// Shared device/host helpers for the sm_100a kernels of the UniAudio2 hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace ua2 {
+
+// ---- error plumbing (thread-local message surfaced through ua2_last_error) ----
+void set_error(const std::string& msg);
+#define UA2_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::ua2::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                       std::to_string(__LINE__));                                                 \
+      return UA2_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+#define UA2_REQUIRE(cond, msg)                    \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::ua2::set_error(std::string("invalid argument: ") + (msg)); \
+      return UA2_ERR_INVALID;                     \
+    }                                             \
+  } while (0)
+
+// ---- device helpers ----
+// Streaming 128-bit load for weights: read-only path, do not allocate in L1 (weights are touched once per
+// launch; activations staged in shared memory keep L1/smem for themselves).
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Programmatic dependent launch (PDL): wait for the producer grid's memory to be visible / let the
+// dependent grid start its prologue early.  No-ops when the launch carries no PDL attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Per-launch context shared by the host-side launchers.
+struct LaunchCtx {
+  cudaStream_t stream = nullptr;
+  bool pdl = false;       // attach the programmatic-stream-serialization attribute
+  int* launch_counter = nullptr;
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (lc.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (lc.launch_counter) ++*lc.launch_counter;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+}  // namespace ua2

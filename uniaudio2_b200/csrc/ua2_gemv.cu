@@ -1,0 +1,311 @@
+// Skinny fp32 linear family (M <= 8 rows per tile) for the AR-decode hot path.
+//
+// Replaces the F.linear call sites of llm_models/lit_model.py:424 (qkv), :511 (attn proj), :592-595 (LLaMAMLP) and
+// llm_models/model_new.py:617 (lm_head), :631 (projection), :632 (audio_head mm) - all bias-free, fp32.
+//
+// Roofline: HBM.  At M <= 8 the arithmetic intensity is <= 4 FLOP/B, so the kernel is a weight streamer:
+//   * each warp owns two weight rows ("unit") and streams them with 128-bit ld.global.nc.L1::no_allocate loads,
+//     16 loads (8 KB) in flight per warp before the first FMA; the first batch is issued BEFORE the activation
+//     prologue (and before griddepcontrol.wait), so the weight stream does not stall on the producer kernel;
+//   * the M x K activation tile is produced once per CTA in shared memory by a fused prologue
+//     (plain copy | RMSNorm | embedding gather | split-softmax attention combine) and read conflict-free;
+//   * a fused epilogue consumes the two row sums (store | residual add | RoPE + KV-cache append | SwiGLU).
+// Algorithmic bytes per launch = 4*N*K (weights) (+ 4*M*(K+N) activations, negligible).
+#include "ua2_kernels.cuh"
+
+namespace ua2 {
+
+namespace {
+
+constexpr int U = 8;  // k-iterations (of 128 floats) per load batch
+
+template <int EPI>
+__device__ __forceinline__ void unit_rows(const GemvParams& p, int u, const float*& rowA, const float*& rowB, int& nA,
+                                          int& nB) {
+  if (EPI == EPI_SWIGLU) {
+    nA = nB = u;
+    rowA = p.W + (size_t)u * p.K;
+    rowB = p.W2 + (size_t)u * p.K;
+  } else if (EPI == EPI_QKV) {
+    const int half = p.hs >> 1;
+    const int hh = u / half, i = u - hh * half;
+    nA = hh * p.hs + i;
+    nB = nA + half;
+    rowA = p.W + (size_t)nA * p.K;
+    rowB = p.W + (size_t)nB * p.K;
+  } else {
+    nA = 2 * u;
+    nB = nA + 1;
+    rowA = p.W + (size_t)nA * p.K;
+    rowB = p.W + (size_t)nB * p.K;
+  }
+}
+
+__device__ __forceinline__ void load_batch(const float* rowA, const float* rowB, int it0, int lane, int K,
+                                           float4 (&wa)[U], float4 (&wb)[U]) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int k4 = ((it0 + u) * 32 + lane) * 4;
+    if (k4 < K) {
+      wa[u] = ldg_stream(rowA + k4);
+      wb[u] = ldg_stream(rowB + k4);
+    } else {
+      wa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <int MT, int PRO, int EPI>
+__global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
+  extern __shared__ __align__(16) float xs[];  // MT x Kp
+  __shared__ float red[8][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int K = p.K;
+  const int nIt = (K + 127) >> 7;
+  const int Kp = nIt << 7;
+  const int m0 = blockIdx.x * MT;
+  const int mcount = min(MT, p.M - m0);
+  const int n_units = (EPI == EPI_SWIGLU) ? p.N : (p.N >> 1);
+  int unit = blockIdx.y * nwarps + warp;
+  const int unit_stride = gridDim.y * nwarps;
+
+  // ---- issue the first weight batch before anything that depends on the producer kernel
+  float4 wa[U], wb[U];
+  const float *rowA = nullptr, *rowB = nullptr;
+  int nA = 0, nB = 0;
+  if (unit < n_units) {
+    unit_rows<EPI>(p, unit, rowA, rowB, nA, nB);
+    load_batch(rowA, rowB, 0, lane, K, wa, wb);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- prologue: activation tile -> shared memory
+  if (PRO == PRO_PLAIN || PRO == PRO_RMSNORM || PRO == PRO_GATHER) {
+    float ss[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) ss[m] = 0.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float* src = nullptr;
+      if (m < mcount) {
+        if (PRO == PRO_GATHER) {
+          const long long row = (long long)p.gidx[(size_t)(m0 + m) * p.gidx_stride] + p.gidx_offset;
+          src = p.emb + (size_t)row * K;
+        } else {
+          src = p.X + (size_t)(m0 + m) * p.ldx;
+        }
+      }
+      for (int k = tid * 4; k < Kp; k += blockDim.x * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr && k < K) v = *reinterpret_cast<const float4*>(src + k);
+        if (PRO == PRO_RMSNORM) ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
+      }
+    }
+    if (PRO == PRO_RMSNORM) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float s = warp_sum(ss[m]);
+        if (lane == 0) red[m][warp] = s;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        float tot = 0.f;
+        for (int w = 0; w < nwarps; ++w) tot += red[m][w];
+        const float rs = rsqrtf(tot / (float)K + p.eps);  // lit_model.py:887-888
+        for (int k = tid * 4; k < K; k += blockDim.x * 4) {
+          float4 v = *reinterpret_cast<float4*>(xs + m * Kp + k);
+          const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k);
+          v.x = (v.x * rs) * g.x;
+          v.y = (v.y * rs) * g.y;
+          v.z = (v.z * rs) * g.z;
+          v.w = (v.w * rs) * g.w;
+          *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
+        }
+      }
+    }
+  } else {  // PRO_ATTN: merge the split-softmax partials (flash-decoding combine) into y (M, n_head*hs)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const int n_s = (m < mcount) ? (p.pos[m0 + m] + ATTN_CHUNK) / ATTN_CHUNK : 0;
+      for (int k = tid * 4; k < Kp; k += blockDim.x * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_s > 0 && k < K) {
+          const int hh = k / p.hs, d = k - hh * p.hs;
+          const size_t base = ((size_t)(m0 + m) * p.n_head + hh) * p.max_splits;
+          float mx = -INFINITY;
+          for (int s = 0; s < n_s; ++s) mx = fmaxf(mx, p.ml_part[(base + s) * 2]);
+          float den = 0.f;
+          for (int s = 0; s < n_s; ++s) {
+            const float w = __expf(p.ml_part[(base + s) * 2] - mx);
+            den += w * p.ml_part[(base + s) * 2 + 1];
+            const float4 o = *reinterpret_cast<const float4*>(p.o_part + (base + s) * p.hs + d);
+            v.x += w * o.x;
+            v.y += w * o.y;
+            v.z += w * o.z;
+            v.w += w * o.w;
+          }
+          const float inv = 1.f / den;
+          v.x *= inv;
+          v.y *= inv;
+          v.z *= inv;
+          v.w *= inv;
+        }
+        *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- main loop: two weight rows per warp, all M rows of the tile at once
+  bool first = true;
+  while (unit < n_units) {
+    if (!first) unit_rows<EPI>(p, unit, rowA, rowB, nA, nB);
+    float accA[MT], accB[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) accA[m] = accB[m] = 0.f;
+    for (int it0 = 0; it0 < nIt; it0 += U) {
+      if (!(first && it0 == 0)) load_batch(rowA, rowB, it0, lane, K, wa, wb);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k4 = ((it0 + u) * 32 + lane) * 4;
+        if (k4 < Kp) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + m * Kp + k4);
+            accA[m] = fmaf(wa[u].x, xv.x, accA[m]);
+            accA[m] = fmaf(wa[u].y, xv.y, accA[m]);
+            accA[m] = fmaf(wa[u].z, xv.z, accA[m]);
+            accA[m] = fmaf(wa[u].w, xv.w, accA[m]);
+            accB[m] = fmaf(wb[u].x, xv.x, accB[m]);
+            accB[m] = fmaf(wb[u].y, xv.y, accB[m]);
+            accB[m] = fmaf(wb[u].z, xv.z, accB[m]);
+            accB[m] = fmaf(wb[u].w, xv.w, accB[m]);
+          }
+        }
+      }
+    }
+    first = false;
+    // ---- warp reduction; lane m keeps row m
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float sa = warp_sum(accA[m]);
+      const float sb = warp_sum(accB[m]);
+      if (lane == m) {
+        a = sa;
+        b = sb;
+      }
+    }
+    if (lane < mcount) {
+      const int m = m0 + lane;
+      if (EPI == EPI_STORE) {
+        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a, b);
+      } else if (EPI == EPI_RESADD) {
+        const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
+        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a + r.x, b + r.y);
+      } else if (EPI == EPI_SWIGLU) {
+        const float s = a / (1.0f + expf(-a));  // F.silu, lit_model.py:594
+        p.Y[(size_t)m * p.ldy + nA] = s * b;
+      } else {  // EPI_QKV: split, half-split RoPE (lit_model.py:795-806), KV-cache append (:854-855)
+        const int hs = p.hs, half = hs >> 1;
+        const int hh = nA / hs, i = nA - hh * hs;
+        const int ps = p.pos[m];
+        if (hh < p.n_head + p.n_groups) {
+          const float c0 = p.cos[(size_t)ps * hs + i], s0 = p.sin[(size_t)ps * hs + i];
+          const float c1 = p.cos[(size_t)ps * hs + i + half], s1 = p.sin[(size_t)ps * hs + i + half];
+          const float ra = __fadd_rn(__fmul_rn(a, c0), __fmul_rn(-b, s0));
+          const float rb = __fadd_rn(__fmul_rn(b, c1), __fmul_rn(a, s1));
+          if (hh < p.n_head) {
+            float* q = p.q_out + (size_t)m * (p.n_head * hs) + hh * hs + i;
+            q[0] = ra;
+            q[half] = rb;
+          } else {
+            const int g = hh - p.n_head;
+            float* kc = p.k_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
+            kc[0] = ra;
+            kc[half] = rb;
+          }
+        } else {
+          const int g = hh - p.n_head - p.n_groups;
+          float* vc = p.v_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
+          vc[0] = a;
+          vc[half] = b;
+        }
+      }
+    }
+    unit += unit_stride;
+  }
+}
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <int MT, int PRO, int EPI>
+cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
+  const int nIt = (p.K + 127) >> 7;
+  const size_t smem = (size_t)MT * nIt * 128 * sizeof(float);
+  auto kern = gemv_kernel<MT, PRO, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  const int n_units = (EPI == EPI_SWIGLU) ? p.N : p.N / 2;
+  const int m_tiles = (p.M + MT - 1) / MT;
+  // 8 warps per CTA when that still gives >= 2 CTAs per SM, else 4 (finer granules balance small N)
+  int nwarps = (n_units >= 8 * 2 * sm_count()) ? 8 : 4;
+  int gy = (n_units + nwarps - 1) / nwarps;
+  const int cap = sm_count() * 8;  // persistent cap for very tall matrices (lm_head): warps loop over units
+  if (gy > cap) gy = cap;
+  return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), smem, p);
+}
+
+template <int PRO, int EPI>
+cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
+  // tile of M rows per CTA; bounded by shared memory (MT*K*4 <= 200 KB)
+  const size_t rowb = (size_t)((p.K + 127) / 128) * 128 * 4;
+  int mt = p.M >= 8 ? 8 : (p.M >= 3 ? 4 : p.M);
+  while (mt > 1 && mt * rowb > 160 * 1024) mt >>= 1;
+  switch (mt) {
+    case 1: return launch_one<1, PRO, EPI>(lc, p);
+    case 2: return launch_one<2, PRO, EPI>(lc, p);
+    case 4: return launch_one<4, PRO, EPI>(lc, p);
+    default: return launch_one<8, PRO, EPI>(lc, p);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;
+#define UA2_CASE(P, E) \
+  if (pro == P && epi == E) return launch_mt<P, E>(lc, p);
+  UA2_CASE(PRO_PLAIN, EPI_STORE)
+  UA2_CASE(PRO_PLAIN, EPI_RESADD)
+  UA2_CASE(PRO_PLAIN, EPI_SWIGLU)
+  UA2_CASE(PRO_PLAIN, EPI_QKV)
+  UA2_CASE(PRO_RMSNORM, EPI_STORE)
+  UA2_CASE(PRO_RMSNORM, EPI_RESADD)
+  UA2_CASE(PRO_RMSNORM, EPI_SWIGLU)
+  UA2_CASE(PRO_RMSNORM, EPI_QKV)
+  UA2_CASE(PRO_GATHER, EPI_STORE)
+  UA2_CASE(PRO_ATTN, EPI_RESADD)
+#undef UA2_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace ua2

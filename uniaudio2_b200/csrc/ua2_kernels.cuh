@@ -1,0 +1,100 @@
+// Kernel launch surface shared between the handle API (ua2_llm.cu) and the stand-alone operator API.
+#pragma once
+#include "ua2_common.cuh"
+
+namespace ua2 {
+
+// ---------------------------------------------------------------- skinny linear (GEMV family)
+enum : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_GATHER = 2, PRO_ATTN = 3 };
+enum : int { EPI_STORE = 0, EPI_RESADD = 1, EPI_QKV = 2, EPI_SWIGLU = 3 };
+
+constexpr int ATTN_CHUNK = 128;  // keys per split CTA of the attention kernel
+
+struct GemvParams {
+  // weights: W (N x K) row-major fp32 (nn.Linear layout); W2 second matrix for SwiGLU
+  const float* W = nullptr;
+  const float* W2 = nullptr;
+  int N = 0, K = 0, M = 0;
+  // ---- prologue (how the M x K activation tile is produced in shared memory)
+  const float* X = nullptr;  // PLAIN / RMSNORM source, row stride ldx
+  int ldx = 0;
+  const float* norm_w = nullptr;  // RMSNORM weight (K)
+  float eps = 0.f;
+  const float* emb = nullptr;  // GATHER: X[m] = emb[(gidx[m*gidx_stride] + gidx_offset) * K ...]
+  const int32_t* gidx = nullptr;
+  int gidx_stride = 0, gidx_offset = 0;
+  const float* o_part = nullptr;  // ATTN: split-softmax partials of the attention kernel
+  const float* ml_part = nullptr;
+  int max_splits = 0;
+  const int32_t* pos = nullptr;   // (M) cache slot / position of each row
+  const int32_t* bidx = nullptr;  // (M) batch row of each row
+  int n_head = 0, n_groups = 0, hs = 0;
+  // ---- epilogue
+  float* Y = nullptr;  // STORE / RESADD / SWIGLU destination, row stride ldy
+  int ldy = 0;
+  const float* R = nullptr;  // RESADD residual, row stride ldr (may alias Y)
+  int ldr = 0;
+  float* q_out = nullptr;  // QKV: roped queries (M, n_head*hs)
+  float* k_cache = nullptr;  // (B, G, S_max, hs)
+  float* v_cache = nullptr;
+  const float* cos = nullptr;  // (positions, hs)
+  const float* sin = nullptr;
+  int S_max = 0;
+};
+cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
+
+// ---------------------------------------------------------------- attention over the KV cache
+struct AttnParams {
+  const float* q = nullptr;  // (M, n_head*hs) roped
+  const float* k_cache = nullptr;
+  const float* v_cache = nullptr;
+  const int32_t* pos = nullptr;
+  const int32_t* bidx = nullptr;
+  float* o_part = nullptr;   // (M, n_head, max_splits, hs)
+  float* ml_part = nullptr;  // (M, n_head, max_splits, 2)
+  int M = 0, n_head = 0, n_groups = 0, hs = 0, S_max = 0, max_splits = 0;
+  int n_splits_launch = 0;  // grid.x (>= splits needed by the largest pos in this launch)
+};
+cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p);
+cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float* y);
+
+// ---------------------------------------------------------------- small fused elementwise kernels
+struct FrameScalars {  // per-call scalars living in device memory so captured graphs stay valid
+  float temperature;
+  int topk;
+  int forbid_prefix;
+  float cfg_scale;
+  unsigned long long seed;
+  unsigned long long offset;
+  const float* noise;  // nullable
+  int32_t* out;        // (B, 1+nq)
+  int rows;            // sampled rows R
+  int B;
+};
+
+// embedding merge of model_new.py:598-604: audio_in[m] = sum_c mask[m,c] * E[tok[m,c] + c*V]; text_emb[m] = wte[tok[m,nq]]
+cudaError_t launch_embed(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, const float* audio_emb,
+                         const float* wte, float* audio_in, float* text_emb, int M, int nq, int V, int D);
+// out[m] = RMSNorm(x[m]; w) * ma[m] + add[m] * mt[m]; optional normed copy kept in `keep`
+//   ma = mask[m*(nq+1)+0], mt = mask[m*(nq+1)+nq] (audio-step / text-step masks, model_new.py:594-595)
+cudaError_t launch_norm_mix(const LaunchCtx& lc, const float* x, const float* w, float eps, const uint8_t* mask,
+                            int nq, const float* add, float* keep, float* out, int M, int D, int mode);
+enum : int { MIX_UND_TO_BACKBONE = 0, MIX_BACKBONE_TO_GEN = 1, MIX_FINAL = 2, MIX_NORM_ONLY = 3 };
+
+// per-frame begin: copy caller tokens/mask into the handle's fixed buffers and write scalars
+cudaError_t launch_frame_begin(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, int n_tok,
+                               int64_t* d_tokens, uint8_t* d_mask, int32_t* d_pos, int32_t* d_bidx, int B,
+                               int32_t pos_value, FrameScalars* d_fs, FrameScalars fs);
+cudaError_t launch_prefill_begin(const LaunchCtx& lc, const int64_t* pos64, int32_t* d_pos, int32_t* d_bidx, int M,
+                                 int T, int row0);
+// audio_head (nq, d, V) -> (nq, V, d)
+cudaError_t launch_transpose_head(const LaunchCtx& lc, const float* src, float* dst, int nq, int d, int V);
+
+// ---------------------------------------------------------------- sampler
+// logits: (rows_in, V); rows sampled = fs->rows; CFG mixes row 0 (cond) and row 1 (uncond).
+// out_col: column of FrameScalars::out to write (row stride out_ld); noise_off: float offset into fs->noise
+cudaError_t launch_sampler(const LaunchCtx& lc, const float* logits, int V, const FrameScalars* d_fs, int is_audio,
+                           int out_col, int out_ld, long long noise_off, unsigned long long stream_id, int B,
+                           int rows);
+
+}  // namespace ua2

@@ -1,0 +1,152 @@
+// Stand-alone operator entry points of the C ABI (unit-parity surface).  Same kernels as the handle path.
+#include "../../include/ua2_b200.h"
+#include "ua2_kernels.cuh"
+
+using namespace ua2;
+
+extern "C" {
+
+int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float eps, const float* residual, float* y,
+                   int M, int N, int K, void* stream) {
+  UA2_REQUIRE(x && W && y, "null argument");
+  UA2_REQUIRE(M >= 1 && N >= 2 && (N % 2) == 0 && K >= 4 && (K % 4) == 0, "need M>=1, even N, K % 4 == 0");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  GemvParams p;
+  p.W = W;
+  p.N = N;
+  p.K = K;
+  p.M = M;
+  p.X = x;
+  p.ldx = K;
+  p.norm_w = norm_w;
+  p.eps = eps;
+  p.Y = y;
+  p.ldy = N;
+  p.R = residual;
+  p.ldr = N;
+  UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, residual ? EPI_RESADD : EPI_STORE, p));
+  return UA2_OK;
+}
+
+int ua2_swiglu_f32(const float* x, const float* W1, const float* W2, const float* norm_w, float eps, float* y, int M,
+                   int N, int K, void* stream) {
+  UA2_REQUIRE(x && W1 && W2 && y, "null argument");
+  UA2_REQUIRE(M >= 1 && N >= 1 && K >= 4 && (K % 4) == 0, "need M>=1, K % 4 == 0");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  GemvParams p;
+  p.W = W1;
+  p.W2 = W2;
+  p.N = N;
+  p.K = K;
+  p.M = M;
+  p.X = x;
+  p.ldx = K;
+  p.norm_w = norm_w;
+  p.eps = eps;
+  p.Y = y;
+  p.ldy = N;
+  UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, EPI_SWIGLU, p));
+  return UA2_OK;
+}
+
+int ua2_qkv_rope_f32(const float* x, const float* Wqkv, const float* norm_w, float eps, const int32_t* pos,
+                     const int32_t* bidx, const float* cos, const float* sin, float* q_out, float* k_cache,
+                     float* v_cache, int M, int K, int n_head, int n_groups, int hs, int S_max, void* stream) {
+  UA2_REQUIRE(x && Wqkv && pos && bidx && cos && sin && q_out && k_cache && v_cache, "null argument");
+  UA2_REQUIRE(hs == 32 || hs == 64 || hs == 128, "head_size must be 32/64/128");
+  UA2_REQUIRE(M >= 1 && K >= 4 && (K % 4) == 0 && n_groups >= 1 && n_head % n_groups == 0, "bad shape");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  GemvParams p;
+  p.W = Wqkv;
+  p.N = (n_head + 2 * n_groups) * hs;
+  p.K = K;
+  p.M = M;
+  p.X = x;
+  p.ldx = K;
+  p.norm_w = norm_w;
+  p.eps = eps;
+  p.pos = pos;
+  p.bidx = bidx;
+  p.n_head = n_head;
+  p.n_groups = n_groups;
+  p.hs = hs;
+  p.q_out = q_out;
+  p.k_cache = k_cache;
+  p.v_cache = v_cache;
+  p.cos = cos;
+  p.sin = sin;
+  p.S_max = S_max;
+  UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, EPI_QKV, p));
+  return UA2_OK;
+}
+
+int64_t ua2_attn_workspace_floats(int M, int n_head, int hs, int S_max) {
+  const int64_t splits = (S_max + ATTN_CHUNK - 1) / ATTN_CHUNK;
+  return (int64_t)M * n_head * splits * (hs + 2);
+}
+
+int ua2_attn_f32(const float* q, const float* k_cache, const float* v_cache, const int32_t* pos, const int32_t* bidx,
+                 float* y, float* workspace, int M, int n_head, int n_groups, int hs, int S_max, void* stream) {
+  UA2_REQUIRE(q && k_cache && v_cache && pos && bidx && y && workspace, "null argument");
+  UA2_REQUIRE(hs == 32 || hs == 64 || hs == 128, "head_size must be 32/64/128");
+  UA2_REQUIRE(M >= 1 && M <= 65535 && n_groups >= 1 && n_head % n_groups == 0 && n_head / n_groups <= 4, "bad shape");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  AttnParams a;
+  a.q = q;
+  a.k_cache = k_cache;
+  a.v_cache = v_cache;
+  a.pos = pos;
+  a.bidx = bidx;
+  a.M = M;
+  a.n_head = n_head;
+  a.n_groups = n_groups;
+  a.hs = hs;
+  a.S_max = S_max;
+  a.max_splits = (S_max + ATTN_CHUNK - 1) / ATTN_CHUNK;
+  a.n_splits_launch = a.max_splits;
+  a.o_part = workspace;
+  a.ml_part = workspace + (size_t)M * n_head * a.max_splits * hs;
+  UA2_CHECK_CUDA(launch_attn(lc, a));
+  UA2_CHECK_CUDA(launch_attn_combine(lc, a, y));
+  return UA2_OK;
+}
+
+int ua2_sample_topk_f32(const float* logits, int R, int V, float temperature, int topk, int forbid_prefix,
+                        float cfg_scale, const float* noise, uint64_t seed, uint64_t offset, int32_t* out,
+                        void* stream) {
+  UA2_REQUIRE(logits && out, "null argument");
+  UA2_REQUIRE(temperature > 0.f, "temperature must be > 0");          // model_new.py:165-166
+  UA2_REQUIRE(forbid_prefix >= 0, "forbid_prefix must be >= 0");      // :167-168
+  UA2_REQUIRE(forbid_prefix < V, "forbid_prefix must be smaller than vocab size");  // :171-172
+  UA2_REQUIRE(topk >= 1 && topk <= V - forbid_prefix, "topk must be in 1..effective_vocab given forbid_prefix");  // :179-180
+  UA2_REQUIRE(R >= 1, "R >= 1");
+  const bool use_cfg = cfg_scale > 1.0f;
+  UA2_REQUIRE(!use_cfg || R == 1, "CFG samples one row from (cond, uncond)");
+  static FrameScalars* d_fs = nullptr;
+  if (!d_fs) UA2_CHECK_CUDA(cudaMalloc(&d_fs, sizeof(FrameScalars)));
+  FrameScalars fs;
+  fs.temperature = temperature;
+  fs.topk = topk;
+  fs.forbid_prefix = forbid_prefix;
+  fs.cfg_scale = cfg_scale;
+  fs.seed = seed;
+  fs.offset = offset;
+  fs.noise = noise;
+  fs.out = out;
+  fs.rows = R;
+  fs.B = use_cfg ? 2 : R;
+  cudaStream_t s = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(cudaMemcpyAsync(d_fs, &fs, sizeof(fs), cudaMemcpyHostToDevice, s));
+  UA2_CHECK_CUDA(cudaStreamSynchronize(s));  // fs lives on the host stack
+  LaunchCtx lc;
+  lc.stream = s;
+  // under CFG the single sampled token is replicated to both rows (out_ld = 1 -> out[0], out[1])
+  UA2_CHECK_CUDA(launch_sampler(lc, logits, V, d_fs, 1, 0, 1, 0, 0, fs.B, R));
+  return UA2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// Top-k / temperature / Gumbel-style sampler, one thread-block CLUSTER per sampled row.
+//
+// Replaces llm_models/model_new.py:146-156 sample_topk, :158-187 audio_sample_topk and :141-143
+// _multinomial_sample_one_no_sync:
+//     logits = logits / T ; logits[:forbid] = -inf
+//     keep   = logits >= kth_largest(logits)            (ties at the threshold are kept)
+//     p      = softmax(log_softmax(masked logits))
+//     token  = argmax(p / q),  q ~ Exp(1)               (first index wins ties, torch.argmax)
+// plus the CFG mix of model_new.py:618-622 / :634-637 (row 0 = cond, row 1 = uncond):  u + (c - u) * scale.
+//
+// Design: the V logits of a row are split across the CTAs of a cluster (8 CTAs for the 128256-entry text head,
+// 1 CTA for a 12300-entry codebook head); each CTA keeps its slice in shared memory, so the row is read from
+// L2 exactly once.  The exact k-th largest value is found by a 4-pass MSB-first radix select on order-preserving
+// keys; per-CTA 256-bin histograms are merged through distributed shared memory (each CTA reads its peers'
+// bins), as are the max / sum / argmax reductions.  Integer outputs are bit-exact functions of the fp32 logits.
+// Roofline: latency (a few cluster barriers); bytes = 4*V (+4*V noise) per row.
+#include <cooperative_groups.h>
+
+#include "ua2_kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ua2 {
+namespace {
+
+constexpr int SAMPLE_THREADS = 512;
+constexpr int SLICE_CAP = 16384;  // floats of a row slice cached in shared memory per CTA (64 KB)
+constexpr int MAX_CLUSTER = 8;
+
+__device__ __forceinline__ uint32_t f2key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Philox4x32-10 (Salmon et al. 2011) - used only when the caller supplies no noise tensor.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0;
+  c[1] = n1;
+  c[2] = n2;
+  c[3] = n3;
+}
+__device__ __forceinline__ float philox_exp1(unsigned long long seed, unsigned long long stream, uint32_t idx) {
+  uint32_t c[4] = {idx, (uint32_t)stream, (uint32_t)(stream >> 32), 0x5EEDu};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return -logf(u);
+}
+
+struct SampleArgs {
+  const float* logits;  // (rows_in, V)
+  int V;
+  const FrameScalars* fs;
+  int is_audio;  // audio heads apply forbid_prefix; the text head does not (model_new.py:623 vs :639)
+  int out_col, out_ld;
+  long long noise_off;
+  unsigned long long stream_id;
+  int B;
+};
+
+template <bool CLUSTERED>
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleArgs a) {
+  extern __shared__ __align__(16) float vals[];      // slice of scaled logits (<= SLICE_CAP)
+  __shared__ unsigned int hist[4][256];              // one histogram per radix pass (never reused -> 1 barrier/pass)
+  __shared__ float red_f[4][SAMPLE_THREADS / 32];    // block-level scratch
+  __shared__ int red_i[SAMPLE_THREADS / 32];
+  __shared__ float cl_f[4];                          // per-CTA results exchanged across the cluster
+  __shared__ int cl_i[2];
+  __shared__ unsigned int sel_bin, sel_k;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = SAMPLE_THREADS / 32;
+  int csize = 1, crank = 0;
+  if (CLUSTERED) {
+    cg::cluster_group cl = cg::this_cluster();
+    csize = cl.num_blocks();
+    crank = cl.block_rank();
+  }
+  const int row = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const FrameScalars fs = *a.fs;
+  const int V = a.V;
+  const bool use_cfg = fs.cfg_scale > 1.0f && fs.B > 1;
+  const int forbid = a.is_audio ? fs.forbid_prefix : 0;
+  const int per = (V + csize - 1) / csize;
+  const int lo = min(V, crank * per), hi = min(V, lo + per);
+  const int n = hi - lo;
+
+  for (int i = tid; i < 4 * 256; i += SAMPLE_THREADS) (&hist[0][0])[i] = 0u;
+
+  // value of (scaled, masked) logit i of this row; cached in smem when it fits
+  auto raw = [&](int i) -> float {
+    float x;
+    if (use_cfg) {
+      const float c = a.logits[i], u = a.logits[(size_t)V + i];
+      x = u + (c - u) * fs.cfg_scale;  // model_new.py:619
+    } else {
+      x = a.logits[(size_t)row * V + i];
+    }
+    x = x / fs.temperature;
+    if (i < forbid) x = -INFINITY;
+    return x;
+  };
+  for (int i = tid; i < n; i += SAMPLE_THREADS) {
+    const float x = raw(lo + i);
+    if (i < SLICE_CAP) vals[i] = x;
+  }
+  __syncthreads();
+  auto val = [&](int i) -> float { return (i < SLICE_CAP) ? vals[i] : raw(lo + i); };
+
+  // cluster-wide all-reduce helpers (every CTA ends up with the same value)
+  auto cluster_barrier = [&]() {
+    if (CLUSTERED)
+      cg::this_cluster().sync();
+    else
+      __syncthreads();
+  };
+
+  // ---- 1. max
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += SAMPLE_THREADS) mx = fmaxf(mx, val(i));
+  mx = warp_max(mx);
+  if (lane == 0) red_f[0][warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m2 = -INFINITY;
+    for (int w = 0; w < NW; ++w) m2 = fmaxf(m2, red_f[0][w]);
+    cl_f[0] = m2;
+  }
+  cluster_barrier();
+  if (CLUSTERED) {
+    cg::cluster_group cl = cg::this_cluster();
+    float m2 = -INFINITY;
+    for (int r = 0; r < csize; ++r) m2 = fmaxf(m2, *cl.map_shared_rank(&cl_f[0], r));
+    mx = m2;
+  } else {
+    mx = cl_f[0];
+  }
+
+  // ---- 2. exact k-th largest via MSB-first radix select
+  uint32_t thr_key;
+  if (fs.topk <= 1) {
+    thr_key = f2key(mx);
+  } else {
+    uint32_t prefix = 0, pmask = 0;
+    unsigned int k_rem = (unsigned int)fs.topk;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = tid; i < n; i += SAMPLE_THREADS) {
+        const uint32_t key = f2key(val(i));
+        if ((key & pmask) == prefix) atomicAdd(&hist[pass][(key >> shift) & 255u], 1u);
+      }
+      cluster_barrier();
+      // every CTA redundantly merges the histograms and picks the same bin
+      if (warp == 0) {
+        unsigned int cnt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int bin = 255 - (lane * 8 + j);  // descending bins; lane 0 holds the largest values
+          unsigned int c = 0;
+          if (CLUSTERED) {
+            cg::cluster_group cl = cg::this_cluster();
+            for (int r = 0; r < csize; ++r) c += *cl.map_shared_rank(&hist[pass][bin], r);
+          } else {
+            c = hist[pass][bin];
+          }
+          cnt[j] = c;
+        }
+        unsigned int tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tot += cnt[j];
+        // exclusive prefix over lanes (descending value order)
+        unsigned int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        unsigned int above = incl - tot;
+        if (above < k_rem && k_rem <= incl) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (above < k_rem && k_rem <= above + cnt[j]) {
+              sel_bin = 255u - (unsigned int)(lane * 8 + j);
+              sel_k = k_rem - above;
+            }
+            above += cnt[j];
+          }
+        }
+      }
+      __syncthreads();
+      prefix |= sel_bin << shift;
+      pmask |= 255u << shift;
+      k_rem = sel_k;
+      __syncthreads();
+    }
+    thr_key = prefix;
+  }
+
+  // ---- 3. Z = sum_{kept} exp(x - mx)
+  float z = 0.f;
+  for (int i = tid; i < n; i += SAMPLE_THREADS) {
+    const float x = val(i);
+    if (f2key(x) >= thr_key) z += expf(x - mx);
+  }
+  z = warp_sum(z);
+  if (lane == 0) red_f[1][warp] = z;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < NW; ++w) s += red_f[1][w];
+    cl_f[1] = s;
+  }
+  cluster_barrier();
+  if (CLUSTERED) {
+    cg::cluster_group cl = cg::this_cluster();
+    float s = 0.f;
+    for (int r = 0; r < csize; ++r) s += *cl.map_shared_rank(&cl_f[1], r);
+    z = s;
+  } else {
+    z = cl_f[1];
+  }
+  const float lse = logf(z);
+  // log_softmax value of element x is (x - mx) - lse; its max over the row is (0 - lse)
+  const float max_ls = 0.f - lse;
+
+  // ---- 4. Z2 = sum exp(ls - max_ls)   (the second softmax of model_new.py:153)
+  float z2 = 0.f;
+  for (int i = tid; i < n; i += SAMPLE_THREADS) {
+    const float x = val(i);
+    if (f2key(x) >= thr_key) z2 += expf(((x - mx) - lse) - max_ls);
+  }
+  z2 = warp_sum(z2);
+  if (lane == 0) red_f[2][warp] = z2;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < NW; ++w) s += red_f[2][w];
+    cl_f[2] = s;
+  }
+  cluster_barrier();
+  if (CLUSTERED) {
+    cg::cluster_group cl = cg::this_cluster();
+    float s = 0.f;
+    for (int r = 0; r < csize; ++r) s += *cl.map_shared_rank(&cl_f[2], r);
+    z2 = s;
+  } else {
+    z2 = cl_f[2];
+  }
+
+  // ---- 5. argmax p / q  (first index wins ties)
+  float best = -1.f;
+  int best_i = 0x7fffffff;
+  const float* noise = fs.noise ? fs.noise + a.noise_off + (size_t)row * V : nullptr;
+  for (int i = tid; i < n; i += SAMPLE_THREADS) {
+    const float x = val(i);
+    if (f2key(x) >= thr_key) {
+      const float p = expf(((x - mx) - lse) - max_ls) / z2;
+      const float q = noise ? noise[lo + i] : philox_exp1(fs.seed, fs.offset * 65536ull + a.stream_id * 1024ull + row, lo + i);
+      const float sc = p / q;
+      if (sc > best || (sc == best && lo + i < best_i)) {
+        best = sc;
+        best_i = lo + i;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if (lane == 0) {
+    red_f[3][warp] = best;
+    red_i[warp] = best_i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 0; w < NW; ++w) {
+      if (red_f[3][w] > best || (red_f[3][w] == best && red_i[w] < best_i)) {
+        best = red_f[3][w];
+        best_i = red_i[w];
+      }
+    }
+    cl_f[3] = best;
+    cl_i[0] = best_i;
+  }
+  cluster_barrier();
+  if (crank == 0 && tid == 0) {
+    if (CLUSTERED) {
+      cg::cluster_group cl = cg::this_cluster();
+      for (int r = 1; r < csize; ++r) {
+        const float ob = *cl.map_shared_rank(&cl_f[3], r);
+        const int oi = *cl.map_shared_rank(&cl_i[0], r);
+        if (ob > best || (ob == best && oi < best_i)) {
+          best = ob;
+          best_i = oi;
+        }
+      }
+    }
+    if (use_cfg) {
+      for (int b = 0; b < fs.B; ++b) fs.out[(size_t)b * a.out_ld + a.out_col] = best_i;  // .repeat(2,1), model_new.py:621
+    } else {
+      fs.out[(size_t)row * a.out_ld + a.out_col] = best_i;
+    }
+  }
+  // keep every CTA's shared memory alive until all remote reads are done
+  cluster_barrier();
+}
+
+}  // namespace
+
+cudaError_t launch_sampler(const LaunchCtx& lc, const float* logits, int V, const FrameScalars* d_fs, int is_audio,
+                           int out_col, int out_ld, long long noise_off, unsigned long long stream_id, int B,
+                           int rows) {
+  SampleArgs a{logits, V, d_fs, is_audio, out_col, out_ld, noise_off, stream_id, B};
+  int csize = 1;
+  while (csize < MAX_CLUSTER && (V + csize - 1) / csize > SLICE_CAP) csize <<= 1;
+  const int per = (V + csize - 1) / csize;
+  const size_t smem = (size_t)(per < SLICE_CAP ? per : SLICE_CAP) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_CAP * 4);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_CAP * 4);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (lc.launch_counter) ++*lc.launch_counter;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(csize, rows);
+  cfg.blockDim = dim3(SAMPLE_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (csize > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = csize;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (lc.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (csize > 1) return cudaLaunchKernelEx(&cfg, sample_kernel<true>, a);
+  return cudaLaunchKernelEx(&cfg, sample_kernel<false>, a);
+}
+
+}  // namespace ua2
