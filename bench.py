@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the UniAudio2 AR-decode hot path on B200.
+
+metric   : audio tokens/s of the autoregressive decode (BASELINE.json), TTS-10 s workload (configs[1]):
+           40-position text prompt prefill + fixed 179-frame schedule (52 reason-phase frames, forbid_prefix=0;
+           127 semantic-phase frames, forbid_prefix=4100) = 1432 audio tokens per utterance,
+           full-size model (Llama-3.2-3B backbone + 3 L / 2 L experts + Llama-3.2-300M local decoder, 4.86 B params),
+           fp32 like the reference (multi_task_inference.py:181-183), random-init weights, synthetic tokens.
+step     : one whole utterance (reset_caches + forward_prefix + 179 x generate_frame) per GPU.
+value    : whole-job audio tokens/s, inputs resident in HBM, no host sync inside the timed region.
+e2e      : same metric through the public API (evaluation.tts_task.Generator.generate_tts) with HOST buffers:
+           prompt H2D from pinned memory and one D2H of the sampled frame per AR step inside the timed region.
+N > 1    : one replica per GPU (torchrun), one utterance per rank per step (weak scaling), a single NCCL
+           all_gather of the generated tokens at the end of each step; time = max over ranks.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3
+  python bench.py --impl reference ...      # the reference's algorithm on the host CPU (oracle port, torch CPU fp32)
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "audio_tokens_per_s_ar_decode_tts10s"
+UNIT = "audio tokens/s"
+PROMPT_LEN = 40
+N_REASON, N_SEMANTIC = 52, 127
+N_FRAMES = N_REASON + N_SEMANTIC
+NQ = 8
+REASON_CARD, SEMANTIC_CARD = 4100, 8200
+TEMPERATURE, TOPK = 0.9, 50
+# parameters touched once per frame / per local step
+P_GLOB, P_LOC = 3.715e9, 2.748e8
+
+
+def frame_bytes(S):
+    """Algorithmic HBM bytes of one generate_frame at context S (fp32): all weights once + KV read + logits."""
+    kv = S * 33 * 2 * 8 * 128 * 4
+    return 4.0 * (P_GLOB + NQ * P_LOC) + kv
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        os.unlink(self.f.name)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------- model construction
+def model_args():
+    from uniaudio2_b200.llm_models.model_new import ModelArgs
+
+    return ModelArgs(llm_name="Llama-3.2-3B", decoder_name="Llama-3.2-300M", llm_pretrained_model="", audio_embeddings_path="",
+                     audio_understanding_expert_path="", audio_semantic_vocab_size=SEMANTIC_CARD,
+                     audio_reason_vocab_size=REASON_CARD, audio_num_codebooks=NQ)
+
+
+def init_weights_(model, seed=0):
+    """Seeded synthetic weights directly on the device (no checkpoints offline): Linear ~ U(+-1/sqrt(fan_in)),
+    embeddings ~ N(0,1), norms ~ 1 + 0.1 N(0,1), audio_head ~ N(0, 0.02^2)."""
+    dev = next(model.parameters()).device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    for name, p in model.named_parameters():
+        if "norm_" in name or "ln_f" in name:
+            p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
+        elif name == "audio_head":
+            p.normal_(0.0, 0.02, generator=g)
+        elif name.endswith("wte.weight") or name == "audio_embeddings.weight":
+            p.normal_(0.0, 1.0, generator=g)
+        else:
+            p.uniform_(-1.0, 1.0, generator=g).mul_(1.0 / math.sqrt(p.shape[-1]))
+
+
+def synthetic_prompt(rank, seed=888):
+    g = torch.Generator().manual_seed(seed + rank)
+    task_prompt = torch.randint(0, 128000, (10,), generator=g)
+    text = torch.randint(0, 128000, (PROMPT_LEN - 10 - 2,), generator=g)  # + <transcription> </transcription> = 40 rows
+    return task_prompt, text
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_utterance_device(model, tokens, mask, pos):
+    """One step with everything resident on the device and no host sync: prefill + 179 frames."""
+    S = tokens.size(1)
+    model.reset_caches()
+    model.forward_prefix(tokens[:, :-1], labels=None, tokens_mask=mask, loss_mask=None, input_pos=pos[:, :-1], input_pos_maxp1=S - 1)
+    curr_tokens, curr_mask = tokens[:, -1:], mask[:, -1:]
+    audio_mask = torch.cat([torch.ones(1, 1, NQ, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1).to(tokens.device)
+    frames = []
+    launches = model.last_launch_count()
+    for f in range(N_FRAMES):
+        forbid = 0 if f < N_REASON else REASON_CARD
+        s = model.generate_frame(curr_tokens, curr_mask, input_pos=S - 1 + f, input_pos_maxp1=S + f, temperature=TEMPERATURE,
+                                 topk=TOPK, forbid_prefix=forbid)
+        launches += model.last_launch_count()
+        frames.append(s)
+        sl = s.long()
+        curr_tokens = torch.cat([sl[:, 1:], sl[:, 0:1]], dim=-1).unsqueeze(1)
+        curr_mask = audio_mask
+    return torch.stack(frames), launches
+
+
+def time_dominant_kernel(model, hbm_peak, reps=3):
+    """Roofline of the dominant kernel: the fused RMSNorm -> fc_1|fc_2 -> SiLU*mul skinny linear (gemv_kernel<1,RMSNORM,
+    SWIGLU>) of the backbone MLP, 2 x 8192 x 3072 fp32 weights = 201.3 MB algorithmic bytes per launch; 28+3+2 such
+    launches per frame = 28% of all frame bytes.  Timed alone with CUDA events on the launching stream, cycling through
+    the 28 backbone layers' weights (5.6 GB >> 126 MB L2, so every launch streams from HBM)."""
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    dev = next(model.parameters()).device
+    blocks = model.backbone.transformer.h
+    D, Fi = model.backbone.config.n_embd, model.backbone.config.intermediate_size
+    x = torch.randn(1, D, device=dev)
+    y = torch.empty(1, Fi, device=dev)
+    st = _lib.current_stream()
+
+    def one_pass():
+        for b in blocks:
+            _lib.check(L.ua2_swiglu_f32(_lib.ptr(x), _lib.ptr(b.mlp.fc_1.weight), _lib.ptr(b.mlp.fc_2.weight), _lib.ptr(b.norm_2.weight),
+                                        1e-5, _lib.ptr(y), 1, Fi, D, st))
+
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    n = reps * len(blocks)
+    us = e0.elapsed_time(e1) * 1e3 / n
+    bytes_per_launch = 2.0 * Fi * D * 4 + (D + Fi + D) * 4
+    achieved = bytes_per_launch / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "gemv_kernel<1,PRO_RMSNORM,EPI_SWIGLU> (backbone mlp fc_1|fc_2, N=8192 K=3072)",
+            "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+            "traffic": None, "launch_us": round(us, 2), "bytes_per_launch": bytes_per_launch, "launches_timed": n}
+
+
+def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
+    """The reference's algorithm (oracle port: torch CPU fp32, same ATen ops as the reference) on the host cores.
+    Bounded sample: one 39-position prefill + n_frames generate_frame calls at the start of the TTS-10 s schedule;
+    the utterance time is extrapolated as prefill + 179 x mean frame time."""
+    from oracle import llm_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = O.full_size_cfg(REASON_CARD, SEMANTIC_CARD)
+    orc = O.Stage3Oracle(cfg, state_dict_cpu)
+    orc.setup_caches(1)
+    task_prompt, text = synthetic_prompt(0)
+    seq = torch.cat([task_prompt, torch.tensor([128011]), text, torch.tensor([128012])])
+    S = seq.numel()
+    tokens = torch.zeros(1, S, NQ + 1, dtype=torch.long)
+    tokens[0, :, -1] = seq
+    mask = torch.zeros(1, S, NQ + 1, dtype=torch.bool)
+    mask[..., -1] = True
+    pos = torch.arange(S).unsqueeze(0)
+    torch.manual_seed(888)
+    with torch.inference_mode():
+        orc.reset_caches()
+        t0 = time.perf_counter()
+        orc.forward_prefix(tokens[:, :-1], mask, pos[:, :-1])
+        t_prefill = time.perf_counter() - t0
+        curr_tokens, curr_mask = tokens[:, -1:], mask[:, -1:]
+        times = []
+        for f in range(n_frames + 1):
+            t0 = time.perf_counter()
+            s = orc.generate_frame(curr_tokens, curr_mask, torch.tensor([S - 1 + f]), S + f, TEMPERATURE, TOPK, 0)
+            times.append(time.perf_counter() - t0)
+            sl = s.long()
+            curr_tokens = torch.cat([sl[:, 1:], sl[:, 0:1]], dim=-1).unsqueeze(1)
+            curr_mask = torch.cat([torch.ones(1, 1, NQ, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1)
+    frame_t = sum(times[1:]) / len(times[1:])  # first frame = warm-up
+    est = t_prefill + N_FRAMES * frame_t
+    return {"value": round(NQ * N_FRAMES / est, 2), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 prefill({S - 1} pos, {t_prefill:.2f}s) + {n_frames} frames ({frame_t * 1e3:.0f} ms/frame, 1 warm-up frame discarded); "
+                      f"utterance extrapolated to prefill + {N_FRAMES} frames = {est:.1f}s", "frame_ms": round(frame_t * 1e3, 1),
+            "prefill_s": round(t_prefill, 3)}, est
+
+
+def state_dict_to_cpu(model):
+    return {k: v.detach().to("cpu") for k, v in model.state_dict().items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ua2", choices=["ua2", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "0")))
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "ua2" else args.warmup
+    config = {"workload": "TTS-10s AR decode: 40-pos prefill + 179 frames (52 reason + 127 semantic), B=1 per GPU, "
+                          "Llama-3.2-3B backbone + 3L/2L experts + 300M local decoder (4.86B params), topk=50 T=0.9",
+              "frames_per_step": N_FRAMES, "audio_tokens_per_step": NQ * N_FRAMES, "prompt_len": PROMPT_LEN,
+              "parallelism": f"replica x{world} (one utterance per GPU)", "l2_policy": "inputs larger than L2 (19.5 GB weights streamed per frame)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        from uniaudio2_b200.llm_models.model_new import Model_stage3
+
+        with torch.inference_mode():
+            m = Model_stage3(model_args(), device=dev)
+            init_weights_(m, 0)
+            sd = state_dict_to_cpu(m)
+        del m
+        if dev != "cpu":
+            torch.cuda.empty_cache()
+        ests, last = [], None
+        for i in range(args.warmup + args.steps):
+            cb, est = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
+            if i >= args.warmup:
+                ests.append(est)
+                last = cb
+        est = sum(ests) / len(ests)
+        v = NQ * N_FRAMES / est
+        last["value"] = round(v, 2)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(est * 1e3, 1), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+                          "cpu_baseline": last, "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0,
+                                                        "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ product arm (GPU)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback on the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from uniaudio2_b200.evaluation.tts_task import Generator, default_train_args
+    from uniaudio2_b200.llm_models.model_new import Model_stage3
+
+    with torch.inference_mode():
+        model = Model_stage3(model_args(), device=dev)
+        init_weights_(model, 0)  # same weights on every replica
+        gen = Generator(model, default_train_args(REASON_CARD, SEMANTIC_CARD), is_cfg=False)  # setup_caches(1)
+        if args.pdl:
+            model.set_option("pdl", 1)
+        task_prompt, text = synthetic_prompt(rank)
+        tokens, mask = gen.prepare_tts_task(task_prompt, text)
+        assert tokens.size(0) == PROMPT_LEN
+        tokens_d = tokens.unsqueeze(0).to(dev)
+        mask_d = mask.bool().unsqueeze(0).to(dev)
+        pos_d = torch.arange(PROMPT_LEN, device=dev).unsqueeze(0)
+        gather_buf = [torch.empty(N_FRAMES, 1, NQ + 1, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+
+        def step_device():
+            frames, launches = run_utterance_device(model, tokens_d, mask_d, pos_d)
+            if world > 1:
+                dist.all_gather(gather_buf, frames)  # the single collective: generated tokens of every rank
+            return frames, launches
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        torch.manual_seed(888 + rank)
+        for _ in range(warmup):
+            step_device()
+        barrier()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            _, l = step_device()
+            launches += l
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        ms_per_step = ms / args.steps
+        value = world * NQ * N_FRAMES * args.steps / (ms * 1e-3)
+
+        # ---- e2e through the public API with host buffers (prompt H2D, per-frame D2H of the sample)
+        e2e = None
+        if not args.no_e2e:
+            for _ in range(2):
+                gen.generate_tts(task_prompt, "TTS", text_token=text, temperature=TEMPERATURE, topk=TOPK, fixed_schedule=(N_REASON, N_SEMANTIC))
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                r, s = gen.generate_tts(task_prompt, "TTS", text_token=text, temperature=TEMPERATURE, topk=TOPK,
+                                        fixed_schedule=(N_REASON, N_SEMANTIC))
+                if world > 1:
+                    dist.all_gather(gather_buf, torch.zeros_like(gather_buf[0]))
+            e1.record()
+            barrier()
+            ems = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ems], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ems = float(t.item())
+            assert gen.n_frames == N_FRAMES and r.shape == (NQ, N_REASON - 2) and s.shape == (NQ, N_SEMANTIC - 1), (gen.n_frames, r.shape, s.shape)
+            e2e = {"value": round(world * NQ * N_FRAMES * args.steps / (ems * 1e-3), 1), "unit": UNIT,
+                   "h2d_bytes_per_step": int(gen.h2d_bytes), "d2h_bytes_per_step": int(gen.d2h_bytes),
+                   "ms_per_step": round(ems / args.steps, 2)}
+
+        hbm_peak, peak_src = load_peaks()
+        roofline = cpu_base = None
+        if rank == 0:
+            roofline = time_dominant_kernel(model, hbm_peak)
+            roofline["peak_source"] = peak_src
+            mean_bytes = sum(frame_bytes(PROMPT_LEN + f) for f in range(N_FRAMES)) / N_FRAMES
+            frame_ms = ms_per_step / N_FRAMES  # includes the prefill (1 of 180 calls)
+            roofline["frame_effective_gbs"] = round(mean_bytes / (frame_ms * 1e-3) / 1e9, 1)
+            roofline["frame_frac_of_peak"] = round(roofline["frame_effective_gbs"] / hbm_peak, 4)
+            roofline["frame_algorithmic_bytes"] = mean_bytes
+            if world == 1 and not args.no_cpu_baseline:
+                sd = state_dict_to_cpu(model)
+                cpu_base, _ = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
+                del sd
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
+                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

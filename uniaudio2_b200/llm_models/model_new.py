@@ -258,6 +258,8 @@ class Model_stage3(nn.Module):
             pos = int(input_pos.item()) if input_pos.device.type == "cpu" else int(input_pos.reshape(-1)[0].item())
         else:
             pos = int(input_pos)
+        if B > self._max_batch:
+            raise ValueError(f"batch size {B} exceeds setup_caches({self._max_batch})")
         use_cfg = cfg_scale > 1.0 and B > 1
         rows = 1 if use_cfg else B
         with torch.cuda.device(dev):
