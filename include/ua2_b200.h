@@ -34,6 +34,8 @@ const char* ua2_last_error(void);
 /* library / device probe: returns the SM count of the current device (e.g. 148), <0 on error */
 int ua2_device_sm_count(void);
 const char* ua2_version(void);
+/* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (cp.async.bulk + mbarrier rings, default) */
+int ua2_set_global_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * AR decode: llm_models/model_new.py::Model_stage3 over llm_models/lit_model.py::GPT

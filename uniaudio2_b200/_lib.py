@@ -32,6 +32,7 @@ SYMBOLS = {
     "ua2_last_error": (C.c_char_p, []),
     "ua2_device_sm_count": (C.c_int, []),
     "ua2_version": (C.c_char_p, []),
+    "ua2_set_global_option": (C.c_int, [C.c_char_p, C.c_int]),
     "ua2_llm_create": (C.c_int, [C.POINTER(LlmCfg), C.POINTER(_P)]),
     "ua2_llm_destroy": (C.c_int, [_P]),
     "ua2_llm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),

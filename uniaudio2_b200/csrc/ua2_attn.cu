@@ -16,53 +16,102 @@ namespace {
 
 constexpr int MAX_QPK = 4;
 
+__device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One CTA = (split of ATTN_CHUNK keys, KV group, query row).  The K and V chunks are contiguous in the cache
+// ((b, g, pos, hs) layout), so each is fetched with ONE bulk copy (cp.async.bulk -> mbarrier) into shared memory:
+// every byte of the chunk is in flight at once and the whole kernel is a single memory round trip.
+//   phase 1 (QK^T): 8 lanes per key (conflict-free 128-bit LDS), q in registers, 3-step shuffle reduce
+//   phase 2       : warp h = softmax statistics of query head h over the chunk
+//   phase 3 (PV)  : warp w = keys [w*C/4, (w+1)*C/4), lanes over head dims (float4), cross-warp reduce in smem
 template <int HS>
 __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
-  __shared__ __align__(16) float qs[MAX_QPK][HS];
+  extern __shared__ __align__(128) float kv_s[];  // K chunk [C][HS] then V chunk [C][HS]
   __shared__ float sc[MAX_QPK][ATTN_CHUNK];
+  __shared__ __align__(16) float redp[4][MAX_QPK][HS];
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int C = ATTN_CHUNK;
+  constexpr int NI = HS / 32;  // float4 per lane per key in phase 1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, g = blockIdx.y, m = blockIdx.z;
   pdl_launch_dependents();
   pdl_wait();
   const int n_keys = p.pos[m] + 1;
-  const int start = split * ATTN_CHUNK;
+  const int start = split * C;
   if (start >= n_keys) return;
-  const int cnt = min(ATTN_CHUNK, n_keys - start);
+  const int cnt = min(C, n_keys - start);
   const int qpk = p.n_head / p.n_groups;
   const int b = p.bidx[m];
   const float scale = rsqrtf((float)HS);
   const float* Kc = p.k_cache + (((size_t)b * p.n_groups + g) * p.S_max + start) * HS;
   const float* Vc = p.v_cache + (((size_t)b * p.n_groups + g) * p.S_max + start) * HS;
+  float* Ks = kv_s;
+  float* Vs = kv_s + C * HS;
 
-  for (int i = tid; i < qpk * HS; i += 128) {
-    const int h = i / HS, d = i - h * HS;
-    qs[h][d] = p.q[(size_t)m * p.n_head * HS + (g * qpk + h) * HS + d];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32a(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)cnt * HS * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32a(&bar)), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32a(Ks)),
+                 "l"(Kc), "r"(bytes), "r"(smem_u32a(&bar))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32a(Vs)),
+                 "l"(Vc), "r"(bytes), "r"(smem_u32a(&bar))
+                 : "memory");
   }
-  __syncthreads();
+  // q -> registers while the copies fly: lane (kk = lane>>3, part = lane&7) needs q[h][part*4 + 32*i .. +3]
+  const int kk = lane >> 3, part = lane & 7;
+  float4 qr[MAX_QPK][NI];
+#pragma unroll
+  for (int h = 0; h < MAX_QPK; ++h)
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+      qr[h][i] = (h < qpk) ? *reinterpret_cast<const float4*>(p.q + (size_t)m * p.n_head * HS + (g * qpk + h) * HS +
+                                                               part * 4 + 32 * i)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();  // barrier init visible to every waiter
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32a(&bar)),
+      "r"(0u)
+      : "memory");
 
-  // ---- phase 1: one thread per key, scores for all q heads of the group
-  if (tid < cnt) {
-    const float4* kr = reinterpret_cast<const float4*>(Kc + (size_t)tid * HS);
+  // ---- phase 1: scores.  16 keys per iteration over the CTA (4 warps x 4 keys)
+#pragma unroll
+  for (int it = 0; it < C / 16; ++it) {
+    const int j = it * 16 + warp * 4 + kk;
     float s[MAX_QPK];
 #pragma unroll
     for (int h = 0; h < MAX_QPK; ++h) s[h] = 0.f;
-#pragma unroll 8
-    for (int d4 = 0; d4 < HS / 4; ++d4) {
-      const float4 kv = kr[d4];
+    if (j < cnt) {
 #pragma unroll
-      for (int h = 0; h < MAX_QPK; ++h) {
-        if (h < qpk) {
-          const float4 qv = *reinterpret_cast<const float4*>(&qs[h][d4 * 4]);
-          s[h] = fmaf(kv.x, qv.x, s[h]);
-          s[h] = fmaf(kv.y, qv.y, s[h]);
-          s[h] = fmaf(kv.z, qv.z, s[h]);
-          s[h] = fmaf(kv.w, qv.w, s[h]);
+      for (int i = 0; i < NI; ++i) {
+        const float4 kv = *reinterpret_cast<const float4*>(Ks + (size_t)j * HS + part * 4 + 32 * i);
+#pragma unroll
+        for (int h = 0; h < MAX_QPK; ++h) {
+          s[h] = fmaf(kv.x, qr[h][i].x, s[h]);
+          s[h] = fmaf(kv.y, qr[h][i].y, s[h]);
+          s[h] = fmaf(kv.z, qr[h][i].z, s[h]);
+          s[h] = fmaf(kv.w, qr[h][i].w, s[h]);
         }
       }
     }
 #pragma unroll
-    for (int h = 0; h < MAX_QPK; ++h)
-      if (h < qpk) sc[h][tid] = s[h] * scale;
+    for (int h = 0; h < MAX_QPK; ++h) {
+      s[h] += __shfl_xor_sync(0xffffffffu, s[h], 1);
+      s[h] += __shfl_xor_sync(0xffffffffu, s[h], 2);
+      s[h] += __shfl_xor_sync(0xffffffffu, s[h], 4);
+      if (part == 0 && j < cnt && h < qpk) sc[h][j] = s[h] * scale;
+    }
   }
   __syncthreads();
 
@@ -87,38 +136,45 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   }
   __syncthreads();
 
-  // ---- phase 3: P @ V, thread per output dim (HS==128) or per (key-half, dim) (HS==64, HS==32)
-  constexpr int PARTS = 128 / HS;
-  const int part = tid / HS, d = tid - part * HS;
-  float acc[MAX_QPK];
+  // ---- phase 3: P @ V.  warp w owns keys [w*C/4, (w+1)*C/4); LPK lanes span one key row (float4 each)
+  constexpr int LPK = HS / 4;    // lanes per key row: 32 / 16 / 8
+  constexpr int KPI = 32 / LPK;  // keys per warp iteration: 1 / 2 / 4
+  const int ksub = lane / LPK, d4 = lane - ksub * LPK;
+  float4 acc[MAX_QPK];
 #pragma unroll
-  for (int h = 0; h < MAX_QPK; ++h) acc[h] = 0.f;
+  for (int h = 0; h < MAX_QPK; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int t0 = warp * (C / 4);
 #pragma unroll 4
-  for (int t = part; t < cnt; t += PARTS) {
-    const float v = Vc[(size_t)t * HS + d];
-#pragma unroll
-    for (int h = 0; h < MAX_QPK; ++h)
-      if (h < qpk) acc[h] = fmaf(sc[h][t], v, acc[h]);
-  }
-  if (PARTS > 1) {
-    // reduce the key-parts through shared memory (PARTS = 2 or 4)
-    __shared__ float redp[4][MAX_QPK][HS];
-#pragma unroll
-    for (int h = 0; h < MAX_QPK; ++h) redp[part][h][d] = acc[h];
-    __syncthreads();
-    if (part == 0) {
+  for (int tt = 0; tt < C / 4; tt += KPI) {
+    const int t = t0 + tt + ksub;
+    if (t < cnt) {
+      const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)t * HS + d4 * 4);
 #pragma unroll
       for (int h = 0; h < MAX_QPK; ++h) {
-        float s = 0.f;
-        for (int q = 0; q < PARTS; ++q) s += redp[q][h][d];
-        acc[h] = s;
+        const float w = (h < qpk) ? sc[h][t] : 0.f;
+        acc[h].x = fmaf(w, v.x, acc[h].x);
+        acc[h].y = fmaf(w, v.y, acc[h].y);
+        acc[h].z = fmaf(w, v.z, acc[h].z);
+        acc[h].w = fmaf(w, v.w, acc[h].w);
       }
     }
   }
-  if (part == 0) {
 #pragma unroll
-    for (int h = 0; h < MAX_QPK; ++h)
-      if (h < qpk) p.o_part[(((size_t)m * p.n_head + g * qpk + h) * p.max_splits + split) * HS + d] = acc[h];
+  for (int h = 0; h < MAX_QPK; ++h) {
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) {
+      acc[h].x += __shfl_xor_sync(0xffffffffu, acc[h].x, o);
+      acc[h].y += __shfl_xor_sync(0xffffffffu, acc[h].y, o);
+      acc[h].z += __shfl_xor_sync(0xffffffffu, acc[h].z, o);
+      acc[h].w += __shfl_xor_sync(0xffffffffu, acc[h].w, o);
+    }
+    if (ksub == 0) *reinterpret_cast<float4*>(&redp[warp][h][d4 * 4]) = acc[h];
+  }
+  __syncthreads();
+  for (int i = tid; i < qpk * HS; i += 128) {
+    const int h = i / HS, d = i - h * HS;
+    const float o = (redp[0][h][d] + redp[1][h][d]) + (redp[2][h][d] + redp[3][h][d]);
+    p.o_part[(((size_t)m * p.n_head + g * qpk + h) * p.max_splits + split) * HS + d] = o;
   }
 }
 
@@ -144,15 +200,27 @@ __global__ void attn_combine_kernel(const AttnParams p, float* y) {
   }
 }
 
+template <int HS>
+cudaError_t launch_attn_hs(const LaunchCtx& lc, const AttnParams& p) {
+  const size_t smem = (size_t)2 * ATTN_CHUNK * HS * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_split_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const dim3 grid(p.n_splits_launch, p.n_groups, p.M), block(128);
+  return launch(lc, attn_split_kernel<HS>, grid, block, smem, p);
+}
+
 }  // namespace
 
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p) {
   if (p.n_head % p.n_groups != 0 || p.n_head / p.n_groups > MAX_QPK) return cudaErrorInvalidValue;
-  const dim3 grid(p.n_splits_launch, p.n_groups, p.M), block(128);
   switch (p.hs) {
-    case 128: return launch(lc, attn_split_kernel<128>, grid, block, 0, p);
-    case 64: return launch(lc, attn_split_kernel<64>, grid, block, 0, p);
-    case 32: return launch(lc, attn_split_kernel<32>, grid, block, 0, p);
+    case 128: return launch_attn_hs<128>(lc, p);
+    case 64: return launch_attn_hs<64>(lc, p);
+    case 32: return launch_attn_hs<32>(lc, p);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -56,32 +56,13 @@ __device__ __forceinline__ void load_batch(const float* rowA, const float* rowB,
   }
 }
 
-template <int MT, int PRO, int EPI>
-__global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
-  extern __shared__ __align__(16) float xs[];  // MT x Kp
-  __shared__ float red[8][8];
+
+// ---- fused prologue: produce the MT x Kp activation tile in shared memory (all threads of the CTA)
+template <int MT, int PRO>
+__device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs, float (*red)[8], int Kp, int m0,
+                                                  int mcount) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int K = p.K;
-  const int nIt = (K + 127) >> 7;
-  const int Kp = nIt << 7;
-  const int m0 = blockIdx.x * MT;
-  const int mcount = min(MT, p.M - m0);
-  const int n_units = (EPI == EPI_SWIGLU) ? p.N : (p.N >> 1);
-  int unit = blockIdx.y * nwarps + warp;
-  const int unit_stride = gridDim.y * nwarps;
-
-  // ---- issue the first weight batch before anything that depends on the producer kernel
-  float4 wa[U], wb[U];
-  const float *rowA = nullptr, *rowB = nullptr;
-  int nA = 0, nB = 0;
-  if (unit < n_units) {
-    unit_rows<EPI>(p, unit, rowA, rowB, nA, nB);
-    load_batch(rowA, rowB, 0, lane, K, wa, wb);
-  }
-  pdl_launch_dependents();
-  pdl_wait();
-
-  // ---- prologue: activation tile -> shared memory
   if (PRO == PRO_PLAIN || PRO == PRO_RMSNORM || PRO == PRO_GATHER) {
     float ss[MT];
 #pragma unroll
@@ -160,6 +141,78 @@ __global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
   }
   __syncthreads();
 
+}
+
+// ---- fused epilogue: lane m (< mcount) holds the two row sums (a, b) of output rows (nA, nB) for activation row m0+m
+template <int EPI>
+__device__ __forceinline__ void epilogue(const GemvParams& p, int lane, int mcount, int m0, float a, float b, int nA,
+                                         int nB) {
+  if (lane < mcount) {
+      const int m = m0 + lane;
+      if (EPI == EPI_STORE) {
+        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a, b);
+      } else if (EPI == EPI_RESADD) {
+        const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
+        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a + r.x, b + r.y);
+      } else if (EPI == EPI_SWIGLU) {
+        const float s = a / (1.0f + expf(-a));  // F.silu, lit_model.py:594
+        p.Y[(size_t)m * p.ldy + nA] = s * b;
+      } else {  // EPI_QKV: split, half-split RoPE (lit_model.py:795-806), KV-cache append (:854-855)
+        const int hs = p.hs, half = hs >> 1;
+        const int hh = nA / hs, i = nA - hh * hs;
+        const int ps = p.pos[m];
+        if (hh < p.n_head + p.n_groups) {
+          const float c0 = p.cos[(size_t)ps * hs + i], s0 = p.sin[(size_t)ps * hs + i];
+          const float c1 = p.cos[(size_t)ps * hs + i + half], s1 = p.sin[(size_t)ps * hs + i + half];
+          const float ra = __fadd_rn(__fmul_rn(a, c0), __fmul_rn(-b, s0));
+          const float rb = __fadd_rn(__fmul_rn(b, c1), __fmul_rn(a, s1));
+          if (hh < p.n_head) {
+            float* q = p.q_out + (size_t)m * (p.n_head * hs) + hh * hs + i;
+            q[0] = ra;
+            q[half] = rb;
+          } else {
+            const int g = hh - p.n_head;
+            float* kc = p.k_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
+            kc[0] = ra;
+            kc[half] = rb;
+          }
+        } else {
+          const int g = hh - p.n_head - p.n_groups;
+          float* vc = p.v_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
+          vc[0] = a;
+          vc[half] = b;
+        }
+      }
+    }
+}
+
+template <int MT, int PRO, int EPI>
+__global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
+  extern __shared__ __align__(16) float xs[];  // MT x Kp
+  __shared__ float red[8][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int K = p.K;
+  const int nIt = (K + 127) >> 7;
+  const int Kp = nIt << 7;
+  const int m0 = blockIdx.x * MT;
+  const int mcount = min(MT, p.M - m0);
+  const int n_units = (EPI == EPI_SWIGLU) ? p.N : (p.N >> 1);
+  int unit = blockIdx.y * nwarps + warp;
+  const int unit_stride = gridDim.y * nwarps;
+
+  // ---- issue the first weight batch before anything that depends on the producer kernel
+  float4 wa[U], wb[U];
+  const float *rowA = nullptr, *rowB = nullptr;
+  int nA = 0, nB = 0;
+  if (unit < n_units) {
+    unit_rows<EPI>(p, unit, rowA, rowB, nA, nB);
+    load_batch(rowA, rowB, 0, lane, K, wa, wb);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+
+  stage_activations<MT, PRO>(p, xs, red, Kp, m0, mcount);
+
   // ---- main loop: two weight rows per warp, all M rows of the tile at once
   bool first = true;
   while (unit < n_units) {
@@ -200,46 +253,156 @@ __global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
         b = sb;
       }
     }
-    if (lane < mcount) {
-      const int m = m0 + lane;
-      if (EPI == EPI_STORE) {
-        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a, b);
-      } else if (EPI == EPI_RESADD) {
-        const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
-        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a + r.x, b + r.y);
-      } else if (EPI == EPI_SWIGLU) {
-        const float s = a / (1.0f + expf(-a));  // F.silu, lit_model.py:594
-        p.Y[(size_t)m * p.ldy + nA] = s * b;
-      } else {  // EPI_QKV: split, half-split RoPE (lit_model.py:795-806), KV-cache append (:854-855)
-        const int hs = p.hs, half = hs >> 1;
-        const int hh = nA / hs, i = nA - hh * hs;
-        const int ps = p.pos[m];
-        if (hh < p.n_head + p.n_groups) {
-          const float c0 = p.cos[(size_t)ps * hs + i], s0 = p.sin[(size_t)ps * hs + i];
-          const float c1 = p.cos[(size_t)ps * hs + i + half], s1 = p.sin[(size_t)ps * hs + i + half];
-          const float ra = __fadd_rn(__fmul_rn(a, c0), __fmul_rn(-b, s0));
-          const float rb = __fadd_rn(__fmul_rn(b, c1), __fmul_rn(a, s1));
-          if (hh < p.n_head) {
-            float* q = p.q_out + (size_t)m * (p.n_head * hs) + hh * hs + i;
-            q[0] = ra;
-            q[half] = rb;
-          } else {
-            const int g = hh - p.n_head;
-            float* kc = p.k_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
-            kc[0] = ra;
-            kc[half] = rb;
-          }
-        } else {
-          const int g = hh - p.n_head - p.n_groups;
-          float* vc = p.v_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
-          vc[0] = a;
-          vc[half] = b;
-        }
-      }
-    }
+    epilogue<EPI>(p, lane, mcount, m0, a, b, nA, nB);
     unit += unit_stride;
   }
 }
+
+
+// =====================================================================================================
+// v2: same math, weights fetched by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) instead of registers.
+//
+// Every warp owns a private ring of STAGES shared-memory slots (2 rows x KC floats each) with one mbarrier per
+// slot: lane 0 arms the barrier with expect_tx and issues two 1-D bulk copies (row A chunk, row B chunk); all
+// lanes wait on the barrier's phase, consume the chunk with conflict-free 128-bit LDS, __syncwarp, and lane 0
+// immediately refills the slot with the chunk STAGES ahead.  The prefetch distance (16 KB per warp) is therefore
+// independent of the register budget, continuous across unit boundaries, and is issued before the activation
+// prologue and before griddepcontrol.wait - so under programmatic dependent launch the weight stream of kernel
+// N+1 is already in flight while kernel N drains.
+// =====================================================================================================
+constexpr int KC = 512;     // floats per row chunk (2 KB bulk copies)
+constexpr int STAGES = 4;   // ring depth per warp: 4 x 2 x 2 KB = 16 KB in flight per warp
+constexpr int V2_WARPS = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int MT, int PRO, int EPI>
+__global__ void __launch_bounds__(V2_WARPS * 32) gemv2_kernel(const GemvParams p) {
+  extern __shared__ __align__(128) float smem2[];
+  __shared__ float red[8][8];
+  __shared__ __align__(8) uint64_t bars[V2_WARPS][STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K;
+  const int nIt = (K + 127) >> 7;
+  const int Kp = nIt << 7;
+  const int nCh = (K + KC - 1) / KC;
+  const int m0 = blockIdx.x * MT;
+  const int mcount = min(MT, p.M - m0);
+  const int n_units = (EPI == EPI_SWIGLU) ? p.N : (p.N >> 1);
+  const int unit0 = blockIdx.y * V2_WARPS + warp;
+  const int unit_stride = gridDim.y * V2_WARPS;
+  float* xs = smem2;                                                   // MT x Kp
+  float* ring = smem2 + (size_t)MT * Kp + (size_t)warp * STAGES * 2 * KC;  // this warp's slots
+  const int my_units = unit0 < n_units ? (n_units - unit0 + unit_stride - 1) / unit_stride : 0;
+  const int total = my_units * nCh;  // chunks this warp will consume
+
+  // producer side (lane 0): issue chunk t of this warp's flattened (unit, chunk) sequence
+  auto issue = [&](int t) {
+    const int uo = t / nCh, c = t - uo * nCh;
+    const float *rowA, *rowB;
+    int nA, nB;
+    unit_rows<EPI>(p, unit0 + uo * unit_stride, rowA, rowB, nA, nB);
+    const int k0 = c * KC;
+    const uint32_t bytes = (uint32_t)min(KC, K - k0) * 4u;
+    const int st = t % STAGES;
+    uint64_t* bar = &bars[warp][st];
+    mbar_expect_tx(bar, 2u * bytes);
+    bulk_g2s(ring + (size_t)st * 2 * KC, rowA + k0, bytes, bar);
+    bulk_g2s(ring + (size_t)st * 2 * KC + KC, rowB + k0, bytes, bar);
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[warp][s], 1);
+    fence_mbar_init();
+    const int pre = min(total, STAGES);
+    for (int t = 0; t < pre; ++t) issue(t);  // weights do not depend on the producer kernel: prefetch first
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  stage_activations<MT, PRO>(p, xs, red, Kp, m0, mcount);  // ends with __syncthreads()
+
+  float accA[MT], accB[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) accA[m] = accB[m] = 0.f;
+  for (int t = 0; t < total; ++t) {
+    const int uo = t / nCh, c = t - uo * nCh;
+    const int st = t % STAGES;
+    mbar_wait(&bars[warp][st], (uint32_t)((t / STAGES) & 1));
+    const float* sa = ring + (size_t)st * 2 * KC;
+    const float* sb = sa + KC;
+    const int k0 = c * KC;
+#pragma unroll
+    for (int it = 0; it < KC / 128; ++it) {
+      const int kk = (it * 32 + lane) * 4;
+      if (k0 + kk < K) {
+        const float4 wa = *reinterpret_cast<const float4*>(sa + kk);
+        const float4 wb = *reinterpret_cast<const float4*>(sb + kk);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + m * Kp + k0 + kk);
+          accA[m] = fmaf(wa.x, xv.x, accA[m]);
+          accA[m] = fmaf(wa.y, xv.y, accA[m]);
+          accA[m] = fmaf(wa.z, xv.z, accA[m]);
+          accA[m] = fmaf(wa.w, xv.w, accA[m]);
+          accB[m] = fmaf(wb.x, xv.x, accB[m]);
+          accB[m] = fmaf(wb.y, xv.y, accB[m]);
+          accB[m] = fmaf(wb.z, xv.z, accB[m]);
+          accB[m] = fmaf(wb.w, xv.w, accB[m]);
+        }
+      }
+    }
+    __syncwarp();  // every lane has consumed the slot -> refill it with the chunk STAGES ahead
+    if (lane == 0 && t + STAGES < total) issue(t + STAGES);
+    if (c == nCh - 1) {  // unit finished: reduce + fused epilogue
+      const float *rowA, *rowB;
+      int nA, nB;
+      unit_rows<EPI>(p, unit0 + uo * unit_stride, rowA, rowB, nA, nB);
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float sa2 = warp_sum(accA[m]);
+        const float sb2 = warp_sum(accB[m]);
+        if (lane == m) {
+          a = sa2;
+          b = sb2;
+        }
+        accA[m] = accB[m] = 0.f;
+      }
+      epilogue<EPI>(p, lane, mcount, m0, a, b, nA, nB);
+    }
+  }
+}
+
+int g_gemv_impl = 2;
 
 int g_sm_count = 0;
 int sm_count() {
@@ -255,23 +418,43 @@ int sm_count() {
 template <int MT, int PRO, int EPI>
 cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
   const int nIt = (p.K + 127) >> 7;
-  const size_t smem = (size_t)MT * nIt * 128 * sizeof(float);
-  auto kern = gemv_kernel<MT, PRO, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  const size_t xbytes = (size_t)MT * nIt * 128 * sizeof(float);
   const int n_units = (EPI == EPI_SWIGLU) ? p.N : p.N / 2;
   const int m_tiles = (p.M + MT - 1) / MT;
+  const size_t kMaxSmem = 220 * 1024;
+  if (g_gemv_impl == 2) {
+    auto kern = gemv2_kernel<MT, PRO, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    const size_t smem = xbytes + (size_t)V2_WARPS * STAGES * 2 * KC * sizeof(float);
+    if (smem > kMaxSmem) return cudaErrorInvalidValue;
+    // one wave of co-resident CTAs (shared memory bounds the CTAs per SM); beyond that warps loop over units
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int gy = (n_units + V2_WARPS - 1) / V2_WARPS;
+    const int cap = sm_count() * per_sm;
+    if (gy > cap) gy = cap;
+    return launch(lc, kern, dim3(m_tiles, gy), dim3(V2_WARPS * 32), smem, p);
+  }
+  auto kern = gemv_kernel<MT, PRO, EPI>;
+  static bool attr_set1 = false;
+  if (!attr_set1) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set1 = true;
+  }
+  if (xbytes > 200 * 1024) return cudaErrorInvalidValue;
   // 8 warps per CTA when that still gives >= 2 CTAs per SM, else 4 (finer granules balance small N)
   int nwarps = (n_units >= 8 * 2 * sm_count()) ? 8 : 4;
   int gy = (n_units + nwarps - 1) / nwarps;
   const int cap = sm_count() * 8;  // persistent cap for very tall matrices (lm_head): warps loop over units
   if (gy > cap) gy = cap;
-  return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), smem, p);
+  return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), xbytes, p);
 }
 
 template <int PRO, int EPI>
@@ -279,7 +462,7 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
   // tile of M rows per CTA; bounded by shared memory (MT*K*4 <= 200 KB)
   const size_t rowb = (size_t)((p.K + 127) / 128) * 128 * 4;
   int mt = p.M >= 8 ? 8 : (p.M >= 3 ? 4 : p.M);
-  while (mt > 1 && mt * rowb > 160 * 1024) mt >>= 1;
+  while (mt > 1 && mt * rowb > 128 * 1024) mt >>= 1;
   switch (mt) {
     case 1: return launch_one<1, PRO, EPI>(lc, p);
     case 2: return launch_one<2, PRO, EPI>(lc, p);
@@ -289,6 +472,8 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
 }
 
 }  // namespace
+
+void set_gemv_impl(int v) { g_gemv_impl = (v == 1) ? 1 : 2; }
 
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;

@@ -8,7 +8,7 @@ namespace ua2 {
 enum : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_GATHER = 2, PRO_ATTN = 3 };
 enum : int { EPI_STORE = 0, EPI_RESADD = 1, EPI_QKV = 2, EPI_SWIGLU = 3 };
 
-constexpr int ATTN_CHUNK = 128;  // keys per split CTA of the attention kernel
+constexpr int ATTN_CHUNK = 64;  // keys per split CTA of the attention kernel
 
 struct GemvParams {
   // weights: W (N x K) row-major fp32 (nn.Linear layout); W2 second matrix for SwiGLU
@@ -42,6 +42,7 @@ struct GemvParams {
   int S_max = 0;
 };
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
+void set_gemv_impl(int v);  // 1 = register-streamed (LDG), 2 = bulk-copy ring (cp.async.bulk + mbarrier), default 2
 
 // ---------------------------------------------------------------- attention over the KV cache
 struct AttnParams {

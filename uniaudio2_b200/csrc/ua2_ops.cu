@@ -6,6 +6,15 @@ using namespace ua2;
 
 extern "C" {
 
+int ua2_set_global_option(const char* name, int value) {
+  UA2_REQUIRE(name, "null name");
+  if (std::string(name) == "gemv_impl") {
+    set_gemv_impl(value);
+    return UA2_OK;
+  }
+  UA2_REQUIRE(false, std::string("unknown global option ") + name);
+}
+
 int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float eps, const float* residual, float* y,
                    int M, int N, int K, void* stream) {
   UA2_REQUIRE(x && W && y, "null argument");

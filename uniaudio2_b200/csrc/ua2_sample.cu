@@ -158,9 +158,17 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleArgs
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
       const int shift = 24 - 8 * pass;
-      for (int i = tid; i < n; i += SAMPLE_THREADS) {
-        const uint32_t key = f2key(val(i));
-        if ((key & pmask) == prefix) atomicAdd(&hist[pass][(key >> shift) & 255u], 1u);
+      // warp-aggregated increments: logits share their top bits, so un-aggregated atomics would serialise on
+      // a handful of bins (one ATOMS per distinct bin per warp instead of one per element)
+      for (int base = 0; base < n; base += SAMPLE_THREADS) {
+        const int i = base + tid;
+        uint32_t bin = 256u;
+        if (i < n) {
+          const uint32_t key = f2key(val(i));
+          if ((key & pmask) == prefix) bin = (key >> shift) & 255u;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[pass][bin], (unsigned)__popc(peers));
       }
       cluster_barrier();
       // every CTA redundantly merges the histograms and picks the same bin
