@@ -253,7 +253,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
-    ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "0")))
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
+    ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -303,15 +304,17 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    from uniaudio2_b200 import _lib
     from uniaudio2_b200.evaluation.tts_task import Generator, default_train_args
     from uniaudio2_b200.llm_models.model_new import Model_stage3
 
+    if args.gemv_impl:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv_impl", args.gemv_impl))
     with torch.inference_mode():
         model = Model_stage3(model_args(), device=dev)
         init_weights_(model, 0)  # same weights on every replica
         gen = Generator(model, default_train_args(REASON_CARD, SEMANTIC_CARD), is_cfg=False)  # setup_caches(1)
-        if args.pdl:
-            model.set_option("pdl", 1)
+        model.set_option("pdl", int(args.pdl))
         task_prompt, text = synthetic_prompt(rank)
         tokens, mask = gen.prepare_tts_task(task_prompt, text)
         assert tokens.size(0) == PROMPT_LEN

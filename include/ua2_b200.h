@@ -34,7 +34,8 @@ const char* ua2_last_error(void);
 /* library / device probe: returns the SM count of the current device (e.g. 148), <0 on error */
 int ua2_device_sm_count(void);
 const char* ua2_version(void);
-/* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (cp.async.bulk + mbarrier rings, default) */
+/* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (per-warp cp.async.bulk + mbarrier rings, default) |
+ * 3 (one persistent CTA per SM, slab + K-split rings) */
 int ua2_set_global_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -116,7 +117,7 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
 int ua2_llm_get_kv(ua2_llm* h, int which, int layer, float** k, float** v);
 /* name: "h_final" (B x n_embd), "text_logits" (B x text_vocab), "audio_logits" (nq x B x audio_vocab) */
 int ua2_llm_get_buffer(ua2_llm* h, const char* name, float** ptr, int64_t* numel);
-/* knobs: "graph" (0/1, default 1: replay the frame as a CUDA graph), "pdl" (0/1) */
+/* knobs: "graph" (0/1, default 1: replay the frame as a CUDA graph), "pdl" (0/1, default 1: programmatic dependent launch) */
 int ua2_llm_set_option(ua2_llm* h, const char* name, int value);
 /* number of kernels launched (or graph kernel nodes replayed) by the last prefill / generate_frame */
 int ua2_llm_last_launch_count(ua2_llm* h);

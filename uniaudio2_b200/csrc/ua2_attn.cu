@@ -38,9 +38,16 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   pdl_wait();
   const int n_keys = p.pos[m] + 1;
   const int start = split * C;
-  if (start >= n_keys) return;
-  const int cnt = min(C, n_keys - start);
   const int qpk = p.n_head / p.n_groups;
+  if (start >= n_keys) {  // empty split: publish weight-0 statistics so consumers can merge all launched splits blindly
+    if (tid < qpk) {
+      const size_t idx = (((size_t)m * p.n_head + g * qpk + tid) * p.max_splits + split) * 2;
+      p.ml_part[idx] = -INFINITY;
+      p.ml_part[idx + 1] = 0.f;
+    }
+    return;
+  }
+  const int cnt = min(C, n_keys - start);
   const int b = p.bidx[m];
   const float scale = rsqrtf((float)HS);
   const float* Kc = p.k_cache + (((size_t)b * p.n_groups + g) * p.S_max + start) * HS;
@@ -207,6 +214,8 @@ cudaError_t launch_attn_hs(const LaunchCtx& lc, const AttnParams& p) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_split_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = prefer_max_smem(attn_split_kernel<HS>);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const dim3 grid(p.n_splits_launch, p.n_groups, p.M), block(128);
@@ -226,6 +235,11 @@ cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p) {
 }
 
 cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float* y) {
+  static bool once = false;
+  if (!once) {
+    prefer_max_smem(attn_combine_kernel);
+    once = true;
+  }
   return launch(lc, attn_combine_kernel, dim3(p.M), dim3(256), 0, p, y);
 }
 

@@ -60,6 +60,13 @@ struct LaunchCtx {
   int* launch_counter = nullptr;
 };
 
+// Every kernel of the path asks for the maximum shared-memory carveout, so consecutive (and, under PDL,
+// co-resident) kernels never force an L1/shared reconfiguration of the SM between launches.
+template <typename K>
+inline cudaError_t prefer_max_smem(K kern) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                           Args... args) {

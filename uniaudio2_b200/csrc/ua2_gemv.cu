@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
 // prologue and before griddepcontrol.wait - so under programmatic dependent launch the weight stream of kernel
 // N+1 is already in flight while kernel N drains.
 // =====================================================================================================
-constexpr int KC = 512;     // floats per row chunk (2 KB bulk copies)
-constexpr int STAGES = 4;   // ring depth per warp: 4 x 2 x 2 KB = 16 KB in flight per warp
+constexpr int KC = 1024;    // floats per row chunk: 4 KB bulk copies (1-2 KB copies cap at 2.8-5.8 TB/s, see microbench)
+constexpr int STAGES = 2;   // ring depth per warp: 2 x 2 x 4 KB = 16 KB in flight per warp
 constexpr int V2_WARPS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -428,6 +428,8 @@ cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
       if (e != cudaSuccess) return e;
+      e = prefer_max_smem(kern);
+      if (e != cudaSuccess) return e;
       attr_set = true;
     }
     const size_t smem = xbytes + (size_t)V2_WARPS * STAGES * 2 * KC * sizeof(float);
@@ -445,6 +447,8 @@ cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
   static bool attr_set1 = false;
   if (!attr_set1) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = prefer_max_smem(kern);
     if (e != cudaSuccess) return e;
     attr_set1 = true;
   }
@@ -473,10 +477,11 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
 
 }  // namespace
 
-void set_gemv_impl(int v) { g_gemv_impl = (v == 1) ? 1 : 2; }
+void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 2; }
 
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;
+  if (g_gemv_impl == 3) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
 #define UA2_CASE(P, E) \
   if (pro == P && epi == E) return launch_mt<P, E>(lc, p);
   UA2_CASE(PRO_PLAIN, EPI_STORE)

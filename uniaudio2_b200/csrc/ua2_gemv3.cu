@@ -1,0 +1,477 @@
+// Skinny fp32 linear, v3: one persistent CTA per SM, bulk-copy weight rings, K split across warps.
+//
+// Why (measured, profiles/r1_launches_v1.md): at M = 1 every linear of the AR frame is a 3-35 us weight stream and the
+// frame has ~355 of them, so what is lost is not steady-state bandwidth but the bubble at every kernel boundary
+// (drain -> launch -> activation prologue -> first weight round trip, ~7 us per kernel with v1/v2).  v3 is built so
+// that the HBM stream does not stop at a boundary:
+//   * exactly ONE CTA per SM and <= ~110 KB of shared memory, so the CTAs of the NEXT kernel (programmatic dependent
+//     launch) are co-resident with this kernel's CTAs from its start: they fill their weight rings and park on
+//     griddepcontrol.wait while this kernel is still streaming;
+//   * each warp owns a ring of shared-memory slots fed by cp.async.bulk (SASS UBLKCP) completing on per-slot
+//     mbarriers; the ring is filled BEFORE griddepcontrol.wait / the activation prologue and refilled the moment a
+//     slot is consumed, so ~64-96 KB per SM are always in flight, independent of the register budget;
+//   * work is balanced to one weight-row pair: CTA c owns the contiguous slab of units [c*U/G, (c+1)*U/G) and its 8
+//     warps split K (nsl slices per unit), partial sums meet in shared memory once per round of <= 32 units;
+//   * the prologue is a single L2 round trip: RMSNorm's rsqrt(mean(x^2)+eps) is a per-row scalar, so it is applied in
+//     the epilogue ((sum_k W[n,k] x[k] g[k]) * rs) instead of forcing a reduce-then-scale pass before the first FMA;
+//     the attention combine reads all launched splits at once (empty splits carry weight 0).
+#include "ua2_kernels.cuh"
+
+namespace ua2 {
+namespace {
+
+constexpr int NWARPS = 9;   // reduction slots (8 or 9 warps per CTA)
+constexpr int MAXW_RED = NWARPS;
+constexpr int MAX_STAGES = 6;
+constexpr int ROUND_UNITS = 32;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+               "l"(src), "r"(bytes), "r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(s32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int EPI>
+__device__ __forceinline__ void unit_rows(const GemvParams& p, int u, const float*& rowA, const float*& rowB, int& nA,
+                                          int& nB) {
+  if (EPI == EPI_SWIGLU) {
+    nA = nB = u;
+    rowA = p.W + (size_t)u * p.K;
+    rowB = p.W2 + (size_t)u * p.K;
+  } else if (EPI == EPI_QKV) {
+    const int half = p.hs >> 1;
+    const int hh = u / half, i = u - hh * half;
+    nA = hh * p.hs + i;
+    nB = nA + half;
+    rowA = p.W + (size_t)nA * p.K;
+    rowB = p.W + (size_t)nB * p.K;
+  } else {
+    nA = 2 * u;
+    nB = nA + 1;
+    rowA = p.W + (size_t)nA * p.K;
+    rowB = p.W + (size_t)nB * p.K;
+  }
+}
+
+// activation tile -> shared memory in ONE L2 round trip; RMSNorm: xs = x*g, per-warp partial sum of squares -> red
+template <int MT, int PRO>
+__device__ __forceinline__ void stage_activations3(const GemvParams& p, float* xs, float (*red)[MAXW_RED], int Kp, int m0,
+                                                   int mcount, int n_splits) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K;
+  if (PRO == PRO_ATTN) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      for (int k = tid * 4; k < Kp; k += blockDim.x * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < mcount && k < K) {
+          const int hh = k / p.hs, d = k - hh * p.hs;
+          const size_t base = ((size_t)(m0 + m) * p.n_head + hh) * p.max_splits;
+          if (n_splits == 1) {  // common case: one split, y = o / l
+            const float l = p.ml_part[base * 2 + 1];
+            const float4 o = *reinterpret_cast<const float4*>(p.o_part + base * p.hs + d);
+            const float inv = 1.f / l;
+            v = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+          } else {
+            float mx = -INFINITY;
+            for (int s = 0; s < n_splits; ++s) mx = fmaxf(mx, p.ml_part[(base + s) * 2]);
+            float den = 0.f;
+            for (int s = 0; s < n_splits; ++s) {
+              const float w = __expf(p.ml_part[(base + s) * 2] - mx);  // empty split: exp(-inf) = 0
+              if (w > 0.f) {
+                den += w * p.ml_part[(base + s) * 2 + 1];
+                const float4 o = *reinterpret_cast<const float4*>(p.o_part + (base + s) * p.hs + d);
+                v.x += w * o.x;
+                v.y += w * o.y;
+                v.z += w * o.z;
+                v.w += w * o.w;
+              }
+            }
+            const float inv = 1.f / den;
+            v.x *= inv;
+            v.y *= inv;
+            v.z *= inv;
+            v.w *= inv;
+          }
+        }
+        *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
+      }
+    }
+  } else {
+    float ss[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) ss[m] = 0.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float* src = nullptr;
+      if (m < mcount) {
+        if (PRO == PRO_GATHER) {
+          const long long row = (long long)p.gidx[(size_t)(m0 + m) * p.gidx_stride] + p.gidx_offset;
+          src = p.emb + (size_t)row * K;
+        } else {
+          src = p.X + (size_t)(m0 + m) * p.ldx;
+        }
+      }
+      for (int k = tid * 4; k < Kp; k += blockDim.x * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr && k < K) {
+          v = *reinterpret_cast<const float4*>(src + k);
+          if (PRO == PRO_RMSNORM) {
+            ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k);
+            v.x *= g.x;
+            v.y *= g.y;
+            v.z *= g.z;
+            v.w *= g.w;
+          }
+        }
+        *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
+      }
+    }
+    if (PRO == PRO_RMSNORM) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float s = warp_sum(ss[m]);
+        if (lane == 0) red[m][warp] = s;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// epilogue of one (activation row m, unit) pair given the two complete row sums
+template <int EPI>
+__device__ __forceinline__ void epilogue_one(const GemvParams& p, int m, float a, float b, int nA) {
+  if (EPI == EPI_STORE) {
+    *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a, b);
+  } else if (EPI == EPI_RESADD) {
+    const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
+    *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a + r.x, b + r.y);
+  } else if (EPI == EPI_SWIGLU) {
+    const float s = a / (1.0f + expf(-a));  // F.silu, lit_model.py:594
+    p.Y[(size_t)m * p.ldy + nA] = s * b;
+  } else {  // EPI_QKV: split, half-split RoPE (lit_model.py:795-806), KV-cache append (:854-855)
+    const int hs = p.hs, half = hs >> 1;
+    const int hh = nA / hs, i = nA - hh * hs;
+    const int ps = p.pos[m];
+    if (hh < p.n_head + p.n_groups) {
+      const float c0 = p.cos[(size_t)ps * hs + i], s0 = p.sin[(size_t)ps * hs + i];
+      const float c1 = p.cos[(size_t)ps * hs + i + half], s1 = p.sin[(size_t)ps * hs + i + half];
+      const float ra = __fadd_rn(__fmul_rn(a, c0), __fmul_rn(-b, s0));
+      const float rb = __fadd_rn(__fmul_rn(b, c1), __fmul_rn(a, s1));
+      if (hh < p.n_head) {
+        float* q = p.q_out + (size_t)m * (p.n_head * hs) + hh * hs + i;
+        q[0] = ra;
+        q[half] = rb;
+      } else {
+        const int g = hh - p.n_head;
+        float* kc = p.k_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
+        kc[0] = ra;
+        kc[half] = rb;
+      }
+    } else {
+      const int g = hh - p.n_head - p.n_groups;
+      float* vc = p.v_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
+      vc[0] = a;
+      vc[half] = b;
+    }
+  }
+}
+
+struct V3Cfg {
+  int nsl;       // K slices per unit; one warp per (group, slice)
+  int ngrp;      // unit groups per CTA; warps = ngrp * nsl (8 or 9)
+  int SL;        // floats per slice (multiple of 128)
+  int KCW;       // floats per bulk copy (<= 1024): sized so a copy is >= 4 KB whenever K allows (see microbench)
+  int stages;    // ring depth per warp (slots of KCW floats)
+  int n_splits;  // attention splits to merge (PRO_ATTN)
+};
+
+constexpr int MAXW = 9;
+
+// ROWS = weight rows per unit: 2 for the paired epilogues (QKV rotation pair / SwiGLU fc_1+fc_2), 1 for store / residual
+template <int EPI>
+struct RowsOf {
+  static constexpr int value = (EPI == EPI_QKV || EPI == EPI_SWIGLU) ? 2 : 1;
+};
+
+template <int EPI>
+__device__ __forceinline__ const float* unit_row(const GemvParams& p, int u, int r, int& nA) {
+  if (EPI == EPI_SWIGLU) {
+    nA = u;
+    return (r == 0 ? p.W : p.W2) + (size_t)u * p.K;
+  } else if (EPI == EPI_QKV) {
+    const int half = p.hs >> 1;
+    const int hh = u / half, i = u - hh * half;
+    nA = hh * p.hs + i;
+    return p.W + (size_t)(nA + r * half) * p.K;
+  } else {
+    nA = u;
+    return p.W + (size_t)u * p.K;
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_v3(const GemvParams& p, int m, float a, float b, int nA) {
+  if (EPI == EPI_STORE) {
+    p.Y[(size_t)m * p.ldy + nA] = a;
+  } else if (EPI == EPI_RESADD) {
+    p.Y[(size_t)m * p.ldy + nA] = a + p.R[(size_t)m * p.ldr + nA];
+  } else {
+    epilogue_one<EPI>(p, m, a, b, nA);
+  }
+}
+
+template <int MT, int PRO, int EPI>
+__global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p, const V3Cfg c) {
+  constexpr int ROWS = RowsOf<EPI>::value;
+  extern __shared__ __align__(128) float smem3[];
+  __shared__ float red[8][NWARPS];
+  __shared__ __align__(8) uint64_t bars[MAXW][MAX_STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthreads = blockDim.x;
+  const int K = p.K;
+  const int Kp = ((K + 127) >> 7) << 7;
+  const int m0 = blockIdx.x * MT;
+  const int mcount = min(MT, p.M - m0);
+  const int n_units = (ROWS == 2) ? ((EPI == EPI_SWIGLU) ? p.N : (p.N >> 1)) : p.N;
+  // slab of this CTA
+  const int G = gridDim.y, cta = blockIdx.y;
+  const int u_lo = (int)(((long long)cta * n_units) / G), u_hi = (int)(((long long)(cta + 1) * n_units) / G);
+  const int slab = u_hi - u_lo;
+  const int ngrp = c.ngrp;
+  const int grp = warp / c.nsl, sl = warp - grp * c.nsl;
+  const int ks = sl * c.SL;
+  const int klen = max(0, min(K, ks + c.SL) - ks);
+  const int nCh = (klen + c.KCW - 1) / c.KCW;
+  const int per_unit = nCh * ROWS;                                        // bulk copies per unit for this warp
+  const int my_units = slab > grp ? (slab - grp + ngrp - 1) / ngrp : 0;  // units grp, grp+ngrp, ... of the slab
+  const int total = my_units * per_unit;
+
+  float* xs = smem3;                       // MT x Kp
+  float* part = smem3 + (size_t)MT * Kp;  // [2 buffers][ROUND_UNITS][nsl][ROWS][MT]
+  const int part_stride = ROUND_UNITS * c.nsl * ROWS * MT;
+  float* ring = part + 2 * part_stride + (size_t)warp * c.stages * c.KCW;
+
+  auto issue = [&](int t) {
+    const int uo = t / per_unit, rem = t - uo * per_unit;
+    const int r = rem / nCh, ch = rem - r * nCh;
+    int nA;
+    const float* row = unit_row<EPI>(p, u_lo + grp + uo * ngrp, r, nA);
+    const int k0 = ks + ch * c.KCW;
+    const uint32_t bytes = (uint32_t)min(c.KCW, ks + klen - k0) * 4u;
+    const int st = t % c.stages;
+    uint64_t* bar = &bars[warp][st];
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(ring + (size_t)st * c.KCW, row + k0, bytes, bar);
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < c.stages; ++s) mbar_init(&bars[warp][s], 1);
+    fence_mbar_init();
+    const int pre = min(total, c.stages);
+    for (int t = 0; t < pre; ++t) issue(t);  // weights never depend on the producer kernel
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  stage_activations3<MT, PRO>(p, xs, red, Kp, m0, mcount, c.n_splits);  // ends with __syncthreads()
+
+  float acc[ROWS][MT];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
+
+  const int n_rounds = (slab + ROUND_UNITS - 1) / ROUND_UNITS;
+  int t = 0;
+  for (int rd = 0; rd < n_rounds; ++rd) {
+    const int r_lo = rd * ROUND_UNITS, r_hi = min(slab, r_lo + ROUND_UNITS);  // slab-local units of this round
+    float* pb = part + (rd & 1) * part_stride;
+    while (t < total) {
+      const int uo = t / per_unit, rem = t - uo * per_unit;
+      const int ul = grp + uo * ngrp;
+      if (ul >= r_hi) break;
+      const int r = rem / nCh, ch = rem - r * nCh;
+      const int st = t % c.stages;
+      mbar_wait(&bars[warp][st], (uint32_t)((t / c.stages) & 1));
+      const float* sw = ring + (size_t)st * c.KCW;
+      const int k0 = ks + ch * c.KCW;
+      const int kend = min(c.KCW, ks + klen - k0);
+      float part_acc[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) part_acc[m] = 0.f;
+#pragma unroll 4
+      for (int kk = lane * 4; kk < kend; kk += 128) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + kk);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + m * Kp + k0 + kk);
+          part_acc[m] = fmaf(w.x, xv.x, part_acc[m]);
+          part_acc[m] = fmaf(w.y, xv.y, part_acc[m]);
+          part_acc[m] = fmaf(w.z, xv.z, part_acc[m]);
+          part_acc[m] = fmaf(w.w, xv.w, part_acc[m]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && t + c.stages < total) issue(t + c.stages);
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr)
+        if (rr == r) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) acc[rr][m] += part_acc[m];
+        }
+      if (rem == per_unit - 1) {  // slice of this unit finished: publish the partial sums
+        float* dst = pb + ((size_t)(ul - r_lo) * c.nsl + sl) * ROWS * MT;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const float s2 = warp_sum(acc[rr][m]);
+            if (lane == 0) dst[rr * MT + m] = s2;
+            acc[rr][m] = 0.f;
+          }
+      }
+      ++t;
+    }
+    __syncthreads();  // all partial sums of the round are in shared memory
+    const int n_ru = r_hi - r_lo;
+    for (int idx = tid; idx < n_ru * mcount; idx += nthreads) {
+      const int ul = idx / mcount, m = idx - ul * mcount;
+      float a = 0.f, b = 0.f;
+      const float* src = pb + (size_t)ul * c.nsl * ROWS * MT;
+      for (int s = 0; s < c.nsl; ++s) {
+        if (s * c.SL < K) {  // slices past the end of K never wrote
+          a += src[s * ROWS * MT + m];
+          if (ROWS == 2) b += src[s * ROWS * MT + MT + m];
+        }
+      }
+      if (PRO == PRO_RMSNORM) {
+        float tot = 0.f;
+        for (int w = 0; w < (nthreads >> 5); ++w) tot += red[m][w];
+        const float rs = rsqrtf(tot / (float)K + p.eps);  // lit_model.py:887-888, applied after the dot product
+        a *= rs;
+        b *= rs;
+      }
+      int nA;
+      unit_row<EPI>(p, u_lo + r_lo + ul, 0, nA);
+      epilogue_v3<EPI>(p, m0 + m, a, b, nA);
+    }
+    // no second barrier: the next round writes the other partial buffer, and a thread only reaches the barrier of
+    // round rd+1 after finishing its epilogue share of round rd
+  }
+}
+
+int g_sms = 0;
+int sm_count3() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+template <int MT, int PRO, int EPI>
+cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
+  constexpr int ROWS = RowsOf<EPI>::value;
+  auto kern = gemv3_kernel<MT, PRO, EPI>;
+  const size_t kMaxSmem = 224 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (e != cudaSuccess) return e;
+    e = prefer_max_smem(kern);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int K = p.K;
+  const int Kp = ((K + 127) / 128) * 128;
+  V3Cfg c;
+  // K slices of ~1024 floats: every bulk copy is >= 4 KB, the size at which 8-9 warps x 2 slots saturate HBM
+  // (profiles/r1_microbench_hbm_streaming.txt: 4 KB copies, depth 2, 8 warps -> 7.16 TB/s; 1 KB copies -> 2.8 TB/s)
+  c.nsl = (K + 1023) / 1024;
+  if (c.nsl > 8) c.nsl = 8;
+  if (c.nsl < 1) c.nsl = 1;
+  c.ngrp = 8 / c.nsl;
+  if (c.nsl == 3) c.ngrp = 3;  // 9 warps
+  if (c.ngrp < 1) c.ngrp = 1;
+  const int nwarps = c.nsl * c.ngrp;
+  const int per = (K + c.nsl - 1) / c.nsl;
+  c.SL = ((per + 127) / 128) * 128;
+  c.KCW = c.SL < 1024 ? c.SL : 1024;
+  c.n_splits = n_splits;
+  const size_t xbytes = (size_t)MT * Kp * 4;
+  const size_t pbytes = (size_t)2 * ROUND_UNITS * c.nsl * ROWS * MT * 4;
+  const size_t stage_bytes = (size_t)nwarps * c.KCW * 4;
+  // M <= 2 (decode): stay under ~half an SM's shared memory so the dependent kernel's CTA is co-resident (PDL)
+  const size_t budget = (MT <= 2 ? 112 * 1024 : kMaxSmem);
+  int stages = (int)((budget > xbytes + pbytes ? budget - xbytes - pbytes : 0) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  c.stages = stages;
+  const size_t smem = xbytes + pbytes + stage_bytes * stages;
+  if (smem > kMaxSmem) return cudaErrorInvalidValue;
+  const int n_units = (ROWS == 2) ? ((EPI == EPI_SWIGLU) ? p.N : p.N / 2) : p.N;
+  const int m_tiles = (p.M + MT - 1) / MT;
+  int gy = sm_count3();
+  if (gy > n_units) gy = n_units;
+  return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), smem, p, c);
+}
+
+template <int PRO, int EPI>
+cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
+  const size_t rowb = (size_t)((p.K + 127) / 128) * 128 * 4;
+  int mt = p.M >= 8 ? 8 : (p.M >= 3 ? 4 : p.M);
+  while (mt > 1 && mt * rowb > 128 * 1024) mt >>= 1;
+  switch (mt) {
+    case 1: return launch3_one<1, PRO, EPI>(lc, p, n_splits);
+    case 2: return launch3_one<2, PRO, EPI>(lc, p, n_splits);
+    case 4: return launch3_one<4, PRO, EPI>(lc, p, n_splits);
+    default: return launch3_one<8, PRO, EPI>(lc, p, n_splits);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits) {
+#define UA2_CASE3(P, E) \
+  if (pro == P && epi == E) return launch3_mt<P, E>(lc, p, n_splits);
+  UA2_CASE3(PRO_PLAIN, EPI_STORE)
+  UA2_CASE3(PRO_PLAIN, EPI_RESADD)
+  UA2_CASE3(PRO_PLAIN, EPI_SWIGLU)
+  UA2_CASE3(PRO_PLAIN, EPI_QKV)
+  UA2_CASE3(PRO_RMSNORM, EPI_STORE)
+  UA2_CASE3(PRO_RMSNORM, EPI_RESADD)
+  UA2_CASE3(PRO_RMSNORM, EPI_SWIGLU)
+  UA2_CASE3(PRO_RMSNORM, EPI_QKV)
+  UA2_CASE3(PRO_GATHER, EPI_STORE)
+  UA2_CASE3(PRO_ATTN, EPI_RESADD)
+#undef UA2_CASE3
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace ua2

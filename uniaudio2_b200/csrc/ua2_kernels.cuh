@@ -26,6 +26,7 @@ struct GemvParams {
   const float* o_part = nullptr;  // ATTN: split-softmax partials of the attention kernel
   const float* ml_part = nullptr;
   int max_splits = 0;
+  int n_splits = 0;  // splits launched by the attention kernel (empty ones carry (m=-inf, l=0))
   const int32_t* pos = nullptr;   // (M) cache slot / position of each row
   const int32_t* bidx = nullptr;  // (M) batch row of each row
   int n_head = 0, n_groups = 0, hs = 0;
@@ -42,7 +43,8 @@ struct GemvParams {
   int S_max = 0;
 };
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
-void set_gemv_impl(int v);  // 1 = register-streamed (LDG), 2 = bulk-copy ring (cp.async.bulk + mbarrier), default 2
+void set_gemv_impl(int v);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
+cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);
 
 // ---------------------------------------------------------------- attention over the KV cache
 struct AttnParams {

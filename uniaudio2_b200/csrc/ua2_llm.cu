@@ -54,7 +54,7 @@ struct ua2_llm {
   int64_t h_final_numel = 0, text_logits_numel = 0, audio_logits_numel = 0;
   std::vector<void*> owned;
   // options / stats
-  int opt_graph = 1, opt_pdl = 0;
+  int opt_graph = 1, opt_pdl = 1;
   int last_launches = 0;
   unsigned long long frame_counter = 0;
   struct GraphEntry {
@@ -142,6 +142,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.o_part = h->o_part;
     p.ml_part = h->ml_part;
     p.max_splits = h->max_splits;
+    p.n_splits = n_splits;
     p.pos = pos;
     p.n_head = c.n_head;
     p.hs = hs;

@@ -140,8 +140,19 @@ __global__ void transpose_head_kernel(const float* __restrict__ src, float* __re
 
 }  // namespace
 
+static void misc_attrs_once() {
+  static bool done = false;
+  if (done) return;
+  prefer_max_smem(embed_kernel);
+  prefer_max_smem(norm_mix_kernel);
+  prefer_max_smem(frame_begin_kernel);
+  prefer_max_smem(prefill_begin_kernel);
+  done = true;
+}
+
 cudaError_t launch_embed(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, const float* audio_emb,
                          const float* wte, float* audio_in, float* text_emb, int M, int nq, int V, int D) {
+  misc_attrs_once();
   const int threads = 128;
   const dim3 grid((D / 4 + threads - 1) / threads, M);
   return launch(lc, embed_kernel, grid, dim3(threads), 0, tokens, mask, audio_emb, wte, audio_in, text_emb, nq, V, D);
@@ -149,12 +160,14 @@ cudaError_t launch_embed(const LaunchCtx& lc, const int64_t* tokens, const uint8
 
 cudaError_t launch_norm_mix(const LaunchCtx& lc, const float* x, const float* w, float eps, const uint8_t* mask,
                             int nq, const float* add, float* keep, float* out, int M, int D, int mode) {
+  misc_attrs_once();
   return launch(lc, norm_mix_kernel, dim3(M), dim3(256), 0, x, w, eps, mask, nq, add, keep, out, D, mode);
 }
 
 cudaError_t launch_frame_begin(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, int n_tok,
                                int64_t* d_tokens, uint8_t* d_mask, int32_t* d_pos, int32_t* d_bidx, int B,
                                int32_t pos_value, FrameScalars* d_fs, FrameScalars fs) {
+  misc_attrs_once();
   return launch(lc, frame_begin_kernel, dim3(1), dim3(128), 0, tokens, mask, n_tok, d_tokens, d_mask, d_pos, d_bidx, B,
                 pos_value, d_fs, fs);
 }

@@ -347,6 +347,8 @@ cudaError_t launch_sampler(const LaunchCtx& lc, const float* logits, int V, cons
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_CAP * 4);
     if (e != cudaSuccess) return e;
+    prefer_max_smem(sample_kernel<true>);
+    prefer_max_smem(sample_kernel<false>);
     attr_set = true;
   }
   if (lc.launch_counter) ++*lc.launch_counter;
