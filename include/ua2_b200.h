@@ -152,6 +152,67 @@ int ua2_sample_topk_f32(const float* logits, int R, int V, float temperature, in
                         float cfg_scale, const float* noise, uint64_t seed, uint64_t offset, int32_t* out,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Codec operators: SEANet causal convolutions and residual VQ (tools/tokenizer/MimiCodec/model/*, the
+ * importable twin of llm_modules/{seanet,conv,resample}.py + quantization/{core_vq,vq}.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* StreamingConv1d.forward, non-streaming causal branch (modules/conv.py:232-254): left pad k_eff - stride, right
+ * "extra" pad to a full last window, T_out = ceil(T_in / stride).  w_ckc: weights repacked (Cin, K, Cout).
+ * pre_elu: apply the nn.ELU that SEANet places in front of the conv (modules/seanet.py:52-66, :196, :214).
+ * residual != NULL: y = residual + conv (SEANetResnetBlock skip, modules/seanet.py:92-94).
+ * replicate_pad: pad_mode 'replicate' (ConvDownsample1d, modules/resample.py:48) instead of zeros. */
+int ua2_conv1d_causal_f32(const float* x, const float* w_ckc, const float* bias, const float* residual, float* y, int B,
+                          int Cin, int Cout, int T_in, int K, int stride, int dilation, int pre_elu, int replicate_pad,
+                          void* stream);
+/* StreamingConvTranspose1d.forward, causal, trim_right_ratio = 1 (modules/conv.py:306-329): kernel = 2*stride,
+ * T_out = T_in * stride.  w_ckc: torch's (Cin, Cout, K) weights repacked to (Cin, K, Cout). */
+int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bias, float* y, int B, int Cin, int Cout,
+                            int T_in, int stride, int pre_elu, void* stream);
+/* ConvTrUpsample1d(learnt, channel_wise) (modules/resample.py:68-119): depthwise, w (C, 1, 2*stride). */
+int ua2_convtr1d_depthwise_f32(const float* x, const float* w, float* y, int B, int C, int T_in, int stride, void* stream);
+/* ResidualVectorQuantization.encode (quantization/core_vq.py:365-376) on an already projected input x (B, D, T):
+ * for q in 0..n_q-1: code = argmin_j ||r - emb[q][j]||  (EuclideanCodebook._quantize :179-185); r -= emb[q][code].
+ * emb (n_q, K, D) = embedding_sum / clamp(cluster_usage, eps) (:142-150); emb_sqnorm (n_q, K) = row squared norms.
+ * Writes codes[b, q_off + q, t] (int64) of a (B, n_q_total, T) tensor. */
+int ua2_rvq_encode_f32(const float* x, const float* emb, const float* emb_sqnorm, int64_t* codes, int B, int D, int T, int K,
+                       int n_q, int n_q_total, int q_off, void* stream);
+/* ResidualVectorQuantization.decode (core_vq.py:378-384): out (B, D, T) = sum_q emb[q][codes[b, q_off + q, t]]. */
+int ua2_rvq_decode_f32(const int64_t* codes, const float* emb, float* out, int B, int D, int T, int K, int n_q, int n_q_total,
+                       int q_off, void* stream);
+
+/* ---- codec handle: tools/tokenizer/MimiCodec/model/models/MimiCodec.py::MimiCodec (encode :93-101, decode :103-110) ---- */
+typedef struct ua2_codec_cfg {
+  int32_t n_filters;        /* SEANet base width (64) */
+  int32_t ratios[8];        /* encoder_rates in DECODER order, e.g. {8,6,5,4}; the encoder walks them reversed */
+  int32_t n_ratios;
+  int32_t latent_dim;       /* 512 */
+  int32_t codebook_size;    /* 2048 */
+  int32_t codebook_dim;     /* 256 */
+  int32_t rvq_layers;       /* 32 = 1 semantic + 31 acoustic quantizers (SplitResidualVectorQuantizer) */
+  int32_t num_heads;        /* 8 */
+  int32_t num_layers;       /* 8 */
+  int32_t context;          /* 250: causal attention window of the Moshi-family transformer */
+  int32_t dim_feedforward;  /* 2048 */
+  int32_t resample_stride;  /* int(encoder_frame_rate / target_frame_rate) = 2 (MimiCodec.py:66-67) */
+  float max_period;         /* RoPE max period, 10000 */
+} ua2_codec_cfg;
+typedef struct ua2_codec ua2_codec;
+
+int ua2_codec_create(const ua2_codec_cfg* cfg, ua2_codec** out);
+int ua2_codec_destroy(ua2_codec* h);
+/* register a parameter / buffer by its reference state-dict key ("encoder.model.3.conv.conv.weight",
+ * "quantizer.rvq_rest.vq.layers.4._codebook.embedding_sum", ...); tensors must outlive the handle */
+int ua2_codec_load_weight(ua2_codec* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+/* repack conv weights to (Cin, K, Cout), materialise codebooks (embedding_sum / clamp(cluster_usage, eps)) */
+int ua2_codec_finalize(ua2_codec* h, void* stream);
+/* number of code frames for T samples: ceil through every strided stage */
+int64_t ua2_codec_frames(ua2_codec* h, int64_t T_samples);
+/* MimiCodec.encode: wav (B, 1, T) fp32 -> codes (B, rvq_layers, frames) int64 */
+int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* codes, void* stream);
+/* MimiCodec.decode: codes (B, rvq_layers, Tq) int64 -> wav (B, 1, Tq * resample_stride * hop_length) fp32 */
+int ua2_codec_decode(ua2_codec* h, const int64_t* codes, int B, int Tq, float* wav, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,13 @@ class LlmCfg(C.Structure):
                 ("max_seq_length", C.c_int32)]
 
 
+class CodecCfg(C.Structure):
+    _fields_ = [("n_filters", C.c_int32), ("ratios", C.c_int32 * 8), ("n_ratios", C.c_int32), ("latent_dim", C.c_int32),
+                ("codebook_size", C.c_int32), ("codebook_dim", C.c_int32), ("rvq_layers", C.c_int32), ("num_heads", C.c_int32),
+                ("num_layers", C.c_int32), ("context", C.c_int32), ("dim_feedforward", C.c_int32),
+                ("resample_stride", C.c_int32), ("max_period", C.c_float)]
+
+
 # every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -51,6 +58,19 @@ SYMBOLS = {
                                    C.c_int, C.c_int, C.c_int, _P]),
     "ua2_attn_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_attn_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ua2_conv1d_causal_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, _P]),
+    "ua2_convtr1d_causal_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_convtr1d_depthwise_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_rvq_encode_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_rvq_decode_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_codec_create": (C.c_int, [C.POINTER(CodecCfg), C.POINTER(_P)]),
+    "ua2_codec_destroy": (C.c_int, [_P]),
+    "ua2_codec_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_codec_finalize": (C.c_int, [_P, _P]),
+    "ua2_codec_frames": (C.c_int64, [_P, C.c_int64]),
+    "ua2_codec_encode": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "ua2_codec_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "ua2_sample_topk_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, _P, C.c_uint64,
                                       C.c_uint64, _P, _P]),
 }

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   const int n_keys = p.pos[m] + 1;
   const int start = split * C;
   const int qpk = p.n_head / p.n_groups;
-  if (start >= n_keys) {  // empty split: publish weight-0 statistics so consumers can merge all launched splits blindly
+  const int lo = (p.window > 0) ? max(0, n_keys - p.window) : 0;  // first visible key (Moshi context window)
+  if (start >= n_keys || start + C <= lo) {  // empty split: publish weight-0 statistics so consumers can merge blindly
     if (tid < qpk) {
       const size_t idx = (((size_t)m * p.n_head + g * qpk + tid) * p.max_splits + split) * 2;
       p.ml_part[idx] = -INFINITY;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
       s[h] += __shfl_xor_sync(0xffffffffu, s[h], 1);
       s[h] += __shfl_xor_sync(0xffffffffu, s[h], 2);
       s[h] += __shfl_xor_sync(0xffffffffu, s[h], 4);
-      if (part == 0 && j < cnt && h < qpk) sc[h][j] = s[h] * scale;
+      if (part == 0 && j < cnt && h < qpk) sc[h][j] = (start + j >= lo) ? s[h] * scale : -INFINITY;
     }
   }
   __syncthreads();

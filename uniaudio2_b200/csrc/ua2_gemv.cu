@@ -63,7 +63,7 @@ __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs
                                                   int mcount) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int K = p.K;
-  if (PRO == PRO_PLAIN || PRO == PRO_RMSNORM || PRO == PRO_GATHER) {
+  if (PRO == PRO_PLAIN || PRO == PRO_RMSNORM || PRO == PRO_GATHER || PRO == PRO_LAYERNORM) {
     float ss[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) ss[m] = 0.f;
@@ -82,6 +82,7 @@ __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (src != nullptr && k < K) v = *reinterpret_cast<const float4*>(src + k);
         if (PRO == PRO_RMSNORM) ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (PRO == PRO_LAYERNORM) ss[m] += (v.x + v.y) + (v.z + v.w);
         *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
       }
     }
@@ -108,10 +109,55 @@ __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs
         }
       }
     }
+    if (PRO == PRO_LAYERNORM) {  // nn.LayerNorm(eps=1e-5) with affine weight + bias (transformer.py create_norm_fn)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float s1 = warp_sum(ss[m]);
+        if (lane == 0) red[m][warp] = s1;
+      }
+      __syncthreads();
+      float mean[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        float tot = 0.f;
+        for (int w = 0; w < nwarps; ++w) tot += red[m][w];
+        mean[m] = tot / (float)K;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        float sq = 0.f;
+        for (int k = tid * 4; k < K; k += blockDim.x * 4) {
+          const float4 v = *reinterpret_cast<float4*>(xs + m * Kp + k);
+          const float a = v.x - mean[m], b = v.y - mean[m], c = v.z - mean[m], d = v.w - mean[m];
+          sq += a * a + b * b + c * c + d * d;
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) red[m][warp] = sq;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        float tot = 0.f;
+        for (int w = 0; w < nwarps; ++w) tot += red[m][w];
+        const float rs = rsqrtf(tot / (float)K + p.eps);
+        for (int k = tid * 4; k < K; k += blockDim.x * 4) {
+          float4 v = *reinterpret_cast<float4*>(xs + m * Kp + k);
+          const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k);
+          const float4 bb = *reinterpret_cast<const float4*>(p.norm_b + k);
+          v.x = (v.x - mean[m]) * rs * g.x + bb.x;
+          v.y = (v.y - mean[m]) * rs * g.y + bb.y;
+          v.z = (v.z - mean[m]) * rs * g.z + bb.z;
+          v.w = (v.w - mean[m]) * rs * g.w + bb.w;
+          *reinterpret_cast<float4*>(xs + m * Kp + k) = v;
+        }
+      }
+    }
   } else {  // PRO_ATTN: merge the split-softmax partials (flash-decoding combine) into y (M, n_head*hs)
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const int n_s = (m < mcount) ? (p.pos[m0 + m] + ATTN_CHUNK) / ATTN_CHUNK : 0;
+      // all launched splits are merged; empty / out-of-window ones carry (m = -inf, l = 0) and get weight 0
+      const int n_s = (m < mcount) ? (p.n_splits > 0 ? p.n_splits : (p.pos[m0 + m] + ATTN_CHUNK) / ATTN_CHUNK) : 0;
       for (int k = tid * 4; k < Kp; k += blockDim.x * 4) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n_s > 0 && k < K) {
@@ -122,12 +168,14 @@ __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs
           float den = 0.f;
           for (int s = 0; s < n_s; ++s) {
             const float w = __expf(p.ml_part[(base + s) * 2] - mx);
-            den += w * p.ml_part[(base + s) * 2 + 1];
-            const float4 o = *reinterpret_cast<const float4*>(p.o_part + (base + s) * p.hs + d);
-            v.x += w * o.x;
-            v.y += w * o.y;
-            v.z += w * o.z;
-            v.w += w * o.w;
+            if (w > 0.f) {
+              den += w * p.ml_part[(base + s) * 2 + 1];
+              const float4 o = *reinterpret_cast<const float4*>(p.o_part + (base + s) * p.hs + d);
+              v.x += w * o.x;
+              v.y += w * o.y;
+              v.z += w * o.z;
+              v.w += w * o.w;
+            }
           }
           const float inv = 1.f / den;
           v.x *= inv;
@@ -157,6 +205,35 @@ __device__ __forceinline__ void epilogue(const GemvParams& p, int lane, int mcou
       } else if (EPI == EPI_SWIGLU) {
         const float s = a / (1.0f + expf(-a));  // F.silu, lit_model.py:594
         p.Y[(size_t)m * p.ldy + nA] = s * b;
+      } else if (EPI == EPI_GELU) {  // F.gelu (exact erf form), transformer.py:553
+        const float ga = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
+        const float gb = 0.5f * b * (1.0f + erff(b * 0.70710678118654752440f));
+        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(ga, gb);
+      } else if (EPI == EPI_SCALE_RESADD) {  // x_orig + layer_scale(update), transformer.py:569, :578
+        const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
+        const float2 sc = *reinterpret_cast<const float2*>(p.scale + nA);
+        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(r.x + sc.x * a, r.y + sc.y * b);
+      } else if (EPI == EPI_QKV_IL) {
+        // in_proj rows are ordered (p h d) (transformer.py:391-393); interleaved-pair RoPE on q and k with the angle
+        // computed on the fly in fp32 (rope.py:40-58); K/V go to (B, H, T, D) buffers indexed by (bidx, pos)
+        const int hs = p.hs, HD = p.n_head * hs;
+        const int part = nA / HD, rem = nA - part * HD;
+        const int hh = rem / hs, d = rem - hh * hs;  // d even
+        const int ps = p.pos[m];
+        float oa = a, ob = b;
+        if (part < 2) {
+          const float freq = expf((float)(d >> 1) * (-logf(p.rope_max_period) * 2.0f / (float)hs));
+          const float ang = freq * (float)ps;
+          const float c = cosf(ang), sn = sinf(ang);
+          oa = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, sn));
+          ob = __fadd_rn(__fmul_rn(a, sn), __fmul_rn(b, c));
+        }
+        if (part == 0) {
+          *reinterpret_cast<float2*>(p.q_out + (size_t)m * HD + hh * hs + d) = make_float2(oa, ob);
+        } else {
+          float* dst = (part == 1 ? p.k_cache : p.v_cache) + (((size_t)p.bidx[m] * p.n_head + hh) * p.S_max + ps) * hs + d;
+          *reinterpret_cast<float2*>(dst) = make_float2(oa, ob);
+        }
       } else {  // EPI_QKV: split, half-split RoPE (lit_model.py:795-806), KV-cache append (:854-855)
         const int hs = p.hs, half = hs >> 1;
         const int hh = nA / hs, i = nA - hh * hs;
@@ -422,7 +499,7 @@ cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
   const int n_units = (EPI == EPI_SWIGLU) ? p.N : p.N / 2;
   const int m_tiles = (p.M + MT - 1) / MT;
   const size_t kMaxSmem = 220 * 1024;
-  if (g_gemv_impl == 2) {
+  if (g_gemv_impl != 1) {
     auto kern = gemv2_kernel<MT, PRO, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -481,7 +558,7 @@ void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 2; }
 
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;
-  if (g_gemv_impl == 3) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
+  if (g_gemv_impl == 3 && pro < PRO_LAYERNORM && epi < EPI_GELU) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
 #define UA2_CASE(P, E) \
   if (pro == P && epi == E) return launch_mt<P, E>(lc, p);
   UA2_CASE(PRO_PLAIN, EPI_STORE)
@@ -494,6 +571,11 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
   UA2_CASE(PRO_RMSNORM, EPI_QKV)
   UA2_CASE(PRO_GATHER, EPI_STORE)
   UA2_CASE(PRO_ATTN, EPI_RESADD)
+  UA2_CASE(PRO_LAYERNORM, EPI_QKV_IL)
+  UA2_CASE(PRO_LAYERNORM, EPI_GELU)
+  UA2_CASE(PRO_ATTN, EPI_SCALE_RESADD)
+  UA2_CASE(PRO_PLAIN, EPI_SCALE_RESADD)
+  UA2_CASE(PRO_PLAIN, EPI_QKV_IL)
 #undef UA2_CASE
   return cudaErrorInvalidValue;
 }

@@ -5,8 +5,9 @@
 namespace ua2 {
 
 // ---------------------------------------------------------------- skinny linear (GEMV family)
-enum : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_GATHER = 2, PRO_ATTN = 3 };
-enum : int { EPI_STORE = 0, EPI_RESADD = 1, EPI_QKV = 2, EPI_SWIGLU = 3 };
+enum : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_GATHER = 2, PRO_ATTN = 3, PRO_LAYERNORM = 4 };
+// EPI_GELU / EPI_SCALE_RESADD / EPI_QKV_IL serve the Moshi-family transformer layer (llm_modules/transformer.py:430-588)
+enum : int { EPI_STORE = 0, EPI_RESADD = 1, EPI_QKV = 2, EPI_SWIGLU = 3, EPI_GELU = 4, EPI_SCALE_RESADD = 5, EPI_QKV_IL = 6 };
 
 constexpr int ATTN_CHUNK = 64;  // keys per split CTA of the attention kernel
 
@@ -18,7 +19,8 @@ struct GemvParams {
   // ---- prologue (how the M x K activation tile is produced in shared memory)
   const float* X = nullptr;  // PLAIN / RMSNORM source, row stride ldx
   int ldx = 0;
-  const float* norm_w = nullptr;  // RMSNORM weight (K)
+  const float* norm_w = nullptr;  // RMSNORM / LAYERNORM weight (K)
+  const float* norm_b = nullptr;  // LAYERNORM bias (K)
   float eps = 0.f;
   const float* emb = nullptr;  // GATHER: X[m] = emb[(gidx[m*gidx_stride] + gidx_offset) * K ...]
   const int32_t* gidx = nullptr;
@@ -35,6 +37,8 @@ struct GemvParams {
   int ldy = 0;
   const float* R = nullptr;  // RESADD residual, row stride ldr (may alias Y)
   int ldr = 0;
+  const float* scale = nullptr;  // SCALE_RESADD: per-output-channel LayerScale (N)
+  float rope_max_period = 10000.f;  // QKV_IL: interleaved-pair RoPE computed on the fly (llm_modules/rope.py:11-68)
   float* q_out = nullptr;  // QKV: roped queries (M, n_head*hs)
   float* k_cache = nullptr;  // (B, G, S_max, hs)
   float* v_cache = nullptr;
@@ -56,6 +60,7 @@ struct AttnParams {
   float* o_part = nullptr;   // (M, n_head, max_splits, hs)
   float* ml_part = nullptr;  // (M, n_head, max_splits, 2)
   int M = 0, n_head = 0, n_groups = 0, hs = 0, S_max = 0, max_splits = 0;
+  int window = 0;  // > 0: only keys with pos - j < window are visible (Moshi `context`, transformer.py:404-408)
   int n_splits_launch = 0;  // grid.x (>= splits needed by the largest pos in this launch)
 };
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p);
