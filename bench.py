@@ -240,6 +240,71 @@ def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
             "prefill_s": round(t_prefill, 3)}, est
 
 
+def bench_codec(dev, batch=16, clip_s=10.0, reps=3, cpu=True):
+    """Codec real-time factor (BASELINE.json 'codec RTF'): SEANet + 8-layer transformer + 32 x 2048 x 256 residual VQ
+    (mimi_config.yaml geometry, the in-repo twin of llm_modules/{seanet,conv,resample,transformer}.py), encode + decode of
+    `batch` synthetic clips of `clip_s` seconds at 24 kHz, fp32, random weights.  RTF = audio seconds / wall seconds."""
+    from oracle import codec_oracle as CO  # weights/shapes helper + the CPU baseline leg only
+    from uniaudio2_b200.tools.tokenizer.MimiCodec.mimi_codec import MimiCodec
+
+    cfg = CO.MimiCfg()
+    sd = CO.random_mimi_state_dict(cfg, seed=7)
+    m = MimiCodec(n_filters=cfg.n_filters, encoder_rates=cfg.encoder_rates, latent_dim=cfg.latent_dim, codebook_size=cfg.codebook_size,
+                  codebook_dim=cfg.codebook_dim, rvq_layers=cfg.rvq_layers, num_heads=cfg.num_heads, num_layers=cfg.num_layers,
+                  layer_scale=cfg.layer_scale, context=cfg.context, device=dev)
+    full = m.state_dict()
+    full.update({k: v.to(dev) for k, v in sd.items()})
+    m.load_state_dict(full, strict=True)
+    T = int(clip_s * 24000)
+    g = torch.Generator().manual_seed(0)
+    wav_h = (torch.randn(batch, 1, T, generator=g) * 0.1).pin_memory()
+    wav = wav_h.to(dev)
+    for _ in range(2):
+        codes = m.encode(wav)
+        out = m.decode(codes)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    enc_ms = dec_ms = 0.0
+    for _ in range(reps):
+        e0.record()
+        codes = m.encode(wav)
+        e1.record()
+        out = m.decode(codes)
+        e2.record()
+        torch.cuda.synchronize()
+        enc_ms += e0.elapsed_time(e1)
+        dec_ms += e1.elapsed_time(e2)
+    enc_ms /= reps
+    dec_ms /= reps
+    # end to end with host buffers: H2D of the waveform, D2H of codes and of the reconstruction
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        c = m.encode(wav_h.to(dev, non_blocking=True))
+        ch = c.cpu()
+        oh = m.decode(ch.to(dev)).cpu()
+    e2e_s = (time.perf_counter() - t0) / reps
+    audio_s = batch * clip_s
+    res = {"config": f"Mimi-twin codec, batch {batch} x {clip_s:.0f} s @24 kHz, fp32", "encode_ms": round(enc_ms, 2), "decode_ms": round(dec_ms, 2),
+           "rtf_x_realtime": round(audio_s / ((enc_ms + dec_ms) * 1e-3), 1), "encode_x_realtime": round(audio_s / (enc_ms * 1e-3), 1),
+           "decode_x_realtime": round(audio_s / (dec_ms * 1e-3), 1), "e2e_x_realtime": round(audio_s / e2e_s, 1),
+           "codes_shape": list(codes.shape), "gflop_per_audio_s": 11.0}
+    if cpu:
+        orc = CO.MimiOracle(cfg, sd)
+        w1 = wav_h[:1, :, : 2 * 24000].clone()
+        with torch.inference_mode():
+            orc.decode(orc.encode(w1[..., :12000]))  # warm-up
+            t0 = time.perf_counter()
+            cc = orc.encode(w1)
+            t1 = time.perf_counter()
+            orc.decode(cc)
+            t2 = time.perf_counter()
+        res["cpu_baseline"] = {"kind": "port", "cores": torch.get_num_threads(), "sample": "1 clip x 2 s encode+decode",
+                               "rtf_x_realtime": round(2.0 / (t2 - t0), 2), "encode_s": round(t1 - t0, 3), "decode_s": round(t2 - t1, 3)}
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def state_dict_to_cpu(model):
     return {k: v.detach().to("cpu") for k, v in model.state_dict().items()}
 
@@ -253,6 +318,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--no-codec", action="store_true")
+    ap.add_argument("--v3-cps", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
     ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
     args = ap.parse_args()
@@ -310,6 +377,8 @@ def main():
 
     if args.gemv_impl:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv_impl", args.gemv_impl))
+    if args.v3_cps:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_ctas_per_sm", args.v3_cps))
     with torch.inference_mode():
         model = Model_stage3(model_args(), device=dev)
         init_weights_(model, 0)  # same weights on every replica
@@ -321,12 +390,13 @@ def main():
         tokens_d = tokens.unsqueeze(0).to(dev)
         mask_d = mask.bool().unsqueeze(0).to(dev)
         pos_d = torch.arange(PROMPT_LEN, device=dev).unsqueeze(0)
-        gather_buf = [torch.empty(N_FRAMES, 1, NQ + 1, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+        from uniaudio2_b200.distributed import gather_variable
 
         def step_device():
             frames, launches = run_utterance_device(model, tokens_d, mask_d, pos_d)
             if world > 1:
-                dist.all_gather(gather_buf, frames)  # the single collective: generated tokens of every rank
+                # the single exchange of the path: every rank's generated (9, 179) token matrix, gathered over NCCL
+                gather_variable([frames[:, 0, :].t().contiguous()], world)
             return frames, launches
 
         def barrier():
@@ -370,7 +440,7 @@ def main():
                 r, s = gen.generate_tts(task_prompt, "TTS", text_token=text, temperature=TEMPERATURE, topk=TOPK,
                                         fixed_schedule=(N_REASON, N_SEMANTIC))
                 if world > 1:
-                    dist.all_gather(gather_buf, torch.zeros_like(gather_buf[0]))
+                    gather_variable([torch.cat([r, s], dim=1)], world)
             e1.record()
             barrier()
             ems = e0.elapsed_time(e1)
@@ -384,7 +454,7 @@ def main():
                    "ms_per_step": round(ems / args.steps, 2)}
 
         hbm_peak, peak_src = load_peaks()
-        roofline = cpu_base = None
+        roofline = cpu_base = codec = None
         if rank == 0:
             roofline = time_dominant_kernel(model, hbm_peak)
             roofline["peak_source"] = peak_src
@@ -397,11 +467,13 @@ def main():
                 sd = state_dict_to_cpu(model)
                 cpu_base, _ = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
                 del sd
+            if world == 1 and not args.no_codec:
+                codec = bench_codec(dev, cpu=not args.no_cpu_baseline)
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
-                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base}))
+                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "codec": codec}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
   }
 }
 
+int g_v3_ctas_per_sm = 2;
 int g_sms = 0;
 int sm_count3() {
   if (g_sms == 0) {
@@ -416,8 +417,13 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   c.nsl = (K + 1023) / 1024;
   if (c.nsl > 8) c.nsl = 8;
   if (c.nsl < 1) c.nsl = 1;
-  c.ngrp = 8 / c.nsl;
-  if (c.nsl == 3) c.ngrp = 3;  // 9 warps
+  if (g_v3_ctas_per_sm <= 1) {
+    c.ngrp = 8 / c.nsl;
+    if (c.nsl == 3) c.ngrp = 3;  // 9 warps
+  } else {
+    // two smaller CTAs per SM: finer slabs (better static balance), dynamic CTA placement under PDL
+    c.ngrp = c.nsl >= 5 ? 1 : (c.nsl >= 3 ? 2 : (c.nsl == 2 ? 4 : 8));
+  }
   if (c.ngrp < 1) c.ngrp = 1;
   const int nwarps = c.nsl * c.ngrp;
   const int per = (K + c.nsl - 1) / c.nsl;
@@ -428,16 +434,16 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   const size_t pbytes = (size_t)2 * ROUND_UNITS * c.nsl * ROWS * MT * 4;
   const size_t stage_bytes = (size_t)nwarps * c.KCW * 4;
   // M <= 2 (decode): stay under ~half an SM's shared memory so the dependent kernel's CTA is co-resident (PDL)
-  const size_t budget = (MT <= 2 ? 112 * 1024 : kMaxSmem);
+  const size_t budget = (MT <= 2 ? 110 * 1024 : kMaxSmem);
   int stages = (int)((budget > xbytes + pbytes ? budget - xbytes - pbytes : 0) / stage_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > (g_v3_ctas_per_sm <= 1 ? 4 : 3)) stages = (g_v3_ctas_per_sm <= 1 ? 4 : 3);
   if (stages < 2) stages = 2;
   c.stages = stages;
   const size_t smem = xbytes + pbytes + stage_bytes * stages;
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
   const int n_units = (ROWS == 2) ? ((EPI == EPI_SWIGLU) ? p.N : p.N / 2) : p.N;
   const int m_tiles = (p.M + MT - 1) / MT;
-  int gy = sm_count3();
+  int gy = sm_count3() * (g_v3_ctas_per_sm <= 1 ? 1 : g_v3_ctas_per_sm);
   if (gy > n_units) gy = n_units;
   return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), smem, p, c);
 }
@@ -456,6 +462,8 @@ cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
 }
 
 }  // namespace
+
+void set_gemv3_ctas_per_sm(int v) { g_v3_ctas_per_sm = v < 1 ? 1 : (v > 3 ? 3 : v); }
 
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits) {
 #define UA2_CASE3(P, E) \
