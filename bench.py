@@ -320,6 +320,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--v3-cps", type=int, default=0)
+    ap.add_argument("--v3-stages", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
     ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
     args = ap.parse_args()
@@ -377,6 +378,8 @@ def main():
 
     if args.gemv_impl:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv_impl", args.gemv_impl))
+    if args.v3_stages:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_max_stages", args.v3_stages))
     if args.v3_cps:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_ctas_per_sm", args.v3_cps))
     with torch.inference_mode():

@@ -34,8 +34,9 @@ const char* ua2_last_error(void);
 /* library / device probe: returns the SM count of the current device (e.g. 148), <0 on error */
 int ua2_device_sm_count(void);
 const char* ua2_version(void);
-/* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (per-warp cp.async.bulk + mbarrier rings, default) |
- * 3 (one persistent CTA per SM, slab + K-split rings) */
+/* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (per-warp cp.async.bulk + mbarrier rings) |
+ * 3 (persistent CTAs, slab partition + K split across warps, bulk-copy rings; default);
+ * "gemv3_ctas_per_sm" (1..3, default 2), "gemv3_max_stages" (2..6, default 3) */
 int ua2_set_global_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32) gemv2_kernel(const GemvParams p
   }
 }
 
-int g_gemv_impl = 2;
+int g_gemv_impl = 3;
 
 int g_sm_count = 0;
 int sm_count() {
@@ -554,7 +554,7 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
 
 }  // namespace
 
-void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 2; }
+void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 3; }
 
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;

@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
 }
 
 int g_v3_ctas_per_sm = 2;
+int g_v3_max_stages = 3;
 int g_sms = 0;
 int sm_count3() {
   if (g_sms == 0) {
@@ -436,7 +437,7 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   // M <= 2 (decode): stay under ~half an SM's shared memory so the dependent kernel's CTA is co-resident (PDL)
   const size_t budget = (MT <= 2 ? 110 * 1024 : kMaxSmem);
   int stages = (int)((budget > xbytes + pbytes ? budget - xbytes - pbytes : 0) / stage_bytes);
-  if (stages > (g_v3_ctas_per_sm <= 1 ? 4 : 3)) stages = (g_v3_ctas_per_sm <= 1 ? 4 : 3);
+  if (stages > g_v3_max_stages) stages = g_v3_max_stages;
   if (stages < 2) stages = 2;
   c.stages = stages;
   const size_t smem = xbytes + pbytes + stage_bytes * stages;
@@ -464,6 +465,7 @@ cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
 }  // namespace
 
 void set_gemv3_ctas_per_sm(int v) { g_v3_ctas_per_sm = v < 1 ? 1 : (v > 3 ? 3 : v); }
+void set_gemv3_max_stages(int v) { g_v3_max_stages = v < 2 ? 2 : (v > MAX_STAGES ? MAX_STAGES : v); }
 
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits) {
 #define UA2_CASE3(P, E) \

@@ -50,6 +50,7 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
 void set_gemv_impl(int v);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);
 void set_gemv3_ctas_per_sm(int v);
+void set_gemv3_max_stages(int v);
 
 // ---------------------------------------------------------------- attention over the KV cache
 struct AttnParams {

@@ -12,6 +12,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_gemv_impl(value);
     return UA2_OK;
   }
+  if (std::string(name) == "gemv3_max_stages") {
+    set_gemv3_max_stages(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "gemv3_ctas_per_sm") {
     set_gemv3_ctas_per_sm(value);
     return UA2_OK;
