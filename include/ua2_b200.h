@@ -118,7 +118,8 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
 int ua2_llm_get_kv(ua2_llm* h, int which, int layer, float** k, float** v);
 /* name: "h_final" (B x n_embd), "text_logits" (B x text_vocab), "audio_logits" (nq x B x audio_vocab) */
 int ua2_llm_get_buffer(ua2_llm* h, const char* name, float** ptr, int64_t* numel);
-/* knobs: "graph" (0/1, default 1: replay the frame as a CUDA graph), "pdl" (0/1, default 1: programmatic dependent launch) */
+/* knobs: "graph" (0/1, default 1: replay the frame as a CUDA graph), "pdl" (0/1, default 1: programmatic dependent launch),
+ * "chain" (0/1, default 0: B = 1 frames run as persistent multi-op cooperative kernels, see csrc/ua2_chain.cu) */
 int ua2_llm_set_option(ua2_llm* h, const char* name, int value);
 /* number of kernels launched (or graph kernel nodes replayed) by the last prefill / generate_frame */
 int ua2_llm_last_launch_count(ua2_llm* h);

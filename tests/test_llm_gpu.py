@@ -28,13 +28,16 @@ def models():
     return out
 
 
-@pytest.mark.parametrize("graph", [0, 1])
+@pytest.mark.parametrize("mode", ["eager", "graph", "chain"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_frames_match_reference_golden(models, golden, case, graph):
+def test_frames_match_reference_golden(models, golden, case, mode):
+    """eager: one launch per kernel; graph: CUDA-graph replay with PDL edges; chain: persistent multi-op cooperative
+    kernels (B = 1 only - larger batches fall back to the graph path)."""
     name, cname, kind, B, S, nf, topk, temp, cfg_scale = case
     cfg, sd, m = models[cname]
     fx = golden[name]
-    m.set_option("graph", graph)
+    m.set_option("graph", 0 if mode == "eager" else 1)
+    m.set_option("chain", 1 if mode == "chain" else 0)
     r = run_case(m, kind, cfg, B, S, nf, topk, temp, cfg_scale, REASON_CARD[cname], 42, True, device="cuda",
                  explicit_noise=True)
     torch.cuda.synchronize()
@@ -112,4 +115,61 @@ def test_rng_modes_run(models):
         # second half of the frames runs with forbid_prefix = reason_card
         assert int(f[2:, :, 1:].min()) >= REASON_CARD["tiny"]
     m.rng_mode = "torch"
-    assert m.last_launch_count() > 50
+    assert m.last_launch_count() >= 19  # chain mode: 1 frame_begin + 9 persistent chains + 9 samplers
+
+
+def test_task_generators(models):
+    """The mirrored task drivers (evaluation/tts_task.py, evaluation/asr_task.py) against the oracle driven by the same
+    loops: prompt packing, phase switch, fixed synthetic schedule, greedy text decode."""
+    from types import SimpleNamespace
+
+    from uniaudio2_b200.evaluation import asr_task, tts_task
+
+    cfg, sd, m = models["tiny"]
+    args = SimpleNamespace(text_pad_token=3, semantic_pad_token=80, semantic_eos=81, semantic_bos=82, reason_eos=37, reason_bos=38,
+                           reason_pad_token=36, parallel_number=9, audio_reason_card=REASON_CARD["tiny"], audio_semantic_card=90)
+    g = torch.Generator().manual_seed(9)
+    prompt = torch.randint(0, 1000, (5,), generator=g)
+    text = torch.randint(0, 1000, (7,), generator=g)
+    # ---- TTS: 3 reason-phase + 4 semantic-phase frames, greedy
+    gen = tts_task.Generator(m, args)
+    gen.special_token_dict = {k: 1000 + i for i, k in enumerate(tts_task.SPECIAL_TOKENS)}  # ids inside the tiny vocab
+    r, s = gen.generate_tts(prompt, "TTS", text_token=text, temperature=1.0, topk=1, fixed_schedule=(3, 4))
+    assert r.shape == (8, 1) and s.shape == (8, 3) and gen.n_frames == 7
+    orc = O.Stage3Oracle(cfg, sd)
+    orc.setup_caches(1)
+    tokens, mask = gen.prepare_tts_task(prompt, text)
+    S = tokens.size(0)
+    tokens, mask = tokens.unsqueeze(0), mask.bool().unsqueeze(0)
+    orc.reset_caches()
+    orc.forward_prefix(tokens[:, :-1], mask, torch.arange(S).unsqueeze(0)[:, :-1])
+    ct, cm, frames = tokens[:, -1:], mask[:, -1:], []
+    for f in range(7):
+        smp = orc.generate_frame(ct, cm, torch.tensor([S - 1 + f]), S + f, 1.0, 1, 0 if f < 3 else REASON_CARD["tiny"])
+        frames.append(smp[0, 1:].long())
+        ct = torch.cat([smp[:, 1:], smp[:, 0:1]], -1).long().unsqueeze(1)
+        cm = torch.cat([torch.ones(1, 1, 8, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1)
+    assert torch.equal(r.cpu(), torch.stack(frames[1:2]).t())  # frames 1..2 saved minus the first; frame 3 is the switch
+    assert torch.equal(s.cpu(), torch.stack(frames[4:7]).t() - REASON_CARD["tiny"])
+    # ---- ASR-style text decode, greedy, 6 frames
+    agen = asr_task.Generator(m, args)
+    reason = torch.randint(0, 36, (4, 8), generator=g)
+    sem = torch.randint(0, 80, (6, 8), generator=g)
+    ids = agen.generate_asr(prompt, "ASR", semantic_token=sem, reason_token=reason, temperature=1.0, topk=1, max_audio_frames=6)
+    tokens, mask = agen.prepare_asr_task(prompt, reason, sem)
+    S = tokens.size(0)
+    assert S == 5 + 6 + 8
+    tokens, mask = tokens.unsqueeze(0), mask.bool().unsqueeze(0)
+    orc.reset_caches()
+    orc.forward_prefix(tokens[:, :-1], mask, torch.arange(S).unsqueeze(0)[:, :-1])
+    ct, cm, ref_ids = tokens[:, -1:], mask[:, -1:], []
+    for f in range(6):
+        smp = orc.generate_frame(ct, cm, torch.tensor([S - 1 + f]), S + f, 1.0, 1, 0)
+        t = int(smp[0, 0])
+        if t == asr_task.EOS_TEXT:
+            break
+        ref_ids.append(t)
+        ct = torch.zeros(1, 1, 9, dtype=torch.long)
+        ct[0, 0, -1] = t
+        cm = torch.cat([torch.zeros(1, 1, 8, dtype=torch.bool), torch.ones(1, 1, 1, dtype=torch.bool)], -1)
+    assert ids == ref_ids and len(ids) == 6
