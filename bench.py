@@ -193,7 +193,7 @@ def time_dominant_kernel(model, hbm_peak, reps=3):
     us = e0.elapsed_time(e1) * 1e3 / n
     bytes_per_launch = 2.0 * Fi * D * 4 + (D + Fi + D) * 4
     achieved = bytes_per_launch / (us * 1e-6) / 1e9
-    return {"bound": "hbm", "kernel": "gemv_kernel<1,PRO_RMSNORM,EPI_SWIGLU> (backbone mlp fc_1|fc_2, N=8192 K=3072)",
+    return {"bound": "hbm", "kernel": "gemv3_kernel<1,PRO_RMSNORM,EPI_SWIGLU> (backbone mlp fc_1|fc_2, N=8192 K=3072; same template serves every linear of the frame)",
             "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
             "traffic": None, "launch_us": round(us, 2), "bytes_per_launch": bytes_per_launch, "launches_timed": n}
 
@@ -321,6 +321,8 @@ def main():
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--v3-cps", type=int, default=0)
     ap.add_argument("--v3-stages", type=int, default=0)
+    ap.add_argument("--v3-kcw", type=int, default=0)
+    ap.add_argument("--v3-budget", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
     ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
     args = ap.parse_args()
@@ -378,6 +380,10 @@ def main():
 
     if args.gemv_impl:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv_impl", args.gemv_impl))
+    if args.v3_kcw:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_kcw", args.v3_kcw))
+    if args.v3_budget:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_budget_kb", args.v3_budget))
     if args.v3_stages:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_max_stages", args.v3_stages))
     if args.v3_cps:

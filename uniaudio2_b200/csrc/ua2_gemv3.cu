@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
 
 int g_v3_ctas_per_sm = 2;
 int g_v3_max_stages = 3;
+int g_v3_kcw = 1024;
+int g_v3_budget_kb = 110;
 int g_sms = 0;
 int sm_count3() {
   if (g_sms == 0) {
@@ -208,13 +210,13 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   const int nwarps = c.nsl * c.ngrp;
   const int per = (K + c.nsl - 1) / c.nsl;
   c.SL = ((per + 127) / 128) * 128;
-  c.KCW = c.SL < 1024 ? c.SL : 1024;
+  c.KCW = c.SL < g_v3_kcw ? c.SL : g_v3_kcw;
   c.n_splits = n_splits;
   const size_t xbytes = (size_t)MT * Kp * 4;
   const size_t pbytes = (size_t)2 * ROUND_UNITS * c.nsl * ROWS * MT * 4;
   const size_t stage_bytes = (size_t)nwarps * c.KCW * 4;
   // M <= 2 (decode): stay under ~half an SM's shared memory so the dependent kernel's CTA is co-resident (PDL)
-  const size_t budget = (MT <= 2 ? 110 * 1024 : kMaxSmem);
+  const size_t budget = (MT <= 2 ? (size_t)g_v3_budget_kb * 1024 : kMaxSmem);
   int stages = (int)((budget > xbytes + pbytes ? budget - xbytes - pbytes : 0) / stage_bytes);
   if (stages > g_v3_max_stages) stages = g_v3_max_stages;
   if (stages < 2) stages = 2;
@@ -244,6 +246,8 @@ cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
 }  // namespace
 
 void set_gemv3_ctas_per_sm(int v) { g_v3_ctas_per_sm = v < 1 ? 1 : (v > 3 ? 3 : v); }
+void set_gemv3_kcw(int v) { g_v3_kcw = (v >= 128 && v <= 1024 && v % 128 == 0) ? v : 1024; }
+void set_gemv3_budget_kb(int v) { g_v3_budget_kb = (v >= 24 && v <= 220) ? v : 110; }
 void set_gemv3_max_stages(int v) { g_v3_max_stages = v < 2 ? 2 : (v > MAX_STAGES ? MAX_STAGES : v); }
 
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits) {

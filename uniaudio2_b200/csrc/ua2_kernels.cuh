@@ -51,6 +51,8 @@ void set_gemv_impl(int v);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);
 void set_gemv3_ctas_per_sm(int v);
 void set_gemv3_max_stages(int v);
+void set_gemv3_kcw(int v);
+void set_gemv3_budget_kb(int v);
 
 // ---------------------------------------------------------------- attention over the KV cache
 struct AttnParams {

@@ -12,6 +12,14 @@ int ua2_set_global_option(const char* name, int value) {
     set_gemv_impl(value);
     return UA2_OK;
   }
+  if (std::string(name) == "gemv3_kcw") {
+    set_gemv3_kcw(value);
+    return UA2_OK;
+  }
+  if (std::string(name) == "gemv3_budget_kb") {
+    set_gemv3_budget_kb(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "gemv3_max_stages") {
     set_gemv3_max_stages(value);
     return UA2_OK;
