@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--v3-cps", type=int, default=0)
     ap.add_argument("--v3-stages", type=int, default=0)
     ap.add_argument("--v3-kcw", type=int, default=0)
+    ap.add_argument("--v3-balance", type=int, default=-1)
     ap.add_argument("--v3-budget", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
     ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
@@ -380,6 +381,8 @@ def main():
 
     if args.gemv_impl:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv_impl", args.gemv_impl))
+    if args.v3_balance >= 0:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_balance_grid", args.v3_balance))
     if args.v3_kcw:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_kcw", args.v3_kcw))
     if args.v3_budget:

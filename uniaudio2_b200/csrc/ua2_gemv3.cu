@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
 int g_v3_ctas_per_sm = 2;
 int g_v3_max_stages = 3;
 int g_v3_kcw = 1024;
+int g_v3_balance_grid = 1;
 int g_v3_budget_kb = 110;
 int g_sms = 0;
 int sm_count3() {
@@ -225,7 +226,27 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
   const int n_units = (ROWS == 2) ? ((EPI == EPI_SWIGLU) ? p.N : p.N / 2) : p.N;
   const int m_tiles = (p.M + MT - 1) / MT;
-  int gy = sm_count3() * (g_v3_ctas_per_sm <= 1 ? 1 : g_v3_ctas_per_sm);
+  // Grid size: every (CTA, group) streams ceil(units / (G * ngrp)) units, so pick the G in [SMs, SMs * ctas_per_sm] that
+  // wastes the least on the remainder (e.g. 2560 QKV pairs, 2 groups: G = 256 -> exactly 5 per group instead of 4.3 -> 5
+  // on 296 CTAs).  All CTAs are co-resident either way; the kernel is bound by per-warp stream latency, not by SM count.
+  const int g_max = sm_count3() * (g_v3_ctas_per_sm <= 1 ? 1 : g_v3_ctas_per_sm);
+  int gy = g_max;
+  if (g_v3_balance_grid && n_units > g_max * c.ngrp && n_units < 32 * g_max * c.ngrp) {
+    auto eff_of = [&](int G) {
+      const int slots = G * c.ngrp;
+      const int per = (n_units + slots - 1) / slots;
+      const int slab_max = (n_units + G - 1) / G;  // CTA slabs are floor-partitioned: some hold ceil(units / G)
+      const int per2 = (slab_max + c.ngrp - 1) / c.ngrp;
+      return (double)n_units / ((double)slots * (per2 > per ? per2 : per));
+    };
+    double best = 0.0;
+    for (int G = sm_count3(); G <= g_max; ++G) best = eff_of(G) > best ? eff_of(G) : best;
+    for (int G = g_max; G >= sm_count3(); --G)
+      if (eff_of(G) >= best - 0.03) {  // largest grid within 3 % of the best balance (more warps in flight)
+        gy = G;
+        break;
+      }
+  }
   if (gy > n_units) gy = n_units;
   return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), smem, p, c);
 }
@@ -246,6 +267,7 @@ cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
 }  // namespace
 
 void set_gemv3_ctas_per_sm(int v) { g_v3_ctas_per_sm = v < 1 ? 1 : (v > 3 ? 3 : v); }
+void set_gemv3_balance_grid(int v) { g_v3_balance_grid = v ? 1 : 0; }
 void set_gemv3_kcw(int v) { g_v3_kcw = (v >= 128 && v <= 1024 && v % 128 == 0) ? v : 1024; }
 void set_gemv3_budget_kb(int v) { g_v3_budget_kb = (v >= 24 && v <= 220) ? v : 110; }
 void set_gemv3_max_stages(int v) { g_v3_max_stages = v < 2 ? 2 : (v > MAX_STAGES ? MAX_STAGES : v); }

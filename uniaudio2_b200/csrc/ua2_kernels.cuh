@@ -52,6 +52,7 @@ cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams
 void set_gemv3_ctas_per_sm(int v);
 void set_gemv3_max_stages(int v);
 void set_gemv3_kcw(int v);
+void set_gemv3_balance_grid(int v);
 void set_gemv3_budget_kb(int v);
 
 // ---------------------------------------------------------------- attention over the KV cache

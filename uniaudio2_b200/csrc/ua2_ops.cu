@@ -12,6 +12,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_gemv_impl(value);
     return UA2_OK;
   }
+  if (std::string(name) == "gemv3_balance_grid") {
+    set_gemv3_balance_grid(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "gemv3_kcw") {
     set_gemv3_kcw(value);
     return UA2_OK;
