@@ -174,7 +174,7 @@ def test_codec_full_config_vs_oracle():
     m = _build(cfg, sd)
     orc = CO.MimiOracle(cfg, sd)
     g = torch.Generator().manual_seed(5)
-    wav = torch.randn(2, 1, 24000 + 311, generator=g) * 0.2
+    wav = torch.randn(2, 1, 3 * 24000 + 311, generator=g) * 0.2  # 2 x 79 frames @25 Hz = 158 rows -> tiled GEMM path
     with torch.no_grad():
         ref_codes = orc.encode(wav)
         ref_wav = orc.decode(ref_codes)

@@ -41,7 +41,7 @@ TOL = 2e-5
 
 @pytest.mark.parametrize("M,N,K", [(1, 3072, 3072), (1, 5120, 3072), (1, 2048, 8192), (2, 512, 384), (3, 130, 256),
                                    (4, 1024, 2048), (5, 258, 640), (8, 384, 1280), (11, 96, 132), (1, 12300, 2048),
-                                   (37, 768, 512)])
+                                   (37, 768, 512), (200, 1536, 512), (333, 130, 256), (128, 3072, 1024)])
 @pytest.mark.parametrize("norm,res", [(False, False), (True, False), (False, True), (True, True)])
 def test_linear(L, M, N, K, norm, res):
     g = torch.Generator().manual_seed(M * 1000 + N + K)
@@ -75,7 +75,7 @@ def test_linear_inplace_residual(L):
     assert _rel(y.cpu(), ref) < TOL
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 8192, 3072), (1, 8192, 2048), (2, 384, 256), (4, 513, 384), (9, 640, 768)])
+@pytest.mark.parametrize("M,N,K", [(1, 8192, 3072), (1, 8192, 2048), (2, 384, 256), (4, 513, 384), (9, 640, 768), (150, 640, 768), (257, 129, 512)])
 @pytest.mark.parametrize("norm", [False, True])
 def test_swiglu(L, M, N, K, norm):
     g = torch.Generator().manual_seed(N + K)
@@ -94,10 +94,10 @@ def test_swiglu(L, M, N, K, norm):
 
 
 @pytest.mark.parametrize("hs,n_head,G,D,B,T", [(128, 24, 8, 3072, 1, 1), (64, 32, 8, 2048, 2, 1), (64, 6, 2, 384, 2, 5),
-                                               (128, 6, 2, 768, 3, 7), (32, 8, 2, 256, 1, 9)])
+                                               (128, 6, 2, 768, 3, 7), (32, 8, 2, 256, 1, 9), (64, 8, 2, 512, 4, 40)])
 def test_qkv_rope_and_attention(L, hs, n_head, G, D, B, T):
     """Kernel A (RMSNorm->QKV->RoPE->cache append) then kernel B (attention) vs lit_model.py:424-532 restated."""
-    S_max, past = 160, 131  # > ATTN_CHUNK so the split path is exercised
+    S_max, past = max(160, 131 + T + 8), 131  # > ATTN_CHUNK so the split path is exercised
     g = torch.Generator().manual_seed(hs + n_head + D)
     cfg = O.GPTCfg(n_layer=1, n_embd=D, n_head=n_head, n_query_groups=G, intermediate_size=4 * D, head_size=hs)
     x = torch.randn(B, T, D, generator=g)

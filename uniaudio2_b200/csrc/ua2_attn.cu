@@ -191,7 +191,7 @@ __global__ void attn_combine_kernel(const AttnParams p, float* y) {
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
-  const int n_s = (p.pos[m] + ATTN_CHUNK) / ATTN_CHUNK;
+  const int n_s = p.n_splits_launch > 0 ? p.n_splits_launch : (p.pos[m] + ATTN_CHUNK) / ATTN_CHUNK;  // empties weigh 0
   const int D = p.n_head * p.hs;
   for (int k = threadIdx.x; k < D; k += blockDim.x) {
     const int hh = k / p.hs, d = k - hh * p.hs;
@@ -201,8 +201,10 @@ __global__ void attn_combine_kernel(const AttnParams p, float* y) {
     float den = 0.f, num = 0.f;
     for (int s = 0; s < n_s; ++s) {
       const float w = __expf(p.ml_part[(base + s) * 2] - mx);
-      den += w * p.ml_part[(base + s) * 2 + 1];
-      num += w * p.o_part[(base + s) * p.hs + d];
+      if (w > 0.f) {
+        den += w * p.ml_part[(base + s) * 2 + 1];
+        num += w * p.o_part[(base + s) * p.hs + d];
+      }
     }
     y[(size_t)m * D + k] = num / den;
   }

@@ -184,7 +184,7 @@ int conv(ua2_codec* h, const std::string& key, const float* x, const float* res,
 
 // ProjectedTransformer(conv_layout=True) over x (B, C, T) in place; tmp buffers carved from the workspace by the caller
 int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbuf, float* kbuf, float* vbuf, float* hbuf,
-                    float* o_part, float* ml_part, int B, int T, void* st) {
+                    float* o_part, float* ml_part, float* sg_ws, size_t sg_ws_floats, int B, int T, void* st) {
   const int C = h->cfg.latent_dim, H = h->cfg.num_heads, hs = C / H, F = h->cfg.dim_feedforward;
   const int M = B * T;
   LaunchCtx lc;
@@ -203,6 +203,8 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.N = 3 * C;
       p.K = C;
       p.M = M;
+      p.ws = sg_ws;
+      p.ws_floats = sg_ws_floats;
       p.X = xt;
       p.ldx = C;
       p.norm_w = w.n1w;
@@ -244,6 +246,8 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.N = C;
       p.K = C;
       p.M = Mc;
+      p.ws = sg_ws;
+      p.ws_floats = sg_ws_floats;
       p.o_part = o_part;
       p.ml_part = ml_part;
       p.max_splits = max_splits;
@@ -264,6 +268,8 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.N = F;
       p.K = C;
       p.M = M;
+      p.ws = sg_ws;
+      p.ws_floats = sg_ws_floats;
       p.X = xt;
       p.ldx = C;
       p.norm_w = w.n2w;
@@ -279,6 +285,8 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.N = C;
       p.K = F;
       p.M = M;
+      p.ws = sg_ws;
+      p.ws_floats = sg_ws_floats;
       p.X = hbuf;
       p.ldx = F;
       p.Y = xt;
@@ -298,7 +306,7 @@ size_t transformer_ws_floats(const ua2_codec_cfg& c, int B, int T) {
   const size_t Mc = std::min<size_t>(M, 32768);
   const size_t splits = (T + ATTN_CHUNK - 1) / ATTN_CHUNK;
   // xt, q, k, v (M*C each), hbuf (M*F), o_part (Mc*C*splits), ml_part (Mc*H*splits*2)
-  return 4 * M * C + M * c.dim_feedforward + Mc * C * splits + Mc * c.num_heads * splits * 2 + 1024;
+  return 4 * M * C + M * c.dim_feedforward + Mc * C * splits + Mc * c.num_heads * splits * 2 + (2 * M + Mc * C) + 1024;
 }
 
 }  // namespace
@@ -555,7 +563,8 @@ int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* code
     float *xt = tw, *q = xt + MC, *k = q + MC, *vv = k + MC, *hb = vv + MC, *op = hb + MF;
     const size_t Mc = std::min<size_t>((size_t)B * Tz, 32768), splits = (Tz + ATTN_CHUNK - 1) / ATTN_CHUNK;
     float* ml = op + Mc * D * splits;
-    RUN(run_transformer(h, 0, b, xt, q, k, vv, hb, op, ml, B, Tz, st));
+    float* sg = ml + Mc * c.num_heads * splits * 2;
+    RUN(run_transformer(h, 0, b, xt, q, k, vv, hb, op, ml, sg, 2 * (size_t)B * Tz + Mc * D, B, Tz, st));
   }
   // ConvDownsample1d: kernel 2*stride, replicate padding, no bias (modules/resample.py:14-65)
   const ConvW* dw = find_conv(h, "downsample");
@@ -601,7 +610,8 @@ int ua2_codec_decode(ua2_codec* h, const int64_t* codes, int B, int Tq, float* w
     float *xt = tw, *q = xt + MC, *k = q + MC, *vv = k + MC, *hb = vv + MC, *op = hb + MF;
     const size_t Mc = std::min<size_t>((size_t)B * Tz, 32768), splits = (Tz + ATTN_CHUNK - 1) / ATTN_CHUNK;
     float* ml = op + Mc * D * splits;
-    RUN(run_transformer(h, 1, a, xt, q, k, vv, hb, op, ml, B, Tz, st));
+    float* sg = ml + Mc * c.num_heads * splits * 2;
+    RUN(run_transformer(h, 1, a, xt, q, k, vv, hb, op, ml, sg, 2 * (size_t)B * Tz + Mc * D, B, Tz, st));
   }
   RUN(conv(h, "decoder.model.0.conv.conv", a, nullptr, b, B, Tz, 1, 0, st));
   int idx = 1;

@@ -11,35 +11,16 @@
 //     (plain copy | RMSNorm | embedding gather | split-softmax attention combine) and read conflict-free;
 //   * a fused epilogue consumes the two row sums (store | residual add | RoPE + KV-cache append | SwiGLU).
 // Algorithmic bytes per launch = 4*N*K (weights) (+ 4*M*(K+N) activations, negligible).
+#include "ua2_gemv_dev.cuh"
 #include "ua2_kernels.cuh"
 
 namespace ua2 {
 
 namespace {
 
-constexpr int U = 8;  // k-iterations (of 128 floats) per load batch
+using namespace v1dev;
 
-template <int EPI>
-__device__ __forceinline__ void unit_rows(const GemvParams& p, int u, const float*& rowA, const float*& rowB, int& nA,
-                                          int& nB) {
-  if (EPI == EPI_SWIGLU) {
-    nA = nB = u;
-    rowA = p.W + (size_t)u * p.K;
-    rowB = p.W2 + (size_t)u * p.K;
-  } else if (EPI == EPI_QKV) {
-    const int half = p.hs >> 1;
-    const int hh = u / half, i = u - hh * half;
-    nA = hh * p.hs + i;
-    nB = nA + half;
-    rowA = p.W + (size_t)nA * p.K;
-    rowB = p.W + (size_t)nB * p.K;
-  } else {
-    nA = 2 * u;
-    nB = nA + 1;
-    rowA = p.W + (size_t)nA * p.K;
-    rowB = p.W + (size_t)nB * p.K;
-  }
-}
+constexpr int U = 8;  // k-iterations (of 128 floats) per load batch
 
 __device__ __forceinline__ void load_batch(const float* rowA, const float* rowB, int it0, int lane, int K,
                                            float4 (&wa)[U], float4 (&wb)[U]) {
@@ -189,78 +170,6 @@ __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs
   }
   __syncthreads();
 
-}
-
-// ---- fused epilogue: lane m (< mcount) holds the two row sums (a, b) of output rows (nA, nB) for activation row m0+m
-template <int EPI>
-__device__ __forceinline__ void epilogue(const GemvParams& p, int lane, int mcount, int m0, float a, float b, int nA,
-                                         int nB) {
-  if (lane < mcount) {
-      const int m = m0 + lane;
-      if (EPI == EPI_STORE) {
-        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a, b);
-      } else if (EPI == EPI_RESADD) {
-        const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
-        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(a + r.x, b + r.y);
-      } else if (EPI == EPI_SWIGLU) {
-        const float s = a / (1.0f + expf(-a));  // F.silu, lit_model.py:594
-        p.Y[(size_t)m * p.ldy + nA] = s * b;
-      } else if (EPI == EPI_GELU) {  // F.gelu (exact erf form), transformer.py:553
-        const float ga = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
-        const float gb = 0.5f * b * (1.0f + erff(b * 0.70710678118654752440f));
-        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(ga, gb);
-      } else if (EPI == EPI_SCALE_RESADD) {  // x_orig + layer_scale(update), transformer.py:569, :578
-        const float2 r = *reinterpret_cast<const float2*>(p.R + (size_t)m * p.ldr + nA);
-        const float2 sc = *reinterpret_cast<const float2*>(p.scale + nA);
-        *reinterpret_cast<float2*>(p.Y + (size_t)m * p.ldy + nA) = make_float2(r.x + sc.x * a, r.y + sc.y * b);
-      } else if (EPI == EPI_QKV_IL) {
-        // in_proj rows are ordered (p h d) (transformer.py:391-393); interleaved-pair RoPE on q and k with the angle
-        // computed on the fly in fp32 (rope.py:40-58); K/V go to (B, H, T, D) buffers indexed by (bidx, pos)
-        const int hs = p.hs, HD = p.n_head * hs;
-        const int part = nA / HD, rem = nA - part * HD;
-        const int hh = rem / hs, d = rem - hh * hs;  // d even
-        const int ps = p.pos[m];
-        float oa = a, ob = b;
-        if (part < 2) {
-          const float freq = expf((float)(d >> 1) * (-logf(p.rope_max_period) * 2.0f / (float)hs));
-          const float ang = freq * (float)ps;
-          const float c = cosf(ang), sn = sinf(ang);
-          oa = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, sn));
-          ob = __fadd_rn(__fmul_rn(a, sn), __fmul_rn(b, c));
-        }
-        if (part == 0) {
-          *reinterpret_cast<float2*>(p.q_out + (size_t)m * HD + hh * hs + d) = make_float2(oa, ob);
-        } else {
-          float* dst = (part == 1 ? p.k_cache : p.v_cache) + (((size_t)p.bidx[m] * p.n_head + hh) * p.S_max + ps) * hs + d;
-          *reinterpret_cast<float2*>(dst) = make_float2(oa, ob);
-        }
-      } else {  // EPI_QKV: split, half-split RoPE (lit_model.py:795-806), KV-cache append (:854-855)
-        const int hs = p.hs, half = hs >> 1;
-        const int hh = nA / hs, i = nA - hh * hs;
-        const int ps = p.pos[m];
-        if (hh < p.n_head + p.n_groups) {
-          const float c0 = p.cos[(size_t)ps * hs + i], s0 = p.sin[(size_t)ps * hs + i];
-          const float c1 = p.cos[(size_t)ps * hs + i + half], s1 = p.sin[(size_t)ps * hs + i + half];
-          const float ra = __fadd_rn(__fmul_rn(a, c0), __fmul_rn(-b, s0));
-          const float rb = __fadd_rn(__fmul_rn(b, c1), __fmul_rn(a, s1));
-          if (hh < p.n_head) {
-            float* q = p.q_out + (size_t)m * (p.n_head * hs) + hh * hs + i;
-            q[0] = ra;
-            q[half] = rb;
-          } else {
-            const int g = hh - p.n_head;
-            float* kc = p.k_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
-            kc[0] = ra;
-            kc[half] = rb;
-          }
-        } else {
-          const int g = hh - p.n_head - p.n_groups;
-          float* vc = p.v_cache + (((size_t)p.bidx[m] * p.n_groups + g) * p.S_max + ps) * hs + i;
-          vc[0] = a;
-          vc[half] = b;
-        }
-      }
-    }
 }
 
 template <int MT, int PRO, int EPI>
@@ -480,6 +389,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32) gemv2_kernel(const GemvParams p
 }
 
 int g_gemv_impl = 3;
+int g_sgemm_min_rows = 128;
 
 int g_sm_count = 0;
 int sm_count() {
@@ -554,10 +464,46 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
 
 }  // namespace
 
+void set_sgemm_min_rows(int v) { g_sgemm_min_rows = v < 1 ? 1 : v; }
 void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 3; }
 
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;
+  // many rows: 128 x 128 register-tiled fp32 GEMM (each weight element reused 128x) instead of re-streaming W per 8 rows
+  if (p.M >= g_sgemm_min_rows && p.ws != nullptr) {
+    GemvParams q = p;
+    int pro2 = pro;
+    size_t need = 2 * (size_t)p.M;
+    bool ok = true;
+    if (pro == PRO_ATTN) {
+      need += (size_t)p.M * p.K;
+      if (p.ws_floats >= need) {
+        AttnParams a;
+        a.o_part = const_cast<float*>(p.o_part);
+        a.ml_part = const_cast<float*>(p.ml_part);
+        a.pos = p.pos;
+        a.M = p.M;
+        a.n_head = p.n_head;
+        a.hs = p.hs;
+        a.max_splits = p.max_splits;
+        a.n_splits_launch = p.n_splits;
+        cudaError_t e = launch_attn_combine(lc, a, p.ws + 2 * (size_t)p.M);
+        if (e != cudaSuccess) return e;
+        q.X = p.ws + 2 * (size_t)p.M;
+        q.ldx = p.K;
+        pro2 = PRO_PLAIN;
+      } else {
+        ok = false;
+      }
+    } else if (p.ws_floats < need) {
+      ok = false;
+    }
+    if (ok) {
+      cudaError_t e = launch_sgemm_linear(lc, pro2, epi, q, p.ws);
+      if (e != cudaErrorNotSupported) return e;
+      if (pro == PRO_ATTN) return cudaErrorInvalidValue;  // combine already consumed; should not happen (instances exist)
+    }
+  }
   if (g_gemv_impl == 3 && pro < PRO_LAYERNORM && epi < EPI_GELU) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
 #define UA2_CASE(P, E) \
   if (pro == P && epi == E) return launch_mt<P, E>(lc, p);

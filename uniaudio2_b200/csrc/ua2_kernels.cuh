@@ -38,6 +38,8 @@ struct GemvParams {
   const float* R = nullptr;  // RESADD residual, row stride ldr (may alias Y)
   int ldr = 0;
   const float* scale = nullptr;  // SCALE_RESADD: per-output-channel LayerScale (N)
+  float* ws = nullptr;           // optional scratch for the tiled path (row statistics 2*M floats, attention combine M*K floats)
+  size_t ws_floats = 0;
   float rope_max_period = 10000.f;  // QKV_IL: interleaved-pair RoPE computed on the fly (llm_modules/rope.py:11-68)
   float* q_out = nullptr;  // QKV: roped queries (M, n_head*hs)
   float* k_cache = nullptr;  // (B, G, S_max, hs)
@@ -47,7 +49,9 @@ struct GemvParams {
   int S_max = 0;
 };
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
-void set_gemv_impl(int v);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
+cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, float* stats_ws);
+void set_gemv_impl(int v);
+void set_sgemm_min_rows(int v);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);
 void set_gemv3_ctas_per_sm(int v);
 void set_gemv3_max_stages(int v);

@@ -51,8 +51,9 @@ struct ua2_llm {
   int32_t *d_pos = nullptr, *d_bidx = nullptr, *d_pos_local = nullptr;
   FrameScalars* d_fs = nullptr;
   float *x = nullptr, *audio_in = nullptr, *text_emb = nullptr, *hb = nullptr, *h_final = nullptr, *qbuf = nullptr,
-        *hmlp = nullptr, *o_part = nullptr, *ml_part = nullptr, *dec_x = nullptr, *text_logits = nullptr,
+        *hmlp = nullptr, *sg_ws = nullptr, *o_part = nullptr, *ml_part = nullptr, *dec_x = nullptr, *text_logits = nullptr,
         *audio_logits = nullptr;
+  size_t sg_ws_floats = 0;
   int64_t h_final_numel = 0, text_logits_numel = 0, audio_logits_numel = 0;
   std::vector<void*> owned;
   // persistent chain path (B = 1): op lists in device memory, grid-barrier counters
@@ -109,6 +110,8 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.N = (c.n_head + 2 * c.n_query_groups) * hs;
     p.K = D;
     p.M = M;
+    p.ws = h->sg_ws;
+    p.ws_floats = h->sg_ws_floats;
     p.X = x;
     p.ldx = D;
     p.norm_w = w.norm1;
@@ -150,6 +153,8 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.N = D;
     p.K = QD;
     p.M = M;
+    p.ws = h->sg_ws;
+    p.ws_floats = h->sg_ws_floats;
     p.o_part = h->o_part;
     p.ml_part = h->ml_part;
     p.max_splits = h->max_splits;
@@ -170,6 +175,8 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.N = c.intermediate_size;
     p.K = D;
     p.M = M;
+    p.ws = h->sg_ws;
+    p.ws_floats = h->sg_ws_floats;
     p.X = x;
     p.ldx = D;
     p.norm_w = w.norm2;
@@ -184,6 +191,8 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.N = D;
     p.K = c.intermediate_size;
     p.M = M;
+    p.ws = h->sg_ws;
+    p.ws_floats = h->sg_ws_floats;
     p.X = h->hmlp;
     p.ldx = c.intermediate_size;
     p.Y = x;
@@ -755,6 +764,8 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   if ((rc = alloc(h, (void**)&h->h_final, (size_t)Mc * D * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->qbuf, (size_t)Mc * max_qd * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->hmlp, (size_t)Mc * max_inter * 4))) return rc;
+  h->sg_ws_floats = (size_t)Mc * (2 + max_qd);  // tiled-GEMM scratch: row statistics + attention combine
+  if ((rc = alloc(h, (void**)&h->sg_ws, h->sg_ws_floats * 4))) return rc;
   const size_t chain_splits = (h->cfg.max_seq_length + CHAIN_ATTN_CHUNK - 1) / CHAIN_ATTN_CHUNK;
   const size_t opart_floats = std::max((size_t)Mc * max_heads_hs * h->max_splits, (size_t)max_heads_hs * chain_splits);
   if ((rc = alloc(h, (void**)&h->o_part, opart_floats * 4))) return rc;

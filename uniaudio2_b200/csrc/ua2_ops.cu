@@ -4,6 +4,17 @@
 
 using namespace ua2;
 
+// scratch for the tiled (many-row) path of the stand-alone operators: row statistics + attention combine
+static float* g_ops_ws = nullptr;
+static const size_t kOpsWsFloats = (size_t)16 << 20;
+static int ops_ws(GemvParams& p) {
+  if (p.M < 128) return UA2_OK;
+  if (!g_ops_ws) UA2_CHECK_CUDA(cudaMalloc(&g_ops_ws, kOpsWsFloats * sizeof(float)));
+  p.ws = g_ops_ws;
+  p.ws_floats = kOpsWsFloats;
+  return UA2_OK;
+}
+
 extern "C" {
 
 int ua2_set_global_option(const char* name, int value) {
@@ -14,6 +25,10 @@ int ua2_set_global_option(const char* name, int value) {
   }
   if (std::string(name) == "gemv3_balance_grid") {
     set_gemv3_balance_grid(value);
+    return UA2_OK;
+  }
+  if (std::string(name) == "sgemm_min_rows") {
+    set_sgemm_min_rows(value);
     return UA2_OK;
   }
   if (std::string(name) == "gemv3_kcw") {
@@ -54,6 +69,7 @@ int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float ep
   p.ldy = N;
   p.R = residual;
   p.ldr = N;
+  if (int rc = ops_ws(p)) return rc;
   UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, residual ? EPI_RESADD : EPI_STORE, p));
   return UA2_OK;
 }
@@ -76,6 +92,7 @@ int ua2_swiglu_f32(const float* x, const float* W1, const float* W2, const float
   p.eps = eps;
   p.Y = y;
   p.ldy = N;
+  if (int rc = ops_ws(p)) return rc;
   UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, EPI_SWIGLU, p));
   return UA2_OK;
 }
@@ -108,6 +125,7 @@ int ua2_qkv_rope_f32(const float* x, const float* Wqkv, const float* norm_w, flo
   p.cos = cos;
   p.sin = sin;
   p.S_max = S_max;
+  if (int rc = ops_ws(p)) return rc;
   UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, EPI_QKV, p));
   return UA2_OK;
 }
