@@ -167,10 +167,20 @@ int ua2_sample_topk_f32(const float* logits, int R, int V, float temperature, in
 int ua2_conv1d_causal_f32(const float* x, const float* w_ckc, const float* bias, const float* residual, float* y, int B,
                           int Cin, int Cout, int T_in, int K, int stride, int dilation, int pre_elu, int replicate_pad,
                           void* stream);
+/* Same operator as ua2_conv1d_causal_f32 computed as an implicit GEMM (128 x 128 register tiles); weights stay in the
+ * reference's (Cout, Cin, K) layout.  This is what the codec handle calls. */
+int ua2_conv1d_causal_gemm_f32(const float* x, const float* w_torch, const float* bias, const float* residual, float* y, int B,
+                               int Cin, int Cout, int T_in, int K, int stride, int dilation, int pre_elu, int replicate_pad,
+                               void* stream);
 /* StreamingConvTranspose1d.forward, causal, trim_right_ratio = 1 (modules/conv.py:306-329): kernel = 2*stride,
  * T_out = T_in * stride.  w_ckc: torch's (Cin, Cout, K) weights repacked to (Cin, K, Cout). */
 int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bias, float* y, int B, int Cin, int Cout,
                             int T_in, int stride, int pre_elu, void* stream);
+/* Transposed conv as `stride` phase GEMMs (ua2_sgemm.cu).  w_phase (stride, Cout, Cin, 2) comes from
+ * ua2_convtr1d_repack_phase_f32(torch weight (Cin, Cout, 2*stride)). */
+int ua2_convtr1d_repack_phase_f32(const float* w_torch, float* w_phase, int Cin, int Cout, int stride, void* stream);
+int ua2_convtr1d_causal_gemm_f32(const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin, int Cout,
+                                 int T_in, int stride, int pre_elu, void* stream);
 /* ConvTrUpsample1d(learnt, channel_wise) (modules/resample.py:68-119): depthwise, w (C, 1, 2*stride). */
 int ua2_convtr1d_depthwise_f32(const float* x, const float* w, float* y, int B, int C, int T_in, int stride, void* stream);
 /* ResidualVectorQuantization.encode (quantization/core_vq.py:365-376) on an already projected input x (B, D, T):

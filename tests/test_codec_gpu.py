@@ -69,6 +69,12 @@ def test_conv1d_causal(L, B, Cin, Cout, T, K, stride, dil, elu, res, rep):
     torch.cuda.synchronize()
     assert y.shape == ref.shape
     assert float((y.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    # implicit-GEMM variant (what the codec handle runs), weights in the reference layout
+    y2 = torch.full_like(y, float("nan"))
+    wt = w.contiguous().cuda()
+    _chk(L.ua2_conv1d_causal_gemm_f32(_p(xd), _p(wt), _p(bd), _p(rd), _p(y2), B, Cin, Cout, T, K, stride, dil, elu, rep, None))
+    torch.cuda.synchronize()
+    assert float((y2.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("B,Cin,Cout,T,stride", [(1, 1024, 512, 20, 8), (2, 512, 256, 77, 6), (1, 256, 128, 300, 5),
@@ -85,6 +91,14 @@ def test_convtr1d_causal(L, B, Cin, Cout, T, stride):
     torch.cuda.synchronize()
     assert y.shape == ref.shape
     assert float((y.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    # phase-GEMM variant (what the codec handle runs)
+    wt = w.contiguous().cuda()
+    wp = torch.empty(stride * Cout * Cin * 2, device="cuda")
+    _chk(L.ua2_convtr1d_repack_phase_f32(_p(wt), _p(wp), Cin, Cout, stride, None))
+    y2 = torch.full_like(y, float("nan"))
+    _chk(L.ua2_convtr1d_causal_gemm_f32(_p(xd), _p(wp), _p(bd), _p(y2), B, Cin, Cout, T, stride, 1, None))
+    torch.cuda.synchronize()
+    assert float((y2.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
 
 
 def test_convtr1d_depthwise(L):

@@ -60,7 +60,11 @@ SYMBOLS = {
     "ua2_attn_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ua2_conv1d_causal_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _P]),
+    "ua2_conv1d_causal_gemm_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, _P]),
     "ua2_convtr1d_causal_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_convtr1d_repack_phase_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_convtr1d_causal_gemm_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_convtr1d_depthwise_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_rvq_encode_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_rvq_decode_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

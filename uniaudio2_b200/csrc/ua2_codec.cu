@@ -384,6 +384,18 @@ __global__ void __launch_bounds__(256) rvq_decode_kernel(const int64_t* __restri
   }
 }
 
+// torch ConvTranspose1d weight (Cin, Cout, 2s) -> per-phase GEMM operand (s, Cout, Cin, 2): [ph][n][ci][which] = w[ci][n][ph + which*s]
+__global__ void repack_convtr_phase_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cin, int Cout, int s) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)s * Cout * Cin * 2;
+  if (i >= total) return;
+  const int which = (int)(i & 1);
+  const int ci = (int)((i >> 1) % Cin);
+  const int n = (int)((i / ((size_t)2 * Cin)) % Cout);
+  const int ph = (int)(i / ((size_t)2 * Cin * Cout));
+  dst[i] = src[((size_t)ci * Cout + n) * (2 * s) + ph + which * s];
+}
+
 }  // namespace
 }  // namespace ua2
 
@@ -418,6 +430,24 @@ int ua2_conv1d_causal_f32(const float* x, const float* w_ckc, const float* bias,
   return UA2_OK;
 }
 
+// implicit-GEMM variant: same semantics, weights in the reference's own (Cout, Cin, K) layout, 128-position x 128-channel
+// register-tiled fp32 GEMM tiles (ua2_sgemm.cu).  This is the path the codec handle uses.
+int ua2_conv1d_causal_gemm_f32(const float* x, const float* w_torch, const float* bias, const float* residual, float* y, int B,
+                               int Cin, int Cout, int T_in, int K, int stride, int dilation, int pre_elu, int replicate_pad,
+                               void* stream) {
+  UA2_REQUIRE(x && w_torch && y, "null argument");
+  UA2_REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T_in >= 1 && K >= 1 && stride >= 1 && dilation >= 1, "bad shape");
+  const int k_eff = (K - 1) * dilation + 1;
+  const int padding_total = k_eff - stride;
+  UA2_REQUIRE(padding_total >= 0, "kernel smaller than stride is not a causal SEANet conv");
+  const int T_out = (T_in + stride - 1) / stride;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch_conv1d_gemm(lc, x, w_torch, bias, residual, y, B, Cin, Cout, T_in, T_out, K, stride, dilation, padding_total,
+                                    pre_elu, replicate_pad));
+  return UA2_OK;
+}
+
 int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bias, float* y, int B, int Cin, int Cout,
                             int T_in, int stride, int pre_elu, void* stream) {
   UA2_REQUIRE(x && w_ckc && y, "null argument");
@@ -434,6 +464,26 @@ int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bia
   lc.stream = (cudaStream_t)stream;
   const dim3 grid((T_in + J_T - 1) / J_T, (Cout + CO_T - 1) / CO_T, B);
   UA2_CHECK_CUDA(launch(lc, convtr1d_kernel, grid, dim3(256), smem, p));
+  return UA2_OK;
+}
+
+int ua2_convtr1d_repack_phase_f32(const float* w_torch, float* w_phase, int Cin, int Cout, int stride, void* stream) {
+  UA2_REQUIRE(w_torch && w_phase && Cin >= 1 && Cout >= 1 && stride >= 1, "bad argument");
+  const size_t total = (size_t)stride * Cout * Cin * 2;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch(lc, repack_convtr_phase_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, w_torch, w_phase, Cin, Cout,
+                        stride));
+  return UA2_OK;
+}
+
+int ua2_convtr1d_causal_gemm_f32(const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin, int Cout,
+                                 int T_in, int stride, int pre_elu, void* stream) {
+  UA2_REQUIRE(x && w_phase && y, "null argument");
+  UA2_REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T_in >= 1 && stride >= 1 && stride <= 64, "bad shape");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch_convtr1d_gemm(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, pre_elu));
   return UA2_OK;
 }
 

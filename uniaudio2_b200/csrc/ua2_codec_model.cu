@@ -15,8 +15,12 @@
 extern "C" {
 int ua2_conv1d_causal_f32(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int,
                           int, int, void*);
+int ua2_conv1d_causal_gemm_f32(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int,
+                               int, int, void*);
 int ua2_convtr1d_causal_f32(const float*, const float*, const float*, float*, int, int, int, int, int, int, void*);
 int ua2_convtr1d_depthwise_f32(const float*, const float*, float*, int, int, int, int, void*);
+int ua2_convtr1d_repack_phase_f32(const float*, float*, int, int, int, void*);
+int ua2_convtr1d_causal_gemm_f32(const float*, const float*, const float*, float*, int, int, int, int, int, int, void*);
 int ua2_rvq_encode_f32(const float*, const float*, const float*, int64_t*, int, int, int, int, int, int, int, void*);
 int ua2_rvq_decode_f32(const int64_t*, const float*, float*, int, int, int, int, int, int, int, void*);
 }
@@ -91,7 +95,7 @@ __global__ void posidx_kernel(int32_t* pos, int32_t* bidx, int M, int T) {
 struct ConvW {
   const float* w_src = nullptr;  // torch layout
   const float* bias = nullptr;
-  float* w = nullptr;  // repacked (Cin, K, Cout)
+  float* w = nullptr;  // repacked (Cin, K, Cout) [direct kernels] or (stride, Cout, Cin, 2) [transposed conv, phase GEMM]
   int cout = 0, cin = 0, k = 0, transposed = 0;
 };
 
@@ -179,7 +183,7 @@ int conv(ua2_codec* h, const std::string& key, const float* x, const float* res,
          void* st) {
   const ConvW* c = find_conv(h, key);
   UA2_REQUIRE(c && c->w, key + ": conv weight missing");
-  return ua2_conv1d_causal_f32(x, c->w, c->bias, res, y, B, c->cin, c->cout, T, c->k, stride, 1, pre_elu, 0, st);
+  return ua2_conv1d_causal_gemm_f32(x, c->w_src, c->bias, res, y, B, c->cin, c->cout, T, c->k, stride, 1, pre_elu, 0, st);
 }
 
 // ProjectedTransformer(conv_layout=True) over x (B, C, T) in place; tmp buffers carved from the workspace by the caller
@@ -488,8 +492,11 @@ int ua2_codec_finalize(ua2_codec* h, void* stream) {
     UA2_REQUIRE(c.w_src, kv.first + ": weight missing");
     const size_t n = (size_t)c.cout * c.cin * c.k;
     if ((rc = calloc_dev(h, (void**)&c.w, n * 4))) return rc;
-    UA2_CHECK_CUDA(launch(lc, repack_conv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c.w_src, c.w, c.cout, c.cin, c.k,
-                          c.transposed));
+    if (c.transposed) {
+      if ((rc = ua2_convtr1d_repack_phase_f32(c.w_src, c.w, c.cin, c.cout, c.k / 2, st))) return rc;
+    } else {
+      UA2_CHECK_CUDA(launch(lc, repack_conv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c.w_src, c.w, c.cout, c.cin, c.k, 0));
+    }
   }
   for (int t = 0; t < 2; ++t)
     for (auto& w : h->tl[t])
@@ -568,12 +575,12 @@ int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* code
   }
   // ConvDownsample1d: kernel 2*stride, replicate padding, no bias (modules/resample.py:14-65)
   const ConvW* dw = find_conv(h, "downsample");
-  RUN(ua2_conv1d_causal_f32(b, dw->w, nullptr, nullptr, a, B, D, D, Tz, dw->k, h->rs, 1, 0, 1, st));
+  RUN(ua2_conv1d_causal_gemm_f32(b, dw->w_src, nullptr, nullptr, a, B, D, D, Tz, dw->k, h->rs, 1, 0, 1, st));
   // SplitResidualVectorQuantizer.encode (quantization/vq.py:305-315): both quantizers see the same latent
   float* xq = tw;
   for (int g = 0; g < 2; ++g) {
     Rvq& r = h->rvq[g];
-    RUN(ua2_conv1d_causal_f32(a, r.in_w, nullptr, nullptr, xq, B, D, Dq, Tq, 1, 1, 1, 0, 0, st));
+    RUN(ua2_conv1d_causal_gemm_f32(a, r.in_proj, nullptr, nullptr, xq, B, D, Dq, Tq, 1, 1, 1, 0, 0, st));
     RUN(ua2_rvq_encode_f32(xq, r.emb, r.sq, codes, B, Dq, Tq, c.codebook_size, r.n_q, c.rvq_layers, g == 0 ? 0 : 1, st));
   }
   return UA2_OK;
@@ -601,9 +608,9 @@ int ua2_codec_decode(ua2_codec* h, const int64_t* codes, int B, int Tq, float* w
   float *a = h->ws, *b = a + act, *v = b + act, *tw = v + act;
   // SplitRVQ.decode (vq.py:317-323): first.decode + rest.decode, each = sum of codebook rows -> 1x1 output_proj
   RUN(ua2_rvq_decode_f32(codes, h->rvq[0].emb, v, B, Dq, Tq, c.codebook_size, 1, c.rvq_layers, 0, st));
-  RUN(ua2_conv1d_causal_f32(v, h->rvq[0].out_w, nullptr, nullptr, a, B, Dq, D, Tq, 1, 1, 1, 0, 0, st));
+  RUN(ua2_conv1d_causal_gemm_f32(v, h->rvq[0].out_proj, nullptr, nullptr, a, B, Dq, D, Tq, 1, 1, 1, 0, 0, st));
   RUN(ua2_rvq_decode_f32(codes, h->rvq[1].emb, v, B, Dq, Tq, c.codebook_size, c.rvq_layers - 1, c.rvq_layers, 1, st));
-  RUN(ua2_conv1d_causal_f32(v, h->rvq[1].out_w, nullptr, a, b, B, Dq, D, Tq, 1, 1, 1, 0, 0, st));
+  RUN(ua2_conv1d_causal_gemm_f32(v, h->rvq[1].out_proj, nullptr, a, b, B, Dq, D, Tq, 1, 1, 1, 0, 0, st));
   RUN(ua2_convtr1d_depthwise_f32(b, h->up_w, a, B, D, Tq, h->rs, st));
   {
     const size_t MC = (size_t)B * Tz * D, MF = (size_t)B * Tz * c.dim_feedforward;
@@ -620,7 +627,7 @@ int ua2_codec_decode(ua2_codec* h, const int64_t* codes, int B, int Tq, float* w
     const int ratio = c.ratios[i];
     const ConvW* ct = find_conv(h, "decoder.model." + std::to_string(idx + 1) + ".convtr.convtr");
     UA2_REQUIRE(ct && ct->w, "decoder convtr weight missing");
-    RUN(ua2_convtr1d_causal_f32(x, ct->w, ct->bias, y, B, ct->cin, ct->cout, Ts[i], ratio, 1, st));
+    RUN(ua2_convtr1d_causal_gemm_f32(x, ct->w, ct->bias, y, B, ct->cin, ct->cout, Ts[i], ratio, 1, st));
     const std::string p = "decoder.model." + std::to_string(idx + 2) + ".block.";
     RUN(conv(h, p + "1.conv.conv", y, nullptr, v, B, Ts[i + 1], 1, 1, st));
     RUN(conv(h, p + "3.conv.conv", v, y, x, B, Ts[i + 1], 1, 1, st));

@@ -225,3 +225,217 @@ cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const Gem
 }
 
 }  // namespace ua2
+
+// =====================================================================================================
+// Implicit-GEMM causal Conv1d on the same register-tiled core.
+//   C[n, m] = sum_kk W[n, kk] * A(m, kk),  m = (b, t_out),  kk = ci * Ktaps + tap   (torch weight layout (Cout, Cin, Ktaps))
+//   A(m, kk) = f(x[b, ci, t_out * stride + tap * dilation - pad_left])   f = identity | ELU, out of range -> 0 | edge value
+// Replaces StreamingConv1d.forward + the pre-activation ELU + the resblock skip add (llm_modules/conv.py:232-254,
+// seanet.py:52-66, :92-94; Mimi twin).  Lanes run along m (time), so activation loads and the (B, Cout, T) stores are
+// coalesced; the 128-position x BN-channel tile reuses each weight 128x and each activation BN x.
+// =====================================================================================================
+namespace ua2 {
+namespace {
+
+struct ConvGemmParams {
+  const float* x;     // (B, Cin, T_in)
+  const float* w;     // (Cout, Cin, Ktaps) torch layout, or (Cin, Cout, Ktaps) for the transposed-conv mode
+  const float* bias;  // (Cout) or null
+  const float* res;   // (B, Cout, T_out) or null
+  float* y;           // (B, Cout, T_out)
+  int B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left;
+  int pre_elu, replicate;
+  int out_stride;  // > 1: transposed-conv mode, blockIdx.z = output phase: weights w + z*Cout*Cin*Ktaps, store at t*out_stride + z
+};
+
+__device__ __forceinline__ float elu1g(float x) { return x > 0.f ? x : expm1f(x); }
+
+template <int BNC>  // output channels per CTA: 128 / 64 / 32
+__global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGemmParams p) {
+  constexpr int TN = BNC / 16;  // channels per thread
+  __shared__ __align__(16) float Xs[2][BK][BM + PADM];
+  __shared__ __align__(16) float Ws[2][BK][BNC + PADM];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long M = (long long)p.B * p.T_out;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BNC;
+  const int KT = p.Cin * p.Ktaps;
+  const int phase = blockIdx.z;
+  const float* wbase = p.w + (size_t)phase * p.Cout * KT;
+  const int T_store = p.T_out * p.out_stride;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- activation loader: thread -> position m0 + (tid % 128), 8 consecutive kk starting at (tid / 128) * 8
+  const int lm = tid & 127, lkx = (tid >> 7) * 8;
+  const float* xb = nullptr;
+  int tin0 = 0;
+  {
+    const long long m = m0 + lm;
+    if (m < M) {
+      const int b = (int)(m / p.T_out), t = (int)(m - (long long)b * p.T_out);
+      xb = p.x + (size_t)b * p.Cin * p.T_in;
+      tin0 = t * p.stride - p.pad_left;
+    }
+  }
+  auto load_x = [&](int kk0, float (&v)[8]) {
+    int ci = kk0 / p.Ktaps, tap = kk0 - ci * p.Ktaps;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float val = 0.f;
+      if (xb != nullptr && kk0 + i < KT) {
+        int pos = tin0 + tap * p.dilation;
+        bool inside = pos >= 0 && pos < p.T_in;
+        if (!inside && p.replicate) {
+          pos = pos < 0 ? 0 : p.T_in - 1;
+          inside = true;
+        }
+        if (inside) {
+          val = xb[(size_t)ci * p.T_in + pos];
+          if (p.pre_elu) val = elu1g(val);
+        }
+      }
+      v[i] = val;
+      if (++tap == p.Ktaps) {
+        tap = 0;
+        ++ci;
+      }
+    }
+  };
+  // ---- weight loader: BNC x 16 elements per k-tile
+  constexpr int W_PER_THREAD = BNC * BK / SG_THREADS;  // 8 / 4 / 2
+  auto load_w = [&](int kk0, float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < W_PER_THREAD; ++i) {
+      const int e = tid + SG_THREADS * i;
+      const int k = e & 15, n = e >> 4;
+      const int kk = kk0 + k;
+      v[i] = (n0 + n < p.Cout && kk < KT) ? wbase[(size_t)(n0 + n) * KT + kk] : 0.f;
+    }
+  };
+  auto store_w = [&](int buf, const float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < W_PER_THREAD; ++i) {
+      const int e = tid + SG_THREADS * i;
+      Ws[buf][e & 15][e >> 4] = v[i];
+    }
+  };
+
+  float acc[TN][8];
+#pragma unroll
+  for (int i = 0; i < TN; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float rx[8], rw[8];
+  load_x(lkx, rx);
+  load_w(0, rw);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Xs[0][lkx + i][lm] = rx[i];
+  store_w(0, rw);
+  __syncthreads();
+  const int nkt = (KT + BK - 1) / BK;
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nkt) {
+      load_x((kt + 1) * BK + lkx, rx);
+      load_w((kt + 1) * BK, rw);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&Xs[cur][k][tx * 4]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&Xs[cur][k][64 + tx * 4]);
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      float wv[TN];
+      if (TN == 8) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[cur][k][ty * 4]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[cur][k][64 + ty * 4]);
+        wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+        wv[TN > 4 ? 4 : 0] = w1.x; wv[TN > 5 ? 5 : 0] = w1.y; wv[TN > 6 ? 6 : 0] = w1.z; wv[TN > 7 ? 7 : 0] = w1.w;
+      } else if (TN == 4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[cur][k][ty * 4]);
+        wv[0] = w0.x; wv[1] = w0.y; wv[TN > 2 ? 2 : 0] = w0.z; wv[TN > 3 ? 3 : 0] = w0.w;
+      } else {
+        const float2 w0 = *reinterpret_cast<const float2*>(&Ws[cur][k][ty * 2]);
+        wv[0] = w0.x; wv[1] = w0.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TN; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+    }
+    if (kt + 1 < nkt) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Xs[cur ^ 1][lkx + i][lm] = rx[i];
+      store_w(cur ^ 1, rw);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: thread owns channels (TN == 8: ty*4+i and 64+ty*4+i; else ty*TN+i) and positions {tx*4+j, 64+tx*4+j}
+#pragma unroll
+  for (int i = 0; i < TN; ++i) {
+    int nl;
+    if (TN == 8) nl = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    else nl = ty * TN + i;
+    const int n = n0 + nl;
+    if (n >= p.Cout) continue;
+    const float bv = p.bias ? p.bias[n] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long mb = m0 + h * 64 + tx * 4;
+      if (mb >= M) continue;
+      const int b = (int)(mb / p.T_out), t = (int)(mb - (long long)b * p.T_out);
+      const size_t o = ((size_t)b * p.Cout + n) * p.T_out + t;
+      if (p.out_stride == 1 && t + 3 < p.T_out && mb + 3 < M && ((o & 3) == 0)) {
+        float4 v = make_float4(acc[i][h * 4 + 0] + bv, acc[i][h * 4 + 1] + bv, acc[i][h * 4 + 2] + bv, acc[i][h * 4 + 3] + bv);
+        if (p.res) {
+          const float4 r = *reinterpret_cast<const float4*>(p.res + o);
+          v = make_float4(r.x + v.x, r.y + v.y, r.z + v.z, r.w + v.w);
+        }
+        *reinterpret_cast<float4*>(p.y + o) = v;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long m = mb + j;
+          if (m >= M) break;
+          const int b2 = (int)(m / p.T_out), t2 = (int)(m - (long long)b2 * p.T_out);
+          const size_t o2 = ((size_t)b2 * p.Cout + n) * T_store + (size_t)t2 * p.out_stride + phase;
+          float v = acc[i][h * 4 + j] + bv;
+          if (p.res) v = p.res[o2] + v;
+          p.y[o2] = v;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
+                               float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
+                               int pad_left, int pre_elu, int replicate) {
+  ConvGemmParams p{x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu, replicate, 1};
+  const long long M = (long long)B * T_out;
+  const unsigned gx = (unsigned)((M + BM - 1) / BM);
+  if (Cout > 64) return launch(lc, sgemm_conv_kernel<128>, dim3(gx, (Cout + 127) / 128), dim3(SG_THREADS), 0, p);
+  if (Cout > 32) return launch(lc, sgemm_conv_kernel<64>, dim3(gx, 1), dim3(SG_THREADS), 0, p);
+  return launch(lc, sgemm_conv_kernel<32>, dim3(gx, 1), dim3(SG_THREADS), 0, p);
+}
+
+// Transposed conv (kernel = 2*stride, causal trim) as `stride` phase GEMMs in one launch (grid.z = phase):
+//   y[b, n, j*s + ph] = bias[n] + sum_ci ( w[ci, n, ph] * f(x[b, ci, j]) + w[ci, n, ph + s] * f(x[b, ci, j-1]) )
+// w_phase: (s, Cout, Cin, 2) repacked from torch's (Cin, Cout, 2s) by repack_convtr_phase_kernel.
+cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B,
+                                 int Cin, int Cout, int T_in, int stride, int pre_elu) {
+  // as a conv over the input grid: 2 taps, tap 0 -> x[j], tap 1 -> x[j-1]  (dilation -1, no padding, input stride 1)
+  ConvGemmParams p{x, w_phase, bias, nullptr, y, B, Cin, Cout, T_in, T_in, 2, 1, -1, 0, pre_elu, 0, stride};
+  const long long M = (long long)B * T_in;
+  const unsigned gx = (unsigned)((M + BM - 1) / BM);
+  if (Cout > 64) return launch(lc, sgemm_conv_kernel<128>, dim3(gx, (Cout + 127) / 128, stride), dim3(SG_THREADS), 0, p);
+  if (Cout > 32) return launch(lc, sgemm_conv_kernel<64>, dim3(gx, 1, stride), dim3(SG_THREADS), 0, p);
+  return launch(lc, sgemm_conv_kernel<32>, dim3(gx, 1, stride), dim3(SG_THREADS), 0, p);
+}
+
+}  // namespace ua2
