@@ -189,6 +189,10 @@ int ua2_convtr1d_depthwise_f32(const float* x, const float* w, float* y, int B, 
  * Writes codes[b, q_off + q, t] (int64) of a (B, n_q_total, T) tensor. */
 int ua2_rvq_encode_f32(const float* x, const float* emb, const float* emb_sqnorm, int64_t* codes, int B, int D, int T, int K,
                        int n_q, int n_q_total, int q_off, void* stream);
+/* Same algorithm for many frames: per quantizer a tiled fp32 GEMM (scores) + an argmin / residual-update kernel.
+ * r_md: projected input in frame-major layout (B*T, D), updated in place; S: (B*T, K) scratch. */
+int ua2_rvq_encode_gemm_f32(float* r_md, const float* emb, const float* emb_sqnorm, float* S, int64_t* codes, int B, int D, int T,
+                            int K, int n_q, int n_q_total, int q_off, void* stream);
 /* ResidualVectorQuantization.decode (core_vq.py:378-384): out (B, D, T) = sum_q emb[q][codes[b, q_off + q, t]]. */
 int ua2_rvq_decode_f32(const int64_t* codes, const float* emb, float* out, int B, int D, int T, int K, int n_q, int n_q_total,
                        int q_off, void* stream);

@@ -136,6 +136,15 @@ def test_rvq_encode_decode(L, B, D, T, K, n_q):
     torch.cuda.synchronize()
     assert torch.equal(codes[:, 1:1 + n_q].cpu(), ref_codes)
     assert int(codes[:, 0].max()) == -1 and int(codes[:, -1].max()) == -1  # rows outside [q_off, q_off+n_q) untouched
+    # many-frame variant: frame-major residual, tiled-GEMM scores + argmin/update kernels
+    if D % 8 == 0 and K % 2 == 0:
+        r_md = x.transpose(1, 2).reshape(B * T, D).contiguous().cuda()
+        S = torch.empty(B * T, K, device="cuda")
+        codes2 = torch.full((B, n_q + 2, T), -1, dtype=torch.int64, device="cuda")
+        _chk(L.ua2_rvq_encode_gemm_f32(_p(r_md), _p(ed), _p(sq), _p(S), _p(codes2), B, D, T, K, n_q, n_q + 2, 1, None))
+        torch.cuda.synchronize()
+        assert torch.equal(codes2[:, 1:1 + n_q].cpu(), ref_codes)
+        assert float((r_md.cpu() - residual.transpose(1, 2).reshape(B * T, D)).abs().max()) < 1e-4
     out = torch.empty(B, D, T, device="cuda")
     _chk(L.ua2_rvq_decode_f32(_p(codes), _p(ed), _p(out), B, D, T, K, n_q, n_q + 2, 1, None))
     torch.cuda.synchronize()
@@ -188,7 +197,7 @@ def test_codec_full_config_vs_oracle():
     m = _build(cfg, sd)
     orc = CO.MimiOracle(cfg, sd)
     g = torch.Generator().manual_seed(5)
-    wav = torch.randn(2, 1, 3 * 24000 + 311, generator=g) * 0.2  # 2 x 79 frames @25 Hz = 158 rows -> tiled GEMM path
+    wav = torch.randn(4, 1, 3 * 24000 + 311, generator=g) * 0.2  # 4 x 79 frames @25 Hz (tiled GEMM transformer), 4 x 40 code frames (GEMM RVQ)
     with torch.no_grad():
         ref_codes = orc.encode(wav)
         ref_wav = orc.decode(ref_codes)

@@ -67,6 +67,7 @@ SYMBOLS = {
     "ua2_convtr1d_causal_gemm_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_convtr1d_depthwise_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_rvq_encode_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_rvq_encode_gemm_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_rvq_decode_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_codec_create": (C.c_int, [C.POINTER(CodecCfg), C.POINTER(_P)]),
     "ua2_codec_destroy": (C.c_int, [_P]),

@@ -396,6 +396,53 @@ __global__ void repack_convtr_phase_kernel(const float* __restrict__ src, float*
   dst[i] = src[((size_t)ci * Cout + n) * (2 * s) + ph + which * s];
 }
 
+
+// One warp per frame: code = argmin_j (||e_j||^2 - 2 S[m, j]) with S = r E^T from the tiled GEMM, lowest index on ties
+// (torch.argmin, core_vq.py:184); then r[m, :] -= E[code, :] (core_vq.py:372) and codes[b, q, t] = code.
+__global__ void __launch_bounds__(256) rvq_argmin_update_kernel(const float* __restrict__ S, const float* __restrict__ emb,
+                                                                const float* __restrict__ enorm, float* __restrict__ r,
+                                                                int64_t* __restrict__ codes, int M, int K, int D, int T, int n_q_total,
+                                                                int q_index) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float* s = S + (size_t)m * K;
+  float bd = INFINITY;
+  int bi = 0;
+  for (int j = lane; j < K; j += 32) {
+    const float dist = fmaf(-2.f, s[j], enorm[j]);
+    if (dist < bd) {
+      bd = dist;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (od < bd || (od == bd && oi < bi)) {
+      bd = od;
+      bi = oi;
+    }
+  }
+  const float* e = emb + (size_t)bi * D;
+  float* rr = r + (size_t)m * D;
+  for (int d = lane * 4; d < D; d += 128) {
+    float4 v = *reinterpret_cast<float4*>(rr + d);
+    const float4 ev = *reinterpret_cast<const float4*>(e + d);
+    v.x -= ev.x;
+    v.y -= ev.y;
+    v.z -= ev.z;
+    v.w -= ev.w;
+    *reinterpret_cast<float4*>(rr + d) = v;
+  }
+  if (lane == 0) {
+    const int b = m / T, t = m - b * T;
+    codes[((size_t)b * n_q_total + q_index) * T + t] = bi;
+  }
+}
+
 }  // namespace
 }  // namespace ua2
 
@@ -514,6 +561,33 @@ int ua2_rvq_encode_f32(const float* x, const float* emb, const float* emb_sqnorm
   lc.stream = (cudaStream_t)stream;
   const int N = B * T;
   UA2_CHECK_CUDA(launch(lc, rvq_encode_kernel, dim3((N + FT - 1) / FT), dim3(256), smem, p));
+  return UA2_OK;
+}
+
+// Many-frame RVQ encode: per quantizer one 128 x 128-tiled fp32 GEMM (scores S = r E^T) + one argmin/residual-update
+// kernel.  r_md: residual in frame-major layout (M = B*T, D), updated in place; S: (M, K) scratch.
+int ua2_rvq_encode_gemm_f32(float* r_md, const float* emb, const float* emb_sqnorm, float* S, int64_t* codes, int B, int D, int T,
+                            int K, int n_q, int n_q_total, int q_off, void* stream) {
+  UA2_REQUIRE(r_md && emb && emb_sqnorm && S && codes, "null argument");
+  UA2_REQUIRE(B >= 1 && T >= 1 && n_q >= 1 && (D % 8) == 0 && (K % 2) == 0, "bad shape (D % 8, even K)");
+  UA2_REQUIRE(q_off >= 0 && q_off + n_q <= n_q_total, "quantizer range outside the codes tensor");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  const int M = B * T;
+  for (int q = 0; q < n_q; ++q) {
+    GemvParams p;
+    p.W = emb + (size_t)q * K * D;
+    p.N = K;
+    p.K = D;
+    p.M = M;
+    p.X = r_md;
+    p.ldx = D;
+    p.Y = S;
+    p.ldy = K;
+    UA2_CHECK_CUDA(launch_sgemm_linear(lc, PRO_PLAIN, EPI_STORE, p, nullptr));
+    UA2_CHECK_CUDA(launch(lc, rvq_argmin_update_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, (const float*)S,
+                          emb + (size_t)q * K * D, emb_sqnorm + (size_t)q * K, r_md, codes, M, K, D, T, n_q_total, q_off + q));
+  }
   return UA2_OK;
 }
 

@@ -23,6 +23,7 @@ int ua2_convtr1d_repack_phase_f32(const float*, float*, int, int, int, void*);
 int ua2_convtr1d_causal_gemm_f32(const float*, const float*, const float*, float*, int, int, int, int, int, int, void*);
 int ua2_rvq_encode_f32(const float*, const float*, const float*, int64_t*, int, int, int, int, int, int, int, void*);
 int ua2_rvq_decode_f32(const int64_t*, const float*, float*, int, int, int, int, int, int, int, void*);
+int ua2_rvq_encode_gemm_f32(float*, const float*, const float*, float*, int64_t*, int, int, int, int, int, int, int, void*);
 }
 
 namespace ua2 {
@@ -552,7 +553,8 @@ int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* code
     act = std::max(act, (size_t)B * D * Tz);
   }
   const size_t tws = transformer_ws_floats(c, B, Tz);
-  RUN(reserve_ws(h, 3 * act + tws + (size_t)B * Dq * Tq + 64));
+  const size_t rvq_ws = (size_t)B * Tq * (2 * Dq + c.codebook_size) + 64;  // projected latent, frame-major residual, scores
+  RUN(reserve_ws(h, 3 * act + std::max(tws, rvq_ws) + 64));
   float *a = h->ws, *b = a + act, *v = b + act, *tw = v + act;
   RUN(conv(h, "encoder.model.0.conv.conv", wav, nullptr, a, B, T, 1, 0, st));
   int idx = 1;
@@ -581,7 +583,17 @@ int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* code
   for (int g = 0; g < 2; ++g) {
     Rvq& r = h->rvq[g];
     RUN(ua2_conv1d_causal_gemm_f32(a, r.in_proj, nullptr, nullptr, xq, B, D, Dq, Tq, 1, 1, 1, 0, 0, st));
-    RUN(ua2_rvq_encode_f32(xq, r.emb, r.sq, codes, B, Dq, Tq, c.codebook_size, r.n_q, c.rvq_layers, g == 0 ? 0 : 1, st));
+    if ((size_t)B * Tq >= 128 && (Dq % 8) == 0) {
+      // many frames: frame-major residual + per-quantizer tiled GEMM (scores) + argmin/update
+      float* r_md = xq + (size_t)B * Dq * Tq;
+      float* S = r_md + (size_t)B * Dq * Tq;
+      LaunchCtx lc;
+      lc.stream = (cudaStream_t)st;
+      UA2_CHECK_CUDA(launch(lc, transpose_kernel, dim3((Tq + 31) / 32, (Dq + 31) / 32, B), dim3(32, 8), 0, (const float*)xq, r_md, Dq, Tq));
+      RUN(ua2_rvq_encode_gemm_f32(r_md, r.emb, r.sq, S, codes, B, Dq, Tq, c.codebook_size, r.n_q, c.rvq_layers, g == 0 ? 0 : 1, st));
+    } else {
+      RUN(ua2_rvq_encode_f32(xq, r.emb, r.sq, codes, B, Dq, Tq, c.codebook_size, r.n_q, c.rvq_layers, g == 0 ? 0 : 1, st));
+    }
   }
   return UA2_OK;
 }
