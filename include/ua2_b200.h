@@ -181,6 +181,16 @@ int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bia
 int ua2_convtr1d_repack_phase_f32(const float* w_torch, float* w_phase, int Cin, int Cout, int stride, void* stream);
 int ua2_convtr1d_causal_gemm_f32(const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin, int Cout,
                                  int T_in, int stride, int pre_elu, void* stream);
+/* General forms (explicit left / right zero padding, optional single-slope PReLU after the bias, optional residual add):
+ * building blocks of ScalarModel (tools/tokenizer/ReasoningCodec_film/models/scalar24k.py: Conv1d :30-69, ResidualUnit
+ * :139-150, UpsampleLayer :232-265) and of the non-overlapping strided convs of AudioDiffusion1D.py:244-251.
+ * ua2_convtr1d_f32: kernel = 2*stride; y[t] = full[t + crop_left], t < T_out, full length (T_in + 1) * stride. */
+int ua2_conv1d_f32(const float* x, const float* w_torch, const float* bias, const float* prelu_slope, const float* residual, float* y,
+                   int B, int Cin, int Cout, int T_in, int K, int stride, int dilation, int pad_left, int pad_right, void* stream);
+int ua2_convtr1d_f32(const float* x, const float* w_phase, const float* bias, const float* prelu_slope, float* y, int B, int Cin,
+                     int Cout, int T_in, int stride, int crop_left, int T_out, void* stream);
+/* op 0: round(param * x) / param (round_func9, scalar24k.py:279-288);  op 1: tanh(x) */
+int ua2_elementwise_f32(const float* x, float* y, long long n, int op, float param, void* stream);
 /* ConvTrUpsample1d(learnt, channel_wise) (modules/resample.py:68-119): depthwise, w (C, 1, 2*stride). */
 int ua2_convtr1d_depthwise_f32(const float* x, const float* w, float* y, int B, int C, int T_in, int stride, void* stream);
 /* ResidualVectorQuantization.encode (quantization/core_vq.py:365-376) on an already projected input x (B, D, T):

@@ -443,6 +443,15 @@ __global__ void __launch_bounds__(256) rvq_argmin_update_kernel(const float* __r
   }
 }
 
+// op 0: round(param * x) / param  (scalar quantiser of SQ-codec, scalar24k.py round_func9; torch.round = half to even)
+// op 1: tanh(x)
+__global__ void elementwise_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int op, float param) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = op == 0 ? rintf(param * v) / param : tanhf(v);
+}
+
 }  // namespace
 }  // namespace ua2
 
@@ -530,7 +539,43 @@ int ua2_convtr1d_causal_gemm_f32(const float* x, const float* w_phase, const flo
   UA2_REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T_in >= 1 && stride >= 1 && stride <= 64, "bad shape");
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
-  UA2_CHECK_CUDA(launch_convtr1d_gemm(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, pre_elu));
+  UA2_CHECK_CUDA(launch_convtr1d_gemm(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, pre_elu, 0, T_in * stride));
+  return UA2_OK;
+}
+
+// ---- general (non-causal capable) forms used by the ScalarModel wave decoder of ReasoningCodec_film (models/scalar24k.py)
+int ua2_conv1d_f32(const float* x, const float* w_torch, const float* bias, const float* prelu_slope, const float* residual, float* y,
+                   int B, int Cin, int Cout, int T_in, int K, int stride, int dilation, int pad_left, int pad_right, void* stream) {
+  UA2_REQUIRE(x && w_torch && y, "null argument");
+  UA2_REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T_in >= 1 && K >= 1 && stride >= 1 && dilation >= 1 && pad_left >= 0 && pad_right >= 0,
+              "bad shape");
+  const int k_eff = (K - 1) * dilation + 1;
+  const int span = T_in + pad_left + pad_right - k_eff;
+  UA2_REQUIRE(span >= 0, "input shorter than the kernel");
+  const int T_out = span / stride + 1;  // nn.Conv1d output length
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch_conv1d_gemm(lc, x, w_torch, bias, residual, y, B, Cin, Cout, T_in, T_out, K, stride, dilation, pad_left, 0, 0,
+                                    prelu_slope));
+  return UA2_OK;
+}
+
+int ua2_convtr1d_f32(const float* x, const float* w_phase, const float* bias, const float* prelu_slope, float* y, int B, int Cin,
+                     int Cout, int T_in, int stride, int crop_left, int T_out, void* stream) {
+  UA2_REQUIRE(x && w_phase && y, "null argument");
+  UA2_REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T_in >= 1 && stride >= 1 && crop_left >= 0 && T_out >= 1, "bad shape");
+  UA2_REQUIRE(crop_left + T_out <= (T_in + 1) * stride, "crop window exceeds the full transposed-conv output ((T_in + 1) * stride)");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch_convtr1d_gemm(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, 0, crop_left, T_out, prelu_slope));
+  return UA2_OK;
+}
+
+int ua2_elementwise_f32(const float* x, float* y, long long n, int op, float param, void* stream) {
+  UA2_REQUIRE(x && y && n >= 1 && op >= 0 && op <= 1, "bad argument");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch(lc, elementwise_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, x, y, n, op, param));
   return UA2_OK;
 }
 

@@ -53,11 +53,12 @@ cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const Gem
 void set_gemv_impl(int v);
 void set_sgemm_min_rows(int v);
 cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B,
-                                 int Cin, int Cout, int T_in, int stride, int pre_elu);
+                                 int Cin, int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out,
+                                 const float* prelu = nullptr);
 // implicit-GEMM causal conv1d (weights in torch layout (Cout, Cin, Ktaps))
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
-                               int pad_left, int pre_elu, int replicate);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
+                               int pad_left, int pre_elu, int replicate, const float* prelu = nullptr);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);
 void set_gemv3_ctas_per_sm(int v);
 void set_gemv3_max_stages(int v);

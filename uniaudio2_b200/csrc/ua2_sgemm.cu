@@ -246,6 +246,9 @@ struct ConvGemmParams {
   int B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left;
   int pre_elu, replicate;
   int out_stride;  // > 1: transposed-conv mode, blockIdx.z = output phase: weights w + z*Cout*Cin*Ktaps, store at t*out_stride + z
+  int out_offset;  // transposed conv: samples cropped on the left of the full output (non-causal padding)
+  int T_store;     // time length of y
+  const float* prelu;  // nullable: single-slope nn.PReLU applied after bias, before the residual add
 };
 
 __device__ __forceinline__ float elu1g(float x) { return x > 0.f ? x : expm1f(x); }
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
   const int KT = p.Cin * p.Ktaps;
   const int phase = blockIdx.z;
   const float* wbase = p.w + (size_t)phase * p.Cout * KT;
-  const int T_store = p.T_out * p.out_stride;
+  const int T_store = p.T_store;
   pdl_launch_dependents();
   pdl_wait();
 
@@ -382,14 +385,17 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
     const int n = n0 + nl;
     if (n >= p.Cout) continue;
     const float bv = p.bias ? p.bias[n] : 0.f;
+    const float slope = p.prelu ? p.prelu[0] : 1.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const long long mb = m0 + h * 64 + tx * 4;
       if (mb >= M) continue;
       const int b = (int)(mb / p.T_out), t = (int)(mb - (long long)b * p.T_out);
-      const size_t o = ((size_t)b * p.Cout + n) * p.T_out + t;
-      if (p.out_stride == 1 && t + 3 < p.T_out && mb + 3 < M && ((o & 3) == 0)) {
+      const size_t o = ((size_t)b * p.Cout + n) * T_store + t;
+      if (p.out_stride == 1 && p.out_offset == 0 && t + 3 < p.T_out && mb + 3 < M && ((o & 3) == 0)) {
         float4 v = make_float4(acc[i][h * 4 + 0] + bv, acc[i][h * 4 + 1] + bv, acc[i][h * 4 + 2] + bv, acc[i][h * 4 + 3] + bv);
+        if (p.prelu) v = make_float4(v.x > 0.f ? v.x : slope * v.x, v.y > 0.f ? v.y : slope * v.y, v.z > 0.f ? v.z : slope * v.z,
+                                     v.w > 0.f ? v.w : slope * v.w);
         if (p.res) {
           const float4 r = *reinterpret_cast<const float4*>(p.res + o);
           v = make_float4(r.x + v.x, r.y + v.y, r.z + v.z, r.w + v.w);
@@ -401,8 +407,11 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
           const long long m = mb + j;
           if (m >= M) break;
           const int b2 = (int)(m / p.T_out), t2 = (int)(m - (long long)b2 * p.T_out);
-          const size_t o2 = ((size_t)b2 * p.Cout + n) * T_store + (size_t)t2 * p.out_stride + phase;
+          const long long ts = (long long)t2 * p.out_stride + phase - p.out_offset;
+          if (ts < 0 || ts >= T_store) continue;
+          const size_t o2 = ((size_t)b2 * p.Cout + n) * T_store + (size_t)ts;
           float v = acc[i][h * 4 + j] + bv;
+          if (p.prelu) v = v > 0.f ? v : slope * v;
           if (p.res) v = p.res[o2] + v;
           p.y[o2] = v;
         }
@@ -415,8 +424,9 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
 
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
-                               int pad_left, int pre_elu, int replicate) {
-  ConvGemmParams p{x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu, replicate, 1};
+                               int pad_left, int pre_elu, int replicate, const float* prelu) {
+  ConvGemmParams p{x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu, replicate, 1, 0, T_out,
+                   prelu};
   const long long M = (long long)B * T_out;
   const unsigned gx = (unsigned)((M + BM - 1) / BM);
   if (Cout > 64) return launch(lc, sgemm_conv_kernel<128>, dim3(gx, (Cout + 127) / 128), dim3(SG_THREADS), 0, p);
@@ -428,10 +438,13 @@ cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float*
 //   y[b, n, j*s + ph] = bias[n] + sum_ci ( w[ci, n, ph] * f(x[b, ci, j]) + w[ci, n, ph + s] * f(x[b, ci, j-1]) )
 // w_phase: (s, Cout, Cin, 2) repacked from torch's (Cin, Cout, 2s) by repack_convtr_phase_kernel.
 cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B,
-                                 int Cin, int Cout, int T_in, int stride, int pre_elu) {
-  // as a conv over the input grid: 2 taps, tap 0 -> x[j], tap 1 -> x[j-1]  (dilation -1, no padding, input stride 1)
-  ConvGemmParams p{x, w_phase, bias, nullptr, y, B, Cin, Cout, T_in, T_in, 2, 1, -1, 0, pre_elu, 0, stride};
-  const long long M = (long long)B * T_in;
+                                 int Cin, int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out,
+                                 const float* prelu) {
+  // as a conv over the input grid: 2 taps, tap 0 -> x[j], tap 1 -> x[j-1]  (dilation -1, no padding, input stride 1);
+  // j runs to T_in inclusive when the right tail (x[T_in - 1] * w[ph + s]) survives the crop
+  const int Tj = (crop_left + T_out > T_in * stride) ? T_in + 1 : T_in;
+  ConvGemmParams p{x, w_phase, bias, nullptr, y, B, Cin, Cout, T_in, Tj, 2, 1, -1, 0, pre_elu, 0, stride, crop_left, T_out, prelu};
+  const long long M = (long long)B * Tj;
   const unsigned gx = (unsigned)((M + BM - 1) / BM);
   if (Cout > 64) return launch(lc, sgemm_conv_kernel<128>, dim3(gx, (Cout + 127) / 128, stride), dim3(SG_THREADS), 0, p);
   if (Cout > 32) return launch(lc, sgemm_conv_kernel<64>, dim3(gx, 1, stride), dim3(SG_THREADS), 0, p);
