@@ -160,6 +160,10 @@ def run_utterance_device(model, tokens, mask, pos):
     return torch.stack(frames), launches
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture (per launch)
+NCU_TRAFFIC_BYTES = 205.39e6
+
+
 def time_dominant_kernel(model, hbm_peak, reps=3):
     """Roofline of the dominant kernel: the fused RMSNorm -> fc_1|fc_2 -> SiLU*mul skinny linear (gemv_kernel<1,RMSNORM,
     SWIGLU>) of the backbone MLP, 2 x 8192 x 3072 fp32 weights = 201.3 MB algorithmic bytes per launch; 28+3+2 such
@@ -195,7 +199,8 @@ def time_dominant_kernel(model, hbm_peak, reps=3):
     achieved = bytes_per_launch / (us * 1e-6) / 1e9
     return {"bound": "hbm", "kernel": "gemv3_kernel<1,PRO_RMSNORM,EPI_SWIGLU> (backbone mlp fc_1|fc_2, N=8192 K=3072; same template serves every linear of the frame)",
             "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-            "traffic": None, "launch_us": round(us, 2), "bytes_per_launch": bytes_per_launch, "launches_timed": n}
+            "traffic": NCU_TRAFFIC_BYTES, "traffic_source": "profiles/r1_ncu_full_gemv3.md (ncu --set full, dram read+write per launch)",
+            "launch_us": round(us, 2), "bytes_per_launch": bytes_per_launch, "launches_timed": n}
 
 
 def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
@@ -324,6 +329,9 @@ def main():
     ap.add_argument("--v3-kcw", type=int, default=0)
     ap.add_argument("--v3-balance", type=int, default=-1)
     ap.add_argument("--v3-budget", type=int, default=0)
+    ap.add_argument("--attn-direct", type=int, default=-1, help="local-decoder attention inside the proj prologue (library default 1)")
+    ap.add_argument("--pf-mb", type=int, default=-1, help="tail L2 prefetch budget per linear, MB (-1: library default)")
+    ap.add_argument("--pf-idle-mb", type=int, default=-1, help="extra prefetch budget before attention / sampler kernels, MB")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
     ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
     args = ap.parse_args()
@@ -387,6 +395,10 @@ def main():
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_kcw", args.v3_kcw))
     if args.v3_budget:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_budget_kb", args.v3_budget))
+    if args.pf_mb >= 0:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_mb", args.pf_mb))
+    if args.pf_idle_mb >= 0:
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_idle_mb", args.pf_idle_mb))
     if args.v3_stages:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_max_stages", args.v3_stages))
     if args.v3_cps:
@@ -396,6 +408,8 @@ def main():
         init_weights_(model, 0)  # same weights on every replica
         gen = Generator(model, default_train_args(REASON_CARD, SEMANTIC_CARD), is_cfg=False)  # setup_caches(1)
         model.set_option("pdl", int(args.pdl))
+        if args.attn_direct >= 0:
+            model.set_option("attn_direct", int(args.attn_direct))
         task_prompt, text = synthetic_prompt(rank)
         tokens, mask = gen.prepare_tts_task(task_prompt, text)
         assert tokens.size(0) == PROMPT_LEN

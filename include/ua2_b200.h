@@ -36,7 +36,11 @@ int ua2_device_sm_count(void);
 const char* ua2_version(void);
 /* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (per-warp cp.async.bulk + mbarrier rings) |
  * 3 (persistent CTAs, slab partition + K split across warps, bulk-copy rings; default);
- * "gemv3_ctas_per_sm" (1..3, default 2), "gemv3_max_stages" (2..6, default 3) */
+ * "gemv3_ctas_per_sm" (1..3, default 2), "gemv3_max_stages" (2..6, default 3), "gemv3_kcw" (floats per bulk copy, default 1024),
+ * "gemv3_budget_kb" (shared memory per decode CTA, default 110), "gemv3_balance_grid" (0/1, default 1),
+ * "sgemm_min_rows" (rows from which linears use the tiled GEMM core, default 128),
+ * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with
+ * -DUA2_GEMV3_TAIL_PREFETCH=1 - measured slower, see profiles/r1_l2_prefetch_experiment.md) */
 int ua2_set_global_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -119,7 +123,8 @@ int ua2_llm_get_kv(ua2_llm* h, int which, int layer, float** k, float** v);
 /* name: "h_final" (B x n_embd), "text_logits" (B x text_vocab), "audio_logits" (nq x B x audio_vocab) */
 int ua2_llm_get_buffer(ua2_llm* h, const char* name, float** ptr, int64_t* numel);
 /* knobs: "graph" (0/1, default 1: replay the frame as a CUDA graph), "pdl" (0/1, default 1: programmatic dependent launch),
- * "chain" (0/1, default 0: B = 1 frames run as persistent multi-op cooperative kernels, see csrc/ua2_chain.cu) */
+ * "chain" (0/1, default 0: B = 1 frames run as persistent multi-op cooperative kernels, see csrc/ua2_chain.cu),
+ * "attn_direct" (0/1, default 0: the local decoder's <= 8-key attention runs inside the proj kernel's prologue; measured 0.3 % slower) */
 int ua2_llm_set_option(ua2_llm* h, const char* name, int value);
 /* number of kernels launched (or graph kernel nodes replayed) by the last prefill / generate_frame */
 int ua2_llm_last_launch_count(ua2_llm* h);
@@ -191,6 +196,15 @@ int ua2_convtr1d_f32(const float* x, const float* w_phase, const float* bias, co
                      int Cout, int T_in, int stride, int crop_left, int T_out, void* stream);
 /* op 0: round(param * x) / param (round_func9, scalar24k.py:279-288);  op 1: tanh(x) */
 int ua2_elementwise_f32(const float* x, float* y, long long n, int op, float param, void* stream);
+/* time_film (ReasoningCodec_film/models/AudioDiffusion1D.py:428-438): out = gamma * features + beta with
+ * gamma = 1 + gamma_scale * tanh(params[..., :C]), beta = params[..., C:]; batches with zero_mask[b] != 0 get (1, 0).
+ * params (B, T, 2C), features / out (B, T, C); zero_mask (B) uint8 nullable - the reference's torch.rand(B,1,1) < 0.2 draw. */
+int ua2_film_f32(const float* params, const float* features, const uint8_t* zero_mask, float* out, int B, int T, int C, float gamma_scale,
+                 void* stream);
+/* F.interpolate(x (B, C, T_in), scale_factor, mode='nearest') (AudioDiffusion1D.py:523, :589); T_out = floor(T_in * scale) */
+int ua2_interp_nearest_f32(const float* x, float* y, int B, int C, int T_in, int T_out, float scale_factor, void* stream);
+/* nn.Linear with bias (cond_fusion_layer_*, cond_feature_emb: AudioDiffusion1D.py:278-280, :547) */
+int ua2_linear_bias_f32(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, void* stream);
 /* ConvTrUpsample1d(learnt, channel_wise) (modules/resample.py:68-119): depthwise, w (C, 1, 2*stride). */
 int ua2_convtr1d_depthwise_f32(const float* x, const float* w, float* y, int B, int C, int T_in, int stride, void* stream);
 /* ResidualVectorQuantization.encode (quantization/core_vq.py:365-376) on an already projected input x (B, D, T):

@@ -19,6 +19,9 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+PF_DEFAULT = (0, 0)  # library defaults of gemv3_prefetch_mb / gemv3_prefetch_idle_mb
+
+
 @pytest.fixture(scope="module")
 def models():
     out = {}
@@ -28,19 +31,32 @@ def models():
     return out
 
 
-@pytest.mark.parametrize("mode", ["eager", "graph", "chain"])
+@pytest.mark.parametrize("mode", ["eager", "graph", "chain", "graph_direct_local_attn"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_frames_match_reference_golden(models, golden, case, mode):
     """eager: one launch per kernel; graph: CUDA-graph replay with PDL edges; chain: persistent multi-op cooperative
-    kernels (B = 1 only - larger batches fall back to the graph path)."""
+    kernels (B = 1 only - larger batches fall back to the graph path); graph_direct_local_attn: the local decoder's
+    <= 8-key attention computed inside the proj kernel's prologue instead of its own split-softmax launch (option
+    attn_direct = 1), with the tail-prefetch planner enabled (a no-op unless built with UA2_GEMV3_TAIL_PREFETCH)."""
     name, cname, kind, B, S, nf, topk, temp, cfg_scale = case
     cfg, sd, m = models[cname]
     fx = golden[name]
-    m.set_option("graph", 0 if mode == "eager" else 1)
+    from uniaudio2_b200 import _lib
+
+    m.set_option("graph", 0 if mode.startswith("eager") else 1)
     m.set_option("chain", 1 if mode == "chain" else 0)
-    r = run_case(m, kind, cfg, B, S, nf, topk, temp, cfg_scale, REASON_CARD[cname], 42, True, device="cuda",
-                 explicit_noise=True)
-    torch.cuda.synchronize()
+    m.set_option("attn_direct", 1 if mode == "graph_direct_local_attn" else 0)
+    pf = 48 if mode == "graph_direct_local_attn" else 0
+    _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_mb", pf))
+    _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_idle_mb", pf))
+    try:
+        r = run_case(m, kind, cfg, B, S, nf, topk, temp, cfg_scale, REASON_CARD[cname], 42, True, device="cuda",
+                     explicit_noise=True)
+        torch.cuda.synchronize()
+    finally:
+        m.set_option("attn_direct", 0)
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_mb", PF_DEFAULT[0]))
+        _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_idle_mb", PF_DEFAULT[1]))
     got = r["frames"].cpu()
     assert torch.equal(got, fx["ref_frames"]), (
         f"{name}: token ids differ from the reference (min top-1/top-2 margins: text {fx['margin_text']:.2e}, "
@@ -173,3 +189,21 @@ def test_task_generators(models):
         ct[0, 0, -1] = t
         cm = torch.cat([torch.zeros(1, 1, 8, dtype=torch.bool), torch.ones(1, 1, 1, dtype=torch.bool)], -1)
     assert ids == ref_ids and len(ids) == 6
+
+
+def test_batch32_caption_config():
+    """SURVEY section 8(d) config 3 shape: 32 equal-length mixed prompts, batched prefill (B*S rows go through the tiled
+    GEMM path) + greedy frames at B = 32 (four M tiles of 8 rows per linear), against the oracle run in-process.
+    Also a ragged batch (B = 11: tiles of 8 + 3)."""
+    import copy
+
+    cfg = copy.deepcopy(tiny_cfgs()["tiny"])
+    sd = O.random_state_dict(cfg, seed=77)
+    m = build_product_model(cfg, sd, "cuda", 32)
+    orc = O.Stage3Oracle(cfg, sd)
+    orc.setup_caches(32)
+    for (B, S, nf) in ((32, 21, 4), (11, 13, 3)):
+        o = run_case(orc, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, False, explicit_noise=True)
+        r = run_case(m, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, True, device="cuda", explicit_noise=True)
+        assert torch.equal(r["frames"].cpu(), o["frames"])
+        assert _rel(m.debug_buffer("text_logits", B).cpu(), o["text_logits"][-1]) < REL_TOL

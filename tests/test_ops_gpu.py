@@ -191,6 +191,32 @@ def test_sampler_ties_at_threshold(L):
     assert out.item() == ref2.item() == 5
 
 
+@pytest.mark.parametrize("V", [12300, 128256])
+@pytest.mark.parametrize("topk", [3, 128, 129])
+def test_sampler_candidate_path_edges(L, V, topk):
+    """The candidate-list fast path (k <= 128) and its overflow fallback: (a) a plateau of equal logits far longer than
+    the list (every element ties with the k-th value -> all kept, model_new.py:150), (b) a row whose top values sit in
+    one 4-thread group, (c) the largest k served by the fast path and the first k that is not."""
+    g = torch.Generator().manual_seed(V * 7 + topk)
+    rows = []
+    plateau = torch.full((V,), 0.25)
+    plateau[torch.randperm(V, generator=g)[:5]] = -3.0
+    rows.append(plateau)
+    clustered = torch.randn(V, generator=g)
+    clustered[1000:1000 + 4 * 140:4] += 20.0  # 140 large values at stride 4: few thread groups own all of the top k
+    rows.append(clustered)
+    rows.append(torch.randn(V, generator=g) * 4)
+    logits = torch.stack(rows)
+    R = logits.shape[0]
+    q = _noise(R, V, 99 + topk)
+    ref = O.audio_sample_topk(logits, topk, 0.9, 0, noise=q).squeeze(1)
+    out = torch.empty(R, dtype=torch.int32, device="cuda")
+    ld, qd = logits.cuda(), q.cuda()
+    _chk(L.ua2_sample_topk_f32(_p(ld), R, V, 0.9, topk, 0, 1.0, _p(qd), 0, 0, _p(out), None))
+    torch.cuda.synchronize()
+    assert out.cpu().tolist() == ref.tolist()
+
+
 @pytest.mark.parametrize("V", [800, 128256])
 def test_sampler_cfg(L, V):
     """CFG mix of model_new.py:618-622: u + (c-u)*scale with row 0 = cond, row 1 = uncond; one sample, repeated."""

@@ -92,3 +92,37 @@ def test_general_conv1d(B, Cin, Cout, T, K, stride, dil, pl, pr):
                                 Cin, Cout, T, K, stride, dil, pl, pr, None))
     torch.cuda.synchronize()
     assert float((y.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_film_interp_linear_bias():
+    """time_film, nearest x2.5 interpolation and the biased fusion Linear of AudioDiffusion1D.py (:428-438, :523, :278-280)."""
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(4)
+    B, T, C, Kin = 3, 375, 768, 1024
+    x = torch.randn(B, T, Kin, generator=g)
+    W = torch.randn(2 * C, Kin, generator=g) / Kin ** 0.5
+    bias = torch.randn(2 * C, generator=g) * 0.1
+    feat = torch.randn(B, T, C, generator=g)
+    mask = torch.tensor([0, 1, 0], dtype=torch.uint8)
+    params = F.linear(x, W, bias)
+    dg, beta = params.chunk(2, dim=-1)
+    gamma = 1.0 + 0.1 * dg.tanh()
+    mk = mask.float().view(B, 1, 1)
+    ref = (gamma * (1 - mk) + 1.0 * mk) * feat + (beta * (1 - mk) + 0.0 * mk)
+    xd, Wd, bd, fd, md = x.cuda(), W.cuda(), bias.cuda(), feat.cuda(), mask.cuda()
+    pd = torch.empty(B, T, 2 * C, device="cuda")
+    out = torch.empty(B, T, C, device="cuda")
+    _lib.check(L.ua2_linear_bias_f32(_lib.ptr(xd), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(pd), B * T, 2 * C, Kin, None))
+    _lib.check(L.ua2_film_f32(_lib.ptr(pd), _lib.ptr(fd), _lib.ptr(md), _lib.ptr(out), B, T, C, 0.1, None))
+    torch.cuda.synchronize()
+    assert float((pd.cpu() - params).abs().max()) < 2e-5 * float(params.abs().max())
+    assert float((out.cpu() - ref).abs().max()) < 1e-4
+    r = torch.randn(2, 768, 150, generator=g)
+    ref_i = F.interpolate(r, scale_factor=2.5, mode="nearest")
+    rd = r.cuda()
+    yi = torch.empty(2, 768, ref_i.shape[-1], device="cuda")
+    _lib.check(L.ua2_interp_nearest_f32(_lib.ptr(rd), _lib.ptr(yi), 2, 768, 150, ref_i.shape[-1], 2.5, None))
+    torch.cuda.synchronize()
+    assert torch.equal(yi.cpu(), ref_i)

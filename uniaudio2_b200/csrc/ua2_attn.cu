@@ -36,40 +36,43 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   const int split = blockIdx.x, g = blockIdx.y, m = blockIdx.z;
   pdl_launch_dependents();
   pdl_wait();
-  const int n_keys = p.pos[m] + 1;
+  // The K/V chunk copy does not wait for pos[m]: it always fetches the whole chunk (clipped to the cache), so the position
+  // load, the q load and the two bulk copies are ONE L2 round trip instead of two.  Rows past n_keys are never read.
   const int start = split * C;
-  const int qpk = p.n_head / p.n_groups;
-  const int lo = (p.window > 0) ? max(0, n_keys - p.window) : 0;  // first visible key (Moshi context window)
-  if (start >= n_keys || start + C <= lo) {  // empty split: publish weight-0 statistics so consumers can merge blindly
-    if (tid < qpk) {
-      const size_t idx = (((size_t)m * p.n_head + g * qpk + tid) * p.max_splits + split) * 2;
-      p.ml_part[idx] = -INFINITY;
-      p.ml_part[idx + 1] = 0.f;
-    }
-    return;
-  }
-  const int cnt = min(C, n_keys - start);
-  const int b = p.bidx[m];
-  const float scale = rsqrtf((float)HS);
+  const int b = p.bidx_identity ? m : p.bidx[m];
+  const int span = max(0, min(C, p.S_max - start));
   const float* Kc = p.k_cache + (((size_t)b * p.n_groups + g) * p.S_max + start) * HS;
   const float* Vc = p.v_cache + (((size_t)b * p.n_groups + g) * p.S_max + start) * HS;
   float* Ks = kv_s;
   float* Vs = kv_s + C * HS;
-
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32a(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = (uint32_t)cnt * HS * 4u;
+    const uint32_t bytes = (uint32_t)span * HS * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32a(&bar)), "r"(2u * bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32a(Ks)),
-                 "l"(Kc), "r"(bytes), "r"(smem_u32a(&bar))
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32a(Vs)),
-                 "l"(Vc), "r"(bytes), "r"(smem_u32a(&bar))
-                 : "memory");
+    if (bytes > 0) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32a(Ks)),
+                   "l"(Kc), "r"(bytes), "r"(smem_u32a(&bar))
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32a(Vs)),
+                   "l"(Vc), "r"(bytes), "r"(smem_u32a(&bar))
+                   : "memory");
+    }
   }
+  const int n_keys = p.pos[m] + 1;
+  const int qpk = p.n_head / p.n_groups;
+  const int lo = (p.window > 0) ? max(0, n_keys - p.window) : 0;  // first visible key (Moshi context window)
+  const bool empty = start >= n_keys || start + C <= lo;
+  if (empty && tid < qpk) {  // empty split: publish weight-0 statistics so consumers can merge blindly
+    const size_t idx = (((size_t)m * p.n_head + g * qpk + tid) * p.max_splits + split) * 2;
+    p.ml_part[idx] = -INFINITY;
+    p.ml_part[idx + 1] = 0.f;
+  }
+  const int cnt = min(C, n_keys - start);
+  const float scale = rsqrtf((float)HS);
+
   // q -> registers while the copies fly: lane (kk = lane>>3, part = lane&7) needs q[h][part*4 + 32*i .. +3]
   const int kk = lane >> 3, part = lane & 7;
   float4 qr[MAX_QPK][NI];
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
       "}\n" ::"r"(smem_u32a(&bar)),
       "r"(0u)
       : "memory");
+  if (empty) return;  // (only after the copies have landed: the CTA's shared memory must outlive them)
 
   // ---- phase 1: scores.  16 keys per iteration over the CTA (4 warps x 4 keys)
 #pragma unroll

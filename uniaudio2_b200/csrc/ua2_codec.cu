@@ -443,6 +443,43 @@ __global__ void __launch_bounds__(256) rvq_argmin_update_kernel(const float* __r
   }
 }
 
+
+// time_film (AudioDiffusion1D.py:428-438): gamma = 1 + g * tanh(params[..., :C]); beta = params[..., C:]; rows of batches whose
+// zero-condition flag is set get gamma = 1, beta = 0 (the reference draws that flag with torch.rand(B,1,1) < 0.2 even at
+// inference; the draw is an INPUT here so that results are reproducible); out = gamma * features + beta.
+__global__ void film_kernel(const float* __restrict__ params, const float* __restrict__ feat, const uint8_t* __restrict__ zero_mask,
+                            float* __restrict__ out, long long M, int C, int T, float g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const long long m = i / C;
+  const int c = (int)(i - m * C);
+  const int b = (int)(m / T);
+  float gamma = 1.0f + g * tanhf(params[m * 2 * C + c]);
+  float beta = params[m * 2 * C + C + c];
+  const float mk = (zero_mask && zero_mask[b]) ? 1.f : 0.f;
+  gamma = gamma * (1.f - mk) + 1.0f * mk;
+  beta = beta * (1.f - mk) + 0.0f * mk;
+  out[i] = gamma * feat[i] + beta;
+}
+
+// F.interpolate(x (B, C, T_in), scale_factor=s, mode='nearest') as used on the reasoning feature (AudioDiffusion1D.py:523):
+// T_out = floor(T_in * s), src = min(floor(dst * (1 / s)), T_in - 1)  (torch's legacy nearest with a given scale factor)
+__global__ void interp_nearest_kernel(const float* __restrict__ x, float* __restrict__ y, long long BC, int T_in, int T_out, float inv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC * T_out) return;
+  const long long r = i / T_out;
+  const int t = (int)(i - r * T_out);
+  int src = (int)floorf((float)t * inv);
+  if (src > T_in - 1) src = T_in - 1;
+  y[i] = x[r * T_in + src];
+}
+
+// y[m, n] += bias[n]  (nn.Linear bias of the cond_fusion / film heads, AudioDiffusion1D.py:278-284)
+__global__ void add_bias_kernel(float* __restrict__ y, const float* __restrict__ bias, long long MN, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < MN) y[i] += bias[i % N];
+}
+
 // op 0: round(param * x) / param  (scalar quantiser of SQ-codec, scalar24k.py round_func9; torch.round = half to even)
 // op 1: tanh(x)
 __global__ void elementwise_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int op, float param) {
@@ -576,6 +613,38 @@ int ua2_elementwise_f32(const float* x, float* y, long long n, int op, float par
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
   UA2_CHECK_CUDA(launch(lc, elementwise_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, x, y, n, op, param));
+  return UA2_OK;
+}
+
+int ua2_film_f32(const float* params, const float* features, const uint8_t* zero_mask, float* out, int B, int T, int C, float gamma_scale,
+                 void* stream) {
+  UA2_REQUIRE(params && features && out && B >= 1 && T >= 1 && C >= 1, "bad argument");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  const long long M = (long long)B * T;
+  UA2_CHECK_CUDA(launch(lc, film_kernel, dim3((unsigned)((M * C + 255) / 256)), dim3(256), 0, params, features, zero_mask, out, M, C, T,
+                        gamma_scale));
+  return UA2_OK;
+}
+
+int ua2_interp_nearest_f32(const float* x, float* y, int B, int C, int T_in, int T_out, float scale_factor, void* stream) {
+  UA2_REQUIRE(x && y && B >= 1 && C >= 1 && T_in >= 1 && T_out >= 1 && scale_factor > 0.f, "bad argument");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  const long long BC = (long long)B * C;
+  UA2_CHECK_CUDA(launch(lc, interp_nearest_kernel, dim3((unsigned)((BC * T_out + 255) / 256)), dim3(256), 0, x, y, BC, T_in, T_out,
+                        1.0f / scale_factor));
+  return UA2_OK;
+}
+
+int ua2_linear_bias_f32(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, void* stream) {
+  UA2_REQUIRE(x && W && y, "null argument");
+  int rc = ua2_linear_f32(x, W, nullptr, 0.f, nullptr, y, M, N, K, stream);
+  if (rc != UA2_OK || bias == nullptr) return rc;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  const long long MN = (long long)M * N;
+  UA2_CHECK_CUDA(launch(lc, add_bias_kernel, dim3((unsigned)((MN + 255) / 256)), dim3(256), 0, y, bias, MN, N));
   return UA2_OK;
 }
 

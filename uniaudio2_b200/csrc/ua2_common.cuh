@@ -54,10 +54,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Per-launch context shared by the host-side launchers.
+struct GemvSeq;
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   bool pdl = false;       // attach the programmatic-stream-serialization attribute
   int* launch_counter = nullptr;
+  struct GemvSeq* seq = nullptr;  // frame-level launch sequence (tail L2 prefetch of the next linears' weights)
 };
 
 // Every kernel of the path asks for the maximum shared-memory carveout, so consecutive (and, under PDL,

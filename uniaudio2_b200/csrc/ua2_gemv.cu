@@ -465,12 +465,46 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
 }  // namespace
 
 void set_sgemm_min_rows(int v) { g_sgemm_min_rows = v < 1 ? 1 : v; }
+int get_gemv_impl() { return g_gemv_impl; }
+int get_sgemm_min_rows() { return g_sgemm_min_rows; }
 void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 3; }
 
-cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
+namespace {
+// Record / replay the frame's sequence of linears (GemvSeq) and attach the tail-prefetch specs of the following ones.
+const GemvParams& with_prefetch(const LaunchCtx& lc, int epi, const GemvParams& p, GemvParams& tmp) {
+  GemvSeq* sq = lc.seq;
+  if (sq == nullptr) return p;
+  if (!sq->recorded) {
+    GemvSeqEntry e;
+    e.W = p.W;
+    e.W2 = p.W2;
+    e.N = p.N;
+    e.K = p.K;
+    e.M = p.M;
+    e.epi = epi;
+    e.hs = p.hs;
+    sq->ops.push_back(e);
+    return p;
+  }
+  const int n = (int)sq->ops.size();
+  const int i = sq->pos++;
+  if (i >= n || sq->ops[i].W != p.W || sq->ops[i].M != p.M) return p;  // not the recorded frame: no prefetch
+  const size_t budget = gemv3_prefetch_budget(sq->ops[i].idle_after);
+  if (budget == 0 || g_gemv_impl != 3) return p;
+  GemvSeqEntry nxt[PF_MAX];
+  for (int j = 0; j < PF_MAX; ++j) nxt[j] = sq->ops[(i + 1 + j) % n];  // wraps into the next frame (same weights)
+  tmp = p;
+  tmp.n_pf = gemv3_make_pf(nxt, PF_MAX < n ? PF_MAX : n, budget, tmp.pf);
+  return tmp;
+}
+}  // namespace
+
+cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p_in) {
+  GemvParams p_tmp;
+  const GemvParams& p = with_prefetch(lc, epi, p_in, p_tmp);
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;
   // many rows: 128 x 128 register-tiled fp32 GEMM (each weight element reused 128x) instead of re-streaming W per 8 rows
-  if (p.M >= g_sgemm_min_rows && p.ws != nullptr) {
+  if (p.M >= g_sgemm_min_rows && p.ws != nullptr && pro != PRO_ATTN_DIRECT) {
     GemvParams q = p;
     int pro2 = pro;
     size_t need = 2 * (size_t)p.M;
@@ -503,6 +537,10 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
       if (e != cudaErrorNotSupported) return e;
       if (pro == PRO_ATTN) return cudaErrorInvalidValue;  // combine already consumed; should not happen (instances exist)
     }
+  }
+  if (pro == PRO_ATTN_DIRECT) {
+    if (g_gemv_impl != 3 || epi != EPI_RESADD || p.hs != 64 || p.S_max > ATTN_DIRECT_MAX_KEYS) return cudaErrorInvalidValue;
+    return launch_gemv3(lc, pro, epi, p, 1);
   }
   if (g_gemv_impl == 3 && pro < PRO_LAYERNORM && epi < EPI_GELU) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
 #define UA2_CASE(P, E) \

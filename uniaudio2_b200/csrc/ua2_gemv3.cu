@@ -22,6 +22,46 @@ namespace {
 
 using namespace v3dev;
 
+// Tail L2 prefetch of the following linears' weights: measured SLOWER on B200 (1421 -> 1366 / 1306 / 1246 audio tok/s for
+// 16 / 32 / 48 MB per boundary, profiles/r1_l2_prefetch_experiment.md), so the device side is compiled out by default;
+// build with -DUA2_GEMV3_TAIL_PREFETCH=1 to reproduce.
+#ifndef UA2_GEMV3_TAIL_PREFETCH
+#define UA2_GEMV3_TAIL_PREFETCH 0
+#endif
+
+// fire-and-forget L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+// One lane per warp: prefetch this CTA's share of the following linears' first rows (see PfSpec).  CTA `cta` of a grid
+// of G covers the slabs c2 = cta, cta + G, ... of each next kernel; the rows of a slab are dealt round-robin to warps.
+__device__ __forceinline__ void tail_prefetch(const GemvParams& p, int cta, int G, int warp, int nwarps) {
+  for (int j = 0; j < p.n_pf; ++j) {
+    const PfSpec& f = p.pf[j];
+    const uint32_t rbytes = (uint32_t)f.K * 4u;
+    const int rows = f.mode == 0 ? 1 : 2;
+    for (int c2 = cta; c2 < f.G; c2 += G) {
+      const int u0 = (int)(((long long)c2 * f.n_units) / f.G), u1 = (int)(((long long)(c2 + 1) * f.n_units) / f.G);
+      const int n = min(f.n, u1 - u0);
+      for (int i = warp; i < n * rows; i += nwarps) {
+        const int u = u0 + i / rows, r = i - (i / rows) * rows;
+        const float* row;
+        if (f.mode == 1) {
+          row = (r == 0 ? f.W : f.W2) + (size_t)u * f.K;
+        } else if (f.mode == 2) {
+          const int half = f.hs >> 1;
+          const int hh = u / half, ii = u - hh * half;
+          row = f.W + (size_t)(hh * f.hs + ii + r * half) * f.K;
+        } else {
+          row = f.W + (size_t)u * f.K;
+        }
+        l2_prefetch_bulk(row, rbytes);
+      }
+    }
+  }
+}
+
 template <int MT, int PRO, int EPI>
 __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p, const V3Cfg c) {
   constexpr int ROWS = RowsOf<EPI>::value;
@@ -71,11 +111,29 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
     fence_mbar_init();
     const int pre = min(total, c.stages);
     for (int t = 0; t < pre; ++t) issue(t);  // weights never depend on the producer kernel
+#if UA2_GEMV3_TAIL_PREFETCH
+    if (p.n_pf > 0 && total <= c.stages) tail_prefetch(p, cta, G, warp, nthreads >> 5);  // nothing more to issue
+#endif
   }
   __syncwarp();
   pdl_launch_dependents();
   pdl_wait();
 
+  int ps_row[MT];  // EPI_QKV: cache slot of each row, fetched with the activations instead of at the tail
+#pragma unroll
+  for (int m = 0; m < MT; ++m) ps_row[m] = (EPI == EPI_QKV && m < mcount) ? p.pos[m0 + m] : -1;
+  int b_row[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) b_row[m] = (EPI == EPI_QKV && m < mcount) ? (p.bidx_identity ? m0 + m : p.bidx[m0 + m]) : -1;
+  // EPI_RESADD: the residual element this thread will add in round 0 is fetched now, not at the tail
+  float r_pre = 0.f;
+  if (EPI == EPI_RESADD) {
+    const int n_ru0 = min(slab, ROUND_UNITS);
+    if (tid < n_ru0 * mcount) {
+      const int ul = tid / mcount, m = tid - ul * mcount;
+      r_pre = p.R[(size_t)(m0 + m) * p.ldr + (u_lo + ul)];
+    }
+  }
   stage_activations3<MT, PRO>(p, xs, red, Kp, m0, mcount, c.n_splits);  // ends with __syncthreads()
 
   float acc[ROWS][MT];
@@ -115,7 +173,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
         }
       }
       __syncwarp();
+#if UA2_GEMV3_TAIL_PREFETCH
+      if (lane == 0) {
+        if (t + c.stages < total) {
+          issue(t + c.stages);
+          // this warp's last own copy is on its way: queue the next kernels' first rows behind it
+          if (p.n_pf > 0 && t + c.stages == total - 1) tail_prefetch(p, cta, G, warp, nthreads >> 5);
+        }
+      }
+#else
       if (lane == 0 && t + c.stages < total) issue(t + c.stages);
+#endif
 #pragma unroll
       for (int rr = 0; rr < ROWS; ++rr)
         if (rr == r) {
@@ -156,7 +224,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gemv3_kernel(const GemvParams p,
       }
       int nA;
       unit_row<EPI>(p, u_lo + r_lo + ul, 0, nA);
-      epilogue_v3<EPI>(p, m0 + m, a, b, nA);
+      int ps = -1, bq = -1;
+      if (EPI == EPI_QKV) {
+#pragma unroll
+        for (int mm = 0; mm < MT; ++mm)
+          if (mm == m) {
+            ps = ps_row[mm];
+            bq = b_row[mm];
+          }
+      }
+      if (EPI == EPI_RESADD && rd == 0 && idx == tid)
+        p.Y[(size_t)(m0 + m) * p.ldy + nA] = a + r_pre;
+      else
+        epilogue_v3<EPI>(p, m0 + m, a, b, nA, ps, bq);
     }
     // no second barrier: the next round writes the other partial buffer, and a thread only reaches the barrier of
     // round rd+1 after finishing its epilogue share of round rd
@@ -179,22 +259,22 @@ int sm_count3() {
   return g_sms;
 }
 
-template <int MT, int PRO, int EPI>
-cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
-  constexpr int ROWS = RowsOf<EPI>::value;
-  auto kern = gemv3_kernel<MT, PRO, EPI>;
-  const size_t kMaxSmem = 224 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e != cudaSuccess) return e;
-    e = prefer_max_smem(kern);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  const int K = p.K;
-  const int Kp = ((K + 127) / 128) * 128;
+// Launch shape of one v3 linear (shared by the launcher and by the prefetch planner of the PRECEDING kernel, which must
+// reproduce the slab partition of the kernel it prefetches for).
+struct V3Plan {
   V3Cfg c;
+  int gy = 0, n_units = 0, nwarps = 0, m_tiles = 0, rows = 1;
+  size_t smem = 0;
+  bool ok = false;
+};
+
+V3Plan plan_v3(int MT, int epi, int M, int N, int K, int n_splits) {
+  V3Plan pl;
+  const int ROWS = (epi == EPI_QKV || epi == EPI_SWIGLU) ? 2 : 1;
+  pl.rows = ROWS;
+  const size_t kMaxSmem = 224 * 1024;
+  const int Kp = ((K + 127) / 128) * 128;
+  V3Cfg& c = pl.c;
   // K slices of ~1024 floats: every bulk copy is >= 4 KB, the size at which 8-9 warps x 2 slots saturate HBM
   // (profiles/r1_microbench_hbm_streaming.txt: 4 KB copies, depth 2, 8 warps -> 7.16 TB/s; 1 KB copies -> 2.8 TB/s)
   c.nsl = (K + 1023) / 1024;
@@ -209,6 +289,7 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   }
   if (c.ngrp < 1) c.ngrp = 1;
   const int nwarps = c.nsl * c.ngrp;
+  pl.nwarps = nwarps;
   const int per = (K + c.nsl - 1) / c.nsl;
   c.SL = ((per + 127) / 128) * 128;
   c.KCW = c.SL < g_v3_kcw ? c.SL : g_v3_kcw;
@@ -222,10 +303,11 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
   if (stages > g_v3_max_stages) stages = g_v3_max_stages;
   if (stages < 2) stages = 2;
   c.stages = stages;
-  const size_t smem = xbytes + pbytes + stage_bytes * stages;
-  if (smem > kMaxSmem) return cudaErrorInvalidValue;
-  const int n_units = (ROWS == 2) ? ((EPI == EPI_SWIGLU) ? p.N : p.N / 2) : p.N;
-  const int m_tiles = (p.M + MT - 1) / MT;
+  pl.smem = xbytes + pbytes + stage_bytes * stages;
+  if (pl.smem > kMaxSmem) return pl;
+  const int n_units = (ROWS == 2) ? ((epi == EPI_SWIGLU) ? N : N / 2) : N;
+  pl.n_units = n_units;
+  pl.m_tiles = (M + MT - 1) / MT;
   // Grid size: every (CTA, group) streams ceil(units / (G * ngrp)) units, so pick the G in [SMs, SMs * ctas_per_sm] that
   // wastes the least on the remainder (e.g. 2560 QKV pairs, 2 groups: G = 256 -> exactly 5 per group instead of 4.3 -> 5
   // on 296 CTAs).  All CTAs are co-resident either way; the kernel is bound by per-warp stream latency, not by SM count.
@@ -248,15 +330,37 @@ cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) 
       }
   }
   if (gy > n_units) gy = n_units;
-  return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), smem, p, c);
+  pl.gy = gy;
+  pl.ok = true;
+  return pl;
+}
+
+int mt_of(int M, int K) {
+  const size_t rowb = (size_t)((K + 127) / 128) * 128 * 4;
+  int mt = M >= 8 ? 8 : (M >= 3 ? 4 : M);
+  while (mt > 1 && mt * rowb > 128 * 1024) mt >>= 1;
+  return mt;
+}
+
+template <int MT, int PRO, int EPI>
+cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
+  auto kern = gemv3_kernel<MT, PRO, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return e;
+    e = prefer_max_smem(kern);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const V3Plan pl = plan_v3(MT, EPI, p.M, p.N, p.K, n_splits);
+  if (!pl.ok) return cudaErrorInvalidValue;
+  return launch(lc, kern, dim3(pl.m_tiles, pl.gy), dim3(pl.nwarps * 32), pl.smem, p, pl.c);
 }
 
 template <int PRO, int EPI>
 cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
-  const size_t rowb = (size_t)((p.K + 127) / 128) * 128 * 4;
-  int mt = p.M >= 8 ? 8 : (p.M >= 3 ? 4 : p.M);
-  while (mt > 1 && mt * rowb > 128 * 1024) mt >>= 1;
-  switch (mt) {
+  switch (mt_of(p.M, p.K)) {
     case 1: return launch3_one<1, PRO, EPI>(lc, p, n_splits);
     case 2: return launch3_one<2, PRO, EPI>(lc, p, n_splits);
     case 4: return launch3_one<4, PRO, EPI>(lc, p, n_splits);
@@ -264,8 +368,50 @@ cudaError_t launch3_mt(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
   }
 }
 
+int g_v3_pf_mb = 0, g_v3_pf_idle_mb = 0;
 }  // namespace
 
+size_t gemv3_prefetch_budget(int idle_after) {
+  size_t b = (size_t)g_v3_pf_mb << 20;
+  if (idle_after) b += (size_t)g_v3_pf_idle_mb << 20;
+  return b;
+}
+void set_gemv3_prefetch_mb(int mb, int idle_mb) {
+  if (mb >= 0) g_v3_pf_mb = mb > 96 ? 96 : mb;
+  if (idle_mb >= 0) g_v3_pf_idle_mb = idle_mb > 96 ? 96 : idle_mb;
+}
+// Prefetch specs for the next linears of the frame: walk the sequence until the byte budget is spent (at most PF_MAX
+// kernels ahead).  Only decode-shaped launches (one M tile) are planned; anything else ends the walk.
+int gemv3_make_pf(const GemvSeqEntry* next, int n_next, size_t budget_bytes, PfSpec* out) {
+  int n_out = 0;
+  for (int i = 0; i < n_next && n_out < PF_MAX && budget_bytes > 0; ++i) {
+    const GemvSeqEntry& e = next[i];
+    if (e.epi > EPI_SWIGLU || e.M > 2) break;
+    const V3Plan pl = plan_v3(mt_of(e.M, e.K), e.epi, e.M, e.N, e.K, 0);
+    if (!pl.ok || pl.m_tiles != 1) break;
+    PfSpec f;
+    f.W = e.W;
+    f.W2 = e.W2;
+    f.K = e.K;
+    f.n_units = pl.n_units;
+    f.G = pl.gy;
+    f.mode = e.epi == EPI_SWIGLU ? 1 : (e.epi == EPI_QKV ? 2 : 0);
+    f.hs = e.hs;
+    const size_t unit_bytes = (size_t)pl.rows * e.K * 4;
+    const size_t total = unit_bytes * pl.n_units;
+    const size_t want = total < budget_bytes ? total : budget_bytes;
+    int n = (int)((want + unit_bytes * pl.gy - 1) / (unit_bytes * pl.gy));
+    const int slab_max = (pl.n_units + pl.gy - 1) / pl.gy;
+    if (n > slab_max) n = slab_max;
+    if (n < 1) break;
+    f.n = n;
+    out[n_out++] = f;
+    const size_t used = (size_t)n * unit_bytes * pl.gy;
+    budget_bytes = used >= budget_bytes ? 0 : budget_bytes - used;
+    if (want < total) break;  // partial prefetch of this matrix: its own stream takes over from here
+  }
+  return n_out;
+}
 void set_gemv3_ctas_per_sm(int v) { g_v3_ctas_per_sm = v < 1 ? 1 : (v > 3 ? 3 : v); }
 void set_gemv3_balance_grid(int v) { g_v3_balance_grid = v ? 1 : 0; }
 void set_gemv3_kcw(int v) { g_v3_kcw = (v >= 128 && v <= 1024 && v % 128 == 0) ? v : 1024; }
@@ -285,6 +431,7 @@ cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams
   UA2_CASE3(PRO_RMSNORM, EPI_QKV)
   UA2_CASE3(PRO_GATHER, EPI_STORE)
   UA2_CASE3(PRO_ATTN, EPI_RESADD)
+  UA2_CASE3(PRO_ATTN_DIRECT, EPI_RESADD)
 #undef UA2_CASE3
   return cudaErrorInvalidValue;
 }

@@ -1,15 +1,35 @@
 // Kernel launch surface shared between the handle API (ua2_llm.cu) and the stand-alone operator API.
 #pragma once
+#include <vector>
 #include "ua2_common.cuh"
 
 namespace ua2 {
 
 // ---------------------------------------------------------------- skinny linear (GEMV family)
-enum : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_GATHER = 2, PRO_ATTN = 3, PRO_LAYERNORM = 4 };
+// PRO_ATTN_DIRECT: the whole single-query attention over a SHORT cache (<= ATTN_DIRECT_MAX_KEYS keys, head size 64: the
+// local decoder, model_new.py:626-643) is computed inside the proj kernel's prologue - no attention launch at all.
+enum : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_GATHER = 2, PRO_ATTN = 3, PRO_LAYERNORM = 4, PRO_ATTN_DIRECT = 5 };
+constexpr int ATTN_DIRECT_MAX_KEYS = 8;
 // EPI_GELU / EPI_SCALE_RESADD / EPI_QKV_IL serve the Moshi-family transformer layer (llm_modules/transformer.py:430-588)
 enum : int { EPI_STORE = 0, EPI_RESADD = 1, EPI_QKV = 2, EPI_SWIGLU = 3, EPI_GELU = 4, EPI_SCALE_RESADD = 5, EPI_QKV_IL = 6 };
 
 constexpr int ATTN_CHUNK = 64;  // keys per split CTA of the attention kernel
+
+// L2 prefetch of the NEXT linears' weights, issued by the tail of the current kernel (fire-and-forget
+// cp.async.bulk.prefetch.L2): the HBM pipe keeps streaming through the kernel boundary / the attention and sampler
+// kernels, and the next kernel's first ring fills hit L2.  One spec describes the first `n` units of every CTA slab of
+// a following gemv3 launch (same slab partition as that kernel computes for itself).
+struct PfSpec {
+  const float* W = nullptr;
+  const float* W2 = nullptr;  // SwiGLU second matrix
+  int K = 0;
+  int n_units = 0;  // units of the next kernel
+  int G = 0;        // its grid (CTA slabs)
+  int mode = 0;     // 0 one row per unit, 1 SwiGLU (row u of W and of W2), 2 QKV rotation pair (rows nA, nA + hs/2)
+  int hs = 0;
+  int n = 0;  // units to prefetch per slab
+};
+constexpr int PF_MAX = 3;
 
 struct GemvParams {
   // weights: W (N x K) row-major fp32 (nn.Linear layout); W2 second matrix for SwiGLU
@@ -31,6 +51,7 @@ struct GemvParams {
   int n_splits = 0;  // splits launched by the attention kernel (empty ones carry (m=-inf, l=0))
   const int32_t* pos = nullptr;   // (M) cache slot / position of each row
   const int32_t* bidx = nullptr;  // (M) batch row of each row
+  int bidx_identity = 0;          // decode frames: row m IS batch row m (kernels may skip the bidx load)
   int n_head = 0, n_groups = 0, hs = 0;
   // ---- epilogue
   float* Y = nullptr;  // STORE / RESADD / SWIGLU destination, row stride ldy
@@ -47,10 +68,33 @@ struct GemvParams {
   const float* cos = nullptr;  // (positions, hs)
   const float* sin = nullptr;
   int S_max = 0;
+  // ---- tail prefetch (filled by launch_gemv from the recorded launch sequence; see GemvSeq)
+  int n_pf = 0;
+  PfSpec pf[PF_MAX];
 };
+
+// The sequence of skinny linears of one frame, recorded on the first (eager) run of a shape and used from then on to
+// tell every launch which weights come next.  idle_after: the launches after this op that do not touch HBM much
+// (1 = attention, 2 = sampler) - the prefetch budget grows accordingly.
+struct GemvSeqEntry {
+  const float* W = nullptr;
+  const float* W2 = nullptr;
+  int N = 0, K = 0, M = 0, epi = 0, hs = 0;
+  int idle_after = 0;
+};
+struct GemvSeq {
+  std::vector<GemvSeqEntry> ops;
+  int pos = 0;
+  bool recorded = false;
+};
+void set_gemv3_prefetch_mb(int mb, int idle_mb);
+size_t gemv3_prefetch_budget(int idle_after);
+int gemv3_make_pf(const GemvSeqEntry* next, int n_next, size_t budget_bytes, PfSpec* out);
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
 cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, float* stats_ws);
 void set_gemv_impl(int v);
+int get_gemv_impl();
+int get_sgemm_min_rows();
 void set_sgemm_min_rows(int v);
 cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B,
                                  int Cin, int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out,
@@ -78,6 +122,7 @@ struct AttnParams {
   int M = 0, n_head = 0, n_groups = 0, hs = 0, S_max = 0, max_splits = 0;
   int window = 0;  // > 0: only keys with pos - j < window are visible (Moshi `context`, transformer.py:404-408)
   int n_splits_launch = 0;  // grid.x (>= splits needed by the largest pos in this launch)
+  int bidx_identity = 0;    // decode frames: row m is batch row m
 };
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p);
 cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float* y);

@@ -66,6 +66,8 @@ struct ua2_llm {
   int chain_max_splits = 0;
   bool chain_ok = false;
   // options / stats
+  bool rows_are_batch = false;  // generate_frame: activation row m belongs to batch row m (prefill flattens B x T)
+  int opt_attn_direct = 0;  // local decoder: attention inside the proj prologue (32 fewer launches; measured 1466 vs 1471 tok/s: off)
   int opt_graph = 1, opt_pdl = 1, opt_chain = 0;  // chain: measured 1184 vs 1438 tok/s for graph+PDL (profiles/r1_chain_experiment.md)
   int last_launches = 0;
   unsigned long long frame_counter = 0;
@@ -74,6 +76,7 @@ struct ua2_llm {
     int launches = 0;
   };  // an entry with exec == nullptr means "seen once, ran eagerly" (lazy kernel attributes are set by then)
   std::map<unsigned long long, GraphEntry> graphs;
+  std::map<unsigned long long, GemvSeq> seqs;  // per frame shape: the sequence of linears (tail L2 prefetch planning)
 };
 
 namespace {
@@ -98,6 +101,11 @@ bool parse_layer_key(const std::string& rest, int& layer, std::string& leaf) {
 const char* kPrefix[4] = {"backbone.", "decoder.", "audio_understanding_expert.", "audio_generation_expert."};
 
 // One transformer Block (lit_model.py:307-349) on M rows: 5 kernels.
+// the kernel just launched barely touches HBM (1 attention, 2 sampler): the preceding linear may prefetch more
+inline void mark_idle(const LaunchCtx& lc, int kind) {
+  if (lc.seq && !lc.seq->recorded && !lc.seq->ops.empty()) lc.seq->ops.back().idle_after |= kind;
+}
+
 cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x, int M, const int32_t* pos,
                       const int32_t* bidx, int n_splits) {
   const ua2_gpt_cfg& c = s.cfg;
@@ -118,6 +126,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.eps = c.norm_eps;
     p.pos = pos;
     p.bidx = bidx;
+    p.bidx_identity = h->rows_are_batch ? 1 : 0;
     p.n_head = c.n_head;
     p.n_groups = c.n_query_groups;
     p.hs = hs;
@@ -129,13 +138,16 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.S_max = s.S_max;
     if ((e = launch_gemv(lc, PRO_RMSNORM, EPI_QKV, p)) != cudaSuccess) return e;
   }
-  {  // B: split-softmax attention over the cache
+  // short caches (the local decoder's <= 8 codebook steps): attention runs inside the proj kernel's prologue
+  const bool direct = h->opt_attn_direct && s.S_max <= ATTN_DIRECT_MAX_KEYS && hs == 64 && M <= 16 && get_gemv_impl() == 3;
+  if (!direct) {  // B: split-softmax attention over the cache
     AttnParams a;
     a.q = h->qbuf;
     a.k_cache = s.kc[l];
     a.v_cache = s.vc[l];
     a.pos = pos;
     a.bidx = bidx;
+    a.bidx_identity = h->rows_are_batch ? 1 : 0;
     a.o_part = h->o_part;
     a.ml_part = h->ml_part;
     a.M = M;
@@ -146,6 +158,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     a.max_splits = h->max_splits;
     a.n_splits_launch = n_splits;
     if ((e = launch_attn(lc, a)) != cudaSuccess) return e;
+    mark_idle(lc, 1);
   }
   {  // C: combine splits -> proj -> + residual
     GemvParams p;
@@ -166,7 +179,18 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.ldy = D;
     p.R = x;
     p.ldr = D;
-    if ((e = launch_gemv(lc, PRO_ATTN, EPI_RESADD, p)) != cudaSuccess) return e;
+    if (direct) {
+      p.X = h->qbuf;
+      p.ldx = QD;
+      p.k_cache = s.kc[l];
+      p.v_cache = s.vc[l];
+      p.bidx = bidx;
+      p.n_groups = c.n_query_groups;
+      p.S_max = s.S_max;
+      if ((e = launch_gemv(lc, PRO_ATTN_DIRECT, EPI_RESADD, p)) != cudaSuccess) return e;
+    } else if ((e = launch_gemv(lc, PRO_ATTN, EPI_RESADD, p)) != cudaSuccess) {
+      return e;
+    }
   }
   {  // D: RMSNorm -> fc_1 | fc_2 -> silu * mul
     GemvParams p;
@@ -253,6 +277,7 @@ cudaError_t run_heads(ua2_llm* h, const LaunchCtx& lc, int B, int rows) {
     p.ldy = Vt;
     if ((e = launch_gemv(lc, PRO_PLAIN, EPI_STORE, p)) != cudaSuccess) return e;
     if ((e = launch_sampler(lc, h->text_logits, Vt, h->d_fs, 0, 0, nq + 1, 0, 0, B, rows)) != cudaSuccess) return e;
+    mark_idle(lc, 2);
   }
   // the sampler writes the int32 frame into a mirror buffer placed right after the audio logits; the next step's
   // projection gathers audio_embeddings[tok_{i-1} + (i-1)*V_a] (model_new.py:640-641, :662-663) straight from it
@@ -297,6 +322,7 @@ cudaError_t run_heads(ua2_llm* h, const LaunchCtx& lc, int B, int rows) {
       if ((e = launch_sampler(lc, h->audio_logits + (size_t)i * B * Va, Va, h->d_fs, 1, 1 + i, nq + 1,
                               (long long)rows * Vt + (long long)i * rows * Va, 1 + i, B, rows)) != cudaSuccess)
         return e;
+      mark_idle(lc, 2);
     }
   }
   return cudaSuccess;
@@ -840,6 +866,7 @@ int ua2_llm_prefill(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, cons
                                    cudaMemcpyDeviceToDevice, stream));
     LaunchCtx lc0 = lc;
     lc0.pdl = false;
+    h->rows_are_batch = false;
     UA2_CHECK_CUDA(launch_prefill_begin(lc0, pos, h->d_pos, h->d_bidx, M, T, row0));
     UA2_CHECK_CUDA(run_global(h, lc, M, n_splits, false));
   }
@@ -888,18 +915,31 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
   LaunchCtx lc;
   lc.stream = stream;
   lc.launch_counter = &launches;
+  h->rows_are_batch = true;
   UA2_CHECK_CUDA(launch_frame_begin(lc, tokens, mask, B * (nq + 1), h->d_tokens, h->d_mask, h->d_pos, h->d_bidx, B,
                                     (int32_t)input_pos, h->d_fs, fs));
   const int n_splits = (int)(input_pos / ATTN_CHUNK) + 1;
   lc.pdl = h->opt_pdl != 0;
+  const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |
+                                 (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull) | (h->opt_attn_direct ? 4ull : 0ull);
+  // the frame's sequence of linears: recorded by the first run of this shape, replayed (with tail prefetch specs of the
+  // following weights) by every later run / by the graph capture
+  GemvSeq& sq = h->seqs[key];
+  sq.pos = 0;
+  struct SeqDone {
+    GemvSeq& s;
+    ~SeqDone() { s.recorded = s.recorded || !s.ops.empty(); }
+  };
   if (B == 1 && h->opt_chain && h->chain_ok) {
     UA2_CHECK_CUDA(run_frame_chain(h, lc, rows));
   } else if (!h->opt_graph) {
+    lc.seq = &sq;
+    SeqDone done{sq};
     UA2_CHECK_CUDA(run_global(h, lc, B, n_splits, true));
     UA2_CHECK_CUDA(run_heads(h, lc, B, rows));
   } else {
-    const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |
-                                   (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull);
+    lc.seq = &sq;
+    SeqDone done{sq};
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
       // first use of this shape: run eagerly (also sets the lazily-initialised kernel attributes)
@@ -976,6 +1016,8 @@ int ua2_llm_set_option(ua2_llm* h, const char* name, int value) {
     h->opt_pdl = value;
   else if (n == "chain")
     h->opt_chain = value;
+  else if (n == "attn_direct")
+    h->opt_attn_direct = value ? 1 : 0;
   else
     UA2_REQUIRE(false, "unknown option " + n);
   return UA2_OK;

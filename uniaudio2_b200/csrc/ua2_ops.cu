@@ -35,6 +35,14 @@ int ua2_set_global_option(const char* name, int value) {
     set_gemv3_kcw(value);
     return UA2_OK;
   }
+  if (std::string(name) == "gemv3_prefetch_mb") {
+    set_gemv3_prefetch_mb(value, -1);
+    return UA2_OK;
+  }
+  if (std::string(name) == "gemv3_prefetch_idle_mb") {
+    set_gemv3_prefetch_mb(-1, value);
+    return UA2_OK;
+  }
   if (std::string(name) == "gemv3_budget_kb") {
     set_gemv3_budget_kb(value);
     return UA2_OK;

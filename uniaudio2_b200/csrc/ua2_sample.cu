@@ -26,6 +26,8 @@ namespace {
 constexpr int SAMPLE_THREADS = 512;
 constexpr int SLICE_CAP = 16384;  // floats of a row slice cached in shared memory per CTA (64 KB)
 constexpr int MAX_CLUSTER = 8;
+constexpr int FAST_GROUPS = SAMPLE_THREADS / 4;  // group maxima per CTA = largest k served by the candidate path
+constexpr int CAND_CAP = 1536;                   // candidate list capacity (floats + ints in static shared memory)
 
 __device__ __forceinline__ uint32_t f2key(float x) {
   const uint32_t u = __float_as_uint(x);
@@ -77,6 +79,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleArgs
   __shared__ float cl_f[4];                          // per-CTA results exchanged across the cluster
   __shared__ int cl_i[2];
   __shared__ unsigned int sel_bin, sel_k;
+  __shared__ float gmax[FAST_GROUPS];                // fast path: group maxima, candidate list
+  __shared__ float cand_v[CAND_CAP];
+  __shared__ int cand_i[CAND_CAP];
+  __shared__ int cand_n;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = SAMPLE_THREADS / 32;
@@ -112,13 +118,34 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleArgs
     if (i < forbid) x = -INFINITY;
     return x;
   };
-  for (int i = tid; i < n; i += SAMPLE_THREADS) {
-    const float x = raw(lo + i);
-    if (i < SLICE_CAP) vals[i] = x;
-  }
-  __syncthreads();
-  auto val = [&](int i) -> float { return (i < SLICE_CAP) ? vals[i] : raw(lo + i); };
-
+  // slice -> shared memory (scaled, masked), returns the thread's running maximum.  All loads of a thread are issued before
+  // their first use: a plain `for` over raw() serialises ~24-32 L2 round trips per thread (17 of the sampler's 21 us).
+  auto load_slice = [&]() -> float {
+    float lm = -INFINITY;
+    constexpr int UNR = 8;
+    const float* lrow = a.logits + (use_cfg ? (size_t)0 : (size_t)row * V) + lo;
+    for (int i0 = tid; i0 < n; i0 += SAMPLE_THREADS * UNR) {
+      float xc[UNR], xu[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = i0 + u * SAMPLE_THREADS;
+        xc[u] = i < n ? lrow[i] : 0.f;
+        xu[u] = (use_cfg && i < n) ? lrow[(size_t)V + i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = i0 + u * SAMPLE_THREADS;
+        if (i < n) {
+          float x = use_cfg ? xu[u] + (xc[u] - xu[u]) * fs.cfg_scale : xc[u];  // model_new.py:619
+          x = x / fs.temperature;
+          if (lo + i < forbid) x = -INFINITY;
+          if (i < SLICE_CAP) vals[i] = x;
+          lm = fmaxf(lm, x);
+        }
+      }
+    }
+    return lm;
+  };
   // cluster-wide all-reduce helpers (every CTA ends up with the same value)
   auto cluster_barrier = [&]() {
     if (CLUSTERED)
@@ -126,11 +153,176 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleArgs
     else
       __syncthreads();
   };
+  const float* noise = fs.noise ? fs.noise + a.noise_off + (size_t)row * V : nullptr;
+
+  // ------------------------------------------------------------------------------------------------------------------
+  // Fast path (1 < k <= FAST_GROUPS, slice cached in shared memory): candidate filtering instead of a radix select.
+  //   * every group of 4 threads keeps the maximum of its elements: FAST_GROUPS disjoint group maxima per CTA.  The k-th
+  //     largest group maximum `lb` is a lower bound of the row's k-th largest value (the k largest group maxima are k
+  //     distinct elements >= lb), and so is the largest `lb` over the CTAs of the cluster;
+  //   * the elements >= lb (typically ~1.2 k of them; all of the row's top k) are compacted into a candidate list;
+  //   * the exact k-th largest (ties kept, like `logits >= kth`) is found by rank counting inside the list, and one warp
+  //     finishes softmax(log_softmax) and argmax(p / q) over the <= CAND_CAP candidates - no more passes over V.
+  // Falls through to the generic radix path when the list overflows (heavy ties / -inf plateaus).
+  if (fs.topk > 1 && fs.topk <= FAST_GROUPS && n <= SLICE_CAP && per <= SLICE_CAP) {
+    const int k = fs.topk;
+    const float lm = load_slice();
+    float g = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, 1));
+    g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, 2));
+    if ((lane & 3) == 0) gmax[tid >> 2] = g;
+    const float wm = warp_max(g);
+    if (lane == 0) red_f[0][warp] = wm;
+    if (tid == 0) cand_n = 0;
+    __syncthreads();
+    if (tid < FAST_GROUPS) {
+      const float mine = gmax[tid];
+      int gt = 0;
+#pragma unroll 8
+      for (int j = 0; j < FAST_GROUPS; ++j) {
+        const float o = gmax[j];
+        gt += (o > mine || (o == mine && j < tid)) ? 1 : 0;
+      }
+      if (gt == k - 1) cl_f[1] = mine;  // exactly one thread: ranks are a permutation
+    }
+    if (tid == 0) {
+      float m2 = -INFINITY;
+      for (int w = 0; w < NW; ++w) m2 = fmaxf(m2, red_f[0][w]);
+      cl_f[0] = m2;
+    }
+    cluster_barrier();
+    float mx, lb;
+    if (CLUSTERED) {
+      cg::cluster_group cl = cg::this_cluster();
+      mx = -INFINITY;
+      lb = -INFINITY;
+      for (int r = 0; r < csize; ++r) {
+        mx = fmaxf(mx, *cl.map_shared_rank(&cl_f[0], r));
+        lb = fmaxf(lb, *cl.map_shared_rank(&cl_f[1], r));
+      }
+    } else {
+      mx = cl_f[0];
+      lb = cl_f[1];
+    }
+    // compact the candidates (warp-aggregated append)
+    for (int i0 = 0; i0 < n; i0 += SAMPLE_THREADS) {
+      const int i = i0 + tid;
+      const float x = i < n ? vals[i] : -INFINITY;
+      const bool c = i < n && x >= lb;
+      const unsigned m = __ballot_sync(0xffffffffu, c);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&cand_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (c && pos < CAND_CAP) {
+          cand_v[pos] = x;
+          cand_i[pos] = lo + i;
+        }
+      }
+    }
+    cluster_barrier();
+    int C = 0;
+    if (CLUSTERED) {
+      cg::cluster_group cl = cg::this_cluster();
+      int mine_off = 0;
+      for (int r = 0; r < csize; ++r) {
+        const int cr = *cl.map_shared_rank(&cand_n, r);
+        if (r == 0) mine_off = cr;  // CTA 0 appends the peers' lists behind its own
+        C += cr;
+      }
+      bool ok = C <= CAND_CAP;
+      for (int r = 0; r < csize; ++r) ok = ok && (*cl.map_shared_rank(&cand_n, r) <= CAND_CAP);
+      if (ok && crank == 0) {
+        int off = mine_off;
+        for (int r = 1; r < csize; ++r) {
+          const int cr = *cl.map_shared_rank(&cand_n, r);
+          const float* rv = cl.map_shared_rank(&cand_v[0], r);
+          const int* ri = cl.map_shared_rank(&cand_i[0], r);
+          for (int t = tid; t < cr; t += SAMPLE_THREADS) {
+            cand_v[off + t] = rv[t];
+            cand_i[off + t] = ri[t];
+          }
+          off += cr;
+        }
+      }
+      cluster_barrier();  // peers' lists have been read: they may retire
+      if (ok && crank != 0) return;
+      if (!ok) C = CAND_CAP + 1;
+    } else {
+      C = cand_n;
+    }
+    if (C <= CAND_CAP) {
+      // exact k-th largest inside the list
+      for (int t = tid; t < C; t += SAMPLE_THREADS) {
+        const float v = cand_v[t];
+        int gt = 0, ge = 0;
+        for (int j = 0; j < C; ++j) {
+          const float o = cand_v[j];
+          gt += o > v ? 1 : 0;
+          ge += o >= v ? 1 : 0;
+        }
+        if (gt < k && k <= ge) cl_f[2] = v;  // every thread that qualifies holds the same value
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const float thr = cl_f[2];
+        float z = 0.f;
+        for (int t = lane; t < C; t += 32) {
+          const float x = cand_v[t];
+          if (x >= thr) z += expf(x - mx);
+        }
+        z = warp_sum(z);
+        const float lse = logf(z);
+        const float max_ls = 0.f - lse;
+        float z2 = 0.f;
+        for (int t = lane; t < C; t += 32) {
+          const float x = cand_v[t];
+          if (x >= thr) z2 += expf(((x - mx) - lse) - max_ls);
+        }
+        z2 = warp_sum(z2);
+        float best = -1.f;
+        int best_i = 0x7fffffff;
+        for (int t = lane; t < C; t += 32) {
+          const float x = cand_v[t];
+          if (x >= thr) {
+            const int gi = cand_i[t];
+            const float p = expf(((x - mx) - lse) - max_ls) / z2;
+            const float q = noise ? noise[gi] : philox_exp1(fs.seed, fs.offset * 65536ull + a.stream_id * 1024ull + row, gi);
+            const float sc = p / q;
+            if (sc > best || (sc == best && gi < best_i)) {
+              best = sc;
+              best_i = gi;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ob > best || (ob == best && oi < best_i)) {
+            best = ob;
+            best_i = oi;
+          }
+        }
+        if (lane == 0) {
+          if (use_cfg) {
+            for (int b = 0; b < fs.B; ++b) fs.out[(size_t)b * a.out_ld + a.out_col] = best_i;  // .repeat(2,1), model_new.py:621
+          } else {
+            fs.out[(size_t)row * a.out_ld + a.out_col] = best_i;
+          }
+        }
+      }
+      return;
+    }
+    __syncthreads();  // overflow: generic path below (re-reads the row)
+  }
+
+  const float lm_generic = load_slice();
+  __syncthreads();
+  auto val = [&](int i) -> float { return (i < SLICE_CAP) ? vals[i] : raw(lo + i); };
 
   // ---- 1. max
-  float mx = -INFINITY;
-  for (int i = tid; i < n; i += SAMPLE_THREADS) mx = fmaxf(mx, val(i));
-  mx = warp_max(mx);
+  float mx = warp_max(lm_generic);
   if (lane == 0) red_f[0][warp] = mx;
   __syncthreads();
   if (tid == 0) {
@@ -274,7 +466,6 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SampleArgs
   // ---- 5. argmax p / q  (first index wins ties)
   float best = -1.f;
   int best_i = 0x7fffffff;
-  const float* noise = fs.noise ? fs.noise + a.noise_off + (size_t)row * V : nullptr;
   for (int i = tid; i < n; i += SAMPLE_THREADS) {
     const float x = val(i);
     if (f2key(x) >= thr_key) {
