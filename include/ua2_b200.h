@@ -39,6 +39,10 @@ const char* ua2_version(void);
  * "gemv3_ctas_per_sm" (1..3, default 2), "gemv3_max_stages" (2..6, default 3), "gemv3_kcw" (floats per bulk copy, default 1024),
  * "gemv3_budget_kb" (shared memory per decode CTA, default 110), "gemv3_balance_grid" (0/1, default 1),
  * "sgemm_min_rows" (rows from which linears use the tiled GEMM core, default 128),
+ * "tc_gemm" (0/1, default 1 when built with the CUTLASS headers: linears with >= "tc_min_rows" (default 128) rows run as
+ * 3xTF32 tcgen05 GEMMs - fp32-class accuracy, csrc/ua2_tcgemm.cu), "tc_persistent_weights" (0/1, default 0: keep the
+ * tf32-split copy of every weight the tensor-core path has used, 12 B per parameter, instead of re-splitting per call -
+ * for batched decode frames, e.g. tc_min_rows = 16 with batch 32),
  * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with
  * -DUA2_GEMV3_TAIL_PREFETCH=1 - measured slower, see profiles/r1_l2_prefetch_experiment.md) */
 int ua2_set_global_option(const char* name, int value);

@@ -19,6 +19,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+TC_DEFAULT = 1  # library default of the global option tc_gemm (builds with the CUTLASS headers)
 PF_DEFAULT = (0, 0)  # library defaults of gemv3_prefetch_mb / gemv3_prefetch_idle_mb
 
 
@@ -80,6 +81,7 @@ def test_fresh_inputs_vs_oracle_long_context(models):
     cfg = copy.deepcopy(cfg0)
     cfg.max_seq_length = 320
     m = build_product_model(cfg, sd, "cuda", 2, max_seq=320)
+    m.set_option("prefill_chunk_rows", 256)  # the 300-row prompt below is prefilled in two passes
     orc = O.Stage3Oracle(cfg, sd)
     orc.setup_caches(2)
     for (kind, B, S, nf, topk, temp) in (("mixed", 2, 140, 6, 1, 1.0), ("text", 1, 300, 4, 8, 0.9)):
@@ -202,8 +204,22 @@ def test_batch32_caption_config():
     m = build_product_model(cfg, sd, "cuda", 32)
     orc = O.Stage3Oracle(cfg, sd)
     orc.setup_caches(32)
-    for (B, S, nf) in ((32, 21, 4), (11, 13, 3)):
-        o = run_case(orc, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, False, explicit_noise=True)
-        r = run_case(m, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, True, device="cuda", explicit_noise=True)
-        assert torch.equal(r["frames"].cpu(), o["frames"])
-        assert _rel(m.debug_buffer("text_logits", B).cpu(), o["text_logits"][-1]) < REL_TOL
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    # (tc_gemm, tc_min_rows, tc_persistent_weights): skinny kernels; tensor cores for the 32-row frames with split weights
+    # re-made per call; the same with the split weights cached across calls (second frame onwards hits the cache)
+    for (tc, min_rows, persist) in ((0, 128, 0), (1, 16, 0), (1, 16, 1)):
+        _lib.check(L.ua2_set_global_option(b"tc_gemm", tc))
+        _lib.check(L.ua2_set_global_option(b"tc_min_rows", min_rows))
+        _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", persist))
+        try:
+            for (B, S, nf) in ((32, 21, 4), (11, 13, 3)):
+                o = run_case(orc, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, False, explicit_noise=True)
+                r = run_case(m, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, True, device="cuda", explicit_noise=True)
+                assert torch.equal(r["frames"].cpu(), o["frames"]), (tc, min_rows, persist, B)
+                assert _rel(m.debug_buffer("text_logits", B).cpu(), o["text_logits"][-1]) < REL_TOL
+        finally:
+            _lib.check(L.ua2_set_global_option(b"tc_gemm", TC_DEFAULT))
+            _lib.check(L.ua2_set_global_option(b"tc_min_rows", 128))
+            _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", 0))

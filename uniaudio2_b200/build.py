@@ -18,6 +18,24 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
+def _cutlass_include():
+    """CUTLASS / CuTe header tree vendored in the image (site-packages/flashinfer/data/cutlass); None if absent."""
+    cands = [os.environ.get("UA2_CUTLASS_DIR", "")]
+    for p in sys.path:
+        cands.append(os.path.join(p, "flashinfer", "data", "cutlass"))
+        cands.append(os.path.join(p, "tilelang", "3rdparty", "cutlass"))
+    for c in cands:
+        if c and os.path.exists(os.path.join(c, "include", "cutlass", "gemm", "collective", "collective_builder.hpp")):
+            return c
+    return None
+
+
+CUTLASS = _cutlass_include()
+# the tensor-core GEMM translation unit uses the CUTLASS collective builders when the headers exist (else a stub)
+EXTRA = {"ua2_tcgemm.cu": (["-DUA2_HAVE_CUTLASS", "--expt-relaxed-constexpr", "-diag-suppress", "20012", "-I", os.path.join(CUTLASS, "include"),
+                             "-I", os.path.join(CUTLASS, "tools", "util", "include")] if CUTLASS else [])}
+
+
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -36,10 +54,10 @@ def _compile(src, hdig, verbose):
     os.makedirs(OBJ, exist_ok=True)
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
     stamp = obj + ".stamp"
-    dig = hashlib.sha1(open(src, "rb").read() + hdig.encode()).hexdigest()
+    dig = hashlib.sha1(open(src, "rb").read() + hdig.encode() + " ".join(EXTRA.get(os.path.basename(src), [])).encode()).hexdigest()
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA.get(os.path.basename(src), []) + ["-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -504,10 +504,12 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
   const GemvParams& p = with_prefetch(lc, epi, p_in, p_tmp);
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.K & 3) || (epi != EPI_SWIGLU && (p.N & 1))) return cudaErrorInvalidValue;
   // many rows: 128 x 128 register-tiled fp32 GEMM (each weight element reused 128x) instead of re-streaming W per 8 rows
-  if (p.M >= g_sgemm_min_rows && p.ws != nullptr && pro != PRO_ATTN_DIRECT) {
+  const bool tc_on = get_tc_gemm() && p.tc != nullptr && p.M >= get_tc_min_rows();
+  if ((p.M >= g_sgemm_min_rows || tc_on) && p.ws != nullptr && pro != PRO_ATTN_DIRECT) {
     GemvParams q = p;
     int pro2 = pro;
-    size_t need = 2 * (size_t)p.M;
+    const size_t stats_floats = ((2 * (size_t)p.M + 3) / 4) * 4;  // keeps the combine buffer behind it 16-byte aligned (odd M)
+    size_t need = stats_floats;
     bool ok = true;
     if (pro == PRO_ATTN) {
       need += (size_t)p.M * p.K;
@@ -521,9 +523,9 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
         a.hs = p.hs;
         a.max_splits = p.max_splits;
         a.n_splits_launch = p.n_splits;
-        cudaError_t e = launch_attn_combine(lc, a, p.ws + 2 * (size_t)p.M);
+        cudaError_t e = launch_attn_combine(lc, a, p.ws + stats_floats);
         if (e != cudaSuccess) return e;
-        q.X = p.ws + 2 * (size_t)p.M;
+        q.X = p.ws + stats_floats;
         q.ldx = p.K;
         pro2 = PRO_PLAIN;
       } else {
@@ -533,9 +535,15 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
       ok = false;
     }
     if (ok) {
-      cudaError_t e = launch_sgemm_linear(lc, pro2, epi, q, p.ws);
-      if (e != cudaErrorNotSupported) return e;
-      if (pro == PRO_ATTN) return cudaErrorInvalidValue;  // combine already consumed; should not happen (instances exist)
+      if (tc_on) {  // tcgen05 3xTF32 path (ua2_tcgemm.cu); unsupported combinations fall through
+        cudaError_t et = launch_tc_linear(lc, pro2, epi, q);
+        if (et != cudaErrorNotSupported) return et;
+      }
+      if (p.M >= g_sgemm_min_rows) {
+        cudaError_t e = launch_sgemm_linear(lc, pro2, epi, q, p.ws);
+        if (e != cudaErrorNotSupported) return e;
+      }
+      // otherwise: the skinny path below, from the original operands (a combined attention tile in scratch is simply unused)
     }
   }
   if (pro == PRO_ATTN_DIRECT) {

@@ -31,6 +31,25 @@ struct PfSpec {
 };
 constexpr int PF_MAX = 3;
 
+// scratch of the tensor-core path for many-row linears (ua2_tcgemm.cu): split operands and the raw product
+struct TcWeightCache;
+TcWeightCache* tc_cache_create();
+void tc_cache_destroy(TcWeightCache* c);
+size_t tc_cache_bytes(const TcWeightCache* c);
+void set_tc_persistent(int v);
+int get_tc_persistent();
+void set_tc_min_rows(int v);
+int get_tc_min_rows();
+struct TcWorkspace {
+  TcWeightCache* cache = nullptr;  // optional persistent split weights (option tc_persistent_weights)
+  float* a = nullptr;  // (M, 3K)
+  size_t a_floats = 0;
+  float* w = nullptr;  // (N_total, 3K)
+  size_t w_floats = 0;
+  float* c = nullptr;  // (M, N_total)
+  size_t c_floats = 0;
+};
+
 struct GemvParams {
   // weights: W (N x K) row-major fp32 (nn.Linear layout); W2 second matrix for SwiGLU
   const float* W = nullptr;
@@ -68,6 +87,7 @@ struct GemvParams {
   const float* cos = nullptr;  // (positions, hs)
   const float* sin = nullptr;
   int S_max = 0;
+  const TcWorkspace* tc = nullptr;  // optional: enables the tcgen05 3xTF32 path for M >= sgemm_min_rows
   // ---- tail prefetch (filled by launch_gemv from the recorded launch sequence; see GemvSeq)
   int n_pf = 0;
   PfSpec pf[PF_MAX];
@@ -92,6 +112,10 @@ size_t gemv3_prefetch_budget(int idle_after);
 int gemv3_make_pf(const GemvSeqEntry* next, int n_next, size_t budget_bytes, PfSpec* out);
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
 cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, float* stats_ws);
+cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
+void set_tc_gemm(int v);
+int get_tc_gemm();
+bool tc_gemm_available();
 void set_gemv_impl(int v);
 int get_gemv_impl();
 int get_sgemm_min_rows();

@@ -66,6 +66,8 @@ struct ua2_llm {
   int chain_max_splits = 0;
   bool chain_ok = false;
   // options / stats
+  TcWorkspace tcws;        // scratch of the tcgen05 3xTF32 path (many-row linears of forward_prefix)
+  int opt_chunk_rows = 0;  // prefill rows per pass (0 = M_cap)
   bool rows_are_batch = false;  // generate_frame: activation row m belongs to batch row m (prefill flattens B x T)
   int opt_attn_direct = 0;  // local decoder: attention inside the proj prologue (32 fewer launches; measured 1466 vs 1471 tok/s: off)
   int opt_graph = 1, opt_pdl = 1, opt_chain = 0;  // chain: measured 1184 vs 1438 tok/s for graph+PDL (profiles/r1_chain_experiment.md)
@@ -120,6 +122,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.M = M;
     p.ws = h->sg_ws;
     p.ws_floats = h->sg_ws_floats;
+    p.tc = h->tcws.a ? &h->tcws : nullptr;
     p.X = x;
     p.ldx = D;
     p.norm_w = w.norm1;
@@ -168,6 +171,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.M = M;
     p.ws = h->sg_ws;
     p.ws_floats = h->sg_ws_floats;
+    p.tc = h->tcws.a ? &h->tcws : nullptr;
     p.o_part = h->o_part;
     p.ml_part = h->ml_part;
     p.max_splits = h->max_splits;
@@ -201,6 +205,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.M = M;
     p.ws = h->sg_ws;
     p.ws_floats = h->sg_ws_floats;
+    p.tc = h->tcws.a ? &h->tcws : nullptr;
     p.X = x;
     p.ldx = D;
     p.norm_w = w.norm2;
@@ -217,6 +222,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     p.M = M;
     p.ws = h->sg_ws;
     p.ws_floats = h->sg_ws_floats;
+    p.tc = h->tcws.a ? &h->tcws : nullptr;
     p.X = h->hmlp;
     p.ldx = c.intermediate_size;
     p.Y = x;
@@ -275,6 +281,9 @@ cudaError_t run_heads(ua2_llm* h, const LaunchCtx& lc, int B, int rows) {
     p.ldx = D;
     p.Y = h->text_logits;
     p.ldy = Vt;
+    p.ws = h->sg_ws;
+    p.ws_floats = h->sg_ws_floats;
+    p.tc = h->tcws.a ? &h->tcws : nullptr;
     if ((e = launch_gemv(lc, PRO_PLAIN, EPI_STORE, p)) != cudaSuccess) return e;
     if ((e = launch_sampler(lc, h->text_logits, Vt, h->d_fs, 0, 0, nq + 1, 0, 0, B, rows)) != cudaSuccess) return e;
     mark_idle(lc, 2);
@@ -291,6 +300,9 @@ cudaError_t run_heads(ua2_llm* h, const LaunchCtx& lc, int B, int rows) {
       p.M = B;
       p.Y = h->dec_x;
       p.ldy = d;
+      p.ws = h->sg_ws;
+      p.ws_floats = h->sg_ws_floats;
+      p.tc = h->tcws.a ? &h->tcws : nullptr;
       if (i == 0) {
         p.X = h->h_final;
         p.ldx = D;
@@ -318,6 +330,9 @@ cudaError_t run_heads(ua2_llm* h, const LaunchCtx& lc, int B, int rows) {
       p.eps = dec.cfg.norm_eps;
       p.Y = h->audio_logits + (size_t)i * B * Va;
       p.ldy = Va;
+      p.ws = h->sg_ws;
+      p.ws_floats = h->sg_ws_floats;
+      p.tc = h->tcws.a ? &h->tcws : nullptr;
       if ((e = launch_gemv(lc, PRO_RMSNORM, EPI_STORE, p)) != cudaSuccess) return e;
       if ((e = launch_sampler(lc, h->audio_logits + (size_t)i * B * Va, Va, h->d_fs, 1, 1 + i, nq + 1,
                               (long long)rows * Vt + (long long)i * rows * Va, 1 + i, B, rows)) != cudaSuccess)
@@ -641,6 +656,7 @@ int ua2_llm_destroy(ua2_llm* h) {
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->owned) cudaFree(p);
+  tc_cache_destroy(h->tcws.cache);
   delete h;
   return UA2_OK;
 }
@@ -752,7 +768,7 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   }
   const int B = max_batch_size, nq = h->cfg.num_codebooks, D = h->cfg.backbone.n_embd, d = h->cfg.decoder.n_embd;
   h->B_max = B;
-  h->M_cap = B > 256 ? B : 256;
+  h->M_cap = B > 1024 ? B : 1024;  // prefill rows per pass: large enough for the tiled / tensor-core GEMMs to fill the GPU
   h->max_splits = (h->cfg.max_seq_length + ATTN_CHUNK - 1) / ATTN_CHUNK;
   const int Mc = h->M_cap;
   int rc;
@@ -790,8 +806,27 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   if ((rc = alloc(h, (void**)&h->h_final, (size_t)Mc * D * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->qbuf, (size_t)Mc * max_qd * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->hmlp, (size_t)Mc * max_inter * 4))) return rc;
-  h->sg_ws_floats = (size_t)Mc * (2 + max_qd);  // tiled-GEMM scratch: row statistics + attention combine
+  h->sg_ws_floats = (size_t)Mc * (2 + max_qd) + 4;  // tiled-GEMM scratch: row statistics + attention combine
   if ((rc = alloc(h, (void**)&h->sg_ws, h->sg_ws_floats * 4))) return rc;
+  if (tc_gemm_available()) {
+    size_t kmax = 0, wmax = 0, nmax = 0;
+    for (int si = 0; si < 4; ++si) {
+      const ua2_gpt_cfg& c = h->st[si].cfg;
+      const size_t Dm = c.n_embd, QD = (size_t)c.n_head * c.head_size, QKV = (size_t)(c.n_head + 2 * c.n_query_groups) * c.head_size,
+                   F = c.intermediate_size;
+      kmax = std::max({kmax, Dm, QD, F});
+      wmax = std::max({wmax, QKV * 3 * Dm, Dm * 3 * QD, 2 * F * 3 * Dm, Dm * 3 * F});
+      nmax = std::max({nmax, QKV, Dm, 2 * F});
+    }
+    h->tcws.a_floats = (size_t)Mc * 3 * kmax;
+    h->tcws.w_floats = wmax;
+    const size_t nheads = std::max({nmax, (size_t)h->cfg.text_vocab, (size_t)h->cfg.audio_vocab});
+    h->tcws.c_floats = std::max((size_t)Mc * nmax, (size_t)B * nheads);  // prefill passes never run the heads; frames have M <= B
+    h->tcws.cache = tc_cache_create();
+    if ((rc = alloc(h, (void**)&h->tcws.a, h->tcws.a_floats * 4))) return rc;
+    if ((rc = alloc(h, (void**)&h->tcws.w, h->tcws.w_floats * 4))) return rc;
+    if ((rc = alloc(h, (void**)&h->tcws.c, h->tcws.c_floats * 4))) return rc;
+  }
   const size_t chain_splits = (h->cfg.max_seq_length + CHAIN_ATTN_CHUNK - 1) / CHAIN_ATTN_CHUNK;
   const size_t opart_floats = std::max((size_t)Mc * max_heads_hs * h->max_splits, (size_t)max_heads_hs * chain_splits);
   if ((rc = alloc(h, (void**)&h->o_part, opart_floats * 4))) return rc;
@@ -858,8 +893,13 @@ int ua2_llm_prefill(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, cons
   const int n_splits = max_pos < 0 ? h->max_splits : (int)(max_pos / ATTN_CHUNK) + 1;
   // rows are processed in chunks of <= M_cap, t-major inside each batch row, so causality is preserved:
   // a chunk appends all of its K/V (kernel A) before its own attention (kernel B) runs.
-  for (int row0 = 0; row0 < Mtot; row0 += h->M_cap) {
-    const int M = std::min(h->M_cap, Mtot - row0);
+  int chunk = (h->opt_chunk_rows > 0 && h->opt_chunk_rows < h->M_cap) ? h->opt_chunk_rows : h->M_cap;
+  if (h->opt_chunk_rows <= 0 && Mtot > chunk) {  // equal passes instead of a short tail pass that would fall off the GEMM paths
+    const int n_pass = (Mtot + chunk - 1) / chunk;
+    chunk = std::min(chunk, ((Mtot + n_pass - 1) / n_pass + 7) / 8 * 8);
+  }
+  for (int row0 = 0; row0 < Mtot; row0 += chunk) {
+    const int M = std::min(chunk, Mtot - row0);
     UA2_CHECK_CUDA(cudaMemcpyAsync(h->d_tokens, tokens + (size_t)row0 * (nq + 1), (size_t)M * (nq + 1) * 8,
                                    cudaMemcpyDeviceToDevice, stream));
     UA2_CHECK_CUDA(cudaMemcpyAsync(h->d_mask, mask + (size_t)row0 * (nq + 1), (size_t)M * (nq + 1),
@@ -921,7 +961,8 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
   const int n_splits = (int)(input_pos / ATTN_CHUNK) + 1;
   lc.pdl = h->opt_pdl != 0;
   const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |
-                                 (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull) | (h->opt_attn_direct ? 4ull : 0ull);
+                                 (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull) | (h->opt_attn_direct ? 4ull : 0ull) |
+                                 ((get_tc_gemm() && B >= get_tc_min_rows()) ? 8ull : 0ull) | (get_tc_persistent() ? 16ull : 0ull);
   // the frame's sequence of linears: recorded by the first run of this shape, replayed (with tail prefetch specs of the
   // following weights) by every later run / by the graph capture
   GemvSeq& sq = h->seqs[key];
@@ -1016,6 +1057,8 @@ int ua2_llm_set_option(ua2_llm* h, const char* name, int value) {
     h->opt_pdl = value;
   else if (n == "chain")
     h->opt_chain = value;
+  else if (n == "prefill_chunk_rows")
+    h->opt_chunk_rows = value;
   else if (n == "attn_direct")
     h->opt_attn_direct = value ? 1 : 0;
   else

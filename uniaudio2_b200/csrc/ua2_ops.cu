@@ -35,6 +35,19 @@ int ua2_set_global_option(const char* name, int value) {
     set_gemv3_kcw(value);
     return UA2_OK;
   }
+  if (std::string(name) == "tc_gemm") {
+    UA2_REQUIRE(!value || tc_gemm_available(), "library was built without the CUTLASS headers: no tensor-core path");
+    set_tc_gemm(value);
+    return UA2_OK;
+  }
+  if (std::string(name) == "tc_persistent_weights") {
+    set_tc_persistent(value);
+    return UA2_OK;
+  }
+  if (std::string(name) == "tc_min_rows") {
+    set_tc_min_rows(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "gemv3_prefetch_mb") {
     set_gemv3_prefetch_mb(value, -1);
     return UA2_OK;
