@@ -229,20 +229,39 @@ def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
         orc.forward_prefix(tokens[:, :-1], mask, pos[:, :-1])
         t_prefill = time.perf_counter() - t0
         curr_tokens, curr_mask = tokens[:, -1:], mask[:, -1:]
-        times = []
-        for f in range(n_frames + 1):
+        audio_mask = torch.cat([torch.ones(1, 1, NQ, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1)
+        f = 0
+
+        def one_frame():
+            nonlocal curr_tokens, curr_mask, f
             t0 = time.perf_counter()
             s = orc.generate_frame(curr_tokens, curr_mask, torch.tensor([S - 1 + f]), S + f, TEMPERATURE, TOPK, 0)
-            times.append(time.perf_counter() - t0)
+            dt = time.perf_counter() - t0
             sl = s.long()
             curr_tokens = torch.cat([sl[:, 1:], sl[:, 0:1]], dim=-1).unsqueeze(1)
-            curr_mask = torch.cat([torch.ones(1, 1, NQ, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1)
+            curr_mask = audio_mask
+            f += 1
+            return dt
+
+        times = [one_frame()]  # warm-up
+        # the frame is a memory-bound GEMV chain: more threads than memory channels can be slower, so give the CPU arm the
+        # thread count it runs fastest with (one frame per candidate), then time n_frames with it
+        tried = {}
+        if threads is None:
+            full = torch.get_num_threads()
+            for n in sorted({full, max(1, full // 2), max(1, full // 4), min(full, 16), min(full, 8)}, reverse=True):
+                torch.set_num_threads(n)
+                one_frame()
+                tried[n] = round(one_frame() * 1e3, 1)
+            torch.set_num_threads(min(tried, key=tried.get))
+        for _ in range(n_frames):
+            times.append(one_frame())
     frame_t = sum(times[1:]) / len(times[1:])  # first frame = warm-up
     est = t_prefill + N_FRAMES * frame_t
     return {"value": round(NQ * N_FRAMES / est, 2), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"1 prefill({S - 1} pos, {t_prefill:.2f}s) + {n_frames} frames ({frame_t * 1e3:.0f} ms/frame, 1 warm-up frame discarded); "
                       f"utterance extrapolated to prefill + {N_FRAMES} frames = {est:.1f}s", "frame_ms": round(frame_t * 1e3, 1),
-            "prefill_s": round(t_prefill, 3)}, est
+            "prefill_s": round(t_prefill, 3), "threads_tried_ms_per_frame": tried}, est
 
 
 def bench_codec(dev, batch=16, clip_s=10.0, reps=3, cpu=True):
@@ -329,6 +348,7 @@ def main():
     ap.add_argument("--v3-kcw", type=int, default=0)
     ap.add_argument("--v3-balance", type=int, default=-1)
     ap.add_argument("--v3-budget", type=int, default=0)
+    ap.add_argument("--chain", type=int, default=-1, help="1: persistent multi-op chain kernels for B = 1 frames (library default 0)")
     ap.add_argument("--attn-direct", type=int, default=-1, help="local-decoder attention inside the proj prologue (library default 1)")
     ap.add_argument("--pf-mb", type=int, default=-1, help="tail L2 prefetch budget per linear, MB (-1: library default)")
     ap.add_argument("--pf-idle-mb", type=int, default=-1, help="extra prefetch budget before attention / sampler kernels, MB")
@@ -410,6 +430,8 @@ def main():
         model.set_option("pdl", int(args.pdl))
         if args.attn_direct >= 0:
             model.set_option("attn_direct", int(args.attn_direct))
+        if args.chain >= 0:
+            model.set_option("chain", int(args.chain))
         task_prompt, text = synthetic_prompt(rank)
         tokens, mask = gen.prepare_tts_task(task_prompt, text)
         assert tokens.size(0) == PROMPT_LEN

@@ -129,7 +129,8 @@ __device__ __forceinline__ void pump(Ring& rg, const ChainOp* cur, const Geom* g
 
 template <int PRO, int EPI>
 __device__ __forceinline__ void run_gemv(const ChainOp& op, const Geom& g, float* xs, float* part, float* ring, uint64_t* bars,
-                                         float (*red)[MAXW_RED], Ring& rg, const ChainOp* nxt, const Geom* gn) {
+                                         float (*red)[MAXW_RED], Ring& rg, const ChainOp* nxt, const Geom* gn,
+                                         unsigned long long* pri) {
   constexpr int ROWS = RowsOf<EPI>::value;
   constexpr int MT = 1;
   const GemvParams& p = op.g;
@@ -140,6 +141,7 @@ __device__ __forceinline__ void run_gemv(const ChainOp& op, const Geom& g, float
   const uint32_t base = rg.consumed;  // every chunk of earlier ops has been consumed
   pump(rg, &op, &g, base, nxt, gn, ring, bars, lane);
   stage_activations3<MT, PRO>(p, xs, red, Kp, 0, 1, n_splits);  // ends with __syncthreads()
+  if (pri) pri[1] = clock64();
 
   float acc[ROWS];
 #pragma unroll
@@ -188,6 +190,7 @@ __device__ __forceinline__ void run_gemv(const ChainOp& op, const Geom& g, float
       }
       ++t;
     }
+    if (pri && rd == n_rounds - 1) pri[2] = clock64();
     __syncthreads();
     const int n_ru = r_hi - r_lo;
     for (int ul = tid; ul < n_ru; ul += CW * 32) {
@@ -333,7 +336,9 @@ __device__ __forceinline__ void run_attn_item(const AttnParams& p, int split, in
   asm volatile("bar.sync 1, 128;" ::: "memory");  // smem reusable by the next item
 }
 
-__global__ void __launch_bounds__(CW * 32, 2) chain_kernel(const ChainOp* __restrict__ ops, int n_ops, unsigned* sync_ctr) {
+// prof (nullable): per op, for CTA 0 and CTA G/2: clock64 at {op start, prologue done, weights consumed, op done, barrier passed}
+__global__ void __launch_bounds__(CW * 32, 2) chain_kernel(const ChainOp* __restrict__ ops, int n_ops, unsigned* sync_ctr,
+                                                           unsigned long long* prof) {
   extern __shared__ __align__(128) float smem[];
   __shared__ float red[8][MAXW_RED];
   __shared__ __align__(8) uint64_t bars[CW][CST];
@@ -351,6 +356,8 @@ __global__ void __launch_bounds__(CW * 32, 2) chain_kernel(const ChainOp* __rest
     fence_mbar_init();
   }
   __syncthreads();
+  unsigned long long* pr = nullptr;  // this thread's profile row base (thread 0 of the two sampled CTAs)
+  if (prof != nullptr && tid == 0 && (cta == 0 || cta == G / 2)) pr = prof + (size_t)(cta == 0 ? 0 : 1) * CHAIN_PROF_OPS * 5;
   Ring rg{0u, 0u};
   uint32_t aphase = 0;  // completed phases of the attention staging barrier
   unsigned arrivals = 0;
@@ -367,13 +374,15 @@ __global__ void __launch_bounds__(CW * 32, 2) chain_kernel(const ChainOp* __rest
 
   for (int i = 0; i < n_ops; ++i) {
     const ChainOp& op = ops[i];
+    unsigned long long* pri = (pr != nullptr && i < CHAIN_PROF_OPS) ? pr + (size_t)i * 5 : nullptr;
+    if (pri) pri[0] = clock64();
     if (op.type == OP_GEMV) {
       const Geom g = make_geom(op, cta, G, warp);
       const ChainOp* nxt = op.next_gemv >= 0 ? &ops[op.next_gemv] : nullptr;
       Geom gn;
       if (nxt) gn = make_geom(*nxt, cta, G, warp);
 #define UA2_RUN(P, E) \
-  if (op.pro == P && op.epi == E) run_gemv<P, E>(op, g, xs, part, ring, bars[warp], red, rg, nxt, nxt ? &gn : nullptr);
+  if (op.pro == P && op.epi == E) run_gemv<P, E>(op, g, xs, part, ring, bars[warp], red, rg, nxt, nxt ? &gn : nullptr, pri);
       UA2_RUN(PRO_RMSNORM, EPI_QKV)
       else UA2_RUN(PRO_ATTN, EPI_RESADD)
       else UA2_RUN(PRO_RMSNORM, EPI_SWIGLU)
@@ -451,7 +460,9 @@ __global__ void __launch_bounds__(CW * 32, 2) chain_kernel(const ChainOp* __rest
       }
     }
     arrivals += (unsigned)G;
+    if (pri) pri[3] = clock64();
     if (i + 1 < n_ops) grid_barrier(&sync_ctr[0], arrivals);
+    if (pri) pri[4] = clock64();
   }
   // leave the counters at zero for the next launch: the last CTA to get here resets them
   __syncthreads();
@@ -489,7 +500,8 @@ void chain_cfg_for(int K, V3Cfg_public* out) {
   out->n_splits = 0;
 }
 
-cudaError_t launch_chain(cudaStream_t stream, const ChainOp* d_ops, int n_ops, unsigned* d_sync, int n_ctas) {
+cudaError_t launch_chain(cudaStream_t stream, const ChainOp* d_ops, int n_ops, unsigned* d_sync, int n_ctas,
+                         unsigned long long* d_prof) {
   static bool once = false;
   const size_t smem = chain_smem_bytes();
   if (!once) {
@@ -508,7 +520,7 @@ cudaError_t launch_chain(cudaStream_t stream, const ChainOp* d_ops, int n_ops, u
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, chain_kernel, d_ops, n_ops, d_sync);
+  return cudaLaunchKernelEx(&cfg, chain_kernel, d_ops, n_ops, d_sync, d_prof);
 }
 
 int chain_max_ctas() {

@@ -37,7 +37,9 @@ struct ChainOp {
 
 size_t chain_smem_bytes();
 void chain_cfg_for(int K, V3Cfg_public* out);
-cudaError_t launch_chain(cudaStream_t stream, const ChainOp* d_ops, int n_ops, unsigned* d_sync, int n_ctas);
+constexpr int CHAIN_PROF_OPS = 512;  // ops per launch the optional profile buffer covers (2 CTAs x CHAIN_PROF_OPS x 5 clocks)
+cudaError_t launch_chain(cudaStream_t stream, const ChainOp* d_ops, int n_ops, unsigned* d_sync, int n_ctas,
+                         unsigned long long* d_prof = nullptr);
 int chain_max_ctas();
 
 }  // namespace ua2

@@ -62,6 +62,7 @@ struct ua2_llm {
   std::vector<ChainOp*> d_ops_local;
   std::vector<int> n_ops_local;
   unsigned* d_chain_sync = nullptr;
+  unsigned long long* d_chain_prof = nullptr;  // option chain_profile: clocks of the GLOBAL chain's ops (dev tool)
   int chain_ctas = 0;
   int chain_max_splits = 0;
   bool chain_ok = false;
@@ -597,7 +598,8 @@ cudaError_t run_frame_chain(ua2_llm* h, const LaunchCtx& lc, int rows) {
   cudaError_t e;
   LaunchCtx ls = lc;
   ls.pdl = false;
-  if ((e = launch_chain(lc.stream, h->d_ops_global, h->n_ops_global, h->d_chain_sync, h->chain_ctas)) != cudaSuccess) return e;
+  if ((e = launch_chain(lc.stream, h->d_ops_global, h->n_ops_global, h->d_chain_sync, h->chain_ctas, h->d_chain_prof)) != cudaSuccess)
+    return e;
   if (lc.launch_counter) ++*lc.launch_counter;
   if ((e = launch_sampler(ls, h->text_logits, Vt, h->d_fs, 0, 0, nq + 1, 0, 0, 1, rows)) != cudaSuccess) return e;
   for (int i = 0; i < nq; ++i) {
@@ -1042,6 +1044,10 @@ int ua2_llm_get_buffer(ua2_llm* h, const char* name, float** ptr, int64_t* numel
   } else if (n == "audio_logits") {
     *ptr = h->audio_logits;
     *numel = h->audio_logits_numel;
+  } else if (n == "chain_prof") {  // 2 x CHAIN_PROF_OPS x 5 uint64 clocks, exposed as 2x as many 4-byte words
+    UA2_REQUIRE(h->d_chain_prof != nullptr, "set_option(\"chain_profile\", 1) first");
+    *ptr = reinterpret_cast<float*>(h->d_chain_prof);
+    *numel = (int64_t)2 * CHAIN_PROF_OPS * 5 * 2;
   } else {
     UA2_REQUIRE(false, "unknown buffer " + n);
   }
@@ -1057,7 +1063,15 @@ int ua2_llm_set_option(ua2_llm* h, const char* name, int value) {
     h->opt_pdl = value;
   else if (n == "chain")
     h->opt_chain = value;
-  else if (n == "prefill_chunk_rows")
+  else if (n == "chain_profile") {
+    if (value && h->d_chain_prof == nullptr) {
+      void* p = nullptr;
+      UA2_CHECK_CUDA(cudaMalloc(&p, (size_t)2 * CHAIN_PROF_OPS * 5 * 8));
+      UA2_CHECK_CUDA(cudaMemset(p, 0, (size_t)2 * CHAIN_PROF_OPS * 5 * 8));
+      h->owned.push_back(p);
+      h->d_chain_prof = (unsigned long long*)p;
+    }
+  } else if (n == "prefill_chunk_rows")
     h->opt_chunk_rows = value;
   else if (n == "attn_direct")
     h->opt_attn_direct = value ? 1 : 0;

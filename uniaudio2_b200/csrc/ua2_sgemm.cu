@@ -55,13 +55,18 @@ __global__ void row_stats_kernel(const float* __restrict__ x, int ldx, int M, in
   }
 }
 
-template <int PRO, int EPI>
+// H = 2: 128 x 128 tile, 8 x 8 register tile per thread (two 4-wide halves per dimension);  H = 1: 64 x 64 tile, 4 x 4 per thread,
+// used when the 128-tile grid would leave most SMs idle (e.g. the codec transformer: 2000 rows x 512 outputs = 64 CTAs).
+// Every output element is the same k-ordered fp32 FMA chain in both shapes, so the results are bit-identical.
+template <int PRO, int EPI, int H>
 __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_linear_kernel(const GemvParams p, const float* __restrict__ stats) {
-  __shared__ __align__(16) float As[2][BK][BM + PADM];
-  __shared__ __align__(16) float Bs[2][BK][BN + PADM];
+  constexpr int TBM = 64 * H, TBN = 64 * H, R = 4 * H;  // tile and per-thread register tile
+  constexpr int LK = 4 * H;                             // consecutive k one thread stages per operand row and k-tile
+  __shared__ __align__(16) float As[2][BK][TBM + PADM];
+  __shared__ __align__(16) float Bs[2][BK][TBN + PADM];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;  // n0 in n' space (pairs adjacent)
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;  // n0 in n' space (pairs adjacent)
   const int K = p.K;
   const int n_units = (EPI == EPI_SWIGLU) ? p.N : (p.N >> 1);
   const int Np = 2 * n_units;
@@ -69,8 +74,8 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_linear_kernel(const GemvP
   pdl_launch_dependents();
   pdl_wait();
 
-  // ---- loader state: thread t moves 8 consecutive k (two 128-bit loads) of row t/2 of both operands per k-tile
-  const int lrow = tid >> 1, lk0 = (tid & 1) * 8;
+  // ---- loader state: thread t moves LK consecutive k of row t / (16 / LK) of both operands per k-tile
+  const int lrow = tid / (BK / LK), lk0 = (tid % (BK / LK)) * LK;
   const float* arow = nullptr;
   float amean = 0.f, arstd = 1.f;
   {
@@ -98,47 +103,53 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_linear_kernel(const GemvP
       brow = (np & 1) ? rb : ra;
     }
   }
-  auto load_a = [&](int k, float (&v)[8]) {
-    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-    if (arow != nullptr && k < K) {  // K % 8 == 0 (checked by the launcher)
-      x0 = *reinterpret_cast<const float4*>(arow + k);
-      x1 = *reinterpret_cast<const float4*>(arow + k + 4);
-      if (PRO == PRO_RMSNORM || PRO == PRO_LAYERNORM) {
-        const float4 g0 = *reinterpret_cast<const float4*>(p.norm_w + k), g1 = *reinterpret_cast<const float4*>(p.norm_w + k + 4);
-        if (PRO == PRO_RMSNORM) {  // rs[m] is applied in the epilogue
-          x0 = make_float4(x0.x * g0.x, x0.y * g0.y, x0.z * g0.z, x0.w * g0.w);
-          x1 = make_float4(x1.x * g1.x, x1.y * g1.y, x1.z * g1.z, x1.w * g1.w);
-        } else {
-          const float4 c0 = *reinterpret_cast<const float4*>(p.norm_b + k), c1 = *reinterpret_cast<const float4*>(p.norm_b + k + 4);
-          x0 = make_float4((x0.x - amean) * arstd * g0.x + c0.x, (x0.y - amean) * arstd * g0.y + c0.y,
-                           (x0.z - amean) * arstd * g0.z + c0.z, (x0.w - amean) * arstd * g0.w + c0.w);
-          x1 = make_float4((x1.x - amean) * arstd * g1.x + c1.x, (x1.y - amean) * arstd * g1.y + c1.y,
-                           (x1.z - amean) * arstd * g1.z + c1.z, (x1.w - amean) * arstd * g1.w + c1.w);
+  auto load_a = [&](int k, float (&v)[LK]) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kk = k + 4 * h;
+      if (arow != nullptr && kk < K) {  // K % 8 == 0 (checked by the launcher)
+        x0 = *reinterpret_cast<const float4*>(arow + kk);
+        if (PRO == PRO_RMSNORM || PRO == PRO_LAYERNORM) {
+          const float4 g0 = *reinterpret_cast<const float4*>(p.norm_w + kk);
+          if (PRO == PRO_RMSNORM) {  // rs[m] is applied in the epilogue
+            x0 = make_float4(x0.x * g0.x, x0.y * g0.y, x0.z * g0.z, x0.w * g0.w);
+          } else {
+            const float4 c0 = *reinterpret_cast<const float4*>(p.norm_b + kk);
+            x0 = make_float4((x0.x - amean) * arstd * g0.x + c0.x, (x0.y - amean) * arstd * g0.y + c0.y,
+                             (x0.z - amean) * arstd * g0.z + c0.z, (x0.w - amean) * arstd * g0.w + c0.w);
+          }
         }
       }
+      v[4 * h] = x0.x;
+      v[4 * h + 1] = x0.y;
+      v[4 * h + 2] = x0.z;
+      v[4 * h + 3] = x0.w;
     }
-    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
   };
-  auto load_b = [&](int k, float (&v)[8]) {
-    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-    if (brow != nullptr && k < K) {
-      x0 = ldg_stream(brow + k);
-      x1 = ldg_stream(brow + k + 4);
+  auto load_b = [&](int k, float (&v)[LK]) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (brow != nullptr && k + 4 * h < K) x0 = ldg_stream(brow + k + 4 * h);
+      v[4 * h] = x0.x;
+      v[4 * h + 1] = x0.y;
+      v[4 * h + 2] = x0.z;
+      v[4 * h + 3] = x0.w;
     }
-    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
   };
 
-  float acc[8][8];
+  float acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
 
-  float ra[8], rb[8];
+  float ra[LK], rb[LK];
   load_a(lk0, ra);
   load_b(lk0, rb);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < LK; ++i) {
     As[0][lk0 + i][lrow] = ra[i];
     Bs[0][lk0 + i][lrow] = rb[i];
   }
@@ -152,20 +163,28 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_linear_kernel(const GemvP
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float av[R], bv[R];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int h = 0; h < H; ++h) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[cur][k][64 * h + ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 * h + tx * 4]);
+        av[4 * h] = a4.x;
+        av[4 * h + 1] = a4.y;
+        av[4 * h + 2] = a4.z;
+        av[4 * h + 3] = a4.w;
+        bv[4 * h] = b4.x;
+        bv[4 * h + 1] = b4.y;
+        bv[4 * h + 2] = b4.z;
+        bv[4 * h + 3] = b4.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     if (kt + 1 < nkt) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < LK; ++i) {
         As[cur ^ 1][lk0 + i][lrow] = ra[i];
         Bs[cur ^ 1][lk0 + i][lrow] = rb[i];
       }
@@ -173,16 +192,16 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_linear_kernel(const GemvP
     __syncthreads();
   }
 
-  // ---- epilogue: thread owns rows {ty*4+i, 64+ty*4+i} and n' columns {tx*4+j, 64+tx*4+j}: pairs (0,1), (2,3) of each half
+  // ---- epilogue: thread owns rows {64h + ty*4 + i} and n' columns {64h + tx*4 + j}: pairs (0,1), (2,3) of each half
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + 64 * (i >> 2) + ty * 4 + (i & 3);
     if (m >= p.M) continue;
     const float rs = (PRO == PRO_RMSNORM) ? stats[m] : 1.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < R / 2; ++q) {
       const int j = 2 * q;
-      const int np = n0 + (q < 2 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      const int np = n0 + 64 * (j >> 2) + tx * 4 + (j & 3);
       if (np >= Np) continue;
       const float *rA, *rB;
       int nA, nB;
@@ -192,21 +211,36 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_linear_kernel(const GemvP
   }
 }
 
+int g_sms_sg = 0;
+int sm_count_sg() {
+  if (g_sms_sg == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms_sg, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms_sg <= 0) g_sms_sg = 148;
+  }
+  return g_sms_sg;
+}
+
 }  // namespace
 
 // returns cudaErrorNotSupported when the (pro, epi) combination has no tiled instance (caller falls back to the skinny path)
 cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, float* stats_ws) {
   if ((p.K & 7) || (p.ldx & 3)) return cudaErrorNotSupported;  // 2 x 128-bit loads per thread along K
   const int n_units = (epi == EPI_SWIGLU) ? p.N : p.N / 2;
-  const dim3 grid((2 * n_units + BN - 1) / BN, (p.M + BM - 1) / BM);
+  dim3 grid((2 * n_units + BN - 1) / BN, (p.M + BM - 1) / BM);
+  const bool small = (int)(grid.x * grid.y) < sm_count_sg();  // few big tiles: quarter them so every SM gets work
+  if (small) grid = dim3((2 * n_units + 63) / 64, (p.M + 63) / 64);
   if (pro == PRO_RMSNORM || pro == PRO_LAYERNORM) {
     if (stats_ws == nullptr) return cudaErrorNotSupported;
     cudaError_t e = launch(lc, row_stats_kernel, dim3((p.M * 32 + 255) / 256), dim3(256), 0, p.X, p.ldx, p.M, p.K, p.eps,
                            pro == PRO_LAYERNORM ? 1 : 0, stats_ws);
     if (e != cudaSuccess) return e;
   }
-#define UA2_SG(P, E) \
-  if (pro == P && epi == E) return launch(lc, sgemm_linear_kernel<P, E>, grid, dim3(SG_THREADS), 0, p, (const float*)stats_ws);
+#define UA2_SG(P, E)                                                                                                        \
+  if (pro == P && epi == E)                                                                                                 \
+    return small ? launch(lc, sgemm_linear_kernel<P, E, 1>, grid, dim3(SG_THREADS), 0, p, (const float*)stats_ws)           \
+                 : launch(lc, sgemm_linear_kernel<P, E, 2>, grid, dim3(SG_THREADS), 0, p, (const float*)stats_ws);
   UA2_SG(PRO_PLAIN, EPI_STORE)
   UA2_SG(PRO_PLAIN, EPI_RESADD)
   UA2_SG(PRO_PLAIN, EPI_SWIGLU)

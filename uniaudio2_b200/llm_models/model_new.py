@@ -299,7 +299,9 @@ class Model_stage3(nn.Module):
         if name == "audio_logits":
             Va = self.config.audio_semantic_vocab_size + self.config.audio_reason_vocab_size
             return t[: nq * B * Va].view(nq, B, Va)
-        return t[:B]
+        if name in ("h_final", "text_logits"):
+            return t[:B]
+        return t  # raw word buffer (e.g. "chain_prof")
 
     def get_fsdp_wrap_module_list(self) -> List[nn.Module]:  # model_new.py:686-687 (API surface only)
         return (list(self.backbone.transformer.h) + list(self.audio_understanding_expert.transformer.h)
