@@ -380,8 +380,10 @@ def main():
         if dev != "cpu":
             torch.cuda.empty_cache()
         ests, last = [], None
+        threads = None  # the first sample picks the fastest thread count, the others reuse it
         for i in range(args.warmup + args.steps):
-            cb, est = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
+            cb, est = cpu_baseline_sample(sd, n_frames=args.cpu_frames, threads=threads)
+            threads = cb["cores"]
             if i >= args.warmup:
                 ests.append(est)
                 last = cb

@@ -23,15 +23,6 @@
 #include "ua2_gemv_dev.cuh"
 #include "ua2_kernels.cuh"
 
-#ifdef UA2_HAVE_CUTLASS
-#include "cute/tensor.hpp"
-#include "cutlass/cutlass.h"
-#include "cutlass/epilogue/collective/collective_builder.hpp"
-#include "cutlass/gemm/collective/collective_builder.hpp"
-#include "cutlass/gemm/device/gemm_universal_adapter.h"
-#include "cutlass/gemm/kernel/gemm_universal.hpp"
-#include "cutlass/util/packed_stride.hpp"
-#endif
 
 namespace ua2 {
 namespace {
@@ -140,49 +131,15 @@ __global__ void __launch_bounds__(256) tc_epilogue_kernel(const GemvParams p, co
 }
 
 #ifdef UA2_HAVE_CUTLASS
-using namespace cute;
-using ElementA = float;  // fp32 storage, consumed as tf32 by tcgen05.mma kind::tf32
-using LayoutA = cutlass::layout::RowMajor;
-using ElementB = float;
-using LayoutB = cutlass::layout::ColumnMajor;  // W3 is (N, 3K) row-major = (3K, N) column-major
-using ElementC = float;
-using LayoutC = cutlass::layout::RowMajor;
-constexpr int kAlign = 4;
-using MmaTile = Shape<_128, _128, _32>;
-using Cluster = Shape<_1, _1, _1>;
-using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTile, Cluster, cutlass::epilogue::collective::EpilogueTileAuto, float,
-    float, ElementC, LayoutC, kAlign, ElementC, LayoutC, kAlign, cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
-using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, kAlign, ElementB, LayoutB, kAlign, float, MmaTile, Cluster,
-    cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
-    cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
-using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>;
-using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
-
+}  // namespace
+// the CUTLASS instantiations live in their own translation units (ua2_tcgemm_t128.cu / ua2_tcgemm_t64.cu) so they build in parallel
+cudaError_t run_tf32_gemm_128x128(cudaStream_t st, const float* A, const float* B, float* C, int M, int N, int K);
+cudaError_t run_tf32_gemm_64x32(cudaStream_t st, const float* A, const float* B, float* C, int M, int N, int K);
+namespace {
+// 128 x 128 x 32 tiles for prefill passes; 64 x 32 x 32 tiles for decode-sized M (<= 64 rows): N / 32 CTAs keep every SM
+// streaming weights where N / 128 would leave most of them idle
 cudaError_t run_tf32_gemm(cudaStream_t st, const float* A, const float* B, float* C, int M, int N, int K) {
-  using StrideA = typename Gemm::GemmKernel::StrideA;
-  using StrideB = typename Gemm::GemmKernel::StrideB;
-  using StrideC = typename Gemm::GemmKernel::StrideC;
-  using StrideD = typename Gemm::GemmKernel::StrideD;
-  const StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, K, 1));
-  const StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(N, K, 1));
-  const StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, make_shape(M, N, 1));
-  const StrideD sd = cutlass::make_cute_packed_stride(StrideD{}, make_shape(M, N, 1));
-  typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}, {A, sa, B, sb}, {{1.f, 0.f}, C, sc, C, sd}};
-  static int sms = 0, dev = -1;
-  if (dev < 0) {
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  args.hw_info.device_id = dev;
-  args.hw_info.sm_count = sms;
-  Gemm gemm;
-  if (gemm.can_implement(args) != cutlass::Status::kSuccess) return cudaErrorNotSupported;
-  if (Gemm::get_workspace_size(args) != 0) return cudaErrorNotSupported;
-  if (gemm.initialize(args, nullptr, st) != cutlass::Status::kSuccess) return cudaErrorInvalidValue;
-  if (gemm.run(st) != cutlass::Status::kSuccess) return cudaErrorLaunchFailure;
-  return cudaSuccess;
+  return M <= 64 ? run_tf32_gemm_64x32(st, A, B, C, M, N, K) : run_tf32_gemm_128x128(st, A, B, C, M, N, K);
 }
 #endif
 
