@@ -133,6 +133,8 @@ struct ua2_codec {
   size_t ws_floats = 0;
   int32_t *pos = nullptr, *bidx = nullptr;
   size_t posidx_cap = 0;
+  TcWorkspace tc;  // scratch of the tcgen05 3xTF32 path for the transformer linears (grown on demand)
+  size_t tc_rows = 0;
   int hop = 1, rs = 1;
 };
 
@@ -169,6 +171,30 @@ int reserve_posidx(ua2_codec* h, size_t M) {
   return UA2_OK;
 }
 
+// split operands + raw product of the largest transformer linear at M rows (ua2_tcgemm.cu)
+int reserve_tc(ua2_codec* h, size_t M) {
+  if (!tc_gemm_available() || M > 65536) return UA2_OK;  // larger batches stay on the fp32 SIMT tiles
+  if (M <= h->tc_rows) return UA2_OK;
+  const size_t C = h->cfg.latent_dim, F = h->cfg.dim_feedforward;
+  if (h->tc.a) {
+    UA2_CHECK_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->tc.a);
+    cudaFree(h->tc.w);
+    cudaFree(h->tc.c);
+    h->tc = TcWorkspace();
+    h->tc_rows = 0;
+  }
+  const size_t kmax = std::max(C, F), nmax = std::max(3 * C, F);
+  h->tc.a_floats = M * 3 * kmax;
+  h->tc.w_floats = std::max({3 * C * 3 * C, F * 3 * C, C * 3 * F, C * 3 * C});
+  h->tc.c_floats = M * nmax;
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.a, h->tc.a_floats * 4));
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.w, h->tc.w_floats * 4));
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.c, h->tc.c_floats * 4));
+  h->tc_rows = M;
+  return UA2_OK;
+}
+
 const ConvW* find_conv(ua2_codec* h, const std::string& key) {
   auto it = h->convs.find(key);
   return it == h->convs.end() ? nullptr : &it->second;
@@ -195,6 +221,8 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
   LaunchCtx lc;
   lc.stream = (cudaStream_t)st;
   RUN(reserve_posidx(h, M));
+  RUN(reserve_tc(h, M));
+  const TcWorkspace* tcw = (h->tc.a != nullptr && (size_t)M <= h->tc_rows) ? &h->tc : nullptr;
   UA2_CHECK_CUDA(launch(lc, posidx_kernel, dim3((M + 255) / 256), dim3(256), 0, h->pos, h->bidx, M, T));
   // (B, C, T) -> (B, T, C)
   UA2_CHECK_CUDA(launch(lc, transpose_kernel, dim3((T + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, (const float*)x_bct, xt, C, T));
@@ -210,6 +238,7 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.M = M;
       p.ws = sg_ws;
       p.ws_floats = sg_ws_floats;
+      p.tc = tcw;
       p.X = xt;
       p.ldx = C;
       p.norm_w = w.n1w;
@@ -253,6 +282,7 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.M = Mc;
       p.ws = sg_ws;
       p.ws_floats = sg_ws_floats;
+      p.tc = tcw;
       p.o_part = o_part;
       p.ml_part = ml_part;
       p.max_splits = max_splits;
@@ -275,6 +305,7 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.M = M;
       p.ws = sg_ws;
       p.ws_floats = sg_ws_floats;
+      p.tc = tcw;
       p.X = xt;
       p.ldx = C;
       p.norm_w = w.n2w;
@@ -292,6 +323,7 @@ int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbu
       p.M = M;
       p.ws = sg_ws;
       p.ws_floats = sg_ws_floats;
+      p.tc = tcw;
       p.X = hbuf;
       p.ldx = F;
       p.Y = xt;
@@ -350,6 +382,11 @@ int ua2_codec_destroy(ua2_codec* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->pos) cudaFree(h->pos);
   if (h->bidx) cudaFree(h->bidx);
+  if (h->tc.a) {
+    cudaFree(h->tc.a);
+    cudaFree(h->tc.w);
+    cudaFree(h->tc.c);
+  }
   delete h;
   return UA2_OK;
 }

@@ -53,7 +53,35 @@ __global__ void __launch_bounds__(256) tc_split_a_kernel(const GemvParams p, flo
   } else {
     src = p.X + (size_t)m * p.ldx;
   }
-  float rs = 1.f;
+  float rs = 1.f, mean = 0.f;
+  if (PRO == PRO_LAYERNORM) {  // two-pass statistics like row_stats_kernel (ua2_sgemm.cu): mean, then centred sum of squares
+    float s = 0.f;
+    for (int k = tid * 4; k < K; k += 256 * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + k);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    mean = tot / (float)K;
+    __syncthreads();
+    float sq = 0.f;
+    for (int k = tid * 4; k < K; k += 256 * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + k);
+      const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+    sq = warp_sum(sq);
+    if ((tid & 31) == 0) red[tid >> 5] = sq;
+    __syncthreads();
+    tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    rs = rsqrtf(tot / (float)K + p.eps);
+  }
   if (PRO == PRO_RMSNORM) {
     float ss = 0.f;
     for (int k = tid * 4; k < K; k += 256 * 4) {
@@ -74,6 +102,11 @@ __global__ void __launch_bounds__(256) tc_split_a_kernel(const GemvParams p, flo
     if (PRO == PRO_RMSNORM) {
       const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k);
       v = make_float4((v.x * rs) * g.x, (v.y * rs) * g.y, (v.z * rs) * g.z, (v.w * rs) * g.w);
+    }
+    if (PRO == PRO_LAYERNORM) {  // same expression as the SIMT loader (ua2_sgemm.cu)
+      const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k), c = *reinterpret_cast<const float4*>(p.norm_b + k);
+      v = make_float4((v.x - mean) * rs * g.x + c.x, (v.y - mean) * rs * g.y + c.y, (v.z - mean) * rs * g.z + c.z,
+                      (v.w - mean) * rs * g.w + c.w);
     }
     float4 hi, lo;
     split4(v, hi, lo);
@@ -189,8 +222,10 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   return cudaErrorNotSupported;
 #else
   if (p.tc == nullptr || (p.K & 3) || (p.ldx & 3)) return cudaErrorNotSupported;
-  if (!(pro == PRO_PLAIN || pro == PRO_RMSNORM || pro == PRO_GATHER)) return cudaErrorNotSupported;
-  if (!(epi == EPI_STORE || epi == EPI_RESADD || epi == EPI_SWIGLU || epi == EPI_QKV)) return cudaErrorNotSupported;
+  if (!(pro == PRO_PLAIN || pro == PRO_RMSNORM || pro == PRO_GATHER || pro == PRO_LAYERNORM)) return cudaErrorNotSupported;
+  if (!(epi == EPI_STORE || epi == EPI_RESADD || epi == EPI_SWIGLU || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_SCALE_RESADD ||
+        epi == EPI_QKV_IL))
+    return cudaErrorNotSupported;
   const TcWorkspace& ws = *p.tc;
   const int M = p.M, K = p.K, K3 = 3 * p.K;
   const int Ntot = epi == EPI_SWIGLU ? 2 * p.N : p.N;
@@ -230,6 +265,7 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   UA2_TCA(PRO_PLAIN)
   UA2_TCA(PRO_RMSNORM)
   UA2_TCA(PRO_GATHER)
+  UA2_TCA(PRO_LAYERNORM)
 #undef UA2_TCA
   if (e != cudaSuccess) return e;
   if (need_split) {
@@ -250,6 +286,9 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   UA2_TCE(EPI_RESADD)
   UA2_TCE(EPI_SWIGLU)
   UA2_TCE(EPI_QKV)
+  UA2_TCE(EPI_GELU)
+  UA2_TCE(EPI_SCALE_RESADD)
+  UA2_TCE(EPI_QKV_IL)
 #undef UA2_TCE
   return cudaErrorNotSupported;
 #endif
