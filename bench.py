@@ -254,6 +254,13 @@ def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
                 one_frame()
                 tried[n] = round(one_frame() * 1e3, 1)
             torch.set_num_threads(min(tried, key=tried.get))
+            # re-time the prefill with the chosen thread count (the first one ran before the calibration)
+            orc.reset_caches()
+            t0 = time.perf_counter()
+            orc.forward_prefix(tokens[:, :-1], mask, pos[:, :-1])
+            t_prefill = time.perf_counter() - t0
+            curr_tokens, curr_mask, f = tokens[:, -1:], mask[:, -1:], 0
+            one_frame()
         for _ in range(n_frames):
             times.append(one_frame())
     frame_t = sum(times[1:]) / len(times[1:])  # first frame = warm-up
