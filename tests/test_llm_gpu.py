@@ -223,3 +223,26 @@ def test_batch32_caption_config():
             _lib.check(L.ua2_set_global_option(b"tc_gemm", TC_DEFAULT))
             _lib.check(L.ua2_set_global_option(b"tc_min_rows", 128))
             _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", 0))
+
+
+def test_cache_filled_to_the_last_slot():
+    """Maximum size: prefill + frames up to position max_seq_length - 1 (the last KV slot, lit_model.py:120-124 allows
+    input_pos < max_seq_length), ids equal to the oracle; the next position is rejected like the reference does."""
+    import copy
+
+    cfg = copy.deepcopy(tiny_cfgs()["tiny"])
+    cfg.max_seq_length = 72  # crosses the 64-key attention split at the very end
+    sd = O.random_state_dict(cfg, seed=3)
+    m = build_product_model(cfg, sd, "cuda", 1, max_seq=72)
+    orc = O.Stage3Oracle(cfg, sd)
+    orc.setup_caches(1)
+    S, nf = 66, 7  # frames at positions 65 .. 71
+    o = run_case(orc, "text", cfg, 1, S, nf, 4, 0.8, 1.0, REASON_CARD["tiny"], 13, False, explicit_noise=True)
+    r = run_case(m, "text", cfg, 1, S, nf, 4, 0.8, 1.0, REASON_CARD["tiny"], 13, True, device="cuda", explicit_noise=True)
+    assert torch.equal(r["frames"].cpu(), o["frames"])
+    k, _ = m.kv_cache(0, cfg.backbone.n_layer - 1)
+    assert _rel(k[:1, :, :72].cpu(), orc.backbone.kv[-1].k[:1, :, :72]) < REL_TOL
+    tok = torch.zeros(1, 1, 9, dtype=torch.long, device="cuda")
+    msk = torch.ones(1, 1, 9, dtype=torch.bool, device="cuda")
+    with pytest.raises(ValueError):
+        m.generate_frame(tok, msk, torch.tensor([72], device="cuda"), None, temperature=1.0, topk=1)

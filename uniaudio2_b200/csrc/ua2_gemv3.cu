@@ -1,20 +1,22 @@
-// Skinny fp32 linear, v3: one persistent CTA per SM, bulk-copy weight rings, K split across warps.
+// Skinny fp32 linear, v3: persistent CTAs (2 per SM), slab partition of the weight rows, K split across the warps of a
+// CTA, per-warp bulk-copy weight rings.  The default linear of every decode frame (M < 128 rows).
 //
-// Why (measured, profiles/r1_launches_v1.md): at M = 1 every linear of the AR frame is a 3-35 us weight stream and the
-// frame has ~355 of them, so what is lost is not steady-state bandwidth but the bubble at every kernel boundary
-// (drain -> launch -> activation prologue -> first weight round trip, ~7 us per kernel with v1/v2).  v3 is built so
-// that the HBM stream does not stop at a boundary:
-//   * exactly ONE CTA per SM and <= ~110 KB of shared memory, so the CTAs of the NEXT kernel (programmatic dependent
-//     launch) are co-resident with this kernel's CTAs from its start: they fill their weight rings and park on
-//     griddepcontrol.wait while this kernel is still streaming;
-//   * each warp owns a ring of shared-memory slots fed by cp.async.bulk (SASS UBLKCP) completing on per-slot
-//     mbarriers; the ring is filled BEFORE griddepcontrol.wait / the activation prologue and refilled the moment a
-//     slot is consumed, so ~64-96 KB per SM are always in flight, independent of the register budget;
-//   * work is balanced to one weight-row pair: CTA c owns the contiguous slab of units [c*U/G, (c+1)*U/G) and its 8
-//     warps split K (nsl slices per unit), partial sums meet in shared memory once per round of <= 32 units;
-//   * the prologue is a single L2 round trip: RMSNorm's rsqrt(mean(x^2)+eps) is a per-row scalar, so it is applied in
-//     the epilogue ((sum_k W[n,k] x[k] g[k]) * rs) instead of forcing a reduce-then-scale pass before the first FMA;
-//     the attention combine reads all launched splits at once (empty splits carry weight 0).
+// Why (measured, profiles/r1_launches.md): at M = 1 every linear of the AR frame is a 9-37 us weight stream and the frame
+// has ~330 of them, so what is lost is not steady-state bandwidth but the bubble at every kernel boundary (drain ->
+// launch -> activation prologue -> first weight round trip).  v3 keeps that bubble small:
+//   * <= ~110 KB of shared memory and 6-8 warps per CTA, two CTAs per SM: under programmatic dependent launch the CTAs of
+//     the NEXT kernel take over SM slots as this kernel's CTAs retire, fill their weight rings and park on
+//     griddepcontrol.wait;
+//   * each warp owns a ring of 3 shared-memory slots of 4 KB fed by cp.async.bulk (SASS UBLKCP) completing on per-slot
+//     mbarriers - the copy size / depth the HBM microbenchmark calls for (profiles/r1_microbench_hbm_streaming.txt); the
+//     ring is filled BEFORE griddepcontrol.wait / the activation prologue and refilled the moment a slot is consumed;
+//   * work is balanced to one weight-row unit: CTA c owns the contiguous slab of units [c*U/G, (c+1)*U/G), the grid G is
+//     chosen in [SMs, 2 SMs] for the best remainder balance, and the warps split K (nsl slices of ~1024 floats per unit);
+//     partial sums meet in shared memory once per round of <= 32 units;
+//   * the prologue is a single L2 round trip: every global load of a thread is issued before its first use
+//     (ua2_gemv3_dev.cuh), RMSNorm's rsqrt(mean(x^2)+eps) is a per-row scalar applied in the epilogue
+//     ((sum_k W[n,k] x[k] g[k]) * rs), the attention combine reads all launched splits at once, and the epilogue's
+//     residual / position operands are fetched together with the activations.
 #include "ua2_gemv3_dev.cuh"
 
 namespace ua2 {

@@ -305,7 +305,6 @@ __device__ __forceinline__ void epilogue_one(const GemvParams& p, int m, float a
   }
 }
 
-struct V3Cfg_unused_marker {};
 struct V3Cfg {
   int nsl;       // K slices per unit; one warp per (group, slice)
   int ngrp;      // unit groups per CTA; warps = ngrp * nsl (8 or 9)
