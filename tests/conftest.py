@@ -19,8 +19,20 @@ def golden():
     return torch.load(os.path.join(ROOT, "tests", "golden", "llm_golden.pt"), weights_only=False)
 
 
+def build_product_model_cpu(cfg):
+    """The drop-in Model_stage3 for an oracle Stage3Cfg with its parameters on the CPU (no handle, no kernels)."""
+    return _make_product_model(cfg, "cpu", None)
+
+
 def build_product_model(cfg, sd, device, max_batch, max_seq=None):
     """Instantiate the product's Model_stage3 for an oracle Stage3Cfg and load the oracle's state dict."""
+    m = _make_product_model(cfg, device, max_seq)
+    m.load_state_dict(sd, strict=True)
+    m.setup_caches(max_batch)
+    return m
+
+
+def _make_product_model(cfg, device, max_seq):
     from uniaudio2_b200.llm_models import config as pc
     from uniaudio2_b200.llm_models.model_new import Model_stage3, ModelArgs
 
@@ -39,6 +51,4 @@ def build_product_model(cfg, sd, device, max_batch, max_seq=None):
         m = Model_stage3(args, device=device, max_seq_length=max_seq or cfg.max_seq_length)
     finally:
         pc.name_to_config.update(saved)
-    m.load_state_dict(sd, strict=True)
-    m.setup_caches(max_batch)
     return m
