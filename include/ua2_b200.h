@@ -39,7 +39,7 @@ const char* ua2_version(void);
  * "gemv3_ctas_per_sm" (1..3, default 2), "gemv3_max_stages" (2..6, default 3), "gemv3_kcw" (floats per bulk copy, default 1024),
  * "gemv3_budget_kb" (shared memory per decode CTA, default 110), "gemv3_balance_grid" (0/1, default 1),
  * "sgemm_min_rows" (rows from which linears use the tiled GEMM core, default 128),
- * "tc_gemm" (0/1, default 1 when built with the CUTLASS headers: linears with >= "tc_min_rows" (default 128) rows run as
+ * "tc_gemm" (0/1, default 1 when built with the CUTLASS headers: linears with >= "tc_min_rows" (default 32) rows run as
  * 3xTF32 tcgen05 GEMMs - fp32-class accuracy, csrc/ua2_tcgemm.cu), "tc_persistent_weights" (0/1, default 0: keep the
  * tf32-split copy of every weight the tensor-core path has used, 12 B per parameter, instead of re-splitting per call -
  * for batched decode frames, e.g. tc_min_rows = 16 with batch 32),

@@ -221,7 +221,7 @@ def test_batch32_caption_config():
                 assert _rel(m.debug_buffer("text_logits", B).cpu(), o["text_logits"][-1]) < REL_TOL
         finally:
             _lib.check(L.ua2_set_global_option(b"tc_gemm", TC_DEFAULT))
-            _lib.check(L.ua2_set_global_option(b"tc_min_rows", 128))
+            _lib.check(L.ua2_set_global_option(b"tc_min_rows", 32))
             _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", 0))
 
 

@@ -114,7 +114,7 @@ def main():
                          prefill_ms=round(pre, 1), ms_per_frame=round((ms - pre) / NF, 2),
                          text_tokens_per_s=round(B * NF / (ms * 1e-3), 1), clips_per_s=round(B / (ms * 1e-3), 2))
                 _lib.check(L.ua2_set_global_option(b"tc_gemm", 0))
-                _lib.check(L.ua2_set_global_option(b"tc_min_rows", 128))
+                _lib.check(L.ua2_set_global_option(b"tc_min_rows", 32))
                 _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", 0))
 
             if "ttm500" in only:
