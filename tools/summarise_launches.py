@@ -25,6 +25,9 @@ def main():
     agg = collections.OrderedDict()
     for r in rows:
         name = re.sub(r"^void |\(.*$", "", r["Kernel Name"]).replace("(anonymous namespace)::", "").replace("unnamed>::", "").replace("ua2::<", "")
+        if name.startswith("cutlass::device_kernel"):  # keep the MMA atom of the CUTLASS collective, drop the rest of the type
+            m = re.search(r"SM100_MMA_\w+<[^>]*>", r["Kernel Name"])
+            name = "cutlass::device_kernel<GemmUniversal<TMA + UMMA warp-specialised, " + (m.group(0) if m else "?") + ">>"
         key = (name, r["Grid Size"], r["Block Size"])
         v = float(r["Metric Value"].replace(",", ""))
         if r["Metric Unit"] in ("ns", "nsecond"):
