@@ -1,5 +1,4 @@
 """GPU parity of the stand-alone C-ABI operators against the CPU oracle (oracle/llm_oracle.py primitives)."""
-import ctypes as C
 import math
 
 import pytest

@@ -6,7 +6,7 @@ The B200 equivalent keeps replica-per-GPU (the 4.86 B-parameter fp32 model is 19
 i -> rank i mod W, and adds ONE collective: an all_gather of the (padded) generated tokens + lengths over NCCL/NVLink
 (SURVEY.md section 8e).  Works with the gloo backend on CPU tensors too (used by the CPU tests).
 """
-from typing import List, Sequence, Tuple
+from typing import List, Sequence
 
 import torch
 import torch.distributed as dist

@@ -9,7 +9,6 @@ the parameters (torch tensors on the GPU) and the native handle.  No torch/CPU f
 """
 import ctypes as C
 import math
-from typing import List
 
 import torch
 import torch.nn as nn

@@ -7,10 +7,8 @@ Same constructor arguments and state-dict keys (weight_norm `weight_g` / `weight
 phase GEMM on the register-tiled fp32 core of libua2_b200.so with the PReLU, bias and residual add fused in the epilogue.
 `num_samples > 1` (PreProcessor / PostProcessor pooling) is not on the shipped path and is rejected.
 """
-import ctypes as C
 from typing import Dict, Tuple
 
-import numpy as np
 import torch
 import torch.nn as nn
 
