@@ -18,22 +18,27 @@ from typing import Optional, Tuple
 import torch
 
 
+def _newest_checkpoint(exp_dir: str) -> str:
+    """Path of the most recently created `ep*.checkpoint` under exp_dir (creation-time order, like the reference)."""
+    found = sorted(Path(exp_dir).glob("ep*.checkpoint"), key=lambda p: os.stat(str(p)).st_ctime)
+    if not found:
+        raise ValueError("Model for resume is not provided and cannot be detected.")
+    return str(found[-1])
+
+
+def _strip_wrapper_prefix(key: str) -> str:
+    # DDP / FSDP save parameters as 'module.<name>'; the reference keeps what follows the LAST 'module.' of such keys
+    return key.split("module.")[-1] if key.startswith("module.") else key
+
+
 def resume_for_inference(resume: Optional[str], exp_dir: Optional[str], model, device="cpu") -> str:
-    if resume is not None:
-        checkpoint = resume
-        logging.info(f"Resume from the provided checkpoint {resume}")
-    else:
-        ckpts = list(Path(exp_dir).glob("ep*.checkpoint"))
-        if len(ckpts) == 0:
-            raise ValueError("Model for resume is not provided and cannot be detected.")
-        ckpts.sort(key=lambda x: os.stat(str(x)).st_ctime)
-        checkpoint = str(ckpts[-1])
-        logging.info(f"Automatically resume from the latest checkpoint {checkpoint}")
-    state_dict = torch.load(checkpoint, map_location="cpu")["model"]
-    state_dict = {k.split("module.")[-1] if k.startswith("module.") else k: v for k, v in state_dict.items()}
-    model.load_state_dict(state_dict)
-    del state_dict
-    return checkpoint
+    """Restore `model` from an explicit checkpoint path, or from the newest one in `exp_dir`; returns the path used.
+    The checkpoint is the dict written by the reference's trainer: weights under the key 'model'."""
+    path = resume if resume is not None else _newest_checkpoint(exp_dir)
+    logging.info("restoring weights from %s", path)
+    weights = torch.load(path, map_location="cpu")["model"]
+    model.load_state_dict({_strip_wrapper_prefix(k): v for k, v in weights.items()})  # strict: same keys as the reference
+    return path
 
 
 def load_llm_config(path: str) -> argparse.Namespace:
