@@ -105,3 +105,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
+    # dev tools measure / profile the product: they must not pull the oracle in either
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            txt = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt, f"tools/{f} imports the oracle"
+    # bench.py: only inside the CPU-baseline legs (cpu_baseline_sample, the `if cpu:` block of bench_codec)
+    import ast
+
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        imports = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
+        if imports:
+            assert fn.name in ("cpu_baseline_sample", "bench_codec"), f"bench.py::{fn.name} imports the oracle"
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n)]
+    assert not top, "bench.py imports the oracle at module level"

@@ -134,17 +134,7 @@ def main():
             torch.cuda.empty_cache()
 
     if "codec_sweep" in only:
-        from oracle import codec_oracle as CO  # weight / shape helper only
-        from uniaudio2_b200.tools.tokenizer.MimiCodec.mimi_codec import MimiCodec
-
-        cfg = CO.MimiCfg()
-        sd = CO.random_mimi_state_dict(cfg, seed=7)
-        m = MimiCodec(n_filters=cfg.n_filters, encoder_rates=cfg.encoder_rates, latent_dim=cfg.latent_dim, codebook_size=cfg.codebook_size,
-                      codebook_dim=cfg.codebook_dim, rvq_layers=cfg.rvq_layers, num_heads=cfg.num_heads, num_layers=cfg.num_layers,
-                      layer_scale=cfg.layer_scale, context=cfg.context, device=dev)
-        full = m.state_dict()
-        full.update({k: v.to(dev) for k, v in sd.items()})
-        m.load_state_dict(full, strict=True)
+        m = bench.make_codec(dev)
         g = torch.Generator().manual_seed(0)
         for clip_s in (1, 5, 30):
             for batch in (1, 4, 16, 64):
