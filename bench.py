@@ -559,9 +559,12 @@ def main():
             roofline["frame_frac_of_peak"] = round(roofline["frame_effective_gbs"] / hbm_peak, 4)
             roofline["frame_algorithmic_bytes"] = mean_bytes
             if world == 1 and not args.no_cpu_baseline:
-                sd = state_dict_to_cpu(model)
-                cpu_base, _ = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
-                del sd
+                try:
+                    sd = state_dict_to_cpu(model)
+                    cpu_base, _ = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
+                    del sd
+                except Exception as e:  # noqa: BLE001  (e.g. host memory): report it instead of losing the GPU measurement
+                    cpu_base = {"error": f"{type(e).__name__}: {e}", "kind": "port"}
             if world == 1 and not args.no_codec:
                 try:  # secondary metric: never let it take the headline line down
                     codec = bench_codec(dev, cpu=not args.no_cpu_baseline)
