@@ -257,6 +257,87 @@ int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* code
 /* MimiCodec.decode: codes (B, rvq_layers, Tq) int64 -> wav (B, 1, Tq * resample_stride * hop_length) fp32 */
 int ua2_codec_decode(ua2_codec* h, const int64_t* codes, int B, int Tq, float* wav, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Moshi-family streaming transformer and sampler: llm_modules/transformer.py (StreamingTransformer,
+ * StreamingTransformerLayer, StreamingMultiheadAttention, RingKVCache, multi_linear, _rms_norm), llm_modules/gating.py
+ * (ActivationGating), llm_modules/rope.py (apply_rope) and llm_utils/sampling.py (sample_token) - the modules
+ * BASELINE.json's north_star names for the AR decode.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Position held by ring slot j after `end_offset` keys were written (RingKVCache.complete, transformer.py:254-276):
+ *   j >= end_offset -> -1 (never written); delta = j - end_offset % cap; delta <= 0 ? end_offset + delta
+ *   : end_offset + delta - cap.  (The reference's `<=` makes the slot at end_offset % cap report a future position once
+ *   the ring has wrapped, so the oldest key is never visible - reproduced as is.)  ring = 0: linear cache, position = j.
+ * StreamingMultiheadAttention.forward, transformer.py:375-419, after the in_proj: interleaved-pair RoPE of q and k
+ * (rope.py:40-58; angle = freqs[i] * pos, freqs (hs/2) = exp(i * -ln(max_period) * 2 / hs) supplied by the host, NULL =
+ * no RoPE) and the append of k / v to the cache (B, H, cap, hs) at slot pos % cap (ring) or pos (linear).
+ *   qkv (M rows of 3*H*hs, row stride ld_qkv), ordered (p h d) as `rearrange(projected, "b t (p h d) -> p b h t d")`;
+ *   pos (M) int32 absolute position of each row, bidx (M) int32 batch row; q_out (M, H*hs). */
+int ua2_rope_ring_append_f32(const float* qkv, int ld_qkv, const int32_t* pos, const int32_t* bidx, const float* freqs,
+                             float* q_out, float* k_cache, float* v_cache, int M, int H, int hs, int cap, int ring,
+                             void* stream);
+/* F.scaled_dot_product_attention with the streaming mask of transformer.py:399-410: key slot j of batch row bidx[m] is
+ * visible to row m iff its position p_j >= 0 and (causal == 0 or (0 <= pos[m] - p_j and (context <= 0 or pos[m] - p_j <
+ * context))).  end_offset = keys written so far INCLUDING this call's.  y (M, H*hs). */
+int ua2_ring_attn_f32(const float* q, const float* k_cache, const float* v_cache, const int32_t* pos, const int32_t* bidx,
+                      float* y, int M, int H, int hs, int cap, int64_t end_offset, int ring, int causal, int context,
+                      void* stream);
+
+/* sample_token (llm_utils/sampling.py:84-105) and sample_token_audio (:107-130) on R rows of V logits -> out (R) int64.
+ *   use_sampling == 0 or temp <= 0: argmax(logits) (first maximum).  Otherwise probs = softmax(logits / temp), ids >=
+ *   end_token get probability -inf when end_token >= 0, and
+ *     top_p > 0 : sort descending, keep ranks whose exclusive cumulative sum is <= top_p, renormalise      (:64-81; V <= 4096)
+ *     top_k > 0 : the k largest probabilities in descending order                                         (:49-61; k <= 1024)
+ *     else      : all V probabilities                                                                     (:15-46)
+ *   then token = argmax(p / q) with q ~ Exp(1) (multinomial without replacement, :41-43), first maximum wins.
+ *   noise: the Exp(1) draws, (R, n) with n = top_k for the top-k branch (one draw per RANK, as torch.topk orders them)
+ *   and n = V otherwise; NULL = drawn by the library from Philox4x32-10 keyed by (seed, offset). */
+int ua2_sample_token_f32(const float* logits, int R, int V, int use_sampling, float temp, int top_k, float top_p,
+                         int end_token, const float* noise, uint64_t seed, uint64_t offset, int64_t* out, void* stream);
+
+/* StreamingTransformer(d_model, num_heads, num_layers, dim_feedforward, causal, context, positional_embedding, max_period,
+ * positional_scale, norm, layer_scale, gating, weights_per_step) - transformer.py:616-669, :449-543. */
+#define UA2_STX_MAX_STEPS 64
+typedef struct ua2_stx_cfg {
+  int32_t d_model;
+  int32_t num_heads;          /* head size d_model / num_heads must be 32, 64 or 128 */
+  int32_t num_layers;
+  int32_t causal;
+  int32_t context;            /* 0 = None */
+  int32_t positional_embedding; /* 0 none, 1 sin, 2 rope, 3 sin_rope */
+  int32_t norm;               /* 0 layer_norm (eps 1e-5), 1 layer_norm_f32 (1e-8), 2 rms_norm (1e-5), 3 rms_norm_f32 (1e-8) */
+  int32_t gating;             /* 0 none: linear2(gelu(linear1 x));  1 silu: ActivationGating(F.silu), gating.py:24-51 */
+  int32_t weights_per_step;   /* 0, or the number of per-step weight slabs (multi_linear, transformer.py:155-179) */
+  int32_t layer_scale;        /* 0 / 1 (LayerScale parameters present) */
+  int32_t dim_feedforward[UA2_STX_MAX_STEPS]; /* [0] unless weights_per_step > 0 with a per-step list */
+  float max_period;
+  float positional_scale;
+} ua2_stx_cfg;
+typedef struct ua2_stx ua2_stx;
+
+int ua2_stx_create(const ua2_stx_cfg* cfg, ua2_stx** out);
+int ua2_stx_destroy(ua2_stx* h);
+/* one fp32 parameter by its reference state-dict key ("layers.0.self_attn.in_proj_weight", "layers.0.norm1.alpha",
+ * "layers.1.gating.3.linear_in.weight", "layers.0.layer_scale_1.scale", ...) plus the host-computed tables "rope_freqs"
+ * (hs/2; rope.py:37-38) and "sin_denoms" (d_model/2; max_period ** (i / (half - 1)), transformer.py:150); tensors must
+ * outlive the handle */
+int ua2_stx_load_weight(ua2_stx* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+/* validates that every parameter of the configuration has been registered */
+int ua2_stx_finalize(ua2_stx* h);
+/* StreamingModule._start_streaming(batch_size) (llm_modules/streaming.py:86-91): allocates one zeroed ring
+ * (batch, H, capacity, hs) x {k, v} per layer, capacity = context, or weights_per_step when context is None
+ * (transformer.py:337-346); offsets = 0.  _stop_streaming / reset_streaming (streaming.py:93-126; reset of a module
+ * that is not streaming -> UA2_ERR_INVALID like the reference's ValueError). */
+int ua2_stx_start_streaming(ua2_stx* h, int batch_size, void* stream);
+int ua2_stx_stop_streaming(ua2_stx* h);
+int ua2_stx_reset_streaming(ua2_stx* h);
+/* StreamingTransformer.forward (transformer.py:671-692): x (B, T, d_model) -> y (B, T, d_model); y may alias x.
+ * Streaming: B must equal the streaming batch size, T <= capacity, and offset + T <= weights_per_step when per-step
+ * weights are used (the reference indexes past the weight slab otherwise). */
+int ua2_stx_forward(ua2_stx* h, const float* x, float* y, int B, int T, void* stream);
+/* introspection: ring buffers (batch, H, capacity, hs) of a layer and the number of keys written so far */
+int ua2_stx_get_kv(ua2_stx* h, int layer, float** k, float** v, int64_t* end_offset, int* capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,3 +63,29 @@ def install_mimi_shims():
     p = os.path.join(REF_ROOT, "tools", "tokenizer", "MimiCodec")
     if p not in sys.path:
         sys.path.insert(0, p)
+
+
+def install_moshi_shims():
+    """Make the named Moshi-family modules importable as the reference itself addresses them (`from modules.gating import
+    ...`, `from utils.compile import ...`, llm_modules/transformer.py:21-24): `modules` -> llm_modules (by __path__, so the
+    package __init__ with its dead imports never runs), `utils.compile` -> llm_utils.compile.  Returns
+    (modules.transformer, llm_utils.sampling)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not present at {REF_ROOT}")
+    os.environ.setdefault("NO_TORCH_COMPILE", "1")
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import importlib
+
+    mods = types.ModuleType("modules")
+    mods.__path__ = [os.path.join(REF_ROOT, "llm_modules")]
+    sys.modules["modules"] = mods
+    utils = types.ModuleType("utils")
+    utils.__path__ = []
+    sys.modules["utils"] = utils
+    comp = importlib.import_module("llm_utils.compile")
+    sys.modules["utils.compile"] = comp
+    utils.compile = comp
+    tr = importlib.import_module("modules.transformer")
+    samp = importlib.import_module("llm_utils.sampling")
+    return tr, samp

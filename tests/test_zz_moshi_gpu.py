@@ -1,0 +1,220 @@
+"""GPU parity suite for the Moshi-family streaming transformer and sampler, called through
+the C ABI (ua2_stx_*, ua2_ring_attn_f32, ua2_rope_ring_append_f32, ua2_sample_token_f32) behind the reference's own
+interface (uniaudio2_b200.llm_modules.transformer.StreamingTransformer, uniaudio2_b200.llm_utils.sampling.sample_token).
+
+Checked against (a) the committed fixtures tests/golden/moshi_golden.pt produced by the UNMODIFIED reference modules and
+(b) the CPU oracle on fresh seeded inputs.  Bars: hidden states / ring contents within 1e-4 max-abs relative to the
+tensor's scale (fp32 arithmetic, different summation order); sampled ids bit-equal given the same Exp(1) draws."""
+import os
+
+import pytest
+import torch
+
+from oracle import moshi_oracle as MO
+from oracle.make_golden_moshi import stx_cfgs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def moshi_golden():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "moshi_golden.pt"), weights_only=False)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+def _product(cfg, sd):
+    from uniaudio2_b200.llm_modules.transformer import StreamingTransformer
+
+    m = StreamingTransformer(d_model=cfg.d_model, num_heads=cfg.num_heads, num_layers=cfg.num_layers,
+                             dim_feedforward=cfg.dim_feedforward, causal=cfg.causal, context=cfg.context,
+                             positional_embedding=cfg.positional_embedding, max_period=cfg.max_period,
+                             positional_scale=cfg.positional_scale, norm=cfg.norm, layer_scale=cfg.layer_scale,
+                             gating=cfg.gating, weights_per_step=cfg.weights_per_step)
+    m.load_state_dict(sd, strict=True)
+    return m.to("cuda:0")
+
+
+@pytest.mark.parametrize("name", ["mimi_like", "lm_like", "dep_like", "sin_like"])
+def test_streaming_transformer_matches_reference_golden(moshi_golden, name):
+    cfg = stx_cfgs()[name]
+    fx = moshi_golden[name]
+    m = _product(cfg, MO.random_state_dict(cfg, seed=2025))
+    y = m(fx["x_nonstream"].cuda())
+    assert _rel(y.cpu(), fx["y_nonstream"]) < TOL, f"{name}: non-streaming forward"
+    n = len(fx["schedule"])
+    with m.streaming(fx["batch"]):
+        assert m.is_streaming
+        for i, (x, yref) in enumerate(zip(fx["xs"], fx["ys"])):
+            if i == n:
+                m.reset_streaming()
+            y = m(x.cuda())
+            assert _rel(y.cpu(), yref) < TOL, f"{name}: streaming call {i} (T = {x.shape[1]})"
+        k, v, end = m.streaming_kv(cfg.num_layers - 1)
+        torch.cuda.synchronize()
+        assert end == fx["last_end"]
+        assert _rel(k.cpu(), fx["last_cache"][0]) < TOL and _rel(v.cpu(), fx["last_cache"][1]) < TOL
+    assert not m.is_streaming
+    with pytest.raises(ValueError):
+        m.reset_streaming()
+
+
+def test_streaming_equals_oracle_on_fresh_inputs_and_long_run():
+    """Far past the ring wrap (5 x capacity), one step at a time and in ragged chunks, batch 3."""
+    cfg = MO.StxCfg(d_model=256, num_heads=4, num_layers=2, dim_feedforward=768, context=10, positional_embedding="rope",
+                    norm="rms_norm_f32", gating="silu")
+    sd = MO.random_state_dict(cfg, seed=77)
+    m = _product(cfg, sd)
+    orc = MO.StxOracle(cfg, sd)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad(), m.streaming(3):
+        orc.start_streaming(3)
+        for T in [1] * 23 + [3, 2, 5, 1, 4, 10, 1, 1, 7]:
+            x = torch.randn(3, T, cfg.d_model, generator=g)
+            assert _rel(m(x.cuda()).cpu(), orc.forward(x)) < TOL, f"T = {T} at offset {orc.state['offset']}"
+
+
+@pytest.mark.parametrize("norm,gating", [("rms_norm", "none"), ("layer_norm", "silu"), ("layer_norm_f32", "silu")])
+def test_remaining_norm_feed_forward_combinations(norm, gating):
+    """RMSNorm in front of the GELU feed-forward and LayerNorm in front of the SiLU gating (the golden configurations hold
+    the other two pairings); hidden = 21 d / 8 = 336 is not a multiple of 128."""
+    cfg = MO.StxCfg(d_model=128, num_heads=4, num_layers=2, dim_feedforward=512, context=6, positional_embedding="rope",
+                    norm=norm, gating=gating, layer_scale=0.3)
+    sd = MO.random_state_dict(cfg, seed=11)
+    m = _product(cfg, sd)
+    orc = MO.StxOracle(cfg, sd)
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad(), m.streaming(2):
+        orc.start_streaming(2)
+        for T in [1, 2, 1, 3, 1, 1, 2, 1]:
+            x = torch.randn(2, T, cfg.d_model, generator=g)
+            assert _rel(m(x.cuda()).cpu(), orc.forward(x)) < TOL, f"T = {T} at offset {orc.state['offset']}"
+
+
+def test_non_causal_and_context_free_forward():
+    cfg = MO.StxCfg(d_model=128, num_heads=2, num_layers=1, dim_feedforward=256, causal=False, context=None,
+                    positional_embedding="sin", norm="layer_norm", gating="none", layer_scale=0.1)
+    sd = MO.random_state_dict(cfg, seed=3)
+    m = _product(cfg, sd)
+    x = torch.randn(2, 37, cfg.d_model, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = MO.StxOracle(cfg, sd).forward(x)
+    assert _rel(m(x.cuda()).cpu(), ref) < TOL
+    with pytest.raises(RuntimeError):  # no context, no weights_per_step: no capacity for a ring (transformer.py:341-343)
+        m.streaming_forever(1)
+
+
+def test_many_row_forward_takes_the_tiled_path():
+    """B * T >= 128 rows: the linears run on the tiled GEMM core where an instance exists."""
+    cfg = MO.StxCfg(d_model=256, num_heads=4, num_layers=1, dim_feedforward=512, context=40, positional_embedding="rope",
+                    norm="layer_norm", gating="none", layer_scale=0.5)
+    sd = MO.random_state_dict(cfg, seed=5)
+    m = _product(cfg, sd)
+    x = torch.randn(2, 150, cfg.d_model, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = MO.StxOracle(cfg, sd).forward(x)
+    assert _rel(m(x.cuda()).cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("hs", [32, 64, 128])
+def test_ring_attention_operator(hs):
+    """ua2_rope_ring_append_f32 + ua2_ring_attn_f32 against the restated RingKVCache / SDPA, wrapped ring, T = 3."""
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    B, H, cap, T, offset, context = 2, 3, 9, 3, 20, 7
+    C = H * hs
+    g = torch.Generator().manual_seed(hs)
+    ring = MO.RingKV(B, H, hs, cap)
+    for t0 in range(0, offset, 4):  # history written in chunks of 4 (positions 0..19)
+        n = min(4, offset - t0)
+        ring.complete(torch.randn(B, H, n, hs, generator=g), torch.randn(B, H, n, hs, generator=g))
+    kc, vc = ring.cache[0].clone().cuda(), ring.cache[1].clone().cuda()
+    qkv = torch.randn(B, T, 3, H, hs, generator=g)
+    q, k, v = qkv.permute(2, 0, 3, 1, 4)
+    off_t = torch.full((1,), offset, dtype=torch.long)
+    qr, kr = MO.apply_rope(q, k, off_t, 10000.0)
+    keys, values, pos_k = ring.complete(kr, v)
+    pos_q = off_t + torch.arange(T).view(-1, 1)
+    delta = pos_q - pos_k.view(1, -1)
+    bias = (pos_k.view(1, -1) >= 0) & (delta >= 0) & (delta < context)
+    ref = torch.nn.functional.scaled_dot_product_attention(qr, keys, values, bias).permute(0, 2, 1, 3).reshape(B * T, C)
+
+    pos = (offset + torch.arange(B * T) % T).int().cuda()
+    bidx = (torch.arange(B * T) // T).int().cuda()
+    freqs = MO.rope_freqs(hs, 10000.0).cuda()
+    qkv_d = qkv.reshape(B * T, 3 * C).contiguous().cuda()
+    q_out = torch.empty(B * T, C, device="cuda")
+    y = torch.empty(B * T, C, device="cuda")
+    st = _lib.current_stream()
+    _lib.check(L.ua2_rope_ring_append_f32(_lib.ptr(qkv_d), 3 * C, _lib.ptr(pos), _lib.ptr(bidx), _lib.ptr(freqs), _lib.ptr(q_out),
+                                          _lib.ptr(kc), _lib.ptr(vc), B * T, H, hs, cap, 1, st))
+    _lib.check(L.ua2_ring_attn_f32(_lib.ptr(q_out), _lib.ptr(kc), _lib.ptr(vc), _lib.ptr(pos), _lib.ptr(bidx), _lib.ptr(y), B * T, H,
+                                   hs, cap, offset + T, 1, 1, context, st))
+    torch.cuda.synchronize()
+    assert _rel(kc.cpu(), ring.cache[0]) < 1e-5 and torch.equal(vc.cpu(), ring.cache[1])
+    assert _rel(q_out.cpu(), qr.permute(0, 2, 1, 3).reshape(B * T, C)) < 1e-5
+    assert _rel(y.cpu(), ref) < TOL
+
+
+def test_sample_token_matches_reference_golden(moshi_golden):
+    from uniaudio2_b200.llm_utils import sampling as S
+
+    n = 0
+    for key, fx in moshi_golden.items():
+        if not key.startswith("sampler_"):
+            continue
+        kw = dict(fx["kwargs"])
+        end_token = kw.pop("end_token", None)
+        lg = fx["logits"].cuda()
+        if end_token is None:
+            tok = S.sample_token(lg, noise=fx["q"], **kw)
+        else:
+            tok = S.sample_token_audio(lg, end_token=end_token, noise=fx["q"], **kw)
+        assert tok.dtype == torch.int64 and tok.shape == fx["tokens"].shape
+        assert torch.equal(tok.cpu(), fx["tokens"]), key
+        n += 1
+    assert n >= 9
+
+
+@pytest.mark.parametrize("V,k", [(2048, 250), (32000, 25), (128256, 50), (1000, 1000), (70, 1)])
+def test_sample_token_topk_equals_oracle(V, k):
+    from uniaudio2_b200.llm_utils.sampling import sample_token
+
+    g = torch.Generator().manual_seed(V + k)
+    logits = torch.randn(4, 2, V, generator=g) * 2.5
+    q = torch.empty(8, k).exponential_(1, generator=g)
+    ref = MO.sample_token(logits, use_sampling=True, temp=0.85, top_k=k, q=q)
+    got = sample_token(logits.cuda(), use_sampling=True, temp=0.85, top_k=k, noise=q)
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_sample_token_plain_top_p_and_greedy_equal_oracle():
+    from uniaudio2_b200.llm_utils.sampling import sample_token
+
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randn(5, 3000, generator=g) * 2.0
+    q = torch.empty(5, 3000).exponential_(1, generator=g)
+    assert torch.equal(sample_token(logits.cuda()).cpu(), logits.argmax(-1))
+    ref = MO.sample_token(logits, use_sampling=True, temp=1.2, q=q)
+    assert torch.equal(sample_token(logits.cuda(), use_sampling=True, temp=1.2, noise=q).cpu(), ref)
+    for top_p in (0.3, 0.9):
+        ref = MO.sample_token(logits, use_sampling=True, temp=0.9, top_p=top_p, q=q)
+        assert torch.equal(sample_token(logits.cuda(), use_sampling=True, temp=0.9, top_p=top_p, noise=q).cpu(), ref), top_p
+
+
+def test_sample_token_draws_like_the_reference_from_the_device_generator():
+    """Without explicit noise the draws come from torch's CUDA generator with the reference's shapes (sampling.py:41)."""
+    from uniaudio2_b200.llm_utils.sampling import sample_token
+
+    logits = (torch.randn(6, 512, generator=torch.Generator().manual_seed(0)) * 2).cuda()
+    torch.manual_seed(123)
+    a = sample_token(logits, use_sampling=True, temp=0.8, top_k=20)
+    torch.manual_seed(123)
+    q = torch.empty(6, 20, device="cuda").exponential_(1)
+    b = MO.sample_token(logits.cpu(), use_sampling=True, temp=0.8, top_k=20, q=q.cpu())
+    assert torch.equal(a.cpu(), b)

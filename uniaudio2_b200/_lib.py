@@ -33,6 +33,13 @@ class CodecCfg(C.Structure):
                 ("resample_stride", C.c_int32), ("max_period", C.c_float)]
 
 
+class StxCfg(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("num_heads", C.c_int32), ("num_layers", C.c_int32), ("causal", C.c_int32),
+                ("context", C.c_int32), ("positional_embedding", C.c_int32), ("norm", C.c_int32), ("gating", C.c_int32),
+                ("weights_per_step", C.c_int32), ("layer_scale", C.c_int32), ("dim_feedforward", C.c_int32 * 64),
+                ("max_period", C.c_float), ("positional_scale", C.c_float)]
+
+
 # every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -85,6 +92,20 @@ SYMBOLS = {
     "ua2_codec_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "ua2_sample_topk_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, _P, C.c_uint64,
                                       C.c_uint64, _P, _P]),
+    "ua2_rope_ring_append_f32": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_ring_attn_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                    C.c_int, _P]),
+    "ua2_sample_token_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, _P, C.c_uint64,
+                                       C.c_uint64, _P, _P]),
+    "ua2_stx_create": (C.c_int, [C.POINTER(StxCfg), C.POINTER(_P)]),
+    "ua2_stx_destroy": (C.c_int, [_P]),
+    "ua2_stx_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_stx_finalize": (C.c_int, [_P]),
+    "ua2_stx_start_streaming": (C.c_int, [_P, C.c_int, _P]),
+    "ua2_stx_stop_streaming": (C.c_int, [_P]),
+    "ua2_stx_reset_streaming": (C.c_int, [_P]),
+    "ua2_stx_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
+    "ua2_stx_get_kv": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
 }
 
 

@@ -568,6 +568,11 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
   UA2_CASE(PRO_ATTN, EPI_SCALE_RESADD)
   UA2_CASE(PRO_PLAIN, EPI_SCALE_RESADD)
   UA2_CASE(PRO_PLAIN, EPI_QKV_IL)
+  // Moshi-family streaming layer (ua2_stream.cu): LayerNorm in front of a plain store (in_proj before the ring append) and
+  // of the SiLU gating, RMSNorm in front of the GELU feed-forward
+  UA2_CASE(PRO_LAYERNORM, EPI_STORE)
+  UA2_CASE(PRO_LAYERNORM, EPI_SWIGLU)
+  UA2_CASE(PRO_RMSNORM, EPI_GELU)
 #undef UA2_CASE
   return cudaErrorInvalidValue;
 }
