@@ -95,6 +95,23 @@ def test_remaining_norm_feed_forward_combinations(norm, gating):
             assert _rel(m(x.cuda()).cpu(), orc.forward(x)) < TOL, f"T = {T} at offset {orc.state['offset']}"
 
 
+def test_long_ring_is_split_across_ctas():
+    """context 700 > 256 slots: the ring attention runs as 3 splits + combine; fed in chunks of 7 past the wrap."""
+    cfg = MO.StxCfg(d_model=128, num_heads=4, num_layers=1, dim_feedforward=256, context=700, positional_embedding="rope",
+                    norm="layer_norm", gating="none")
+    sd = MO.random_state_dict(cfg, seed=13)
+    m = _product(cfg, sd)
+    orc = MO.StxOracle(cfg, sd)
+    g = torch.Generator().manual_seed(8)
+    with torch.no_grad(), m.streaming(1):
+        orc.start_streaming(1)
+        for i in range(110):
+            x = torch.randn(1, 7, cfg.d_model, generator=g)
+            y, yref = m(x.cuda()), orc.forward(x)
+            if i % 10 == 9 or i > 98:
+                assert _rel(y.cpu(), yref) < TOL, f"chunk {i}"
+
+
 def test_non_causal_and_context_free_forward():
     cfg = MO.StxCfg(d_model=128, num_heads=2, num_layers=1, dim_feedforward=256, causal=False, context=None,
                     positional_embedding="sin", norm="layer_norm", gating="none", layer_scale=0.1)

@@ -13,10 +13,12 @@
 // norm fused into the prologue and residual / LayerScale / SwiGLU / GELU into the epilogue; per-step weights
 // (multi_linear) are pointer offsets into the stacked weight, one launch per time step.  New here:
 //   rope_ring_append_kernel  q/k rotation + append of k, v at slot pos % capacity          (activations only)
-//   ring_attn_kernel         one CTA per (head, query row): keys are read once with coalesced 128-bit loads (a group of
-//                            hs/4 lanes per key), online softmax per group, merged through shared memory.  Slot
-//                            positions are recovered from end_offset exactly like RingKVCache.complete, including its
-//                            `delta <= 0` quirk.  Bytes per launch = 2 * B * H * min(end, cap) * hs * 4 (HBM/L2 bound).
+//   ring_attn_kernel         one CTA per (head, query row, split of <= ~256 slots): keys are read once with coalesced
+//                            128-bit loads (a group of hs/4 lanes per key, two keys in flight per group), online softmax
+//                            per group, merged through shared memory; rings longer than 256 slots are split across CTAs
+//                            and merged by ring_attn_combine_kernel.  Slot positions are recovered from end_offset exactly
+//                            like RingKVCache.complete, including its `delta <= 0` quirk.
+//                            Bytes per launch = 2 * B * H * min(end, cap) * hs * 4 (HBM/L2 bound).
 //   sample_token_kernel      one CTA per row: softmax statistics, then plain / top-k (4-pass radix select + rank
 //                            counting, one noise draw per RANK like torch.topk + multinomial) / top-p (bitonic sort in
 //                            shared memory, double-precision running sum like ATen's CPU cumsum).  Bytes = 4 * V per pass.
@@ -42,6 +44,11 @@ struct RingAttnParams {
   int M, H, cap;
   long long end;  // keys written so far, this call's included
   int ring, causal, context;
+  // split-softmax over the slots (long rings): CTA z handles slots [z * per_split, (z + 1) * per_split) and, when
+  // n_splits > 1, writes un-normalised partials (max, sum, acc) that ring_attn_combine_kernel merges
+  int n_splits, per_split;
+  float* part_ml;   // (M, H, n_splits, 2)
+  float* part_acc;  // (M, H, n_splits, hs)
 };
 
 // RingKVCache.complete, transformer.py:254-276 (ring) / KVCacheResult.from_kv :200-205 (linear)
@@ -54,6 +61,9 @@ __device__ __forceinline__ long long slot_position(int j, long long end, int cap
 }
 
 constexpr int RA_WARPS = 8;
+constexpr int RA_UNROLL = 2;         // keys per group per iteration (all their loads are issued before the first use)
+constexpr int RA_SPLIT_KEYS = 256;   // slots per CTA from which the ring is split across CTAs
+constexpr int RA_MAX_SPLITS = 16;
 
 template <int HS>
 __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttnParams p) {
@@ -62,7 +72,7 @@ __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttn
   constexpr int NG = RA_WARPS * KPW;   // independent online-softmax groups in the CTA
   __shared__ float s_m[NG], s_l[NG];
   __shared__ __align__(16) float s_acc[NG][HS];
-  const int h = blockIdx.x, m = blockIdx.y;
+  const int h = blockIdx.x, m = blockIdx.y, z = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane / LPK, d4 = lane - sub * LPK;
   const int grp = warp * KPW + sub;
@@ -74,39 +84,48 @@ __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttn
   const float scale = rsqrtf((float)HS);
   const float* Kb = p.kc + ((size_t)b * p.H + h) * (size_t)p.cap * HS;
   const float* Vb = p.vc + ((size_t)b * p.H + h) * (size_t)p.cap * HS;
+  const int j_lo = z * p.per_split, j_hi = min(p.cap, j_lo + p.per_split);
   float mx = -INFINITY, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j0 = 0; j0 < p.cap; j0 += NG) {
-    const int j = j0 + grp;
-    bool vis = false;
-    if (j < p.cap) {
-      const long long pk = slot_position(j, p.end, p.cap, p.ring);
-      const long long delta = pq - pk;
-      vis = pk >= 0 && (!p.causal || (delta >= 0 && (p.context <= 0 || delta < p.context)));
-    }
-    float s = 0.f;
-    float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vis) {  // uniform over the LPK lanes of a group
-      const float4 kv = *reinterpret_cast<const float4*>(Kb + (size_t)j * HS + d4 * 4);
-      vv = *reinterpret_cast<const float4*>(Vb + (size_t)j * HS + d4 * 4);
-      s = fmaf(kv.x, qv.x, s);
-      s = fmaf(kv.y, qv.y, s);
-      s = fmaf(kv.z, qv.z, s);
-      s = fmaf(kv.w, qv.w, s);
+  for (int j0 = j_lo; j0 < j_hi; j0 += RA_UNROLL * NG) {
+    bool vis[RA_UNROLL];
+    float4 kv[RA_UNROLL], vv[RA_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RA_UNROLL; ++u) {
+      const int j = j0 + u * NG + grp;
+      vis[u] = false;
+      if (j < j_hi) {
+        const long long pk = slot_position(j, p.end, p.cap, p.ring);
+        const long long delta = pq - pk;
+        vis[u] = pk >= 0 && (!p.causal || (delta >= 0 && (p.context <= 0 || delta < p.context)));
+      }
+      kv[u] = vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vis[u]) {  // uniform over the LPK lanes of a group
+        kv[u] = *reinterpret_cast<const float4*>(Kb + (size_t)j * HS + d4 * 4);
+        vv[u] = *reinterpret_cast<const float4*>(Vb + (size_t)j * HS + d4 * 4);
+      }
     }
 #pragma unroll
-    for (int o = LPK >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (vis) {
-      s *= scale;
-      const float mn = fmaxf(mx, s);
-      const float c = expf(mx - mn);  // first key: exp(-inf) = 0
-      const float e = expf(s - mn);
-      l = fmaf(l, c, e);
-      acc.x = fmaf(acc.x, c, e * vv.x);
-      acc.y = fmaf(acc.y, c, e * vv.y);
-      acc.z = fmaf(acc.z, c, e * vv.z);
-      acc.w = fmaf(acc.w, c, e * vv.w);
-      mx = mn;
+    for (int u = 0; u < RA_UNROLL; ++u) {
+      float s = 0.f;
+      s = fmaf(kv[u].x, qv.x, s);
+      s = fmaf(kv[u].y, qv.y, s);
+      s = fmaf(kv[u].z, qv.z, s);
+      s = fmaf(kv[u].w, qv.w, s);
+#pragma unroll
+      for (int o = LPK >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (vis[u]) {
+        s *= scale;
+        const float mn = fmaxf(mx, s);
+        const float c = expf(mx - mn);  // first key: exp(-inf) = 0
+        const float e = expf(s - mn);
+        l = fmaf(l, c, e);
+        acc.x = fmaf(acc.x, c, e * vv[u].x);
+        acc.y = fmaf(acc.y, c, e * vv[u].y);
+        acc.z = fmaf(acc.z, c, e * vv[u].z);
+        acc.w = fmaf(acc.w, c, e * vv[u].w);
+        mx = mn;
+      }
     }
   }
   if (d4 == 0) {
@@ -128,18 +147,63 @@ __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttn
         num = fmaf(w, s_acc[g][d], num);
       }
     }
-    p.y[((size_t)m * p.H + h) * HS + d] = num / den;  // no visible key: 0 / 0 = NaN, like SDPA on a fully masked row
+    const size_t row = (size_t)m * p.H + h;
+    if (p.n_splits <= 1) {
+      p.y[row * HS + d] = num / den;  // no visible key: 0 / 0 = NaN, like SDPA on a fully masked row
+    } else {
+      p.part_acc[(row * p.n_splits + z) * HS + d] = num;
+      if (d == 0) {
+        p.part_ml[(row * p.n_splits + z) * 2] = gm;
+        p.part_ml[(row * p.n_splits + z) * 2 + 1] = den;
+      }
+    }
   }
 }
 
-cudaError_t launch_ring_attn(const LaunchCtx& lc, const RingAttnParams& p, int hs) {
-  const dim3 grid(p.H, p.M), block(RA_WARPS * 32);
+// merge of the split partials: one thread per output element
+__global__ void ring_attn_combine_kernel(const RingAttnParams p, int hs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.M * p.H * hs) return;
+  const size_t row = (size_t)(idx / hs);
+  const int d = (int)(idx - (long long)row * hs);
+  float gm = -INFINITY;
+  for (int z = 0; z < p.n_splits; ++z) gm = fmaxf(gm, p.part_ml[(row * p.n_splits + z) * 2]);
+  float den = 0.f, num = 0.f;
+  for (int z = 0; z < p.n_splits; ++z) {
+    const float mz = p.part_ml[(row * p.n_splits + z) * 2];
+    if (mz > -INFINITY) {
+      const float w = expf(mz - gm);
+      den = fmaf(w, p.part_ml[(row * p.n_splits + z) * 2 + 1], den);
+      num = fmaf(w, p.part_acc[(row * p.n_splits + z) * hs + d], num);
+    }
+  }
+  p.y[idx] = num / den;
+}
+
+// splits for a ring of `cap` slots (1 = the attention kernel writes y itself)
+int ring_attn_splits(int cap) {
+  int s = (cap + RA_SPLIT_KEYS - 1) / RA_SPLIT_KEYS;
+  return s < 1 ? 1 : (s > RA_MAX_SPLITS ? RA_MAX_SPLITS : s);
+}
+
+// p.n_splits > 1 needs p.part_ml / p.part_acc; per_split is derived here
+cudaError_t launch_ring_attn(const LaunchCtx& lc, RingAttnParams p, int hs) {
+  if (p.n_splits < 1) p.n_splits = 1;
+  if (p.n_splits > 1 && (p.part_ml == nullptr || p.part_acc == nullptr)) return cudaErrorInvalidValue;
+  p.per_split = (p.cap + p.n_splits - 1) / p.n_splits;
+  const dim3 grid(p.H, p.M, p.n_splits), block(RA_WARPS * 32);
+  cudaError_t e;
   switch (hs) {
-    case 128: return launch(lc, ring_attn_kernel<128>, grid, block, 0, p);
-    case 64: return launch(lc, ring_attn_kernel<64>, grid, block, 0, p);
-    case 32: return launch(lc, ring_attn_kernel<32>, grid, block, 0, p);
+    case 128: e = launch(lc, ring_attn_kernel<128>, grid, block, 0, p); break;
+    case 64: e = launch(lc, ring_attn_kernel<64>, grid, block, 0, p); break;
+    case 32: e = launch(lc, ring_attn_kernel<32>, grid, block, 0, p); break;
     default: return cudaErrorInvalidValue;
   }
+  if (e != cudaSuccess || p.n_splits == 1) return e;
+  const long long n = (long long)p.M * p.H * hs;
+  return launch(lc, ring_attn_combine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p, hs);
 }
 
 // ------------------------------------------------------------------------------------------------ RoPE + cache append
@@ -492,6 +556,7 @@ struct ua2_stx {
   // workspace for M rows
   size_t rows = 0;
   float *xt = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *hb = nullptr, *tk = nullptr, *tv = nullptr, *stats = nullptr;
+  float *part_ml = nullptr, *part_acc = nullptr;  // split-softmax partials of the ring attention (RA_MAX_SPLITS per row)
   int32_t *pos = nullptr, *bidx = nullptr;
 };
 
@@ -505,9 +570,9 @@ namespace {
 
 void free_ws(ua2_stx* h) {
   for (void* p : {(void*)h->xt, (void*)h->qkv, (void*)h->q, (void*)h->att, (void*)h->hb, (void*)h->tk, (void*)h->tv,
-                  (void*)h->stats, (void*)h->pos, (void*)h->bidx})
+                  (void*)h->stats, (void*)h->part_ml, (void*)h->part_acc, (void*)h->pos, (void*)h->bidx})
     if (p) cudaFree(p);
-  h->xt = h->qkv = h->q = h->att = h->hb = h->tk = h->tv = h->stats = nullptr;
+  h->xt = h->qkv = h->q = h->att = h->hb = h->tk = h->tv = h->stats = h->part_ml = h->part_acc = nullptr;
   h->pos = h->bidx = nullptr;
   h->rows = 0;
 }
@@ -535,6 +600,8 @@ int reserve_rows(ua2_stx* h, size_t M) {
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->tk, M * C * 4));
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->tv, M * C * 4));
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->stats, (2 * M + 8) * 4));
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->part_ml, M * h->cfg.num_heads * RA_MAX_SPLITS * 2 * 4));
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->part_acc, M * C * RA_MAX_SPLITS * 4));
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->pos, M * 4));
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->bidx, M * 4));
   h->rows = M;
@@ -624,7 +691,21 @@ int ua2_ring_attn_f32(const float* q, const float* k_cache, const float* v_cache
   UA2_REQUIRE(hs == 32 || hs == 64 || hs == 128, "head size must be 32 / 64 / 128");
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
-  RingAttnParams p{q, k_cache, v_cache, pos, bidx, y, M, H, cap, (long long)end_offset, ring, causal, context};
+  RingAttnParams p{};
+  p.q = q;
+  p.kc = k_cache;
+  p.vc = v_cache;
+  p.pos = pos;
+  p.bidx = bidx;
+  p.y = y;
+  p.M = M;
+  p.H = H;
+  p.cap = cap;
+  p.end = end_offset;
+  p.ring = ring;
+  p.causal = causal;
+  p.context = context;
+  p.n_splits = 1;  // the operator form has no workspace: one CTA per (head, row) walks the whole ring
   UA2_CHECK_CUDA(launch_ring_attn(lc, p, hs));
   return UA2_OK;
 }
@@ -907,7 +988,23 @@ int ua2_stx_forward(ua2_stx* h, const float* x, float* y, int B, int T, void* st
                              (const float*)h->qkv, 3 * C, (const int32_t*)h->pos, (const int32_t*)h->bidx,
                              rope ? h->rope_freqs : (const float*)nullptr, h->q, kc, vc, M, H, hs, cap, h->streaming ? 1 : 0);
       if (e == cudaSuccess) {
-        RingAttnParams a{h->q, kc, vc, h->pos, h->bidx, h->att, M, H, cap, end, h->streaming ? 1 : 0, c.causal, c.context};
+        RingAttnParams a{};
+        a.q = h->q;
+        a.kc = kc;
+        a.vc = vc;
+        a.pos = h->pos;
+        a.bidx = h->bidx;
+        a.y = h->att;
+        a.M = M;
+        a.H = H;
+        a.cap = cap;
+        a.end = end;
+        a.ring = h->streaming ? 1 : 0;
+        a.causal = c.causal;
+        a.context = c.context;
+        a.n_splits = ring_attn_splits(cap);
+        a.part_ml = h->part_ml;
+        a.part_acc = h->part_acc;
         e = launch_ring_attn(lc, a, hs);
       }
       if (e != cudaSuccess) {
