@@ -335,6 +335,11 @@ int ua2_stx_reset_streaming(ua2_stx* h);
  * Streaming: B must equal the streaming batch size, T <= capacity, and offset + T <= weights_per_step when per-step
  * weights are used (the reference indexes past the weight slab otherwise). */
 int ua2_stx_forward(ua2_stx* h, const float* x, float* y, int B, int T, void* stream);
+/* knobs: "graph" (0/1, default 1: streaming calls replay the layer stack as a CUDA graph per (batch, T, weight step)),
+ * "pdl" (0/1, default 1: programmatic dependent launch between the kernels of a streaming call) */
+int ua2_stx_set_option(ua2_stx* h, const char* name, int value);
+/* kernels launched (or graph kernel nodes replayed) by the last forward */
+int ua2_stx_last_launch_count(ua2_stx* h);
 /* introspection: ring buffers (batch, H, capacity, hs) of a layer and the number of keys written so far */
 int ua2_stx_get_kv(ua2_stx* h, int layer, float** k, float** v, int64_t* end_offset, int* capacity);
 

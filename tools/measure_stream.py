@@ -43,8 +43,9 @@ def main():
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    for name, kw in SHAPES.items():
+    for name, kw, graph in [(n, k, g) for n, k in SHAPES.items() for g in (0, 1)]:
         m = StreamingTransformer(device=dev, **kw)
+        m.set_option("graph", graph)
         B = a.batch
         x = torch.randn(B, 1, kw["d_model"], device=dev)
         wps = kw.get("weights_per_step", 0)
@@ -70,7 +71,8 @@ def main():
         med = ts[len(ts) // 2]
         keys = cap if not wps else (wps + 1) // 2
         by = step_bytes(m, B, keys)
-        print(json.dumps(dict(shape=name, batch=B, ms_per_step=round(med, 4), p10=round(ts[len(ts) // 10], 4),
+        print(json.dumps(dict(shape=name, graph_pdl=graph, launches=m.last_launch_count(), batch=B, ms_per_step=round(med, 4),
+                              p10=round(ts[len(ts) // 10], 4),
                               algorithmic_MB=round(by / 1e6, 2), GBps=round(by / med / 1e6, 1), l2="flushed between steps")))
         del m
         torch.cuda.empty_cache()

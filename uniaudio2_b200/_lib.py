@@ -105,6 +105,8 @@ SYMBOLS = {
     "ua2_stx_stop_streaming": (C.c_int, [_P]),
     "ua2_stx_reset_streaming": (C.c_int, [_P]),
     "ua2_stx_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
+    "ua2_stx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "ua2_stx_last_launch_count": (C.c_int, [_P]),
     "ua2_stx_get_kv": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
 }
 

@@ -43,6 +43,7 @@ struct RingAttnParams {
   float* y;  // (M, H*hs)
   int M, H, cap;
   long long end;  // keys written so far, this call's included
+  const long long* end_ptr;  // non-null: read `end` from device memory instead (captured graphs stay valid as it advances)
   int ring, causal, context;
   // split-softmax over the slots (long rings): CTA z handles slots [z * per_split, (z + 1) * per_split) and, when
   // n_splits > 1, writes un-normalised partials (max, sum, acc) that ring_attn_combine_kernel merges
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttn
   pdl_wait();
   const int b = p.bidx[m];
   const long long pq = p.pos[m];
+  const long long end = p.end_ptr ? *p.end_ptr : p.end;
   const float4 qv = *reinterpret_cast<const float4*>(p.q + ((size_t)m * p.H + h) * HS + d4 * 4);
   const float scale = rsqrtf((float)HS);
   const float* Kb = p.kc + ((size_t)b * p.H + h) * (size_t)p.cap * HS;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttn
       const int j = j0 + u * NG + grp;
       vis[u] = false;
       if (j < j_hi) {
-        const long long pk = slot_position(j, p.end, p.cap, p.ring);
+        const long long pk = slot_position(j, end, p.cap, p.ring);
         const long long delta = pq - pk;
         vis[u] = pk >= 0 && (!p.causal || (delta >= 0 && (p.context <= 0 || delta < p.context)));
       }
@@ -149,7 +151,9 @@ __global__ void __launch_bounds__(RA_WARPS * 32) ring_attn_kernel(const RingAttn
     }
     const size_t row = (size_t)m * p.H + h;
     if (p.n_splits <= 1) {
-      p.y[row * HS + d] = num / den;  // no visible key: 0 / 0 = NaN, like SDPA on a fully masked row
+      // a row without any visible key (e.g. T = capacity: the first query's own key sits in the slot that reports a future
+      // position) gives 0 like torch's SDPA, which routes fully masked rows through its safe softmax
+      p.y[row * HS + d] = den > 0.f ? num / den : 0.f;
     } else {
       p.part_acc[(row * p.n_splits + z) * HS + d] = num;
       if (d == 0) {
@@ -179,7 +183,7 @@ __global__ void ring_attn_combine_kernel(const RingAttnParams p, int hs) {
       num = fmaf(w, p.part_acc[(row * p.n_splits + z) * hs + d], num);
     }
   }
-  p.y[idx] = num / den;
+  p.y[idx] = den > 0.f ? num / den : 0.f;
 }
 
 // splits for a ring of `cap` slots (1 = the attention kernel writes y itself)
@@ -244,13 +248,15 @@ __global__ void rope_ring_append_kernel(const float* __restrict__ qkv, int ld, c
 }
 
 // xt = x + positional_scale * [cos(pos / denom) | sin(pos / denom)]  (create_sin_embedding, transformer.py:126-152);
-// denoms == nullptr: plain copy.  pos[m] = offset + m % T, bidx[m] = m / T are written on the way.
+// denoms == nullptr: plain copy.  pos[m] = offset + m % T, bidx[m] = m / T and the ring's end_offset after this call are
+// written on the way (per-call scalars live in device memory so that the captured layer graph stays valid).
 __global__ void stx_begin_kernel(const float* __restrict__ x, float* __restrict__ xt, int32_t* __restrict__ pos,
                                  int32_t* __restrict__ bidx, const float* __restrict__ denoms, float pscale, int M, int T, int C,
-                                 int offset) {
+                                 int offset, long long end_after, long long* __restrict__ d_end) {
   pdl_launch_dependents();
   pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *d_end = end_after;
   if (idx >= (long long)M * C) return;
   const int m = (int)(idx / C), c = (int)(idx - (long long)m * C);
   const int ps = offset + m % T;
@@ -269,7 +275,7 @@ __global__ void stx_begin_kernel(const float* __restrict__ x, float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ sample_token
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 1024;
 constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_MAX_K = 1024;
 constexpr int ST_MAX_SORT = 4096;
@@ -341,11 +347,12 @@ __global__ void __launch_bounds__(ST_THREADS) sample_token_kernel(const SampleTo
   __shared__ int sh_i[ST_WARPS];
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix, s_mask;
-  __shared__ int s_remaining, s_ncand;
+  __shared__ int s_remaining, s_ncand, s_total_eq;
   __shared__ uint32_t cand_key[ST_MAX_K];
   __shared__ int cand_idx[ST_MAX_K];
   __shared__ int rank_idx[ST_MAX_K];
-  __shared__ int eq_cnt[ST_THREADS];
+  static_assert(ST_MAX_K >= ST_THREADS, "eq_cnt aliases rank_idx");
+  int* eq_cnt = rank_idx;  // per-thread tie counts: dead before the ranks are written
   const int tid = threadIdx.x;
   const int row = blockIdx.x, V = a.V;
   const float* lg = a.logits + (size_t)row * V;
@@ -448,7 +455,7 @@ __global__ void __launch_bounds__(ST_THREADS) sample_token_kernel(const SampleTo
     s_ncand = 0;
   }
   for (int shift = 24; shift >= 0; shift -= 8) {
-    hist[tid] = 0;  // ST_THREADS == 256 bins
+    if (tid < 256) hist[tid] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix, mask = s_mask;
     for (int i = tid; i < V; i += ST_THREADS) {
@@ -464,6 +471,7 @@ __global__ void __launch_bounds__(ST_THREADS) sample_token_kernel(const SampleTo
         cum += hist[bsel];
       }
       s_remaining = rem - cum;
+      s_total_eq = hist[bsel];  // after the last pass: how many entries carry exactly the threshold key
       s_prefix = prefix | ((uint32_t)bsel << shift);
       s_mask = mask | (0xFFu << shift);
     }
@@ -472,9 +480,10 @@ __global__ void __launch_bounds__(ST_THREADS) sample_token_kernel(const SampleTo
   const uint32_t thr = s_prefix;      // key of the k-th largest probability
   const int need_eq = s_remaining;    // how many entries equal to it belong to the top k (lowest ids first)
   const int n_gt = k - need_eq;
+  const bool ties_cut = s_total_eq > need_eq;  // only some of the entries equal to the threshold belong to the top k
   for (int i = tid; i < V; i += ST_THREADS) {
     const uint32_t key = st_key(prob(i));
-    if (key > thr) {
+    if (key > thr || (!ties_cut && key == thr)) {
       const int slot = atomicAdd(&s_ncand, 1);
       if (slot < ST_MAX_K) {
         cand_key[slot] = key;
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(ST_THREADS) sample_token_kernel(const SampleTo
       }
     }
   }
-  {  // entries equal to the threshold, in id order: contiguous chunk per thread + exclusive prefix of the counts
+  if (ties_cut) {  // the lowest ids among the tied entries: contiguous chunk per thread + exclusive prefix of the counts
     const int chunk = (V + ST_THREADS - 1) / ST_THREADS;
     const int lo = min(V, tid * chunk), hi = min(V, lo + chunk);
     int c = 0;
@@ -557,6 +566,16 @@ struct ua2_stx {
   size_t rows = 0;
   float *xt = nullptr, *qkv = nullptr, *q = nullptr, *att = nullptr, *hb = nullptr, *tk = nullptr, *tv = nullptr, *stats = nullptr;
   float *part_ml = nullptr, *part_acc = nullptr;  // split-softmax partials of the ring attention (RA_MAX_SPLITS per row)
+  long long* d_end = nullptr;  // end_offset of the rings after the current call (read by the attention kernels)
+  // streaming steps replay the layer stack as a CUDA graph with programmatic-dependent-launch edges, one graph per
+  // (batch, T, weight step): first use of a shape runs eagerly (lazy kernel attributes), second use captures
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+  };
+  std::map<unsigned long long, GraphEntry> graphs;
+  int opt_graph = 1, opt_pdl = 1;
+  int last_launches = 0;
   int32_t *pos = nullptr, *bidx = nullptr;
 };
 
@@ -568,7 +587,14 @@ namespace {
     if (_rc != UA2_OK) return _rc; \
   } while (0)
 
+void clear_graphs(ua2_stx* h) {
+  for (auto& kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+
 void free_ws(ua2_stx* h) {
+  clear_graphs(h);  // captured graphs hold the workspace addresses
   for (void* p : {(void*)h->xt, (void*)h->qkv, (void*)h->q, (void*)h->att, (void*)h->hb, (void*)h->tk, (void*)h->tv,
                   (void*)h->stats, (void*)h->part_ml, (void*)h->part_acc, (void*)h->pos, (void*)h->bidx})
     if (p) cudaFree(p);
@@ -578,6 +604,7 @@ void free_ws(ua2_stx* h) {
 }
 
 void free_rings(ua2_stx* h) {
+  clear_graphs(h);
   for (float* p : h->kc)
     if (p) cudaFree(p);
   for (float* p : h->vc)
@@ -663,6 +690,171 @@ bool parse_layer_key(const std::string& key, int& layer, std::string& rest) {
   layer = std::stoi(key.substr(i, j - i));
   rest = key.substr(j + 1);
   return true;
+}
+
+// The layer stack over the M = B*T rows staged in h->xt (positions in h->pos / h->bidx, end_offset in h->d_end): every
+// launch takes only device pointers and shape constants, so the sequence can be captured once per shape.
+int run_layers(ua2_stx* h, const LaunchCtx& lc, int B, int T, long long offset) {
+  const ua2_stx_cfg& c = h->cfg;
+  const int C = c.d_model, H = c.num_heads, hs = C / H;
+  const int M = B * T;
+  const bool per_step = c.weights_per_step > 0;
+  const bool rope = c.positional_embedding >= 2;
+  const bool ln = c.norm <= 1;
+  const float eps = (c.norm == 0 || c.norm == 2) ? 1e-5f : 1e-8f;  // create_norm_fn, transformer.py:111-121
+  const int pro_norm = ln ? PRO_LAYERNORM : PRO_RMSNORM;
+  const int epi_res = c.layer_scale ? EPI_SCALE_RESADD : EPI_RESADD;
+  const long long saved_offset = h->offset;
+  h->offset = offset;  // run_linear indexes the per-step slabs with it (0 when not streaming)
+  int rc = UA2_OK;
+  for (int li = 0; li < c.num_layers && rc == UA2_OK; ++li) {
+    const StxLayer& l = h->layers[li];
+    {  // norm1 -> in_proj
+      LinSpec s;
+      s.pro = pro_norm;
+      s.epi = EPI_STORE;
+      s.W = l.in_proj;
+      s.slab = (size_t)3 * C * C;
+      s.N = 3 * C;
+      s.K = C;
+      s.X = h->xt;
+      s.ldx = C;
+      s.Y = h->qkv;
+      s.ldy = 3 * C;
+      s.norm_w = l.n1w;
+      s.norm_b = l.n1b;
+      s.eps = eps;
+      if ((rc = run_linear(h, lc, s, B, T, per_step)) != UA2_OK) break;
+    }
+    float* kc = h->streaming ? h->kc[li] : h->tk;
+    float* vc = h->streaming ? h->vc[li] : h->tv;
+    const int cap = h->streaming ? h->cap : T;
+    {
+      const long long total = (long long)M * H * (hs / 2);
+      cudaError_t e = launch(lc, rope_ring_append_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                             (const float*)h->qkv, 3 * C, (const int32_t*)h->pos, (const int32_t*)h->bidx,
+                             rope ? h->rope_freqs : (const float*)nullptr, h->q, kc, vc, M, H, hs, cap, h->streaming ? 1 : 0);
+      if (e == cudaSuccess) {
+        RingAttnParams a{};
+        a.q = h->q;
+        a.kc = kc;
+        a.vc = vc;
+        a.pos = h->pos;
+        a.bidx = h->bidx;
+        a.y = h->att;
+        a.M = M;
+        a.H = H;
+        a.cap = cap;
+        a.end_ptr = h->d_end;
+        a.ring = h->streaming ? 1 : 0;
+        a.causal = c.causal;
+        a.context = c.context;
+        a.n_splits = ring_attn_splits(cap);
+        a.part_ml = h->part_ml;
+        a.part_acc = h->part_acc;
+        e = launch_ring_attn(lc, a, hs);
+      }
+      if (e != cudaSuccess) {
+        set_error(std::string("attention launch: ") + cudaGetErrorString(e));
+        rc = UA2_ERR_CUDA;
+        break;
+      }
+    }
+    {  // out_proj -> x + layer_scale_1 * update
+      LinSpec s;
+      s.pro = PRO_PLAIN;
+      s.epi = epi_res;
+      s.W = l.out_proj;
+      s.slab = (size_t)C * C;
+      s.N = C;
+      s.K = C;
+      s.X = h->att;
+      s.ldx = C;
+      s.Y = h->xt;
+      s.ldy = C;
+      s.R = h->xt;
+      s.ldr = C;
+      s.scale = l.ls1;
+      if ((rc = run_linear(h, lc, s, B, T, per_step)) != UA2_OK) break;
+    }
+    if (!c.gating) {  // norm2 -> linear1 -> gelu -> linear2 -> x + layer_scale_2 * update
+      LinSpec s;
+      s.pro = pro_norm;
+      s.epi = EPI_GELU;
+      s.W = l.lin1;
+      s.N = h->hidden[0];
+      s.K = C;
+      s.X = h->xt;
+      s.ldx = C;
+      s.Y = h->hb;
+      s.ldy = h->f_max;
+      s.norm_w = l.n2w;
+      s.norm_b = l.n2b;
+      s.eps = eps;
+      if ((rc = run_linear(h, lc, s, B, T, false)) != UA2_OK) break;
+      LinSpec o;
+      o.pro = PRO_PLAIN;
+      o.epi = epi_res;
+      o.W = l.lin2;
+      o.N = C;
+      o.K = h->hidden[0];
+      o.X = h->hb;
+      o.ldx = h->f_max;
+      o.Y = h->xt;
+      o.ldy = C;
+      o.R = h->xt;
+      o.ldr = C;
+      o.scale = l.ls2;
+      if ((rc = run_linear(h, lc, o, B, T, false)) != UA2_OK) break;
+    } else {  // ActivationGating: linear_in viewed (2, hidden): silu(first half) * second half, then linear_out
+      const int n_launch = per_step ? T : 1;
+      for (int t = 0; t < n_launch && rc == UA2_OK; ++t) {
+        const int step = per_step ? (int)offset + t : 0;
+        const int Hh = h->hidden[step];
+        const int rows = per_step ? B : M, mul = per_step ? T : 1;
+        GemvParams p;
+        p.W = l.g_in[step];
+        p.W2 = l.g_in[step] + (size_t)Hh * C;
+        p.N = Hh;
+        p.K = C;
+        p.M = rows;
+        p.X = h->xt + (size_t)t * C * (per_step ? 1 : 0);
+        p.ldx = C * mul;
+        p.Y = h->hb + (size_t)t * h->f_max * (per_step ? 1 : 0);
+        p.ldy = h->f_max * mul;
+        p.norm_w = l.n2w;
+        p.norm_b = l.n2b;
+        p.eps = eps;
+        p.ws = h->stats;
+        p.ws_floats = 2 * h->rows + 8;
+        cudaError_t e = launch_gemv(lc, pro_norm, EPI_SWIGLU, p);
+        if (e == cudaSuccess) {
+          GemvParams o;
+          o.W = l.g_out[step];
+          o.N = C;
+          o.K = Hh;
+          o.M = rows;
+          o.X = p.Y;
+          o.ldx = p.ldy;
+          o.Y = h->xt + (size_t)t * C * (per_step ? 1 : 0);
+          o.ldy = C * mul;
+          o.R = o.Y;
+          o.ldr = o.ldy;
+          o.scale = l.ls2;
+          o.ws = h->stats;
+          o.ws_floats = 2 * h->rows + 8;
+          e = launch_gemv(lc, PRO_PLAIN, epi_res, o);
+        }
+        if (e != cudaSuccess) {
+          set_error(std::string("gating launch: ") + cudaGetErrorString(e));
+          rc = UA2_ERR_CUDA;
+        }
+      }
+      if (rc != UA2_OK) break;
+    }
+  }
+  h->offset = saved_offset;
+  return rc;
 }
 
 }  // namespace
@@ -776,6 +968,7 @@ int ua2_stx_destroy(ua2_stx* h) {
   cudaDeviceSynchronize();
   free_ws(h);
   free_rings(h);
+  if (h->d_end) cudaFree(h->d_end);
   delete h;
   return UA2_OK;
 }
@@ -934,7 +1127,7 @@ int ua2_stx_forward(ua2_stx* h, const float* x, float* y, int B, int T, void* st
   UA2_REQUIRE(x && y, "null argument");
   UA2_REQUIRE(B >= 1 && T >= 1 && (long long)B * T <= 65535, "need B, T >= 1 and B * T <= 65535 rows per call");
   const ua2_stx_cfg& c = h->cfg;
-  const int C = c.d_model, H = c.num_heads, hs = C / H;
+  const int C = c.d_model;
   const int M = B * T;
   const bool per_step = c.weights_per_step > 0;
   const long long offset = h->streaming ? h->offset : 0;
@@ -945,175 +1138,75 @@ int ua2_stx_forward(ua2_stx* h, const float* x, float* y, int B, int T, void* st
   }
   if (per_step) UA2_REQUIRE(offset + T <= c.weights_per_step, "time step beyond weights_per_step");
   RUN(reserve_rows(h, (size_t)M));
+  if (!h->d_end) UA2_CHECK_CUDA(cudaMalloc((void**)&h->d_end, sizeof(long long)));
+  int launches = 0;
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
-  const bool rope = c.positional_embedding >= 2;
+  lc.launch_counter = &launches;
   const bool sin = c.positional_embedding == 1 || c.positional_embedding == 3;
-  const bool ln = c.norm <= 1;
-  const float eps = (c.norm == 0 || c.norm == 2) ? 1e-5f : 1e-8f;  // create_norm_fn, transformer.py:111-121
-  const int pro_norm = ln ? PRO_LAYERNORM : PRO_RMSNORM;
-  const int epi_res = c.layer_scale ? EPI_SCALE_RESADD : EPI_RESADD;
+  const long long end_after = h->streaming ? h->end[0] + T : T;
   const long long n_el = (long long)M * C;
   UA2_CHECK_CUDA(launch(lc, stx_begin_kernel, dim3((unsigned)((n_el + 255) / 256)), dim3(256), 0, x, h->xt, h->pos, h->bidx,
-                        sin ? h->sin_denoms : (const float*)nullptr, c.positional_scale, M, T, C, (int)offset));
-  const long long saved_offset = h->offset;
-  h->offset = offset;  // run_linear indexes the per-step slabs with it (0 when not streaming)
-  int rc = UA2_OK;
-  for (int li = 0; li < c.num_layers && rc == UA2_OK; ++li) {
-    const StxLayer& l = h->layers[li];
-    {  // norm1 -> in_proj
-      LinSpec s;
-      s.pro = pro_norm;
-      s.epi = EPI_STORE;
-      s.W = l.in_proj;
-      s.slab = (size_t)3 * C * C;
-      s.N = 3 * C;
-      s.K = C;
-      s.X = h->xt;
-      s.ldx = C;
-      s.Y = h->qkv;
-      s.ldy = 3 * C;
-      s.norm_w = l.n1w;
-      s.norm_b = l.n1b;
-      s.eps = eps;
-      if ((rc = run_linear(h, lc, s, B, T, per_step)) != UA2_OK) break;
-    }
-    float* kc = h->streaming ? h->kc[li] : h->tk;
-    float* vc = h->streaming ? h->vc[li] : h->tv;
-    const int cap = h->streaming ? h->cap : T;
-    const long long end = h->streaming ? h->end[li] + T : T;
-    {
-      const long long total = (long long)M * H * (hs / 2);
-      cudaError_t e = launch(lc, rope_ring_append_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
-                             (const float*)h->qkv, 3 * C, (const int32_t*)h->pos, (const int32_t*)h->bidx,
-                             rope ? h->rope_freqs : (const float*)nullptr, h->q, kc, vc, M, H, hs, cap, h->streaming ? 1 : 0);
-      if (e == cudaSuccess) {
-        RingAttnParams a{};
-        a.q = h->q;
-        a.kc = kc;
-        a.vc = vc;
-        a.pos = h->pos;
-        a.bidx = h->bidx;
-        a.y = h->att;
-        a.M = M;
-        a.H = H;
-        a.cap = cap;
-        a.end = end;
-        a.ring = h->streaming ? 1 : 0;
-        a.causal = c.causal;
-        a.context = c.context;
-        a.n_splits = ring_attn_splits(cap);
-        a.part_ml = h->part_ml;
-        a.part_acc = h->part_acc;
-        e = launch_ring_attn(lc, a, hs);
-      }
-      if (e != cudaSuccess) {
-        set_error(std::string("attention launch: ") + cudaGetErrorString(e));
-        rc = UA2_ERR_CUDA;
-        break;
-      }
-    }
-    {  // out_proj -> x + layer_scale_1 * update
-      LinSpec s;
-      s.pro = PRO_PLAIN;
-      s.epi = epi_res;
-      s.W = l.out_proj;
-      s.slab = (size_t)C * C;
-      s.N = C;
-      s.K = C;
-      s.X = h->att;
-      s.ldx = C;
-      s.Y = h->xt;
-      s.ldy = C;
-      s.R = h->xt;
-      s.ldr = C;
-      s.scale = l.ls1;
-      if ((rc = run_linear(h, lc, s, B, T, per_step)) != UA2_OK) break;
-    }
-    if (!c.gating) {  // norm2 -> linear1 -> gelu -> linear2 -> x + layer_scale_2 * update
-      LinSpec s;
-      s.pro = pro_norm;
-      s.epi = EPI_GELU;
-      s.W = l.lin1;
-      s.N = h->hidden[0];
-      s.K = C;
-      s.X = h->xt;
-      s.ldx = C;
-      s.Y = h->hb;
-      s.ldy = h->f_max;
-      s.norm_w = l.n2w;
-      s.norm_b = l.n2b;
-      s.eps = eps;
-      if ((rc = run_linear(h, lc, s, B, T, false)) != UA2_OK) break;
-      LinSpec o;
-      o.pro = PRO_PLAIN;
-      o.epi = epi_res;
-      o.W = l.lin2;
-      o.N = C;
-      o.K = h->hidden[0];
-      o.X = h->hb;
-      o.ldx = h->f_max;
-      o.Y = h->xt;
-      o.ldy = C;
-      o.R = h->xt;
-      o.ldr = C;
-      o.scale = l.ls2;
-      if ((rc = run_linear(h, lc, o, B, T, false)) != UA2_OK) break;
-    } else {  // ActivationGating: linear_in viewed (2, hidden): silu(first half) * second half, then linear_out
-      const int n_launch = per_step ? T : 1;
-      for (int t = 0; t < n_launch && rc == UA2_OK; ++t) {
-        const int step = per_step ? (int)offset + t : 0;
-        const int Hh = h->hidden[step];
-        const int rows = per_step ? B : M, mul = per_step ? T : 1;
-        GemvParams p;
-        p.W = l.g_in[step];
-        p.W2 = l.g_in[step] + (size_t)Hh * C;
-        p.N = Hh;
-        p.K = C;
-        p.M = rows;
-        p.X = h->xt + (size_t)t * C * (per_step ? 1 : 0);
-        p.ldx = C * mul;
-        p.Y = h->hb + (size_t)t * h->f_max * (per_step ? 1 : 0);
-        p.ldy = h->f_max * mul;
-        p.norm_w = l.n2w;
-        p.norm_b = l.n2b;
-        p.eps = eps;
-        p.ws = h->stats;
-        p.ws_floats = 2 * h->rows + 8;
-        cudaError_t e = launch_gemv(lc, pro_norm, EPI_SWIGLU, p);
-        if (e == cudaSuccess) {
-          GemvParams o;
-          o.W = l.g_out[step];
-          o.N = C;
-          o.K = Hh;
-          o.M = rows;
-          o.X = p.Y;
-          o.ldx = p.ldy;
-          o.Y = h->xt + (size_t)t * C * (per_step ? 1 : 0);
-          o.ldy = C * mul;
-          o.R = o.Y;
-          o.ldr = o.ldy;
-          o.scale = l.ls2;
-          o.ws = h->stats;
-          o.ws_floats = 2 * h->rows + 8;
-          e = launch_gemv(lc, PRO_PLAIN, epi_res, o);
+                        sin ? h->sin_denoms : (const float*)nullptr, c.positional_scale, M, T, C, (int)offset, end_after,
+                        h->d_end));
+  if (h->streaming && h->opt_graph) {
+    lc.pdl = h->opt_pdl != 0;
+    const unsigned long long key = ((unsigned long long)B << 40) | ((unsigned long long)T << 16) |
+                                   ((unsigned long long)(per_step ? offset + 1 : 0) << 1) | (h->opt_pdl ? 1ull : 0ull);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {  // first use of this shape: eager (also sets the lazily-initialised kernel attributes)
+      RUN(run_layers(h, lc, B, T, offset));
+      h->graphs.emplace(key, ua2_stx::GraphEntry());
+    } else {
+      if (it->second.exec == nullptr) {  // second use: capture on a private stream
+        cudaStream_t cs;
+        UA2_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        LaunchCtx lcc = lc;
+        lcc.stream = cs;
+        int glaunches = 0;
+        lcc.launch_counter = &glaunches;
+        cudaGraph_t graph = nullptr;
+        UA2_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_layers(h, lcc, B, T, offset);
+        const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+        if (rc != UA2_OK || e != cudaSuccess) {
+          if (rc == UA2_OK) set_error(std::string("graph capture failed: ") + cudaGetErrorString(e));
+          if (graph) cudaGraphDestroy(graph);
+          cudaStreamDestroy(cs);
+          return rc != UA2_OK ? rc : UA2_ERR_CUDA;
         }
-        if (e != cudaSuccess) {
-          set_error(std::string("gating launch: ") + cudaGetErrorString(e));
-          rc = UA2_ERR_CUDA;
-        }
+        UA2_CHECK_CUDA(cudaGraphInstantiate(&it->second.exec, graph, 0));
+        it->second.launches = glaunches;
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
       }
-      if (rc != UA2_OK) break;
+      UA2_CHECK_CUDA(cudaGraphLaunch(it->second.exec, lc.stream));
+      launches += it->second.launches;
     }
+  } else {
+    RUN(run_layers(h, lc, B, T, offset));
   }
-  h->offset = saved_offset;
-  if (rc != UA2_OK) return rc;
   UA2_CHECK_CUDA(cudaMemcpyAsync(y, h->xt, (size_t)M * C * sizeof(float), cudaMemcpyDeviceToDevice, lc.stream));
+  h->last_launches = launches;
   if (h->streaming) {
     h->offset += T;
     for (auto& e : h->end) e += T;
   }
   return UA2_OK;
 }
+
+int ua2_stx_set_option(ua2_stx* h, const char* name, int value) {
+  UA2_REQUIRE(h && name, "null argument");
+  const std::string n(name);
+  if (n == "graph")
+    h->opt_graph = value;
+  else if (n == "pdl")
+    h->opt_pdl = value;
+  else
+    UA2_REQUIRE(false, "unknown option " + n);
+  return UA2_OK;
+}
+
+int ua2_stx_last_launch_count(ua2_stx* h) { return h ? h->last_launches : 0; }
 
 }  // extern "C"

@@ -209,6 +209,14 @@ class StreamingTransformer(nn.Module):
             raise ValueError("Trying to reset streaming, but  wasn't streaming.")  # streaming.py:118-121
         _lib.check(_lib.lib().ua2_stx_reset_streaming(self._h), "reset_streaming")
 
+    def set_option(self, name: str, value: int):
+        """'graph' / 'pdl' (0/1): how streaming calls are launched (include/ua2_b200.h, ua2_stx_set_option)."""
+        self._ensure()
+        _lib.check(_lib.lib().ua2_stx_set_option(self._h, name.encode(), int(value)), f"set_option({name})")
+
+    def last_launch_count(self) -> int:
+        return int(_lib.lib().ua2_stx_last_launch_count(self._h)) if self._h is not None else 0
+
     def streaming_kv(self, layer: int):
         """(k, v, end_offset): zero-copy views of a layer's ring buffers (batch, H, capacity, head_dim) - RingKVCache.cache[0/1]."""
         from ..llm_models.model_new import _from_ptr
