@@ -343,6 +343,41 @@ int ua2_stx_last_launch_count(ua2_stx* h);
 /* introspection: ring buffers (batch, H, capacity, hs) of a layer and the number of keys written so far */
 int ua2_stx_get_kv(ua2_stx* h, int layer, float** k, float** v, int64_t* end_offset, int* capacity);
 
+/* ------------------------------------------------------------------------------------------------
+ * Flow-matching decoder of ReasoningCodec_film: the DiT estimator
+ * tools/tokenizer/ReasoningCodec_film/models/transformer_1d_flow.py::Transformer1DModel (adaLN-single blocks of
+ * models/attention.py::BasicTransformerBlock) and models/AudioDiffusion1D.py::BASECFM.solve_euler (:89-129).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ua2_dit_cfg {     /* models/model_config.json */
+  int32_t num_attention_heads;   /* 24 */
+  int32_t attention_head_dim;    /* 64 (32 / 64 / 128 served) */
+  int32_t in_channels;           /* 1040 = latent 136 + in-context latent 136 + condition 768 */
+  int32_t out_channels;          /* 136 */
+  int32_t num_layers;            /* 32 */
+  int32_t num_positional_embeddings; /* rows of pos_embed.pe (3000, transformer_1d_flow.py:195) */
+  int32_t flow_t_size;           /* 512 (transformer_1d_flow.py:47) */
+  float norm_eps;                /* 1e-6 */
+} ua2_dit_cfg;
+typedef struct ua2_dit ua2_dit;
+
+int ua2_dit_create(const ua2_dit_cfg* cfg, ua2_dit** out);
+int ua2_dit_destroy(ua2_dit* h);
+/* one fp32 parameter / buffer by its reference state-dict key ("proj_in.ffn_1.weight", "pos_embed.pe",
+ * "transformer_blocks.3.attn1.to_q.bias", "adaln_single.linear.weight", ...) plus the host-evaluated table "tfreqs"
+ * (flow_t_size / 2: exp(-ln(10000) * i / half), transformer_1d_flow.py:67); tensors must outlive the handle */
+int ua2_dit_load_weight(ua2_dit* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+/* validates the parameter set; repacks the k = 3 convolutions of ProjectLayer to GEMM form and concatenates to_q/k/v */
+int ua2_dit_finalize(ua2_dit* h, void* stream);
+/* Transformer1DModel.forward(hidden_states (B, T, in_channels), timestep (B) fp32 on the device).sample -> (B, T, out_channels) */
+int ua2_dit_forward(ua2_dit* h, const float* hidden_states, const float* timestep, float* out, int B, int T, void* stream);
+/* BASECFM.solve_euler for batch 1 with classifier-free guidance (the reference's only working configuration: it repeats the
+ * timestep twice, AudioDiffusion1D.py:114): x (1, T, out_channels) noise in, solution out (in place);
+ * incontext_x (1, T, out_channels); mu (1, T, in_channels - 2 * out_channels); t_span: HOST array of n_span time points
+ * (torch.linspace(0, 1, steps + 1)); guidance_scale > 1; sigma_min = 1e-4 (:68). */
+int ua2_dit_solve_euler(ua2_dit* h, float* x, const float* incontext_x, int incontext_length, const float* t_span, int n_span,
+                        const float* mu, int T, float guidance_scale, float sigma_min, void* stream);
+int ua2_dit_last_launch_count(ua2_dit* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,12 @@ class StxCfg(C.Structure):
                 ("max_period", C.c_float), ("positional_scale", C.c_float)]
 
 
+class DitCfg(C.Structure):
+    _fields_ = [("num_attention_heads", C.c_int32), ("attention_head_dim", C.c_int32), ("in_channels", C.c_int32),
+                ("out_channels", C.c_int32), ("num_layers", C.c_int32), ("num_positional_embeddings", C.c_int32),
+                ("flow_t_size", C.c_int32), ("norm_eps", C.c_float)]
+
+
 # every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -97,6 +103,13 @@ SYMBOLS = {
                                     C.c_int, _P]),
     "ua2_sample_token_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, _P, C.c_uint64,
                                        C.c_uint64, _P, _P]),
+    "ua2_dit_create": (C.c_int, [C.POINTER(DitCfg), C.POINTER(_P)]),
+    "ua2_dit_destroy": (C.c_int, [_P]),
+    "ua2_dit_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_dit_finalize": (C.c_int, [_P, _P]),
+    "ua2_dit_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "ua2_dit_solve_euler": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.c_int, _P, C.c_int, C.c_float, C.c_float, _P]),
+    "ua2_dit_last_launch_count": (C.c_int, [_P]),
     "ua2_stx_create": (C.c_int, [C.POINTER(StxCfg), C.POINTER(_P)]),
     "ua2_stx_destroy": (C.c_int, [_P]),
     "ua2_stx_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),

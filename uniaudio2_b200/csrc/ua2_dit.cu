@@ -1,0 +1,769 @@
+// Flow-matching decoder of ReasoningCodec_film: the DiT estimator (Transformer1DModel, adaLN-single) and the Euler solver
+// with classifier-free guidance (BASECFM.solve_euler) - SURVEY.md section 8(f) rank 1, the "tokens -> latent" cost of
+// `--stage all` (32 layers x 24 heads x 64, ~1.9 TFLOP per Euler step for a 20 s window).
+//
+// Replaces (paths relative to tools/tokenizer/ReasoningCodec_film/models/):
+//   transformer_1d_flow.py  Transformer1DModel.forward :284-386, ProjectLayer :19-34, PixArtAlphaCombinedFlowEmbeddings
+//                           :37-84, AdaLayerNormSingleFlow :87-117
+//   attention.py            BasicTransformerBlock.forward :284-418 (ada_norm_single branch), FeedForward :623-681
+//   AudioDiffusion1D.py     BASECFM.solve_euler :89-129
+//   diffusers (un-vendored, >= 0.25): Attention / AttnProcessor2_0, GELU(tanh), TimestepEmbedding, SinusoidalPositionalEmbedding
+//
+// Roofline: TENSOR bound - every linear has M = B*T >= 1000 rows at production size and runs on the tcgen05 3xTF32 path
+// of ua2_tcgemm.cu (fp32-class accuracy; the reference autocasts these linears to bf16); the kernels in this file are the
+// HBM-bound glue around the GEMMs, one pass over the activations each:
+//   dit_im2col3_kernel   k = 3 'same' convolution of ProjectLayer as a GEMM over [x[t-1] | x[t] | x[t+1]]
+//   dit_epilogue_kernel  bias (+ scale | + positional table | + GELU-tanh | + SiLU | gate * . + residual | q/k/v head split)
+//   dit_ln_mod_kernel    LayerNorm without affine, then * (1 + scale) + shift with the adaLN-single table + timestep rows
+//   dit_attn_kernel      unmasked self-attention, CTA = 16 query rows x one head; K/V tiles of 32 keys staged in shared
+//                        memory and shared by the 16 rows; online softmax per row (one warp = 2 rows)
+//   dit_euler_*          in-context blend, CFG batch assembly, guidance mix and Euler update of the solver
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ua2_b200.h"
+#include "ua2_kernels.cuh"
+
+namespace ua2 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ conv k3 as GEMM input
+// out[m, k*C + c] = x[b, t + k - 1, c] (0 outside the sequence), m = b*T + t
+__global__ void dit_im2col3_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int T, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n = (long long)B * T * 3 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int k = (int)((i / C) % 3);
+    const long long m = i / (3LL * C);
+    const int t = (int)(m % T);
+    const int ts = t + k - 1;
+    out[i] = (ts >= 0 && ts < T) ? x[(m + (k - 1)) * C + c] : 0.f;
+  }
+}
+
+// Conv1d weight (Cout, Cin, 3) -> GEMM weight (Cout, 3*Cin) with column k*Cin + ci
+__global__ void dit_repack_conv3_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
+  const long long n = (long long)Cout * Cin * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int k = (int)((i / Cin) % 3);
+    const long long co = i / (3LL * Cin);
+    out[i] = w[(co * Cin + ci) * 3 + k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused epilogues
+enum : int {
+  DE_BIAS = 0,        // y = y + bias
+  DE_BIAS_SCALE = 1,  // y = (y + bias) * s                      ProjectLayer: ffn_1 then * kernel_size ** -0.5
+  DE_BIAS_PE = 2,     // y = (y + bias) + pe[t]                  proj_in.ffn_2 then SinusoidalPositionalEmbedding
+  DE_BIAS_GELU = 3,   // y = gelu_tanh(y + bias)                 FeedForward 'gelu-approximate'
+  DE_BIAS_SILU = 4,   // y = silu(y + bias)                      TimestepEmbedding.act
+  DE_BIAS_KEEP_SILU = 5,  // y = y + bias, y2 = silu(y)          embedded_timestep and the input of adaln_single.linear
+  DE_GATE_RES = 6,    // res = gate_b * (y + bias) + res         attention.py:350-353, :409-412
+  DE_QKV_SPLIT = 7    // q (M, D) = y[:, :D] + b; k, v -> (B, H, T, hs)
+};
+
+struct DitEpi {
+  float* y;           // (M, N) raw GEMM output, updated in place unless stated
+  const float* bias;  // (N)
+  int M, N, T;
+  float s;
+  const float* pe;    // (positions, N)
+  float* y2;          // KEEP_SILU: silu copy; GATE_RES: the residual stream (M, N), updated in place
+  const float* table; // GATE_RES: scale_shift_table (6, N)
+  const float* t6;    // GATE_RES: timestep modulation (B, 6N)
+  int gate_idx;
+  float *q, *k, *v;   // QKV_SPLIT destinations
+  int H, hs;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {  // F.gelu(approximate='tanh')
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  const float inner = kBeta * (x + kKappa * x * x * x);
+  return 0.5f * x * (1.f + tanhf(inner));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+
+template <int MODE>
+__global__ void dit_epilogue_kernel(const DitEpi e) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n = (long long)e.M * e.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % e.N);
+    const long long m = i / e.N;
+    const float v = __fadd_rn(e.y[i], e.bias[c]);
+    if (MODE == DE_BIAS) {
+      e.y[i] = v;
+    } else if (MODE == DE_BIAS_SCALE) {
+      e.y[i] = __fmul_rn(v, e.s);
+    } else if (MODE == DE_BIAS_PE) {
+      e.y[i] = __fadd_rn(v, e.pe[(size_t)(m % e.T) * e.N + c]);
+    } else if (MODE == DE_BIAS_GELU) {
+      e.y[i] = gelu_tanh(v);
+    } else if (MODE == DE_BIAS_SILU) {
+      e.y[i] = silu(v);
+    } else if (MODE == DE_BIAS_KEEP_SILU) {
+      e.y[i] = v;
+      e.y2[i] = silu(v);
+    } else if (MODE == DE_GATE_RES) {
+      const int b = (int)(m / e.T);
+      const float gate = __fadd_rn(e.table[(size_t)e.gate_idx * e.N + c], e.t6[((size_t)b * 6 + e.gate_idx) * e.N + c]);
+      e.y2[i] = __fadd_rn(__fmul_rn(gate, v), e.y2[i]);
+    } else {  // DE_QKV_SPLIT: N = 3*D, columns ordered [q | k | v], each (h d)
+      const int D = e.N / 3;
+      const int part = c / D, cc = c - part * D;
+      if (part == 0) {
+        e.q[m * D + cc] = v;
+      } else {
+        const int hh = cc / e.hs, d = cc - hh * e.hs;
+        const int b = (int)(m / e.T), t = (int)(m % e.T);
+        (part == 1 ? e.k : e.v)[(((size_t)b * e.H + hh) * e.T + t) * e.hs + d] = v;
+      }
+    }
+  }
+}
+
+template <int MODE>
+cudaError_t launch_epi(const LaunchCtx& lc, const DitEpi& e) {
+  const long long n = (long long)e.M * e.N;
+  const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32);
+  return launch(lc, dit_epilogue_kernel<MODE>, dim3(grid), dim3(256), 0, e);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm + modulation
+// out[m] = LN(x[m]; eps, no affine) * (1 + scale_b) + shift_b,  scale_b = table[scale_idx] + t[b, scale_idx * t_stride ...]
+// (attention.py:312-317 / :399-401 with t = the 6*D rows of adaln_single; transformer_1d_flow.py:378-381 with t = the
+// embedded timestep, t_stride = 0: both rows of the (2, D) table get the same D-vector added)
+__global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                         const float* __restrict__ table, const float* __restrict__ t, int t_row,
+                                                         int t_stride, int shift_idx, int scale_idx, float eps, int T, int D) {
+  __shared__ float red[8];
+  __shared__ float stat[2];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x, b = m / T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* xr = x + (size_t)m * D;
+  float s = 0.f;
+  for (int c = tid; c < D; c += 256) s += xr[c];
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    stat[0] = tot / (float)D;
+  }
+  __syncthreads();
+  const float mean = stat[0];
+  float q = 0.f;
+  for (int c = tid; c < D; c += 256) {
+    const float d = xr[c] - mean;
+    q += d * d;
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    stat[1] = rsqrtf(tot / (float)D + eps);
+  }
+  __syncthreads();
+  const float rstd = stat[1];
+  const float* tb = t + (size_t)b * t_row;
+  for (int c = tid; c < D; c += 256) {
+    const float scale = __fadd_rn(table[(size_t)scale_idx * D + c], tb[(size_t)scale_idx * t_stride + c]);
+    const float shift = __fadd_rn(table[(size_t)shift_idx * D + c], tb[(size_t)shift_idx * t_stride + c]);
+    const float nrm = (xr[c] - mean) * rstd;
+    out[(size_t)m * D + c] = __fadd_rn(__fmul_rn(nrm, __fadd_rn(1.f, scale)), shift);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+constexpr int DA_ROWS = 16;   // query rows per CTA
+constexpr int DA_KEYS = 32;   // keys per shared-memory tile (one per lane)
+
+template <int HS>
+__global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__ q, const float* __restrict__ kc,
+                                                       const float* __restrict__ vc, float* __restrict__ out, int T, int H) {
+  constexpr int DPL = HS / 32;  // output dims per lane
+  __shared__ float Ks[DA_KEYS][HS + 1];
+  __shared__ float Vs[DA_KEYS][HS];
+  __shared__ float Qs[DA_ROWS][HS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t0 = blockIdx.x * DA_ROWS, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * HS;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = tid; i < DA_ROWS * HS; i += 256) {
+    const int r = i / HS, d = i - r * HS;
+    Qs[r][d] = (t0 + r < T) ? q[((size_t)b * T + t0 + r) * D + h * HS + d] : 0.f;
+  }
+  const float* Kb = kc + ((size_t)b * H + h) * (size_t)T * HS;
+  const float* Vb = vc + ((size_t)b * H + h) * (size_t)T * HS;
+  const float scale = rsqrtf((float)HS);
+  float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  float acc[2][DPL];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) acc[r][d] = 0.f;
+  for (int j0 = 0; j0 < T; j0 += DA_KEYS) {
+    __syncthreads();  // previous tile fully consumed (also orders the Qs fill before the first use)
+    for (int i = tid; i < DA_KEYS * HS; i += 256) {
+      const int j = i / HS, d = i - j * HS;
+      const bool ok = j0 + j < T;
+      Ks[j][d] = ok ? Kb[(size_t)(j0 + j) * HS + d] : 0.f;
+      Vs[j][d] = ok ? Vb[(size_t)(j0 + j) * HS + d] : 0.f;
+    }
+    __syncthreads();
+    const bool valid = j0 + lane < T;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = warp * 2 + r;
+      float s = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < HS; ++d) s = fmaf(Qs[row][d], Ks[lane][d], s);
+      s = valid ? s * scale : -INFINITY;
+      const float mn = fmaxf(mx[r], warp_max(s));  // every tile holds at least one valid key, so mn is finite
+      const float corr = expf(mx[r] - mn);
+      const float p = valid ? expf(s - mn) : 0.f;
+      l[r] = l[r] * corr + warp_sum(p);
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) acc[r][d] *= corr;
+#pragma unroll 8
+      for (int j = 0; j < DA_KEYS; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) acc[r][d] = fmaf(pj, Vs[j][lane + 32 * d], acc[r][d]);
+      }
+      mx[r] = mn;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = t0 + warp * 2 + r;
+    if (t < T) {
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) out[((size_t)b * T + t) * D + h * HS + lane + 32 * d] = acc[r][d] / l[r];
+    }
+  }
+}
+
+cudaError_t launch_dit_attn(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H,
+                            int hs) {
+  const dim3 grid((T + DA_ROWS - 1) / DA_ROWS, H, B), block(256);
+  switch (hs) {
+    case 32: return launch(lc, dit_attn_kernel<32>, grid, block, 0, q, kc, vc, out, T, H);
+    case 64: return launch(lc, dit_attn_kernel<64>, grid, block, 0, q, kc, vc, out, T, H);
+    case 128: return launch(lc, dit_attn_kernel<128>, grid, block, 0, q, kc, vc, out, T, H);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ timestep embedding
+// proj[b] = [cos(args) | sin(args)], args = t[b] * freqs * 1000 (transformer_1d_flow.py:58-71); t from device memory or by value
+__global__ void dit_tproj_kernel(const float* __restrict__ t_dev, float t_val, const float* __restrict__ freqs,
+                                 float* __restrict__ proj, int B, int half) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i - b * half;
+  const float t = t_dev ? t_dev[b] : t_val;
+  const float a = __fmul_rn(__fmul_rn(t, freqs[k]), 1000.f);
+  proj[(size_t)b * 2 * half + k] = cosf(a);
+  proj[(size_t)b * 2 * half + half + k] = sinf(a);
+}
+
+// ------------------------------------------------------------------------------------------------ Euler solver glue
+// x[:, :ic] = (1 - (1 - sigma_min) * t) * noise[:, :ic] + t * incontext[:, :ic]   (AudioDiffusion1D.py:106), then the CFG
+// batch of the estimator: rows [x | incontext | 0] and [x | incontext | mu]        (:108-113)
+__global__ void dit_euler_pack_kernel(float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ incontext,
+                                      const float* __restrict__ mu, float* __restrict__ inp, int T, int lat, int cond, int ic,
+                                      float t, float one_minus_sigma) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int in_ch = 2 * lat + cond;
+  const long long n = (long long)T * in_ch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % in_ch), tt = (int)(i / in_ch);
+    float u, cnd;
+    if (c < lat) {
+      float xv = x[(size_t)tt * lat + c];
+      if (tt < ic) {
+        const float c1 = __fsub_rn(1.f, __fmul_rn(one_minus_sigma, t));
+        xv = __fadd_rn(__fmul_rn(c1, noise[(size_t)tt * lat + c]), __fmul_rn(t, incontext[(size_t)tt * lat + c]));
+        x[(size_t)tt * lat + c] = xv;
+      }
+      u = cnd = xv;
+    } else if (c < 2 * lat) {
+      u = cnd = incontext[(size_t)tt * lat + (c - lat)];
+    } else {
+      u = 0.f;
+      cnd = mu[(size_t)tt * cond + (c - 2 * lat)];
+    }
+    inp[i] = u;
+    inp[n + i] = cnd;
+  }
+}
+
+// dphi = uncond + g * (cond - uncond); x = x + dt * dphi   (AudioDiffusion1D.py:116-123)
+__global__ void dit_euler_update_kernel(float* __restrict__ x, const float* __restrict__ d, long long n, float g, float dt) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = d[i], c = d[n + i];
+    const float dphi = __fadd_rn(u, __fmul_rn(g, __fsub_rn(c, u)));
+    x[i] = __fadd_rn(x[i], __fmul_rn(dt, dphi));
+  }
+}
+
+unsigned grid_for(long long n) { return (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32); }
+
+struct Lin {
+  const float *w = nullptr, *b = nullptr;
+};
+struct DitBlock {
+  const float* table = nullptr;  // (6, D)
+  Lin q, k, v, o, ff1, ff2;
+  float *wqkv = nullptr, *bqkv = nullptr;  // concatenated [to_q; to_k; to_v]
+};
+
+}  // namespace
+}  // namespace ua2
+
+using namespace ua2;
+
+struct ua2_dit {
+  ua2_dit_cfg cfg{};
+  std::vector<DitBlock> blocks;
+  const float *table = nullptr, *pe = nullptr, *tfreqs = nullptr;
+  Lin in1, in2, out1, out2, te1, te2, ada;
+  float *in1_w = nullptr, *out1_w = nullptr;  // conv weights repacked (Cout, 3*Cin)
+  bool ready = false;
+  std::vector<void*> owned;
+  // workspace for M rows / B batch rows
+  size_t rows = 0, brows = 0;
+  float *col = nullptr, *h = nullptr, *n = nullptr, *qkv = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr,
+        *ff = nullptr, *stats = nullptr;
+  float *tproj = nullptr, *temb = nullptr, *tsemb = nullptr, *t6 = nullptr, *ttmp = nullptr;
+  // solver
+  size_t srows = 0;
+  float *noise = nullptr, *sinp = nullptr, *sout = nullptr;
+  TcWorkspace tc;
+  int last_launches = 0;
+};
+
+namespace {
+
+#define RUN(expr)                  \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != UA2_OK) return _rc; \
+  } while (0)
+#define CU(expr)                                                                   \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+      return UA2_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+void free_list(std::initializer_list<float**> ps) {
+  for (float** p : ps) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+}
+
+int dmalloc(float** p, size_t floats) {
+  UA2_CHECK_CUDA(cudaMalloc((void**)p, std::max<size_t>(floats, 4) * sizeof(float)));
+  return UA2_OK;
+}
+
+int reserve(ua2_dit* h, size_t M, size_t B) {
+  const ua2_dit_cfg& c = h->cfg;
+  const size_t D = (size_t)c.num_attention_heads * c.attention_head_dim, I = c.in_channels, O = c.out_channels;
+  if (M > h->rows) {
+    if (h->rows) UA2_CHECK_CUDA(cudaDeviceSynchronize());
+    free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.w, &h->tc.c});
+    RUN(dmalloc(&h->col, M * 3 * std::max(I, D)));
+    RUN(dmalloc(&h->h, M * D));
+    RUN(dmalloc(&h->n, M * D));
+    RUN(dmalloc(&h->qkv, M * 3 * D));
+    RUN(dmalloc(&h->q, M * D));
+    RUN(dmalloc(&h->k, M * D));
+    RUN(dmalloc(&h->v, M * D));
+    RUN(dmalloc(&h->att, M * D));
+    RUN(dmalloc(&h->ff, M * 4 * D));
+    RUN(dmalloc(&h->stats, 2 * M + 8));
+    if (tc_gemm_available()) {  // scratch of the tcgen05 3xTF32 path: split activations / weights, raw product
+      const size_t kmax = std::max({3 * I, 4 * D, 3 * D}), nmax = std::max({4 * D, 3 * D, O});
+      h->tc.a_floats = M * 3 * kmax;
+      h->tc.w_floats = std::max({D * 9 * I, 3 * D * 3 * D, 4 * D * 3 * D, D * 12 * D, O * 9 * D, O * 3 * O});
+      h->tc.c_floats = M * nmax;
+      RUN(dmalloc(&h->tc.a, h->tc.a_floats));
+      RUN(dmalloc(&h->tc.w, h->tc.w_floats));
+      RUN(dmalloc(&h->tc.c, h->tc.c_floats));
+    }
+    h->rows = M;
+  }
+  if (B > h->brows) {
+    if (h->brows) UA2_CHECK_CUDA(cudaDeviceSynchronize());
+    free_list({&h->tproj, &h->temb, &h->tsemb, &h->t6, &h->ttmp});
+    RUN(dmalloc(&h->tproj, B * c.flow_t_size));
+    RUN(dmalloc(&h->temb, B * D));
+    RUN(dmalloc(&h->tsemb, B * D));
+    RUN(dmalloc(&h->ttmp, B * D));
+    RUN(dmalloc(&h->t6, B * 6 * D));
+    h->brows = B;
+  }
+  return UA2_OK;
+}
+
+// y (M, N) = x (M, K, row stride K) @ W^T, raw (no bias): tensor cores for M >= tc_min_rows, skinny fp32 kernels below
+int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K) {
+  GemvParams p;
+  p.W = W;
+  p.N = N;
+  p.K = K;
+  p.M = M;
+  p.X = x;
+  p.ldx = K;
+  p.Y = y;
+  p.ldy = N;
+  p.ws = h->stats;
+  p.ws_floats = 2 * h->rows + 8;
+  p.tc = h->tc.a ? &h->tc : nullptr;
+  CU(launch_gemv(lc, PRO_PLAIN, EPI_STORE, p));
+  return UA2_OK;
+}
+
+DitEpi epi(float* y, const float* bias, int M, int N, int T) {
+  DitEpi e{};
+  e.y = y;
+  e.bias = bias;
+  e.M = M;
+  e.N = N;
+  e.T = T;
+  return e;
+}
+
+// ProjectLayer.forward: (B, T, Cin) -> (B, T, Cout); `pe` != nullptr adds the positional table after ffn_2 (proj_in)
+int project_layer(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* w1_repacked, const Lin& l1, const Lin& l2,
+                  float* tmp, float* y, int B, int T, int Cin, int Cout, const float* pe) {
+  const int M = B * T;
+  CU(launch(lc, dit_im2col3_kernel, dim3(grid_for((long long)M * 3 * Cin)), dim3(256), 0, x, h->col, B, T, Cin));
+  RUN(linear_raw(h, lc, h->col, w1_repacked, tmp, M, Cout, 3 * Cin));
+  DitEpi e1 = epi(tmp, l1.b, M, Cout, T);
+  e1.s = 0.57735026918962576451f;  // 3 ** -0.5 rounded to fp32, transformer_1d_flow.py:32
+  CU(launch_epi<DE_BIAS_SCALE>(lc, e1));
+  RUN(linear_raw(h, lc, tmp, l2.w, y, M, Cout, Cout));
+  DitEpi e2 = epi(y, l2.b, M, Cout, T);
+  if (pe) {
+    e2.pe = pe;
+    CU(launch_epi<DE_BIAS_PE>(lc, e2));
+  } else {
+    CU(launch_epi<DE_BIAS>(lc, e2));
+  }
+  return UA2_OK;
+}
+
+// Transformer1DModel.forward on device buffers: x (B, T, in) -> out (B, T, out_channels); timestep from t_dev (B) or t_val
+int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_dev, float t_val, float* out, int B, int T) {
+  const ua2_dit_cfg& c = h->cfg;
+  const int H = c.num_attention_heads, hs = c.attention_head_dim, D = H * hs, M = B * T;
+  // ---- adaln_single: timestep -> embedded_timestep (temb) and the 6*D modulation rows (t6)
+  const int half = c.flow_t_size / 2;
+  CU(launch(lc, dit_tproj_kernel, dim3((B * half + 255) / 256), dim3(256), 0, t_dev, t_val, h->tfreqs, h->tproj, B, half));
+  RUN(linear_raw(h, lc, h->tproj, h->te1.w, h->ttmp, B, D, c.flow_t_size));
+  CU(launch_epi<DE_BIAS_SILU>(lc, epi(h->ttmp, h->te1.b, B, D, 1)));
+  RUN(linear_raw(h, lc, h->ttmp, h->te2.w, h->temb, B, D, D));
+  {
+    DitEpi e = epi(h->temb, h->te2.b, B, D, 1);
+    e.y2 = h->tsemb;
+    CU(launch_epi<DE_BIAS_KEEP_SILU>(lc, e));
+  }
+  RUN(linear_raw(h, lc, h->tsemb, h->ada.w, h->t6, B, 6 * D, D));
+  CU(launch_epi<DE_BIAS>(lc, epi(h->t6, h->ada.b, B, 6 * D, 1)));
+  // ---- proj_in + positional embedding
+  RUN(project_layer(h, lc, x, h->in1_w, h->in1, h->in2, h->n, h->h, B, T, c.in_channels, D, h->pe));
+  // ---- blocks
+  for (const DitBlock& bl : h->blocks) {
+    CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 0, 1,
+              c.norm_eps, T, D));
+    RUN(linear_raw(h, lc, h->n, bl.wqkv, h->qkv, M, 3 * D, D));
+    {
+      DitEpi e = epi(h->qkv, bl.bqkv, M, 3 * D, T);
+      e.q = h->q;
+      e.k = h->k;
+      e.v = h->v;
+      e.H = H;
+      e.hs = hs;
+      CU(launch_epi<DE_QKV_SPLIT>(lc, e));
+    }
+    CU(launch_dit_attn(lc, h->q, h->k, h->v, h->att, B, T, H, hs));
+    RUN(linear_raw(h, lc, h->att, bl.o.w, h->n, M, D, D));
+    {
+      DitEpi e = epi(h->n, bl.o.b, M, D, T);
+      e.y2 = h->h;
+      e.table = bl.table;
+      e.t6 = h->t6;
+      e.gate_idx = 2;
+      CU(launch_epi<DE_GATE_RES>(lc, e));
+    }
+    CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 3, 4,
+              c.norm_eps, T, D));
+    RUN(linear_raw(h, lc, h->n, bl.ff1.w, h->ff, M, 4 * D, D));
+    CU(launch_epi<DE_BIAS_GELU>(lc, epi(h->ff, bl.ff1.b, M, 4 * D, T)));
+    RUN(linear_raw(h, lc, h->ff, bl.ff2.w, h->n, M, D, 4 * D));
+    {
+      DitEpi e = epi(h->n, bl.ff2.b, M, D, T);
+      e.y2 = h->h;
+      e.table = bl.table;
+      e.t6 = h->t6;
+      e.gate_idx = 5;
+      CU(launch_epi<DE_GATE_RES>(lc, e));
+    }
+  }
+  // ---- norm_out + modulation with (scale_shift_table + embedded_timestep) (eps 1e-6 hard-wired, :234), proj_out
+  CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, h->table, (const float*)h->temb, D, 0, 0, 1, 1e-6f,
+            T, D));
+  RUN(project_layer(h, lc, h->n, h->out1_w, h->out1, h->out2, h->att, out, B, T, D, c.out_channels, nullptr));
+  return UA2_OK;
+}
+
+bool parse_block_key(const std::string& key, int& idx, std::string& rest) {
+  const std::string pre = "transformer_blocks.";
+  if (key.compare(0, pre.size(), pre) != 0) return false;
+  size_t i = pre.size(), j = i;
+  while (j < key.size() && key[j] >= '0' && key[j] <= '9') ++j;
+  if (j == i || j >= key.size() || key[j] != '.') return false;
+  idx = std::stoi(key.substr(i, j - i));
+  rest = key.substr(j + 1);
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ua2_dit_create(const ua2_dit_cfg* cfg, ua2_dit** out) {
+  UA2_REQUIRE(cfg && out, "null argument");
+  const ua2_dit_cfg& c = *cfg;
+  UA2_REQUIRE(c.num_attention_heads >= 1 && c.num_layers >= 1 && c.in_channels >= 4 && c.out_channels >= 2, "bad dimensions");
+  UA2_REQUIRE(c.attention_head_dim == 32 || c.attention_head_dim == 64 || c.attention_head_dim == 128,
+              "attention_head_dim must be 32 / 64 / 128");
+  UA2_REQUIRE(c.in_channels % 4 == 0 && c.out_channels % 4 == 0, "in_channels and out_channels must be multiples of 4");
+  UA2_REQUIRE(c.flow_t_size >= 8 && c.flow_t_size % 8 == 0, "flow_t_size must be a multiple of 8");
+  UA2_REQUIRE(c.num_positional_embeddings >= 1, "num_positional_embeddings must be >= 1");
+  ua2_dit* h = new ua2_dit();
+  h->cfg = c;
+  h->blocks.resize(c.num_layers);
+  *out = h;
+  return UA2_OK;
+}
+
+int ua2_dit_destroy(ua2_dit* h) {
+  if (!h) return UA2_OK;
+  cudaDeviceSynchronize();
+  free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.w, &h->tc.c,
+             &h->tproj, &h->temb, &h->tsemb, &h->t6, &h->ttmp, &h->noise, &h->sinp, &h->sout});
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return UA2_OK;
+}
+
+int ua2_dit_load_weight(ua2_dit* h, const char* key_c, const float* dptr, const int64_t* shape, int ndim) {
+  UA2_REQUIRE(h && key_c && dptr && shape && ndim >= 1, "null argument");
+  const std::string key(key_c);
+  const ua2_dit_cfg& c = h->cfg;
+  const int64_t D = (int64_t)c.num_attention_heads * c.attention_head_dim, I = c.in_channels, O = c.out_channels;
+  auto is = [&](std::initializer_list<int64_t> want) {
+    if ((int)want.size() != ndim) return false;
+    int i = 0;
+    for (int64_t w : want)
+      if (shape[i++] != w) return false;
+    return true;
+  };
+#define WANT(cond) UA2_REQUIRE(cond, key + ": shape mismatch")
+  struct Top {
+    const char* name;
+    const float** dst;
+    std::initializer_list<int64_t> shp;
+  };
+  const Top tops[] = {
+      {"scale_shift_table", &h->table, {2, D}},
+      {"tfreqs", &h->tfreqs, {c.flow_t_size / 2}},
+      {"proj_in.ffn_1.weight", &h->in1.w, {D, I, 3}},
+      {"proj_in.ffn_1.bias", &h->in1.b, {D}},
+      {"proj_in.ffn_2.weight", &h->in2.w, {D, D}},
+      {"proj_in.ffn_2.bias", &h->in2.b, {D}},
+      {"proj_out.ffn_1.weight", &h->out1.w, {O, D, 3}},
+      {"proj_out.ffn_1.bias", &h->out1.b, {O}},
+      {"proj_out.ffn_2.weight", &h->out2.w, {O, O}},
+      {"proj_out.ffn_2.bias", &h->out2.b, {O}},
+      {"adaln_single.emb.timestep_embedder.linear_1.weight", &h->te1.w, {D, c.flow_t_size}},
+      {"adaln_single.emb.timestep_embedder.linear_1.bias", &h->te1.b, {D}},
+      {"adaln_single.emb.timestep_embedder.linear_2.weight", &h->te2.w, {D, D}},
+      {"adaln_single.emb.timestep_embedder.linear_2.bias", &h->te2.b, {D}},
+      {"adaln_single.linear.weight", &h->ada.w, {6 * D, D}},
+      {"adaln_single.linear.bias", &h->ada.b, {6 * D}},
+  };
+  for (const Top& t : tops)
+    if (key == t.name) {
+      WANT(is(t.shp));
+      *t.dst = dptr;
+      return UA2_OK;
+    }
+  if (key == "pos_embed.pe") {
+    WANT(is({1, c.num_positional_embeddings, D}));
+    h->pe = dptr;
+    return UA2_OK;
+  }
+  int bi = -1;
+  std::string rest;
+  UA2_REQUIRE(parse_block_key(key, bi, rest) && bi >= 0 && bi < c.num_layers, "unexpected key " + key);
+  DitBlock& b = h->blocks[bi];
+  struct Blk {
+    const char* name;
+    const float** dst;
+    std::initializer_list<int64_t> shp;
+  };
+  const Blk blks[] = {
+      {"scale_shift_table", &b.table, {6, D}},
+      {"attn1.to_q.weight", &b.q.w, {D, D}},
+      {"attn1.to_q.bias", &b.q.b, {D}},
+      {"attn1.to_k.weight", &b.k.w, {D, D}},
+      {"attn1.to_k.bias", &b.k.b, {D}},
+      {"attn1.to_v.weight", &b.v.w, {D, D}},
+      {"attn1.to_v.bias", &b.v.b, {D}},
+      {"attn1.to_out.0.weight", &b.o.w, {D, D}},
+      {"attn1.to_out.0.bias", &b.o.b, {D}},
+      {"ff.net.0.proj.weight", &b.ff1.w, {4 * D, D}},
+      {"ff.net.0.proj.bias", &b.ff1.b, {4 * D}},
+      {"ff.net.2.weight", &b.ff2.w, {D, 4 * D}},
+      {"ff.net.2.bias", &b.ff2.b, {D}},
+  };
+  for (const Blk& t : blks)
+    if (rest == t.name) {
+      WANT(is(t.shp));
+      *t.dst = dptr;
+      return UA2_OK;
+    }
+#undef WANT
+  UA2_REQUIRE(false, "unexpected key " + key);
+}
+
+int ua2_dit_finalize(ua2_dit* h, void* stream) {
+  UA2_REQUIRE(h, "null handle");
+  const ua2_dit_cfg& c = h->cfg;
+  const size_t D = (size_t)c.num_attention_heads * c.attention_head_dim, I = c.in_channels, O = c.out_channels;
+  UA2_REQUIRE(h->table && h->pe && h->tfreqs && h->in1.w && h->in1.b && h->in2.w && h->in2.b && h->out1.w && h->out1.b &&
+                  h->out2.w && h->out2.b && h->te1.w && h->te1.b && h->te2.w && h->te2.b && h->ada.w && h->ada.b,
+              "missing top-level parameters (scale_shift_table, pos_embed.pe, tfreqs, proj_in/out.*, adaln_single.*)");
+  for (int i = 0; i < c.num_layers; ++i) {
+    const DitBlock& b = h->blocks[i];
+    UA2_REQUIRE(b.table && b.q.w && b.q.b && b.k.w && b.k.b && b.v.w && b.v.b && b.o.w && b.o.b && b.ff1.w && b.ff1.b && b.ff2.w &&
+                    b.ff2.b,
+                "missing parameters of transformer_blocks." + std::to_string(i));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchCtx lc;
+  lc.stream = st;
+  auto own = [&](float** p, size_t floats) -> int {
+    UA2_CHECK_CUDA(cudaMalloc((void**)p, floats * sizeof(float)));
+    h->owned.push_back(*p);
+    return UA2_OK;
+  };
+  if (!h->ready) {
+    RUN(own(&h->in1_w, D * 3 * I));
+    RUN(own(&h->out1_w, O * 3 * D));
+    for (DitBlock& b : h->blocks) {
+      RUN(own(&b.wqkv, 3 * D * D));
+      RUN(own(&b.bqkv, 3 * D));
+    }
+  }
+  UA2_CHECK_CUDA(launch(lc, dit_repack_conv3_kernel, dim3(grid_for((long long)D * 3 * I)), dim3(256), 0, h->in1.w, h->in1_w, (int)D, (int)I));
+  UA2_CHECK_CUDA(launch(lc, dit_repack_conv3_kernel, dim3(grid_for((long long)O * 3 * D)), dim3(256), 0, h->out1.w, h->out1_w, (int)O, (int)D));
+  for (DitBlock& b : h->blocks) {
+    const Lin* src[3] = {&b.q, &b.k, &b.v};
+    for (int j = 0; j < 3; ++j) {
+      UA2_CHECK_CUDA(cudaMemcpyAsync(b.wqkv + (size_t)j * D * D, src[j]->w, D * D * 4, cudaMemcpyDeviceToDevice, st));
+      UA2_CHECK_CUDA(cudaMemcpyAsync(b.bqkv + (size_t)j * D, src[j]->b, D * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  h->ready = true;
+  return UA2_OK;
+}
+
+int ua2_dit_forward(ua2_dit* h, const float* hidden_states, const float* timestep, float* out, int B, int T, void* stream) {
+  UA2_REQUIRE(h && h->ready, "handle not finalized");
+  UA2_REQUIRE(hidden_states && timestep && out, "null argument");
+  UA2_REQUIRE(B >= 1 && T >= 1 && B <= 65535, "need B, T >= 1");
+  UA2_REQUIRE(T <= h->cfg.num_positional_embeddings, "sequence longer than the positional table");
+  RUN(reserve(h, (size_t)B * T, (size_t)B));
+  int launches = 0;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  lc.launch_counter = &launches;
+  RUN(dit_forward(h, lc, hidden_states, timestep, 0.f, out, B, T));
+  h->last_launches = launches;
+  return UA2_OK;
+}
+
+int ua2_dit_solve_euler(ua2_dit* h, float* x, const float* incontext_x, int incontext_length, const float* t_span, int n_span,
+                        const float* mu, int T, float guidance_scale, float sigma_min, void* stream) {
+  UA2_REQUIRE(h && h->ready, "handle not finalized");
+  UA2_REQUIRE(x && incontext_x && t_span && mu, "null argument");
+  UA2_REQUIRE(n_span >= 2 && T >= 1, "need at least one step and one frame");
+  UA2_REQUIRE(incontext_length >= 0 && incontext_length <= T, "incontext_length out of range");
+  UA2_REQUIRE(T <= h->cfg.num_positional_embeddings, "sequence longer than the positional table");
+  // the reference's other branch concatenates along time (AudioDiffusion1D.py:119) and cannot run this estimator
+  UA2_REQUIRE(guidance_scale > 1.0f, "solve_euler is served with classifier-free guidance (guidance_scale > 1) only");
+  const ua2_dit_cfg& c = h->cfg;
+  const int lat = c.out_channels, cond = c.in_channels - 2 * lat;
+  UA2_REQUIRE(cond > 0, "in_channels must exceed 2 * out_channels (latent | in-context latent | condition)");
+  RUN(reserve(h, (size_t)2 * T, 2));
+  if ((size_t)T > h->srows) {
+    if (h->srows) UA2_CHECK_CUDA(cudaDeviceSynchronize());
+    free_list({&h->noise, &h->sinp, &h->sout});
+    RUN(dmalloc(&h->noise, (size_t)T * lat));
+    RUN(dmalloc(&h->sinp, (size_t)2 * T * c.in_channels));
+    RUN(dmalloc(&h->sout, (size_t)2 * T * lat));
+    h->srows = T;
+  }
+  int launches = 0;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  lc.launch_counter = &launches;
+  const long long n_lat = (long long)T * lat;
+  UA2_CHECK_CUDA(cudaMemcpyAsync(h->noise, x, n_lat * sizeof(float), cudaMemcpyDeviceToDevice, lc.stream));  // noise = x.clone()
+  // fp32 scalar arithmetic of the reference's 0-dim tensors (AudioDiffusion1D.py:98, :122-126), one rounding per operation
+  float t = t_span[0], dt = t_span[1] - t_span[0];
+  const float one_minus_sigma = (float)(1.0 - (double)sigma_min);
+  for (int step = 1; step < n_span; ++step) {
+    UA2_CHECK_CUDA(launch(lc, dit_euler_pack_kernel, dim3(grid_for((long long)T * c.in_channels)), dim3(256), 0, x,
+                          (const float*)h->noise, incontext_x, mu, h->sinp, T, lat, cond, incontext_length, t, one_minus_sigma));
+    RUN(dit_forward(h, lc, h->sinp, nullptr, t, h->sout, 2, T));
+    UA2_CHECK_CUDA(launch(lc, dit_euler_update_kernel, dim3(grid_for(n_lat)), dim3(256), 0, x, (const float*)h->sout, n_lat,
+                          guidance_scale, dt));
+    t = t + dt;
+    if (step < n_span - 1) dt = t_span[step + 1] - t;
+  }
+  h->last_launches = launches;
+  return UA2_OK;
+}
+
+int ua2_dit_last_launch_count(ua2_dit* h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"
