@@ -15,8 +15,8 @@
 //   dit_im2col3_kernel   k = 3 'same' convolution of ProjectLayer as a GEMM over [x[t-1] | x[t] | x[t+1]]
 //   dit_epilogue_kernel  bias (+ scale | + positional table | + GELU-tanh | + SiLU | gate * . + residual | q/k/v head split)
 //   dit_ln_mod_kernel    LayerNorm without affine, then * (1 + scale) + shift with the adaLN-single table + timestep rows
-//   dit_attn_kernel      unmasked self-attention, CTA = 16 query rows x one head; K/V tiles of 32 keys staged in shared
-//                        memory and shared by the 16 rows; online softmax per row (one warp = 2 rows)
+//   dit_attn_kernel      unmasked self-attention, CTA = 32 query rows x one head; K/V tiles of 32 keys staged in shared
+//                        memory and shared by all rows; online softmax per row (one warp = 4 rows), fp32 FMA
 //   dit_euler_*          in-context blend, CFG batch assembly, guidance mix and Euler update of the solver
 #include <algorithm>
 #include <map>
@@ -187,69 +187,111 @@ __global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-constexpr int DA_ROWS = 16;   // query rows per CTA
-constexpr int DA_KEYS = 32;   // keys per shared-memory tile (one per lane)
+constexpr int DA_KEYS = 32;  // keys per shared-memory tile (one per lane in the score phase)
 
-template <int HS>
+// CTA = 8 warps x RPW query rows of one (batch, head); K / V tiles of 32 keys are staged in shared memory once and shared by
+// all rows.  Score phase: lane = key, K row read with 128-bit loads (row stride HS + 4 keeps them conflict-free), the RPW
+// query rows of the warp are broadcast reads - (1 + RPW) loads per 4 * RPW FMAs.  Online softmax per row; the probabilities
+// go through a per-warp shared tile so that the P @ V phase (lane = output dim) reads them as broadcast float4.
+template <int HS, int RPW>
 __global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__ q, const float* __restrict__ kc,
                                                        const float* __restrict__ vc, float* __restrict__ out, int T, int H) {
   constexpr int DPL = HS / 32;  // output dims per lane
-  __shared__ float Ks[DA_KEYS][HS + 1];
-  __shared__ float Vs[DA_KEYS][HS];
-  __shared__ float Qs[DA_ROWS][HS];
+  constexpr int ROWS = 8 * RPW;
+  constexpr int KST = HS + 4;
+  __shared__ __align__(16) float Qs[ROWS][HS];
+  __shared__ __align__(16) float Ks[DA_KEYS][KST];
+  __shared__ __align__(16) float Vs[DA_KEYS][HS];
+  __shared__ __align__(16) float Ps[8][RPW][DA_KEYS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t0 = blockIdx.x * DA_ROWS, h = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * ROWS, h = blockIdx.y, b = blockIdx.z;
   const int D = H * HS;
   pdl_launch_dependents();
   pdl_wait();
-  for (int i = tid; i < DA_ROWS * HS; i += 256) {
-    const int r = i / HS, d = i - r * HS;
-    Qs[r][d] = (t0 + r < T) ? q[((size_t)b * T + t0 + r) * D + h * HS + d] : 0.f;
+  for (int i = tid; i < ROWS * HS / 4; i += 256) {
+    const int r = i / (HS / 4), d4 = i - r * (HS / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t0 + r < T) v = *reinterpret_cast<const float4*>(q + ((size_t)b * T + t0 + r) * D + h * HS + d4 * 4);
+    *reinterpret_cast<float4*>(&Qs[r][d4 * 4]) = v;
   }
   const float* Kb = kc + ((size_t)b * H + h) * (size_t)T * HS;
   const float* Vb = vc + ((size_t)b * H + h) * (size_t)T * HS;
   const float scale = rsqrtf((float)HS);
-  float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-  float acc[2][DPL];
+  float mx[RPW], l[RPW], acc[RPW][DPL];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < RPW; ++r) {
+    mx[r] = -INFINITY;
+    l[r] = 0.f;
 #pragma unroll
     for (int d = 0; d < DPL; ++d) acc[r][d] = 0.f;
+  }
   for (int j0 = 0; j0 < T; j0 += DA_KEYS) {
     __syncthreads();  // previous tile fully consumed (also orders the Qs fill before the first use)
-    for (int i = tid; i < DA_KEYS * HS; i += 256) {
-      const int j = i / HS, d = i - j * HS;
-      const bool ok = j0 + j < T;
-      Ks[j][d] = ok ? Kb[(size_t)(j0 + j) * HS + d] : 0.f;
-      Vs[j][d] = ok ? Vb[(size_t)(j0 + j) * HS + d] : 0.f;
+    for (int i = tid; i < DA_KEYS * HS / 4; i += 256) {
+      const int j = i / (HS / 4), d4 = i - j * (HS / 4);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j0 + j < T) {
+        kv = *reinterpret_cast<const float4*>(Kb + (size_t)(j0 + j) * HS + d4 * 4);
+        vv = *reinterpret_cast<const float4*>(Vb + (size_t)(j0 + j) * HS + d4 * 4);
+      }
+      *reinterpret_cast<float4*>(&Ks[j][d4 * 4]) = kv;
+      *reinterpret_cast<float4*>(&Vs[j][d4 * 4]) = vv;
     }
     __syncthreads();
+    // ---- scores of this lane's key against the warp's rows
+    float s[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) s[r] = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < HS / 4; ++d4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(&Ks[lane][d4 * 4]);
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&Qs[warp * RPW + r][d4 * 4]);
+        s[r] = fmaf(q4.x, k4.x, s[r]);
+        s[r] = fmaf(q4.y, k4.y, s[r]);
+        s[r] = fmaf(q4.z, k4.z, s[r]);
+        s[r] = fmaf(q4.w, k4.w, s[r]);
+      }
+    }
     const bool valid = j0 + lane < T;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int row = warp * 2 + r;
-      float s = 0.f;
-#pragma unroll 16
-      for (int d = 0; d < HS; ++d) s = fmaf(Qs[row][d], Ks[lane][d], s);
-      s = valid ? s * scale : -INFINITY;
-      const float mn = fmaxf(mx[r], warp_max(s));  // every tile holds at least one valid key, so mn is finite
+    for (int r = 0; r < RPW; ++r) {
+      const float sv = valid ? s[r] * scale : -INFINITY;
+      const float mn = fmaxf(mx[r], warp_max(sv));  // every tile holds at least one valid key, so mn is finite
       const float corr = expf(mx[r] - mn);
-      const float p = valid ? expf(s - mn) : 0.f;
+      const float p = valid ? expf(sv - mn) : 0.f;
       l[r] = l[r] * corr + warp_sum(p);
 #pragma unroll
       for (int d = 0; d < DPL; ++d) acc[r][d] *= corr;
-#pragma unroll 8
-      for (int j = 0; j < DA_KEYS; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, p, j);
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) acc[r][d] = fmaf(pj, Vs[j][lane + 32 * d], acc[r][d]);
-      }
       mx[r] = mn;
+      Ps[warp][r][lane] = p;
     }
+    __syncwarp();
+    // ---- P @ V: lane owns output dims lane + 32 * d
+#pragma unroll 2
+    for (int j4 = 0; j4 < DA_KEYS / 4; ++j4) {
+      float4 p4[RPW];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) p4[r] = *reinterpret_cast<const float4*>(&Ps[warp][r][j4 * 4]);
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) {
+        const float v0 = Vs[j4 * 4 + 0][lane + 32 * d], v1 = Vs[j4 * 4 + 1][lane + 32 * d];
+        const float v2 = Vs[j4 * 4 + 2][lane + 32 * d], v3 = Vs[j4 * 4 + 3][lane + 32 * d];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          acc[r][d] = fmaf(p4[r].x, v0, acc[r][d]);
+          acc[r][d] = fmaf(p4[r].y, v1, acc[r][d]);
+          acc[r][d] = fmaf(p4[r].z, v2, acc[r][d]);
+          acc[r][d] = fmaf(p4[r].w, v3, acc[r][d]);
+        }
+      }
+    }
+    __syncwarp();  // Ps is rewritten by the next tile
   }
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int t = t0 + warp * 2 + r;
+  for (int r = 0; r < RPW; ++r) {
+    const int t = t0 + warp * RPW + r;
     if (t < T) {
 #pragma unroll
       for (int d = 0; d < DPL; ++d) out[((size_t)b * T + t) * D + h * HS + lane + 32 * d] = acc[r][d] / l[r];
@@ -259,11 +301,11 @@ __global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__
 
 cudaError_t launch_dit_attn(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H,
                             int hs) {
-  const dim3 grid((T + DA_ROWS - 1) / DA_ROWS, H, B), block(256);
-  switch (hs) {
-    case 32: return launch(lc, dit_attn_kernel<32>, grid, block, 0, q, kc, vc, out, T, H);
-    case 64: return launch(lc, dit_attn_kernel<64>, grid, block, 0, q, kc, vc, out, T, H);
-    case 128: return launch(lc, dit_attn_kernel<128>, grid, block, 0, q, kc, vc, out, T, H);
+  const dim3 block(256);
+  switch (hs) {  // 4 rows per warp (32 per CTA); 2 at head size 128 to stay inside 48 KB of static shared memory
+    case 32: return launch(lc, dit_attn_kernel<32, 4>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H);
+    case 64: return launch(lc, dit_attn_kernel<64, 4>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H);
+    case 128: return launch(lc, dit_attn_kernel<128, 2>, dim3((T + 15) / 16, H, B), block, 0, q, kc, vc, out, T, H);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -414,6 +456,8 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
       RUN(dmalloc(&h->tc.a, h->tc.a_floats));
       RUN(dmalloc(&h->tc.w, h->tc.w_floats));
       RUN(dmalloc(&h->tc.c, h->tc.c_floats));
+      if (!h->tc.cache) h->tc.cache = tc_cache_create();
+      h->tc.force_persistent = true;  // every call reuses all 0.9 B parameters: keep their tf32 split (12 B / parameter)
     }
     h->rows = M;
   }
@@ -579,6 +623,7 @@ int ua2_dit_destroy(ua2_dit* h) {
   free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.w, &h->tc.c,
              &h->tproj, &h->temb, &h->tsemb, &h->t6, &h->ttmp, &h->noise, &h->sinp, &h->sout});
   for (void* p : h->owned) cudaFree(p);
+  tc_cache_destroy(h->tc.cache);
   delete h;
   return UA2_OK;
 }

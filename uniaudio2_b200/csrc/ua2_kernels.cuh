@@ -42,6 +42,7 @@ void set_tc_min_rows(int v);
 int get_tc_min_rows();
 struct TcWorkspace {
   TcWeightCache* cache = nullptr;  // optional persistent split weights (option tc_persistent_weights)
+  bool force_persistent = false;   // use `cache` regardless of the global option (handles whose every call reuses all weights)
   float* a = nullptr;  // (M, 3K)
   size_t a_floats = 0;
   float* w = nullptr;  // (N_total, 3K)

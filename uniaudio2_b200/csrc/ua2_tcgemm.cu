@@ -234,7 +234,7 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   const float* w3 = nullptr;
   bool need_split = true;
   float* w3_dst = ws.w;
-  TcWeightCache* cache = g_tc_persistent ? ws.cache : nullptr;
+  TcWeightCache* cache = (g_tc_persistent || ws.force_persistent) ? ws.cache : nullptr;
   if (cache != nullptr) {
     auto it = cache->w3.find(p.W);
     if (it != cache->w3.end()) {
