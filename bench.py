@@ -374,6 +374,71 @@ def bench_codec(dev, batch=16, clip_s=10.0, reps=3, cpu=True):
     return res
 
 
+DIT_PROD = dict(num_attention_heads=24, attention_head_dim=64, in_channels=1040, out_channels=136, num_layers=32, attention_bias=True,
+                activation_fn="gelu-approximate", norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6,
+                num_embeds_ada_norm=1000)  # tools/tokenizer/ReasoningCodec_film/models/model_config.json
+
+
+def bench_flow_decoder(dev, frames=500, steps=10, reps=3, cpu=True):
+    """Tokens -> latent of `--stage all`: the flow-matching decoder of ReasoningCodec_film on one
+    20 s window - Euler solver, `steps` steps (test.sh: 10), classifier-free guidance 1.5 (reason_tokenizer.py:273), DiT of
+    model_config.json with random weights.  1.93 TFLOP per estimator call on the 2 x 500-row CFG batch."""
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.AudioDiffusion1D import BASECFM
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.transformer_1d_flow import Transformer1DModel
+
+    torch.manual_seed(0)
+    m = Transformer1DModel(device=dev, **DIT_PROD)
+    cfm = BASECFM(m)
+    T, D, I, O, L = frames, 1536, 1040, 136, 32
+    flop = L * 24 * D * D * 2 * T + L * 4 * T * T * D * 2 + 2 * 2 * T * (3 * I * D + D * D + 3 * D * O + O * O)
+    g = torch.Generator().manual_seed(1)
+    z_h, mu_h = torch.randn(1, T, O, generator=g).pin_memory(), torch.randn(1, T, I - 2 * O, generator=g).pin_memory()
+    ic = torch.zeros(1, T, O, device=dev)
+    t_span = torch.linspace(0, 1, steps + 1)
+    z, mu = z_h.to(dev), mu_h.to(dev)
+    for _ in range(2):
+        cfm.solve_euler(z, ic, 0, t_span, mu, None, 1.5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = cfm.solve_euler(z, ic, 0, t_span, mu, None, 1.5)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):  # end to end with host buffers: H2D of noise and condition, D2H of the latent
+        lat_h = cfm.solve_euler(z_h.to(dev, non_blocking=True), ic, 0, t_span, mu_h.to(dev, non_blocking=True), None, 1.5).cpu()
+    e2e_s = (time.perf_counter() - t0) / reps
+    audio_s = T / 25.0
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    bf16 = float(peaks.get("bf16_tflops_sustained", 0.0))
+    res = {"config": f"DiT 32 x (24 x 64), CFG batch 2 x {T} frames (20 s window), {steps} Euler steps, fp32-class (3xTF32)",
+           "solve_ms": round(ms, 1), "x_realtime": round(audio_s / (ms * 1e-3), 1), "e2e_x_realtime": round(audio_s / e2e_s, 1),
+           "estimator_ms": round(ms / steps, 2), "tflop_per_estimator_call": round(flop / 1e12, 3),
+           "fp32_equiv_tflops": round(flop * steps / ms / 1e9, 1), "tf32_mma_tflops": round(3 * flop * steps / ms / 1e9, 1),
+           "roofline": {"bound": "tensor", "achieved": round(3 * flop * steps / ms / 1e9, 1), "peak": round(bf16 / 2, 1) if bf16 else None,
+                        "unit": "TFLOP/s", "frac": round(3 * flop * steps / ms / 1e9 / (bf16 / 2), 4) if bf16 else None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)",
+                        "note": "achieved counts the 3 tf32 MMAs issued per fp32 product; the launch also holds the fp32 SIMT attention"},
+           "latent_shape": list(lat_h.shape)}
+    if cpu:
+        from oracle import dit_oracle as DO  # the CPU-baseline leg: the oracle port runs one estimator call on the host cores
+
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        orc = DO.DitOracle(DO.DitCfg(), sd)
+        x = torch.randn(2, T, I, generator=g)
+        tt = torch.full((2,), 0.35)
+        with torch.inference_mode():
+            t0 = time.perf_counter()
+            orc.forward(x, tt)
+            dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"kind": "port", "cores": torch.get_num_threads(), "sample": "1 estimator call (of the 10 a solve makes)",
+                               "estimator_s": round(dt, 2), "x_realtime": round(audio_s / (dt * steps), 2)}
+    del cfm, m
+    torch.cuda.empty_cache()
+    return res
+
+
 def state_dict_to_cpu(model):
     return {k: v.detach().to("cpu") for k, v in model.state_dict().items()}
 
@@ -388,6 +453,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-codec", action="store_true")
+    ap.add_argument("--no-flow-decoder", action="store_true")
     ap.add_argument("--v3-cps", type=int, default=0)
     ap.add_argument("--v3-stages", type=int, default=0)
     ap.add_argument("--v3-kcw", type=int, default=0)
@@ -549,7 +615,7 @@ def main():
                    "ms_per_step": round(ems / args.steps, 2)}
 
         hbm_peak, peak_src = load_peaks()
-        roofline = cpu_base = codec = None
+        roofline = cpu_base = codec = flow = None
         if rank == 0:
             roofline = time_dominant_kernel(model, hbm_peak)
             roofline["peak_source"] = peak_src
@@ -570,11 +636,17 @@ def main():
                     codec = bench_codec(dev, cpu=not args.no_cpu_baseline)
                 except Exception as e:  # noqa: BLE001
                     codec = {"error": f"{type(e).__name__}: {e}"}
+            if world == 1 and not args.no_flow_decoder:
+                try:  # secondary metric (tokens -> latent of --stage all), same rule
+                    flow = bench_flow_decoder(dev, cpu=not args.no_cpu_baseline)
+                except Exception as e:  # noqa: BLE001
+                    flow = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
-                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "codec": codec}))
+                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "codec": codec,
+                          "flow_decoder": flow}))
     if world > 1:
         dist.destroy_process_group()
 

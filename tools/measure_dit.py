@@ -3,13 +3,12 @@ heads, in 1040 -> out 136) on the classifier-free-guidance batch of a 20 s windo
 solver (reason_tokenizer.py:273: guidance 1.5; test.sh: 10 steps).  CUDA events on the launching stream after warm-up; random
 weights (the checkpoint is not in the repository).  Prints JSON lines.
 
-    python tools/measure_dit.py [--reps 10] [--cpu]      # --cpu also times the CPU oracle once (host cores, fp32)
+    python tools/measure_dit.py [--reps 10]      (the CPU-oracle baseline of the same call is a leg of bench.py)
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -50,7 +49,6 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--once", action="store_true", help="one estimator call only (profiling driver)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -80,20 +78,6 @@ def main():
     ms = timed(lambda: cfm.solve_euler(z, ic, 0, t_span, mu, None, 1.5), max(3, a.reps // 3))
     print(json.dumps(dict(what="solve_euler, %d steps, 20 s window" % a.steps, ms=round(ms, 2), audio_seconds=T / 25.0,
                           x_realtime=round(T / 25.0 / (ms / 1e3), 1), tc_persistent_weights=1)))
-    if a.cpu:
-        from oracle import dit_oracle as DO
-
-        cfg = DO.DitCfg()
-        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-        orc = DO.DitOracle(cfg, sd)
-        n = torch.get_num_threads()
-        with torch.no_grad():
-            t0 = time.perf_counter()
-            ref = orc.forward(x.cpu(), t.cpu())
-            dt = time.perf_counter() - t0
-        got = m(x, timestep=t).sample.cpu()
-        print(json.dumps(dict(what="CPU oracle, one estimator call", threads=n, s=round(dt, 2), fp32_TFLOPs=round(fl / dt / 1e12, 3),
-                              max_abs_diff_vs_gpu=float((got - ref).abs().max()), ref_scale=float(ref.abs().max()))))
 
 
 if __name__ == "__main__":
