@@ -69,7 +69,8 @@ enum : int {
 };
 
 struct DitEpi {
-  float* y;           // (M, N) raw GEMM output, updated in place unless stated
+  const float* src;   // (M, N) raw GEMM output (the tensor-core path's product buffer, or y itself)
+  float* y;           // (M, N) destination of the element-wise modes
   const float* bias;  // (N)
   int M, N, T;
   float s;
@@ -97,7 +98,7 @@ __global__ void dit_epilogue_kernel(const DitEpi e) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % e.N);
     const long long m = i / e.N;
-    const float v = __fadd_rn(e.y[i], e.bias[c]);
+    const float v = __fadd_rn(e.src[i], e.bias[c]);
     if (MODE == DE_BIAS) {
       e.y[i] = v;
     } else if (MODE == DE_BIAS_SCALE) {
@@ -474,8 +475,9 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
   return UA2_OK;
 }
 
-// y (M, N) = x (M, K, row stride K) @ W^T, raw (no bias): tensor cores for M >= tc_min_rows, skinny fp32 kernels below
-int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K) {
+// x (M, K, row stride K) @ W^T, raw (no bias): tensor cores for M >= tc_min_rows (the product then stays in the path's own
+// buffer, *src points at it and `y` is not written), skinny fp32 kernels below (product in y, *src = y)
+int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K, const float** src) {
   GemvParams p;
   p.W = W;
   p.N = N;
@@ -488,12 +490,16 @@ int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, 
   p.ws = h->stats;
   p.ws_floats = 2 * h->rows + 8;
   p.tc = h->tc.a ? &h->tc : nullptr;
+  const float* raw = nullptr;
+  p.raw_out = &raw;
   CU(launch_gemv(lc, PRO_PLAIN, EPI_STORE, p));
+  *src = raw ? raw : y;
   return UA2_OK;
 }
 
-DitEpi epi(float* y, const float* bias, int M, int N, int T) {
+DitEpi epi(const float* src, float* y, const float* bias, int M, int N, int T) {
   DitEpi e{};
+  e.src = src;
   e.y = y;
   e.bias = bias;
   e.M = M;
@@ -507,12 +513,13 @@ int project_layer(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* 
                   float* tmp, float* y, int B, int T, int Cin, int Cout, const float* pe) {
   const int M = B * T;
   CU(launch(lc, dit_im2col3_kernel, dim3(grid_for((long long)M * 3 * Cin)), dim3(256), 0, x, h->col, B, T, Cin));
-  RUN(linear_raw(h, lc, h->col, w1_repacked, tmp, M, Cout, 3 * Cin));
-  DitEpi e1 = epi(tmp, l1.b, M, Cout, T);
+  const float* src = nullptr;
+  RUN(linear_raw(h, lc, h->col, w1_repacked, tmp, M, Cout, 3 * Cin, &src));
+  DitEpi e1 = epi(src, tmp, l1.b, M, Cout, T);
   e1.s = 0.57735026918962576451f;  // 3 ** -0.5 rounded to fp32, transformer_1d_flow.py:32
   CU(launch_epi<DE_BIAS_SCALE>(lc, e1));
-  RUN(linear_raw(h, lc, tmp, l2.w, y, M, Cout, Cout));
-  DitEpi e2 = epi(y, l2.b, M, Cout, T);
+  RUN(linear_raw(h, lc, tmp, l2.w, y, M, Cout, Cout, &src));
+  DitEpi e2 = epi(src, y, l2.b, M, Cout, T);
   if (pe) {
     e2.pe = pe;
     CU(launch_epi<DE_BIAS_PE>(lc, e2));
@@ -529,25 +536,26 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
   // ---- adaln_single: timestep -> embedded_timestep (temb) and the 6*D modulation rows (t6)
   const int half = c.flow_t_size / 2;
   CU(launch(lc, dit_tproj_kernel, dim3((B * half + 255) / 256), dim3(256), 0, t_dev, t_val, h->tfreqs, h->tproj, B, half));
-  RUN(linear_raw(h, lc, h->tproj, h->te1.w, h->ttmp, B, D, c.flow_t_size));
-  CU(launch_epi<DE_BIAS_SILU>(lc, epi(h->ttmp, h->te1.b, B, D, 1)));
-  RUN(linear_raw(h, lc, h->ttmp, h->te2.w, h->temb, B, D, D));
+  const float* src = nullptr;
+  RUN(linear_raw(h, lc, h->tproj, h->te1.w, h->ttmp, B, D, c.flow_t_size, &src));
+  CU(launch_epi<DE_BIAS_SILU>(lc, epi(src, h->ttmp, h->te1.b, B, D, 1)));
+  RUN(linear_raw(h, lc, h->ttmp, h->te2.w, h->temb, B, D, D, &src));
   {
-    DitEpi e = epi(h->temb, h->te2.b, B, D, 1);
+    DitEpi e = epi(src, h->temb, h->te2.b, B, D, 1);
     e.y2 = h->tsemb;
     CU(launch_epi<DE_BIAS_KEEP_SILU>(lc, e));
   }
-  RUN(linear_raw(h, lc, h->tsemb, h->ada.w, h->t6, B, 6 * D, D));
-  CU(launch_epi<DE_BIAS>(lc, epi(h->t6, h->ada.b, B, 6 * D, 1)));
+  RUN(linear_raw(h, lc, h->tsemb, h->ada.w, h->t6, B, 6 * D, D, &src));
+  CU(launch_epi<DE_BIAS>(lc, epi(src, h->t6, h->ada.b, B, 6 * D, 1)));
   // ---- proj_in + positional embedding
   RUN(project_layer(h, lc, x, h->in1_w, h->in1, h->in2, h->n, h->h, B, T, c.in_channels, D, h->pe));
   // ---- blocks
   for (const DitBlock& bl : h->blocks) {
     CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 0, 1,
               c.norm_eps, T, D));
-    RUN(linear_raw(h, lc, h->n, bl.wqkv, h->qkv, M, 3 * D, D));
+    RUN(linear_raw(h, lc, h->n, bl.wqkv, h->qkv, M, 3 * D, D, &src));
     {
-      DitEpi e = epi(h->qkv, bl.bqkv, M, 3 * D, T);
+      DitEpi e = epi(src, h->qkv, bl.bqkv, M, 3 * D, T);
       e.q = h->q;
       e.k = h->k;
       e.v = h->v;
@@ -556,9 +564,9 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
       CU(launch_epi<DE_QKV_SPLIT>(lc, e));
     }
     CU(launch_dit_attn(lc, h->q, h->k, h->v, h->att, B, T, H, hs));
-    RUN(linear_raw(h, lc, h->att, bl.o.w, h->n, M, D, D));
+    RUN(linear_raw(h, lc, h->att, bl.o.w, h->n, M, D, D, &src));
     {
-      DitEpi e = epi(h->n, bl.o.b, M, D, T);
+      DitEpi e = epi(src, h->n, bl.o.b, M, D, T);
       e.y2 = h->h;
       e.table = bl.table;
       e.t6 = h->t6;
@@ -567,11 +575,11 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
     }
     CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 3, 4,
               c.norm_eps, T, D));
-    RUN(linear_raw(h, lc, h->n, bl.ff1.w, h->ff, M, 4 * D, D));
-    CU(launch_epi<DE_BIAS_GELU>(lc, epi(h->ff, bl.ff1.b, M, 4 * D, T)));
-    RUN(linear_raw(h, lc, h->ff, bl.ff2.w, h->n, M, D, 4 * D));
+    RUN(linear_raw(h, lc, h->n, bl.ff1.w, h->ff, M, 4 * D, D, &src));
+    CU(launch_epi<DE_BIAS_GELU>(lc, epi(src, h->ff, bl.ff1.b, M, 4 * D, T)));
+    RUN(linear_raw(h, lc, h->ff, bl.ff2.w, h->n, M, D, 4 * D, &src));
     {
-      DitEpi e = epi(h->n, bl.ff2.b, M, D, T);
+      DitEpi e = epi(src, h->n, bl.ff2.b, M, D, T);
       e.y2 = h->h;
       e.table = bl.table;
       e.t6 = h->t6;

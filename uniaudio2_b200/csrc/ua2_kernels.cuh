@@ -89,6 +89,10 @@ struct GemvParams {
   const float* sin = nullptr;
   int S_max = 0;
   const TcWorkspace* tc = nullptr;  // optional: enables the tcgen05 3xTF32 path for M >= sgemm_min_rows
+  // optional (host side only, EPI_STORE): when the tensor-core path serves the call, leave the raw product (M x N, row stride
+  // N) in the workspace, skip the copy-out epilogue and report its address here - for callers that run their own fused
+  // epilogue over it (ua2_dit.cu).  Left untouched (nullptr) when another path ran: the result is then in Y as usual.
+  const float** raw_out = nullptr;
   // ---- tail prefetch (filled by launch_gemv from the recorded launch sequence; see GemvSeq)
   int n_pf = 0;
   PfSpec pf[PF_MAX];

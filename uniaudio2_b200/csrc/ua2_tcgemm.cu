@@ -278,6 +278,10 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   }
   if ((e = run_tf32_gemm(lc.stream, ws.a, w3, ws.c, M, Ntot, K3)) != cudaSuccess) return e;
   if (lc.launch_counter) ++*lc.launch_counter;
+  if (p.raw_out != nullptr && epi == EPI_STORE) {  // the caller's own epilogue consumes the product in place
+    *p.raw_out = ws.c;
+    return cudaSuccess;
+  }
   const int n_units = epi == EPI_SWIGLU ? p.N : p.N / 2;
   const dim3 grid((n_units + 255) / 256, M);
 #define UA2_TCE(E) \
