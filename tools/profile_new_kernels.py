@@ -20,7 +20,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     # one layer of the temporal-transformer shape with a full 3000-slot ring, batch 4: 12 splits x 32 heads x 4 rows
-    m = StreamingTransformer(d_model=4096, num_heads=32, num_layers=1, dim_feedforward=4096, causal=True, context=3000,
+    m = StreamingTransformer(d_model=4096, num_heads=32, num_layers=1, dim_feedforward=16384, causal=True, context=3000,
                              positional_embedding="rope", norm="rms_norm_f32", gating="silu", device=dev)
     m.set_option("graph", 0)
     x = torch.randn(4, 1000, 4096, device=dev)
