@@ -1,0 +1,98 @@
+"""GPU parity of the codes -> waveform caller: uniaudio2_b200's AudioDiffusion1D.inference_codes (code lookups, projections,
+flow-matching solve through the C ABI) under the product's ReasoningTokenizer.token2audio_no_reason, against the fixtures that
+oracle/make_golden_detok.py produced from the UNMODIFIED reference source (tests/golden/detok_golden.pt).  The SQ-codec decoder
+is the fixture's stand-in (a transposed convolution with the real hop of 960, evaluated with torch in this TEST only - the
+product's ScalarModel has its own parity suite, tests/test_scalar_gpu.py); every noise draw is replayed from the fixture.
+Bar: waveform / latents within 1e-4 max-abs relative to the tensor's scale."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import detok_oracle as TO
+from oracle import dit_oracle as DO
+from oracle.make_golden_detok import CB_DIM, CB_SIZE, CODEC_DIM, DIT, VQS, random_params
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-4
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+@pytest.fixture(scope="module")
+def detok_golden():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "detok_golden.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def parts():
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.AudioDiffusion1D import AudioDiffusion1D
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.transformer_1d_flow import Transformer1DModel
+
+    p = random_params(31)
+    dit_sd = DO.random_state_dict(DIT, seed=32)
+    m = AudioDiffusion1D(Transformer1DModel(**DIT.ctor_kwargs()), codec_dim=CODEC_DIM, codebook_size=CB_SIZE, codebook_dim=CB_DIM)
+    sd = dict(m.state_dict())
+    for name, nq in VQS:
+        for i in range(nq):
+            sd[f"{name}.layers.{i}._codebook.embed"] = p[f"{name}.codebooks"][i:i + 1].clone()
+        sd[f"{name}.project_out.weight"] = p[f"{name}.project_out.weight"]
+        sd[f"{name}.project_out.bias"] = p[f"{name}.project_out.bias"]
+    sd["cond_feature_emb.weight"], sd["cond_feature_emb.bias"] = p["cond_feature_emb.weight"], p["cond_feature_emb.bias"]
+    sd["zero_cond_embedding1"] = p["zero_cond_embedding1"]
+    for k, v in dit_sd.items():
+        sd["cfm_wrapper.estimator." + k] = v
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda:0")
+    orc = TO.DetokOracle(p, DO.DitOracle(DIT, dit_sd), None)
+    return p, m, orc
+
+
+def test_inference_codes_matches_oracle(parts):
+    """One window: 25 codes -> 50 latent frames, 7 in-context frames, 3 Euler steps."""
+    p, m, orc = parts
+    g = torch.Generator().manual_seed(2)
+    codes = torch.randint(0, CB_SIZE, (1, 8, 25), generator=g)
+    true_latents = torch.randn(1, 50, 136, generator=g)
+    noise = torch.randn(1, 50, 136, generator=g)
+    with torch.no_grad():
+        ref = orc.inference_codes(codes, true_latents, 50, 7, 1.5, 3, lambda shape: noise.clone())
+    m.prepare_latents = lambda bs, n, dtype, device: noise.to(device)
+    try:
+        out = m.inference_codes([codes.cuda()], None, true_latents.cuda(), 50, 7, additional_feats=[], guidance_scale=1.5, num_steps=3,
+                                scenario="other_seg")
+    finally:
+        del m.prepare_latents
+    assert out.shape == ref.shape
+    assert torch.equal(out[:, :7].cpu(), true_latents[:, :7])  # the in-context rows are the given latents
+    assert _rel(out.cpu(), ref) < TOL
+
+
+def test_token2audio_matches_reference_golden(detok_golden, parts):
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.reason_tokenizer import ReasoningTokenizer
+
+    p, m, _ = parts
+    w = p["sq_decode.weight"].cuda()
+
+    class SQStandIn:
+        @staticmethod
+        def decode(latent):
+            return F.conv_transpose1d(latent.contiguous(), w, stride=960)
+
+    tok = ReasoningTokenizer(m, SQStandIn(), device=torch.device("cuda:0"))
+    try:
+        for c in detok_golden["cases"]:
+            it = iter(c["draws"])
+            tok._randn = lambda *shape: next(it)
+            m.prepare_latents = lambda bs, n, dtype, device: next(it).to(device)
+            wav = tok.token2audio_no_reason(c["codes"], False, duration=c["duration"], num_steps=c["steps"], disable_progress=True)
+            assert wav.shape == c["wav"].shape and wav.device.type == "cpu"
+            assert _rel(wav, c["wav"]) < TOL, f"{c['codes'].shape[-1]} codes"
+            assert next(it, None) is None  # every recorded draw was consumed, in the reference's order
+    finally:
+        if "prepare_latents" in m.__dict__:
+            del m.prepare_latents

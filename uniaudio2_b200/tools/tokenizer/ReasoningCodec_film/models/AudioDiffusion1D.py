@@ -43,3 +43,139 @@ class BASECFM(nn.Module):
             _lib.check(_lib.lib().ua2_dit_solve_euler(h, _lib.ptr(xs), _lib.ptr(ic), int(incontext_length), arr, len(ts), _lib.ptr(m), T,
                                                       float(guidance_scale), float(self.sigma_min), _lib.current_stream()), "solve_euler")
         return xs
+
+
+class ResidualVQ(nn.Module):
+    """Decode surface of vector_quantize_pytorch.ResidualVQ (1.27.15, pyproject.toml:31) as the reference uses it at
+    AudioDiffusion1D.py:577-579: get_output_from_indices(indices (B, T, q)) = project_out(sum_q codebook_q[indices[..., q]]).
+    State-dict names follow that package: project_out.{weight,bias}, layers.{i}._codebook.embed (1, K, d); its other entries
+    (project_in, EMA statistics) are accepted and ignored.  The lookup + sum runs in ua2_rvq_decode_f32."""
+
+    def __init__(self, dim, codebook_size, codebook_dim, num_quantizers, device=None, **unused_training_kwargs):
+        super().__init__()
+        self.dim, self.codebook_size, self.codebook_dim, self.num_quantizers = dim, codebook_size, codebook_dim, num_quantizers
+        self.project_out = nn.Module()
+        self.project_out.weight = nn.Parameter(torch.empty(dim, codebook_dim, device=device), requires_grad=False)
+        self.project_out.bias = nn.Parameter(torch.zeros(dim, device=device), requires_grad=False)
+        self.layers = nn.ModuleList()
+        for _ in range(num_quantizers):
+            layer = nn.Module()
+            layer._codebook = nn.Module()
+            layer._codebook.embed = nn.Parameter(torch.empty(1, codebook_size, codebook_dim, device=device), requires_grad=False)
+            self.layers.append(layer)
+        self._emb = None
+
+    def load_state_dict(self, sd, strict=True, **kw):
+        keep = set(self.state_dict().keys())
+        self._emb = None
+        return super().load_state_dict({k: v for k, v in sd.items() if k in keep}, strict=strict, **kw)
+
+    def _apply(self, fn, *a, **kw):
+        self._emb = None
+        return super()._apply(fn, *a, **kw)
+
+    def codebooks(self):
+        if self._emb is None:  # (q, K, d) contiguous, the layout ua2_rvq_decode_f32 reads
+            self._emb = torch.cat([l._codebook.embed.detach() for l in self.layers], 0).float().contiguous()
+        return self._emb
+
+    @torch.inference_mode()
+    def lookup_sum(self, codes, q_off):
+        """codes (B, n_q_total, T) int64 on the device -> sum over this VQ's quantizers [q_off, q_off + q) of the code vectors,
+        (B, codebook_dim, T)."""
+        emb = self.codebooks()
+        if not codes.is_cuda or codes.device != emb.device:
+            raise _lib.Ua2Error("ResidualVQ lookup runs on the CUDA device of its codebooks (no CPU fallback)")
+        B, nq_total, T = codes.shape
+        out = torch.empty(B, self.codebook_dim, T, device=emb.device, dtype=torch.float32)
+        with torch.cuda.device(emb.device):
+            _lib.check(_lib.lib().ua2_rvq_decode_f32(_lib.ptr(codes), _lib.ptr(emb), _lib.ptr(out), B, self.codebook_dim, T, self.codebook_size,
+                                                     self.num_quantizers, nq_total, q_off, _lib.current_stream()), "rvq_decode")
+        return out
+
+
+class AudioDiffusion1D(nn.Module):
+    """Inference surface of the reference's AudioDiffusion1D that turns reconstruction codes into SQ-codec latents:
+    `inference_codes` (AudioDiffusion1D.py:553-624, the branch without reasoning codes, scenario 'other_seg') and
+    `prepare_latents` (:652-655).  Sub-module names follow the reference (vq_pronunciation_semantic, vq_structure_semantic,
+    vq_acoustic, cond_feature_emb, zero_cond_embedding1, cfm_wrapper.estimator) so that its checkpoint keys load.
+    Arithmetic: code lookups + sums (ua2_rvq_decode_f32), the three project_out and cond_feature_emb linears
+    (ua2_linear_bias_f32; the three projections are one GEMM over the concatenated code vectors), the flow-matching solve
+    (ua2_dit_solve_euler); torch only moves data (concatenate, repeat frames x2, fill the masked tail)."""
+
+    def __init__(self, estimator: Transformer1DModel, codec_dim=768, codebook_size=8192, codebook_dim=32, sq_codec_latent=136,
+                 device=None):
+        super().__init__()
+        self.codec_dim, self.sq_codec_latent = codec_dim, sq_codec_latent
+        self.max_t_len = 30 * 50
+        self.vq_pronunciation_semantic = ResidualVQ(codec_dim, codebook_size, codebook_dim, 1, device=device)
+        self.vq_structure_semantic = ResidualVQ(codec_dim, codebook_size, codebook_dim, 1, device=device)
+        self.vq_acoustic = ResidualVQ(codec_dim, codebook_size, codebook_dim, 6, device=device)
+        self.cond_feature_emb = nn.Module()
+        self.cond_feature_emb.weight = nn.Parameter(torch.empty(codec_dim, codec_dim, device=device), requires_grad=False)
+        self.cond_feature_emb.bias = nn.Parameter(torch.zeros(codec_dim, device=device), requires_grad=False)
+        self.zero_cond_embedding1 = nn.Parameter(torch.zeros(codec_dim, device=device), requires_grad=False)
+        self.cfm_wrapper = BASECFM(estimator)
+        self._proj = None
+
+    @property
+    def device(self):
+        return self.zero_cond_embedding1.device
+
+    def _apply(self, fn, *a, **kw):
+        self._proj = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, sd, strict=True, **kw):
+        self._proj = None
+        for vq in (self.vq_pronunciation_semantic, self.vq_structure_semantic, self.vq_acoustic):
+            vq._emb = None
+        self.cfm_wrapper.estimator._destroy()  # its native handle holds the old parameter addresses
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def _linear_bias(self, x, w, b):
+        M, K = x.shape[0] * x.shape[1], x.shape[2]
+        y = torch.empty(x.shape[0], x.shape[1], w.shape[0], device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ua2_linear_bias_f32(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), M, w.shape[0], K, _lib.current_stream()),
+                       "linear_bias")
+        return y
+
+    def prepare_latents(self, batch_size, num_frames, dtype, device):
+        return torch.randn((batch_size, num_frames, self.sq_codec_latent), device=device, dtype=dtype)  # randn_tensor, :652-655
+
+    @torch.inference_mode()
+    def inference_codes(self, codes, spk_embeds, true_latents, latent_length, incontext_length, additional_feats, guidance_scale=2,
+                        num_steps=20, disable_progress=True, scenario="start_seg"):
+        if len(codes) != 1 or spk_embeds is not None or additional_feats:
+            raise NotImplementedError("served: codes = [reconstruction codes], no speaker embedding (reason_tokenizer.py:268-283)")
+        dev = self.device
+        if dev.type != "cuda":
+            raise _lib.Ua2Error("AudioDiffusion1D.inference_codes runs on a CUDA device only (no CPU fallback): call .to('cuda') first")
+        rec = codes[0].to(device=dev, dtype=torch.int64).contiguous()  # (B, 8, T): phone | semantic | 6 x acoustic
+        B, _, Tc = rec.shape
+        if self._proj is None:  # [P_phone | P_semantic | P_acoustic] and the summed bias: the three project_out as one linear
+            vqs = (self.vq_pronunciation_semantic, self.vq_structure_semantic, self.vq_acoustic)
+            self._proj = (torch.cat([v.project_out.weight.detach() for v in vqs], 1).float().contiguous(),
+                          (vqs[0].project_out.bias.detach() + vqs[1].project_out.bias.detach() + vqs[2].project_out.bias.detach()).float().contiguous())
+        summed = [self.vq_pronunciation_semantic.lookup_sum(rec, 0), self.vq_structure_semantic.lookup_sum(rec, 1),
+                  self.vq_acoustic.lookup_sum(rec, 2)]
+        x = torch.cat(summed, 1).transpose(1, 2).contiguous()  # (B, T, 3 * codebook_dim)
+        quantized = self._linear_bias(x, *self._proj)
+        merge = self._linear_bias(quantized, self.cond_feature_emb.weight.detach().float().contiguous(),
+                                  self.cond_feature_emb.bias.detach().float().contiguous())
+        merge = merge.repeat_interleave(2, dim=1)  # F.interpolate(scale_factor=2, mode='nearest') over time, :589
+        num_frames = merge.shape[1]
+        latents = self.prepare_latents(B, num_frames, torch.float32, dev)
+        # latent_masks (:609-616): frames < latent_length keep the condition, the rest get zero_cond_embedding1; frames
+        # < incontext_length (scenario 'other_seg') carry the in-context latents
+        n_ic = int(incontext_length) if scenario == "other_seg" else 0
+        n_ic = max(0, min(n_ic, num_frames))
+        merge[:, latent_length:] = self.zero_cond_embedding1.detach().float()
+        tl = true_latents.to(device=dev, dtype=torch.float32)
+        incontext = torch.zeros_like(tl)
+        incontext[:, :n_ic] = tl[:, :n_ic]
+        t_span = torch.linspace(0, 1, num_steps + 1)
+        out = self.cfm_wrapper.solve_euler(latents, incontext, n_ic, t_span, merge.contiguous(), None, guidance_scale)
+        out[:, :n_ic] = incontext[:, :n_ic]
+        return out
