@@ -14,7 +14,11 @@ from oracle import detok_oracle as TO
 from oracle import dit_oracle as DO
 from oracle.make_golden_detok import CB_DIM, CB_SIZE, CODEC_DIM, DIT, VQS, random_params
 
-pytestmark = pytest.mark.gpu
+# Written after round 1's GPU budget was spent: these two tests have never run on a B200.  They are opt-in until they have
+# (UA2_RUN_UNVERIFIED=1 python -m pytest tests/test_zzz_detok_gpu.py -m gpu) so that an unproven test cannot mask the proven suite;
+# the first GPU call of the next round runs them and removes this guard.
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("UA2_RUN_UNVERIFIED") != "1",
+                                                  reason="never run on a B200 yet (round-1 GPU budget exhausted): set UA2_RUN_UNVERIFIED=1")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-4
 
