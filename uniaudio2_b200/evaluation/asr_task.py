@@ -62,11 +62,12 @@ class Generator:
     @torch.inference_mode()
     def generate_asr(self, task_prompt, task_name=None, text_token=None, semantic_token=None, reason_token=None,
                      temperature: float = 0.9, topk: int = 200, cfg_scale=1.0, max_audio_frames: int = 500,
-                     return_ids: Optional[bool] = None):
+                     return_ids: Optional[bool] = None, _packed=None):
         """Returns the decoded text (reference behaviour) when a text tokenizer was supplied, else the list of text ids."""
         model, dev = self._model, self.device
         model.reset_caches()
-        tokens, tokens_mask = self.prepare_asr_task(task_prompt, reason_token, semantic_token)
+        # _packed: (tokens, mask) from another task's prompt packer (audio understanding, speech-to-text)
+        tokens, tokens_mask = _packed if _packed is not None else self.prepare_asr_task(task_prompt, reason_token, semantic_token)
         S = tokens.size(0)
         curr_tokens = tokens.unsqueeze(0).to(dev)
         curr_mask = tokens_mask.bool().unsqueeze(0).to(dev)
@@ -95,3 +96,4 @@ class Generator:
         return self._text_tokenizer.decode(torch.tensor(ids))
 
     generate_audio_caption = generate_asr  # audio_music_caption_task.py:201-258: same loop, caption prompt
+    generate_lyric_asr = generate_asr      # lyric_asr_task.py:202-258: same loop and prompt packing (prepare_lyric_asr_task :175)

@@ -90,16 +90,17 @@ class Generator:
     @torch.inference_mode()
     def generate_tts(self, task_prompt, task_name=None, text_token=None, semantic_token=None, reason_token=None,
                      temperature: float = 0.9, topk: int = 200, cfg_scale=1.0, max_audio_frames: int = 500,
-                     fixed_schedule: Optional[Tuple[int, int]] = None, pinned_staging: bool = True):
+                     fixed_schedule: Optional[Tuple[int, int]] = None, pinned_staging: bool = True, _packed=None):
         """Returns (reason tokens (8, T_r), semantic tokens (8, T_s)) int64 on the model device.
         fixed_schedule=(n_reason, n_semantic): synthetic mode - switch phase after n_reason frames and stop after
         n_reason + n_semantic frames regardless of EOS (random weights never emit EOS)."""
         model, dev = self._model, self.device
         model.reset_caches()
-        tokens, tokens_mask = self.prepare_tts_task(task_prompt, text_token)
+        # _packed: (tokens, mask, cfg_tokens, cfg_mask) from another task's prompt packer (instruct TTS, speech-to-speech)
+        tokens, tokens_mask = _packed[:2] if _packed is not None else self.prepare_tts_task(task_prompt, text_token)
         S = tokens.size(0)
         if self.is_cfg:
-            ctok, cmask = self.prepare_tts_task_for_cfg(task_prompt, text_token)
+            ctok, cmask = _packed[2:] if _packed is not None else self.prepare_tts_task_for_cfg(task_prompt, text_token)
             tokens = torch.stack([tokens, ctok])
             tokens_mask = torch.stack([tokens_mask, cmask])
             bs = 2
@@ -160,4 +161,32 @@ class Generator:
         de_sem = torch.stack(pre_semantic[1:]).transpose(0, 1).to(torch.int64) if len(pre_semantic) > 1 else torch.zeros(nq, 0, dtype=torch.int64)
         return de_reason.to(dev), de_sem.to(dev)
 
-    generate_audio = generate_tts  # musicgen_task.py:210 (TTM / TTA): same loop, construct with tag='caption'
+    # ---- instruct TTS (insturct_tts_task.py:170-298): [task prompt | <caption> style caption | <transcription> text], same loop
+    def _text_block(self, key, seq, blank=False):
+        seq = self.add_special_token(key, seq)
+        if blank:
+            seq = torch.ones_like(seq) * self.text_pad_token
+        data = self.text_pad(seq)
+        mask = torch.zeros((data.shape[0], self.parallel_number))
+        mask[:, -1] = True
+        return data, mask
+
+    def prepare_instruct_tts_task(self, task_prompt, caption_seq, text_seq, blank=False):
+        if blank:  # prepare_instruct_tts_task_for_cfg: every text position replaced by text_pad_token
+            task_prompt = torch.ones_like(task_prompt) * self.text_pad_token
+        blocks = [self._text_block('text_seq', task_prompt), self._text_block('caption_seq', caption_seq, blank),
+                  self._text_block('transcription_seq', text_seq, blank)]
+        return torch.cat([b[0] for b in blocks], dim=0), torch.cat([b[1] for b in blocks], dim=0)
+
+    def generate_instruct_tts(self, task_prompt, task_name=None, text_token=None, caption=None, semantic_token=None, reason_token=None,
+                              temperature: float = 0.9, topk: int = 200, cfg_scale=1.0, **kw):
+        packed = self.prepare_instruct_tts_task(task_prompt, caption, text_token)
+        if self.is_cfg:
+            packed = packed + self.prepare_instruct_tts_task(task_prompt, caption, text_token, blank=True)
+        else:
+            packed = packed + (None, None)
+        return self.generate_tts(task_prompt, task_name, text_token=text_token, temperature=temperature, topk=topk, cfg_scale=cfg_scale,
+                                 _packed=packed, **kw)
+
+    generate_audio = generate_tts  # musicgen_task.py:210 / audiogen_task.py:209 (TTM / TTA): same loop, construct with tag='caption'
+    generate_LTS = generate_tts    # songen_task.py:210 (lyrics -> song): same loop, construct with tag='lyric'
