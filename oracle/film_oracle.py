@@ -11,7 +11,6 @@ cannot be imported: whisper, peft, fairseq ... are absent) on a stand-in `self` 
 tests/golden/film_golden.pt.  The product operators ua2_film_f32 / ua2_interp_nearest_f32 / ua2_linear_bias_f32 are compared
 with the same formulas on the GPU (tests/test_scalar_gpu.py::test_film_interp_linear_bias).
 """
-import torch
 import torch.nn.functional as F
 
 

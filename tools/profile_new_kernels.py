@@ -1,7 +1,11 @@
 """Profiling driver (run under ncu): a few launches of the kernels added late in round 1 - the streaming transformer's ring
 attention, sample_token and the flow decoder's attention.  Not a benchmark.
 
-    ncu --set full --clock-control none --import-source on -k regex:"ring_attn_kernel|sample_token_kernel|dit_attn_kernel" -c 6 \
+Round-1 note: the one attempt to capture this under `ncu --set full` hit its 200 s limit before the first matching kernel (the
+first `import torch` on a fresh box takes about a minute by itself, more under ncu's injection) and used up the round's GPU
+budget - page torch in first (`python -c "import torch"` in the same gpurun command) and give the call a longer limit:
+
+    python -c "import torch"; ncu --set full --clock-control none --import-source on -k regex:"ring_attn_kernel|sample_token_kernel|dit_attn_kernel" -s 6 -c 6 \
         -o gpurun_out/new_kernels python tools/profile_new_kernels.py
 """
 import os
@@ -23,10 +27,10 @@ def main():
     m = StreamingTransformer(d_model=4096, num_heads=32, num_layers=1, dim_feedforward=16384, causal=True, context=3000,
                              positional_embedding="rope", norm="rms_norm_f32", gating="silu", device=dev)
     m.set_option("graph", 0)
-    x = torch.randn(4, 1000, 4096, device=dev)
+    x = torch.randn(4, 500, 4096, device=dev)
     with m.streaming(4):
-        for _ in range(3):
-            m(x)          # fills the ring 1000 rows at a time (many-row path)
+        for _ in range(6):
+            m(x)          # fills the 3000-slot ring 500 rows at a time (many-row path)
         for _ in range(2):
             m(x[:, :1])   # decode steps against the full ring: the launches to look at
     lg = torch.randn(8, 2048, device=dev) * 2
