@@ -376,6 +376,10 @@ int ua2_dit_forward(ua2_dit* h, const float* hidden_states, const float* timeste
  * (torch.linspace(0, 1, steps + 1)); guidance_scale > 1; sigma_min = 1e-4 (:68). */
 int ua2_dit_solve_euler(ua2_dit* h, float* x, const float* incontext_x, int incontext_length, const float* t_span, int n_span,
                         const float* mu, int T, float guidance_scale, float sigma_min, void* stream);
+/* knobs: "bf16" (0/1, default 0): linears of >= 32 rows run on bf16 operands with fp32 accumulation (tcgen05 kind::f16) - the
+ * arithmetic of the reference, which calls this model under torch.autocast(bfloat16) (reason_tokenizer.py:265); the default
+ * keeps fp32-class accuracy (3xTF32).  A bf16 copy of every weight is kept (2 B per parameter). */
+int ua2_dit_set_option(ua2_dit* h, const char* name, int value);
 int ua2_dit_last_launch_count(ua2_dit* h);
 
 #ifdef __cplusplus

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--once", action="store_true", help="one estimator call only (profiling driver)")
+    ap.add_argument("--bf16", action="store_true", help="also time the bf16 option (many-row linears on bf16 operands)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -70,6 +71,15 @@ def main():
         print(json.dumps(dict(what="estimator call, CFG batch 2 x %d frames" % T, tc_persistent_weights=persistent,
                               launches=m.last_launch_count(), ms=round(ms, 3), algorithmic_TFLOP=round(fl / 1e12, 3),
                               fp32_equiv_TFLOPs=round(fl / ms / 1e9, 1), tf32_mma_TFLOPs=round(3 * fl / ms / 1e9, 1))))
+    if a.bf16:
+        ref = m(x, timestep=t).sample
+        m.set_option("bf16", 1)
+        ms = timed(lambda: m(x, timestep=t), a.reps)
+        got = m(x, timestep=t).sample
+        m.set_option("bf16", 0)
+        print(json.dumps(dict(what="estimator call, bf16 option", launches=m.last_launch_count(), ms=round(ms, 3),
+                              bf16_mma_TFLOPs=round(fl / ms / 1e9, 1), max_abs_diff_vs_3xtf32=float((got - ref).abs().max()),
+                              out_scale=float(ref.abs().max()))))
     cfm = BASECFM(m)
     z = torch.randn(1, T, 136, device=dev)
     ic = torch.zeros(1, T, 136, device=dev)

@@ -109,6 +109,7 @@ SYMBOLS = {
     "ua2_dit_finalize": (C.c_int, [_P, _P]),
     "ua2_dit_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "ua2_dit_solve_euler": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.c_int, _P, C.c_int, C.c_float, C.c_float, _P]),
+    "ua2_dit_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ua2_dit_last_launch_count": (C.c_int, [_P]),
     "ua2_stx_create": (C.c_int, [C.POINTER(StxCfg), C.POINTER(_P)]),
     "ua2_stx_destroy": (C.c_int, [_P]),

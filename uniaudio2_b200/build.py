@@ -34,7 +34,8 @@ CUTLASS = _cutlass_include()
 # the tensor-core GEMM translation unit uses the CUTLASS collective builders when the headers exist (else a stub)
 _CUTLASS_FLAGS = (["-DUA2_HAVE_CUTLASS", "--expt-relaxed-constexpr", "-diag-suppress", "20012", "-I", os.path.join(CUTLASS, "include"),
                    "-I", os.path.join(CUTLASS, "tools", "util", "include")] if CUTLASS else [])
-EXTRA = {"ua2_tcgemm.cu": ["-DUA2_HAVE_CUTLASS"] if CUTLASS else [], "ua2_tcgemm_t128.cu": _CUTLASS_FLAGS, "ua2_tcgemm_t64.cu": _CUTLASS_FLAGS}
+EXTRA = {"ua2_tcgemm.cu": ["-DUA2_HAVE_CUTLASS"] if CUTLASS else [], "ua2_tcgemm_t128.cu": _CUTLASS_FLAGS, "ua2_tcgemm_t64.cu": _CUTLASS_FLAGS,
+         "ua2_tcgemm_bf16.cu": _CUTLASS_FLAGS, "ua2_dit.cu": ["-DUA2_HAVE_CUTLASS"] if CUTLASS else []}
 
 
 def _sources():

@@ -23,11 +23,29 @@
 #include <string>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "../../include/ua2_b200.h"
 #include "ua2_kernels.cuh"
 
 namespace ua2 {
+#ifdef UA2_HAVE_CUTLASS
+// ua2_tcgemm_bf16.cu: C (M x N, fp32) = A (M x K, bf16) * B (N x K, bf16)^T on tcgen05, fp32 accumulation
+cudaError_t run_bf16_gemm_128x128(cudaStream_t st, const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N, int K);
+#endif
 namespace {
+
+// fp32 -> bf16 (round to nearest even), 4 elements per thread; n must be a multiple of 4 (K % 8 == 0 on this path)
+__global__ void dit_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<__nv_bfloat162*>(y)[2 * i] = a;
+    reinterpret_cast<__nv_bfloat162*>(y)[2 * i + 1] = b;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ conv k3 as GEMM input
 // out[m, k*C + c] = x[b, t + k - 1, c] (0 outside the sequence), m = b*T + t
@@ -402,6 +420,10 @@ struct ua2_dit {
   size_t srows = 0;
   float *noise = nullptr, *sinp = nullptr, *sout = nullptr;
   TcWorkspace tc;
+  // option "bf16": linears of >= 32 rows on bf16 operands with fp32 accumulation (the reference's autocast arithmetic)
+  int opt_bf16 = 0;
+  __nv_bfloat16* a16 = nullptr;  // (M, kmax) activations converted per call
+  std::map<const float*, __nv_bfloat16*> w16;  // weights converted once, keyed by the fp32 tensor
   int last_launches = 0;
 };
 
@@ -457,6 +479,9 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
       RUN(dmalloc(&h->tc.a, h->tc.a_floats));
       RUN(dmalloc(&h->tc.w, h->tc.w_floats));
       RUN(dmalloc(&h->tc.c, h->tc.c_floats));
+      if (h->a16) cudaFree(h->a16);
+      h->a16 = nullptr;
+      UA2_CHECK_CUDA(cudaMalloc((void**)&h->a16, M * kmax * sizeof(__nv_bfloat16)));
       if (!h->tc.cache) h->tc.cache = tc_cache_create();
       h->tc.force_persistent = true;  // every call reuses all 0.9 B parameters: keep their tf32 split (12 B / parameter)
     }
@@ -478,6 +503,27 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
 // x (M, K, row stride K) @ W^T, raw (no bias): tensor cores for M >= tc_min_rows (the product then stays in the path's own
 // buffer, *src points at it and `y` is not written), skinny fp32 kernels below (product in y, *src = y)
 int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K, const float** src) {
+#ifdef UA2_HAVE_CUTLASS
+  if (h->opt_bf16 && h->a16 != nullptr && M >= 32 && (K % 8) == 0 && (N % 4) == 0 && (size_t)M * N <= h->tc.c_floats) {
+    auto it = h->w16.find(W);
+    if (it == h->w16.end()) {  // first use of this weight: keep a bf16 copy (2 B / parameter)
+      __nv_bfloat16* wb = nullptr;
+      UA2_CHECK_CUDA(cudaMalloc((void**)&wb, (size_t)N * K * sizeof(__nv_bfloat16)));
+      it = h->w16.emplace(W, wb).first;
+      const long long n4 = (long long)N * K / 4;
+      CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, W, wb, n4));
+    }
+    const long long n4 = (long long)M * K / 4;
+    CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, x, h->a16, n4));
+    const cudaError_t e = run_bf16_gemm_128x128(lc.stream, h->a16, it->second, h->tc.c, M, N, K);
+    if (e == cudaSuccess) {
+      if (lc.launch_counter) ++*lc.launch_counter;
+      *src = h->tc.c;
+      return UA2_OK;
+    }
+    if (e != cudaErrorNotSupported) CU(e);
+  }
+#endif
   GemvParams p;
   p.W = W;
   p.N = N;
@@ -631,6 +677,8 @@ int ua2_dit_destroy(ua2_dit* h) {
   free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.w, &h->tc.c,
              &h->tproj, &h->temb, &h->tsemb, &h->t6, &h->ttmp, &h->noise, &h->sinp, &h->sout});
   for (void* p : h->owned) cudaFree(p);
+  for (auto& kv : h->w16) cudaFree(kv.second);
+  if (h->a16) cudaFree(h->a16);
   tc_cache_destroy(h->tc.cache);
   delete h;
   return UA2_OK;
@@ -815,6 +863,21 @@ int ua2_dit_solve_euler(ua2_dit* h, float* x, const float* incontext_x, int inco
   }
   h->last_launches = launches;
   return UA2_OK;
+}
+
+int ua2_dit_set_option(ua2_dit* h, const char* name, int value) {
+  UA2_REQUIRE(h && name, "null argument");
+  const std::string n(name);
+  if (n == "bf16") {
+#ifdef UA2_HAVE_CUTLASS
+    h->opt_bf16 = value ? 1 : 0;
+    return UA2_OK;
+#else
+    UA2_REQUIRE(!value, "library was built without the CUTLASS headers: no bf16 tensor-core path");
+    return UA2_OK;
+#endif
+  }
+  UA2_REQUIRE(false, "unknown option " + n);
 }
 
 int ua2_dit_last_launch_count(ua2_dit* h) { return h ? h->last_launches : 0; }

@@ -156,6 +156,11 @@ class Transformer1DModel(nn.Module):
         self._h, self._keep = h, keep
         return h
 
+    def set_option(self, name: str, value: int):
+        """'bf16' (0/1, default 0): run the many-row linears on bf16 operands with fp32 accumulation, like the reference under
+        torch.autocast(bfloat16) (reason_tokenizer.py:265); the default is fp32-class (3xTF32)."""
+        _lib.check(_lib.lib().ua2_dit_set_option(self._ensure(), name.encode(), int(value)), f"set_option({name})")
+
     def last_launch_count(self) -> int:
         return int(_lib.lib().ua2_dit_last_launch_count(self._h)) if self._h is not None else 0
 
