@@ -9,7 +9,10 @@ Bar: waveform / latents within 1e-4 max-abs relative to the tensor's scale.
 
 (2) The "bf16" option of the flow-matching decoder (ua2_dit_set_option): many-row linears on bf16 operands with fp32 accumulation
 (CUTLASS tcgen05 kind::f16 collective, csrc/ua2_tcgemm_bf16.cu) against the fp32 oracle, bar 3e-2 relative to the output scale
-(bf16 has 8 mantissa bits; the reference runs these linears under torch.autocast(bfloat16) itself)."""
+(bf16 has 8 mantissa bits; the reference runs these linears under torch.autocast(bfloat16) itself).
+
+(3) The global option "conv_tc": causal convolutions with Cin * K >= 1024 as im2col + tcgen05 3xTF32 GEMM (csrc/ua2_convtc.cu)
+against the conv oracle (2e-5 relative, the bar of the SIMT core's own test) and, on the full codec geometry, bit-equal VQ indices."""
 import os
 
 import pytest
@@ -131,3 +134,73 @@ def test_dit_bf16_option_against_fp32_oracle(heads, hd, T, B):
     assert _rel(y32, ref) < 1e-4 and torch.equal(y32, y32b)  # the option leaves the default path untouched
     err = _rel(y16, ref)
     assert 1e-6 < err < 3e-2, err  # really a different arithmetic, and within bf16's reach
+
+
+# (3) option "conv_tc": wide causal convolutions as im2col + tcgen05 3xTF32 GEMM (csrc/ua2_convtc.cu)
+@pytest.mark.parametrize("B,Cin,Cout,T,K,stride,elu,res,rep", [
+    (2, 128, 256, 2501, 10, 5, 1, 0, 0),    # K_total 1280: one chunk, ragged length
+    (1, 512, 1024, 640, 16, 8, 1, 0, 0),    # K_total 8192
+    (1, 1024, 512, 333, 3, 1, 1, 1, 0),     # last encoder conv + residual
+    (2, 512, 512, 400, 4, 2, 0, 0, 1),      # ConvDownsample1d: replicate pad, no bias
+    (1, 64, 128, 4000, 8, 4, 1, 0, 0),      # K_total 512 < 1024: stays on the SIMT core (the option must not change it)
+])
+def test_conv_tc_option_matches_oracle(B, Cin, Cout, T, K, stride, elu, res, rep):
+    import math
+
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cin + Cout + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = None if rep else torch.randn(Cout, generator=g) * 0.1
+    ref = CO.conv1d_causal(F.elu(x) if elu else x, w, b, stride=stride, dilation=1, pad_mode="replicate" if rep else "constant")
+    r = torch.randn_like(ref) if res else None
+    if res:
+        ref = r + ref
+    xd, wd = x.cuda(), w.contiguous().cuda()
+    bd = b.cuda() if b is not None else None
+    rd = r.cuda() if res else None
+    outs = []
+    try:
+        for opt in (0, 1):
+            _lib.check(L.ua2_set_global_option(b"conv_tc", opt))
+            y = torch.full((B, Cout, ref.shape[-1]), float("nan"), device="cuda")
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(rd), _lib.ptr(y), B, Cin, Cout, T, K,
+                                                    stride, 1, elu, rep, None))
+            torch.cuda.synchronize()
+            outs.append(y.cpu())
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
+    for y in outs:
+        assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    if Cin * K < 1024:
+        assert torch.equal(outs[0], outs[1])
+
+
+def test_conv_tc_option_keeps_codec_indices():
+    """Full mimi_config.yaml geometry: VQ indices with the wide convolutions on the tensor cores equal the oracle's."""
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+    from uniaudio2_b200.tools.tokenizer.MimiCodec.mimi_codec import MimiCodec
+
+    cfg = CO.MimiCfg()
+    sd = CO.random_mimi_state_dict(cfg, seed=7)
+    m = MimiCodec(sample_rate=cfg.sample_rate, n_filters=cfg.n_filters, encoder_rates=cfg.encoder_rates, compress=cfg.compress,
+                  latent_dim=cfg.latent_dim, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim, rvq_layers=cfg.rvq_layers,
+                  num_heads=cfg.num_heads, num_layers=cfg.num_layers, layer_scale=cfg.layer_scale, context=cfg.context, device="cuda")
+    full = m.state_dict()
+    full.update({k: v.cuda() for k, v in sd.items()})
+    m.load_state_dict(full, strict=True)
+    wav = torch.randn(4, 1, 3 * 24000 + 311, generator=torch.Generator().manual_seed(5)) * 0.2
+    with torch.no_grad():
+        ref_codes = CO.MimiOracle(cfg, sd).encode(wav)
+    L = _lib.lib()
+    try:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", 1))
+        codes = m.encode(wav.cuda())
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
+    assert torch.equal(codes.cpu(), ref_codes), f"VQ index agreement {float((codes.cpu() == ref_codes).float().mean()):.4f}"

@@ -1,0 +1,160 @@
+// Wide SEANet convolutions on the tensor cores (option "conv_tc", default 0 - written at the end of round 1, NOT yet run on a
+// B200).
+//
+// profiles/r1_kernel_rooflines.md: the register-tiled fp32 core runs the strided down-convolutions (k = 2 * stride, 64..1024
+// channels) at 25-30 TFLOP/s (34-40 % of the fp32 pipe) while the tcgen05 3xTF32 GEMM of the linears sustains ~170
+// fp32-equivalent TFLOP/s.  For layers whose reduction length Cin * K is >= 1024 the convolution is therefore run as
+//     im2col  : A[(b, t)][ci * K + tap] = f(x[b, ci, t * stride - pad + tap * dilation])      (f = identity | ELU, zero / replicate pad)
+//     GEMM    : C = A W^T with W = the torch weight (Cout, Cin, K) read as (Cout, Cin * K) - no repack - on the 3xTF32 path
+//     epilogue: y[b, co, t] = C[(b, t)][co] + bias[co] (+ residual), transposed back to the (B, C, T) layout through shared memory
+// in chunks of rows that bound the scratch.  Same arithmetic class as the transformer linears of the codec (VQ indices stayed
+// bit-equal there).  The im2col matrix costs 4 * Cin * K bytes per output position of extra traffic, which is why the narrow
+// 24 kHz layers (Cin * K <= 512) stay on the SIMT core.
+#include <algorithm>
+
+#include "ua2_kernels.cuh"
+
+namespace ua2 {
+namespace {
+
+__device__ __forceinline__ float elu1c(float x) { return x > 0.f ? x : expm1f(x); }
+
+// rows [m0, m0 + rows) of the im2col matrix; consecutive threads walk k (coalesced stores; loads are runs of K taps)
+__global__ void conv_im2col_kernel(const float* __restrict__ x, float* __restrict__ A, int Cin, int T_in, int T_out, int Ktaps, int stride,
+                                   int dilation, int pad_left, int pre_elu, int replicate, long long m0, int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int KT = Cin * Ktaps;
+  const long long n = (long long)rows * KT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % KT);
+    const long long m = m0 + i / KT;
+    const int b = (int)(m / T_out), t = (int)(m - (long long)b * T_out);
+    const int ci = k / Ktaps, tap = k - ci * Ktaps;
+    int pos = t * stride - pad_left + tap * dilation;
+    bool inside = pos >= 0 && pos < T_in;
+    if (!inside && replicate) {
+      pos = pos < 0 ? 0 : T_in - 1;
+      inside = true;
+    }
+    float v = 0.f;
+    if (inside) {
+      v = x[((size_t)b * Cin + ci) * T_in + pos];
+      if (pre_elu) v = elu1c(v);
+    }
+    A[i] = v;
+  }
+}
+
+// y[b, co, t] = C[r][co] + bias[co] (+ res[b, co, t]) for rows r of the chunk; 32 x 32 tiles through shared memory
+__global__ void conv_tc_epilogue_kernel(const float* __restrict__ C, const float* __restrict__ bias, const float* __restrict__ res,
+                                        float* __restrict__ y, int Cout, int T_out, long long m0, int rows) {
+  __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // read: threadIdx.x walks channels
+    const int r = r0 + i, co = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && co < Cout) ? C[(size_t)r * Cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // write: threadIdx.x walks positions
+    const int co = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && co < Cout) {
+      const long long m = m0 + r;
+      const int b = (int)(m / T_out), t = (int)(m - (long long)b * T_out);
+      const size_t o = ((size_t)b * Cout + co) * T_out + t;
+      float v = tile[threadIdx.x][i] + (bias ? bias[co] : 0.f);
+      if (res) v += res[o];
+      y[o] = v;
+    }
+  }
+}
+
+struct ConvTcScratch {
+  float *a = nullptr, *c = nullptr;
+  size_t a_floats = 0, c_floats = 0;
+  TcWorkspace tc;
+};
+ConvTcScratch g_ws;
+int g_conv_tc = 0;
+
+cudaError_t grow(float** p, size_t* have, size_t want) {
+  if (want <= *have) return cudaSuccess;
+  if (*p) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+  }
+  cudaError_t e = cudaMalloc((void**)p, want * sizeof(float));
+  if (e == cudaSuccess) *have = want;
+  return e;
+}
+
+}  // namespace
+
+void set_conv_tc(int v) { g_conv_tc = v ? 1 : 0; }
+int get_conv_tc() { return g_conv_tc; }
+
+// returns cudaErrorNotSupported when the layer is not served here (the caller continues on the SIMT core)
+cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y,
+                             int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
+                             int replicate) {
+  const int KT = Cin * Ktaps;
+  const long long M = (long long)B * T_out;
+  if (!tc_gemm_available() || !get_tc_gemm() || KT < 1024 || (KT & 3) || (Cout & 3) || M < 128) return cudaErrorNotSupported;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(lc.stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return cudaErrorNotSupported;  // the scratch may have to grow
+  // rows per chunk: im2col chunk <= 64 Mi floats (256 MB; its tf32 split is 3x that)
+  long long R = std::max<long long>(128, ((64LL << 20) / KT) / 128 * 128);
+  R = std::min(R, M);
+  cudaError_t e;
+  if ((e = grow(&g_ws.a, &g_ws.a_floats, (size_t)R * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.c, &g_ws.c_floats, (size_t)R * Cout)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 3 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, (size_t)Cout * 3 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.c, &g_ws.tc.c_floats, (size_t)R * Cout)) != cudaSuccess) return e;
+  if (!g_ws.tc.cache) g_ws.tc.cache = tc_cache_create();
+  g_ws.tc.force_persistent = true;  // codec weights are long-lived: keep their tf32 split (12 B per parameter)
+  for (long long m0 = 0; m0 < M; m0 += R) {
+    const int rows = (int)std::min<long long>(R, M - m0);
+    const long long n = (long long)rows * KT;
+    const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 64);
+    if ((e = launch(lc, conv_im2col_kernel, dim3(grid), dim3(256), 0, x, g_ws.a, Cin, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
+                    replicate, m0, rows)) != cudaSuccess)
+      return e;
+    GemvParams p;
+    p.W = w_torch;
+    p.N = Cout;
+    p.K = KT;
+    p.M = rows;
+    p.X = g_ws.a;
+    p.ldx = KT;
+    p.Y = g_ws.c;
+    p.ldy = Cout;
+    p.tc = &g_ws.tc;
+    const float* raw = nullptr;
+    p.raw_out = &raw;
+    if (rows >= get_tc_min_rows()) {
+      e = launch_tc_linear(lc, PRO_PLAIN, EPI_STORE, p);
+    } else {
+      e = cudaErrorNotSupported;
+    }
+    if (e == cudaErrorNotSupported) {  // tail chunk too small for the tensor-core path: skinny fp32 kernels into g_ws.c
+      p.raw_out = nullptr;
+      p.tc = nullptr;
+      e = launch_gemv(lc, PRO_PLAIN, EPI_STORE, p);
+    }
+    if (e != cudaSuccess) return e;
+    const float* src = raw ? raw : g_ws.c;
+    if ((e = launch(lc, conv_tc_epilogue_kernel, dim3((rows + 31) / 32, (Cout + 31) / 32), dim3(32, 8), 0, src, bias, res, y, Cout, T_out, m0,
+                    rows)) != cudaSuccess)
+      return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace ua2

@@ -132,6 +132,12 @@ cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const floa
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
                                int pad_left, int pre_elu, int replicate, const float* prelu = nullptr);  // 1 = register-streamed LDG, 2 = per-warp bulk-copy rings, 3 = persistent slab + K-split rings (default)
+// wide convolutions (Cin * Ktaps >= 1024) as im2col + tcgen05 3xTF32 GEMM (ua2_convtc.cu; option "conv_tc", default 0)
+cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y,
+                             int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
+                             int replicate);
+void set_conv_tc(int v);
+int get_conv_tc();
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);
 void set_gemv3_ctas_per_sm(int v);
 void set_gemv3_max_stages(int v);

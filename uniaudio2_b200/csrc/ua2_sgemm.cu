@@ -459,6 +459,11 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
                                int pad_left, int pre_elu, int replicate, const float* prelu) {
+  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 0): wide layers on the tensor cores, ua2_convtc.cu
+    const cudaError_t e = launch_conv1d_tc(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
+                                           replicate);
+    if (e != cudaErrorNotSupported) return e;
+  }
   ConvGemmParams p{x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu, replicate, 1, 0, T_out,
                    prelu};
   const long long M = (long long)B * T_out;
