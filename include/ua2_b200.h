@@ -43,8 +43,8 @@ const char* ua2_version(void);
  * 3xTF32 tcgen05 GEMMs - fp32-class accuracy, csrc/ua2_tcgemm.cu), "tc_persistent_weights" (0/1, default 0: keep the
  * tf32-split copy of every weight the tensor-core path has used, 12 B per parameter, instead of re-splitting per call -
  * for batched decode frames, e.g. tc_min_rows = 16 with batch 32),
- * "conv_tc" (0/1, default 0: causal convolutions with Cin * K >= 1024 run as im2col + tcgen05 3xTF32 GEMM instead of the fp32
- * register-tiled core - csrc/ua2_convtc.cu; written at the end of round 1 and not yet measured),
+ * "conv_tc" (0/1, default 0: causal convolutions with Cin * K >= 1024 and transposed convolutions with Cin >= 128 run as im2col +
+ * tcgen05 3xTF32 GEMM instead of the fp32 register-tiled core - csrc/ua2_convtc.cu; written at the end of round 1 and not yet measured),
  * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with
  * -DUA2_GEMV3_TAIL_PREFETCH=1 - measured slower, see profiles/r1_l2_prefetch_experiment.md) */
 int ua2_set_global_option(const char* name, int value);

@@ -204,3 +204,65 @@ def test_conv_tc_option_keeps_codec_indices():
     finally:
         _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
     assert torch.equal(codes.cpu(), ref_codes), f"VQ index agreement {float((codes.cpu() == ref_codes).float().mean()):.4f}"
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,stride", [(1, 1024, 512, 40, 8), (2, 512, 256, 177, 6), (1, 256, 128, 700, 5), (2, 128, 64, 3001, 4),
+                                                 (1, 64, 32, 500, 4)])  # the last one (2 * Cin < 256) stays on the SIMT phase GEMMs
+def test_convtr_tc_option_matches_oracle(B, Cin, Cout, T, stride):
+    import math
+
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cin + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, 2 * stride, generator=g) / math.sqrt(Cin * 2)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = CO.convtr1d_causal(F.elu(x), w, b, stride)
+    xd, wt, bd = x.cuda(), w.contiguous().cuda(), b.cuda()
+    wp = torch.empty(stride * Cout * Cin * 2, device="cuda")
+    _lib.check(L.ua2_convtr1d_repack_phase_f32(_lib.ptr(wt), _lib.ptr(wp), Cin, Cout, stride, None))
+    outs = []
+    try:
+        for opt in (0, 1):
+            _lib.check(L.ua2_set_global_option(b"conv_tc", opt))
+            y = torch.full((B, Cout, T * stride), float("nan"), device="cuda")
+            _lib.check(L.ua2_convtr1d_causal_gemm_f32(_lib.ptr(xd), _lib.ptr(wp), _lib.ptr(bd), _lib.ptr(y), B, Cin, Cout, T, stride, 1, None))
+            torch.cuda.synchronize()
+            outs.append(y.cpu())
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
+    for y in outs:
+        assert y.shape == ref.shape
+        assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    if 2 * Cin < 256:
+        assert torch.equal(outs[0], outs[1])
+
+
+def test_conv_tc_option_keeps_decoded_waveform():
+    """Full mimi_config.yaml geometry, decode: waveform within 1e-4 max-abs of the oracle with the wide (transposed) convolutions
+    on the tensor cores."""
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+    from uniaudio2_b200.tools.tokenizer.MimiCodec.mimi_codec import MimiCodec
+
+    cfg = CO.MimiCfg()
+    sd = CO.random_mimi_state_dict(cfg, seed=7)
+    m = MimiCodec(sample_rate=cfg.sample_rate, n_filters=cfg.n_filters, encoder_rates=cfg.encoder_rates, compress=cfg.compress,
+                  latent_dim=cfg.latent_dim, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim, rvq_layers=cfg.rvq_layers,
+                  num_heads=cfg.num_heads, num_layers=cfg.num_layers, layer_scale=cfg.layer_scale, context=cfg.context, device="cuda")
+    full = m.state_dict()
+    full.update({k: v.cuda() for k, v in sd.items()})
+    m.load_state_dict(full, strict=True)
+    codes = torch.randint(0, cfg.codebook_size, (4, cfg.rvq_layers, 40), generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        ref = CO.MimiOracle(cfg, sd).decode(codes)
+    L = _lib.lib()
+    try:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", 1))
+        out = m.decode(codes.cuda())
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
+    assert float((out.cpu() - ref).abs().max()) < 1e-4

@@ -7,7 +7,9 @@
 //     im2col  : A[(b, t)][ci * K + tap] = f(x[b, ci, t * stride - pad + tap * dilation])      (f = identity | ELU, zero / replicate pad)
 //     GEMM    : C = A W^T with W = the torch weight (Cout, Cin, K) read as (Cout, Cin * K) - no repack - on the 3xTF32 path
 //     epilogue: y[b, co, t] = C[(b, t)][co] + bias[co] (+ residual), transposed back to the (B, C, T) layout through shared memory
-// in chunks of rows that bound the scratch.  Same arithmetic class as the transformer linears of the codec (VQ indices stayed
+// in chunks of rows that bound the scratch.  Transposed convolutions (kernel = 2 * stride) are ONE GEMM over all output phases
+// (K = 2 * Cin, N = stride * Cout) with a scattering epilogue; there the im2col matrix is only twice the input, so they are
+// served from Cin >= 128 on (the SIMT phase GEMMs run the 128 -> 64 stage at 13 TFLOP/s).  Same arithmetic class as the transformer linears of the codec (VQ indices stayed
 // bit-equal there).  The im2col matrix costs 4 * Cin * K bytes per output position of extra traffic, which is why the narrow
 // 24 kHz layers (Cin * K <= 512) stay on the SIMT core.
 #include <algorithm>
@@ -67,6 +69,75 @@ __global__ void conv_tc_epilogue_kernel(const float* __restrict__ C, const float
       float v = tile[threadIdx.x][i] + (bias ? bias[co] : 0.f);
       if (res) v += res[o];
       y[o] = v;
+    }
+  }
+}
+
+
+// ---- transposed convolution (kernel = 2 * stride): every output phase is a 2-tap filter over the input grid (ua2_sgemm.cu,
+// launch_convtr1d_gemm), so all `stride` phases are ONE GEMM:  A[(b, j)][ci * 2 + tap] = f(x[b, ci, j - tap]),
+// W = w_phase (stride, Cout, Cin, 2) read as (stride * Cout, Cin * 2),  C[(b, j)][ph * Cout + co] -> y[b, co, j * stride + ph - crop]
+// 32 rows x 32 input channels per CTA through shared memory: loads walk j (coalesced), stores walk k (coalesced float2)
+__global__ void convtr_im2col_kernel(const float* __restrict__ x, float* __restrict__ A, int Cin, int T_in, int Tj, int pre_elu,
+                                     long long m0, int rows) {
+  __shared__ float t0[32][33], t1[32][33];  // [ci][row]: tap 0 = x[j], tap 1 = x[j - 1]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int r = r0 + threadIdx.x;
+  int b = 0, j = 0;
+  if (r < rows) {
+    const long long m = m0 + r;
+    b = (int)(m / Tj);
+    j = (int)(m - (long long)b * Tj);
+  }
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ci = c0 + i;
+    float a = 0.f, bb = 0.f;
+    if (r < rows && ci < Cin) {
+      const float* xr = x + ((size_t)b * Cin + ci) * T_in;
+      if (j < T_in) a = pre_elu ? elu1c(xr[j]) : xr[j];
+      if (j >= 1 && j - 1 < T_in) bb = pre_elu ? elu1c(xr[j - 1]) : xr[j - 1];
+    }
+    t0[i][threadIdx.x] = a;
+    t1[i][threadIdx.x] = bb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int rr = r0 + i, ci = c0 + threadIdx.x;
+    if (rr < rows && ci < Cin)
+      *reinterpret_cast<float2*>(A + (size_t)rr * 2 * Cin + 2 * ci) = make_float2(t0[threadIdx.x][i], t1[threadIdx.x][i]);
+  }
+}
+
+constexpr int TR_J = 8;      // input positions per CTA of the epilogue
+constexpr int TR_MAX_S = 8;  // largest stride served (SEANet ratios are <= 8)
+
+// y[b, co, j * s + ph - crop] = C[(b, j)][ph * Cout + co] + bias[co]; reads walk co, writes walk the 8 * s consecutive samples
+__global__ void convtr_tc_epilogue_kernel(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ y, int Cout, int s,
+                                          int Tj, int T_out, int crop_left, long long m0, int rows) {
+  __shared__ float tile[TR_J][TR_MAX_S][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * TR_J, c0 = blockIdx.y * 32;
+  const int N = s * Cout;
+  {
+    const int jl = threadIdx.y, co = c0 + threadIdx.x;  // blockDim = (32, TR_J)
+    for (int ph = 0; ph < s; ++ph)
+      tile[jl][ph][threadIdx.x] = (r0 + jl < rows && co < Cout) ? C[(size_t)(r0 + jl) * N + ph * Cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int cl = threadIdx.y; cl < 32; cl += blockDim.y) {
+    const int co = c0 + cl;
+    if (co >= Cout) continue;
+    const float bv = bias ? bias[co] : 0.f;
+    for (int e = threadIdx.x; e < TR_J * s; e += 32) {
+      const int jl = e / s, ph = e - jl * s;
+      if (r0 + jl >= rows) continue;
+      const long long m = m0 + r0 + jl;
+      const int b = (int)(m / Tj), j = (int)(m - (long long)b * Tj);
+      const int t = j * s + ph - crop_left;
+      if (t >= 0 && t < T_out) y[((size_t)b * Cout + co) * T_out + t] = tile[jl][ph][cl] + bv;
     }
   }
 }
@@ -152,6 +223,59 @@ cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w
     const float* src = raw ? raw : g_ws.c;
     if ((e = launch(lc, conv_tc_epilogue_kernel, dim3((rows + 31) / 32, (Cout + 31) / 32), dim3(32, 8), 0, src, bias, res, y, Cout, T_out, m0,
                     rows)) != cudaSuccess)
+      return e;
+  }
+  return cudaSuccess;
+}
+
+
+// Transposed conv of launch_convtr1d_gemm (kernel = 2 * stride) on the tensor cores; cudaErrorNotSupported -> SIMT phase GEMMs
+cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin,
+                               int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out) {
+  const int KT = 2 * Cin, N = stride * Cout;
+  const int Tj = (crop_left + T_out > T_in * stride) ? T_in + 1 : T_in;  // same input grid as the SIMT launcher
+  const long long M = (long long)B * Tj;
+  if (!tc_gemm_available() || !get_tc_gemm() || KT < 256 || (KT & 3) || (N & 3) || stride > TR_MAX_S || M < 128) return cudaErrorNotSupported;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(lc.stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return cudaErrorNotSupported;
+  long long R = std::max<long long>(128, ((64LL << 20) / std::max(KT, N)) / 128 * 128);
+  R = std::min(R, M);
+  cudaError_t e;
+  if ((e = grow(&g_ws.a, &g_ws.a_floats, (size_t)R * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.c, &g_ws.c_floats, (size_t)R * N)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 3 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, (size_t)N * 3 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.c, &g_ws.tc.c_floats, (size_t)R * N)) != cudaSuccess) return e;
+  if (!g_ws.tc.cache) g_ws.tc.cache = tc_cache_create();
+  g_ws.tc.force_persistent = true;
+  for (long long m0 = 0; m0 < M; m0 += R) {
+    const int rows = (int)std::min<long long>(R, M - m0);
+    if ((e = launch(lc, convtr_im2col_kernel, dim3((rows + 31) / 32, (Cin + 31) / 32), dim3(32, 8), 0, x, g_ws.a, Cin, T_in, Tj, pre_elu, m0,
+                    rows)) != cudaSuccess)
+      return e;
+    GemvParams p;
+    p.W = w_phase;
+    p.N = N;
+    p.K = KT;
+    p.M = rows;
+    p.X = g_ws.a;
+    p.ldx = KT;
+    p.Y = g_ws.c;
+    p.ldy = N;
+    p.tc = &g_ws.tc;
+    const float* raw = nullptr;
+    p.raw_out = &raw;
+    e = rows >= get_tc_min_rows() ? launch_tc_linear(lc, PRO_PLAIN, EPI_STORE, p) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported) {
+      p.raw_out = nullptr;
+      p.tc = nullptr;
+      e = launch_gemv(lc, PRO_PLAIN, EPI_STORE, p);
+    }
+    if (e != cudaSuccess) return e;
+    const float* src = raw ? raw : g_ws.c;
+    if ((e = launch(lc, convtr_tc_epilogue_kernel, dim3((rows + TR_J - 1) / TR_J, (Cout + 31) / 32), dim3(32, TR_J), 0, src, bias, y, Cout, stride,
+                    Tj, T_out, crop_left, m0, rows)) != cudaSuccess)
       return e;
   }
   return cudaSuccess;

@@ -136,6 +136,8 @@ cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float*
 cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y,
                              int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
                              int replicate);
+cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin,
+                               int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out);
 void set_conv_tc(int v);
 int get_conv_tc();
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);

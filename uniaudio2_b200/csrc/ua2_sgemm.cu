@@ -481,6 +481,10 @@ cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const floa
                                  const float* prelu) {
   // as a conv over the input grid: 2 taps, tap 0 -> x[j], tap 1 -> x[j-1]  (dilation -1, no padding, input stride 1);
   // j runs to T_in inclusive when the right tail (x[T_in - 1] * w[ph + s]) survives the crop
+  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 0): all phases as one tensor-core GEMM, ua2_convtc.cu
+    const cudaError_t e = launch_convtr1d_tc(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, pre_elu, crop_left, T_out);
+    if (e != cudaErrorNotSupported) return e;
+  }
   const int Tj = (crop_left + T_out > T_in * stride) ? T_in + 1 : T_in;
   ConvGemmParams p{x, w_phase, bias, nullptr, y, B, Cin, Cout, T_in, Tj, 2, 1, -1, 0, pre_elu, 0, stride, crop_left, T_out, prelu};
   const long long M = (long long)B * Tj;
