@@ -43,6 +43,7 @@ const char* ua2_version(void);
  * 3xTF32 tcgen05 GEMMs - fp32-class accuracy, csrc/ua2_tcgemm.cu), "tc_persistent_weights" (0/1, default 0: keep the
  * tf32-split copy of every weight the tensor-core path has used, 12 B per parameter, instead of re-splitting per call -
  * for batched decode frames, e.g. tc_min_rows = 16 with batch 32),
+ * "resblock_fused" (0/1, default 0: the 64-channel SEANet residual blocks of the codec handle run as one kernel, csrc/ua2_resblock.cu),
  * "conv_tc" (0/1, default 0: causal convolutions with Cin * K >= 1024 and transposed convolutions with Cin >= 128 run as im2col +
  * tcgen05 3xTF32 GEMM instead of the fp32 register-tiled core - csrc/ua2_convtc.cu; written at the end of round 1 and not yet measured),
  * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with
@@ -183,6 +184,12 @@ int ua2_conv1d_causal_f32(const float* x, const float* w_ckc, const float* bias,
 int ua2_conv1d_causal_gemm_f32(const float* x, const float* w_torch, const float* bias, const float* residual, float* y, int B,
                                int Cin, int Cout, int T_in, int K, int stride, int dilation, int pre_elu, int replicate_pad,
                                void* stream);
+/* SEANetResnetBlock.forward (modules/seanet.py:21-94, dilation 1, true_skip) as ONE kernel that keeps the hidden activation on
+ * chip: y = x + conv_k1(ELU(conv_k3(ELU(x)))).  w1 (H, C, 3), w2 (C, H, 1) in torch's Conv1d layout; served for C = 64, H = 32
+ * (the blocks that run at 24 kHz).  The codec handle uses it when the global option "resblock_fused" is 1 (default 0: written at
+ * the end of round 1, not yet run on a B200). */
+int ua2_resblock_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int B, int C, int H,
+                     int T, void* stream);
 /* StreamingConvTranspose1d.forward, causal, trim_right_ratio = 1 (modules/conv.py:306-329): kernel = 2*stride,
  * T_out = T_in * stride.  w_ckc: torch's (Cin, Cout, K) weights repacked to (Cin, K, Cout). */
 int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bias, float* y, int B, int Cin, int Cout,

@@ -12,7 +12,10 @@ Bar: waveform / latents within 1e-4 max-abs relative to the tensor's scale.
 (bf16 has 8 mantissa bits; the reference runs these linears under torch.autocast(bfloat16) itself).
 
 (3) The global option "conv_tc": causal convolutions with Cin * K >= 1024 as im2col + tcgen05 3xTF32 GEMM (csrc/ua2_convtc.cu)
-against the conv oracle (2e-5 relative, the bar of the SIMT core's own test) and, on the full codec geometry, bit-equal VQ indices."""
+against the conv oracle (2e-5 relative, the bar of the SIMT core's own test) and, on the full codec geometry, bit-equal VQ indices.
+
+(4) The fused SEANet residual block (ua2_resblock_f32, global option "resblock_fused") against the two-convolution oracle and on
+the full codec geometry."""
 import os
 
 import pytest
@@ -266,3 +269,64 @@ def test_conv_tc_option_keeps_decoded_waveform():
     finally:
         _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
     assert float((out.cpu() - ref).abs().max()) < 1e-4
+
+
+# (4) fused SEANet residual block (csrc/ua2_resblock.cu, global option "resblock_fused")
+@pytest.mark.parametrize("B,T", [(1, 128), (2, 1000), (3, 4099), (1, 5)])
+def test_fused_resblock_matches_oracle(B, T):
+    import math
+
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    C, H = 64, 32
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(B, C, T, generator=g)
+    w1 = torch.randn(H, C, 3, generator=g) / math.sqrt(C * 3)
+    b1 = torch.randn(H, generator=g) * 0.1
+    w2 = torch.randn(C, H, 1, generator=g) / math.sqrt(H)
+    b2 = torch.randn(C, generator=g) * 0.1
+    hid = CO.conv1d_causal(F.elu(x), w1, b1)
+    ref = x + CO.conv1d_causal(F.elu(hid), w2, b2)
+    xd = x.cuda()
+    y = torch.full_like(xd, float("nan"))
+    _lib.check(L.ua2_resblock_f32(_lib.ptr(xd), _lib.ptr(w1.cuda()), _lib.ptr(b1.cuda()), _lib.ptr(w2.contiguous().cuda()), _lib.ptr(b2.cuda()),
+                                  _lib.ptr(y), B, C, H, T, None))
+    torch.cuda.synchronize()
+    assert float((y.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_resblock_f32(_lib.ptr(xd), _lib.ptr(w1.cuda()), _lib.ptr(b1.cuda()), _lib.ptr(w2.cuda()), _lib.ptr(b2.cuda()), _lib.ptr(y),
+                                      B, 128, 64, T, None))
+
+
+def test_resblock_fused_option_keeps_codec_results():
+    """Full mimi_config.yaml geometry with the 64-channel residual blocks fused: indices equal the oracle's, decoded waveform
+    within 1e-4."""
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+    from uniaudio2_b200.tools.tokenizer.MimiCodec.mimi_codec import MimiCodec
+
+    cfg = CO.MimiCfg()
+    sd = CO.random_mimi_state_dict(cfg, seed=7)
+    m = MimiCodec(sample_rate=cfg.sample_rate, n_filters=cfg.n_filters, encoder_rates=cfg.encoder_rates, compress=cfg.compress,
+                  latent_dim=cfg.latent_dim, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim, rvq_layers=cfg.rvq_layers,
+                  num_heads=cfg.num_heads, num_layers=cfg.num_layers, layer_scale=cfg.layer_scale, context=cfg.context, device="cuda")
+    full = m.state_dict()
+    full.update({k: v.cuda() for k, v in sd.items()})
+    m.load_state_dict(full, strict=True)
+    wav = torch.randn(2, 1, 2 * 24000 + 311, generator=torch.Generator().manual_seed(5)) * 0.2
+    orc = CO.MimiOracle(cfg, sd)
+    with torch.no_grad():
+        ref_codes = orc.encode(wav)
+        ref_wav = orc.decode(ref_codes)
+    L = _lib.lib()
+    try:
+        _lib.check(L.ua2_set_global_option(b"resblock_fused", 1))
+        codes = m.encode(wav.cuda())
+        out = m.decode(ref_codes.cuda())
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(L.ua2_set_global_option(b"resblock_fused", 0))
+    assert torch.equal(codes.cpu(), ref_codes)
+    assert float((out.cpu() - ref_wav).abs().max()) < 1e-4

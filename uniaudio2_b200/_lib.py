@@ -75,6 +75,7 @@ SYMBOLS = {
                                         C.c_int, C.c_int, _P]),
     "ua2_conv1d_causal_gemm_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, _P]),
+    "ua2_resblock_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_convtr1d_causal_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_convtr1d_repack_phase_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_convtr1d_causal_gemm_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -541,6 +541,20 @@ int ua2_conv1d_causal_gemm_f32(const float* x, const float* w_torch, const float
   return UA2_OK;
 }
 
+// SEANetResnetBlock as one kernel (ua2_resblock.cu); served shape: C = 64, hidden 32, kernel 3 / 1, dilation 1
+int ua2_resblock_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int B, int C, int H,
+                     int T, void* stream) {
+  UA2_REQUIRE(x && w1 && b1 && w2 && b2 && y, "null argument");
+  UA2_REQUIRE(B >= 1 && T >= 1, "bad shape");
+  UA2_REQUIRE(x != y, "y must not alias x");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  const cudaError_t e = launch_resblock_fused(lc, x, w1, b1, w2, b2, y, B, C, H, T);
+  UA2_REQUIRE(e != cudaErrorNotSupported, "the fused residual block is served for C = 64, hidden = 32 only");
+  UA2_CHECK_CUDA(e);
+  return UA2_OK;
+}
+
 int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bias, float* y, int B, int Cin, int Cout,
                             int T_in, int stride, int pre_elu, void* stream) {
   UA2_REQUIRE(x && w_ckc && y, "null argument");

@@ -213,6 +213,23 @@ int conv(ua2_codec* h, const std::string& key, const float* x, const float* res,
   return ua2_conv1d_causal_gemm_f32(x, c->w_src, c->bias, res, y, B, c->cin, c->cout, T, c->k, stride, 1, pre_elu, 0, st);
 }
 
+// SEANetResnetBlock (modules/seanet.py:21-94): y = x + conv_k1(ELU(conv_k3(ELU(x)))); `tmp` holds the hidden activation of the
+// two-launch form.  Option "resblock_fused": one kernel for the 64 -> 32 -> 64 blocks (ua2_resblock.cu).
+int resblock(ua2_codec* h, const std::string& p, const float* x, float* tmp, float* y, int B, int T, void* st) {
+  if (get_resblock_fused()) {
+    const ConvW *c1 = find_conv(h, p + "1.conv.conv"), *c3 = find_conv(h, p + "3.conv.conv");
+    if (c1 && c3 && c1->w_src && c3->w_src && c1->k == 3 && c3->k == 1 && c1->cout == c3->cin && c1->cin == c3->cout) {
+      LaunchCtx lc;
+      lc.stream = (cudaStream_t)st;
+      const cudaError_t e = launch_resblock_fused(lc, x, c1->w_src, c1->bias, c3->w_src, c3->bias, y, B, c1->cin, c1->cout, T);
+      if (e == cudaSuccess) return UA2_OK;
+      if (e != cudaErrorNotSupported) UA2_CHECK_CUDA(e);
+    }
+  }
+  RUN(conv(h, p + "1.conv.conv", x, nullptr, tmp, B, T, 1, 1, st));
+  return conv(h, p + "3.conv.conv", tmp, x, y, B, T, 1, 1, st);  // x + block(x)
+}
+
 // ProjectedTransformer(conv_layout=True) over x (B, C, T) in place; tmp buffers carved from the workspace by the caller
 int run_transformer(ua2_codec* h, int which, float* x_bct, float* xt, float* qbuf, float* kbuf, float* vbuf, float* hbuf,
                     float* o_part, float* ml_part, float* sg_ws, size_t sg_ws_floats, int B, int T, void* st) {
@@ -598,8 +615,7 @@ int ua2_codec_encode(ua2_codec* h, const float* wav, int B, int T, int64_t* code
   for (int i = 0; i < c.n_ratios; ++i) {
     const int ratio = c.ratios[c.n_ratios - 1 - i];
     const std::string p = "encoder.model." + std::to_string(idx) + ".block.";
-    RUN(conv(h, p + "1.conv.conv", a, nullptr, v, B, Ts[i], 1, 1, st));
-    RUN(conv(h, p + "3.conv.conv", v, a, b, B, Ts[i], 1, 1, st));  // x + block(x)
+    RUN(resblock(h, p, a, v, b, B, Ts[i], st));
     RUN(conv(h, "encoder.model." + std::to_string(idx + 2) + ".conv.conv", b, nullptr, a, B, Ts[i], ratio, 1, st));
     idx += 3;
   }
@@ -678,8 +694,7 @@ int ua2_codec_decode(ua2_codec* h, const int64_t* codes, int B, int Tq, float* w
     UA2_REQUIRE(ct && ct->w, "decoder convtr weight missing");
     RUN(ua2_convtr1d_causal_gemm_f32(x, ct->w, ct->bias, y, B, ct->cin, ct->cout, Ts[i], ratio, 1, st));
     const std::string p = "decoder.model." + std::to_string(idx + 2) + ".block.";
-    RUN(conv(h, p + "1.conv.conv", y, nullptr, v, B, Ts[i + 1], 1, 1, st));
-    RUN(conv(h, p + "3.conv.conv", v, y, x, B, Ts[i + 1], 1, 1, st));
+    RUN(resblock(h, p, y, v, x, B, Ts[i + 1], st));
     idx += 3;
   }
   RUN(conv(h, "decoder.model." + std::to_string(idx + 1) + ".conv.conv", x, nullptr, wav, B, Ts.back(), 1, 1, st));

@@ -138,6 +138,11 @@ cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w
                              int replicate);
 cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin,
                                int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out);
+// fused SEANet residual block for the 64-channel / 24 kHz stages (ua2_resblock.cu; option "resblock_fused", default 0)
+cudaError_t launch_resblock_fused(const LaunchCtx& lc, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  float* y, int B, int C, int H, int T);
+void set_resblock_fused(int v);
+int get_resblock_fused();
 void set_conv_tc(int v);
 int get_conv_tc();
 cudaError_t launch_gemv3(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, int n_splits);

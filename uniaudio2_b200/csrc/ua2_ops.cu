@@ -40,6 +40,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_tc_gemm(value);
     return UA2_OK;
   }
+  if (std::string(name) == "resblock_fused") {
+    set_resblock_fused(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "conv_tc") {
     UA2_REQUIRE(!value || tc_gemm_available(), "library was built without the CUTLASS headers: no tensor-core path");
     set_conv_tc(value);
