@@ -73,53 +73,38 @@ class DetokOracle:
 
     def token2audio_no_reason(self, rec_codec: torch.Tensor, duration=20, num_steps=20, randn: Callable = None):
         """ReasoningTokenizer.token2audio_no_reason (:228-306): rec_codec (B, 8, T2) int64 -> wave (B, samples) on the host.
-        (The reference pins guidance_scale = 1.5 in its inference_codes calls, :273/:282.)"""
+        (The reference pins guidance_scale = 1.5 in its inference_codes calls, :273/:282.)  Written with explicit index
+        arithmetic: the reference's repeated `cat([x, x])` + crop is periodic indexing, first with the period of the input
+        (when it is shorter than a window), then with the period of that result (to reach a whole number of hops)."""
         randn = randn or (lambda shape: torch.randn(*shape))
-        first_latent = randn((rec_codec.shape[0], int(duration * 25), self.lat))
-        first_latent_length = 0
-        min_samples = int(duration * self.rec_frame_rate)
-        hop_samples = min_samples // 4 * 3
-        ovlp_samples = min_samples - hop_samples
-        ovlp_frames = ovlp_samples // 2
-        rec_codes_len = rec_codec.shape[-1]
-        target_len = int((rec_codes_len - 0) / 12.5 * self.sample_rate)
-        if rec_codes_len < min_samples:
-            while rec_codec.shape[-1] < min_samples:
-                rec_codec = torch.cat([rec_codec, rec_codec], -1)
-            rec_codec = rec_codec[:, :, 0:min_samples]
-        rec_codes_len = rec_codec.shape[-1]
-        if (rec_codes_len - ovlp_samples) % hop_samples > 0:
-            len_codes = math.ceil((rec_codes_len - ovlp_samples) / float(hop_samples)) * hop_samples + ovlp_samples
-            while rec_codec.shape[-1] < len_codes:
-                rec_codec = torch.cat([rec_codec, rec_codec], -1)
-            rec_codec = rec_codec[:, :, 0:len_codes]
-        latent_length = int(duration * self.sq_codec_hz)
-        latent_list: List[torch.Tensor] = []
-        for sinx in range(0, rec_codec.shape[-1] - hop_samples, hop_samples):
-            codes_input = rec_codec[:, :, sinx:sinx + min_samples]
-            if sinx == 0:
-                latents = self.inference_codes(codes_input, first_latent, latent_length, first_latent_length, 1.5, num_steps, randn)
-            else:
-                true_latent = latent_list[-1][:, -ovlp_frames:, :]
-                len_add = latent_length - true_latent.shape[1]
-                incontext_length = true_latent.shape[1]
-                true_latent = torch.cat([true_latent, randn((true_latent.shape[0], len_add, true_latent.shape[-1]))], 1)
-                latents = self.inference_codes(codes_input, true_latent, latent_length, incontext_length, 1.5, num_steps, randn)
-            latent_list.append(latents)
-        latent_list = [l.float() for l in latent_list]
-        latent_list[0] = latent_list[0][:, first_latent_length:, :]
-        min_samples = int(duration * self.sample_rate)
-        hop_samples = min_samples // 4 * 3
-        ovlp_samples = min_samples - hop_samples
-        output = None
-        for latent in latent_list:
-            cur_output = self.sq_decode(latent.transpose(1, 2)).squeeze(0)
-            cur_output = cur_output[:, 0:min_samples].detach().cpu()
-            if output is None:
-                output = cur_output
-            else:
-                ov_win = torch.from_numpy(np.linspace(0, 1, ovlp_samples)[None, :])
-                ov_win = torch.cat([ov_win, 1 - ov_win], -1)
-                output[:, -ovlp_samples:] = output[:, -ovlp_samples:] * ov_win[:, -ovlp_samples:] + cur_output[:, 0:ovlp_samples] * ov_win[:, 0:ovlp_samples]
-                output = torch.cat([output, cur_output[:, ovlp_samples:]], -1)
-        return output[:, 0:target_len]
+        n_in = rec_codec.shape[-1]
+        win = int(duration * self.rec_frame_rate)      # code frames per window
+        hop = win // 4 * 3
+        ov = win - hop
+        n_lat = int(duration * self.sq_codec_hz)       # latent frames per window
+        prior = randn((rec_codec.shape[0], int(duration * 25), self.lat))
+        idx = torch.arange(max(n_in, win)) % n_in      # :247-250
+        if (len(idx) - ov) % hop > 0:                  # :252-256
+            n_full = math.ceil((len(idx) - ov) / float(hop)) * hop + ov
+            idx = idx[torch.arange(n_full) % len(idx)]
+        codes = rec_codec[:, :, idx]
+        lat_windows: List[torch.Tensor] = []
+        for k, start in enumerate(range(0, codes.shape[-1] - hop, hop)):
+            pinned = 0
+            if k > 0:                                  # :276-283: the last ov // 2 latent frames of the previous window lead
+                tail = lat_windows[-1][:, -(ov // 2):, :]
+                pinned = tail.shape[1]
+                prior = torch.cat([tail, randn((tail.shape[0], n_lat - pinned, tail.shape[-1]))], 1)
+            lat_windows.append(self.inference_codes(codes[:, :, start:start + win], prior, n_lat, pinned, 1.5, num_steps, randn))
+        n_wave = int(duration * self.sample_rate)
+        wave_ov = n_wave - n_wave // 4 * 3
+        fade_in = torch.from_numpy(np.linspace(0, 1, wave_ov)[None, :])  # float64, :299-301
+        out = None
+        for lat in lat_windows:
+            cur = self.sq_decode(lat.float().transpose(1, 2)).squeeze(0)[:, :n_wave].detach().cpu()
+            if out is None:
+                out = cur
+                continue
+            blended = out[:, -wave_ov:] * (1 - fade_in) + cur[:, :wave_ov] * fade_in
+            out = torch.cat([out[:, :-wave_ov], blended.to(out.dtype), cur[:, wave_ov:]], -1)
+        return out[:, :int(n_in / 12.5 * self.sample_rate)]

@@ -3,17 +3,64 @@
     wave = tok.detokenize_no_reason(rec_codec (8, T2), return_reasoning_text=False, steps=10)        # :399-404
     wave = tok.token2audio_no_reason(rec_codec (B, 8, T2), False, duration=20, num_steps=20)         # :228-306
 
-i.e. the codes -> waveform caller of `--stage all` (multi_task_inference.py:546): windows of `duration` seconds with a 3/4 hop,
-every window = AudioDiffusion1D.inference_codes (flow-matching solve with the previous window's tail as in-context latents) ->
-ScalarModel.decode, linear cross-fade of the overlaps on the host (the reference does the cross-fade on the CPU in float64 too).
-The host logic below is the reference's, statement for statement (tests/test_detok_oracle.py runs it against fixtures produced
-by the unmodified reference source); `model` and `SQCodec` are the uniaudio2_b200 drop-ins (GPU only).
-The tokenize direction (Whisper / WavLM / BEST-RQ front-ends) is not on this path.
+i.e. the codes -> waveform caller of `--stage all` (multi_task_inference.py:546).  What the reference does, and this does too:
+the code sequence is made periodic and cut into windows of `duration` seconds that advance by 3/4 of a window; every window is
+one AudioDiffusion1D.inference_codes call (a flow-matching solve) whose first latent frames are pinned to the tail of the previous
+window's latents; each window's latents go through the SQ-codec decoder, and consecutive waveforms are joined by a linear
+cross-fade over the shared quarter (on the host, in float64, like the reference).  tests/test_detok_oracle.py checks this host
+logic bit-exactly against fixtures produced by the unmodified reference source; `model` and `SQCodec` are the uniaudio2_b200
+drop-ins (GPU only).  The tokenize direction (Whisper / WavLM / BEST-RQ front-ends) is not on this path.
 """
 import math
+from dataclasses import dataclass
 
 import numpy as np
 import torch
+
+LATENT_DIM = 136          # SQ-codec latent width, hard-wired at reason_tokenizer.py:234
+GUIDANCE_IN_LOOP = 1.5    # the reference ignores its guidance_scale argument inside the window loop (:273, :282)
+
+
+@dataclass
+class _Windows:
+    """Window geometry in code frames (12.5 Hz) and in waveform samples (24 kHz); the reference's `*_samples` variables."""
+
+    codes: int          # code frames per window
+    hop: int            # window advance, 3/4 of a window (integer arithmetic of the reference: codes // 4 * 3)
+    overlap: int        # codes - hop
+    latents: int        # latent frames per window (25 Hz)
+    wave: int           # samples per window
+    wave_overlap: int   # samples shared by consecutive windows
+
+    @staticmethod
+    def of(duration, rec_frame_rate, sq_codec_hz, sample_rate):
+        codes = int(duration * rec_frame_rate)
+        hop = codes // 4 * 3
+        wave = int(duration * sample_rate)
+        return _Windows(codes, hop, codes - hop, int(duration * sq_codec_hz), wave, wave - wave // 4 * 3)
+
+
+def _make_periodic(rec_codec, w: _Windows):
+    """Repeat the code sequence (by doubling, like the reference) until it covers a whole number of hops plus one overlap."""
+    def tile_to(x, n):
+        while x.shape[-1] < n:
+            x = torch.cat([x, x], -1)
+        return x[:, :, :n]
+
+    if rec_codec.shape[-1] < w.codes:
+        rec_codec = tile_to(rec_codec, w.codes)
+    n = rec_codec.shape[-1]
+    if (n - w.overlap) % w.hop > 0:
+        rec_codec = tile_to(rec_codec, math.ceil((n - w.overlap) / float(w.hop)) * w.hop + w.overlap)
+    return rec_codec
+
+
+def _cross_fade(joined, nxt, n):
+    """Blend the last n samples of `joined` into the first n of `nxt` with a linear ramp (float64 ramp from numpy, as the
+    reference builds it) and append the rest."""
+    ramp = torch.from_numpy(np.linspace(0, 1, n)[None, :])
+    joined[:, -n:] = joined[:, -n:] * (1 - ramp) + nxt[:, :n] * ramp
+    return torch.cat([joined, nxt[:, n:]], -1)
 
 
 class ReasoningTokenizer:
@@ -21,76 +68,46 @@ class ReasoningTokenizer:
         self.sample_rate = 24000
         self.device = device
         self.n_codebook = 8
-        self.sq_codec_hz = 25        # the frame-rate of SQCodec
-        self.rec_frame_rate = 12.5
+        self.sq_codec_hz = 25        # latent frames per second
+        self.rec_frame_rate = 12.5   # reconstruction-code frames per second
         self.reason_frame_rate = 5
         self.model = model
         self.SQCodec = SQCodec
 
     def _randn(self, *shape):
-        """The reference draws these on the CPU generator and moves them to the device (reason_tokenizer.py:234, :279)."""
+        """Noise the reference draws on the CPU generator and then moves to the device (reason_tokenizer.py:234, :279)."""
         return torch.randn(*shape)
+
+    def _solve_window(self, codes, prior, n_pinned, latent_frames, num_steps, disable_progress):
+        return self.model.inference_codes([codes], None, prior, latent_frames, n_pinned, additional_feats=[], guidance_scale=GUIDANCE_IN_LOOP,
+                                          num_steps=num_steps, disable_progress=disable_progress, scenario="other_seg")
 
     @torch.no_grad()
     def token2audio_no_reason(self, rec_codec, return_reasoning_text, duration=20, guidance_scale=1.5, num_steps=20, disable_progress=False):
+        w = _Windows.of(duration, self.rec_frame_rate, self.sq_codec_hz, self.sample_rate)
         rec_codec = rec_codec.to(self.device)
-        first_latent = self._randn(rec_codec.shape[0], int(duration * 25), 136).to(self.device)
-        first_latent_length = 0
-        first_latent_codes_length = 0
-        min_samples = int(duration * self.rec_frame_rate)
-        hop_samples = min_samples // 4 * 3
-        ovlp_samples = min_samples - hop_samples
-        ovlp_frames = ovlp_samples // 2
-        rec_codes_len = rec_codec.shape[-1]
-        target_len = int((rec_codes_len - first_latent_codes_length) / 12.5 * self.sample_rate)
-        if rec_codes_len < min_samples:
-            while rec_codec.shape[-1] < min_samples:
-                rec_codec = torch.cat([rec_codec, rec_codec], -1)
-            rec_codec = rec_codec[:, :, 0:min_samples]
-        rec_codes_len = rec_codec.shape[-1]
-        if (rec_codes_len - ovlp_samples) % hop_samples > 0:
-            len_codes = math.ceil((rec_codes_len - ovlp_samples) / float(hop_samples)) * hop_samples + ovlp_samples
-            while rec_codec.shape[-1] < len_codes:
-                rec_codec = torch.cat([rec_codec, rec_codec], -1)
-            rec_codec = rec_codec[:, :, 0:len_codes]
-        latent_length = int(duration * self.sq_codec_hz)
-        latent_list = []
-        spk_embeds = None
-        for sinx in range(0, rec_codec.shape[-1] - hop_samples, hop_samples):
-            codes_input = [rec_codec[:, :, sinx:sinx + min_samples]]
-            if sinx == 0:
-                incontext_length = first_latent_length
-                latents = self.model.inference_codes(codes_input, spk_embeds, first_latent, latent_length, incontext_length,
-                                                     additional_feats=[], guidance_scale=1.5, num_steps=num_steps,
-                                                     disable_progress=disable_progress, scenario="other_seg")
-            else:
-                true_latent = latent_list[-1][:, -ovlp_frames:, :]
-                len_add_to_latent = latent_length - true_latent.shape[1]
-                incontext_length = true_latent.shape[1]
-                true_latent = torch.cat([true_latent, self._randn(true_latent.shape[0], len_add_to_latent, true_latent.shape[-1]).to(self.device)], 1)
-                latents = self.model.inference_codes(codes_input, spk_embeds, true_latent, latent_length, incontext_length,
-                                                     additional_feats=[], guidance_scale=1.5, num_steps=num_steps,
-                                                     disable_progress=disable_progress, scenario="other_seg")
-            latent_list.append(latents)
-        latent_list = [l.float() for l in latent_list]
-        latent_list[0] = latent_list[0][:, first_latent_length:, :]
-        min_samples = int(duration * self.sample_rate)
-        hop_samples = min_samples // 4 * 3
-        ovlp_samples = min_samples - hop_samples
-        output = None
-        for latent in latent_list:
-            cur_output = self.SQCodec.decode(latent.transpose(1, 2)).squeeze(0)
-            cur_output = cur_output[:, 0:min_samples].detach().cpu()  # B, T
-            if output is None:
-                output = cur_output
-            else:
-                ov_win = torch.from_numpy(np.linspace(0, 1, ovlp_samples)[None, :])
-                ov_win = torch.cat([ov_win, 1 - ov_win], -1)
-                output[:, -ovlp_samples:] = output[:, -ovlp_samples:] * ov_win[:, -ovlp_samples:] + cur_output[:, 0:ovlp_samples] * ov_win[:, 0:ovlp_samples]
-                output = torch.cat([output, cur_output[:, ovlp_samples:]], -1)
-        return output[:, 0:target_len]
+        n_out = int(rec_codec.shape[-1] / 12.5 * self.sample_rate)  # samples the caller gets back: the ORIGINAL code length
+        prior = self._randn(rec_codec.shape[0], int(duration * 25), LATENT_DIM).to(self.device)  # drawn before the codes are tiled
+        rec_codec = _make_periodic(rec_codec, w)
+        # ---- latents, window by window; from the second window on the first overlap/2 latent frames continue the previous window
+        carried = w.overlap // 2
+        latents = []
+        for start in range(0, rec_codec.shape[-1] - w.hop, w.hop):
+            n_pinned = 0
+            if latents:
+                tail = latents[-1][:, -carried:, :]
+                n_pinned = tail.shape[1]
+                fresh = self._randn(tail.shape[0], w.latents - n_pinned, tail.shape[-1]).to(self.device)
+                prior = torch.cat([tail, fresh], 1)
+            latents.append(self._solve_window(rec_codec[:, :, start:start + w.codes], prior, n_pinned, w.latents, num_steps, disable_progress))
+        # ---- waveforms, joined on the host
+        joined = None
+        for lat in latents:
+            wave = self.SQCodec.decode(lat.float().transpose(1, 2)).squeeze(0)[:, :w.wave].detach().cpu()
+            joined = wave if joined is None else _cross_fade(joined, wave, w.wave_overlap)
+        return joined[:, :n_out]
 
     def detokenize_no_reason(self, rec_codec, return_reasoning_text, min_duration=30, steps=50, guidance_scale=1.5, disable_progress=False):
-        """rec_codec: (8, T2)"""
+        """rec_codec (8, T2) -> wave (1, samples); 20 s windows (the default of token2audio_no_reason)."""
         return self.token2audio_no_reason(rec_codec.unsqueeze(0), return_reasoning_text=return_reasoning_text, guidance_scale=guidance_scale,
                                           num_steps=steps, disable_progress=disable_progress)
