@@ -8,7 +8,7 @@ convolutions - measured stand-alone through the C ABI on one B200 (CUDA events o
               10 s; FLOP = 2 * B * T_out * Cout * Cin * K; bound = fp32 FMA pipe (148 SMs x 128 lanes x 2 x SM clock) for all but
               the first / last layer, whose intensity is low enough for HBM to bind
 
-    python tools/measure_kernels.py
+    python tools/measure_kernels.py [--conv-tc] [--resblock]     (also time the not-yet-measured options)
 """
 import json
 import os
@@ -77,7 +77,9 @@ def main():
         ("enc down k16 s8 512->1024", 512, 1024, 16, 8, T0 // 120),
         ("enc last k3 1024->512", 1024, 512, 3, 1, T0 // 960),
     ]
-    for name, Cin, Cout, K, stride, T in convs:
+    conv_opts = (0, 1) if "--conv-tc" in sys.argv else (0,)
+    for name, Cin, Cout, K, stride, T, conv_tc in [c + (o,) for c in convs for o in conv_opts]:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", conv_tc))
         x = torch.randn(Bc, Cin, T, device=dev)
         w = torch.randn(Cout, Cin, K, device=dev) / (Cin * K) ** 0.5
         b = torch.zeros(Cout, device=dev)
@@ -91,11 +93,16 @@ def main():
         fl = 2.0 * Bc * T_out * Cout * Cin * K
         by = 4.0 * (x.numel() + yb.numel() + w.numel())
         t_roof = max(by / (hbm * 1e9), fl / (fp32_peak * 1e12)) * 1e3
-        print(json.dumps(dict(kernel="sgemm_conv_kernel (ua2_conv1d_causal_gemm_f32)", layer=name, ms=round(ms, 3), GFLOP=round(fl / 1e9, 1),
+        print(json.dumps(dict(kernel="sgemm_conv_kernel (ua2_conv1d_causal_gemm_f32)", layer=name, conv_tc=conv_tc, ms=round(ms, 3), GFLOP=round(fl / 1e9, 1),
                               TFLOPs=round(fl / ms / 1e9, 1), MB=round(by / 1e6, 1), GBps=round(by / ms / 1e6, 1),
                               flop_per_byte=round(fl / by, 1), bound="hbm" if by / (hbm * 1e9) > fl / (fp32_peak * 1e12) else "fp32",
                               frac_of_roofline=round(t_roof / ms, 3))))
-    for name, Cin, Cout, stride, T in (("dec up k16 s8 1024->512", 1024, 512, 8, T0 // 960), ("dec up k8 s4 128->64", 128, 64, 4, T0 // 4)):
+    _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
+    for name, Cin, Cout, stride, T, conv_tc in [c + (o,) for c in (("dec up k16 s8 1024->512", 1024, 512, 8, T0 // 960),
+                                                                     ("dec up k12 s6 512->256", 512, 256, 6, T0 // 120),
+                                                                     ("dec up k10 s5 256->128", 256, 128, 5, T0 // 20),
+                                                                     ("dec up k8 s4 128->64", 128, 64, 4, T0 // 4)) for o in conv_opts]:
+        _lib.check(L.ua2_set_global_option(b"conv_tc", conv_tc))
         x = torch.randn(Bc, Cin, T, device=dev)
         w = torch.randn(Cin, Cout, 2 * stride, device=dev) / (Cin * 2) ** 0.5
         wp = torch.empty(stride, Cout, Cin, 2, device=dev)
@@ -110,10 +117,31 @@ def main():
         fl = 2.0 * Bc * T * stride * Cout * Cin * 2
         by = 4.0 * (x.numel() + yb.numel() + w.numel())
         t_roof = max(by / (hbm * 1e9), fl / (fp32_peak * 1e12)) * 1e3
-        print(json.dumps(dict(kernel="sgemm_conv_kernel phase GEMMs (ua2_convtr1d_causal_gemm_f32)", layer=name, ms=round(ms, 3),
+        print(json.dumps(dict(kernel="sgemm_conv_kernel phase GEMMs (ua2_convtr1d_causal_gemm_f32)", layer=name, conv_tc=conv_tc, ms=round(ms, 3),
                               GFLOP=round(fl / 1e9, 1), TFLOPs=round(fl / ms / 1e9, 1), GBps=round(by / ms / 1e6, 1),
                               flop_per_byte=round(fl / by, 1), bound="hbm" if by / (hbm * 1e9) > fl / (fp32_peak * 1e12) else "fp32",
                               frac_of_roofline=round(t_roof / ms, 3))))
+    _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
+    if "--resblock" in sys.argv:  # the 64-channel residual block at 24 kHz: two implicit GEMMs vs the fused kernel
+        C, H, T = 64, 32, T0
+        x = torch.randn(Bc, C, T, device=dev)
+        w1 = torch.randn(H, C, 3, device=dev) / (C * 3) ** 0.5
+        w2 = torch.randn(C, H, 1, device=dev) / H ** 0.5
+        b1, b2 = torch.zeros(H, device=dev), torch.zeros(C, device=dev)
+        hid, yb = torch.empty(Bc, H, T, device=dev), torch.empty(Bc, C, T, device=dev)
+
+        def two(i):
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(P(x), P(w1), P(b1), None, P(hid), Bc, C, H, T, 3, 1, 1, 1, 0, None))
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(P(hid), P(w2), P(b2), P(x), P(yb), Bc, H, C, T, 1, 1, 1, 1, 0, None))
+
+        def fused(i):
+            _lib.check(L.ua2_resblock_f32(P(x), P(w1), P(b1), P(w2), P(b2), P(yb), Bc, C, H, T, None))
+
+        fl = 2.0 * Bc * T * (C * H * 3 + H * C)
+        for name, fn in (("two implicit GEMMs", two), ("fused (ua2_resblock_f32)", fused)):
+            ms = timed(fn, 10)
+            print(json.dumps(dict(kernel="SEANet resblock 64 -> 32 -> 64 @ 24 kHz", impl=name, ms=round(ms, 3), GFLOP=round(fl / 1e9, 1),
+                                  TFLOPs=round(fl / ms / 1e9, 1), frac_of_fp32_pipe=round(fl / ms / 1e9 / fp32_peak, 3))))
     print(json.dumps(dict(peaks=dict(hbm_GBps=hbm, fp32_fma_TFLOPs=round(fp32_peak, 1)))))
 
 
