@@ -29,6 +29,46 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 inline std::barrier<>* g_block_barrier = nullptr;
 inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
 
+// ---- warp shuffles: the 32 OS threads of a warp meet at a per-warp barrier around an exchange buffer.  Serves full warps in which
+// every lane executes the shuffle (true for the reductions of csrc/); the mask argument is ignored.
+struct ShimWarp {
+  std::barrier<> bar{32};
+  uint32_t slot[32];
+};
+inline std::vector<std::unique_ptr<ShimWarp>>* g_warps = nullptr;
+inline thread_local int t_linear_tid = 0;
+template <typename T>
+inline T shim_exchange(T v, int src_lane) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  ShimWarp& w = *(*g_warps)[t_linear_tid >> 5];
+  uint32_t bits;
+  std::memcpy(&bits, &v, 4);
+  w.slot[t_linear_tid & 31] = bits;
+  w.bar.arrive_and_wait();
+  bits = w.slot[src_lane & 31];
+  w.bar.arrive_and_wait();
+  T out;
+  std::memcpy(&out, &bits, 4);
+  return out;
+}
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return shim_exchange(v, (t_linear_tid & 31) ^ lane_mask); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int src_lane) { return shim_exchange(v, src_lane); }
+inline void __syncwarp() { (*g_warps)[t_linear_tid >> 5]->bar.arrive_and_wait(); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline float __expf(float x) { return std::exp(x); }
+struct __nv_bfloat16 { uint16_t v; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+inline __nv_bfloat16 shim_f2bf16_rn(float f) {  // round to nearest even (finite inputs)
+  uint32_t u = __float_as_uint(f);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return {(uint16_t)(u >> 16)};
+}
+inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return {shim_f2bf16_rn(a), shim_f2bf16_rn(b)}; }
+
 #define __global__
 #define __device__
 #define __host__
@@ -36,7 +76,7 @@ inline void __syncthreads() { g_block_barrier->arrive_and_wait(); }
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 using std::max;
 using std::min;
 inline float __fadd_rn(float a, float b) { return a + b; }
@@ -66,10 +106,14 @@ inline cudaError_t run_grid(void (*kernel)(KArgs...), dim3 grid, dim3 block, Arg
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         std::barrier<> bar(nthreads);
         g_block_barrier = &bar;
+        std::vector<std::unique_ptr<ShimWarp>> warps;
+        for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) warps.push_back(std::make_unique<ShimWarp>());
+        g_warps = &warps;
         std::vector<std::thread> ts;
         ts.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t)
           ts.emplace_back([=, &bar]() {
+            t_linear_tid = (int)t;
             threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
             blockIdx = dim3(bx, by, bz);
             blockDim = block;

@@ -9,6 +9,14 @@ enum : int { PRO_PLAIN = 0 };
 enum : int { EPI_STORE = 0 };
 inline void pdl_wait() {}
 inline void pdl_launch_dependents() {}
+inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+inline float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = std::fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   bool pdl = false;

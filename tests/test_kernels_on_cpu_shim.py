@@ -88,3 +88,154 @@ def test_resblock_source_on_cpu(shim, B, T):
     assert rc == 0, rc
     assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
     assert shim.shim_resblock(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y), B, 128, 64, T) == 801  # not served: cudaErrorNotSupported
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# kernels that ARE parity-green on the GPU (ua2_stream.cu, ua2_dit.cu): their source also runs on the shim, so that the CPU-only
+# test tier notices regressions in them
+@pytest.fixture(scope="module")
+def shim2(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("shim2"))
+    for name in ("ua2_stream", "ua2_dit"):
+        src = open(os.path.join(CSRC, name + ".cu")).read()
+        src = src[:src.index("\nusing namespace ua2;")]  # kernels + launchers; the handle code behind it needs the CUDA runtime
+        src = re.sub(r"extern __shared__[^;]*;", "", src)
+        src = re.sub(r'#include ["<](\.\./\.\./include/ua2_b200\.h|ua2_kernels\.cuh|ua2_philox\.cuh|cuda_bf16\.h)[">]', "", src)
+        open(os.path.join(d, name + "_kernels.inc"), "w").write(src)
+    so = os.path.join(d, "libshim2.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I", d, "-I", SHIM, "-I", CSRC,
+           os.path.join(SHIM, "harness_stream_dit.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return C.CDLL(so)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("hs,n_splits", [(32, 1), (64, 1), (32, 2)])
+def test_ring_attention_source_on_cpu(shim2, hs, n_splits):
+    """rope_ring_append_kernel + ring_attn_kernel (+ combine): wrapped ring, T = 3 query rows per sequence - the shapes of
+    tests/test_zz_moshi_gpu.py::test_ring_attention_operator, smaller."""
+    from oracle import moshi_oracle as MO
+
+    B, H, cap, T, offset, context = 2, 2, 9, 3, 20, 7
+    Cd = H * hs
+    g = torch.Generator().manual_seed(hs)
+    ring = MO.RingKV(B, H, hs, cap)
+    for t0 in range(0, offset, 4):
+        n = min(4, offset - t0)
+        ring.complete(torch.randn(B, H, n, hs, generator=g), torch.randn(B, H, n, hs, generator=g))
+    kc, vc = ring.cache[0].clone().contiguous(), ring.cache[1].clone().contiguous()
+    qkv = torch.randn(B, T, 3, H, hs, generator=g)
+    q, k, v = qkv.permute(2, 0, 3, 1, 4)
+    off_t = torch.full((1,), offset, dtype=torch.long)
+    qr, kr = MO.apply_rope(q, k, off_t, 10000.0)
+    keys, values, pos_k = ring.complete(kr, v)
+    delta = (off_t + torch.arange(T).view(-1, 1)) - pos_k.view(1, -1)
+    bias = (pos_k.view(1, -1) >= 0) & (delta >= 0) & (delta < context)
+    ref = F.scaled_dot_product_attention(qr, keys, values, bias).permute(0, 2, 1, 3).reshape(B * T, Cd)
+    pos = (offset + torch.arange(B * T) % T).int()
+    bidx = (torch.arange(B * T) // T).int()
+    freqs = MO.rope_freqs(hs, 10000.0).contiguous()
+    qkv_f = qkv.reshape(B * T, 3 * Cd).contiguous()
+    q_out, y = torch.empty(B * T, Cd), torch.full((B * T, Cd), float("nan"))
+    assert shim2.shim_rope_ring_append(_p(qkv_f), 3 * Cd, _p(pos), _p(bidx), _p(freqs), _p(q_out), _p(kc), _p(vc), B * T, H, hs, cap, 1) == 0
+    assert _rel(kc, ring.cache[0]) < 1e-5 and torch.equal(vc, ring.cache[1])
+    part_ml, part_acc = torch.zeros(B * T * H * n_splits * 2), torch.zeros(B * T * H * n_splits * hs)
+    rc = shim2.shim_ring_attn(_p(q_out), _p(kc), _p(vc), _p(pos), _p(bidx), _p(y), B * T, H, hs, cap, C.c_longlong(offset + T), 1, 1, context,
+                              n_splits, _p(part_ml), _p(part_acc))
+    assert rc == 0
+    assert _rel(y, ref) < 1e-4
+
+
+def test_sample_token_source_on_cpu(shim2):
+    from oracle import moshi_oracle as MO
+
+    g = torch.Generator().manual_seed(4)
+    logits = (torch.randn(3, 200, generator=g) * 2.5).contiguous()
+
+    def run(use_sampling, temp, top_k, top_p, end_token, noise):
+        out = torch.full((3,), -1, dtype=torch.int64)
+        rc = shim2.shim_sample_token(_p(logits), 3, 200, use_sampling, C.c_float(temp), top_k, C.c_float(top_p), end_token, _p(noise), _p(out))
+        assert rc == 0
+        return out
+
+    assert torch.equal(run(0, 1.0, 0, 0.0, -1, None), logits.argmax(-1))
+    q = torch.empty(3, 200).exponential_(1, generator=g)
+    assert torch.equal(run(1, 0.8, 0, 0.0, -1, q), MO.sample_token(logits, True, 0.8, q=q))
+    qk = torch.empty(3, 17).exponential_(1, generator=g)
+    assert torch.equal(run(1, 0.9, 17, 0.0, -1, qk), MO.sample_token(logits, True, 0.9, top_k=17, q=qk))
+    assert torch.equal(run(1, 1.1, 0, 0.7, -1, q), MO.sample_token(logits, True, 1.1, top_p=0.7, q=q))
+    assert torch.equal(run(1, 0.9, 17, 0.0, 120, qk), MO.sample_token(logits, True, 0.9, top_k=17, q=qk, end_token=120))
+    tied = torch.randint(0, 3, (3, 200), generator=g).float().contiguous()  # ties at the threshold: any of the k largest is valid
+    out = torch.full((3,), -1, dtype=torch.int64)
+    assert shim2.shim_sample_token(_p(tied), 3, 200, 1, C.c_float(1.0), 9, C.c_float(0.0), -1, _p(qk[:, :9].contiguous()), _p(out)) == 0
+    assert bool((tied.gather(1, out[:, None])[:, 0] >= torch.topk(tied, 9).values[:, -1]).all())
+
+
+@pytest.mark.parametrize("hs,T,B", [(32, 45, 2), (64, 33, 1), (128, 20, 1)])
+def test_dit_attention_source_on_cpu(shim2, hs, T, B):
+    H = 2
+    g = torch.Generator().manual_seed(T)
+    q = torch.randn(B, T, H, hs, generator=g)
+    k = torch.randn(B, H, T, hs, generator=g).contiguous()
+    v = torch.randn(B, H, T, hs, generator=g).contiguous()
+    ref = F.scaled_dot_product_attention(q.permute(0, 2, 1, 3), k, v).permute(0, 2, 1, 3).reshape(B * T, H * hs)
+    out = torch.full((B * T, H * hs), float("nan"))
+    assert shim2.shim_dit_attn(_p(q.reshape(B * T, H * hs).contiguous()), _p(k), _p(v), _p(out), B, T, H, hs) == 0
+    assert _rel(out, ref) < 1e-5
+
+
+def test_dit_glue_sources_on_cpu(shim2):
+    """LayerNorm + adaLN modulation, the k = 3 im2col, bias / gate / GELU / head-split epilogues and the Euler glue."""
+    g = torch.Generator().manual_seed(8)
+    B, T, D, H, hs = 2, 7, 64, 2, 32
+    M = B * T
+    x = torch.randn(M, D, generator=g)
+    table = torch.randn(6, D, generator=g)
+    t6 = torch.randn(B, 6 * D, generator=g)
+    out = torch.empty(M, D)
+    assert shim2.shim_dit_ln_mod(_p(x), _p(out), _p(table), _p(t6), 6 * D, D, 3, 4, C.c_float(1e-6), M, T, D) == 0
+    mod = table[None] + t6.reshape(B, 6, D)
+    ref = F.layer_norm(x.view(B, T, D), (D,), None, None, 1e-6) * (1 + mod[:, 4:5]) + mod[:, 3:4]
+    assert _rel(out.view(B, T, D), ref) < 1e-5
+    # im2col of the k = 3 'same' convolution
+    Cc = 5
+    xi = torch.randn(B, T, Cc, generator=g).contiguous()
+    col = torch.empty(M, 3 * Cc)
+    assert shim2.shim_dit_im2col3(_p(xi), _p(col), B, T, Cc) == 0
+    w = torch.randn(4, Cc, 3, generator=g)
+    ref = F.conv1d(xi.transpose(1, 2), w, None, padding=1).transpose(1, 2).reshape(M, 4)
+    # column k * C + c of the im2col matrix multiplies w[:, c, k]  (dit_repack_conv3_kernel)
+    assert _rel(col @ w.permute(0, 2, 1).reshape(4, 3 * Cc).t(), ref) < 1e-5
+    # gate * (y + bias) + residual
+    src, bias, res = torch.randn(M, D, generator=g), torch.randn(D, generator=g), torch.randn(M, D, generator=g)
+    res0 = res.clone()
+    assert shim2.shim_dit_gate_res(_p(src), _p(bias), _p(res), _p(table), _p(t6), 2, M, D, T) == 0
+    assert _rel(res.view(B, T, D), mod[:, 2:3] * (src + bias).view(B, T, D) + res0.view(B, T, D)) < 1e-6
+    # q / k / v split with biases, K and V in (B, H, T, hs)
+    raw, b3 = torch.randn(M, 3 * D, generator=g), torch.randn(3 * D, generator=g)
+    qo, ko, vo = torch.empty(M, D), torch.empty(B, H, T, hs), torch.empty(B, H, T, hs)
+    assert shim2.shim_dit_qkv_split(_p(raw), _p(b3), _p(qo), _p(ko), _p(vo), M, D, T, H, hs) == 0
+    full = (raw + b3).view(B, T, 3, H, hs)
+    assert torch.equal(qo, full[:, :, 0].reshape(M, D)) and torch.equal(ko, full[:, :, 1].permute(0, 2, 1, 3)) and torch.equal(vo, full[:, :, 2].permute(0, 2, 1, 3))
+    # GELU (tanh form)
+    yg = torch.empty(M, D)
+    assert shim2.shim_dit_bias_gelu(_p(src), _p(bias), _p(yg), M, D) == 0
+    assert _rel(yg, F.gelu(src + bias, approximate="tanh")) < 1e-6
+    # Euler glue: in-context blend + CFG batch assembly, then guidance mix + update
+    lat, cond, ic, tt = 6, 4, 3, 0.3
+    xs, noise, inc, mu = (torch.randn(T, n, generator=g) for n in (lat, lat, lat, cond))
+    xs0 = xs.clone()
+    inp = torch.empty(2, T, 2 * lat + cond)
+    assert shim2.shim_dit_euler(_p(xs), _p(noise), _p(inc), _p(mu), _p(inp), None, T, lat, cond, ic, C.c_float(tt), C.c_float(0.9999), C.c_float(0), C.c_float(0), 0) == 0
+    xb = xs0.clone()
+    xb[:ic] = (1 - torch.tensor(0.9999) * tt) * noise[:ic] + tt * inc[:ic]
+    assert torch.allclose(xs, xb, atol=1e-6)
+    assert torch.allclose(inp[0], torch.cat([xb, inc, torch.zeros(T, cond)], 1), atol=1e-6) and torch.allclose(inp[1], torch.cat([xb, inc, mu], 1), atol=1e-6)
+    d = torch.randn(2, T, lat, generator=g).contiguous()
+    x1 = xs.clone()
+    assert shim2.shim_dit_euler(_p(x1), None, None, None, None, _p(d), T, lat, cond, ic, C.c_float(0), C.c_float(0), C.c_float(1.5), C.c_float(0.25), 1) == 0
+    assert torch.allclose(x1, xs + 0.25 * (d[0] + 1.5 * (d[1] - d[0])), atol=1e-6)
