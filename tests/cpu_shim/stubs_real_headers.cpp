@@ -1,0 +1,50 @@
+// TEST INFRASTRUCTURE ONLY: the launchers that the shim cannot run (bulk-copy GEMV family, tcgen05 GEMM) replaced by a CPU GEMM, plus
+// the error plumbing of ua2_llm.cu, for building csrc/ua2_codec.cu + ua2_sgemm.cu + ua2_convtc.cu + ua2_resblock.cu with -DUA2_CPU_SHIM.
+#include "../../include/ua2_b200.h"
+#include "ua2_kernels.cuh"
+
+namespace ua2 {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+struct TcWeightCache {};
+TcWeightCache* tc_cache_create() { return nullptr; }
+void tc_cache_destroy(TcWeightCache*) {}
+bool tc_gemm_available() { return true; }
+int get_tc_gemm() { return 1; }
+int get_tc_min_rows() { return 32; }
+static void cpu_gemm(const GemvParams& p, float* C, int ldc) {
+  for (int m = 0; m < p.M; ++m)
+    for (int n = 0; n < p.N; ++n) {
+      double acc = 0.0;
+      for (int k = 0; k < p.K; ++k) acc += (double)p.X[(size_t)m * p.ldx + k] * p.W[(size_t)n * p.K + k];
+      C[(size_t)m * ldc + n] = (float)acc;
+    }
+}
+cudaError_t launch_tc_linear(const LaunchCtx&, int pro, int epi, const GemvParams& p) {
+  if (pro != PRO_PLAIN || epi != EPI_STORE || p.tc == nullptr || (size_t)p.M * p.N > p.tc->c_floats) return cudaErrorNotSupported;
+  cpu_gemm(p, p.tc->c, p.N);
+  if (p.raw_out) {
+    *p.raw_out = p.tc->c;
+  } else {
+    for (int m = 0; m < p.M; ++m) std::memcpy(p.Y + (size_t)m * p.ldy, p.tc->c + (size_t)m * p.N, sizeof(float) * p.N);
+  }
+  return cudaSuccess;
+}
+cudaError_t launch_gemv(const LaunchCtx&, int pro, int epi, const GemvParams& p) {
+  if (pro != PRO_PLAIN || epi != EPI_STORE) return cudaErrorNotSupported;
+  cpu_gemm(p, p.Y, p.ldy);
+  return cudaSuccess;
+}
+}  // namespace ua2
+
+extern "C" {
+const char* ua2_last_error(void) { return ua2::g_err.c_str(); }
+void shim_set_conv_tc(int v) { ua2::set_conv_tc(v); }  // ua2_set_global_option("conv_tc") lives in ua2_ops.cu, outside this build
+int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float, const float* residual, float* y, int M, int N, int K, void*) {
+  if (norm_w || residual) return UA2_ERR_INVALID;
+  ua2::GemvParams p;
+  p.W = W; p.N = N; p.K = K; p.M = M; p.X = x; p.ldx = K; p.Y = y; p.ldy = N;
+  ua2::cpu_gemm(p, y, N);
+  return UA2_OK;
+}
+}

@@ -239,3 +239,213 @@ def test_dit_glue_sources_on_cpu(shim2):
     x1 = xs.clone()
     assert shim2.shim_dit_euler(_p(x1), None, None, None, None, _p(d), T, lat, cond, ic, C.c_float(0), C.c_float(0), C.c_float(1.5), C.c_float(0.25), 1) == 0
     assert torch.allclose(x1, xs + 0.25 * (d[0] + 1.5 * (d[1] - d[0])), atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# whole translation units with the REAL headers: csrc/ua2_codec.cu + ua2_sgemm.cu (+ ua2_convtc.cu, ua2_resblock.cu) build with
+# -DUA2_CPU_SHIM (csrc/ua2_common.cuh swaps its three PTX helpers and `launch` for shim versions) and export their C-ABI
+# operators unchanged - the operator tests of tests/test_codec_gpu.py, at small shapes, on the CPU
+@pytest.fixture(scope="module")
+def shim3(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("shim3"))
+    srcs = []
+    hdr = os.path.join(ROOT, "include", "ua2_b200.h")
+    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock"):
+        src = open(os.path.join(CSRC, name + ".cu")).read()
+        src = re.sub(r"extern __shared__([^;\[]*?)(\w+)\[\];", r"static\1\2[1 << 16];", src)  # dynamic shared memory -> a static array
+        src = src.replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
+        open(os.path.join(d, name + ".cpp"), "w").write(src)
+        srcs.append(os.path.join(d, name + ".cpp"))
+    stub = open(os.path.join(SHIM, "stubs_real_headers.cpp")).read().replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
+    open(os.path.join(d, "stubs.cpp"), "w").write(stub)
+    so = os.path.join(d, "libshim3.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-DUA2_CPU_SHIM", "-I", CSRC, "-I", os.path.join(SHIM, "rt"),
+           "-Wl,--no-undefined"] + srcs + [os.path.join(d, "stubs.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    lib = C.CDLL(so)
+    lib.ua2_last_error.restype = C.c_char_p
+    return lib
+
+
+def _ok(lib, rc):
+    assert rc == 0, lib.ua2_last_error()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,K,stride,dil,elu,res,rep", [
+    (1, 1, 64, 200, 7, 1, 1, 0, 0, 0), (1, 64, 32, 150, 3, 1, 1, 1, 0, 0), (1, 32, 64, 150, 1, 1, 1, 1, 1, 0), (2, 64, 128, 203, 8, 4, 1, 1, 0, 0),
+    (1, 96, 200, 133, 12, 6, 1, 1, 0, 0), (2, 128, 128, 57, 4, 2, 1, 0, 0, 1), (1, 16, 24, 100, 3, 1, 2, 1, 0, 0), (1, 64, 1, 199, 3, 1, 1, 1, 0, 0)])
+def test_conv1d_operators_on_cpu(shim3, B, Cin, Cout, T, K, stride, dil, elu, res, rep):
+    """ua2_conv1d_causal_f32 (direct kernel) and ua2_conv1d_causal_gemm_f32 (implicit GEMM) - tests/test_codec_gpu.py::test_conv1d_causal."""
+    g = torch.Generator().manual_seed(Cin + Cout + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = None if rep else torch.randn(Cout, generator=g) * 0.1
+    ref = CO.conv1d_causal(F.elu(x) if elu else x, w, b, stride=stride, dilation=dil, pad_mode="replicate" if rep else "constant")
+    r = torch.randn_like(ref) if res else None
+    if res:
+        ref = r + ref
+    tol = 2e-5 * max(1.0, float(ref.abs().max()))
+    y, wd = torch.full_like(ref, float("nan")), w.permute(1, 2, 0).contiguous()
+    _ok(shim3, shim3.ua2_conv1d_causal_f32(_p(x), _p(wd), _p(b), _p(r), _p(y), B, Cin, Cout, T, K, stride, dil, elu, rep, None))
+    assert float((y - ref).abs().max()) < tol
+    y2 = torch.full_like(ref, float("nan"))
+    _ok(shim3, shim3.ua2_conv1d_causal_gemm_f32(_p(x), _p(w), _p(b), _p(r), _p(y2), B, Cin, Cout, T, K, stride, dil, elu, rep, None))
+    assert float((y2 - ref).abs().max()) < tol
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,stride", [(1, 128, 64, 30, 8), (2, 96, 40, 77, 6), (1, 48, 20, 65, 3), (1, 32, 32, 40, 2)])
+def test_convtr1d_operators_on_cpu(shim3, B, Cin, Cout, T, stride):
+    g = torch.Generator().manual_seed(Cin + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, 2 * stride, generator=g) / math.sqrt(Cin * 2)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = CO.convtr1d_causal(F.elu(x), w, b, stride)
+    tol = 2e-5 * max(1.0, float(ref.abs().max()))
+    y, wd = torch.full_like(ref, float("nan")), w.permute(0, 2, 1).contiguous()
+    _ok(shim3, shim3.ua2_convtr1d_causal_f32(_p(x), _p(wd), _p(b), _p(y), B, Cin, Cout, T, stride, 1, None))
+    assert float((y - ref).abs().max()) < tol
+    wp = torch.empty(stride * Cout * Cin * 2)
+    _ok(shim3, shim3.ua2_convtr1d_repack_phase_f32(_p(w), _p(wp), Cin, Cout, stride, None))
+    y2 = torch.full_like(ref, float("nan"))
+    _ok(shim3, shim3.ua2_convtr1d_causal_gemm_f32(_p(x), _p(wp), _p(b), _p(y2), B, Cin, Cout, T, stride, 1, None))
+    assert float((y2 - ref).abs().max()) < tol
+
+
+def test_depthwise_film_interp_elementwise_on_cpu(shim3):
+    g = torch.Generator().manual_seed(3)
+    B, Cc, T, s = 2, 64, 37, 2
+    x = torch.randn(B, Cc, T, generator=g)
+    w = torch.randn(Cc, 1, 2 * s, generator=g)
+    y = torch.empty(B, Cc, T * s)
+    _ok(shim3, shim3.ua2_convtr1d_depthwise_f32(_p(x), _p(w), _p(y), B, Cc, T, s, None))
+    assert float((y - CO.convtr1d_causal(x, w, None, s, groups=Cc)).abs().max()) < 1e-6
+    from oracle import film_oracle as FO
+
+    params, feat = torch.randn(3, 11, 2 * 24, generator=g), torch.randn(3, 11, 24, generator=g)
+    mask = torch.tensor([0, 1, 0], dtype=torch.uint8)
+    out = torch.empty(3, 11, 24)
+    _ok(shim3, shim3.ua2_film_f32(_p(params), _p(feat), _p(mask), _p(out), 3, 11, 24, C.c_float(0.1), None))
+    assert float((out - FO.time_film(params, feat, mask, 0.1)).abs().max()) < 1e-6
+    r = torch.randn(2, 12, 30, generator=g)
+    ref_i = F.interpolate(r, scale_factor=2.5, mode="nearest")
+    yi = torch.empty_like(ref_i)
+    _ok(shim3, shim3.ua2_interp_nearest_f32(_p(r), _p(yi), 2, 12, 30, ref_i.shape[-1], C.c_float(2.5), None))
+    assert torch.equal(yi, ref_i)
+    z = torch.randn(1000, generator=g)
+    yz = torch.empty_like(z)
+    _ok(shim3, shim3.ua2_elementwise_f32(_p(z), _p(yz), C.c_longlong(1000), 0, C.c_float(9.0), None))
+    assert torch.equal(yz, torch.round(9 * z) / 9)  # round_func9, scalar24k.py:279-288
+
+
+@pytest.mark.parametrize("B,D,T,K,n_q", [(2, 32, 21, 64, 4), (1, 64, 33, 300, 3)])
+def test_rvq_operators_on_cpu(shim3, B, D, T, K, n_q):
+    """ua2_rvq_encode_f32 / ua2_rvq_encode_gemm_f32 / ua2_rvq_decode_f32 - tests/test_codec_gpu.py::test_rvq_encode_decode."""
+    g = torch.Generator().manual_seed(D + K)
+    x = torch.randn(B, D, T, generator=g)
+    emb = torch.randn(n_q, K, D, generator=g)
+    residual, ref_codes = x.clone(), []
+    for q in range(n_q):
+        flat = residual.transpose(1, 2).reshape(-1, D)
+        codes = torch.cdist(flat[None], emb[q][None], p=2)[0].argmin(-1).view(B, T)
+        residual = residual - F.embedding(codes, emb[q]).transpose(1, 2)
+        ref_codes.append(codes)
+    ref_codes = torch.stack(ref_codes, 1)
+    sq = (emb * emb).sum(-1).contiguous()
+    codes = torch.full((B, n_q + 2, T), -1, dtype=torch.int64)
+    _ok(shim3, shim3.ua2_rvq_encode_f32(_p(x), _p(emb), _p(sq), _p(codes), B, D, T, K, n_q, n_q + 2, 1, None))
+    assert torch.equal(codes[:, 1:1 + n_q], ref_codes)
+    assert int(codes[:, 0].max()) == -1 and int(codes[:, -1].max()) == -1
+    r_md = x.transpose(1, 2).reshape(B * T, D).contiguous()
+    S = torch.empty(B * T, K)
+    codes2 = torch.full((B, n_q + 2, T), -1, dtype=torch.int64)
+    _ok(shim3, shim3.ua2_rvq_encode_gemm_f32(_p(r_md), _p(emb), _p(sq), _p(S), _p(codes2), B, D, T, K, n_q, n_q + 2, 1, None))
+    assert torch.equal(codes2[:, 1:1 + n_q], ref_codes)
+    out = torch.empty(B, D, T)
+    _ok(shim3, shim3.ua2_rvq_decode_f32(_p(codes), _p(emb), _p(out), B, D, T, K, n_q, n_q + 2, 1, None))
+    ref = sum(F.embedding(ref_codes[:, q], emb[q]).transpose(1, 2) for q in range(n_q))
+    assert float((out - ref).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,K,stride,dil,pl,pr", [(2, 96, 96, 120, 4, 4, 1, 0, 0), (1, 64, 64, 90, 2, 2, 1, 0, 0), (1, 48, 48, 199, 7, 1, 9, 27, 27),
+                                                             (1, 136, 200, 50, 5, 1, 1, 2, 2)])
+def test_general_conv1d_operator_on_cpu(shim3, B, Cin, Cout, T, K, stride, dil, pl, pr):
+    """ua2_conv1d_f32: the nn.Conv1d forms of the ScalarModel decoder with bias + PReLU + residual fused (tests/test_scalar_gpu.py)."""
+    g = torch.Generator().manual_seed(K + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    slope = torch.tensor([0.2])
+    ref = F.prelu(F.conv1d(F.pad(x, (pl, pr)), w, b, stride=stride, dilation=dil), slope)
+    use_res = Cin == Cout and stride == 1 and ref.shape[-1] == T
+    if use_res:
+        ref = ref + x
+    y = torch.full_like(ref, float("nan"))
+    _ok(shim3, shim3.ua2_conv1d_f32(_p(x), _p(w), _p(b), _p(slope), _p(x) if use_res else None, _p(y), B, Cin, Cout, T, K, stride, dil, pl, pr, None))
+    assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,stride,crop", [(1, 96, 48, 40, 5, 2), (2, 64, 32, 33, 4, 0), (1, 48, 24, 50, 2, 1)])
+def test_general_convtr1d_operator_on_cpu(shim3, B, Cin, Cout, T, stride, crop):
+    """ua2_convtr1d_f32: nn.ConvTranspose1d (kernel 2 * stride) + PReLU, cropped to [crop, crop + T * stride) - ScalarModel upsamplers."""
+    g = torch.Generator().manual_seed(Cin + stride)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, 2 * stride, generator=g) / (2 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    slope = torch.tensor([0.3])
+    T_out = T * stride
+    ref = F.prelu(F.conv_transpose1d(x, w, b, stride=stride), slope)[..., crop:crop + T_out]
+    wp = torch.empty(stride * Cout * Cin * 2)
+    _ok(shim3, shim3.ua2_convtr1d_repack_phase_f32(_p(w), _p(wp), Cin, Cout, stride, None))
+    y = torch.full_like(ref, float("nan"))
+    _ok(shim3, shim3.ua2_convtr1d_f32(_p(x), _p(wp), _p(b), _p(slope), _p(y), B, Cin, Cout, T, stride, crop, T_out, None))
+    assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    assert shim3.ua2_convtr1d_f32(_p(x), _p(wp), _p(b), _p(slope), _p(y), B, Cin, Cout, T, stride, stride + 1, T_out, None) != 0  # window too far right
+
+
+@pytest.mark.parametrize("B,T", [(2, 300), (1, 128), (1, 77)])
+def test_resblock_operator_on_cpu(shim3, B, T):
+    """ua2_resblock_f32 through its C-ABI entry (argument checks included): y = x + conv_k1(ELU(conv_k3(ELU(x)))), modules/seanet.py:21-94."""
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(B, 64, T, generator=g)
+    w1, b1 = torch.randn(32, 64, 3, generator=g) / 14, torch.randn(32, generator=g) * 0.1
+    w2, b2 = torch.randn(64, 32, 1, generator=g) / 6, torch.randn(64, generator=g) * 0.1
+    ref = x + CO.conv1d_causal(F.elu(CO.conv1d_causal(F.elu(x), w1, b1)), w2, b2)
+    y = torch.full_like(ref, float("nan"))
+    _ok(shim3, shim3.ua2_resblock_f32(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y), B, 64, 32, T, None))
+    assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    assert shim3.ua2_resblock_f32(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(x), B, 64, 32, T, None) != 0    # aliasing refused
+    assert shim3.ua2_resblock_f32(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y), B, 32, 16, T, None) != 0    # other widths refused
+
+
+def test_conv_tc_dispatch_through_real_launchers_on_cpu(shim3):
+    """Option "conv_tc": the C-ABI conv operators route wide layers through launch_conv1d_tc / launch_convtr1d_tc (host code of
+    csrc/ua2_convtc.cu: scratch growth, chunking, raw-product epilogue) - here with the tensor-core GEMM replaced by a CPU GEMM
+    (stubs_real_headers.cpp), so everything but the tcgen05 kernel itself is the shipped source.  Narrow layers must fall through."""
+    g = torch.Generator().manual_seed(11)
+    shim3.shim_set_conv_tc(1)
+    try:
+        for (B, Cin, Cout, T, K, stride, elu, res, rep) in [(2, 160, 24, 150, 8, 4, 1, 0, 0), (1, 352, 16, 140, 3, 1, 1, 1, 0), (1, 300, 8, 260, 4, 2, 0, 0, 1),
+                                                            (1, 32, 16, 200, 3, 1, 1, 0, 0)]:  # the last one (Cin * K < 1024) stays on the SIMT path
+            x = torch.randn(B, Cin, T, generator=g)
+            w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+            b = None if rep else torch.randn(Cout, generator=g) * 0.1
+            ref = CO.conv1d_causal(F.elu(x) if elu else x, w, b, stride=stride, pad_mode="replicate" if rep else "constant")
+            r = torch.randn_like(ref) if res else None
+            if res:
+                ref = r + ref
+            y = torch.full_like(ref, float("nan"))
+            _ok(shim3, shim3.ua2_conv1d_causal_gemm_f32(_p(x), _p(w), _p(b), _p(r), _p(y), B, Cin, Cout, T, K, stride, 1, elu, rep, None))
+            assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max())), (Cin, K)
+        for (B, Cin, Cout, T, stride) in [(2, 160, 12, 70, 4), (1, 128, 8, 131, 8), (1, 64, 8, 150, 2)]:  # the last one (2 * Cin < 256) falls through
+            x = torch.randn(B, Cin, T, generator=g)
+            w = torch.randn(Cin, Cout, 2 * stride, generator=g) / math.sqrt(Cin * 2)
+            b = torch.randn(Cout, generator=g) * 0.1
+            ref = CO.convtr1d_causal(F.elu(x), w, b, stride)
+            wp = torch.empty(stride * Cout * Cin * 2)
+            _ok(shim3, shim3.ua2_convtr1d_repack_phase_f32(_p(w), _p(wp), Cin, Cout, stride, None))
+            y = torch.full_like(ref, float("nan"))
+            _ok(shim3, shim3.ua2_convtr1d_causal_gemm_f32(_p(x), _p(wp), _p(b), _p(y), B, Cin, Cout, T, stride, 1, None))
+            assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max())), (Cin, stride)
+    finally:
+        shim3.shim_set_conv_tc(0)

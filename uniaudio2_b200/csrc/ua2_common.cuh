@@ -29,6 +29,7 @@ void set_error(const std::string& msg);
 // ---- device helpers ----
 // Streaming 128-bit load for weights: read-only path, do not allocate in L1 (weights are touched once per
 // launch; activations staged in shared memory keep L1/smem for themselves).
+#ifndef UA2_CPU_SHIM
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -36,6 +37,9 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
                : "l"(p));
   return r;
 }
+#else  // tests/cpu_shim: the kernels of this file set compile with g++ and run one OS thread per CUDA thread
+__device__ __forceinline__ float4 ldg_stream(const float* p) { return *reinterpret_cast<const float4*>(p); }
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -50,8 +54,13 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // Programmatic dependent launch (PDL): wait for the producer grid's memory to be visible / let the
 // dependent grid start its prologue early.  No-ops when the launch carries no PDL attribute.
+#ifndef UA2_CPU_SHIM
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#endif
 
 // Per-launch context shared by the host-side launchers.
 struct GemvSeq;
@@ -64,6 +73,17 @@ struct LaunchCtx {
 
 // Every kernel of the path asks for the maximum shared-memory carveout, so consecutive (and, under PDL,
 // co-resident) kernels never force an L1/shared reconfiguration of the SM between launches.
+#ifdef UA2_CPU_SHIM
+template <typename K>
+inline cudaError_t prefer_max_smem(K) {
+  return cudaSuccess;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, Args... args) {
+  if (lc.launch_counter) ++*lc.launch_counter;
+  return shim::run_grid(kernel, grid, block, args...);
+}
+#else
 template <typename K>
 inline cudaError_t prefer_max_smem(K kern) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
@@ -89,5 +109,6 @@ inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 gr
   if (lc.launch_counter) ++*lc.launch_counter;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+#endif
 
 }  // namespace ua2
