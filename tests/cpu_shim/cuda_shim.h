@@ -100,6 +100,11 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return c
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "ok" : "shim error"; }
 
 namespace shim {
+// dynamic shared memory of the running block when the launcher states its size (run_grid_smem): an exactly-sized heap block, so an
+// address sanitizer sees overruns, refilled with 0xFF bytes (NaN as float) before every block since its contents are undefined
+inline void* g_dyn_smem = nullptr;
+inline size_t g_dyn_smem_bytes = 0;
+
 // run `kernel(args...)` for every thread of every block of the grid
 template <typename... KArgs, typename... Args>
 inline cudaError_t run_grid(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
@@ -107,6 +112,7 @@ inline cudaError_t run_grid(void (*kernel)(KArgs...), dim3 grid, dim3 block, Arg
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
+        if (g_dyn_smem) std::memset(g_dyn_smem, 0xFF, g_dyn_smem_bytes);
         std::barrier<> bar(nthreads);
         g_block_barrier = &bar;
         std::vector<std::unique_ptr<ShimWarp>> warps;
@@ -127,5 +133,19 @@ inline cudaError_t run_grid(void (*kernel)(KArgs...), dim3 grid, dim3 block, Arg
         for (auto& th : ts) th.join();
       }
   return cudaSuccess;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t run_grid_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+  if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;  // the sm_100a opt-in limit per CTA
+  void* buf = nullptr;
+  if (smem_bytes && posix_memalign(&buf, 128, smem_bytes) != 0) return 2;
+  g_dyn_smem = buf;
+  g_dyn_smem_bytes = smem_bytes;
+  const cudaError_t e = run_grid(kernel, grid, block, args...);
+  g_dyn_smem = nullptr;
+  g_dyn_smem_bytes = 0;
+  std::free(buf);
+  return e;
 }
 }  // namespace shim

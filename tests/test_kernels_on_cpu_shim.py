@@ -18,6 +18,11 @@ from oracle import codec_oracle as CO
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = os.path.join(ROOT, "tests", "cpu_shim")
 CSRC = os.path.join(ROOT, "uniaudio2_b200", "csrc")
+# UA2_SHIM_ASAN=1: build the harnesses with the address sanitizer (run pytest under LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+# ASAN_OPTIONS=detect_leaks=0): global-memory overruns of the kernels land in the red zones of the torch CPU allocations, shared-
+# memory overruns in those of the static arrays / of the exactly-sized dynamic block.  tools/shim_asan.sh is the whole command.
+GXX = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread"] + (["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
+                                                                        if os.environ.get("UA2_SHIM_ASAN") == "1" else [])
 
 
 @pytest.fixture(scope="module")
@@ -30,7 +35,7 @@ def shim(tmp_path_factory):
         src = re.sub(r'#include "ua2_kernels.cuh"', "", src)
         open(os.path.join(d, name + "_shim.inc"), "w").write(src)
     so = os.path.join(d, "libshim.so")
-    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I", d, "-I", SHIM, os.path.join(SHIM, "harness.cpp"), "-o", so]
+    cmd = GXX + [ "-I", d, "-I", SHIM, os.path.join(SHIM, "harness.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)
@@ -103,7 +108,7 @@ def shim2(tmp_path_factory):
         src = re.sub(r'#include ["<](\.\./\.\./include/ua2_b200\.h|ua2_kernels\.cuh|ua2_philox\.cuh|cuda_bf16\.h)[">]', "", src)
         open(os.path.join(d, name + "_kernels.inc"), "w").write(src)
     so = os.path.join(d, "libshim2.so")
-    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I", d, "-I", SHIM, "-I", CSRC,
+    cmd = GXX + [ "-I", d, "-I", SHIM, "-I", CSRC,
            os.path.join(SHIM, "harness_stream_dit.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
@@ -252,14 +257,16 @@ def shim3(tmp_path_factory):
     hdr = os.path.join(ROOT, "include", "ua2_b200.h")
     for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock"):
         src = open(os.path.join(CSRC, name + ".cu")).read()
-        src = re.sub(r"extern __shared__([^;\[]*?)(\w+)\[\];", r"static\1\2[1 << 16];", src)  # dynamic shared memory -> a static array
+        # dynamic shared memory -> the exactly-sized block that the shim's launch() allocates from the launcher's byte count
+        src = re.sub(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(shim::g_dyn_smem);", src)
+        assert "extern __shared__" not in src
         src = src.replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
         open(os.path.join(d, name + ".cpp"), "w").write(src)
         srcs.append(os.path.join(d, name + ".cpp"))
     stub = open(os.path.join(SHIM, "stubs_real_headers.cpp")).read().replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
     open(os.path.join(d, "stubs.cpp"), "w").write(stub)
     so = os.path.join(d, "libshim3.so")
-    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-DUA2_CPU_SHIM", "-I", CSRC, "-I", os.path.join(SHIM, "rt"),
+    cmd = GXX + [ "-DUA2_CPU_SHIM", "-I", CSRC, "-I", os.path.join(SHIM, "rt"),
            "-Wl,--no-undefined"] + srcs + [os.path.join(d, "stubs.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]

@@ -79,9 +79,9 @@ inline cudaError_t prefer_max_smem(K) {
   return cudaSuccess;
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, Args... args) {
+inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
   if (lc.launch_counter) ++*lc.launch_counter;
-  return shim::run_grid(kernel, grid, block, args...);
+  return shim::run_grid_smem(kernel, grid, block, smem, args...);
 }
 #else
 template <typename K>
