@@ -44,6 +44,9 @@ const char* ua2_version(void);
  * tf32-split copy of every weight the tensor-core path has used, 12 B per parameter, instead of re-splitting per call -
  * for batched decode frames, e.g. tc_min_rows = 16 with batch 32),
  * "resblock_fused" (0/1, default 0: the 64-channel SEANet residual blocks of the codec handle run as one kernel, csrc/ua2_resblock.cu),
+ * "attn_ring" (0/1, default 0: KV-cache attention launches with >= 592 (row, group, 64-key split) items run on persistent CTAs that
+ * stream the K / V chunks through a 3-slot bulk-copy ring instead of one fetch-compute-exit CTA per item - csrc/ua2_attn.cu; same
+ * partial-result layout and arithmetic; written at the end of round 1 and not yet measured),
  * "conv_tc" (0/1, default 0: causal convolutions with Cin * K >= 1024 and transposed convolutions with Cin >= 128 run as im2col +
  * tcgen05 3xTF32 GEMM instead of the fp32 register-tiled core - csrc/ua2_convtc.cu; written at the end of round 1 and not yet measured),
  * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with

@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -96,19 +98,62 @@ inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 enum { cudaDevAttrMultiProcessorCount = 16 };
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+inline int g_shim_sm_count = 148;  // tests shrink it so that persistent kernels walk many work items per CTA
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = g_shim_sm_count; return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "ok" : "shim error"; }
 
 namespace shim {
 // dynamic shared memory of the running block when the launcher states its size (run_grid_smem): an exactly-sized heap block, so an
 // address sanitizer sees overruns, refilled with 0xFF bytes (NaN as float) before every block since its contents are undefined
+inline dim3 g_last_grid;  // grid of the most recent launch (tests check which kernel variant a launcher chose)
 inline void* g_dyn_smem = nullptr;
 inline size_t g_dyn_smem_bytes = 0;
+
+// ---- mbarrier / bulk-copy emulation (csrc/ua2_common.cuh wrappers).  State per barrier word, guarded by one mutex: the shim has
+// no asynchronous copy engine - bulk_copy() is a checked memcpy done by the issuing thread, and its complete_tx follows at once.
+struct MbarState { uint32_t phase = 0, count = 1, pending = 1; int64_t tx = 0; };
+inline std::mutex g_mbar_mu;
+inline std::map<const void*, MbarState> g_mbar;
+inline void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  std::lock_guard<std::mutex> l(g_mbar_mu);
+  g_mbar[bar] = MbarState{0, arrivals, arrivals, 0};
+}
+inline void mbar_update(uint64_t* bar, uint32_t arrive, int64_t tx_delta) {
+  std::lock_guard<std::mutex> l(g_mbar_mu);
+  auto it = g_mbar.find(bar);
+  if (it == g_mbar.end()) { std::fprintf(stderr, "shim: mbarrier used before mbarrier.init\n"); std::abort(); }
+  MbarState& b = it->second;
+  b.tx += tx_delta;
+  if (arrive > b.pending) { std::fprintf(stderr, "shim: more arrivals than the mbarrier expects\n"); std::abort(); }
+  b.pending -= arrive;
+  if (b.pending == 0 && b.tx == 0) {  // phase completes
+    b.phase ^= 1u;
+    b.pending = b.count;
+  }
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> l(g_mbar_mu);
+      auto it = g_mbar.find(bar);
+      if (it != g_mbar.end() && it->second.phase != (parity & 1u)) return;  // the phase with this parity has completed
+    }
+    std::this_thread::yield();
+  }
+}
+inline void bulk_copy(void* dst, const void* src, uint32_t bytes) {
+  if ((bytes & 15u) || ((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u)) {  // cp.async.bulk: 16-byte size and alignment
+    std::fprintf(stderr, "shim: cp.async.bulk needs 16-byte aligned addresses and size (dst %p src %p bytes %u)\n", dst, src, bytes);
+    std::abort();
+  }
+  std::memcpy(dst, src, bytes);
+}
 
 // run `kernel(args...)` for every thread of every block of the grid
 template <typename... KArgs, typename... Args>
 inline cudaError_t run_grid(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
   const unsigned nthreads = block.x * block.y * block.z;
+  g_last_grid = grid;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {

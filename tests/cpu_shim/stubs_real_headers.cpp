@@ -39,6 +39,25 @@ cudaError_t launch_gemv(const LaunchCtx&, int pro, int epi, const GemvParams& p)
 
 extern "C" {
 const char* ua2_last_error(void) { return ua2::g_err.c_str(); }
+void shim_set_sm_count(int n) { g_shim_sm_count = n; }  // before the first launch of a persistent kernel (launchers cache it)
+// ua2_attn_f32 of ua2_ops.cu (outside this build) + the Moshi context window and the "attn_ring" option
+int shim_attn(const float* q, const float* k_cache, const float* v_cache, const int32_t* pos, const int32_t* bidx, float* y, float* workspace,
+              int M, int n_head, int n_groups, int hs, int S_max, int window, int ring, int* grid_x) {
+  ua2::LaunchCtx lc;
+  ua2::AttnParams a;
+  a.q = q; a.k_cache = k_cache; a.v_cache = v_cache; a.pos = pos; a.bidx = bidx;
+  a.M = M; a.n_head = n_head; a.n_groups = n_groups; a.hs = hs; a.S_max = S_max; a.window = window;
+  a.max_splits = (S_max + ua2::ATTN_CHUNK - 1) / ua2::ATTN_CHUNK;
+  a.n_splits_launch = a.max_splits;
+  a.o_part = workspace;
+  a.ml_part = workspace + (size_t)M * n_head * a.max_splits * hs;
+  ua2::set_attn_ring(ring);
+  cudaError_t e = ua2::launch_attn(lc, a);
+  ua2::set_attn_ring(0);
+  *grid_x = (int)shim::g_last_grid.x;
+  if (e != cudaSuccess) return (int)e;
+  return (int)ua2::launch_attn_combine(lc, a, y);
+}
 void shim_set_conv_tc(int v) { ua2::set_conv_tc(v); }  // ua2_set_global_option("conv_tc") lives in ua2_ops.cu, outside this build
 int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float, const float* residual, float* y, int M, int N, int K, void*) {
   if (norm_w || residual) return UA2_ERR_INVALID;

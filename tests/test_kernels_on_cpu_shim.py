@@ -255,7 +255,7 @@ def shim3(tmp_path_factory):
     d = str(tmp_path_factory.mktemp("shim3"))
     srcs = []
     hdr = os.path.join(ROOT, "include", "ua2_b200.h")
-    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock"):
+    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock", "ua2_attn"):
         src = open(os.path.join(CSRC, name + ".cu")).read()
         # dynamic shared memory -> the exactly-sized block that the shim's launch() allocates from the launcher's byte count
         src = re.sub(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(shim::g_dyn_smem);", src)
@@ -266,7 +266,7 @@ def shim3(tmp_path_factory):
     stub = open(os.path.join(SHIM, "stubs_real_headers.cpp")).read().replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
     open(os.path.join(d, "stubs.cpp"), "w").write(stub)
     so = os.path.join(d, "libshim3.so")
-    cmd = GXX + [ "-DUA2_CPU_SHIM", "-I", CSRC, "-I", os.path.join(SHIM, "rt"),
+    cmd = GXX + [ "-DUA2_CPU_SHIM", "-DUA2_ATTN_RING_MIN_ITEMS=64", "-I", CSRC, "-I", os.path.join(SHIM, "rt"),
            "-Wl,--no-undefined"] + srcs + [os.path.join(d, "stubs.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
@@ -456,3 +456,48 @@ def test_conv_tc_dispatch_through_real_launchers_on_cpu(shim3):
             assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max())), (Cin, stride)
     finally:
         shim3.shim_set_conv_tc(0)
+
+
+def _attention_reference(q, kc, vc, pos, bidx, n_head, n_groups, hs, window):
+    """lit_model.py:468-532 for one query row per entry: keys 0..pos of cache row bidx (the last `window` of them when window > 0),
+    each KV group serving n_head / n_groups query heads, softmax(q k / sqrt(hs)) v."""
+    M, qpk = q.shape[0], n_head // n_groups
+    out = torch.empty(M, n_head * hs)
+    for m in range(M):
+        n = int(pos[m]) + 1
+        lo = max(0, n - window) if window > 0 else 0
+        for h in range(n_head):
+            k, v = kc[int(bidx[m]), h // qpk, lo:n].double(), vc[int(bidx[m]), h // qpk, lo:n].double()
+            w = torch.softmax(k @ q[m, h * hs:(h + 1) * hs].double() / math.sqrt(hs), 0)
+            out[m, h * hs:(h + 1) * hs] = (w @ v).float()
+    return out
+
+
+@pytest.mark.parametrize("hs,n_head,n_groups,M,S_max,window", [(128, 6, 2, 8, 600, 0), (64, 4, 4, 5, 500, 0), (32, 4, 2, 10, 520, 150)])
+def test_kv_cache_attention_ring_and_split_sources_on_cpu(shim3, hs, n_head, n_groups, M, S_max, window):
+    """csrc/ua2_attn.cu through launch_attn + launch_attn_combine: the shipped one-shot split kernel (GPU-green; here it validates the
+    shim's mbarrier / bulk-copy emulation) and the not-yet-run persistent ring kernel (option "attn_ring") on ragged positions -
+    rows that end inside a chunk, at a chunk edge, at the last cache slot, a single key; empty splits; permuted cache rows.  The two
+    kernels share item arithmetic, so their outputs must be bit-equal; both must match the fp64 reference."""
+    shim3.shim_set_sm_count(3)  # 6-12 persistent CTAs: a dozen or more items each, every ring slot reused with both parities
+    g = torch.Generator().manual_seed(hs + M)
+    B = M
+    kc, vc = torch.randn(B, n_groups, S_max, hs, generator=g), torch.randn(B, n_groups, S_max, hs, generator=g)
+    q = torch.randn(M, n_head * hs, generator=g)
+    pos = torch.randint(0, S_max, (M,), generator=g).to(torch.int32)
+    pos[0], pos[1], pos[2], pos[3] = S_max - 1, 0, 63, 64
+    bidx = torch.randperm(B, generator=g).to(torch.int32)
+    splits = (S_max + 63) // 64
+    assert M * n_groups * splits >= 64  # the ring threshold of launch_attn in this build (-DUA2_ATTN_RING_MIN_ITEMS; 592 as shipped)
+    ref = _attention_reference(q, kc, vc, pos, bidx, n_head, n_groups, hs, window)
+    outs = []
+    for ring in (0, 1):
+        ws = torch.full((M * n_head * splits * (hs + 2),), float("nan"))
+        y = torch.full((M, n_head * hs), float("nan"))
+        grid_x = C.c_int(0)
+        rc = shim3.shim_attn(_p(q), _p(kc), _p(vc), _p(pos), _p(bidx), _p(y), _p(ws), M, n_head, n_groups, hs, S_max, window, ring, C.byref(grid_x))
+        assert rc == 0, rc
+        assert grid_x.value == (3 * (2 if hs == 128 else 4) if ring else splits)  # persistent CTAs vs one CTA per item
+        assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max())), ring
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])

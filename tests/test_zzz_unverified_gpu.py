@@ -330,3 +330,57 @@ def test_resblock_fused_option_keeps_codec_results():
         _lib.check(L.ua2_set_global_option(b"resblock_fused", 0))
     assert torch.equal(codes.cpu(), ref_codes)
     assert float((out.cpu() - ref_wav).abs().max()) < 1e-4
+
+
+# ---- (5) option "attn_ring": persistent K/V chunk ring for long batched contexts (csrc/ua2_attn.cu)
+@pytest.mark.parametrize("hs,n_head,G,M,S_max", [(128, 24, 8, 32, 2048), (64, 8, 8, 16, 1024), (32, 4, 2, 40, 800), (128, 24, 8, 3, 2048)])
+def test_attn_ring_option_matches_split_kernel_and_reference(hs, n_head, G, M, S_max):
+    """ua2_attn_f32 with the option on: bit-equal to the one-shot split kernel (same item arithmetic) and within 2e-5 of an fp64
+    reference; ragged positions (chunk edges, single key, last slot), permuted cache rows.  The last case (3 x 8 x 32 = 768 items)
+    sits just above the launcher's threshold.  (The Moshi context window is not an argument of this operator; the windowed form of
+    both kernels is compared on the CPU shim, tests/test_kernels_on_cpu_shim.py.)"""
+    from uniaudio2_b200 import _lib
+
+    L, P = _lib.lib(), _lib.ptr
+    g = torch.Generator().manual_seed(hs + M)
+    kc, vc = torch.randn(M, G, S_max, hs, generator=g), torch.randn(M, G, S_max, hs, generator=g)
+    q = torch.randn(M, n_head * hs, generator=g)
+    pos = torch.randint(0, S_max, (M,), generator=g).to(torch.int32)
+    pos[0], pos[1], pos[2] = S_max - 1, 0, 63
+    if M > 3:
+        pos[3] = 64
+    bidx = torch.randperm(M, generator=g).to(torch.int32)
+    qpk = n_head // G
+    ref = torch.empty(M, n_head * hs)
+    for m in range(M):
+        n = int(pos[m]) + 1
+        for h in range(n_head):
+            k, v = kc[int(bidx[m]), h // qpk, :n].double(), vc[int(bidx[m]), h // qpk, :n].double()
+            w = torch.softmax(k @ q[m, h * hs:(h + 1) * hs].double() / hs ** 0.5, 0)
+            ref[m, h * hs:(h + 1) * hs] = (w @ v).float()
+    d = [t.cuda() for t in (q, kc, vc, pos, bidx)]
+    ws = torch.empty(L.ua2_attn_workspace_floats(M, n_head, hs, S_max), device="cuda")
+    outs = []
+    try:
+        for ring in (0, 1):
+            _lib.check(L.ua2_set_global_option(b"attn_ring", ring))
+            y = torch.full((M, n_head * hs), float("nan"), device="cuda")
+            ws.fill_(float("nan"))
+            _lib.check(L.ua2_attn_f32(P(d[0]), P(d[1]), P(d[2]), P(d[3]), P(d[4]), P(y), P(ws), M, n_head, G, hs, S_max, None))
+            torch.cuda.synchronize()
+            assert _rel(y.cpu(), ref) < 2e-5, ring
+            outs.append(y.cpu())
+    finally:
+        _lib.check(L.ua2_set_global_option(b"attn_ring", 0))
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_attn_ring_option_keeps_llm_golden_ids():
+    """The batch-32 decode case of the LLM suite with the option on: same token ids as with it off."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, UA2_OPTIONS="attn_ring=1")  # applied by uniaudio2_b200/_lib.py at load
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_llm_gpu.py"), "-q", "-x", "-m", "gpu", "-k", "batch"],
+                       capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:]

@@ -8,8 +8,9 @@ convolutions - measured stand-alone through the C ABI on one B200 (CUDA events o
               10 s; FLOP = 2 * B * T_out * Cout * Cin * K; bound = fp32 FMA pipe (148 SMs x 128 lanes x 2 x SM clock) for all but
               the first / last layer, whose intensity is low enough for HBM to bind
 
-    python tools/measure_kernels.py [--conv-tc] [--resblock]     (also time the not-yet-measured options)
+    python tools/measure_kernels.py [--conv-tc] [--resblock] [--attn-ring]     (also time the not-yet-measured options)
 """
+import ctypes as C
 import json
 import os
 import sys
@@ -43,7 +44,8 @@ def main():
     hbm = float(peaks.get("hbm_gbs", 6534.5))
     fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12  # TFLOP/s
     n_head, G, hs, S_max = 24, 8, 128, 2048
-    for B, S in ((1, 256), (1, 2048), (8, 2048), (32, 2048)):
+    ring_opts = (0, 1) if "--attn-ring" in sys.argv else (0,)
+    for B, S in ((1, 256), (1, 2048), (8, 2048), (32, 2048), (32, 540)):
         kv_bytes = 2 * G * S_max * hs * 4 * B
         n_sets = max(1, int(300e6 // kv_bytes) + 1)  # rotate through > 126 MB of caches so that K/V come from HBM
         kcs = [torch.randn(B, G, S_max, hs, device=dev) for _ in range(n_sets)]
@@ -53,16 +55,32 @@ def main():
         bidx = torch.arange(B, dtype=torch.int32, device=dev)
         y = torch.empty(B, n_head * hs, device=dev)
         ws = torch.empty(L.ua2_attn_workspace_floats(B, n_head, hs, S_max), device=dev)
-
-        def run(i):
-            j = i % n_sets
-            _lib.check(L.ua2_attn_f32(P(q), P(kcs[j]), P(vcs[j]), P(pos), P(bidx), P(y), P(ws), B, n_head, G, hs, S_max, None))
-
-        ms = timed(run, 50)
         by = 2 * G * S * hs * 4 * B
-        print(json.dumps(dict(kernel="attn_split_kernel<128> + combine (ua2_attn_f32)", batch=B, keys=S, us=round(ms * 1e3, 2),
-                              algorithmic_MB=round(by / 1e6, 2), GBps=round(by / ms / 1e6, 1), frac_of_hbm_peak=round(by / ms / 1e6 / hbm, 3),
-                              buffers_rotated=n_sets)))
+        for ring in ring_opts:
+            _lib.check(L.ua2_set_global_option(b"attn_ring", ring))
+
+            def run(i, stream=None):
+                j = i % n_sets
+                _lib.check(L.ua2_attn_f32(P(q), P(kcs[j]), P(vcs[j]), P(pos), P(bidx), P(y), P(ws), B, n_head, G, hs, S_max, stream))
+
+            ms = timed(run, 50)
+            # the same calls replayed from a CUDA graph: without the host cost of the two ctypes launches per call (~50 us), which
+            # bounds the eager number for every shape but the largest (profiles/r1_kernel_rooflines.md)
+            side = torch.cuda.Stream()
+            n_calls = max(n_sets, 8)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(n_calls):
+                    run(i, C.c_void_p(side.cuda_stream))
+            ms_graph = timed(lambda i: graph.replay(), 10) / n_calls
+            print(json.dumps(dict(kernel="ua2_attn_f32: %s + combine" % ("attn_ring_kernel<128> (where the launcher takes it)" if ring else "attn_split_kernel<128>"),
+                                  attn_ring=ring, batch=B, keys=S, us=round(ms * 1e3, 2), us_graph_replay=round(ms_graph * 1e3, 2),
+                                  algorithmic_MB=round(by / 1e6, 2), GBps_graph=round(by / ms_graph / 1e6, 1),
+                                  frac_of_hbm_peak_graph=round(by / ms_graph / 1e6 / hbm, 3), frac_of_hbm_peak_eager=round(by / ms / 1e6 / hbm, 3),
+                                  buffers_rotated=n_sets)))
+            del graph
+        _lib.check(L.ua2_set_global_option(b"attn_ring", 0))
         del kcs, vcs
         torch.cuda.empty_cache()
     # ---- SEANet layers (encoder: conv; decoder: transposed conv), batch 16 x 10 s at 24 kHz

@@ -139,6 +139,11 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = l
+        # UA2_OPTIONS="attn_ring=1,conv_tc=1": global options applied at load, for A/B runs of whole programs (bench.py, the test
+        # suite) without editing them; an unknown name or a refused value raises
+        for item in filter(None, (x.strip() for x in os.environ.get("UA2_OPTIONS", "").split(","))):
+            name, _, value = item.partition("=")
+            check(l.ua2_set_global_option(name.strip().encode(), int(value)), f"UA2_OPTIONS {item}")
     return _lib
 
 

@@ -16,8 +16,6 @@ namespace {
 
 constexpr int MAX_QPK = 4;
 
-__device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // One CTA = (split of ATTN_CHUNK keys, KV group, query row).  The K and V chunks are contiguous in the cache
 // ((b, g, pos, hs) layout), so each is fetched with ONE bulk copy (cp.async.bulk -> mbarrier) into shared memory:
 // every byte of the chunk is in flight at once and the whole kernel is a single memory round trip.
@@ -46,19 +44,13 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   float* Ks = kv_s;
   float* Vs = kv_s + C * HS;
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32a(&bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init(&bar, 1);
+    mbar_fence_init();
     const uint32_t bytes = (uint32_t)span * HS * 4u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32a(&bar)), "r"(2u * bytes) : "memory");
+    mbar_arrive_expect_tx(&bar, 2u * bytes);
     if (bytes > 0) {
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32a(Ks)),
-                   "l"(Kc), "r"(bytes), "r"(smem_u32a(&bar))
-                   : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32a(Vs)),
-                   "l"(Vc), "r"(bytes), "r"(smem_u32a(&bar))
-                   : "memory");
+      bulk_copy_g2s(Ks, Kc, bytes, &bar);
+      bulk_copy_g2s(Vs, Vc, bytes, &bar);
     }
   }
   const int n_keys = p.pos[m] + 1;
@@ -84,17 +76,7 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
                                                                part * 4 + 32 * i)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();  // barrier init visible to every waiter
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32a(&bar)),
-      "r"(0u)
-      : "memory");
+  mbar_wait(&bar, 0u);
   if (empty) return;  // (only after the copies have landed: the CTA's shared memory must outlive them)
 
   // ---- phase 1: scores.  16 keys per iteration over the CTA (4 warps x 4 keys)
@@ -190,16 +172,221 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   }
 }
 
-// stand-alone merge of the split partials -> y (M, n_head*hs); the handle path fuses this into PRO_ATTN instead
-__global__ void attn_combine_kernel(const AttnParams p, float* y) {
+// ---------------------------------------------------------------------------------------------------------------------------
+// Option "attn_ring" (default 0 - written at the end of round 1, NOT yet run on a B200): the same split-softmax work items
+// for long, batched contexts, where attn_split_kernel reaches 37 % of the HBM peak (profiles/r1_kernel_rooflines.md: a CTA
+// fetches, waits, computes and exits, so its share of the copy engine idles during the math).  Here a persistent CTA walks a
+// contiguous range of the (row, group, split) items and streams their K and V chunks through a 3-slot ring of bulk copies:
+// while the scores of item j are computed from K_j, V_j and K_{j+1} are in flight; every freed slot is refilled at the next
+// __syncthreads.  Slots hold ONE chunk (K or V, 32 KB at hs 128), so two CTAs fit an SM with 4 chunks in flight between them.
+// Partial outputs and statistics land exactly where attn_split_kernel puts them (same item -> (m, head, split) map, same
+// arithmetic order inside an item), so the consumers (PRO_ATTN, attn_combine_kernel) are unchanged.
+constexpr int RING_SLOTS = 3;
+#ifndef UA2_ATTN_RING_MIN_ITEMS
+#define UA2_ATTN_RING_MIN_ITEMS (4 * 148)  // work items from which launch_attn takes the ring kernel (tests/cpu_shim lowers it)
+#endif
+
+struct RingItem {
+  int m, g, split, start, cnt, lo;
+  bool empty;
+};
+
+__device__ __forceinline__ RingItem ring_item(const AttnParams& p, int it) {
+  RingItem r;
+  const int nsl = p.n_splits_launch;
+  r.split = it % nsl;
+  const int mg = it / nsl;
+  r.g = mg % p.n_groups;
+  r.m = mg / p.n_groups;
+  const int n_keys = p.pos[r.m] + 1;
+  r.start = r.split * ATTN_CHUNK;
+  r.lo = (p.window > 0) ? max(0, n_keys - p.window) : 0;
+  r.empty = r.start >= n_keys || r.start + ATTN_CHUNK <= r.lo;
+  r.cnt = min(ATTN_CHUNK, n_keys - r.start);
+  return r;
+}
+
+template <int HS>
+__global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int n_items) {
+  extern __shared__ __align__(128) float ring_s[];  // RING_SLOTS x [C][HS]
+  __shared__ float sc[MAX_QPK][ATTN_CHUNK];
+  __shared__ __align__(16) float redp[4][MAX_QPK][HS];
+  __shared__ __align__(8) uint64_t full[RING_SLOTS];
+  constexpr int C = ATTN_CHUNK;
+  constexpr int NI = HS / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int it0 = (int)((long long)n_items * blockIdx.x / gridDim.x), it1 = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+  const int qpk = p.n_head / p.n_groups;
+  const float scale = rsqrtf((float)HS);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.x;
+
+  // producer state (thread 0 only): the next copy is the K (half 0) or V (half 1) chunk of item p_it, sequence number p_seq
+  int p_it = it0, p_half = 0;
+  unsigned p_seq = 0;
+  auto issue = [&]() {
+    while (p_half == 0 && p_it < it1 && ring_item(p, p_it).empty) ++p_it;
+    if (p_it >= it1) return;
+    const RingItem r = ring_item(p, p_it);
+    const int b = p.bidx_identity ? r.m : p.bidx[r.m];
+    const float* src = (p_half == 0 ? p.k_cache : p.v_cache) + (((size_t)b * p.n_groups + r.g) * p.S_max + r.start) * HS;
+    const unsigned slot = p_seq % RING_SLOTS;
+    const uint32_t bytes = (uint32_t)r.cnt * HS * 4u;  // only the visible rows of the chunk
+    mbar_arrive_expect_tx(&full[slot], bytes);
+    bulk_copy_g2s(ring_s + (size_t)slot * C * HS, src, bytes, &full[slot]);
+    ++p_seq;
+    if (p_half == 0) {
+      p_half = 1;
+    } else {
+      p_half = 0;
+      ++p_it;
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < RING_SLOTS; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+#pragma unroll
+    for (int s = 0; s < RING_SLOTS; ++s) issue();
+  }
+  __syncthreads();  // barrier init visible to every waiter
+
+  const int kk = lane >> 3, part = lane & 7;
+  float4 qr[MAX_QPK][NI];
+  int q_m = -1, q_g = -1;
+  unsigned c_seq = 0;  // sequence number of the next chunk this CTA consumes
+  for (int it = it0; it < it1; ++it) {
+    const RingItem r = ring_item(p, it);
+    if (r.empty) {  // publish weight-0 statistics so consumers can merge blindly
+      if (tid < qpk) {
+        const size_t idx = (((size_t)r.m * p.n_head + r.g * qpk + tid) * p.max_splits + r.split) * 2;
+        p.ml_part[idx] = -INFINITY;
+        p.ml_part[idx + 1] = 0.f;
+      }
+      continue;
+    }
+    if (r.m != q_m || r.g != q_g) {  // a contiguous item range changes (row, group) once per n_splits_launch items
+#pragma unroll
+      for (int h = 0; h < MAX_QPK; ++h)
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          qr[h][i] = (h < qpk) ? *reinterpret_cast<const float4*>(p.q + (size_t)r.m * p.n_head * HS + (r.g * qpk + h) * HS + part * 4 + 32 * i)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      q_m = r.m;
+      q_g = r.g;
+    }
+    const int cnt = r.cnt;
+    const float* Ks = ring_s + (size_t)(c_seq % RING_SLOTS) * C * HS;
+    mbar_wait(&full[c_seq % RING_SLOTS], (c_seq / RING_SLOTS) & 1u);
+
+    // ---- phase 1: scores (as attn_split_kernel)
+#pragma unroll
+    for (int i16 = 0; i16 < C / 16; ++i16) {
+      const int j = i16 * 16 + warp * 4 + kk;
+      float s[MAX_QPK];
+#pragma unroll
+      for (int h = 0; h < MAX_QPK; ++h) s[h] = 0.f;
+      if (j < cnt) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const float4 kv = *reinterpret_cast<const float4*>(Ks + (size_t)j * HS + part * 4 + 32 * i);
+#pragma unroll
+          for (int h = 0; h < MAX_QPK; ++h) {
+            s[h] = fmaf(kv.x, qr[h][i].x, s[h]);
+            s[h] = fmaf(kv.y, qr[h][i].y, s[h]);
+            s[h] = fmaf(kv.z, qr[h][i].z, s[h]);
+            s[h] = fmaf(kv.w, qr[h][i].w, s[h]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < MAX_QPK; ++h) {
+        s[h] += __shfl_xor_sync(0xffffffffu, s[h], 1);
+        s[h] += __shfl_xor_sync(0xffffffffu, s[h], 2);
+        s[h] += __shfl_xor_sync(0xffffffffu, s[h], 4);
+        if (part == 0 && j < cnt && h < qpk) sc[h][j] = (r.start + j >= r.lo) ? s[h] * scale : -INFINITY;
+      }
+    }
+    __syncthreads();       // the K slot is free
+    if (tid == 0) issue();
+
+    // ---- phase 2: warp h does the local softmax of head h
+    if (warp < qpk) {
+      const int h = warp;
+      float mx = -INFINITY;
+      for (int t = lane; t < cnt; t += 32) mx = fmaxf(mx, sc[h][t]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int t = lane; t < cnt; t += 32) {
+        const float e = expf(sc[h][t] - mx);
+        sc[h][t] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        const size_t idx = (((size_t)r.m * p.n_head + r.g * qpk + h) * p.max_splits + r.split) * 2;
+        p.ml_part[idx] = mx;
+        p.ml_part[idx + 1] = sum;
+      }
+    }
+    __syncthreads();
+    const float* Vs = ring_s + (size_t)((c_seq + 1) % RING_SLOTS) * C * HS;
+    mbar_wait(&full[(c_seq + 1) % RING_SLOTS], ((c_seq + 1) / RING_SLOTS) & 1u);
+
+    // ---- phase 3: P @ V (as attn_split_kernel)
+    constexpr int LPK = HS / 4;
+    constexpr int KPI = 32 / LPK;
+    const int ksub = lane / LPK, d4 = lane - ksub * LPK;
+    float4 acc[MAX_QPK];
+#pragma unroll
+    for (int h = 0; h < MAX_QPK; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int t0 = warp * (C / 4);
+#pragma unroll 4
+    for (int tt = 0; tt < C / 4; tt += KPI) {
+      const int t = t0 + tt + ksub;
+      if (t < cnt) {
+        const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)t * HS + d4 * 4);
+#pragma unroll
+        for (int h = 0; h < MAX_QPK; ++h) {
+          const float w = (h < qpk) ? sc[h][t] : 0.f;
+          acc[h].x = fmaf(w, v.x, acc[h].x);
+          acc[h].y = fmaf(w, v.y, acc[h].y);
+          acc[h].z = fmaf(w, v.z, acc[h].z);
+          acc[h].w = fmaf(w, v.w, acc[h].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < MAX_QPK; ++h) {
+#pragma unroll
+      for (int o = LPK; o < 32; o <<= 1) {
+        acc[h].x += __shfl_xor_sync(0xffffffffu, acc[h].x, o);
+        acc[h].y += __shfl_xor_sync(0xffffffffu, acc[h].y, o);
+        acc[h].z += __shfl_xor_sync(0xffffffffu, acc[h].z, o);
+        acc[h].w += __shfl_xor_sync(0xffffffffu, acc[h].w, o);
+      }
+      if (ksub == 0) *reinterpret_cast<float4*>(&redp[warp][h][d4 * 4]) = acc[h];
+    }
+    __syncthreads();       // the V slot is free; redp complete
+    if (tid == 0) issue();
+    for (int i = tid; i < qpk * HS; i += 128) {
+      const int h = i / HS, d = i - h * HS;
+      const float o = (redp[0][h][d] + redp[1][h][d]) + (redp[2][h][d] + redp[3][h][d]);
+      p.o_part[(((size_t)r.m * p.n_head + r.g * qpk + h) * p.max_splits + r.split) * HS + d] = o;
+    }
+    c_seq += 2;
+  }
+}
+
+// stand-alone merge of the split partials -> y (M, n_head*hs); the handle path fuses this into PRO_ATTN instead
+__global__ void attn_combine_kernel(const AttnParams p, float* y) {  // grid (n_head, M): one CTA per (head, row)
+  pdl_launch_dependents();
+  pdl_wait();
+  const int hh = blockIdx.x, m = blockIdx.y;
   const int n_s = p.n_splits_launch > 0 ? p.n_splits_launch : (p.pos[m] + ATTN_CHUNK) / ATTN_CHUNK;  // empties weigh 0
   const int D = p.n_head * p.hs;
-  for (int k = threadIdx.x; k < D; k += blockDim.x) {
-    const int hh = k / p.hs, d = k - hh * p.hs;
-    const size_t base = ((size_t)m * p.n_head + hh) * p.max_splits;
+  const size_t base = ((size_t)m * p.n_head + hh) * p.max_splits;
+  for (int d = threadIdx.x; d < p.hs; d += blockDim.x) {
     float mx = -INFINITY;
     for (int s = 0; s < n_s; ++s) mx = fmaxf(mx, p.ml_part[(base + s) * 2]);
     float den = 0.f, num = 0.f;
@@ -210,7 +397,7 @@ __global__ void attn_combine_kernel(const AttnParams p, float* y) {
         num += w * p.o_part[(base + s) * p.hs + d];
       }
     }
-    y[(size_t)m * D + k] = num / den;
+    y[(size_t)m * D + hh * p.hs + d] = num / den;
   }
 }
 
@@ -229,10 +416,44 @@ cudaError_t launch_attn_hs(const LaunchCtx& lc, const AttnParams& p) {
   return launch(lc, attn_split_kernel<HS>, grid, block, smem, p);
 }
 
+template <int HS>
+cudaError_t launch_attn_ring_hs(const LaunchCtx& lc, const AttnParams& p, int n_items) {
+  const size_t smem = (size_t)RING_SLOTS * ATTN_CHUNK * HS * sizeof(float);
+  static bool attr_set = false;
+  static int n_sm = 148;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_ring_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = prefer_max_smem(attn_ring_kernel<HS>);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  const int per_sm = HS == 128 ? 2 : 4;  // 105 KB / 57 KB / 31 KB of shared memory per CTA
+  const int grid = std::min(n_items, n_sm * per_sm);
+  return launch(lc, attn_ring_kernel<HS>, dim3(grid), dim3(128), smem, p, n_items);
+}
+
+int g_attn_ring = 0;
+
 }  // namespace
+
+void set_attn_ring(int v) { g_attn_ring = v ? 1 : 0; }
+int get_attn_ring() { return g_attn_ring; }
 
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p) {
   if (p.n_head % p.n_groups != 0 || p.n_head / p.n_groups > MAX_QPK) return cudaErrorInvalidValue;
+  const long long n_items = (long long)p.M * p.n_groups * p.n_splits_launch;
+  // the ring pays off once every CTA walks several items; a decode frame at batch 1 (8-32 items) stays on the one-shot kernel
+  if (g_attn_ring && n_items >= UA2_ATTN_RING_MIN_ITEMS && n_items < (1LL << 30)) {
+    switch (p.hs) {
+      case 128: return launch_attn_ring_hs<128>(lc, p, (int)n_items);
+      case 64: return launch_attn_ring_hs<64>(lc, p, (int)n_items);
+      case 32: return launch_attn_ring_hs<32>(lc, p, (int)n_items);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (p.hs) {
     case 128: return launch_attn_hs<128>(lc, p);
     case 64: return launch_attn_hs<64>(lc, p);
@@ -247,7 +468,7 @@ cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float*
     prefer_max_smem(attn_combine_kernel);
     once = true;
   }
-  return launch(lc, attn_combine_kernel, dim3(p.M), dim3(256), 0, p, y);
+  return launch(lc, attn_combine_kernel, dim3(p.n_head, p.M), dim3(std::min(128, p.hs)), 0, p, y);
 }
 
 }  // namespace ua2

@@ -168,6 +168,9 @@ struct AttnParams {
 };
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p);
 cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float* y);
+// persistent 3-slot K/V chunk ring for long batched contexts (ua2_attn.cu; option "attn_ring", default 0)
+void set_attn_ring(int v);
+int get_attn_ring();
 
 // ---------------------------------------------------------------- small fused elementwise kernels
 struct FrameScalars {  // per-call scalars living in device memory so captured graphs stay valid

@@ -44,6 +44,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_resblock_fused(value);
     return UA2_OK;
   }
+  if (std::string(name) == "attn_ring") {  // persistent K/V chunk ring for long batched contexts (ua2_attn.cu); default 0
+    set_attn_ring(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "conv_tc") {
     UA2_REQUIRE(!value || tc_gemm_available(), "library was built without the CUTLASS headers: no tensor-core path");
     set_conv_tc(value);
