@@ -44,10 +44,10 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
   float* Ks = kv_s;
   float* Vs = kv_s + C * HS;
   if (tid == 0) {
-    mbar_init(&bar, 1);
-    mbar_fence_init();
+    smem_bar_init(&bar, 1);
+    smem_bar_fence_init();
     const uint32_t bytes = (uint32_t)span * HS * 4u;
-    mbar_arrive_expect_tx(&bar, 2u * bytes);
+    smem_bar_arrive_expect_tx(&bar, 2u * bytes);
     if (bytes > 0) {
       bulk_copy_g2s(Ks, Kc, bytes, &bar);
       bulk_copy_g2s(Vs, Vc, bytes, &bar);
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
                                                                part * 4 + 32 * i)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();  // barrier init visible to every waiter
-  mbar_wait(&bar, 0u);
+  smem_bar_wait(&bar, 0u);
   if (empty) return;  // (only after the copies have landed: the CTA's shared memory must outlive them)
 
   // ---- phase 1: scores.  16 keys per iteration over the CTA (4 warps x 4 keys)
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int 
     const float* src = (p_half == 0 ? p.k_cache : p.v_cache) + (((size_t)b * p.n_groups + r.g) * p.S_max + r.start) * HS;
     const unsigned slot = p_seq % RING_SLOTS;
     const uint32_t bytes = (uint32_t)r.cnt * HS * 4u;  // only the visible rows of the chunk
-    mbar_arrive_expect_tx(&full[slot], bytes);
+    smem_bar_arrive_expect_tx(&full[slot], bytes);
     bulk_copy_g2s(ring_s + (size_t)slot * C * HS, src, bytes, &full[slot]);
     ++p_seq;
     if (p_half == 0) {
@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int 
   };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < RING_SLOTS; ++s) mbar_init(&full[s], 1);
-    mbar_fence_init();
+    for (int s = 0; s < RING_SLOTS; ++s) smem_bar_init(&full[s], 1);
+    smem_bar_fence_init();
 #pragma unroll
     for (int s = 0; s < RING_SLOTS; ++s) issue();
   }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int 
     }
     const int cnt = r.cnt;
     const float* Ks = ring_s + (size_t)(c_seq % RING_SLOTS) * C * HS;
-    mbar_wait(&full[c_seq % RING_SLOTS], (c_seq / RING_SLOTS) & 1u);
+    smem_bar_wait(&full[c_seq % RING_SLOTS], (c_seq / RING_SLOTS) & 1u);
 
     // ---- phase 1: scores (as attn_split_kernel)
 #pragma unroll
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int 
     }
     __syncthreads();
     const float* Vs = ring_s + (size_t)((c_seq + 1) % RING_SLOTS) * C * HS;
-    mbar_wait(&full[(c_seq + 1) % RING_SLOTS], ((c_seq + 1) / RING_SLOTS) & 1u);
+    smem_bar_wait(&full[(c_seq + 1) % RING_SLOTS], ((c_seq + 1) / RING_SLOTS) & 1u);
 
     // ---- phase 3: P @ V (as attn_split_kernel)
     constexpr int LPK = HS / 4;

@@ -63,14 +63,14 @@ __device__ __forceinline__ void pdl_launch_dependents() {}
 #endif
 
 // mbarrier + bulk-copy (cp.async.bulk global -> shared) wrappers: one spelling of the PTX for the kernels that stream through
-// shared-memory rings.  `bar` lives in shared memory.  mbar_wait(bar, parity) returns once the phase of that parity has completed.
+// shared-memory rings.  `bar` lives in shared memory.  smem_bar_wait(bar, parity) returns once the phase of that parity has completed.
 #ifndef UA2_CPU_SHIM
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+__device__ __forceinline__ void smem_bar_init(uint64_t* bar, uint32_t arrivals) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(arrivals));
 }
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+__device__ __forceinline__ void smem_bar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void smem_bar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {  // bytes % 16 == 0
@@ -78,7 +78,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, u
                "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void smem_bar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -92,14 +92,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 #else  // tests/cpu_shim: the copy completes inside the issuing call; the barrier word is {phase:1 | arrivals:15 | count:16 | tx:32}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) { shim::mbar_init(bar, arrivals); }
-__device__ __forceinline__ void mbar_fence_init() {}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { shim::mbar_update(bar, 1, (int64_t)bytes); }
+__device__ __forceinline__ void smem_bar_init(uint64_t* bar, uint32_t arrivals) { shim::mbar_init(bar, arrivals); }
+__device__ __forceinline__ void smem_bar_fence_init() {}
+__device__ __forceinline__ void smem_bar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { shim::mbar_update(bar, 1, (int64_t)bytes); }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   shim::bulk_copy(dst_smem, src, bytes);
   shim::mbar_update(bar, 0, -(int64_t)bytes);
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { shim::mbar_wait(bar, parity); }
+__device__ __forceinline__ void smem_bar_wait(uint64_t* bar, uint32_t parity) { shim::mbar_wait(bar, parity); }
 #endif
 
 // Per-launch context shared by the host-side launchers.

@@ -12,6 +12,7 @@ constexpr int MAXW_RED = NWARPS;
 constexpr int MAX_STAGES = 6;
 constexpr int ROUND_UNITS = 32;
 
+#ifndef UA2_CPU_SHIM
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
@@ -38,6 +39,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+#else  // tests/cpu_shim: the emulated barrier / copy of ua2_common.cuh
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { ::ua2::smem_bar_init(bar, (uint32_t)count); }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ::ua2::smem_bar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { ::ua2::bulk_copy_g2s(dst, src, bytes, bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { ::ua2::smem_bar_wait(bar, parity); }
+#endif
 
 template <int EPI>
 __device__ __forceinline__ void unit_rows(const GemvParams& p, int u, const float*& rowA, const float*& rowB, int& nA,
