@@ -36,6 +36,16 @@ def test_header_and_binding_agree(L):
         assert hasattr(L, name), f"{name} declared in include/ua2_b200.h but not exported by the .so"
 
 
+def test_library_matches_the_sources():
+    """The in-tree .so was built from the sources, headers and flags the tree holds now (object stamps of uniaudio2_b200/build.py):
+    a failed or forgotten rebuild must not let a stale library stand in for the code under review."""
+    from uniaudio2_b200 import build as B
+
+    if not os.path.isdir(B.OBJ):
+        pytest.skip("library was not built by uniaudio2_b200.build in this tree (prebuilt .so only)")
+    assert B.stale_sources() == [], "run `python -m uniaudio2_b200.build` (and read its output)"
+
+
 def test_version_and_error_string(L):
     assert b"sm_100a" in L.ua2_version()
     assert isinstance(L.ua2_last_error(), bytes)

@@ -72,6 +72,21 @@ def _compile(src, hdig, verbose):
     return obj, True
 
 
+def stale_sources():
+    """Sources whose object file is missing or was compiled from different text / headers / flags than the tree holds now, plus
+    the library itself when it is older than an object - i.e. what `build()` would redo.  Empty list = the .so is current."""
+    hdig = _headers_digest()
+    stale = []
+    for src in _sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        dig = hashlib.sha1(open(src, "rb").read() + hdig.encode() + " ".join(EXTRA.get(os.path.basename(src), [])).encode()).hexdigest()
+        if not (os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == dig):
+            stale.append(os.path.basename(src))
+        elif not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(obj):
+            stale.append(os.path.basename(LIB))
+    return sorted(set(stale))
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if force and os.path.isdir(OBJ):
         for f in os.listdir(OBJ):
