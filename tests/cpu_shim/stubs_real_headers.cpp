@@ -58,6 +58,19 @@ int shim_attn(const float* q, const float* k_cache, const float* v_cache, const 
   if (e != cudaSuccess) return (int)e;
   return (int)ua2::launch_attn_combine(lc, a, y);
 }
+// the decode-frame linear (csrc/ua2_gemv3.cu) as ua2_linear_f32 / ua2_swiglu_f32 of ua2_ops.cu set it up: norm_w -> PRO_RMSNORM,
+// residual -> EPI_RESADD, W2 -> EPI_SWIGLU
+int shim_gemv3(const float* x, const float* W, const float* W2, const float* norm_w, float eps, const float* residual, float* y, int M, int N,
+               int K, int* grid_y) {
+  ua2::LaunchCtx lc;
+  ua2::GemvParams p;
+  p.W = W; p.W2 = W2; p.N = N; p.K = K; p.M = M; p.X = x; p.ldx = K; p.norm_w = norm_w; p.eps = eps;
+  p.Y = y; p.ldy = N; p.R = residual; p.ldr = N;
+  const int epi = W2 ? ua2::EPI_SWIGLU : (residual ? ua2::EPI_RESADD : ua2::EPI_STORE);
+  const cudaError_t e = ua2::launch_gemv3(lc, norm_w ? ua2::PRO_RMSNORM : ua2::PRO_PLAIN, epi, p, 1);
+  *grid_y = (int)shim::g_last_grid.y;
+  return (int)e;
+}
 void shim_set_conv_tc(int v) { ua2::set_conv_tc(v); }  // ua2_set_global_option("conv_tc") lives in ua2_ops.cu, outside this build
 int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float, const float* residual, float* y, int M, int N, int K, void*) {
   if (norm_w || residual) return UA2_ERR_INVALID;

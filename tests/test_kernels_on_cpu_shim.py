@@ -255,7 +255,7 @@ def shim3(tmp_path_factory):
     d = str(tmp_path_factory.mktemp("shim3"))
     srcs = []
     hdr = os.path.join(ROOT, "include", "ua2_b200.h")
-    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock", "ua2_attn"):
+    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock", "ua2_attn", "ua2_gemv3"):
         src = open(os.path.join(CSRC, name + ".cu")).read()
         # dynamic shared memory -> the exactly-sized block that the shim's launch() allocates from the launcher's byte count
         src = re.sub(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(shim::g_dyn_smem);", src)
@@ -501,3 +501,31 @@ def test_kv_cache_attention_ring_and_split_sources_on_cpu(shim3, hs, n_head, n_g
         assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max())), ring
         outs.append(y)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("M,N,K,norm,res,swiglu", [(1, 384, 3072, True, False, True), (1, 320, 1024, True, False, False), (1, 256, 2048, False, True, False),
+                                                   (2, 130, 256, False, False, False), (5, 258, 640, True, True, False), (11, 96, 132, False, False, True)])
+def test_decode_linear_gemv3_source_on_cpu(shim3, M, N, K, norm, res, swiglu):
+    """gemv3_kernel (csrc/ua2_gemv3.cu + ua2_gemv3_dev.cuh) - the weight-streaming linear of the decode frame and the kernel bench.py
+    reports as dominant; GPU-green (tests/test_ops_gpu.py::test_linear / test_swiglu, the shapes and formulas used here).  On the
+    shim it runs as written: persistent slab-partitioned CTAs, per-warp bulk-copy rings and mbarrier parities (emulated), K-split
+    partial sums exchanged through shared memory, fused RMSNorm prologue / residual / SwiGLU epilogues, row tiles of 1, 2, 4 and 8."""
+    from oracle import llm_oracle as O
+
+    shim3.shim_set_sm_count(3)
+    g = torch.Generator().manual_seed(M * 1000 + N + K)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    W2 = torch.randn(N, K, generator=g) / math.sqrt(K) if swiglu else None
+    nw = 1 + 0.1 * torch.randn(K, generator=g) if norm else None
+    r = torch.randn(M, N, generator=g) if res else None
+    xn = O.rms_norm(x, nw, 1e-5) if norm else x
+    ref = F.silu(F.linear(xn, W)) * F.linear(xn, W2) if swiglu else F.linear(xn, W)
+    if res:
+        ref = ref + r
+    y = torch.full((M, N), float("nan"))
+    grid_y = C.c_int(0)
+    rc = shim3.shim_gemv3(_p(x), _p(W), _p(W2), _p(nw), C.c_float(1e-5), _p(r), _p(y), M, N, K, C.byref(grid_y))
+    assert rc == 0, rc
+    assert 1 <= grid_y.value <= 9  # persistent grid: at most 3 CTAs on each of the 3 pretend SMs
+    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
