@@ -134,3 +134,19 @@ def test_product_does_not_import_oracle():
                 assert fn.name == "cpu_baseline_sample" or any(isinstance(g.test, ast.Name) and g.test.id == "cpu" for g in guards), fn.name
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n)]
     assert not top, "bench.py imports the oracle at module level"
+
+
+def test_ua2_options_environment_is_applied_at_load():
+    """UA2_OPTIONS="name=value,..." (uniaudio2_b200/_lib.py): applied through ua2_set_global_option when the library loads; an
+    unknown option or a malformed item fails the import instead of being ignored."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "from uniaudio2_b200 import _lib; _lib.lib(); print('loaded')"
+    ok = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, env=dict(os.environ, UA2_OPTIONS="attn_ring=1, conv_tc=0"))
+    assert ok.returncode == 0 and "loaded" in ok.stdout, ok.stderr[-2000:]
+    bad = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, env=dict(os.environ, UA2_OPTIONS="no_such_option=1"))
+    assert bad.returncode != 0 and "no_such_option" in bad.stderr
+    bad = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, env=dict(os.environ, UA2_OPTIONS="attn_ring"))
+    assert bad.returncode != 0
