@@ -379,10 +379,10 @@ __global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int 
 }
 
 // stand-alone merge of the split partials -> y (M, n_head*hs); the handle path fuses this into PRO_ATTN instead
-__global__ void attn_combine_kernel(const AttnParams p, float* y) {  // grid (n_head, M): one CTA per (head, row)
+__global__ void attn_combine_kernel(const AttnParams p, float* y) {  // grid (M, n_head): one CTA per (row, head)
   pdl_launch_dependents();
   pdl_wait();
-  const int hh = blockIdx.x, m = blockIdx.y;
+  const int m = blockIdx.x, hh = blockIdx.y;  // rows on x: a batched prefill can exceed the 65535 limit of grid.y
   const int n_s = p.n_splits_launch > 0 ? p.n_splits_launch : (p.pos[m] + ATTN_CHUNK) / ATTN_CHUNK;  // empties weigh 0
   const int D = p.n_head * p.hs;
   const size_t base = ((size_t)m * p.n_head + hh) * p.max_splits;
@@ -468,7 +468,7 @@ cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float*
     prefer_max_smem(attn_combine_kernel);
     once = true;
   }
-  return launch(lc, attn_combine_kernel, dim3(p.n_head, p.M), dim3(std::min(128, p.hs)), 0, p, y);
+  return launch(lc, attn_combine_kernel, dim3(p.M, p.n_head), dim3(std::min(128, p.hs)), 0, p, y);
 }
 
 }  // namespace ua2
