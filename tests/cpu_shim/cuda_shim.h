@@ -93,6 +93,7 @@ enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0 };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* s) { *s = cudaStreamCaptureStatusNone; return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
@@ -163,7 +164,7 @@ inline cudaError_t run_grid(void (*kernel)(KArgs...), dim3 grid, dim3 block, Arg
         std::vector<std::unique_ptr<ShimWarp>> warps;
         for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) warps.push_back(std::make_unique<ShimWarp>());
         g_warps = &warps;
-        std::vector<std::thread> ts;
+        std::vector<std::thread> ts;  // (a persistent worker pool was tried: slower - the cost is the futex traffic of the barriers)
         ts.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t)
           ts.emplace_back([=, &bar]() {

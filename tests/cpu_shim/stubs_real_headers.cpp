@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY: the launchers that the shim cannot run (bulk-copy GEMV family, tcgen05 GEMM) replaced by a CPU GEMM, plus
+// TEST INFRASTRUCTURE ONLY: the launcher that the shim cannot run (tcgen05 GEMM) replaced by a CPU GEMM, plus
 // the error plumbing of ua2_llm.cu, for building csrc/ua2_codec.cu + ua2_sgemm.cu + ua2_convtc.cu + ua2_resblock.cu with -DUA2_CPU_SHIM.
 #include "../../include/ua2_b200.h"
 #include "ua2_kernels.cuh"
@@ -9,8 +9,9 @@ void set_error(const std::string& msg) { g_err = msg; }
 struct TcWeightCache {};
 TcWeightCache* tc_cache_create() { return nullptr; }
 void tc_cache_destroy(TcWeightCache*) {}
-bool tc_gemm_available() { return true; }
-int get_tc_gemm() { return 1; }
+static int g_tc_avail = 1;
+bool tc_gemm_available() { return g_tc_avail != 0; }
+int get_tc_gemm() { return g_tc_avail; }
 int get_tc_min_rows() { return 32; }
 static void cpu_gemm(const GemvParams& p, float* C, int ldc) {
   for (int m = 0; m < p.M; ++m)
@@ -28,11 +29,6 @@ cudaError_t launch_tc_linear(const LaunchCtx&, int pro, int epi, const GemvParam
   } else {
     for (int m = 0; m < p.M; ++m) std::memcpy(p.Y + (size_t)m * p.ldy, p.tc->c + (size_t)m * p.N, sizeof(float) * p.N);
   }
-  return cudaSuccess;
-}
-cudaError_t launch_gemv(const LaunchCtx&, int pro, int epi, const GemvParams& p) {
-  if (pro != PRO_PLAIN || epi != EPI_STORE) return cudaErrorNotSupported;
-  cpu_gemm(p, p.Y, p.ldy);
   return cudaSuccess;
 }
 }  // namespace ua2
@@ -71,7 +67,8 @@ int shim_gemv3(const float* x, const float* W, const float* W2, const float* nor
   *grid_y = (int)shim::g_last_grid.y;
   return (int)e;
 }
-void shim_set_conv_tc(int v) { ua2::set_conv_tc(v); }  // ua2_set_global_option("conv_tc") lives in ua2_ops.cu, outside this build
+void shim_set_conv_tc(int v) { ua2::set_conv_tc(v); }
+void shim_set_tc_available(int v) { ua2::g_tc_avail = v; }  // 0: the build behaves like one without the CUTLASS headers  // ua2_set_global_option("conv_tc") lives in ua2_ops.cu, outside this build
 int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float, const float* residual, float* y, int M, int N, int K, void*) {
   if (norm_w || residual) return UA2_ERR_INVALID;
   ua2::GemvParams p;

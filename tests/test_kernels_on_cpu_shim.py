@@ -255,7 +255,7 @@ def shim3(tmp_path_factory):
     d = str(tmp_path_factory.mktemp("shim3"))
     srcs = []
     hdr = os.path.join(ROOT, "include", "ua2_b200.h")
-    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock", "ua2_attn", "ua2_gemv3"):
+    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock", "ua2_attn", "ua2_gemv3", "ua2_gemv", "ua2_misc", "ua2_codec_model"):
         src = open(os.path.join(CSRC, name + ".cu")).read()
         # dynamic shared memory -> the exactly-sized block that the shim's launch() allocates from the launcher's byte count
         src = re.sub(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(shim::g_dyn_smem);", src)
@@ -529,3 +529,56 @@ def test_decode_linear_gemv3_source_on_cpu(shim3, M, N, K, norm, res, swiglu):
     assert rc == 0, rc
     assert 1 <= grid_y.value <= 9  # persistent grid: at most 3 CTAs on each of the 3 pretend SMs
     assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.skipif(os.environ.get("UA2_SHIM_FULL") != "1", reason="3 minutes of OS-thread emulation: UA2_SHIM_FULL=1 runs it (last run: passed)")
+def test_whole_codec_handle_on_cpu_against_reference_golden(shim3):
+    """csrc/ua2_codec_model.cu - the ua2_codec_* handle as shipped (weight-norm folding, layout repacks, SEANet encoder, projected
+    transformer with its skinny LayerNorm / interleaved-RoPE / GELU / LayerScale linears and windowed attention, down-sampling,
+    residual VQ, and the whole way back) - on CPU tensors through the shim, against tests/golden/codec_golden.pt: the fixtures the
+    UNMODIFIED reference codec produced (oracle/make_golden_codec.py).  Same bar as the GPU test: bit-equal VQ indices, waveform
+    within 1e-4.  The tensor-core GEMM is declared unavailable, so every linear runs on the fp32 kernels of csrc/."""
+    from oracle.make_golden_codec import codec_cfgs
+    from uniaudio2_b200 import _lib
+    from uniaudio2_b200.tools.tokenizer.MimiCodec.mimi_codec import MimiCodec
+
+    golden = torch.load(os.path.join(ROOT, "tests", "golden", "codec_golden.pt"), weights_only=False)
+    cfg = codec_cfgs()["tiny"]
+    sd = CO.random_mimi_state_dict(cfg, seed=4321)
+    assert {k: float(v.double().sum()) for k, v in sd.items()} == golden["__checksum_tiny"]
+    m = MimiCodec(sample_rate=cfg.sample_rate, n_filters=cfg.n_filters, encoder_rates=cfg.encoder_rates, compress=cfg.compress,
+                  latent_dim=cfg.latent_dim, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim, rvq_layers=cfg.rvq_layers,
+                  num_heads=cfg.num_heads, num_layers=cfg.num_layers, layer_scale=cfg.layer_scale, context=cfg.context, device="cpu")
+    full = m.state_dict()
+    full.update(sd)
+    m.load_state_dict(full, strict=True)
+    shim3.shim_set_tc_available(0)
+    shim3.shim_set_sm_count(4)
+    try:
+        ratios = (C.c_int32 * 8)(*(m.encoder_rates + [0] * (8 - len(m.encoder_rates))))
+        c = m.cfg
+        ccfg = _lib.CodecCfg(c["n_filters"], ratios, len(m.encoder_rates), c["latent_dim"], c["codebook_size"], c["codebook_dim"], c["rvq_layers"],
+                             c["num_heads"], c["num_layers"], c["context"], c["dim_feedforward"], m.resample_stride, 10000.0)
+        h = C.c_void_p()
+        shim3.ua2_codec_frames.restype = C.c_int64
+        _ok(shim3, shim3.ua2_codec_create(C.byref(ccfg), C.byref(h)))
+        keep = []
+        for key, t in m.state_dict().items():
+            t = t.detach().contiguous()
+            keep.append(t)
+            _ok(shim3, shim3.ua2_codec_load_weight(h, key.encode(), _p(t), (C.c_int64 * t.dim())(*t.shape), t.dim()))
+        _ok(shim3, shim3.ua2_codec_finalize(h, None))
+        fx = golden["tiny_B2_T5797"]
+        wav = fx["wav"].contiguous()
+        B, _, T = wav.shape
+        Tq = int(shim3.ua2_codec_frames(h, T))
+        codes = torch.full((B, cfg.rvq_layers, Tq), -1, dtype=torch.int64)
+        _ok(shim3, shim3.ua2_codec_encode(h, _p(wav), B, T, _p(codes), None))
+        assert torch.equal(codes, fx["codes"]), "VQ indices differ from the reference"
+        recon = torch.full((B, 1, Tq * m.resample_stride * m.hop_length), float("nan"))
+        _ok(shim3, shim3.ua2_codec_decode(h, _p(fx["codes"].contiguous()), B, Tq, _p(recon), None))
+        assert recon.shape == fx["recon"].shape
+        assert float((recon - fx["recon"]).abs().max()) < 1e-4
+        shim3.ua2_codec_destroy(h)
+    finally:
+        shim3.shim_set_tc_available(1)

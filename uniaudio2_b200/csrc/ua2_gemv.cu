@@ -260,6 +260,7 @@ constexpr int KC = 1024;    // floats per row chunk: 4 KB bulk copies (1-2 KB co
 constexpr int STAGES = 2;   // ring depth per warp: 2 x 2 x 4 KB = 16 KB in flight per warp
 constexpr int V2_WARPS = 4;
 
+#ifndef UA2_CPU_SHIM
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -287,6 +288,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+#else  // tests/cpu_shim: the emulated barrier / copy of ua2_common.cuh
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { ::ua2::smem_bar_init(bar, (uint32_t)count); }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ::ua2::smem_bar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { ::ua2::bulk_copy_g2s(dst, src, bytes, bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { ::ua2::smem_bar_wait(bar, parity); }
+#endif
 
 template <int MT, int PRO, int EPI>
 __global__ void __launch_bounds__(V2_WARPS * 32) gemv2_kernel(const GemvParams p) {
