@@ -1,8 +1,11 @@
-"""CPU suite: the SOURCE of the kernels that have not run on a GPU yet (csrc/ua2_convtc.cu, csrc/ua2_resblock.cu) compiled
-with g++ against a thread-per-CUDA-thread shim (tests/cpu_shim/: OS threads, a barrier for __syncthreads, static __shared__)
-and executed through the product's own launchers, with the tensor-core GEMM replaced by a CPU GEMM.  Checks the kernels as
-written - shared-memory indexing, barriers, halo handling, chunk loops - against the conv oracle.  (Warp shuffles, bulk copies
-and tensor cores are outside the shim: kernels that use them are covered on the GPU only.)"""
+"""CPU suite: the kernel SOURCES of uniaudio2_b200/csrc compiled with g++ against a thread-per-CUDA-thread shim (tests/cpu_shim/:
+one OS thread per CUDA thread, barriers for __syncthreads / __syncwarp, warp shuffles, atomics, software bf16, emulated mbarrier +
+bulk copy, exactly-sized dynamic shared memory) and executed through the product's own launchers, with only the tensor-core GEMM
+replaced by a CPU GEMM.  Three builds: (1) the conv_tc / resblock kernels behind a small harness, (2) the kernel halves of
+ua2_stream.cu / ua2_dit.cu, (3) whole translation units with the real headers (-DUA2_CPU_SHIM) exporting their C-ABI operators,
+up to the complete codec handle.  It checks the kernels as written - shared-memory indexing, barriers, halos, ring parities,
+chunk loops - against the oracles and the reference's golden fixtures; tools/shim_asan.sh runs it under the address sanitizer.
+Outside the shim: tensor cores, clusters / DSMEM, the GPU's weak memory model."""
 import ctypes as C
 import math
 import os
