@@ -203,14 +203,64 @@ def time_dominant_kernel(model, hbm_peak, reps=3):
             "launch_us": round(us, 2), "bytes_per_launch": bytes_per_launch, "launches_timed": n}
 
 
-def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
+def host_threads():
+    """Host threads the CPU arm may use: the cores this process is allowed on, NOT torch's default - torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which made the round-1 reference arm run on one core for N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_greedy_frames(orc, tokens, mask, pos, n_frames):
+    """Full-size parity reference (BASELINE.md section 3 "parity alongside timing"): greedy (topk = 1) prefill + n_frames frames on the
+    CPU oracle; returns the sampled ids (n_frames, 9) and the smallest top-1 / top-2 logit margin of every sampled head."""
+    S = tokens.size(1)
+    audio_mask = torch.cat([torch.ones(1, 1, NQ, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1)
+    frames, margin = [], float("inf")
+    with torch.inference_mode():
+        orc.reset_caches()
+        orc.forward_prefix(tokens[:, :-1], mask, pos[:, :-1])
+        curr_tokens, curr_mask = tokens[:, -1:], mask[:, -1:]
+        for f in range(n_frames):
+            dbg = {}
+            s = orc.generate_frame(curr_tokens, curr_mask, torch.tensor([S - 1 + f]), S + f, 1.0, 1, 0, debug=dbg)
+            for lg in [dbg["text_logits"]] + list(dbg["ci_logits"]):
+                t2 = lg.float().topk(2, dim=-1)[0]
+                margin = min(margin, float((t2[..., 0] - t2[..., 1]).min()))
+            frames.append(s[0].clone())
+            sl = s.long()
+            curr_tokens = torch.cat([sl[:, 1:], sl[:, 0:1]], dim=-1).unsqueeze(1)
+            curr_mask = audio_mask
+    return torch.stack(frames), margin
+
+
+def gpu_greedy_frames_teacher_forced(model, tokens, mask, pos, ref_frames):
+    """The same greedy frames on the GPU model; every frame is fed the ORACLE's previous ids so that each frame compares on its own."""
+    dev = next(model.parameters()).device
+    S = tokens.size(1)
+    tok, msk, ps = tokens.to(dev), mask.to(dev), pos.to(dev)
+    audio_mask = torch.cat([torch.ones(1, 1, NQ, dtype=torch.bool), torch.zeros(1, 1, 1, dtype=torch.bool)], -1).to(dev)
+    model.reset_caches()
+    model.forward_prefix(tok[:, :-1], labels=None, tokens_mask=msk, loss_mask=None, input_pos=ps[:, :-1], input_pos_maxp1=S - 1)
+    curr_tokens, curr_mask = tok[:, -1:], msk[:, -1:]
+    out = []
+    for f in range(ref_frames.size(0)):
+        s = model.generate_frame(curr_tokens, curr_mask, input_pos=S - 1 + f, input_pos_maxp1=S + f, temperature=1.0, topk=1, forbid_prefix=0)
+        out.append(s[0].cpu())
+        sl = ref_frames[f:f + 1].long().to(dev)
+        curr_tokens = torch.cat([sl[:, 1:], sl[:, 0:1]], dim=-1).unsqueeze(1)
+        curr_mask = audio_mask
+    return torch.stack(out)
+
+
+def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None, parity_frames=0):
     """The reference's algorithm (oracle port: torch CPU fp32, same ATen ops as the reference) on the host cores.
     Bounded sample: one 39-position prefill + n_frames generate_frame calls at the start of the TTS-10 s schedule;
     the utterance time is extrapolated as prefill + 179 x mean frame time."""
     from oracle import llm_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads if threads else host_threads())
     cfg = O.full_size_cfg(REASON_CARD, SEMANTIC_CARD)
     orc = O.Stage3Oracle(cfg, state_dict_cpu)
     orc.setup_caches(1)
@@ -265,6 +315,9 @@ def cpu_baseline_sample(state_dict_cpu, n_frames=8, threads=None):
             times.append(one_frame())
     frame_t = sum(times[1:]) / len(times[1:])  # first frame = warm-up
     est = t_prefill + N_FRAMES * frame_t
+    if parity_frames:
+        ref_frames, margin = oracle_greedy_frames(orc, tokens, mask, pos, parity_frames)
+        cpu_baseline_sample.parity_ref = dict(tokens=tokens, mask=mask, pos=pos, frames=ref_frames, min_margin=margin)
     return {"value": round(NQ * N_FRAMES / est, 2), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"1 prefill({S - 1} pos, {t_prefill:.2f}s) + {n_frames} frames ({frame_t * 1e3:.0f} ms/frame, 1 warm-up frame discarded); "
                       f"utterance extrapolated to prefill + {N_FRAMES} frames = {est:.1f}s", "frame_ms": round(frame_t * 1e3, 1),
@@ -452,6 +505,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--parity-frames", type=int, default=8, help="greedy frames compared id-for-id with the CPU oracle at full size (N = 1)")
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--no-flow-decoder", action="store_true")
     ap.add_argument("--v3-cps", type=int, default=0)
@@ -615,7 +669,7 @@ def main():
                    "ms_per_step": round(ems / args.steps, 2)}
 
         hbm_peak, peak_src = load_peaks()
-        roofline = cpu_base = codec = flow = None
+        roofline = cpu_base = codec = flow = parity = None
         if rank == 0:
             roofline = time_dominant_kernel(model, hbm_peak)
             roofline["peak_source"] = peak_src
@@ -627,8 +681,15 @@ def main():
             if world == 1 and not args.no_cpu_baseline:
                 try:
                     sd = state_dict_to_cpu(model)
-                    cpu_base, _ = cpu_baseline_sample(sd, n_frames=args.cpu_frames)
+                    cpu_base, _ = cpu_baseline_sample(sd, n_frames=args.cpu_frames, parity_frames=args.parity_frames)
                     del sd
+                    ref = getattr(cpu_baseline_sample, "parity_ref", None)
+                    if ref is not None:  # full-size parity: the 4.86 B-parameter GPU model against the CPU oracle, id for id
+                        got = gpu_greedy_frames_teacher_forced(model, ref["tokens"], ref["mask"], ref["pos"], ref["frames"])
+                        neq = (got != ref["frames"]).any(dim=1)
+                        parity = {"frames": int(ref["frames"].size(0)), "ids_equal": bool(not neq.any()), "mismatched_frames": int(neq.sum()),
+                                  "ids_compared": int(ref["frames"].numel()), "min_margin": round(ref["min_margin"], 6),
+                                  "mode": "greedy topk=1, teacher-forced with the oracle's ids, prefill 39 positions"}
                 except Exception as e:  # noqa: BLE001  (e.g. host memory): report it instead of losing the GPU measurement
                     cpu_base = {"error": f"{type(e).__name__}: {e}", "kind": "port"}
             if world == 1 and not args.no_codec:
@@ -645,8 +706,8 @@ def main():
         print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
-                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "codec": codec,
-                          "flow_decoder": flow}))
+                          "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
+                          "codec": codec, "flow_decoder": flow}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -148,6 +148,11 @@ int ua2_llm_last_launch_count(ua2_llm* h);
  *   residual != NULL : y += residual (Block.forward residual adds, lit_model.py:344-349)        */
 int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float eps, const float* residual, float* y,
                    int M, int N, int K, void* stream);
+/* The same linear (W2 == NULL; optional RMSNorm prologue and residual) or SwiGLU pair (W2 != NULL) forced onto the tensor-core
+ * path for any M: tcgen05 3xTF32 with the fp32 weights split on chip (csrc/ua2_umma.cu) - what forward_prefix
+ * (model_new.py:456-507) and batched frames use for M >= tc_min_rows.  Scratch is owned by the library. */
+int ua2_tc_linear_f32(const float* x, const float* W, const float* W2, const float* norm_w, float eps, const float* residual, float* y,
+                      int M, int N, int K, void* stream);
 /* y[m, n] = silu(sum_k f(x) W1[n,k]) * (sum_k f(x) W2[n,k])   (LLaMAMLP fc_1/fc_2, lit_model.py:591-594) */
 int ua2_swiglu_f32(const float* x, const float* W1, const float* W2, const float* norm_w, float eps, float* y, int M,
                    int N, int K, void* stream);

@@ -105,6 +105,26 @@ def test_reset_caches_zero_fills(models):
         assert float(k.abs().sum()) == 0.0 and float(v.abs().sum()) == 0.0
 
 
+def test_weights_loaded_after_setup_caches_are_used():
+    """The handle keeps raw parameter pointers and a transposed audio_head copy: load_state_dict / .to() after setup_caches
+    must not leave it stale (round-1 advisor finding).  Both drop the handle; after a new setup_caches the ids follow the NEW weights."""
+    cfg = tiny_cfgs()["tiny"]
+    sd_a, sd_b = O.random_state_dict(cfg, seed=1), O.random_state_dict(cfg, seed=2)
+    m = build_product_model(cfg, sd_a, "cuda", 1)
+    m.load_state_dict(sd_b, strict=True)
+    with pytest.raises(TypeError):
+        m.reset_caches()
+    m.setup_caches(1)
+    orc = O.Stage3Oracle(cfg, sd_b)
+    orc.setup_caches(1)
+    got = run_case(m, "text", cfg, 1, 8, 3, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, True, device="cuda")
+    ref = run_case(orc, "text", cfg, 1, 8, 3, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, False)
+    assert torch.equal(got["frames"].cpu(), ref["frames"])
+    m.float()  # _apply: the tensors may have moved
+    with pytest.raises(TypeError):
+        m.reset_caches()
+
+
 def test_error_behaviour(models):
     """ValueError cases of model_new.py:165-180 and the position range check of lit_model.py:143-144."""
     cfg, sd, m = models["tiny"]

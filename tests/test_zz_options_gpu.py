@@ -1,4 +1,4 @@
-"""GPU tests written after round 1's GPU budget was spent (opt-in, see the guard below).
+"""GPU tests of the kernels behind options (first run on a B200 in round 2: gpurun_out/r2_first, profiles/r2_first_call.md).
 
 (1) GPU parity of the codes -> waveform caller: uniaudio2_b200's AudioDiffusion1D.inference_codes (code lookups, projections,
 flow-matching solve through the C ABI) under the product's ReasoningTokenizer.token2audio_no_reason, against the fixtures that
@@ -26,11 +26,7 @@ from oracle import detok_oracle as TO
 from oracle import dit_oracle as DO
 from oracle.make_golden_detok import CB_DIM, CB_SIZE, CODEC_DIM, DIT, VQS, random_params
 
-# Written after round 1's GPU budget was spent: these two tests have never run on a B200.  They are opt-in until they have
-# (UA2_RUN_UNVERIFIED=1 python -m pytest tests/test_zzz_unverified_gpu.py -m gpu) so that an unproven test cannot mask the proven suite;
-# the first GPU call of the next round runs them and removes this guard.
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("UA2_RUN_UNVERIFIED") != "1",
-                                                  reason="never run on a B200 yet (round-1 GPU budget exhausted): set UA2_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-4
 
@@ -176,8 +172,12 @@ def test_conv_tc_option_matches_oracle(B, Cin, Cout, T, K, stride, elu, res, rep
             outs.append(y.cpu())
     finally:
         _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
-    for y in outs:
-        assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    # the SIMT core meets 2e-5; the tensor-core accumulator (TMEM, fp32) rounds toward zero at every k-step of 8, a bias of about
+    # steps / 2 ulp of the running sum (measured on the B200: 2.4e-5 relative at Cin * K = 2048, i.e. 768 steps of the 3x longer
+    # inner dimension) - bar 1.5 * steps * 2^-24
+    tc_tol = max(2e-5, 1.5 * (3 * Cin * K / 8) * 2.0 ** -24)
+    for y, tol in zip(outs, (2e-5, tc_tol)):
+        assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
     if Cin * K < 1024:
         assert torch.equal(outs[0], outs[1])
 
@@ -289,15 +289,15 @@ def test_fused_resblock_matches_oracle(B, T):
     b2 = torch.randn(C, generator=g) * 0.1
     hid = CO.conv1d_causal(F.elu(x), w1, b1)
     ref = x + CO.conv1d_causal(F.elu(hid), w2, b2)
-    xd = x.cuda()
+    # device operands are named: a temporary `w.cuda()` inside the call would be freed (and its block reused by the next
+    # temporary) before the kernel runs - that, not the kernel, failed the first hardware run of this test
+    xd, w1d, b1d, w2d, b2d = x.cuda(), w1.cuda(), b1.cuda(), w2.contiguous().cuda(), b2.cuda()
     y = torch.full_like(xd, float("nan"))
-    _lib.check(L.ua2_resblock_f32(_lib.ptr(xd), _lib.ptr(w1.cuda()), _lib.ptr(b1.cuda()), _lib.ptr(w2.contiguous().cuda()), _lib.ptr(b2.cuda()),
-                                  _lib.ptr(y), B, C, H, T, None))
+    _lib.check(L.ua2_resblock_f32(_lib.ptr(xd), _lib.ptr(w1d), _lib.ptr(b1d), _lib.ptr(w2d), _lib.ptr(b2d), _lib.ptr(y), B, C, H, T, None))
     torch.cuda.synchronize()
     assert float((y.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
     with pytest.raises(ValueError):
-        _lib.check(L.ua2_resblock_f32(_lib.ptr(xd), _lib.ptr(w1.cuda()), _lib.ptr(b1.cuda()), _lib.ptr(w2.cuda()), _lib.ptr(b2.cuda()), _lib.ptr(y),
-                                      B, 128, 64, T, None))
+        _lib.check(L.ua2_resblock_f32(_lib.ptr(xd), _lib.ptr(w1d), _lib.ptr(b1d), _lib.ptr(w2d), _lib.ptr(b2d), _lib.ptr(y), B, 128, 64, T, None))
 
 
 def test_resblock_fused_option_keeps_codec_results():

@@ -141,21 +141,21 @@ def main():
                               frac_of_roofline=round(t_roof / ms, 3))))
     _lib.check(L.ua2_set_global_option(b"conv_tc", 0))
     if "--resblock" in sys.argv:  # the 64-channel residual block at 24 kHz: two implicit GEMMs vs the fused kernel
-        C, H, T = 64, 32, T0
-        x = torch.randn(Bc, C, T, device=dev)
-        w1 = torch.randn(H, C, 3, device=dev) / (C * 3) ** 0.5
-        w2 = torch.randn(C, H, 1, device=dev) / H ** 0.5
-        b1, b2 = torch.zeros(H, device=dev), torch.zeros(C, device=dev)
-        hid, yb = torch.empty(Bc, H, T, device=dev), torch.empty(Bc, C, T, device=dev)
+        Cc, H, T = 64, 32, T0
+        x = torch.randn(Bc, Cc, T, device=dev)
+        w1 = torch.randn(H, Cc, 3, device=dev) / (Cc * 3) ** 0.5
+        w2 = torch.randn(Cc, H, 1, device=dev) / H ** 0.5
+        b1, b2 = torch.zeros(H, device=dev), torch.zeros(Cc, device=dev)
+        hid, yb = torch.empty(Bc, H, T, device=dev), torch.empty(Bc, Cc, T, device=dev)
 
         def two(i):
-            _lib.check(L.ua2_conv1d_causal_gemm_f32(P(x), P(w1), P(b1), None, P(hid), Bc, C, H, T, 3, 1, 1, 1, 0, None))
-            _lib.check(L.ua2_conv1d_causal_gemm_f32(P(hid), P(w2), P(b2), P(x), P(yb), Bc, H, C, T, 1, 1, 1, 1, 0, None))
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(P(x), P(w1), P(b1), None, P(hid), Bc, Cc, H, T, 3, 1, 1, 1, 0, None))
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(P(hid), P(w2), P(b2), P(x), P(yb), Bc, H, Cc, T, 1, 1, 1, 1, 0, None))
 
         def fused(i):
-            _lib.check(L.ua2_resblock_f32(P(x), P(w1), P(b1), P(w2), P(b2), P(yb), Bc, C, H, T, None))
+            _lib.check(L.ua2_resblock_f32(P(x), P(w1), P(b1), P(w2), P(b2), P(yb), Bc, Cc, H, T, None))
 
-        fl = 2.0 * Bc * T * (C * H * 3 + H * C)
+        fl = 2.0 * Bc * T * (Cc * H * 3 + H * Cc)
         for name, fn in (("two implicit GEMMs", two), ("fused (ua2_resblock_f32)", fused)):
             ms = timed(fn, 10)
             print(json.dumps(dict(kernel="SEANet resblock 64 -> 32 -> 64 @ 24 kHz", impl=name, ms=round(ms, 3), GFLOP=round(fl / 1e9, 1),

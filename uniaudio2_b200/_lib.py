@@ -66,6 +66,7 @@ SYMBOLS = {
     "ua2_llm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ua2_llm_last_launch_count": (C.c_int, [_P]),
     "ua2_linear_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_tc_linear_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_swiglu_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_qkv_rope_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, _P]),

@@ -186,7 +186,7 @@ int reserve_tc(ua2_codec* h, size_t M) {
   }
   const size_t kmax = std::max(C, F), nmax = std::max(3 * C, F);
   h->tc.a_floats = M * 3 * kmax;
-  h->tc.w_floats = std::max({3 * C * 3 * C, F * 3 * C, C * 3 * F, C * 3 * C});
+  h->tc.w_floats = std::max({3 * C * 3 * C, F * 3 * C, C * 3 * F, C * 3 * C, tc_slots_max_floats()});
   h->tc.c_floats = M * nmax;
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.a, h->tc.a_floats * 4));
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.w, h->tc.w_floats * 4));

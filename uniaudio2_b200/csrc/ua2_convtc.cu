@@ -148,7 +148,7 @@ struct ConvTcScratch {
   TcWorkspace tc;
 };
 ConvTcScratch g_ws;
-int g_conv_tc = 0;
+int g_conv_tc = 1;  // default since round 2 (first hardware run: profiles/r2_first_call.md)
 
 cudaError_t grow(float** p, size_t* have, size_t want) {
   if (want <= *have) return cudaSuccess;
@@ -186,7 +186,7 @@ cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w
   if ((e = grow(&g_ws.a, &g_ws.a_floats, (size_t)R * KT)) != cudaSuccess) return e;
   if ((e = grow(&g_ws.c, &g_ws.c_floats, (size_t)R * Cout)) != cudaSuccess) return e;
   if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 3 * KT)) != cudaSuccess) return e;
-  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, (size_t)Cout * 3 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, std::max((size_t)Cout * 3 * KT, tc_slots_max_floats()))) != cudaSuccess) return e;
   if ((e = grow(&g_ws.tc.c, &g_ws.tc.c_floats, (size_t)R * Cout)) != cudaSuccess) return e;
   if (!g_ws.tc.cache) g_ws.tc.cache = tc_cache_create();
   g_ws.tc.force_persistent = true;  // codec weights are long-lived: keep their tf32 split (12 B per parameter)
@@ -245,7 +245,7 @@ cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float*
   if ((e = grow(&g_ws.a, &g_ws.a_floats, (size_t)R * KT)) != cudaSuccess) return e;
   if ((e = grow(&g_ws.c, &g_ws.c_floats, (size_t)R * N)) != cudaSuccess) return e;
   if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 3 * KT)) != cudaSuccess) return e;
-  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, (size_t)N * 3 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, std::max((size_t)N * 3 * KT, tc_slots_max_floats()))) != cudaSuccess) return e;
   if ((e = grow(&g_ws.tc.c, &g_ws.tc.c_floats, (size_t)R * N)) != cudaSuccess) return e;
   if (!g_ws.tc.cache) g_ws.tc.cache = tc_cache_create();
   g_ws.tc.force_persistent = true;

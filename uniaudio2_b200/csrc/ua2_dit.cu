@@ -474,7 +474,7 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
     if (tc_gemm_available()) {  // scratch of the tcgen05 3xTF32 path: split activations / weights, raw product
       const size_t kmax = std::max({3 * I, 4 * D, 3 * D}), nmax = std::max({4 * D, 3 * D, O});
       h->tc.a_floats = M * 3 * kmax;
-      h->tc.w_floats = std::max({D * 9 * I, 3 * D * 3 * D, 4 * D * 3 * D, D * 12 * D, O * 9 * D, O * 3 * O});
+      h->tc.w_floats = std::max({D * 9 * I, 3 * D * 3 * D, 4 * D * 3 * D, D * 12 * D, O * 9 * D, O * 3 * O, tc_slots_max_floats()});
       h->tc.c_floats = M * nmax;
       RUN(dmalloc(&h->tc.a, h->tc.a_floats));
       RUN(dmalloc(&h->tc.w, h->tc.w_floats));

@@ -118,6 +118,9 @@ int gemv3_make_pf(const GemvSeqEntry* next, int n_next, size_t budget_bytes, PfS
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
 cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, float* stats_ws);
 cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
+void set_tc_impl(int v);
+int get_tc_impl();
+size_t tc_slots_max_floats();  // side-slot scratch (TcWorkspace::w) the hand-written mainloop may need: 148 CTAs x 256 x 128 floats
 void set_tc_gemm(int v);
 int get_tc_gemm();
 bool tc_gemm_available();

@@ -821,7 +821,7 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
       nmax = std::max({nmax, QKV, Dm, 2 * F});
     }
     h->tcws.a_floats = (size_t)Mc * 3 * kmax;
-    h->tcws.w_floats = wmax;
+    h->tcws.w_floats = std::max(wmax, tc_slots_max_floats());
     const size_t nheads = std::max({nmax, (size_t)h->cfg.text_vocab, (size_t)h->cfg.audio_vocab});
     h->tcws.c_floats = std::max((size_t)Mc * nmax, (size_t)B * nheads);  // prefill passes never run the heads; frames have M <= B
     h->tcws.cache = tc_cache_create();

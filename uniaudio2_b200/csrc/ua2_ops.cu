@@ -40,6 +40,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_tc_gemm(value);
     return UA2_OK;
   }
+  if (std::string(name) == "tc_impl") {  // 1 = hand-written tcgen05 mainloop (ua2_umma.cu), 0 = library collective (A/B only)
+    set_tc_impl(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "resblock_fused") {
     set_resblock_fused(value);
     return UA2_OK;
@@ -105,6 +109,57 @@ int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float ep
   p.ldr = N;
   if (int rc = ops_ws(p)) return rc;
   UA2_CHECK_CUDA(launch_gemv(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, residual ? EPI_RESADD : EPI_STORE, p));
+  return UA2_OK;
+}
+
+// Many-row linear forced onto the tensor-core path (ua2_tcgemm.cu / ua2_umma.cu) whatever M is; scratch owned by the library.
+static TcWorkspace g_tc_op_ws;
+static int tc_op_ws(size_t a, size_t c) {
+  auto grow = [](float** p, size_t* have, size_t want) -> cudaError_t {
+    if (want <= *have) return cudaSuccess;
+    if (*p) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return e;
+      cudaFree(*p);
+      *p = nullptr;
+      *have = 0;
+    }
+    cudaError_t e = cudaMalloc((void**)p, want * sizeof(float));
+    if (e == cudaSuccess) *have = want;
+    return e;
+  };
+  UA2_CHECK_CUDA(grow(&g_tc_op_ws.a, &g_tc_op_ws.a_floats, a));
+  UA2_CHECK_CUDA(grow(&g_tc_op_ws.c, &g_tc_op_ws.c_floats, c));
+  UA2_CHECK_CUDA(grow(&g_tc_op_ws.w, &g_tc_op_ws.w_floats, tc_slots_max_floats()));
+  return UA2_OK;
+}
+
+int ua2_tc_linear_f32(const float* x, const float* W, const float* W2, const float* norm_w, float eps, const float* residual, float* y, int M,
+                      int N, int K, void* stream) {
+  UA2_REQUIRE(x && W && y, "null argument");
+  UA2_REQUIRE(M >= 1 && N >= 4 && (N % 4) == 0 && K >= 4 && (K % 4) == 0, "need M>=1, N % 4 == 0, K % 4 == 0");
+  UA2_REQUIRE(!(W2 && residual), "SwiGLU form takes no residual");
+  UA2_REQUIRE(get_tc_impl() == 1, "ua2_tc_linear_f32 serves the hand-written mainloop (option tc_impl = 1)");
+  const int Ntot = W2 ? 2 * N : N;
+  if (int rc = tc_op_ws((size_t)M * 3 * K, (size_t)M * Ntot)) return rc;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  GemvParams p;
+  p.W = W;
+  p.W2 = W2;
+  p.N = N;
+  p.K = K;
+  p.M = M;
+  p.X = x;
+  p.ldx = K;
+  p.norm_w = norm_w;
+  p.eps = eps;
+  p.Y = y;
+  p.ldy = N;
+  p.R = residual;
+  p.ldr = N;
+  p.tc = &g_tc_op_ws;
+  UA2_CHECK_CUDA(launch_tc_linear(lc, norm_w ? PRO_RMSNORM : PRO_PLAIN, W2 ? EPI_SWIGLU : residual ? EPI_RESADD : EPI_STORE, p));
   return UA2_OK;
 }
 

@@ -22,6 +22,7 @@
 
 #include "ua2_gemv_dev.cuh"
 #include "ua2_kernels.cuh"
+#include "ua2_umma.cuh"
 
 
 namespace ua2 {
@@ -40,8 +41,9 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 }
 
 // one CTA per activation row
+// planes = 0: A3 = [hi | lo | hi] rows of 3K (library mainloop); planes = 1: [2][M][K] hi / lo planes (ua2_umma.cu)
 template <int PRO>
-__global__ void __launch_bounds__(256) tc_split_a_kernel(const GemvParams p, float* __restrict__ A3) {
+__global__ void __launch_bounds__(256) tc_split_a_kernel(const GemvParams p, float* __restrict__ A3, int planes) {
   __shared__ float red[8];
   pdl_launch_dependents();
   pdl_wait();
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(256) tc_split_a_kernel(const GemvParams p, flo
     for (int w = 0; w < 8; ++w) tot += red[w];
     rs = rsqrtf(tot / (float)K + p.eps);
   }
-  float* out = A3 + (size_t)m * 3 * K;
+  float* out = planes ? A3 + (size_t)m * K : A3 + (size_t)m * 3 * K;
+  const size_t lo_off = planes ? (size_t)p.M * K : (size_t)K;
   for (int k = tid * 4; k < K; k += 256 * 4) {
     float4 v = *reinterpret_cast<const float4*>(src + k);
     if (PRO == PRO_RMSNORM) {
@@ -111,8 +114,8 @@ __global__ void __launch_bounds__(256) tc_split_a_kernel(const GemvParams p, flo
     float4 hi, lo;
     split4(v, hi, lo);
     *reinterpret_cast<float4*>(out + k) = hi;
-    *reinterpret_cast<float4*>(out + K + k) = lo;
-    *reinterpret_cast<float4*>(out + 2 * K + k) = hi;
+    *reinterpret_cast<float4*>(out + lo_off + k) = lo;
+    if (!planes) *reinterpret_cast<float4*>(out + 2 * K + k) = hi;
   }
 }
 
@@ -136,10 +139,11 @@ __global__ void __launch_bounds__(256) tc_split_w_kernel(const float* __restrict
 
 // thread = (row m, output unit u): the pair of sums the skinny kernels' epilogue expects, read back from C
 template <int EPI>
-__global__ void __launch_bounds__(256) tc_epilogue_kernel(const GemvParams p, const float* __restrict__ C, int ldc, int n_units) {
+__global__ void __launch_bounds__(256) tc_epilogue_kernel(const GemvParams p, const float* __restrict__ C, int ldc, int n_units,
+                                                          const float* __restrict__ slots, const UmmaPlan pl) {
   pdl_launch_dependents();
   pdl_wait();
-  const int u = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  const int u = blockIdx.y * blockDim.x + threadIdx.x, m = blockIdx.x;  // rows on grid.x: no 65535 limit
   if (u >= n_units) return;
   int nA, nB, cA, cB;
   if (EPI == EPI_SWIGLU) {
@@ -159,7 +163,11 @@ __global__ void __launch_bounds__(256) tc_epilogue_kernel(const GemvParams p, co
     cA = nA;
     cB = nB;
   }
-  const float a = C[(size_t)m * ldc + cA], b = C[(size_t)m * ldc + cB];
+  float a = C[(size_t)m * ldc + cA], b = C[(size_t)m * ldc + cB];
+  if (slots != nullptr) {  // stream-K tiles continued by other CTAs (ua2_umma.cuh)
+    a += umma_side_sum(pl, slots, m, cA, p.N);
+    b += umma_side_sum(pl, slots, m, cB, p.N);
+  }
   epilogue<EPI>(p, 0, 1, m, a, b, nA, nB);
 }
 
@@ -176,11 +184,8 @@ cudaError_t run_tf32_gemm(cudaStream_t st, const float* A, const float* B, float
 }
 #endif
 
-#ifdef UA2_HAVE_CUTLASS
 int g_tc_gemm = 1;  // many-row linears (M >= tc_min_rows) on tcgen05; 0 = fp32 SIMT tiles (ua2_sgemm.cu)
-#else
-int g_tc_gemm = 0;
-#endif
+int g_tc_impl = 1;  // 1 = hand-written tcgen05 mainloop with the on-chip weight split (ua2_umma.cu); 0 = library collective over pre-split copies
 int g_tc_persistent = 0;
 int g_tc_min_rows = 32;  // measured at 32 rows: 61 ms (skinny kernels, weights re-streamed per 8-row tile) -> 35 ms per frame
 
@@ -206,21 +211,15 @@ int get_tc_persistent() { return g_tc_persistent; }
 void set_tc_min_rows(int v) { g_tc_min_rows = v < 1 ? 1 : v; }
 int get_tc_min_rows() { return g_tc_min_rows; }
 
+void set_tc_impl(int v) { g_tc_impl = v ? 1 : 0; }
+int get_tc_impl() { return g_tc_impl; }
+size_t tc_slots_max_floats() { return (size_t)148 * 256 * 128; }
 void set_tc_gemm(int v) { g_tc_gemm = v ? 1 : 0; }
 int get_tc_gemm() { return g_tc_gemm; }
-bool tc_gemm_available() {
-#ifdef UA2_HAVE_CUTLASS
-  return true;
-#else
-  return false;
-#endif
-}
+bool tc_gemm_available() { return true; }  // the hand-written mainloop needs no third-party headers
 
 // returns cudaErrorNotSupported when this (pro, epi, shape, workspace) is not served (caller falls back to the SIMT core)
 cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p) {
-#ifndef UA2_HAVE_CUTLASS
-  return cudaErrorNotSupported;
-#else
   if (p.tc == nullptr || (p.K & 3) || (p.ldx & 3)) return cudaErrorNotSupported;
   if (!(pro == PRO_PLAIN || pro == PRO_RMSNORM || pro == PRO_GATHER || pro == PRO_LAYERNORM)) return cudaErrorNotSupported;
   if (!(epi == EPI_STORE || epi == EPI_RESADD || epi == EPI_SWIGLU || epi == EPI_QKV || epi == EPI_GELU || epi == EPI_SCALE_RESADD ||
@@ -230,6 +229,42 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   const int M = p.M, K = p.K, K3 = 3 * p.K;
   const int Ntot = epi == EPI_SWIGLU ? 2 * p.N : p.N;
   if ((Ntot & 3) || (size_t)M * K3 > ws.a_floats || (size_t)M * Ntot > ws.c_floats) return cudaErrorNotSupported;
+  if (g_tc_impl == 1) {
+    const UmmaPlan pl = umma_plan(M, p.N, epi == EPI_SWIGLU ? 2 : 1, K);
+    if (pl.slot_floats > ws.w_floats) return cudaErrorNotSupported;
+    cudaError_t e = cudaErrorNotSupported;
+#define UA2_TCA(P) \
+  if (pro == P) e = launch(lc, tc_split_a_kernel<P>, dim3(M), dim3(256), 0, p, ws.a, 1);
+    UA2_TCA(PRO_PLAIN)
+    UA2_TCA(PRO_RMSNORM)
+    UA2_TCA(PRO_GATHER)
+    UA2_TCA(PRO_LAYERNORM)
+#undef UA2_TCA
+    if (e != cudaSuccess) return e;
+    if ((e = run_umma_tf32x3(lc, ws.a, p.W, epi == EPI_SWIGLU ? p.W2 : nullptr, ws.c, Ntot, ws.w, M, p.N, K, pl)) != cudaSuccess) return e;
+    if (p.raw_out != nullptr && epi == EPI_STORE) {  // the caller's own epilogue consumes the product in place
+      if ((e = run_umma_fixup(lc, ws.c, Ntot, ws.w, M, p.N, 1, pl)) != cudaSuccess) return e;
+      *p.raw_out = ws.c;
+      return cudaSuccess;
+    }
+    const float* slots = (pl.L % pl.KB) ? ws.w : nullptr;
+    const int n_units = epi == EPI_SWIGLU ? p.N : p.N / 2;
+    const dim3 grid(M, (n_units + 255) / 256);
+#define UA2_TCE(E) \
+  if (epi == E) return launch(lc, tc_epilogue_kernel<E>, grid, dim3(256), 0, p, (const float*)ws.c, Ntot, n_units, slots, pl);
+    UA2_TCE(EPI_STORE)
+    UA2_TCE(EPI_RESADD)
+    UA2_TCE(EPI_SWIGLU)
+    UA2_TCE(EPI_QKV)
+    UA2_TCE(EPI_GELU)
+    UA2_TCE(EPI_SCALE_RESADD)
+    UA2_TCE(EPI_QKV_IL)
+#undef UA2_TCE
+    return cudaErrorNotSupported;
+  }
+#ifndef UA2_HAVE_CUTLASS
+  return cudaErrorNotSupported;
+#else
   // where the split weights live: the persistent cache (filled on first use, outside any stream capture) or scratch
   const float* w3 = nullptr;
   bool need_split = true;
@@ -260,7 +295,7 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   }
   cudaError_t e;
 #define UA2_TCA(P) \
-  if (pro == P) e = launch(lc, tc_split_a_kernel<P>, dim3(M), dim3(256), 0, p, ws.a);
+  if (pro == P) e = launch(lc, tc_split_a_kernel<P>, dim3(M), dim3(256), 0, p, ws.a, 0);
   e = cudaErrorNotSupported;
   UA2_TCA(PRO_PLAIN)
   UA2_TCA(PRO_RMSNORM)
@@ -283,9 +318,9 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
     return cudaSuccess;
   }
   const int n_units = epi == EPI_SWIGLU ? p.N : p.N / 2;
-  const dim3 grid((n_units + 255) / 256, M);
+  const dim3 grid(M, (n_units + 255) / 256);
 #define UA2_TCE(E) \
-  if (epi == E) return launch(lc, tc_epilogue_kernel<E>, grid, dim3(256), 0, p, (const float*)ws.c, Ntot, n_units);
+  if (epi == E) return launch(lc, tc_epilogue_kernel<E>, grid, dim3(256), 0, p, (const float*)ws.c, Ntot, n_units, (const float*)nullptr, UmmaPlan());
   UA2_TCE(EPI_STORE)
   UA2_TCE(EPI_RESADD)
   UA2_TCE(EPI_SWIGLU)

@@ -1,0 +1,456 @@
+// Hand-written tcgen05 / TMEM / TMA mainloop for the many-row linears of the path (lit_model.py:424, 511, 592-595 F.linear;
+// conv.py:232-254 as implicit GEMM; transformer_1d_flow.py linears) with fp32-class accuracy: "3xTF32, split on chip".
+//
+//   C (M x N) = X (M x K) * W (N x K)^T,  fp32 in HBM, every product evaluated as  X_hi W_hi + X_hi W_lo + X_lo W_hi  with
+//   x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi)   (the dropped lo*lo term is ~2^-22 relative), fp32 accumulation in TMEM.
+//
+// Why not a library mainloop (round 1 used a CUTLASS collective over pre-split copies [hi|hi|lo]): the weights are the big
+// operand (4 B / parameter, 12.4 GB per batch-32 decode frame) and a library mainloop cannot split them on chip - round 1 paid
+// 12-28 B of HBM / L2 traffic per parameter.  Here the fp32 weight tile is loaded ONCE by TMA and split by four warps between
+// shared memory and tensor memory, which is exactly what the tcgen05 "A operand from TMEM" form exists for.
+//
+// Swap-AB: the MMA's M dimension (128 TMEM lanes) carries 128 weight rows, its N dimension the activation rows (NT = 32 .. 256),
+// so a decode batch of 32 rows is one N = 32 instruction instead of a 75 % empty M = 128 tile.
+//
+//   warp 0      TMA producer (one thread): W tile 128 x 32 fp32 (box {32, 128}, SWIZZLE_128B) into the W ring; X_hi / X_lo tiles
+//               NT x 32 (pre-split by tc_split_a_kernel, which also carries the RMSNorm / LayerNorm / gather prologue) into the X ring
+//   warps 2-5   splitter: thread = weight row; 8 x LDS.128 of the swizzled row, cvt.rna.tf32 split, two tcgen05.st 32x32b.x32
+//               -> TMEM columns [slot * 64, +32) = hi, [+32, +64) = lo; releases the W stage as soon as it is in registers
+//   warp 1      MMA issuer (one thread): per k-step of 8:  D += A_hi B_hi;  D += A_lo B_hi;  D += A_hi B_lo   with
+//               tcgen05.mma.cta_group::1.kind::tf32 [D tmem], [A tmem], B smem-descriptor (K-major, SWIZZLE_128B);
+//               tcgen05.commit releases the X stage and the TMEM A slot, and at the end of a tile hands D to the epilogue
+//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 of D (lane = weight row n, column = activation row m) -> C[m][n], coalesced over n
+//
+// Scheduling is stream-K over the flattened (tile, k-block) space: CTA c owns units [c L, (c + 1) L), so every SM streams the same
+// number of weight bytes whatever N / 128 is.  A CTA whose range starts inside a tile writes that partial tile to its side slot;
+// the consumer (tc_epilogue_kernel / umma_fixup_kernel) adds the slots of the continuation CTAs in CTA order - deterministic.
+//
+// TMEM budget (512 columns): A ring 4 slots x 64 columns, accumulator NT columns at column 256.
+#include <cuda.h>
+
+#include "ua2_kernels.cuh"
+#include "ua2_umma.cuh"
+
+namespace ua2 {
+namespace {
+
+constexpr int UM_BM = 128;        // weight rows per tile (TMEM lanes)
+constexpr int UM_BK = 32;         // fp32 per k-block = one 128-byte swizzle row
+constexpr int UM_A_SLOTS = 4;     // TMEM A ring
+constexpr int UM_ACC_COL = 256;   // accumulator base column
+constexpr int UM_THREADS = 320;
+constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
+
+template <int NT>
+struct UmCfg {
+  static constexpr int SW = NT <= 32 ? 8 : NT <= 64 ? 6 : NT <= 128 ? 4 : 2;  // W ring stages (16 KB each)
+  static constexpr int SX = NT <= 32 ? 8 : NT <= 64 ? 6 : NT <= 128 ? 4 : 3;  // X ring stages (2 * NT * 128 B each)
+  static constexpr int W_BYTES = UM_BM * UM_BK * 4;
+  static constexpr int XH_BYTES = NT * UM_BK * 4;
+  static constexpr int X_BYTES = 2 * XH_BYTES;
+  static constexpr int N_BARS = 2 * SW + 2 * SX + 2 * UM_A_SLOTS + 2;
+  static constexpr size_t SMEM = 1024 + (size_t)SW * W_BYTES + (size_t)SX * X_BYTES + N_BARS * 8 + 16;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_addr_u32(dst)),
+      "l"(tm), "r"(smem_addr_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_addr_u32(dst)),
+      "l"(tm), "r"(smem_addr_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 operands, fp32 accumulate; `acc` = 0 overwrites D
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes (32 tf32), SWIZZLE_128B: 8-row groups 1024 B apart
+// (stride byte offset 64 x 16 B), descriptor version 1 (sm_100), layout type 2; advancing k by 8 elements adds 32 B to the start
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct UmSched {
+  int KB;        // k-blocks per tile
+  int n_nt;      // weight tiles (both matrices)
+  int nt_per_mat;
+  int n_tiles;   // n_mt * n_nt
+  long long L;   // units per CTA
+  long long total;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int NT>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                   float* __restrict__ C, int ldc, float* __restrict__ slots, int M, int N, const UmSched sc) {
+  using Cfg = UmCfg<NT>;
+  extern __shared__ uint8_t um_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
+  uint8_t* w_ring = base;
+  uint8_t* x_ring = w_ring + (size_t)Cfg::SW * Cfg::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + (size_t)Cfg::SX * Cfg::X_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + Cfg::SW;
+  uint64_t* x_full = w_empty + Cfg::SW;
+  uint64_t* x_empty = x_full + Cfg::SX;
+  uint64_t* a_full = x_empty + Cfg::SX;
+  uint64_t* a_empty = a_full + UM_A_SLOTS;
+  uint64_t* acc_full = a_empty + UM_A_SLOTS;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u_begin = (long long)blockIdx.x * sc.L;
+  const long long u_end = u_begin + sc.L < sc.total ? u_begin + sc.L : sc.total;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < Cfg::SW; ++i) {
+      smem_bar_init(&w_full[i], 1);
+      smem_bar_init(&w_empty[i], 4);
+    }
+    for (int i = 0; i < Cfg::SX; ++i) {
+      smem_bar_init(&x_full[i], 1);
+      smem_bar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < UM_A_SLOTS; ++i) {
+      smem_bar_init(&a_full[i], 4);
+      smem_bar_init(&a_empty[i], 1);
+    }
+    smem_bar_init(acc_full, 1);
+    smem_bar_init(acc_empty, 4);
+    smem_bar_fence_init();
+  }
+  if (warp == 1) {  // one warp owns the tensor-memory allocation (all 512 columns: one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(tmem_base_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_smem;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ================= TMA producer
+    if (lane == 0 && u_begin < u_end) {
+      pdl_wait();  // X planes come from the preceding split kernel
+      long long it = 0;
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int t = (int)(u / sc.KB), kb = (int)(u - (long long)t * sc.KB);
+        const int mt = t / sc.n_nt, nt = t - mt * sc.n_nt;
+        const int mat = nt / sc.nt_per_mat, row0 = (nt - mat * sc.nt_per_mat) * UM_BM;
+        const int sw = (int)(it % Cfg::SW), sx = (int)(it % Cfg::SX);
+        const uint32_t pw = (uint32_t)((it / Cfg::SW) & 1), px = (uint32_t)((it / Cfg::SX) & 1);
+        smem_bar_wait(&w_empty[sw], pw ^ 1);
+        smem_bar_arrive_expect_tx(&w_full[sw], Cfg::W_BYTES);
+        tma_load_2d(w_ring + (size_t)sw * Cfg::W_BYTES, mat ? &tmW2 : &tmW, kb * UM_BK, row0, &w_full[sw], POLICY_EVICT_FIRST);
+        smem_bar_wait(&x_empty[sx], px ^ 1);
+        smem_bar_arrive_expect_tx(&x_full[sx], Cfg::X_BYTES);
+        uint8_t* xs = x_ring + (size_t)sx * Cfg::X_BYTES;
+        tma_load_3d(xs, &tmX, kb * UM_BK, mt * NT, 0, &x_full[sx], POLICY_EVICT_LAST);
+        tma_load_3d(xs + Cfg::XH_BYTES, &tmX, kb * UM_BK, mt * NT, 1, &x_full[sx], POLICY_EVICT_LAST);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer
+    if (lane == 0 && u_begin < u_end) {
+      // instruction descriptor: D fp32 (bit 4), A/B tf32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+      const uint32_t d_tmem = tmem + UM_ACC_COL;
+      long long it = 0;
+      int tile_j = 0;
+      int cur_t = -1;
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int t = (int)(u / sc.KB);
+        const bool first_of_tile = t != cur_t;
+        if (first_of_tile) {
+          cur_t = t;
+          smem_bar_wait(acc_empty, (uint32_t)((tile_j & 1) ^ 1));  // the epilogue has drained the previous tile
+          tc_fence_after();
+        }
+        const int sx = (int)(it % Cfg::SX), sa = (int)(it % UM_A_SLOTS);
+        const uint32_t px = (uint32_t)((it / Cfg::SX) & 1), pa = (uint32_t)((it / UM_A_SLOTS) & 1);
+        smem_bar_wait(&x_full[sx], px);
+        smem_bar_wait(&a_full[sa], pa);
+        tc_fence_after();
+        const uint32_t xs = smem_addr_u32(x_ring + (size_t)sx * Cfg::X_BYTES);
+        const uint64_t bh = smem_desc_sw128(xs), bl = smem_desc_sw128(xs + Cfg::XH_BYTES);
+        const uint32_t a_hi = tmem + sa * 64, a_lo = a_hi + 32;
+#pragma unroll
+        for (int ks = 0; ks < UM_BK / 8; ++ks) {
+          // +32 bytes per k-step inside the 128-byte swizzle row: +2 in the descriptor's 16-byte address units
+          mma_tf32_ts(d_tmem, a_hi + ks * 8, bh + (uint64_t)(ks * 2), idesc, (first_of_tile && ks == 0) ? 0u : 1u);
+          mma_tf32_ts(d_tmem, a_lo + ks * 8, bh + (uint64_t)(ks * 2), idesc, 1u);
+          mma_tf32_ts(d_tmem, a_hi + ks * 8, bl + (uint64_t)(ks * 2), idesc, 1u);
+        }
+        tc_commit(&x_empty[sx]);
+        tc_commit(&a_empty[sa]);
+        const bool last_of_tile = (u + 1 == u_end) || ((u + 1) % sc.KB == 0);
+        if (last_of_tile) {
+          tc_commit(acc_full);
+          ++tile_j;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ================= splitter: fp32 weight rows -> (hi, lo) tf32 planes in tensor memory
+    const int q = warp & 3;             // TMEM lane quarter this warp may touch
+    const int r = q * 32 + lane;        // weight row inside the tile
+    long long it = 0;
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
+      const int sw = (int)(it % Cfg::SW), sa = (int)(it % UM_A_SLOTS);
+      const uint32_t pw = (uint32_t)((it / Cfg::SW) & 1), pa = (uint32_t)((it / UM_A_SLOTS) & 1);
+      smem_bar_wait(&w_full[sw], pw);
+      const uint8_t* row = w_ring + (size_t)sw * Cfg::W_BYTES + r * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // logical 16-byte chunk j of row r sits at physical chunk j ^ (r & 7)
+        const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t h = tf32_rna_bits(f[e]);
+          hi[j * 4 + e] = h;
+          lo[j * 4 + e] = tf32_rna_bits(f[e] - __uint_as_float(h));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) bar_arrive(&w_empty[sw]);  // the tile is in registers: the TMA producer may refill the stage
+      smem_bar_wait(&a_empty[sa], pa ^ 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + sa * 64;
+      tmem_st32(taddr, hi);
+      tmem_st32(taddr + 32, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(&a_full[sa]);
+    }
+  } else {
+    // ================= epilogue: D (lane = weight row, column = activation row) -> C or the CTA's side slot
+    const int q = warp & 3;
+    int tile_j = 0;
+    for (long long u = u_begin; u < u_end; ++tile_j) {
+      const int t = (int)(u / sc.KB), kb0 = (int)(u - (long long)t * sc.KB);
+      const long long t_end = (long long)(t + 1) * sc.KB;
+      const int mt = t / sc.n_nt, nt = t - mt * sc.n_nt;
+      const int mat = nt / sc.nt_per_mat, row0 = (nt - mat * sc.nt_per_mat) * UM_BM;
+      const int n_local = q * 32 + lane;
+      const bool n_ok = row0 + n_local < N;
+      smem_bar_wait(acc_full, (uint32_t)(tile_j & 1));
+      tc_fence_after();
+      float* dst;
+      int ld;
+      int m_valid;
+      if (kb0 == 0) {  // this CTA owns the tile's first k-block: its sum goes to C
+        dst = C + (size_t)mt * NT * ldc + (size_t)mat * N + row0 + n_local;
+        ld = ldc;
+        m_valid = M - mt * NT < NT ? M - mt * NT : NT;
+      } else {         // continuation of a tile another CTA started: side slot [NT][128]
+        dst = slots + (size_t)blockIdx.x * NT * UM_BM + n_local;
+        ld = UM_BM;
+        m_valid = NT;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + UM_ACC_COL + c0, v);
+        tmem_wait_ld();
+        if (n_ok || kb0 != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < m_valid) dst[(size_t)(c0 + j) * ld] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(acc_empty);
+      u = t_end < u_end ? t_end : u_end;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// C[m][col] += the side slots of the CTAs that continued the tile (for consumers that read C in place)
+__global__ void __launch_bounds__(256) umma_fixup_kernel(float* __restrict__ C, int ldc, const float* __restrict__ slots, int M, int N, int n_mat,
+                                                          const UmmaPlan pl) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int col = blockIdx.y * blockDim.x + threadIdx.x, m = blockIdx.x;  // rows on grid.x: no 65535 limit
+  if (col >= N * n_mat || m >= M) return;
+  const float add = umma_side_sum(pl, slots, m, col, N);
+  if (add != 0.f) C[(size_t)m * ldc + col] += add;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 matrix (rows x K, row-major, optionally `planes` of it) as a TMA tensor; box = {32 floats, box_rows, 1}, SWIZZLE_128B, zero fill
+bool make_tmap(CUtensorMap* tm, const float* ptr, int K, long long rows, int planes, int box_rows, bool weights) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)UM_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const int rank = planes > 1 ? 3 : 2;
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <int NT>
+cudaError_t launch_nt(const LaunchCtx& lc, const CUtensorMap& tmW, const CUtensorMap& tmW2, const CUtensorMap& tmX, float* C, int ldc, float* slots,
+                      int M, int N, const UmSched& sc, int grid) {
+  using Cfg = UmCfg<NT>;
+  cudaError_t e = cudaFuncSetAttribute(umma_tf32x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  return launch(lc, umma_tf32x3_kernel<NT>, dim3(grid), dim3(UM_THREADS), Cfg::SMEM, tmW, tmW2, tmX, C, ldc, slots, M, N, sc);
+}
+
+}  // namespace
+
+int umma_pick_nt(int M) {
+  if (M <= 32) return 32;
+  if (M <= 64) return 64;
+  if (M <= 128) return 128;
+  // many rows: 256-row tiles unless 128-row tiles waste less padding
+  const long long p256 = ((M + 255) / 256) * 256LL, p128 = ((M + 127) / 128) * 128LL;
+  return p128 < p256 ? 128 : 256;
+}
+
+UmmaPlan umma_plan(int M, int N, int n_mat, int K) {
+  UmmaPlan pl;
+  pl.NT = umma_pick_nt(M);
+  pl.KB = (K + UM_BK - 1) / UM_BK;
+  pl.nt_per_mat = (N + UM_BM - 1) / UM_BM;
+  pl.n_nt = pl.nt_per_mat * n_mat;
+  const int n_mt = (M + pl.NT - 1) / pl.NT;
+  pl.n_tiles = n_mt * pl.n_nt;
+  pl.total = (long long)pl.n_tiles * pl.KB;
+  const int sms = sm_count();
+  // at least 4 k-blocks per CTA (a range shorter than the rings is all prologue)
+  long long g = pl.total / 4;
+  if (g < 1) g = 1;
+  if (g > sms) g = sms;
+  pl.L = (pl.total + g - 1) / g;
+  pl.grid = (int)((pl.total + pl.L - 1) / pl.L);
+  pl.slot_floats = (size_t)pl.grid * pl.NT * UM_BM;
+  return pl;
+}
+
+// X2: [2][M][K] split planes (hi, lo) of the activation rows.  C: (M x n_mat * N) row-major, ldc floats per row.
+cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W, const float* W2, float* C, int ldc, float* slots, int M, int N,
+                            int K, const UmmaPlan& pl) {
+  if ((K & 3) || M < 1 || N < 1 || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(X2) & 15) ||
+      (W2 != nullptr && (reinterpret_cast<uintptr_t>(W2) & 15)))
+    return cudaErrorNotSupported;
+  CUtensorMap tmW, tmW2, tmX;
+  if (!make_tmap(&tmW, W, K, N, 1, UM_BM, true)) return cudaErrorNotSupported;
+  if (!make_tmap(&tmW2, W2 ? W2 : W, K, N, 1, UM_BM, true)) return cudaErrorNotSupported;
+  if (!make_tmap(&tmX, X2, K, M, 2, pl.NT, false)) return cudaErrorNotSupported;
+  UmSched sc;
+  sc.KB = pl.KB;
+  sc.n_nt = pl.n_nt;
+  sc.nt_per_mat = pl.nt_per_mat;
+  sc.n_tiles = pl.n_tiles;
+  sc.L = pl.L;
+  sc.total = pl.total;
+  switch (pl.NT) {
+    case 32: return launch_nt<32>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
+    case 64: return launch_nt<64>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
+    case 128: return launch_nt<128>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
+    case 256: return launch_nt<256>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
+  }
+  return cudaErrorNotSupported;
+}
+
+cudaError_t run_umma_fixup(const LaunchCtx& lc, float* C, int ldc, const float* slots, int M, int N, int n_mat, const UmmaPlan& pl) {
+  if (pl.L % pl.KB == 0) return cudaSuccess;  // every CTA owns whole tiles: no side slots in use
+  const dim3 grid(M, (N * n_mat + 255) / 256);
+  return launch(lc, umma_fixup_kernel, grid, dim3(256), 0, C, ldc, slots, M, N, n_mat, pl);
+}
+
+}  // namespace ua2

@@ -120,7 +120,7 @@ class Model_stage3(nn.Module):
                 ("audio_generation_expert.", self.audio_generation_expert))
 
     def _destroy(self):
-        if self._h is not None:
+        if getattr(self, "_h", None) is not None:
             _lib.lib().ua2_llm_destroy(self._h)
             self._h = None
             self._keep = []
@@ -130,6 +130,19 @@ class Model_stage3(nn.Module):
             self._destroy()
         except Exception:
             pass
+
+    # The handle holds raw parameter pointers plus a transposed copy of audio_head made in setup_caches: parameters that change
+    # (load_state_dict, resume_for_inference) or move (.to / .cuda / .float) after setup_caches would leave it stale.  Both drop the
+    # handle; the next forward_prefix / generate_frame raises the reference's "You need to call `setup_caches()`" (lit_model.py:134-135).
+    def load_state_dict(self, *args, **kwargs):
+        self._destroy()
+        self._max_batch = 0
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._destroy()
+        self._max_batch = 0
+        return super()._apply(fn, *args, **kwargs)
 
     def setup_caches(self, max_batch_size: int) -> None:
         """model_new.py:554-565: KV caches for the three global stacks at 2048 slots and the local decoder at

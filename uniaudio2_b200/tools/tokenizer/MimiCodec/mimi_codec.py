@@ -117,7 +117,7 @@ class MimiCodec(nn.Module):
 
     # ------------------------------------------------------------------ native handle
     def _destroy(self):
-        if self._h is not None:
+        if getattr(self, "_h", None) is not None:
             _lib.lib().ua2_codec_destroy(self._h)
             self._h = None
             self._keep = []
@@ -133,6 +133,11 @@ class MimiCodec(nn.Module):
         sd = {k: v for k, v in sd.items() if not k.startswith("semantic_mapping_layer.")}
         self._destroy()
         return super().load_state_dict(sd, strict=strict, **kw)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() move the tensors the handle points at: rebuild it lazily on the next encode / decode
+        self._destroy()
+        return super()._apply(fn, *args, **kwargs)
 
     def _ensure(self):
         if self._h is not None:
