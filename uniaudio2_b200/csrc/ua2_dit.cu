@@ -27,12 +27,9 @@
 
 #include "../../include/ua2_b200.h"
 #include "ua2_kernels.cuh"
+#include "ua2_umma.cuh"
 
 namespace ua2 {
-#ifdef UA2_HAVE_CUTLASS
-// ua2_tcgemm_bf16.cu: C (M x N, fp32) = A (M x K, bf16) * B (N x K, bf16)^T on tcgen05, fp32 accumulation
-cudaError_t run_bf16_gemm_128x128(cudaStream_t st, const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N, int K);
-#endif
 namespace {
 
 // fp32 -> bf16 (round to nearest even), 4 elements per thread; n must be a multiple of 4 (K % 8 == 0 on this path)
@@ -503,7 +500,6 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
 // x (M, K, row stride K) @ W^T, raw (no bias): tensor cores for M >= tc_min_rows (the product then stays in the path's own
 // buffer, *src points at it and `y` is not written), skinny fp32 kernels below (product in y, *src = y)
 int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K, const float** src) {
-#ifdef UA2_HAVE_CUTLASS
   if (h->opt_bf16 && h->a16 != nullptr && M >= 32 && (K % 8) == 0 && (N % 4) == 0 && (size_t)M * N <= h->tc.c_floats) {
     auto it = h->w16.find(W);
     if (it == h->w16.end()) {  // first use of this weight: keep a bf16 copy (2 B / parameter)
@@ -515,15 +511,16 @@ int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, 
     }
     const long long n4 = (long long)M * K / 4;
     CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, x, h->a16, n4));
-    const cudaError_t e = run_bf16_gemm_128x128(lc.stream, h->a16, it->second, h->tc.c, M, N, K);
+    // hand-written tcgen05 kind::f16 mainloop (ua2_umma.cu, bf16 mode): fp32 accumulation in TMEM, product in the handle's buffer
+    const UmmaPlan pl = umma_plan(M, N, 1, K, true);
+    cudaError_t e = pl.slot_floats <= h->tc.w_floats ? run_umma_bf16(lc, h->a16, it->second, h->tc.c, N, h->tc.w, M, N, K, pl) : cudaErrorNotSupported;
+    if (e == cudaSuccess) e = run_umma_fixup(lc, h->tc.c, N, h->tc.w, M, N, 1, pl);
     if (e == cudaSuccess) {
-      if (lc.launch_counter) ++*lc.launch_counter;
       *src = h->tc.c;
       return UA2_OK;
     }
     if (e != cudaErrorNotSupported) CU(e);
   }
-#endif
   GemvParams p;
   p.W = W;
   p.N = N;
@@ -869,13 +866,8 @@ int ua2_dit_set_option(ua2_dit* h, const char* name, int value) {
   UA2_REQUIRE(h && name, "null argument");
   const std::string n(name);
   if (n == "bf16") {
-#ifdef UA2_HAVE_CUTLASS
     h->opt_bf16 = value ? 1 : 0;
     return UA2_OK;
-#else
-    UA2_REQUIRE(!value, "library was built without the CUTLASS headers: no bf16 tensor-core path");
-    return UA2_OK;
-#endif
   }
   UA2_REQUIRE(false, "unknown option " + n);
 }

@@ -231,7 +231,7 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
   if ((Ntot & 3) || (size_t)M * K3 > ws.a_floats || (size_t)M * Ntot > ws.c_floats) return cudaErrorNotSupported;
   if (g_tc_impl == 1) {
     const UmmaPlan pl = umma_plan(M, p.N, epi == EPI_SWIGLU ? 2 : 1, K);
-    if (pl.slot_floats > ws.w_floats) return cudaErrorNotSupported;
+    if (pl.grid < 1 || pl.slot_floats > ws.w_floats) return cudaErrorNotSupported;
     cudaError_t e = cudaErrorNotSupported;
 #define UA2_TCA(P) \
   if (pro == P) e = launch(lc, tc_split_a_kernel<P>, dim3(M), dim3(256), 0, p, ws.a, 1);
@@ -247,7 +247,7 @@ cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvPa
       *p.raw_out = ws.c;
       return cudaSuccess;
     }
-    const float* slots = (pl.L % pl.KB) ? ws.w : nullptr;
+    const float* slots = umma_has_split_tiles(pl) ? ws.w : nullptr;
     const int n_units = epi == EPI_SWIGLU ? p.N : p.N / 2;
     const dim3 grid(M, (n_units + 255) / 256);
 #define UA2_TCE(E) \

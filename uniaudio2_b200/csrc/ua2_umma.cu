@@ -6,24 +6,30 @@
 //
 // Why not a library mainloop (round 1 used a CUTLASS collective over pre-split copies [hi|hi|lo]): the weights are the big
 // operand (4 B / parameter, 12.4 GB per batch-32 decode frame) and a library mainloop cannot split them on chip - round 1 paid
-// 12-28 B of HBM / L2 traffic per parameter.  Here the fp32 weight tile is loaded ONCE by TMA and split by four warps between
+// 12-28 B of HBM / L2 traffic per parameter.  Here the fp32 weight tile is loaded ONCE by TMA and split by eight warps between
 // shared memory and tensor memory, which is exactly what the tcgen05 "A operand from TMEM" form exists for.
 //
 // Swap-AB: the MMA's M dimension (128 TMEM lanes) carries 128 weight rows, its N dimension the activation rows (NT = 32 .. 256),
 // so a decode batch of 32 rows is one N = 32 instruction instead of a 75 % empty M = 128 tile.
 //
-//   warp 0      TMA producer (one thread): W tile 128 x 32 fp32 (box {32, 128}, SWIZZLE_128B) into the W ring; X_hi / X_lo tiles
-//               NT x 32 (pre-split by tc_split_a_kernel, which also carries the RMSNorm / LayerNorm / gather prologue) into the X ring
-//   warps 2-5   splitter: thread = weight row; 8 x LDS.128 of the swizzled row, cvt.rna.tf32 split, two tcgen05.st 32x32b.x32
-//               -> TMEM columns [slot * 64, +32) = hi, [+32, +64) = lo; releases the W stage as soon as it is in registers
-//   warp 1      MMA issuer (one thread): per k-step of 8:  D += A_hi B_hi;  D += A_lo B_hi;  D += A_hi B_lo   with
-//               tcgen05.mma.cta_group::1.kind::tf32 [D tmem], [A tmem], B smem-descriptor (K-major, SWIZZLE_128B);
-//               tcgen05.commit releases the X stage and the TMEM A slot, and at the end of a tile hands D to the epilogue
-//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 of D (lane = weight row n, column = activation row m) -> C[m][n], coalesced over n
+//   warp 0       W producer (one thread): W tile 128 x 32 fp32 (TMA box {32, 128}, SWIZZLE_128B) into the W ring; weights do not
+//                depend on the preceding kernel, so these loads start before griddepcontrol.wait (PDL overlap of the ring fill)
+//   warp 2       X producer (one thread): X_hi / X_lo tiles NT x 32 (one 3-D TMA box {32, NT, 2}; pre-split by tc_split_a_kernel,
+//                which also carries the RMSNorm / LayerNorm / gather prologue) into the X ring
+//   warps 4-11   splitter, two groups of four warps taking alternate k-blocks: thread = weight row; 8 x LDS.128 of the swizzled
+//                row, cvt.rna.tf32 split, two tcgen05.st 32x32b.x32 -> TMEM columns [slot * 64, +32) = hi, [+32, +64) = lo; the W
+//                stage is released as soon as it is in registers
+//   warp 1       MMA issuer (one thread): per k-step of 8:  D += A_hi B_hi;  D += A_lo B_hi;  D += A_hi B_lo   with
+//                tcgen05.mma.cta_group::1.kind::tf32 [D tmem], [A tmem], B smem-descriptor (K-major, SWIZZLE_128B);
+//                tcgen05.commit releases the X stage and the TMEM A slot, and at the end of a tile hands D to the epilogue
+//   warps 12-15  epilogue: tcgen05.ld 32x32b.x32 of D (lane = weight row n, column = activation row m) -> C[m][n], coalesced over n
 //
-// Scheduling is stream-K over the flattened (tile, k-block) space: CTA c owns units [c L, (c + 1) L), so every SM streams the same
-// number of weight bytes whatever N / 128 is.  A CTA whose range starts inside a tile writes that partial tile to its side slot;
-// the consumer (tc_epilogue_kernel / umma_fixup_kernel) adds the slots of the continuation CTAs in CTA order - deterministic.
+// Schedule: tiles are numbered in a rasterised order (groups of GM activation-row tiles, weight tiles inside a group, the GM row
+// tiles innermost) so that the tiles in flight at any moment - G consecutive numbers - share GM activation tiles and G / GM weight
+// tiles through L2.  The first floor(n_tiles / G) * G tiles are dealt round-robin as whole tiles; the remaining tiles (all of them
+// in a decode-sized call) are stream-K: CTA c owns units [c Lr, (c + 1) Lr) of their flattened (tile, k-block) space, so every SM
+// streams the same number of weight bytes whatever N / 128 is.  A CTA whose range starts inside a tile writes that partial tile
+// to its side slot; the consumer (tc_epilogue_kernel / umma_fixup_kernel) adds the continuation slots in CTA order - deterministic.
 //
 // TMEM budget (512 columns): A ring 4 slots x 64 columns, accumulator NT columns at column 256.
 #include <cuda.h>
@@ -38,17 +44,20 @@ constexpr int UM_BM = 128;        // weight rows per tile (TMEM lanes)
 constexpr int UM_BK = 32;         // fp32 per k-block = one 128-byte swizzle row
 constexpr int UM_A_SLOTS = 4;     // TMEM A ring
 constexpr int UM_ACC_COL = 256;   // accumulator base column
-constexpr int UM_THREADS = 320;
+constexpr int UM_THREADS = 512;   // 16 warps, see the role table above
 constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 
-template <int NT>
+// BF16 = false: fp32 operands, 3xTF32 (k-block = 32 floats, X stage = hi + lo planes).
+// BF16 = true : bf16 operands, one tcgen05.mma kind::f16 per k-step of 16 (k-block = 64 bf16 = the same 128-byte rows); the "splitter"
+//               warps only move the weight tile from shared to tensor memory.  The flow decoder's option (the reference autocasts it to bf16).
+template <int NT, bool BF16>
 struct UmCfg {
-  static constexpr int SW = NT <= 32 ? 8 : NT <= 64 ? 6 : NT <= 128 ? 4 : 2;  // W ring stages (16 KB each)
-  static constexpr int SX = NT <= 32 ? 8 : NT <= 64 ? 6 : NT <= 128 ? 4 : 3;  // X ring stages (2 * NT * 128 B each)
-  static constexpr int W_BYTES = UM_BM * UM_BK * 4;
-  static constexpr int XH_BYTES = NT * UM_BK * 4;
-  static constexpr int X_BYTES = 2 * XH_BYTES;
+  static constexpr int SW = NT <= 32 ? 8 : NT <= 64 ? 6 : NT <= 128 ? 4 : (BF16 ? 4 : 2);  // W ring stages (16 KB each)
+  static constexpr int SX = NT <= 32 ? 8 : NT <= 64 ? 6 : NT <= 128 ? 4 : (BF16 ? 4 : 3);  // X ring stages
+  static constexpr int W_BYTES = UM_BM * 128;
+  static constexpr int XH_BYTES = NT * 128;
+  static constexpr int X_BYTES = BF16 ? XH_BYTES : 2 * XH_BYTES;
   static constexpr int N_BARS = 2 * SW + 2 * SX + 2 * UM_A_SLOTS + 2;
   static constexpr size_t SMEM = 1024 + (size_t)SW * W_BYTES + (size_t)SX * X_BYTES + N_BARS * 8 + 16;
 };
@@ -88,6 +97,16 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
@@ -122,21 +141,50 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-struct UmSched {
-  int KB;        // k-blocks per tile
-  int n_nt;      // weight tiles (both matrices)
-  int nt_per_mat;
-  int n_tiles;   // n_mt * n_nt
-  long long L;   // units per CTA
-  long long total;
+
+// The work of one CTA as a sequence of segments (tile, first k-block, end k-block): whole tiles of the data-parallel waves, then
+// its range of the stream-K remainder.  Every warp role walks the same sequence.
+struct UmSeg {
+  const UmmaPlan& pl;
+  int c, j, u, u_end;
+  __device__ UmSeg(const UmmaPlan& p, int cta) : pl(p), c(cta), j(0) {
+    u = cta * p.Lr < p.rem_units ? cta * p.Lr : p.rem_units;
+    u_end = u + p.Lr < p.rem_units ? u + p.Lr : p.rem_units;
+  }
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (j < pl.full_waves) {
+      tile = c + j * pl.grid;
+      kb0 = 0;
+      kb1 = pl.KB;
+      ++j;
+      return true;
+    }
+    if (u >= u_end) return false;
+    const int tr = u / pl.KB;
+    kb0 = u - tr * pl.KB;
+    const int e = (tr + 1) * pl.KB < u_end ? (tr + 1) * pl.KB : u_end;
+    kb1 = kb0 + (e - u);
+    tile = pl.dp_tiles + tr;
+    u = e;
+    return true;
+  }
 };
+// rasterised tile number -> (activation-row tile, weight tile)
+__device__ __forceinline__ void um_tile_coords(const UmmaPlan& pl, int tile, int& mt, int& nt) {
+  const int per_group = pl.GM * pl.n_nt;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int gmg = pl.n_mt - g * pl.GM < pl.GM ? pl.n_mt - g * pl.GM : pl.GM;
+  nt = r / gmg;
+  mt = g * pl.GM + (r - nt * gmg);
+}
 
 // ------------------------------------------------------------------ the kernel
-template <int NT>
+template <int NT, bool BF16>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
-                   float* __restrict__ C, int ldc, float* __restrict__ slots, int M, int N, const UmSched sc) {
-  using Cfg = UmCfg<NT>;
+umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                   float* __restrict__ C, int ldc, float* __restrict__ slots, int M, int N, const UmmaPlan pl) {
+  using Cfg = UmCfg<NT, BF16>;
+  constexpr int BKE = BF16 ? 64 : 32;  // elements per k-block (128 bytes)
   extern __shared__ uint8_t um_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(um_smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
   uint8_t* w_ring = base;
@@ -153,8 +201,7 @@ umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long u_begin = (long long)blockIdx.x * sc.L;
-  const long long u_end = u_begin + sc.L < sc.total ? u_begin + sc.L : sc.total;
+  const int cta = blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
@@ -187,75 +234,92 @@ umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // ================= TMA producer
-    if (lane == 0 && u_begin < u_end) {
-      pdl_wait();  // X planes come from the preceding split kernel
-      long long it = 0;
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int t = (int)(u / sc.KB), kb = (int)(u - (long long)t * sc.KB);
-        const int mt = t / sc.n_nt, nt = t - mt * sc.n_nt;
-        const int mat = nt / sc.nt_per_mat, row0 = (nt - mat * sc.nt_per_mat) * UM_BM;
-        const int sw = (int)(it % Cfg::SW), sx = (int)(it % Cfg::SX);
-        const uint32_t pw = (uint32_t)((it / Cfg::SW) & 1), px = (uint32_t)((it / Cfg::SX) & 1);
-        smem_bar_wait(&w_empty[sw], pw ^ 1);
-        smem_bar_arrive_expect_tx(&w_full[sw], Cfg::W_BYTES);
-        tma_load_2d(w_ring + (size_t)sw * Cfg::W_BYTES, mat ? &tmW2 : &tmW, kb * UM_BK, row0, &w_full[sw], POLICY_EVICT_FIRST);
-        smem_bar_wait(&x_empty[sx], px ^ 1);
-        smem_bar_arrive_expect_tx(&x_full[sx], Cfg::X_BYTES);
-        uint8_t* xs = x_ring + (size_t)sx * Cfg::X_BYTES;
-        tma_load_3d(xs, &tmX, kb * UM_BK, mt * NT, 0, &x_full[sx], POLICY_EVICT_LAST);
-        tma_load_3d(xs + Cfg::XH_BYTES, &tmX, kb * UM_BK, mt * NT, 1, &x_full[sx], POLICY_EVICT_LAST);
+    // ================= W producer (no griddepcontrol.wait: weights are not written by the preceding kernels)
+    if (lane == 0) {
+      UmSeg seg(pl, cta);
+      int tile, kb0, kb1;
+      uint32_t it = 0;
+      while (seg.next(tile, kb0, kb1)) {
+        int mt, nt;
+        um_tile_coords(pl, tile, mt, nt);
+        const int mat = nt / pl.nt_per_mat, row0 = (nt - mat * pl.nt_per_mat) * UM_BM;
+        const CUtensorMap* tm = mat ? &tmW2 : &tmW;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t sw = it % Cfg::SW, pw = (it / Cfg::SW) & 1;
+          smem_bar_wait(&w_empty[sw], pw ^ 1);
+          smem_bar_arrive_expect_tx(&w_full[sw], Cfg::W_BYTES);
+          tma_load_2d(w_ring + (size_t)sw * Cfg::W_BYTES, tm, kb * BKE, row0, &w_full[sw], POLICY_EVICT_FIRST);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= X producer
+    if (lane == 0) {
+      pdl_wait();  // the split planes come from the preceding kernel
+      UmSeg seg(pl, cta);
+      int tile, kb0, kb1;
+      uint32_t it = 0;
+      while (seg.next(tile, kb0, kb1)) {
+        int mt, nt;
+        um_tile_coords(pl, tile, mt, nt);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t sx = it % Cfg::SX, px = (it / Cfg::SX) & 1;
+          smem_bar_wait(&x_empty[sx], px ^ 1);
+          smem_bar_arrive_expect_tx(&x_full[sx], Cfg::X_BYTES);
+          if constexpr (BF16)
+            tma_load_2d(x_ring + (size_t)sx * Cfg::X_BYTES, &tmX, kb * BKE, mt * NT, &x_full[sx], POLICY_EVICT_LAST);
+          else
+            tma_load_3d(x_ring + (size_t)sx * Cfg::X_BYTES, &tmX, kb * BKE, mt * NT, 0, &x_full[sx], POLICY_EVICT_LAST);
+        }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer
-    if (lane == 0 && u_begin < u_end) {
-      // instruction descriptor: D fp32 (bit 4), A/B tf32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (bit 4), A/B format at bits 7 / 10 (tf32 = 2, bf16 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      constexpr uint32_t fmt = BF16 ? 1u : 2u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
       const uint32_t d_tmem = tmem + UM_ACC_COL;
-      long long it = 0;
-      int tile_j = 0;
-      int cur_t = -1;
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int t = (int)(u / sc.KB);
-        const bool first_of_tile = t != cur_t;
-        if (first_of_tile) {
-          cur_t = t;
-          smem_bar_wait(acc_empty, (uint32_t)((tile_j & 1) ^ 1));  // the epilogue has drained the previous tile
-          tc_fence_after();
-        }
-        const int sx = (int)(it % Cfg::SX), sa = (int)(it % UM_A_SLOTS);
-        const uint32_t px = (uint32_t)((it / Cfg::SX) & 1), pa = (uint32_t)((it / UM_A_SLOTS) & 1);
-        smem_bar_wait(&x_full[sx], px);
-        smem_bar_wait(&a_full[sa], pa);
+      UmSeg seg(pl, cta);
+      int tile, kb0, kb1;
+      uint32_t it = 0, tile_j = 0;
+      while (seg.next(tile, kb0, kb1)) {
+        smem_bar_wait(acc_empty, (tile_j & 1) ^ 1);  // the epilogue has drained the previous tile
         tc_fence_after();
-        const uint32_t xs = smem_addr_u32(x_ring + (size_t)sx * Cfg::X_BYTES);
-        const uint64_t bh = smem_desc_sw128(xs), bl = smem_desc_sw128(xs + Cfg::XH_BYTES);
-        const uint32_t a_hi = tmem + sa * 64, a_lo = a_hi + 32;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t sx = it % Cfg::SX, px = (it / Cfg::SX) & 1, sa = it % UM_A_SLOTS, pa = (it / UM_A_SLOTS) & 1;
+          smem_bar_wait(&x_full[sx], px);
+          smem_bar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t xs = smem_addr_u32(x_ring + (size_t)sx * Cfg::X_BYTES);
+          const uint64_t bh = smem_desc_sw128(xs), bl = smem_desc_sw128(xs + Cfg::XH_BYTES);
+          const uint32_t a_hi = tmem + sa * 64, a_lo = a_hi + 32;
 #pragma unroll
-        for (int ks = 0; ks < UM_BK / 8; ++ks) {
-          // +32 bytes per k-step inside the 128-byte swizzle row: +2 in the descriptor's 16-byte address units
-          mma_tf32_ts(d_tmem, a_hi + ks * 8, bh + (uint64_t)(ks * 2), idesc, (first_of_tile && ks == 0) ? 0u : 1u);
-          mma_tf32_ts(d_tmem, a_lo + ks * 8, bh + (uint64_t)(ks * 2), idesc, 1u);
-          mma_tf32_ts(d_tmem, a_hi + ks * 8, bl + (uint64_t)(ks * 2), idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) {
+            // one k-step = 32 bytes of every row (8 tf32 / 16 bf16): +2 in the descriptor's 16-byte address units, +8 TMEM columns
+            if constexpr (BF16) {
+              mma_bf16_ts(d_tmem, a_hi + ks * 8, bh + (uint64_t)(ks * 2), idesc, (kb == kb0 && ks == 0) ? 0u : 1u);
+            } else {
+              mma_tf32_ts(d_tmem, a_hi + ks * 8, bh + (uint64_t)(ks * 2), idesc, (kb == kb0 && ks == 0) ? 0u : 1u);
+              mma_tf32_ts(d_tmem, a_lo + ks * 8, bh + (uint64_t)(ks * 2), idesc, 1u);
+              mma_tf32_ts(d_tmem, a_hi + ks * 8, bl + (uint64_t)(ks * 2), idesc, 1u);
+            }
+          }
+          tc_commit(&x_empty[sx]);
+          tc_commit(&a_empty[sa]);
         }
-        tc_commit(&x_empty[sx]);
-        tc_commit(&a_empty[sa]);
-        const bool last_of_tile = (u + 1 == u_end) || ((u + 1) % sc.KB == 0);
-        if (last_of_tile) {
-          tc_commit(acc_full);
-          ++tile_j;
-        }
+        tc_commit(acc_full);
+        ++tile_j;
       }
     }
-  } else if (warp < 6) {
-    // ================= splitter: fp32 weight rows -> (hi, lo) tf32 planes in tensor memory
+  } else if (warp >= 4 && warp < 12) {
+    // ================= splitter: fp32 weight rows -> (hi, lo) tf32 planes in tensor memory; group g takes k-blocks it = g, g + 2, ...
+    const int grp = (warp - 4) >> 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;        // weight row inside the tile
-    long long it = 0;
-    for (long long u = u_begin; u < u_end; ++u, ++it) {
-      const int sw = (int)(it % Cfg::SW), sa = (int)(it % UM_A_SLOTS);
-      const uint32_t pw = (uint32_t)((it / Cfg::SW) & 1), pa = (uint32_t)((it / UM_A_SLOTS) & 1);
+    const uint32_t n_it = (uint32_t)(pl.full_waves * pl.KB) + (uint32_t)UmSeg(pl, cta).u_end - (uint32_t)UmSeg(pl, cta).u;
+    for (uint32_t it = (uint32_t)grp; it < n_it; it += 2) {
+      const uint32_t sw = it % Cfg::SW, pw = (it / Cfg::SW) & 1, sa = it % UM_A_SLOTS, pa = (it / UM_A_SLOTS) & 1;
       smem_bar_wait(&w_full[sw], pw);
       const uint8_t* row = w_ring + (size_t)sw * Cfg::W_BYTES + r * 128;
       uint32_t hi[32], lo[32];
@@ -265,35 +329,46 @@ umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint32_t h = tf32_rna_bits(f[e]);
-          hi[j * 4 + e] = h;
-          lo[j * 4 + e] = tf32_rna_bits(f[e] - __uint_as_float(h));
+          if constexpr (BF16) {
+            hi[j * 4 + e] = __float_as_uint(f[e]);  // two bf16 per word, moved as they are
+          } else {
+            const uint32_t h = tf32_rna_bits(f[e]);
+            hi[j * 4 + e] = h;
+            lo[j * 4 + e] = tf32_rna_bits(f[e] - __uint_as_float(h));
+          }
         }
       }
-      __syncwarp();
-      if (lane == 0) bar_arrive(&w_empty[sw]);  // the tile is in registers: the TMA producer may refill the stage
+      // The stage may be refilled only after every lane's LDS has RETURNED: an arrive does not wait for outstanding shared-memory
+      // loads (first hardware run of the free-running W producer: single weight rows of a tile came from the next k-block).  The
+      // shuffle reduction consumes one word of each 128-bit load of every lane, so lane 0's arrive is issued after all of them.
+      uint32_t dep = hi[0] ^ hi[4] ^ hi[8] ^ hi[12] ^ hi[16] ^ hi[20] ^ hi[24] ^ hi[28];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dep ^= __shfl_xor_sync(0xffffffffu, dep, o);
+      asm volatile("and.b32 %0, %0, 0;" : "+r"(dep));  // opaque zero that still depends on the loads
+      if (lane == 0) bar_arrive(&w_empty[sw] + dep);  // the tile is in registers: the W producer may refill the stage
       smem_bar_wait(&a_empty[sa], pa ^ 1);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + sa * 64;
       tmem_st32(taddr, hi);
-      tmem_st32(taddr + 32, lo);
+      if constexpr (!BF16) tmem_st32(taddr + 32, lo);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(&a_full[sa]);
     }
-  } else {
+  } else if (warp >= 12) {
     // ================= epilogue: D (lane = weight row, column = activation row) -> C or the CTA's side slot
     const int q = warp & 3;
-    int tile_j = 0;
-    for (long long u = u_begin; u < u_end; ++tile_j) {
-      const int t = (int)(u / sc.KB), kb0 = (int)(u - (long long)t * sc.KB);
-      const long long t_end = (long long)(t + 1) * sc.KB;
-      const int mt = t / sc.n_nt, nt = t - mt * sc.n_nt;
-      const int mat = nt / sc.nt_per_mat, row0 = (nt - mat * sc.nt_per_mat) * UM_BM;
+    UmSeg seg(pl, cta);
+    int tile, kb0, kb1;
+    uint32_t tile_j = 0;
+    while (seg.next(tile, kb0, kb1)) {
+      int mt, nt;
+      um_tile_coords(pl, tile, mt, nt);
+      const int mat = nt / pl.nt_per_mat, row0 = (nt - mat * pl.nt_per_mat) * UM_BM;
       const int n_local = q * 32 + lane;
       const bool n_ok = row0 + n_local < N;
-      smem_bar_wait(acc_full, (uint32_t)(tile_j & 1));
+      smem_bar_wait(acc_full, tile_j & 1);
       tc_fence_after();
       float* dst;
       int ld;
@@ -303,7 +378,7 @@ umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         ld = ldc;
         m_valid = M - mt * NT < NT ? M - mt * NT : NT;
       } else {         // continuation of a tile another CTA started: side slot [NT][128]
-        dst = slots + (size_t)blockIdx.x * NT * UM_BM + n_local;
+        dst = slots + (size_t)cta * NT * UM_BM + n_local;
         ld = UM_BM;
         m_valid = NT;
       }
@@ -321,7 +396,7 @@ umma_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(acc_empty);
-      u = t_end < u_end ? t_end : u_end;
+      ++tile_j;
     }
   }
   tc_fence_before();
@@ -356,16 +431,18 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// fp32 matrix (rows x K, row-major, optionally `planes` of it) as a TMA tensor; box = {32 floats, box_rows, 1}, SWIZZLE_128B, zero fill
-bool make_tmap(CUtensorMap* tm, const float* ptr, int K, long long rows, int planes, int box_rows, bool weights) {
+// matrix (rows x K, row-major, optionally `planes` of it; fp32 or bf16) as a TMA tensor; box = {128 bytes, box_rows, planes}, SWIZZLE_128B, zero fill
+bool make_tmap(CUtensorMap* tm, const void* ptr, int K, long long rows, int planes, int box_rows, bool weights, bool bf16 = false) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return false;
+  const cuuint64_t es_bytes = bf16 ? 2 : 4;
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)planes};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * 4 * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)UM_BK, (cuuint32_t)box_rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)K * es_bytes, (cuuint64_t)K * es_bytes * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es_bytes), (cuuint32_t)box_rows, (cuuint32_t)planes};
   cuuint32_t es[3] = {1, 1, 1};
   const int rank = planes > 1 ? 3 : 2;
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -381,13 +458,13 @@ int sm_count() {
   return g_sm_count;
 }
 
-template <int NT>
+template <int NT, bool BF16>
 cudaError_t launch_nt(const LaunchCtx& lc, const CUtensorMap& tmW, const CUtensorMap& tmW2, const CUtensorMap& tmX, float* C, int ldc, float* slots,
-                      int M, int N, const UmSched& sc, int grid) {
-  using Cfg = UmCfg<NT>;
-  cudaError_t e = cudaFuncSetAttribute(umma_tf32x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+                      int M, int N, const UmmaPlan& pl) {
+  using Cfg = UmCfg<NT, BF16>;
+  cudaError_t e = cudaFuncSetAttribute(umma_kernel<NT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
-  return launch(lc, umma_tf32x3_kernel<NT>, dim3(grid), dim3(UM_THREADS), Cfg::SMEM, tmW, tmW2, tmX, C, ldc, slots, M, N, sc);
+  return launch(lc, umma_kernel<NT, BF16>, dim3(pl.grid), dim3(UM_THREADS), Cfg::SMEM, tmW, tmW2, tmX, C, ldc, slots, M, N, pl);
 }
 
 }  // namespace
@@ -401,22 +478,31 @@ int umma_pick_nt(int M) {
   return p128 < p256 ? 128 : 256;
 }
 
-UmmaPlan umma_plan(int M, int N, int n_mat, int K) {
+UmmaPlan umma_plan(int M, int N, int n_mat, int K, bool bf16) {
   UmmaPlan pl;
   pl.NT = umma_pick_nt(M);
-  pl.KB = (K + UM_BK - 1) / UM_BK;
+  const int bke = bf16 ? 64 : UM_BK;
+  pl.KB = (K + bke - 1) / bke;
   pl.nt_per_mat = (N + UM_BM - 1) / UM_BM;
   pl.n_nt = pl.nt_per_mat * n_mat;
-  const int n_mt = (M + pl.NT - 1) / pl.NT;
-  pl.n_tiles = n_mt * pl.n_nt;
-  pl.total = (long long)pl.n_tiles * pl.KB;
+  pl.n_mt = (M + pl.NT - 1) / pl.NT;
+  pl.GM = std::max(1, std::min(pl.n_mt, 1024 / pl.NT));
+  const long long n_tiles = (long long)pl.n_mt * pl.n_nt;
+  if (n_tiles * pl.KB >= (1LL << 30)) {
+    pl.grid = 0;  // not served (index arithmetic is 32-bit)
+    return pl;
+  }
+  pl.n_tiles = (int)n_tiles;
   const int sms = sm_count();
-  // at least 4 k-blocks per CTA (a range shorter than the rings is all prologue)
-  long long g = pl.total / 4;
-  if (g < 1) g = 1;
-  if (g > sms) g = sms;
-  pl.L = (pl.total + g - 1) / g;
-  pl.grid = (int)((pl.total + pl.L - 1) / pl.L);
+  pl.grid = sms;
+  pl.full_waves = pl.n_tiles / sms;
+  pl.dp_tiles = pl.full_waves * sms;
+  pl.rem_units = (pl.n_tiles - pl.dp_tiles) * pl.KB;
+  if (pl.full_waves == 0) {  // decode-sized: pure stream-K, at least 4 k-blocks per CTA (a shorter range is all prologue)
+    int g = pl.rem_units / 4;
+    pl.grid = std::max(1, std::min(sms, g));
+  }
+  pl.Lr = pl.rem_units ? (pl.rem_units + pl.grid - 1) / pl.grid : 0;
   pl.slot_floats = (size_t)pl.grid * pl.NT * UM_BM;
   return pl;
 }
@@ -424,31 +510,41 @@ UmmaPlan umma_plan(int M, int N, int n_mat, int K) {
 // X2: [2][M][K] split planes (hi, lo) of the activation rows.  C: (M x n_mat * N) row-major, ldc floats per row.
 cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W, const float* W2, float* C, int ldc, float* slots, int M, int N,
                             int K, const UmmaPlan& pl) {
-  if ((K & 3) || M < 1 || N < 1 || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(X2) & 15) ||
+  if ((K & 3) || M < 1 || N < 1 || pl.grid < 1 || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(X2) & 15) ||
       (W2 != nullptr && (reinterpret_cast<uintptr_t>(W2) & 15)))
     return cudaErrorNotSupported;
   CUtensorMap tmW, tmW2, tmX;
   if (!make_tmap(&tmW, W, K, N, 1, UM_BM, true)) return cudaErrorNotSupported;
   if (!make_tmap(&tmW2, W2 ? W2 : W, K, N, 1, UM_BM, true)) return cudaErrorNotSupported;
   if (!make_tmap(&tmX, X2, K, M, 2, pl.NT, false)) return cudaErrorNotSupported;
-  UmSched sc;
-  sc.KB = pl.KB;
-  sc.n_nt = pl.n_nt;
-  sc.nt_per_mat = pl.nt_per_mat;
-  sc.n_tiles = pl.n_tiles;
-  sc.L = pl.L;
-  sc.total = pl.total;
   switch (pl.NT) {
-    case 32: return launch_nt<32>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
-    case 64: return launch_nt<64>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
-    case 128: return launch_nt<128>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
-    case 256: return launch_nt<256>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, sc, pl.grid);
+    case 32: return launch_nt<32, false>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, pl);
+    case 64: return launch_nt<64, false>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, pl);
+    case 128: return launch_nt<128, false>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, pl);
+    case 256: return launch_nt<256, false>(lc, tmW, tmW2, tmX, C, ldc, slots, M, N, pl);
+  }
+  return cudaErrorNotSupported;
+}
+
+// bf16 operands (X (M x K), W (N x K), both row-major bf16), fp32 accumulation and output; plan from umma_plan(..., bf16 = true); K % 8 == 0
+cudaError_t run_umma_bf16(const LaunchCtx& lc, const void* X16, const void* W16, float* C, int ldc, float* slots, int M, int N, int K,
+                          const UmmaPlan& pl) {
+  if ((K & 7) || M < 1 || N < 1 || pl.grid < 1 || (reinterpret_cast<uintptr_t>(W16) & 15) || (reinterpret_cast<uintptr_t>(X16) & 15))
+    return cudaErrorNotSupported;
+  CUtensorMap tmW, tmX;
+  if (!make_tmap(&tmW, W16, K, N, 1, UM_BM, true, true)) return cudaErrorNotSupported;
+  if (!make_tmap(&tmX, X16, K, M, 1, pl.NT, false, true)) return cudaErrorNotSupported;
+  switch (pl.NT) {
+    case 32: return launch_nt<32, true>(lc, tmW, tmW, tmX, C, ldc, slots, M, N, pl);
+    case 64: return launch_nt<64, true>(lc, tmW, tmW, tmX, C, ldc, slots, M, N, pl);
+    case 128: return launch_nt<128, true>(lc, tmW, tmW, tmX, C, ldc, slots, M, N, pl);
+    case 256: return launch_nt<256, true>(lc, tmW, tmW, tmX, C, ldc, slots, M, N, pl);
   }
   return cudaErrorNotSupported;
 }
 
 cudaError_t run_umma_fixup(const LaunchCtx& lc, float* C, int ldc, const float* slots, int M, int N, int n_mat, const UmmaPlan& pl) {
-  if (pl.L % pl.KB == 0) return cudaSuccess;  // every CTA owns whole tiles: no side slots in use
+  if (!umma_has_split_tiles(pl)) return cudaSuccess;  // every CTA owns whole tiles: no side slots in use
   const dim3 grid(M, (N * n_mat + 255) / 256);
   return launch(lc, umma_fixup_kernel, grid, dim3(256), 0, C, ldc, slots, M, N, n_mat, pl);
 }

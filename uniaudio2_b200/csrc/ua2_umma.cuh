@@ -1,6 +1,8 @@
-// Interface of the hand-written tcgen05 3xTF32 GEMM (ua2_umma.cu): the stream-K plan shared by the kernel, its launchers and the
+// Interface of the hand-written tcgen05 3xTF32 GEMM (ua2_umma.cu): the schedule shared by the kernel, its launchers and the
 // consumers that add the side slots of split tiles.
 #pragma once
+#include <algorithm>
+
 #include "ua2_common.cuh"
 
 namespace ua2 {
@@ -10,27 +12,38 @@ struct UmmaPlan {
   int KB = 0;          // 32-float k-blocks per tile
   int nt_per_mat = 0;  // 128-row weight tiles per weight matrix
   int n_nt = 0;        // weight tiles over all matrices (2 matrices for SwiGLU)
+  int n_mt = 0;        // activation-row tiles
+  int GM = 1;          // activation-row tiles per raster group
   int n_tiles = 0;
   int grid = 0;
-  long long L = 0;      // (tile, k-block) units per CTA
-  long long total = 0;  // n_tiles * KB
+  int full_waves = 0;  // whole tiles dealt round-robin: tiles [0, dp_tiles), CTA c takes c, c + grid, ...
+  int dp_tiles = 0;
+  int rem_units = 0;   // (tile, k-block) units of the remaining tiles, split evenly: CTA c takes [c Lr, (c + 1) Lr)
+  int Lr = 0;
   size_t slot_floats = 0;  // side-slot scratch the launch may write: grid * NT * 128
 };
 
 int umma_pick_nt(int M);
-UmmaPlan umma_plan(int M, int N, int n_mat, int K);
+UmmaPlan umma_plan(int M, int N, int n_mat, int K, bool bf16 = false);
 cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W, const float* W2, float* C, int ldc, float* slots, int M, int N,
                             int K, const UmmaPlan& pl);
+cudaError_t run_umma_bf16(const LaunchCtx& lc, const void* X16, const void* W16, float* C, int ldc, float* slots, int M, int N, int K,
+                          const UmmaPlan& pl);
 cudaError_t run_umma_fixup(const LaunchCtx& lc, float* C, int ldc, const float* slots, int M, int N, int n_mat, const UmmaPlan& pl);
+inline bool umma_has_split_tiles(const UmmaPlan& pl) { return pl.rem_units > 0 && (pl.Lr % pl.KB) != 0; }
 
 #ifdef __CUDACC__
 // Sum, in CTA order, of the partial tiles that continuation CTAs left in their side slots for element (m, col) of C; `col` counts
-// over the concatenated matrices (col / N = matrix).  CTA c_first (the one holding the tile's first k-block) wrote C itself.
+// over the concatenated matrices (col / N = matrix).  The CTA holding the tile's first k-block wrote C itself.
 __device__ __forceinline__ float umma_side_sum(const UmmaPlan& pl, const float* __restrict__ slots, int m, int col, int N) {
   const int mat = col / N, cn = col - mat * N;
   const int mt = m / pl.NT, nt = mat * pl.nt_per_mat + (cn >> 7);
-  const long long u0 = ((long long)mt * pl.n_nt + nt) * pl.KB, u1 = u0 + pl.KB - 1;
-  const int c_first = (int)(u0 / pl.L), c_last = (int)(u1 / pl.L);
+  const int g = mt / pl.GM;
+  const int gmg = pl.n_mt - g * pl.GM < pl.GM ? pl.n_mt - g * pl.GM : pl.GM;
+  const int tile = g * pl.GM * pl.n_nt + nt * gmg + (mt - g * pl.GM);  // rasterised tile number (inverse of um_tile_coords)
+  if (tile < pl.dp_tiles) return 0.f;
+  const int u0 = (tile - pl.dp_tiles) * pl.KB, u1 = u0 + pl.KB - 1;
+  const int c_first = u0 / pl.Lr, c_last = u1 / pl.Lr;
   float s = 0.f;
   for (int c = c_first + 1; c <= c_last; ++c) s += slots[((size_t)c * pl.NT + (m - mt * pl.NT)) * 128 + (cn & 127)];
   return s;
