@@ -513,12 +513,10 @@ def main():
     ap.add_argument("--v3-kcw", type=int, default=0)
     ap.add_argument("--v3-balance", type=int, default=-1)
     ap.add_argument("--v3-budget", type=int, default=0)
-    ap.add_argument("--chain", type=int, default=-1, help="1: persistent multi-op chain kernels for B = 1 frames (library default 0)")
     ap.add_argument("--attn-direct", type=int, default=-1, help="local-decoder attention inside the proj prologue (library default 1)")
     ap.add_argument("--pf-mb", type=int, default=-1, help="tail L2 prefetch budget per linear, MB (-1: library default)")
     ap.add_argument("--pf-idle-mb", type=int, default=-1, help="extra prefetch budget before attention / sampler kernels, MB")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("UA2_PDL", "1")))
-    ap.add_argument("--gemv-impl", type=int, default=0, help="0 = library default; 1/2/3 select the skinny-linear kernel generation")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -574,8 +572,6 @@ def main():
     from uniaudio2_b200.evaluation.tts_task import Generator, default_train_args
     from uniaudio2_b200.llm_models.model_new import Model_stage3
 
-    if args.gemv_impl:
-        _lib.check(_lib.lib().ua2_set_global_option(b"gemv_impl", args.gemv_impl))
     if args.v3_balance >= 0:
         _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_balance_grid", args.v3_balance))
     if args.v3_kcw:
@@ -597,8 +593,6 @@ def main():
         model.set_option("pdl", int(args.pdl))
         if args.attn_direct >= 0:
             model.set_option("attn_direct", int(args.attn_direct))
-        if args.chain >= 0:
-            model.set_option("chain", int(args.chain))
         task_prompt, text = synthetic_prompt(rank)
         tokens, mask = gen.prepare_tts_task(task_prompt, text)
         assert tokens.size(0) == PROMPT_LEN

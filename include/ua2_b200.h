@@ -34,21 +34,17 @@ const char* ua2_last_error(void);
 /* library / device probe: returns the SM count of the current device (e.g. 148), <0 on error */
 int ua2_device_sm_count(void);
 const char* ua2_version(void);
-/* process-wide knobs: "gemv_impl" = 1 (register-streamed LDG weights) | 2 (per-warp cp.async.bulk + mbarrier rings) |
- * 3 (persistent CTAs, slab partition + K split across warps, bulk-copy rings; default);
+/* process-wide knobs:
  * "gemv3_ctas_per_sm" (1..3, default 2), "gemv3_max_stages" (2..6, default 3), "gemv3_kcw" (floats per bulk copy, default 1024),
- * "gemv3_budget_kb" (shared memory per decode CTA, default 110), "gemv3_balance_grid" (0/1, default 1),
- * "sgemm_min_rows" (rows from which linears use the tiled GEMM core, default 128),
- * "tc_gemm" (0/1, default 1 when built with the CUTLASS headers: linears with >= "tc_min_rows" (default 32) rows run as
- * 3xTF32 tcgen05 GEMMs - fp32-class accuracy, csrc/ua2_tcgemm.cu), "tc_persistent_weights" (0/1, default 0: keep the
- * tf32-split copy of every weight the tensor-core path has used, 12 B per parameter, instead of re-splitting per call -
- * for batched decode frames, e.g. tc_min_rows = 16 with batch 32),
- * "resblock_fused" (0/1, default 0: the 64-channel SEANet residual blocks of the codec handle run as one kernel, csrc/ua2_resblock.cu),
- * "attn_ring" (0/1, default 0: KV-cache attention launches with >= 592 (row, group, 64-key split) items run on persistent CTAs that
- * stream the K / V chunks through a 3-slot bulk-copy ring instead of one fetch-compute-exit CTA per item - csrc/ua2_attn.cu; same
- * partial-result layout and arithmetic; written at the end of round 1 and not yet measured),
- * "conv_tc" (0/1, default 0: causal convolutions with Cin * K >= 1024 and transposed convolutions with Cin >= 128 run as im2col +
- * tcgen05 3xTF32 GEMM instead of the fp32 register-tiled core - csrc/ua2_convtc.cu; written at the end of round 1 and not yet measured),
+ * "gemv3_budget_kb" (shared memory per decode CTA, default 110), "gemv3_balance_grid" (0/1, default 1): the skinny weight-streaming linear;
+ * "sgemm_min_rows" (rows from which linears use the fp32 register-tiled GEMM core when the tensor-core path is off, default 128);
+ * "tc_gemm" (0/1, default 1: linears with >= "tc_min_rows" (default 32) rows run on the hand-written tcgen05 mainloop - 3xTF32,
+ * fp32-class accuracy, fp32 weights read once and split on chip: csrc/ua2_umma.cu, csrc/ua2_tcgemm.cu);
+ * "resblock_fused" (0/1, default 1: the 64-channel SEANet residual blocks of the codec handle run as one kernel, csrc/ua2_resblock.cu);
+ * "conv_tc" (0/1, default 1: causal convolutions with Cin * K >= 1024 and transposed convolutions with Cin >= 128 run as im2col +
+ * the tcgen05 GEMM instead of the fp32 register-tiled core - csrc/ua2_convtc.cu);
+ * "attn_ring" (0/1: KV-cache attention launches with >= 592 (row, group, 64-key split) items run on persistent CTAs that stream the
+ * K / V chunks through a 3-slot bulk-copy ring instead of one fetch-compute-exit CTA per item - csrc/ua2_attn.cu);
  * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with
  * -DUA2_GEMV3_TAIL_PREFETCH=1 - measured slower, see profiles/r1_l2_prefetch_experiment.md) */
 int ua2_set_global_option(const char* name, int value);

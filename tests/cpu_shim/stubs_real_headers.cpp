@@ -6,9 +6,7 @@
 namespace ua2 {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
-struct TcWeightCache {};
-TcWeightCache* tc_cache_create() { return nullptr; }
-void tc_cache_destroy(TcWeightCache*) {}
+size_t tc_slots_max_floats() { return 16; }
 static int g_tc_avail = 1;
 bool tc_gemm_available() { return g_tc_avail != 0; }
 int get_tc_gemm() { return g_tc_avail; }

@@ -27,15 +27,12 @@ inline cudaError_t launch(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 gr
   if (lc.launch_counter) ++*lc.launch_counter;
   return shim::run_grid(kernel, grid, block, args...);
 }
-struct TcWeightCache;
-inline TcWeightCache* tc_cache_create() { return nullptr; }
+inline size_t tc_slots_max_floats() { return 16; }
 struct TcWorkspace {
-  TcWeightCache* cache = nullptr;
-  bool force_persistent = false;
   float* a = nullptr;
   size_t a_floats = 0;
-  float* w = nullptr;
-  size_t w_floats = 0;
+  float* slots = nullptr;
+  size_t slots_floats = 0;
   float* c = nullptr;
   size_t c_floats = 0;
 };

@@ -108,7 +108,7 @@ def shim2(tmp_path_factory):
         src = open(os.path.join(CSRC, name + ".cu")).read()
         src = src[:src.index("\nusing namespace ua2;")]  # kernels + launchers; the handle code behind it needs the CUDA runtime
         src = re.sub(r"extern __shared__[^;]*;", "", src)
-        src = re.sub(r'#include ["<](\.\./\.\./include/ua2_b200\.h|ua2_kernels\.cuh|ua2_philox\.cuh|cuda_bf16\.h)[">]', "", src)
+        src = re.sub(r'#include ["<](\.\./\.\./include/ua2_b200\.h|ua2_kernels\.cuh|ua2_umma\.cuh|ua2_philox\.cuh|cuda_bf16\.h)[">]', "", src)
         open(os.path.join(d, name + "_kernels.inc"), "w").write(src)
     so = os.path.join(d, "libshim2.so")
     cmd = GXX + [ "-I", d, "-I", SHIM, "-I", CSRC,

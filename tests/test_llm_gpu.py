@@ -19,7 +19,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
-TC_DEFAULT = 1  # library default of the global option tc_gemm (builds with the CUTLASS headers)
+TC_DEFAULT = 1  # library default of the global option tc_gemm
 PF_DEFAULT = (0, 0)  # library defaults of gemv3_prefetch_mb / gemv3_prefetch_idle_mb
 
 
@@ -32,11 +32,10 @@ def models():
     return out
 
 
-@pytest.mark.parametrize("mode", ["eager", "graph", "chain", "graph_direct_local_attn"])
+@pytest.mark.parametrize("mode", ["eager", "graph", "graph_direct_local_attn"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_frames_match_reference_golden(models, golden, case, mode):
-    """eager: one launch per kernel; graph: CUDA-graph replay with PDL edges; chain: persistent multi-op cooperative
-    kernels (B = 1 only - larger batches fall back to the graph path); graph_direct_local_attn: the local decoder's
+    """eager: one launch per kernel; graph: CUDA-graph replay with PDL edges; graph_direct_local_attn: the local decoder's
     <= 8-key attention computed inside the proj kernel's prologue instead of its own split-softmax launch (option
     attn_direct = 1), with the tail-prefetch planner enabled (a no-op unless built with UA2_GEMV3_TAIL_PREFETCH)."""
     name, cname, kind, B, S, nf, topk, temp, cfg_scale = case
@@ -45,7 +44,6 @@ def test_frames_match_reference_golden(models, golden, case, mode):
     from uniaudio2_b200 import _lib
 
     m.set_option("graph", 0 if mode.startswith("eager") else 1)
-    m.set_option("chain", 1 if mode == "chain" else 0)
     m.set_option("attn_direct", 1 if mode == "graph_direct_local_attn" else 0)
     pf = 48 if mode == "graph_direct_local_attn" else 0
     _lib.check(_lib.lib().ua2_set_global_option(b"gemv3_prefetch_mb", pf))
@@ -153,7 +151,7 @@ def test_rng_modes_run(models):
         # second half of the frames runs with forbid_prefix = reason_card
         assert int(f[2:, :, 1:].min()) >= REASON_CARD["tiny"]
     m.rng_mode = "torch"
-    assert m.last_launch_count() >= 19  # chain mode: 1 frame_begin + 9 persistent chains + 9 samplers
+    assert m.last_launch_count() >= 19
 
 
 def test_task_generators(models):
@@ -227,22 +225,19 @@ def test_batch32_caption_config():
     from uniaudio2_b200 import _lib
 
     L = _lib.lib()
-    # (tc_gemm, tc_min_rows, tc_persistent_weights): skinny kernels; tensor cores for the 32-row frames with split weights
-    # re-made per call; the same with the split weights cached across calls (second frame onwards hits the cache)
-    for (tc, min_rows, persist) in ((0, 128, 0), (1, 16, 0), (1, 16, 1)):
+    # (tc_gemm, tc_min_rows): skinny kernels; the tcgen05 mainloop (fp32 weights split on chip, csrc/ua2_umma.cu) for frames of >= 8 rows
+    for (tc, min_rows) in ((0, 128), (1, 8)):
         _lib.check(L.ua2_set_global_option(b"tc_gemm", tc))
         _lib.check(L.ua2_set_global_option(b"tc_min_rows", min_rows))
-        _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", persist))
         try:
             for (B, S, nf) in ((32, 21, 4), (11, 13, 3)):
                 o = run_case(orc, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, False, explicit_noise=True)
                 r = run_case(m, "mixed", cfg, B, S, nf, 1, 1.0, 1.0, REASON_CARD["tiny"], 11, True, device="cuda", explicit_noise=True)
-                assert torch.equal(r["frames"].cpu(), o["frames"]), (tc, min_rows, persist, B)
+                assert torch.equal(r["frames"].cpu(), o["frames"]), (tc, min_rows, B)
                 assert _rel(m.debug_buffer("text_logits", B).cpu(), o["text_logits"][-1]) < REL_TOL
         finally:
             _lib.check(L.ua2_set_global_option(b"tc_gemm", TC_DEFAULT))
             _lib.check(L.ua2_set_global_option(b"tc_min_rows", 32))
-            _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", 0))
 
 
 def test_cache_filled_to_the_last_slot():

@@ -83,7 +83,7 @@ def main():
                         emit(kind="prefill", B=B, S=S, rows=rows, what=what, gemm="tcgen05 3xTF32" if tc else "fp32 SIMT tiles",
                              ms=round(ms, 2), rows_per_s=round(rows / (ms * 1e-3), 1),
                              fp32_equiv_tflops=round(2.0 * rows * P_GLOBAL_LAYERS / (ms * 1e-3) / 1e12, 2), launches=model.last_launch_count())
-                    _lib.check(L.ua2_set_global_option(b"tc_gemm", 0))
+                    _lib.check(L.ua2_set_global_option(b"tc_gemm", 1))
 
             if "caption32" in only:
                 B, S, NF = 32, 189, 64
@@ -91,11 +91,10 @@ def main():
                 text_mask = torch.zeros(B, 1, bench.NQ + 1, dtype=torch.bool, device=dev)
                 text_mask[..., -1] = True
                 have_tc = L.ua2_set_global_option(b"tc_gemm", 1) == 0
-                # (tensor cores, rows from which frames use them, split weights cached across calls)
-                for (tc, min_rows, persist) in (((0, 128, 0), (1, 128, 0), (1, 16, 0), (1, 16, 1)) if have_tc else ((0, 128, 0),)):
+                # (tensor cores, rows from which frames use them)
+                for (tc, min_rows) in (((0, 128), (1, 128), (1, 16)) if have_tc else ((0, 128),)):
                     _lib.check(L.ua2_set_global_option(b"tc_gemm", tc))
                     _lib.check(L.ua2_set_global_option(b"tc_min_rows", min_rows))
-                    _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", persist))
 
                     def run():
                         prefill(tokens, mask)
@@ -109,13 +108,12 @@ def main():
                     ms = timed(run, 1)
                     pre = timed(lambda: prefill(tokens, mask), 1)
                     emit(kind="caption32", B=B, S=S, frames=NF,
-                         gemm=("tcgen05 3xTF32 prefill" + (" + frames" if min_rows <= B else "") + (", cached split weights" if persist else ""))
+                         gemm=("tcgen05 3xTF32 (weights split on chip) prefill" + (" + frames" if min_rows <= B else ""))
                          if tc else "fp32 SIMT tiles / skinny kernels", total_ms=round(ms, 1),
                          prefill_ms=round(pre, 1), ms_per_frame=round((ms - pre) / NF, 2),
                          text_tokens_per_s=round(B * NF / (ms * 1e-3), 1), clips_per_s=round(B / (ms * 1e-3), 2))
-                _lib.check(L.ua2_set_global_option(b"tc_gemm", 0))
+                _lib.check(L.ua2_set_global_option(b"tc_gemm", 1))
                 _lib.check(L.ua2_set_global_option(b"tc_min_rows", 32))
-                _lib.check(L.ua2_set_global_option(b"tc_persistent_weights", 0))
 
             if "ttm500" in only:
                 tp, text = bench.synthetic_prompt(0)

@@ -65,10 +65,9 @@ def main():
         print("launches per estimator call:", m.last_launch_count())
         return
     fl = flops(2, T)
-    for persistent in (0, 1):
-        _lib.check(_lib.lib().ua2_set_global_option(b"tc_persistent_weights", persistent))
+    if True:
         ms = timed(lambda: m(x, timestep=t), a.reps)
-        print(json.dumps(dict(what="estimator call, CFG batch 2 x %d frames" % T, tc_persistent_weights=persistent,
+        print(json.dumps(dict(what="estimator call, CFG batch 2 x %d frames, 3xTF32 (fp32 weights split on chip)" % T,
                               launches=m.last_launch_count(), ms=round(ms, 3), algorithmic_TFLOP=round(fl / 1e12, 3),
                               fp32_equiv_TFLOPs=round(fl / ms / 1e9, 1), tf32_mma_TFLOPs=round(3 * fl / ms / 1e9, 1))))
     if a.bf16:
@@ -87,7 +86,7 @@ def main():
     t_span = torch.linspace(0, 1, a.steps + 1)
     ms = timed(lambda: cfm.solve_euler(z, ic, 0, t_span, mu, None, 1.5), max(3, a.reps // 3))
     print(json.dumps(dict(what="solve_euler, %d steps, 20 s window" % a.steps, ms=round(ms, 2), audio_seconds=T / 25.0,
-                          x_realtime=round(T / 25.0 / (ms / 1e3), 1), tc_persistent_weights=1)))
+                          x_realtime=round(T / 25.0 / (ms / 1e3), 1))))
 
 
 if __name__ == "__main__":

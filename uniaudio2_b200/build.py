@@ -18,24 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
-def _cutlass_include():
-    """CUTLASS / CuTe header tree vendored in the image (site-packages/flashinfer/data/cutlass); None if absent."""
-    cands = [os.environ.get("UA2_CUTLASS_DIR", "")]
-    for p in sys.path:
-        cands.append(os.path.join(p, "flashinfer", "data", "cutlass"))
-        cands.append(os.path.join(p, "tilelang", "3rdparty", "cutlass"))
-    for c in cands:
-        if c and os.path.exists(os.path.join(c, "include", "cutlass", "gemm", "collective", "collective_builder.hpp")):
-            return c
-    return None
-
-
-CUTLASS = _cutlass_include()
-# the tensor-core GEMM translation unit uses the CUTLASS collective builders when the headers exist (else a stub)
-_CUTLASS_FLAGS = (["-DUA2_HAVE_CUTLASS", "--expt-relaxed-constexpr", "-diag-suppress", "20012", "-I", os.path.join(CUTLASS, "include"),
-                   "-I", os.path.join(CUTLASS, "tools", "util", "include")] if CUTLASS else [])
-EXTRA = {"ua2_tcgemm.cu": ["-DUA2_HAVE_CUTLASS"] if CUTLASS else [], "ua2_tcgemm_t128.cu": _CUTLASS_FLAGS, "ua2_tcgemm_t64.cu": _CUTLASS_FLAGS,
-         "ua2_tcgemm_bf16.cu": _CUTLASS_FLAGS, "ua2_dit.cu": ["-DUA2_HAVE_CUTLASS"] if CUTLASS else []}
+EXTRA = {}  # per-file extra flags (none: every kernel, the tcgen05 mainloop included, is this repo's own source)
 
 
 def _sources():

@@ -179,17 +179,17 @@ int reserve_tc(ua2_codec* h, size_t M) {
   if (h->tc.a) {
     UA2_CHECK_CUDA(cudaDeviceSynchronize());
     cudaFree(h->tc.a);
-    cudaFree(h->tc.w);
+    cudaFree(h->tc.slots);
     cudaFree(h->tc.c);
     h->tc = TcWorkspace();
     h->tc_rows = 0;
   }
   const size_t kmax = std::max(C, F), nmax = std::max(3 * C, F);
-  h->tc.a_floats = M * 3 * kmax;
-  h->tc.w_floats = std::max({3 * C * 3 * C, F * 3 * C, C * 3 * F, C * 3 * C, tc_slots_max_floats()});
+  h->tc.a_floats = M * 2 * kmax;
+  h->tc.slots_floats = tc_slots_max_floats();
   h->tc.c_floats = M * nmax;
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.a, h->tc.a_floats * 4));
-  UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.w, h->tc.w_floats * 4));
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.slots, h->tc.slots_floats * 4));
   UA2_CHECK_CUDA(cudaMalloc((void**)&h->tc.c, h->tc.c_floats * 4));
   h->tc_rows = M;
   return UA2_OK;
@@ -401,7 +401,7 @@ int ua2_codec_destroy(ua2_codec* h) {
   if (h->bidx) cudaFree(h->bidx);
   if (h->tc.a) {
     cudaFree(h->tc.a);
-    cudaFree(h->tc.w);
+    cudaFree(h->tc.slots);
     cudaFree(h->tc.c);
   }
   delete h;

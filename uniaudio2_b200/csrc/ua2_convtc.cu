@@ -185,11 +185,9 @@ cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w
   cudaError_t e;
   if ((e = grow(&g_ws.a, &g_ws.a_floats, (size_t)R * KT)) != cudaSuccess) return e;
   if ((e = grow(&g_ws.c, &g_ws.c_floats, (size_t)R * Cout)) != cudaSuccess) return e;
-  if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 3 * KT)) != cudaSuccess) return e;
-  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, std::max((size_t)Cout * 3 * KT, tc_slots_max_floats()))) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 2 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.slots, &g_ws.tc.slots_floats, tc_slots_max_floats())) != cudaSuccess) return e;
   if ((e = grow(&g_ws.tc.c, &g_ws.tc.c_floats, (size_t)R * Cout)) != cudaSuccess) return e;
-  if (!g_ws.tc.cache) g_ws.tc.cache = tc_cache_create();
-  g_ws.tc.force_persistent = true;  // codec weights are long-lived: keep their tf32 split (12 B per parameter)
   for (long long m0 = 0; m0 < M; m0 += R) {
     const int rows = (int)std::min<long long>(R, M - m0);
     const long long n = (long long)rows * KT;
@@ -244,11 +242,9 @@ cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float*
   cudaError_t e;
   if ((e = grow(&g_ws.a, &g_ws.a_floats, (size_t)R * KT)) != cudaSuccess) return e;
   if ((e = grow(&g_ws.c, &g_ws.c_floats, (size_t)R * N)) != cudaSuccess) return e;
-  if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 3 * KT)) != cudaSuccess) return e;
-  if ((e = grow(&g_ws.tc.w, &g_ws.tc.w_floats, std::max((size_t)N * 3 * KT, tc_slots_max_floats()))) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.a, &g_ws.tc.a_floats, (size_t)R * 2 * KT)) != cudaSuccess) return e;
+  if ((e = grow(&g_ws.tc.slots, &g_ws.tc.slots_floats, tc_slots_max_floats())) != cudaSuccess) return e;
   if ((e = grow(&g_ws.tc.c, &g_ws.tc.c_floats, (size_t)R * N)) != cudaSuccess) return e;
-  if (!g_ws.tc.cache) g_ws.tc.cache = tc_cache_create();
-  g_ws.tc.force_persistent = true;
   for (long long m0 = 0; m0 < M; m0 += R) {
     const int rows = (int)std::min<long long>(R, M - m0);
     if ((e = launch(lc, convtr_im2col_kernel, dim3((rows + 31) / 32, (Cin + 31) / 32), dim3(32, 8), 0, x, g_ws.a, Cin, T_in, Tj, pre_elu, m0,

@@ -457,7 +457,7 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
   const size_t D = (size_t)c.num_attention_heads * c.attention_head_dim, I = c.in_channels, O = c.out_channels;
   if (M > h->rows) {
     if (h->rows) UA2_CHECK_CUDA(cudaDeviceSynchronize());
-    free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.w, &h->tc.c});
+    free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.slots, &h->tc.c});
     RUN(dmalloc(&h->col, M * 3 * std::max(I, D)));
     RUN(dmalloc(&h->h, M * D));
     RUN(dmalloc(&h->n, M * D));
@@ -470,17 +470,15 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
     RUN(dmalloc(&h->stats, 2 * M + 8));
     if (tc_gemm_available()) {  // scratch of the tcgen05 3xTF32 path: split activations / weights, raw product
       const size_t kmax = std::max({3 * I, 4 * D, 3 * D}), nmax = std::max({4 * D, 3 * D, O});
-      h->tc.a_floats = M * 3 * kmax;
-      h->tc.w_floats = std::max({D * 9 * I, 3 * D * 3 * D, 4 * D * 3 * D, D * 12 * D, O * 9 * D, O * 3 * O, tc_slots_max_floats()});
+      h->tc.a_floats = M * 2 * kmax;
+      h->tc.slots_floats = tc_slots_max_floats();
       h->tc.c_floats = M * nmax;
       RUN(dmalloc(&h->tc.a, h->tc.a_floats));
-      RUN(dmalloc(&h->tc.w, h->tc.w_floats));
+      RUN(dmalloc(&h->tc.slots, h->tc.slots_floats));
       RUN(dmalloc(&h->tc.c, h->tc.c_floats));
       if (h->a16) cudaFree(h->a16);
       h->a16 = nullptr;
       UA2_CHECK_CUDA(cudaMalloc((void**)&h->a16, M * kmax * sizeof(__nv_bfloat16)));
-      if (!h->tc.cache) h->tc.cache = tc_cache_create();
-      h->tc.force_persistent = true;  // every call reuses all 0.9 B parameters: keep their tf32 split (12 B / parameter)
     }
     h->rows = M;
   }
@@ -513,8 +511,8 @@ int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, 
     CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, x, h->a16, n4));
     // hand-written tcgen05 kind::f16 mainloop (ua2_umma.cu, bf16 mode): fp32 accumulation in TMEM, product in the handle's buffer
     const UmmaPlan pl = umma_plan(M, N, 1, K, true);
-    cudaError_t e = pl.slot_floats <= h->tc.w_floats ? run_umma_bf16(lc, h->a16, it->second, h->tc.c, N, h->tc.w, M, N, K, pl) : cudaErrorNotSupported;
-    if (e == cudaSuccess) e = run_umma_fixup(lc, h->tc.c, N, h->tc.w, M, N, 1, pl);
+    cudaError_t e = pl.slot_floats <= h->tc.slots_floats ? run_umma_bf16(lc, h->a16, it->second, h->tc.c, N, h->tc.slots, M, N, K, pl) : cudaErrorNotSupported;
+    if (e == cudaSuccess) e = run_umma_fixup(lc, h->tc.c, N, h->tc.slots, M, N, 1, pl);
     if (e == cudaSuccess) {
       *src = h->tc.c;
       return UA2_OK;
@@ -671,12 +669,11 @@ int ua2_dit_create(const ua2_dit_cfg* cfg, ua2_dit** out) {
 int ua2_dit_destroy(ua2_dit* h) {
   if (!h) return UA2_OK;
   cudaDeviceSynchronize();
-  free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.w, &h->tc.c,
+  free_list({&h->col, &h->h, &h->n, &h->qkv, &h->q, &h->k, &h->v, &h->att, &h->ff, &h->stats, &h->tc.a, &h->tc.slots, &h->tc.c,
              &h->tproj, &h->temb, &h->tsemb, &h->t6, &h->ttmp, &h->noise, &h->sinp, &h->sout});
   for (void* p : h->owned) cudaFree(p);
   for (auto& kv : h->w16) cudaFree(kv.second);
   if (h->a16) cudaFree(h->a16);
-  tc_cache_destroy(h->tc.cache);
   delete h;
   return UA2_OK;
 }

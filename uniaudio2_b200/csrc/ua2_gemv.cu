@@ -20,24 +20,6 @@ namespace {
 
 using namespace v1dev;
 
-constexpr int U = 8;  // k-iterations (of 128 floats) per load batch
-
-__device__ __forceinline__ void load_batch(const float* rowA, const float* rowB, int it0, int lane, int K,
-                                           float4 (&wa)[U], float4 (&wb)[U]) {
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int k4 = ((it0 + u) * 32 + lane) * 4;
-    if (k4 < K) {
-      wa[u] = ldg_stream(rowA + k4);
-      wb[u] = ldg_stream(rowB + k4);
-    } else {
-      wa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      wb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-}
-
-
 // ---- fused prologue: produce the MT x Kp activation tile in shared memory (all threads of the CTA)
 template <int MT, int PRO>
 __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs, float (*red)[8], int Kp, int m0,
@@ -171,79 +153,6 @@ __device__ __forceinline__ void stage_activations(const GemvParams& p, float* xs
   __syncthreads();
 
 }
-
-template <int MT, int PRO, int EPI>
-__global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
-  extern __shared__ __align__(16) float xs[];  // MT x Kp
-  __shared__ float red[8][8];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const int K = p.K;
-  const int nIt = (K + 127) >> 7;
-  const int Kp = nIt << 7;
-  const int m0 = blockIdx.x * MT;
-  const int mcount = min(MT, p.M - m0);
-  const int n_units = (EPI == EPI_SWIGLU) ? p.N : (p.N >> 1);
-  int unit = blockIdx.y * nwarps + warp;
-  const int unit_stride = gridDim.y * nwarps;
-
-  // ---- issue the first weight batch before anything that depends on the producer kernel
-  float4 wa[U], wb[U];
-  const float *rowA = nullptr, *rowB = nullptr;
-  int nA = 0, nB = 0;
-  if (unit < n_units) {
-    unit_rows<EPI>(p, unit, rowA, rowB, nA, nB);
-    load_batch(rowA, rowB, 0, lane, K, wa, wb);
-  }
-  pdl_launch_dependents();
-  pdl_wait();
-
-  stage_activations<MT, PRO>(p, xs, red, Kp, m0, mcount);
-
-  // ---- main loop: two weight rows per warp, all M rows of the tile at once
-  bool first = true;
-  while (unit < n_units) {
-    if (!first) unit_rows<EPI>(p, unit, rowA, rowB, nA, nB);
-    float accA[MT], accB[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) accA[m] = accB[m] = 0.f;
-    for (int it0 = 0; it0 < nIt; it0 += U) {
-      if (!(first && it0 == 0)) load_batch(rowA, rowB, it0, lane, K, wa, wb);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int k4 = ((it0 + u) * 32 + lane) * 4;
-        if (k4 < Kp) {
-#pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const float4 xv = *reinterpret_cast<const float4*>(xs + m * Kp + k4);
-            accA[m] = fmaf(wa[u].x, xv.x, accA[m]);
-            accA[m] = fmaf(wa[u].y, xv.y, accA[m]);
-            accA[m] = fmaf(wa[u].z, xv.z, accA[m]);
-            accA[m] = fmaf(wa[u].w, xv.w, accA[m]);
-            accB[m] = fmaf(wb[u].x, xv.x, accB[m]);
-            accB[m] = fmaf(wb[u].y, xv.y, accB[m]);
-            accB[m] = fmaf(wb[u].z, xv.z, accB[m]);
-            accB[m] = fmaf(wb[u].w, xv.w, accB[m]);
-          }
-        }
-      }
-    }
-    first = false;
-    // ---- warp reduction; lane m keeps row m
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const float sa = warp_sum(accA[m]);
-      const float sb = warp_sum(accB[m]);
-      if (lane == m) {
-        a = sa;
-        b = sb;
-      }
-    }
-    epilogue<EPI>(p, lane, mcount, m0, a, b, nA, nB);
-    unit += unit_stride;
-  }
-}
-
 
 // =====================================================================================================
 // v2: same math, weights fetched by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) instead of registers.
@@ -396,7 +305,6 @@ __global__ void __launch_bounds__(V2_WARPS * 32) gemv2_kernel(const GemvParams p
   }
 }
 
-int g_gemv_impl = 3;
 int g_sgemm_min_rows = 128;
 
 int g_sm_count = 0;
@@ -417,43 +325,25 @@ cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
   const int n_units = (EPI == EPI_SWIGLU) ? p.N : p.N / 2;
   const int m_tiles = (p.M + MT - 1) / MT;
   const size_t kMaxSmem = 220 * 1024;
-  if (g_gemv_impl != 1) {
-    auto kern = gemv2_kernel<MT, PRO, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-      if (e != cudaSuccess) return e;
-      e = prefer_max_smem(kern);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    const size_t smem = xbytes + (size_t)V2_WARPS * STAGES * 2 * KC * sizeof(float);
-    if (smem > kMaxSmem) return cudaErrorInvalidValue;
-    // one wave of co-resident CTAs (shared memory bounds the CTAs per SM); beyond that warps loop over units
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int gy = (n_units + V2_WARPS - 1) / V2_WARPS;
-    const int cap = sm_count() * per_sm;
-    if (gy > cap) gy = cap;
-    return launch(lc, kern, dim3(m_tiles, gy), dim3(V2_WARPS * 32), smem, p);
-  }
-  auto kern = gemv_kernel<MT, PRO, EPI>;
-  static bool attr_set1 = false;
-  if (!attr_set1) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  auto kern = gemv2_kernel<MT, PRO, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) return e;
     e = prefer_max_smem(kern);
     if (e != cudaSuccess) return e;
-    attr_set1 = true;
+    attr_set = true;
   }
-  if (xbytes > 200 * 1024) return cudaErrorInvalidValue;
-  // 8 warps per CTA when that still gives >= 2 CTAs per SM, else 4 (finer granules balance small N)
-  int nwarps = (n_units >= 8 * 2 * sm_count()) ? 8 : 4;
-  int gy = (n_units + nwarps - 1) / nwarps;
-  const int cap = sm_count() * 8;  // persistent cap for very tall matrices (lm_head): warps loop over units
+  const size_t smem = xbytes + (size_t)V2_WARPS * STAGES * 2 * KC * sizeof(float);
+  if (smem > kMaxSmem) return cudaErrorInvalidValue;
+  // one wave of co-resident CTAs (shared memory bounds the CTAs per SM); beyond that warps loop over units
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int gy = (n_units + V2_WARPS - 1) / V2_WARPS;
+  const int cap = sm_count() * per_sm;
   if (gy > cap) gy = cap;
-  return launch(lc, kern, dim3(m_tiles, gy), dim3(nwarps * 32), xbytes, p);
+  return launch(lc, kern, dim3(m_tiles, gy), dim3(V2_WARPS * 32), smem, p);
 }
 
 template <int PRO, int EPI>
@@ -473,9 +363,7 @@ cudaError_t launch_mt(const LaunchCtx& lc, const GemvParams& p) {
 }  // namespace
 
 void set_sgemm_min_rows(int v) { g_sgemm_min_rows = v < 1 ? 1 : v; }
-int get_gemv_impl() { return g_gemv_impl; }
 int get_sgemm_min_rows() { return g_sgemm_min_rows; }
-void set_gemv_impl(int v) { g_gemv_impl = (v >= 1 && v <= 3) ? v : 3; }
 
 namespace {
 // Record / replay the frame's sequence of linears (GemvSeq) and attach the tail-prefetch specs of the following ones.
@@ -498,7 +386,7 @@ const GemvParams& with_prefetch(const LaunchCtx& lc, int epi, const GemvParams& 
   const int i = sq->pos++;
   if (i >= n || sq->ops[i].W != p.W || sq->ops[i].M != p.M) return p;  // not the recorded frame: no prefetch
   const size_t budget = gemv3_prefetch_budget(sq->ops[i].idle_after);
-  if (budget == 0 || g_gemv_impl != 3) return p;
+  if (budget == 0) return p;
   GemvSeqEntry nxt[PF_MAX];
   for (int j = 0; j < PF_MAX; ++j) nxt[j] = sq->ops[(i + 1 + j) % n];  // wraps into the next frame (same weights)
   tmp = p;
@@ -555,29 +443,19 @@ cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams&
     }
   }
   if (pro == PRO_ATTN_DIRECT) {
-    if (g_gemv_impl != 3 || epi != EPI_RESADD || p.hs != 64 || p.S_max > ATTN_DIRECT_MAX_KEYS) return cudaErrorInvalidValue;
+    if (epi != EPI_RESADD || p.hs != 64 || p.S_max > ATTN_DIRECT_MAX_KEYS) return cudaErrorInvalidValue;
     return launch_gemv3(lc, pro, epi, p, 1);
   }
-  if (g_gemv_impl == 3 && pro < PRO_LAYERNORM && epi < EPI_GELU) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
+  if (pro < PRO_LAYERNORM && epi < EPI_GELU) return launch_gemv3(lc, pro, epi, p, p.n_splits > 0 ? p.n_splits : 1);
+  // the remaining (prologue, epilogue) pairs belong to the Moshi-family layers (llm_modules/transformer.py:430-588, the codec
+  // transformer and ua2_stream.cu): LayerNorm / GELU / LayerScale / interleaved RoPE, on the per-warp bulk-copy-ring kernel
 #define UA2_CASE(P, E) \
   if (pro == P && epi == E) return launch_mt<P, E>(lc, p);
-  UA2_CASE(PRO_PLAIN, EPI_STORE)
-  UA2_CASE(PRO_PLAIN, EPI_RESADD)
-  UA2_CASE(PRO_PLAIN, EPI_SWIGLU)
-  UA2_CASE(PRO_PLAIN, EPI_QKV)
-  UA2_CASE(PRO_RMSNORM, EPI_STORE)
-  UA2_CASE(PRO_RMSNORM, EPI_RESADD)
-  UA2_CASE(PRO_RMSNORM, EPI_SWIGLU)
-  UA2_CASE(PRO_RMSNORM, EPI_QKV)
-  UA2_CASE(PRO_GATHER, EPI_STORE)
-  UA2_CASE(PRO_ATTN, EPI_RESADD)
   UA2_CASE(PRO_LAYERNORM, EPI_QKV_IL)
   UA2_CASE(PRO_LAYERNORM, EPI_GELU)
   UA2_CASE(PRO_ATTN, EPI_SCALE_RESADD)
   UA2_CASE(PRO_PLAIN, EPI_SCALE_RESADD)
   UA2_CASE(PRO_PLAIN, EPI_QKV_IL)
-  // Moshi-family streaming layer (ua2_stream.cu): LayerNorm in front of a plain store (in_proj before the ring append) and
-  // of the SiLU gating, RMSNorm in front of the GELU feed-forward
   UA2_CASE(PRO_LAYERNORM, EPI_STORE)
   UA2_CASE(PRO_LAYERNORM, EPI_SWIGLU)
   UA2_CASE(PRO_RMSNORM, EPI_GELU)

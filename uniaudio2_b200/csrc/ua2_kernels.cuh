@@ -31,22 +31,15 @@ struct PfSpec {
 };
 constexpr int PF_MAX = 3;
 
-// scratch of the tensor-core path for many-row linears (ua2_tcgemm.cu): split operands and the raw product
-struct TcWeightCache;
-TcWeightCache* tc_cache_create();
-void tc_cache_destroy(TcWeightCache* c);
-size_t tc_cache_bytes(const TcWeightCache* c);
-void set_tc_persistent(int v);
-int get_tc_persistent();
+// scratch of the tensor-core path for many-row linears (ua2_tcgemm.cu / ua2_umma.cu): split activations, stream-K side slots, raw product
 void set_tc_min_rows(int v);
 int get_tc_min_rows();
+size_t tc_slots_max_floats();  // largest side-slot scratch a launch may need: 148 CTAs x 256 x 128 floats
 struct TcWorkspace {
-  TcWeightCache* cache = nullptr;  // optional persistent split weights (option tc_persistent_weights)
-  bool force_persistent = false;   // use `cache` regardless of the global option (handles whose every call reuses all weights)
-  float* a = nullptr;  // (M, 3K)
+  float* a = nullptr;  // [2][M][K] hi / lo planes of the activation rows
   size_t a_floats = 0;
-  float* w = nullptr;  // (N_total, 3K)
-  size_t w_floats = 0;
+  float* slots = nullptr;  // partial tiles of stream-K continuation CTAs
+  size_t slots_floats = 0;
   float* c = nullptr;  // (M, N_total)
   size_t c_floats = 0;
 };
@@ -118,14 +111,9 @@ int gemv3_make_pf(const GemvSeqEntry* next, int n_next, size_t budget_bytes, PfS
 cudaError_t launch_gemv(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
 cudaError_t launch_sgemm_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p, float* stats_ws);
 cudaError_t launch_tc_linear(const LaunchCtx& lc, int pro, int epi, const GemvParams& p);
-void set_tc_impl(int v);
-int get_tc_impl();
-size_t tc_slots_max_floats();  // side-slot scratch (TcWorkspace::w) the hand-written mainloop may need: 148 CTAs x 256 x 128 floats
 void set_tc_gemm(int v);
 int get_tc_gemm();
 bool tc_gemm_available();
-void set_gemv_impl(int v);
-int get_gemv_impl();
 int get_sgemm_min_rows();
 void set_sgemm_min_rows(int v);
 cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B,

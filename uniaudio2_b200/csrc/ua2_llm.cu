@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "../../include/ua2_b200.h"
-#include "ua2_chain.cuh"
 #include "ua2_kernels.cuh"
 
 namespace ua2 {
@@ -56,22 +55,12 @@ struct ua2_llm {
   size_t sg_ws_floats = 0;
   int64_t h_final_numel = 0, text_logits_numel = 0, audio_logits_numel = 0;
   std::vector<void*> owned;
-  // persistent chain path (B = 1): op lists in device memory, grid-barrier counters
-  ChainOp* d_ops_global = nullptr;
-  int n_ops_global = 0;
-  std::vector<ChainOp*> d_ops_local;
-  std::vector<int> n_ops_local;
-  unsigned* d_chain_sync = nullptr;
-  unsigned long long* d_chain_prof = nullptr;  // option chain_profile: clocks of the GLOBAL chain's ops (dev tool)
-  int chain_ctas = 0;
-  int chain_max_splits = 0;
-  bool chain_ok = false;
   // options / stats
   TcWorkspace tcws;        // scratch of the tcgen05 3xTF32 path (many-row linears of forward_prefix)
   int opt_chunk_rows = 0;  // prefill rows per pass (0 = M_cap)
   bool rows_are_batch = false;  // generate_frame: activation row m belongs to batch row m (prefill flattens B x T)
   int opt_attn_direct = 0;  // local decoder: attention inside the proj prologue (32 fewer launches; measured 1466 vs 1471 tok/s: off)
-  int opt_graph = 1, opt_pdl = 1, opt_chain = 0;  // chain: measured 1184 vs 1438 tok/s for graph+PDL (profiles/r1_chain_experiment.md)
+  int opt_graph = 1, opt_pdl = 1;  // a persistent one-kernel "chain" form measured 18 % slower than graph + PDL (profiles/r1_chain_experiment.md) and was removed
   int last_launches = 0;
   unsigned long long frame_counter = 0;
   struct GraphEntry {
@@ -143,7 +132,7 @@ cudaError_t run_block(ua2_llm* h, const LaunchCtx& lc, Stack& s, int l, float* x
     if ((e = launch_gemv(lc, PRO_RMSNORM, EPI_QKV, p)) != cudaSuccess) return e;
   }
   // short caches (the local decoder's <= 8 codebook steps): attention runs inside the proj kernel's prologue
-  const bool direct = h->opt_attn_direct && s.S_max <= ATTN_DIRECT_MAX_KEYS && hs == 64 && M <= 16 && get_gemv_impl() == 3;
+  const bool direct = h->opt_attn_direct && s.S_max <= ATTN_DIRECT_MAX_KEYS && hs == 64 && M <= 16;
   if (!direct) {  // B: split-softmax attention over the cache
     AttnParams a;
     a.q = h->qbuf;
@@ -345,273 +334,6 @@ cudaError_t run_heads(ua2_llm* h, const LaunchCtx& lc, int B, int rows) {
 }
 
 
-// ---------------------------------------------------------------------------------------------- chain op lists (B = 1)
-void chain_block_ops(ua2_llm* h, std::vector<ChainOp>& ops, Stack& s, int l, float* x, const int32_t* pos, const int32_t* bidx,
-                     int max_splits) {
-  const ua2_gpt_cfg& c = s.cfg;
-  const LayerW& w = s.layers[l];
-  const int D = c.n_embd, hs = c.head_size, QD = c.n_head * hs;
-  {
-    ChainOp o;
-    o.type = OP_GEMV;
-    o.pro = PRO_RMSNORM;
-    o.epi = EPI_QKV;
-    GemvParams& p = o.g;
-    p.W = w.qkv;
-    p.N = (c.n_head + 2 * c.n_query_groups) * hs;
-    p.K = D;
-    p.M = 1;
-    p.X = x;
-    p.ldx = D;
-    p.norm_w = w.norm1;
-    p.eps = c.norm_eps;
-    p.pos = pos;
-    p.bidx = bidx;
-    p.n_head = c.n_head;
-    p.n_groups = c.n_query_groups;
-    p.hs = hs;
-    p.q_out = h->qbuf;
-    p.k_cache = s.kc[l];
-    p.v_cache = s.vc[l];
-    p.cos = s.cos;
-    p.sin = s.sin;
-    p.S_max = s.S_max;
-    ops.push_back(o);
-  }
-  {
-    ChainOp o;
-    o.type = OP_ATTN;
-    AttnParams& a = o.a;
-    a.q = h->qbuf;
-    a.k_cache = s.kc[l];
-    a.v_cache = s.vc[l];
-    a.pos = pos;
-    a.bidx = bidx;
-    a.o_part = h->o_part;
-    a.ml_part = h->ml_part;
-    a.M = 1;
-    a.n_head = c.n_head;
-    a.n_groups = c.n_query_groups;
-    a.hs = hs;
-    a.S_max = s.S_max;
-    a.max_splits = max_splits;
-    ops.push_back(o);
-  }
-  {
-    ChainOp o;
-    o.type = OP_GEMV;
-    o.pro = PRO_ATTN;
-    o.epi = EPI_RESADD;
-    GemvParams& p = o.g;
-    p.W = w.proj;
-    p.N = D;
-    p.K = QD;
-    p.M = 1;
-    p.o_part = h->o_part;
-    p.ml_part = h->ml_part;
-    p.max_splits = max_splits;
-    p.pos = pos;
-    p.n_head = c.n_head;
-    p.hs = hs;
-    p.Y = x;
-    p.ldy = D;
-    p.R = x;
-    p.ldr = D;
-    ops.push_back(o);
-  }
-  {
-    ChainOp o;
-    o.type = OP_GEMV;
-    o.pro = PRO_RMSNORM;
-    o.epi = EPI_SWIGLU;
-    GemvParams& p = o.g;
-    p.W = w.fc1;
-    p.W2 = w.fc2;
-    p.N = c.intermediate_size;
-    p.K = D;
-    p.M = 1;
-    p.X = x;
-    p.ldx = D;
-    p.norm_w = w.norm2;
-    p.eps = c.norm_eps;
-    p.Y = h->hmlp;
-    p.ldy = c.intermediate_size;
-    ops.push_back(o);
-  }
-  {
-    ChainOp o;
-    o.type = OP_GEMV;
-    o.pro = PRO_PLAIN;
-    o.epi = EPI_RESADD;
-    GemvParams& p = o.g;
-    p.W = w.mproj;
-    p.N = D;
-    p.K = c.intermediate_size;
-    p.M = 1;
-    p.X = h->hmlp;
-    p.ldx = c.intermediate_size;
-    p.Y = x;
-    p.ldy = D;
-    p.R = x;
-    p.ldr = D;
-    ops.push_back(o);
-  }
-}
-
-ChainOp mix_op(ua2_llm* h, const float* x, const float* w, float eps, const float* add, float* keep, float* out, int mode) {
-  ChainOp o;
-  o.type = OP_NORMMIX;
-  o.nm_x = x;
-  o.nm_w = w;
-  o.nm_eps = eps;
-  o.nm_add = add;
-  o.nm_keep = keep;
-  o.nm_out = out;
-  o.nm_mode = mode;
-  o.mask = h->d_mask;
-  o.nq = h->cfg.num_codebooks;
-  o.D = h->cfg.backbone.n_embd;
-  return o;
-}
-
-int upload_ops(ua2_llm* h, std::vector<ChainOp>& ops, ChainOp** d_out) {
-  int last = -1;
-  for (int i = (int)ops.size() - 1; i >= 0; --i) {
-    ops[i].next_gemv = last;
-    if (ops[i].type == OP_GEMV) {
-      chain_cfg_for(ops[i].g.K, &ops[i].c);
-      last = i;
-    }
-  }
-  int rc = alloc(h, (void**)d_out, ops.size() * sizeof(ChainOp));
-  if (rc) return rc;
-  UA2_CHECK_CUDA(cudaMemcpy(*d_out, ops.data(), ops.size() * sizeof(ChainOp), cudaMemcpyHostToDevice));
-  return UA2_OK;
-}
-
-int build_chain(ua2_llm* h) {
-  h->chain_ok = false;
-  int maxK = 0;
-  for (int si = 0; si < 4; ++si) maxK = std::max(maxK, std::max(h->st[si].cfg.n_embd, h->st[si].cfg.intermediate_size));
-  for (int si = 0; si < 4; ++si) maxK = std::max(maxK, h->st[si].cfg.n_head * h->st[si].cfg.head_size);
-  if (maxK > 8192) return UA2_OK;  // activation tile of the chain kernel holds 8192 floats: use the multi-kernel path
-  h->chain_ctas = chain_max_ctas();
-  if (h->chain_ctas <= 0) return UA2_OK;
-  const int nq = h->cfg.num_codebooks, D = h->cfg.backbone.n_embd, d = h->cfg.decoder.n_embd;
-  const int Vt = h->cfg.text_vocab, Va = h->cfg.audio_vocab;
-  const int ms = (h->cfg.max_seq_length + CHAIN_ATTN_CHUNK - 1) / CHAIN_ATTN_CHUNK;
-  h->chain_max_splits = ms;
-  int rc;
-  {
-    std::vector<ChainOp> ops;
-    ChainOp e;
-    e.type = OP_EMBED;
-    e.tokens = h->d_tokens;
-    e.mask = h->d_mask;
-    e.audio_emb = h->audio_emb;
-    e.wte = h->wte;
-    e.audio_in = h->audio_in;
-    e.text_emb = h->text_emb;
-    e.nq = nq;
-    e.V = Va;
-    e.D = D;
-    ops.push_back(e);
-    Stack &und = h->st[2], &bb = h->st[0], &gen = h->st[3];
-    for (int l = 0; l < und.cfg.n_layer; ++l) chain_block_ops(h, ops, und, l, h->audio_in, h->d_pos, h->d_bidx, ms);
-    ops.push_back(mix_op(h, h->audio_in, und.ln_f, und.cfg.norm_eps, h->text_emb, nullptr, h->x, MIX_UND_TO_BACKBONE));
-    for (int l = 0; l < bb.cfg.n_layer; ++l) chain_block_ops(h, ops, bb, l, h->x, h->d_pos, h->d_bidx, ms);
-    ops.push_back(mix_op(h, h->x, bb.ln_f, bb.cfg.norm_eps, nullptr, h->hb, h->audio_in, MIX_BACKBONE_TO_GEN));
-    for (int l = 0; l < gen.cfg.n_layer; ++l) chain_block_ops(h, ops, gen, l, h->audio_in, h->d_pos, h->d_bidx, ms);
-    ops.push_back(mix_op(h, h->audio_in, gen.ln_f, gen.cfg.norm_eps, h->hb, nullptr, h->h_final, MIX_FINAL));
-    ChainOp lm;
-    lm.type = OP_GEMV;
-    lm.pro = PRO_PLAIN;
-    lm.epi = EPI_STORE;
-    lm.g.W = h->lm_head;
-    lm.g.N = Vt;
-    lm.g.K = D;
-    lm.g.M = 1;
-    lm.g.X = h->h_final;
-    lm.g.ldx = D;
-    lm.g.Y = h->text_logits;
-    lm.g.ldy = Vt;
-    ops.push_back(lm);
-    h->n_ops_global = (int)ops.size();
-    if ((rc = upload_ops(h, ops, &h->d_ops_global))) return rc;
-  }
-  Stack& dec = h->st[1];
-  const int32_t* mirror = reinterpret_cast<const int32_t*>(h->audio_logits + h->audio_logits_numel);
-  h->d_ops_local.assign(nq, nullptr);
-  h->n_ops_local.assign(nq, 0);
-  for (int i = 0; i < nq; ++i) {
-    std::vector<ChainOp> ops;
-    ChainOp pr;
-    pr.type = OP_GEMV;
-    pr.epi = EPI_STORE;
-    pr.g.W = h->projection;
-    pr.g.N = d;
-    pr.g.K = D;
-    pr.g.M = 1;
-    pr.g.Y = h->dec_x;
-    pr.g.ldy = d;
-    if (i == 0) {
-      pr.pro = PRO_PLAIN;
-      pr.g.X = h->h_final;
-      pr.g.ldx = D;
-    } else {
-      pr.pro = PRO_GATHER;
-      pr.g.emb = h->audio_emb;
-      pr.g.gidx = mirror + i;
-      pr.g.gidx_stride = nq + 1;
-      pr.g.gidx_offset = (i - 1) * Va;
-    }
-    ops.push_back(pr);
-    const int32_t* pos_i = h->d_pos_local + (size_t)i * h->B_max;
-    for (int l = 0; l < dec.cfg.n_layer; ++l) chain_block_ops(h, ops, dec, l, h->dec_x, pos_i, h->d_bidx, 1);
-    ChainOp hd;
-    hd.type = OP_GEMV;
-    hd.pro = PRO_RMSNORM;
-    hd.epi = EPI_STORE;
-    hd.g.W = h->audio_head_t + (size_t)i * Va * d;
-    hd.g.N = Va;
-    hd.g.K = d;
-    hd.g.M = 1;
-    hd.g.X = h->dec_x;
-    hd.g.ldx = d;
-    hd.g.norm_w = dec.ln_f;
-    hd.g.eps = dec.cfg.norm_eps;
-    hd.g.Y = h->audio_logits + (size_t)i * 1 * Va;  // B = 1 layout (nq, 1, V_a)
-    hd.g.ldy = Va;
-    ops.push_back(hd);
-    h->n_ops_local[i] = (int)ops.size();
-    if ((rc = upload_ops(h, ops, &h->d_ops_local[i]))) return rc;
-  }
-  if ((rc = alloc(h, (void**)&h->d_chain_sync, 2 * sizeof(unsigned)))) return rc;
-  UA2_CHECK_CUDA(cudaMemset(h->d_chain_sync, 0, 2 * sizeof(unsigned)));
-  h->chain_ok = true;
-  return UA2_OK;
-}
-
-// B = 1 frame through the persistent chain kernels: 1 + nq chain launches and 1 + nq sampler launches
-cudaError_t run_frame_chain(ua2_llm* h, const LaunchCtx& lc, int rows) {
-  const int nq = h->cfg.num_codebooks, Vt = h->cfg.text_vocab, Va = h->cfg.audio_vocab;
-  cudaError_t e;
-  LaunchCtx ls = lc;
-  ls.pdl = false;
-  if ((e = launch_chain(lc.stream, h->d_ops_global, h->n_ops_global, h->d_chain_sync, h->chain_ctas, h->d_chain_prof)) != cudaSuccess)
-    return e;
-  if (lc.launch_counter) ++*lc.launch_counter;
-  if ((e = launch_sampler(ls, h->text_logits, Vt, h->d_fs, 0, 0, nq + 1, 0, 0, 1, rows)) != cudaSuccess) return e;
-  for (int i = 0; i < nq; ++i) {
-    if ((e = launch_chain(lc.stream, h->d_ops_local[i], h->n_ops_local[i], h->d_chain_sync, h->chain_ctas)) != cudaSuccess) return e;
-    if (lc.launch_counter) ++*lc.launch_counter;
-    if ((e = launch_sampler(ls, h->audio_logits + (size_t)i * Va, Va, h->d_fs, 1, 1 + i, nq + 1,
-                            (long long)rows * Vt + (long long)i * rows * Va, 1 + i, 1, rows)) != cudaSuccess)
-      return e;
-  }
-  return cudaSuccess;
-}
-
 }  // namespace
 
 extern "C" {
@@ -658,7 +380,6 @@ int ua2_llm_destroy(ua2_llm* h) {
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->owned) cudaFree(p);
-  tc_cache_destroy(h->tcws.cache);
   delete h;
   return UA2_OK;
 }
@@ -811,28 +532,24 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   h->sg_ws_floats = (size_t)Mc * (2 + max_qd) + 4;  // tiled-GEMM scratch: row statistics + attention combine
   if ((rc = alloc(h, (void**)&h->sg_ws, h->sg_ws_floats * 4))) return rc;
   if (tc_gemm_available()) {
-    size_t kmax = 0, wmax = 0, nmax = 0;
+    size_t kmax = 0, nmax = 0;
     for (int si = 0; si < 4; ++si) {
       const ua2_gpt_cfg& c = h->st[si].cfg;
       const size_t Dm = c.n_embd, QD = (size_t)c.n_head * c.head_size, QKV = (size_t)(c.n_head + 2 * c.n_query_groups) * c.head_size,
                    F = c.intermediate_size;
       kmax = std::max({kmax, Dm, QD, F});
-      wmax = std::max({wmax, QKV * 3 * Dm, Dm * 3 * QD, 2 * F * 3 * Dm, Dm * 3 * F});
       nmax = std::max({nmax, QKV, Dm, 2 * F});
     }
-    h->tcws.a_floats = (size_t)Mc * 3 * kmax;
-    h->tcws.w_floats = std::max(wmax, tc_slots_max_floats());
+    h->tcws.a_floats = (size_t)Mc * 2 * kmax;
+    h->tcws.slots_floats = tc_slots_max_floats();
     const size_t nheads = std::max({nmax, (size_t)h->cfg.text_vocab, (size_t)h->cfg.audio_vocab});
     h->tcws.c_floats = std::max((size_t)Mc * nmax, (size_t)B * nheads);  // prefill passes never run the heads; frames have M <= B
-    h->tcws.cache = tc_cache_create();
     if ((rc = alloc(h, (void**)&h->tcws.a, h->tcws.a_floats * 4))) return rc;
-    if ((rc = alloc(h, (void**)&h->tcws.w, h->tcws.w_floats * 4))) return rc;
+    if ((rc = alloc(h, (void**)&h->tcws.slots, h->tcws.slots_floats * 4))) return rc;
     if ((rc = alloc(h, (void**)&h->tcws.c, h->tcws.c_floats * 4))) return rc;
   }
-  const size_t chain_splits = (h->cfg.max_seq_length + CHAIN_ATTN_CHUNK - 1) / CHAIN_ATTN_CHUNK;
-  const size_t opart_floats = std::max((size_t)Mc * max_heads_hs * h->max_splits, (size_t)max_heads_hs * chain_splits);
-  if ((rc = alloc(h, (void**)&h->o_part, opart_floats * 4))) return rc;
-  if ((rc = alloc(h, (void**)&h->ml_part, std::max((size_t)Mc * max_nhead * h->max_splits, (size_t)max_nhead * chain_splits) * 2 * 4))) return rc;
+  if ((rc = alloc(h, (void**)&h->o_part, (size_t)Mc * max_heads_hs * h->max_splits * 4))) return rc;
+  if ((rc = alloc(h, (void**)&h->ml_part, (size_t)Mc * max_nhead * h->max_splits * 2 * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->dec_x, (size_t)B * d * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->text_logits, (size_t)B * h->cfg.text_vocab * 4))) return rc;
   // audio logits (nq, B, V_a) followed by an int32 mirror of the sampled frame (B, nq+1)
@@ -851,7 +568,6 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   lc.stream = stream;
   UA2_CHECK_CUDA(launch_transpose_head(lc, h->audio_head_src, h->audio_head_t, nq, d, h->cfg.audio_vocab));
   UA2_CHECK_CUDA(cudaStreamSynchronize(stream));
-  if ((rc = build_chain(h))) return rc;
   h->ready = true;
   return UA2_OK;
 }
@@ -964,7 +680,7 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
   lc.pdl = h->opt_pdl != 0;
   const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |
                                  (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull) | (h->opt_attn_direct ? 4ull : 0ull) |
-                                 ((get_tc_gemm() && B >= get_tc_min_rows()) ? 8ull : 0ull) | (get_tc_persistent() ? 16ull : 0ull);
+                                 ((get_tc_gemm() && B >= get_tc_min_rows()) ? 8ull : 0ull);
   // the frame's sequence of linears: recorded by the first run of this shape, replayed (with tail prefetch specs of the
   // following weights) by every later run / by the graph capture
   GemvSeq& sq = h->seqs[key];
@@ -973,9 +689,7 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
     GemvSeq& s;
     ~SeqDone() { s.recorded = s.recorded || !s.ops.empty(); }
   };
-  if (B == 1 && h->opt_chain && h->chain_ok) {
-    UA2_CHECK_CUDA(run_frame_chain(h, lc, rows));
-  } else if (!h->opt_graph) {
+  if (!h->opt_graph) {
     lc.seq = &sq;
     SeqDone done{sq};
     UA2_CHECK_CUDA(run_global(h, lc, B, n_splits, true));
@@ -1044,10 +758,6 @@ int ua2_llm_get_buffer(ua2_llm* h, const char* name, float** ptr, int64_t* numel
   } else if (n == "audio_logits") {
     *ptr = h->audio_logits;
     *numel = h->audio_logits_numel;
-  } else if (n == "chain_prof") {  // 2 x CHAIN_PROF_OPS x 5 uint64 clocks, exposed as 2x as many 4-byte words
-    UA2_REQUIRE(h->d_chain_prof != nullptr, "set_option(\"chain_profile\", 1) first");
-    *ptr = reinterpret_cast<float*>(h->d_chain_prof);
-    *numel = (int64_t)2 * CHAIN_PROF_OPS * 5 * 2;
   } else {
     UA2_REQUIRE(false, "unknown buffer " + n);
   }
@@ -1061,17 +771,7 @@ int ua2_llm_set_option(ua2_llm* h, const char* name, int value) {
     h->opt_graph = value;
   else if (n == "pdl")
     h->opt_pdl = value;
-  else if (n == "chain")
-    h->opt_chain = value;
-  else if (n == "chain_profile") {
-    if (value && h->d_chain_prof == nullptr) {
-      void* p = nullptr;
-      UA2_CHECK_CUDA(cudaMalloc(&p, (size_t)2 * CHAIN_PROF_OPS * 5 * 8));
-      UA2_CHECK_CUDA(cudaMemset(p, 0, (size_t)2 * CHAIN_PROF_OPS * 5 * 8));
-      h->owned.push_back(p);
-      h->d_chain_prof = (unsigned long long*)p;
-    }
-  } else if (n == "prefill_chunk_rows")
+  else if (n == "prefill_chunk_rows")
     h->opt_chunk_rows = value;
   else if (n == "attn_direct")
     h->opt_attn_direct = value ? 1 : 0;

@@ -19,10 +19,6 @@ extern "C" {
 
 int ua2_set_global_option(const char* name, int value) {
   UA2_REQUIRE(name, "null name");
-  if (std::string(name) == "gemv_impl") {
-    set_gemv_impl(value);
-    return UA2_OK;
-  }
   if (std::string(name) == "gemv3_balance_grid") {
     set_gemv3_balance_grid(value);
     return UA2_OK;
@@ -36,12 +32,8 @@ int ua2_set_global_option(const char* name, int value) {
     return UA2_OK;
   }
   if (std::string(name) == "tc_gemm") {
-    UA2_REQUIRE(!value || tc_gemm_available(), "library was built without the CUTLASS headers: no tensor-core path");
+    UA2_REQUIRE(!value || tc_gemm_available(), "no tensor-core path in this build");
     set_tc_gemm(value);
-    return UA2_OK;
-  }
-  if (std::string(name) == "tc_impl") {  // 1 = hand-written tcgen05 mainloop (ua2_umma.cu), 0 = library collective (A/B only)
-    set_tc_impl(value);
     return UA2_OK;
   }
   if (std::string(name) == "resblock_fused") {
@@ -53,12 +45,8 @@ int ua2_set_global_option(const char* name, int value) {
     return UA2_OK;
   }
   if (std::string(name) == "conv_tc") {
-    UA2_REQUIRE(!value || tc_gemm_available(), "library was built without the CUTLASS headers: no tensor-core path");
+    UA2_REQUIRE(!value || tc_gemm_available(), "no tensor-core path in this build");
     set_conv_tc(value);
-    return UA2_OK;
-  }
-  if (std::string(name) == "tc_persistent_weights") {
-    set_tc_persistent(value);
     return UA2_OK;
   }
   if (std::string(name) == "tc_min_rows") {
@@ -130,7 +118,7 @@ static int tc_op_ws(size_t a, size_t c) {
   };
   UA2_CHECK_CUDA(grow(&g_tc_op_ws.a, &g_tc_op_ws.a_floats, a));
   UA2_CHECK_CUDA(grow(&g_tc_op_ws.c, &g_tc_op_ws.c_floats, c));
-  UA2_CHECK_CUDA(grow(&g_tc_op_ws.w, &g_tc_op_ws.w_floats, tc_slots_max_floats()));
+  UA2_CHECK_CUDA(grow(&g_tc_op_ws.slots, &g_tc_op_ws.slots_floats, tc_slots_max_floats()));
   return UA2_OK;
 }
 
@@ -139,9 +127,8 @@ int ua2_tc_linear_f32(const float* x, const float* W, const float* W2, const flo
   UA2_REQUIRE(x && W && y, "null argument");
   UA2_REQUIRE(M >= 1 && N >= 4 && (N % 4) == 0 && K >= 4 && (K % 4) == 0, "need M>=1, N % 4 == 0, K % 4 == 0");
   UA2_REQUIRE(!(W2 && residual), "SwiGLU form takes no residual");
-  UA2_REQUIRE(get_tc_impl() == 1, "ua2_tc_linear_f32 serves the hand-written mainloop (option tc_impl = 1)");
   const int Ntot = W2 ? 2 * N : N;
-  if (int rc = tc_op_ws((size_t)M * 3 * K, (size_t)M * Ntot)) return rc;
+  if (int rc = tc_op_ws((size_t)M * 2 * K, (size_t)M * Ntot)) return rc;
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
   GemvParams p;
