@@ -173,15 +173,17 @@ __global__ void __launch_bounds__(128) attn_split_kernel(const AttnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Option "attn_ring" (default 0 - written at the end of round 1, NOT yet run on a B200): the same split-softmax work items
-// for long, batched contexts, where attn_split_kernel reaches 37 % of the HBM peak (profiles/r1_kernel_rooflines.md: a CTA
-// fetches, waits, computes and exits, so its share of the copy engine idles during the math).  Here a persistent CTA walks a
+// Option "attn_ring" (default 1): the same split-softmax work items for batched contexts of moderate length, where the one-shot
+// kernel's CTAs are too short-lived to keep the copy engine busy (a CTA fetches, waits, computes and exits).  Here a persistent CTA walks a
 // contiguous range of the (row, group, split) items and streams their K and V chunks through a 3-slot ring of bulk copies:
 // while the scores of item j are computed from K_j, V_j and K_{j+1} are in flight; every freed slot is refilled at the next
 // __syncthreads.  Slots hold ONE chunk (K or V, 32 KB at hs 128), so two CTAs fit an SM with 4 chunks in flight between them.
 // Partial outputs and statistics land exactly where attn_split_kernel puts them (same item -> (m, head, split) map, same
 // arithmetic order inside an item), so the consumers (PRO_ATTN, attn_combine_kernel) are unchanged.
 constexpr int RING_SLOTS = 3;
+#ifndef UA2_ATTN_RING_MAX_SPLITS
+#define UA2_ATTN_RING_MAX_SPLITS 16
+#endif
 #ifndef UA2_ATTN_RING_MIN_ITEMS
 #define UA2_ATTN_RING_MIN_ITEMS (4 * 148)  // work items from which launch_attn takes the ring kernel (tests/cpu_shim lowers it)
 #endif
@@ -435,7 +437,7 @@ cudaError_t launch_attn_ring_hs(const LaunchCtx& lc, const AttnParams& p, int n_
   return launch(lc, attn_ring_kernel<HS>, dim3(grid), dim3(128), smem, p, n_items);
 }
 
-int g_attn_ring = 0;
+int g_attn_ring = 1;  // default since round 2 (measured on a B200: profiles/r2_kernel_rooflines.md)
 
 }  // namespace
 
@@ -445,8 +447,10 @@ int get_attn_ring() { return g_attn_ring; }
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p) {
   if (p.n_head % p.n_groups != 0 || p.n_head / p.n_groups > MAX_QPK) return cudaErrorInvalidValue;
   const long long n_items = (long long)p.M * p.n_groups * p.n_splits_launch;
-  // the ring pays off once every CTA walks several items; a decode frame at batch 1 (8-32 items) stays on the one-shot kernel
-  if (g_attn_ring && n_items >= UA2_ATTN_RING_MIN_ITEMS && n_items < (1LL << 30)) {
+  // The ring pays off once every CTA walks several items AND the chunks are few per (row, group): batch 32 x 540 keys runs at 0.41
+  // of the HBM peak on the ring against 0.24 one-shot; at 2048 keys (32 splits) the one-shot grid already keeps 0.77 of the peak
+  // in flight and the ring's two co-resident CTAs per SM (0.67) lose.  A decode frame at batch 1 (8-32 items) stays one-shot.
+  if (g_attn_ring && n_items >= UA2_ATTN_RING_MIN_ITEMS && n_items < (1LL << 30) && p.n_splits_launch <= UA2_ATTN_RING_MAX_SPLITS) {
     switch (p.hs) {
       case 128: return launch_attn_ring_hs<128>(lc, p, (int)n_items);
       case 64: return launch_attn_ring_hs<64>(lc, p, (int)n_items);

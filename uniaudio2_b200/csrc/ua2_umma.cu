@@ -81,6 +81,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) { asm v
 __device__ __forceinline__ void bar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
 }
+// One lane of a CONVERGED warp.  The single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) are issued under this predicate
+// from warp-uniform loops: issued from a divergent `lane == 0` branch instead, every one of them compiles into an
+// ELECT / BRA.U.ANY retry loop around the uniform-datapath instruction (first ncu capture: 2400 cycles per k-block in the MMA warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -152,12 +166,14 @@ struct UmSeg {
     u_end = u + p.Lr < p.rem_units ? u + p.Lr : p.rem_units;
   }
   __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
-    if (j < pl.full_waves) {
+    if (j < pl.full_waves) {  // the last wave may be partial (dp_tiles is not a multiple of the grid then)
       tile = c + j * pl.grid;
-      kb0 = 0;
-      kb1 = pl.KB;
       ++j;
-      return true;
+      if (tile < pl.dp_tiles) {
+        kb0 = 0;
+        kb1 = pl.KB;
+        return true;
+      }
     }
     if (u >= u_end) return false;
     const int tr = u / pl.KB;
@@ -235,7 +251,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ================= W producer (no griddepcontrol.wait: weights are not written by the preceding kernels)
-    if (lane == 0) {
+    {
       UmSeg seg(pl, cta);
       int tile, kb0, kb1;
       uint32_t it = 0;
@@ -247,14 +263,17 @@ umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t sw = it % Cfg::SW, pw = (it / Cfg::SW) & 1;
           smem_bar_wait(&w_empty[sw], pw ^ 1);
-          smem_bar_arrive_expect_tx(&w_full[sw], Cfg::W_BYTES);
-          tma_load_2d(w_ring + (size_t)sw * Cfg::W_BYTES, tm, kb * BKE, row0, &w_full[sw], POLICY_EVICT_FIRST);
+          if (elect_one()) {
+            smem_bar_arrive_expect_tx(&w_full[sw], Cfg::W_BYTES);
+            tma_load_2d(w_ring + (size_t)sw * Cfg::W_BYTES, tm, kb * BKE, row0, &w_full[sw], POLICY_EVICT_FIRST);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 2) {
     // ================= X producer
-    if (lane == 0) {
+    {
       pdl_wait();  // the split planes come from the preceding kernel
       UmSeg seg(pl, cta);
       int tile, kb0, kb1;
@@ -265,17 +284,20 @@ umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t sx = it % Cfg::SX, px = (it / Cfg::SX) & 1;
           smem_bar_wait(&x_empty[sx], px ^ 1);
-          smem_bar_arrive_expect_tx(&x_full[sx], Cfg::X_BYTES);
-          if constexpr (BF16)
-            tma_load_2d(x_ring + (size_t)sx * Cfg::X_BYTES, &tmX, kb * BKE, mt * NT, &x_full[sx], POLICY_EVICT_LAST);
-          else
-            tma_load_3d(x_ring + (size_t)sx * Cfg::X_BYTES, &tmX, kb * BKE, mt * NT, 0, &x_full[sx], POLICY_EVICT_LAST);
+          if (elect_one()) {
+            smem_bar_arrive_expect_tx(&x_full[sx], Cfg::X_BYTES);
+            if constexpr (BF16)
+              tma_load_2d(x_ring + (size_t)sx * Cfg::X_BYTES, &tmX, kb * BKE, mt * NT, &x_full[sx], POLICY_EVICT_LAST);
+            else
+              tma_load_3d(x_ring + (size_t)sx * Cfg::X_BYTES, &tmX, kb * BKE, mt * NT, 0, &x_full[sx], POLICY_EVICT_LAST);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer
-    if (lane == 0) {
+    // ================= MMA issuer (warp-uniform loop; one elected lane issues)
+    {
       // instruction descriptor: D fp32 (bit 4), A/B format at bits 7 / 10 (tf32 = 2, bf16 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
       constexpr uint32_t fmt = BF16 ? 1u : 2u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
@@ -294,6 +316,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUt
           const uint32_t xs = smem_addr_u32(x_ring + (size_t)sx * Cfg::X_BYTES);
           const uint64_t bh = smem_desc_sw128(xs), bl = smem_desc_sw128(xs + Cfg::XH_BYTES);
           const uint32_t a_hi = tmem + sa * 64, a_lo = a_hi + 32;
+          if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             // one k-step = 32 bytes of every row (8 tf32 / 16 bf16): +2 in the descriptor's 16-byte address units, +8 TMEM columns
@@ -307,8 +330,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUt
           }
           tc_commit(&x_empty[sx]);
           tc_commit(&a_empty[sa]);
+          if (kb + 1 == kb1) tc_commit(acc_full);
+          }
+          __syncwarp();
         }
-        tc_commit(acc_full);
         ++tile_j;
       }
     }
@@ -317,7 +342,9 @@ umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUt
     const int grp = (warp - 4) >> 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;        // weight row inside the tile
-    const uint32_t n_it = (uint32_t)(pl.full_waves * pl.KB) + (uint32_t)UmSeg(pl, cta).u_end - (uint32_t)UmSeg(pl, cta).u;
+    int n_dp = 0;  // whole tiles of this CTA: c, c + grid, ... below dp_tiles
+    if (cta < pl.dp_tiles) n_dp = (pl.dp_tiles - 1 - cta) / pl.grid + 1;
+    const uint32_t n_it = (uint32_t)(n_dp * pl.KB) + (uint32_t)UmSeg(pl, cta).u_end - (uint32_t)UmSeg(pl, cta).u;
     for (uint32_t it = (uint32_t)grp; it < n_it; it += 2) {
       const uint32_t sw = it % Cfg::SW, pw = (it / Cfg::SW) & 1, sa = it % UM_A_SLOTS, pa = (it / UM_A_SLOTS) & 1;
       smem_bar_wait(&w_full[sw], pw);
@@ -497,6 +524,12 @@ UmmaPlan umma_plan(int M, int N, int n_mat, int K, bool bf16) {
   pl.grid = sms;
   pl.full_waves = pl.n_tiles / sms;
   pl.dp_tiles = pl.full_waves * sms;
+  // a remainder that fills >= 85 % of a wave runs as one more (partial) wave of whole tiles: splitting every one of its tiles
+  // between two CTAs would cost two accumulator drains per CTA and a side-slot pass for nothing
+  if ((long long)(pl.n_tiles - pl.dp_tiles) * 100 >= 85LL * sms) {
+    pl.full_waves += 1;
+    pl.dp_tiles = pl.n_tiles;
+  }
   pl.rem_units = (pl.n_tiles - pl.dp_tiles) * pl.KB;
   if (pl.full_waves == 0) {  // decode-sized: pure stream-K, at least 4 k-blocks per CTA (a shorter range is all prologue)
     int g = pl.rem_units / 4;

@@ -73,6 +73,11 @@ class ReasoningTokenizer:
         self.reason_frame_rate = 5
         self.model = model
         self.SQCodec = SQCodec
+        # The reference runs the window loop under torch.autocast(device_type='cuda', dtype=torch.bfloat16) (reason_tokenizer.py:265):
+        # the flow decoder's linears see bf16 operands with fp32 accumulation.  True mirrors that (the estimator's "bf16" option: the
+        # hand-written tcgen05 kind::f16 mainloop); False keeps the fp32-class 3xTF32 arithmetic that the 1e-4 parity tests compare
+        # with the fp32 CPU oracle.
+        self.autocast_bf16 = True
 
     def _randn(self, *shape):
         """Noise the reference draws on the CPU generator and then moves to the device (reason_tokenizer.py:234, :279)."""
@@ -92,6 +97,9 @@ class ReasoningTokenizer:
         # ---- latents, window by window; from the second window on the first overlap/2 latent frames continue the previous window
         carried = w.overlap // 2
         latents = []
+        estimator = getattr(getattr(self.model, "cfm_wrapper", None), "estimator", None)
+        if estimator is not None and hasattr(estimator, "set_option"):
+            estimator.set_option("bf16", 1 if self.autocast_bf16 else 0)
         for start in range(0, rec_codec.shape[-1] - w.hop, w.hop):
             n_pinned = 0
             if latents:
