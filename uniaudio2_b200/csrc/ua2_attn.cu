@@ -380,6 +380,154 @@ __global__ void __launch_bounds__(128) attn_ring_kernel(const AttnParams p, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Many query rows per sequence (forward_prefix, lit_model.py:468-532 with T > 1; the codec transformer, transformer.py:375-419):
+// the kernels above give every query row its own CTAs, so a 540-row prompt re-fetches each K/V chunk 540 times from L2 (the codec
+// transformer spent 18 % of an encode + decode there).  Here a CTA owns a tile of consecutive query rows of ONE head and walks the
+// keys once: K/V tiles of 32 keys are staged in shared memory for all its rows, scores by 128-bit shared reads, online softmax in
+// registers, causal / window mask per element.  Rows of a tile that belong to different sequences (bidx) are served one sequence
+// after the other.  The result is written in the split-partial format with everything in split 0 (weight 1) and the other splits
+// empty, so the consumers (attn_combine_kernel, PRO_ATTN) stay as they are.
+constexpr int AR_KEYS = 32;
+
+template <int HS, int RPW>
+__global__ void __launch_bounds__(256) attn_rows_kernel(const AttnParams p) {
+  constexpr int DPL = HS / 32;  // output dims per lane
+  constexpr int ROWS = 8 * RPW;
+  constexpr int KST = HS + 4;
+  __shared__ __align__(16) float Qs[ROWS][HS];
+  __shared__ __align__(16) float Ks[AR_KEYS][KST];
+  __shared__ __align__(16) float Vs[AR_KEYS][HS];
+  __shared__ __align__(16) float Ps[8][RPW][AR_KEYS];
+  __shared__ int s_pos[ROWS], s_b[ROWS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * ROWS, h = blockIdx.y;
+  const int qpk = p.n_head / p.n_groups, g = h / qpk;
+  const int D = p.n_head * HS;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (tid < ROWS) {
+    const int m = m0 + tid;
+    s_pos[tid] = m < p.M ? p.pos[m] : -1;
+    s_b[tid] = m < p.M ? (p.bidx_identity ? m : p.bidx[m]) : -1;
+  }
+  for (int i = tid; i < ROWS * HS / 4; i += 256) {
+    const int r = i / (HS / 4), d4 = i - r * (HS / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + r < p.M) v = *reinterpret_cast<const float4*>(p.q + (size_t)(m0 + r) * D + h * HS + d4 * 4);
+    *reinterpret_cast<float4*>(&Qs[r][d4 * 4]) = v;
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)HS);
+  float mx[RPW], l[RPW], acc[RPW][DPL];
+  int rpos[RPW], rlo[RPW], rb[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    mx[r] = -INFINITY;
+    l[r] = 0.f;
+    rpos[r] = s_pos[warp * RPW + r];
+    rb[r] = s_b[warp * RPW + r];
+    rlo[r] = (p.window > 0) ? max(0, rpos[r] + 1 - p.window) : 0;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) acc[r][d] = 0.f;
+  }
+  int seg = 0;
+  while (seg < ROWS && s_b[seg] >= 0) {
+    const int b = s_b[seg];
+    int seg_end = seg + 1, j_hi = s_pos[seg], j_lo = (p.window > 0) ? max(0, s_pos[seg] + 1 - p.window) : 0;
+    while (seg_end < ROWS && s_b[seg_end] == b) {
+      j_hi = max(j_hi, s_pos[seg_end]);
+      j_lo = min(j_lo, (p.window > 0) ? max(0, s_pos[seg_end] + 1 - p.window) : 0);
+      ++seg_end;
+    }
+    const float* Kb = p.k_cache + ((size_t)b * p.n_groups + g) * (size_t)p.S_max * HS;
+    const float* Vb = p.v_cache + ((size_t)b * p.n_groups + g) * (size_t)p.S_max * HS;
+    for (int j0 = (j_lo / AR_KEYS) * AR_KEYS; j0 <= j_hi; j0 += AR_KEYS) {
+      __syncthreads();  // previous tile fully consumed
+      for (int i = tid; i < AR_KEYS * HS / 4; i += 256) {
+        const int j = i / (HS / 4), d4 = i - j * (HS / 4);
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        if (j0 + j <= j_hi) {
+          kv = *reinterpret_cast<const float4*>(Kb + (size_t)(j0 + j) * HS + d4 * 4);
+          vv = *reinterpret_cast<const float4*>(Vb + (size_t)(j0 + j) * HS + d4 * 4);
+        }
+        *reinterpret_cast<float4*>(&Ks[j][d4 * 4]) = kv;
+        *reinterpret_cast<float4*>(&Vs[j][d4 * 4]) = vv;
+      }
+      __syncthreads();
+      // ---- scores of this lane's key against the warp's rows
+      float s[RPW];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) s[r] = 0.f;
+#pragma unroll 4
+      for (int d4 = 0; d4 < HS / 4; ++d4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(&Ks[lane][d4 * 4]);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const float4 q4 = *reinterpret_cast<const float4*>(&Qs[warp * RPW + r][d4 * 4]);
+          s[r] = fmaf(q4.x, k4.x, s[r]);
+          s[r] = fmaf(q4.y, k4.y, s[r]);
+          s[r] = fmaf(q4.z, k4.z, s[r]);
+          s[r] = fmaf(q4.w, k4.w, s[r]);
+        }
+      }
+      const int j = j0 + lane;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const bool valid = rb[r] == b && j <= rpos[r] && j >= rlo[r];
+        const float sv = valid ? s[r] * scale : -INFINITY;
+        const float mn = fmaxf(mx[r], warp_max(sv));
+        float pr = 0.f;
+        if (mn > -INFINITY) {  // (a row with no visible key in the tiles so far keeps its empty state)
+          const float corr = expf(mx[r] - mn);
+          pr = valid ? expf(sv - mn) : 0.f;
+          l[r] = l[r] * corr + warp_sum(pr);
+#pragma unroll
+          for (int d = 0; d < DPL; ++d) acc[r][d] *= corr;
+          mx[r] = mn;
+        }
+        Ps[warp][r][lane] = pr;
+      }
+      __syncwarp();
+      // ---- P @ V: lane owns output dims lane + 32 * d
+#pragma unroll 2
+      for (int j4 = 0; j4 < AR_KEYS / 4; ++j4) {
+        float4 p4[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) p4[r] = *reinterpret_cast<const float4*>(&Ps[warp][r][j4 * 4]);
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+          const float v0 = Vs[j4 * 4 + 0][lane + 32 * d], v1 = Vs[j4 * 4 + 1][lane + 32 * d];
+          const float v2 = Vs[j4 * 4 + 2][lane + 32 * d], v3 = Vs[j4 * 4 + 3][lane + 32 * d];
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) {
+            acc[r][d] = fmaf(p4[r].x, v0, acc[r][d]);
+            acc[r][d] = fmaf(p4[r].y, v1, acc[r][d]);
+            acc[r][d] = fmaf(p4[r].z, v2, acc[r][d]);
+            acc[r][d] = fmaf(p4[r].w, v3, acc[r][d]);
+          }
+        }
+      }
+      __syncwarp();  // Ps is rewritten by the next tile
+    }
+    seg = seg_end;
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int m = m0 + warp * RPW + r;
+    if (m < p.M) {
+      const size_t base = ((size_t)m * p.n_head + h) * p.max_splits;
+      const float inv = 1.f / l[r];
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) p.o_part[base * HS + lane + 32 * d] = acc[r][d] * inv;
+      for (int sidx = lane; sidx < p.n_splits_launch; sidx += 32) {  // split 0 carries everything with weight exp(0) * 1
+        p.ml_part[(base + sidx) * 2] = sidx == 0 ? 0.f : -INFINITY;
+        p.ml_part[(base + sidx) * 2 + 1] = sidx == 0 ? 1.f : 0.f;
+      }
+    }
+  }
+}
+
 // stand-alone merge of the split partials -> y (M, n_head*hs); the handle path fuses this into PRO_ATTN instead
 __global__ void attn_combine_kernel(const AttnParams p, float* y) {  // grid (M, n_head): one CTA per (row, head)
   pdl_launch_dependents();
@@ -437,15 +585,38 @@ cudaError_t launch_attn_ring_hs(const LaunchCtx& lc, const AttnParams& p, int n_
   return launch(lc, attn_ring_kernel<HS>, dim3(grid), dim3(128), smem, p, n_items);
 }
 
+template <int HS, int RPW>
+cudaError_t launch_attn_rows_hs(const LaunchCtx& lc, const AttnParams& p) {
+  static bool once = false;
+  if (!once) {
+    prefer_max_smem(attn_rows_kernel<HS, RPW>);
+    once = true;
+  }
+  return launch(lc, attn_rows_kernel<HS, RPW>, dim3((p.M + 8 * RPW - 1) / (8 * RPW), p.n_head), dim3(256), 0, p);
+}
+
+int g_attn_rows = 1;  // many-row launches (>= 128 rows that share sequences) on the row-tile kernel
 int g_attn_ring = 1;  // default since round 2 (measured on a B200: profiles/r2_kernel_rooflines.md)
 
 }  // namespace
 
+void set_attn_rows(int v) { g_attn_rows = v ? 1 : 0; }
+int get_attn_rows() { return g_attn_rows; }
 void set_attn_ring(int v) { g_attn_ring = v ? 1 : 0; }
 int get_attn_ring() { return g_attn_ring; }
 
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p) {
   if (p.n_head % p.n_groups != 0 || p.n_head / p.n_groups > MAX_QPK) return cudaErrorInvalidValue;
+  // prefill passes / the codec transformer: rows share sequences, so a tile of rows can share its K / V tiles.  (M >= 128 also
+  // guarantees that the consumer merges the partials with attn_combine_kernel, which never reads the data of an empty split.)
+  if (g_attn_rows && p.M >= 128 && !p.bidx_identity && p.n_head <= 65535) {
+    switch (p.hs) {
+      case 128: return launch_attn_rows_hs<128, 2>(lc, p);
+      case 64: return launch_attn_rows_hs<64, 4>(lc, p);
+      case 32: return launch_attn_rows_hs<32, 4>(lc, p);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   const long long n_items = (long long)p.M * p.n_groups * p.n_splits_launch;
   // The ring pays off once every CTA walks several items AND the chunks are few per (row, group): batch 32 x 540 keys runs at 0.41
   // of the HBM peak on the ring against 0.24 one-shot; at 2048 keys (32 splits) the one-shot grid already keeps 0.77 of the peak

@@ -160,6 +160,8 @@ struct AttnParams {
 cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p);
 cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float* y);
 // persistent 3-slot K/V chunk ring for long batched contexts (ua2_attn.cu; option "attn_ring", default 0)
+void set_attn_rows(int v);
+int get_attn_rows();
 void set_attn_ring(int v);
 int get_attn_ring();
 

@@ -40,6 +40,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_resblock_fused(value);
     return UA2_OK;
   }
+  if (std::string(name) == "attn_rows") {  // row-tile attention kernel for many-row launches (ua2_attn.cu); default 1
+    set_attn_rows(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "attn_ring") {  // persistent K/V chunk ring for long batched contexts (ua2_attn.cu); default 0
     set_attn_ring(value);
     return UA2_OK;
