@@ -129,6 +129,13 @@ cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w
                              int replicate);
 cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin,
                                int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out);
+// narrow / strided causal convolutions (Cin % 32 == 0, 16 <= Cout <= 256) as an implicit GEMM on tcgen05 with the activations going
+// global -> registers -> tensor memory (ua2_convumma.cu; option "conv_umma", default 1)
+cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y, int B,
+                               int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
+                               int replicate);
+void set_conv_umma(int v);
+int get_conv_umma();
 // fused SEANet residual block for the 64-channel / 24 kHz stages (ua2_resblock.cu; option "resblock_fused", default 0)
 cudaError_t launch_resblock_fused(const LaunchCtx& lc, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   float* y, int B, int C, int H, int T);

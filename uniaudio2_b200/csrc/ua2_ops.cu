@@ -48,6 +48,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_attn_ring(value);
     return UA2_OK;
   }
+  if (std::string(name) == "conv_umma") {
+    set_conv_umma(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "conv_tc") {
     UA2_REQUIRE(!value || tc_gemm_available(), "no tensor-core path in this build");
     set_conv_tc(value);

@@ -459,7 +459,12 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
                                int pad_left, int pre_elu, int replicate, const float* prelu) {
-  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 0): wide layers on the tensor cores, ua2_convtc.cu
+  if (prelu == nullptr) {  // option "conv_umma" (default 1): implicit GEMM on tcgen05 straight from (B, C, T), ua2_convumma.cu
+    const cudaError_t e = launch_conv1d_umma(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
+                                             replicate);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 1): wide layers as im2col + tensor-core GEMM, ua2_convtc.cu
     const cudaError_t e = launch_conv1d_tc(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
                                            replicate);
     if (e != cudaErrorNotSupported) return e;

@@ -32,21 +32,20 @@
 // to its side slot; the consumer (tc_epilogue_kernel / umma_fixup_kernel) adds the continuation slots in CTA order - deterministic.
 //
 // TMEM budget (512 columns): A ring 4 slots x 64 columns, accumulator NT columns at column 256.
-#include <cuda.h>
-
 #include "ua2_kernels.cuh"
+#include "ua2_tcgen05.cuh"
 #include "ua2_umma.cuh"
 
 namespace ua2 {
 namespace {
+
+using namespace tc;
 
 constexpr int UM_BM = 128;        // weight rows per tile (TMEM lanes)
 constexpr int UM_BK = 32;         // fp32 per k-block = one 128-byte swizzle row
 constexpr int UM_A_SLOTS = 4;     // TMEM A ring
 constexpr int UM_ACC_COL = 256;   // accumulator base column
 constexpr int UM_THREADS = 512;   // 16 warps, see the role table above
-constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
 
 // BF16 = false: fp32 operands, 3xTF32 (k-block = 32 floats, X stage = hi + lo planes).
 // BF16 = true : bf16 operands, one tcgen05.mma kind::f16 per k-step of 16 (k-block = 64 bf16 = the same 128-byte rows); the "splitter"
@@ -61,100 +60,6 @@ struct UmCfg {
   static constexpr int N_BARS = 2 * SW + 2 * SX + 2 * UM_A_SLOTS + 2;
   static constexpr size_t SMEM = 1024 + (size_t)SW * W_BYTES + (size_t)SX * X_BYTES + N_BARS * 8 + 16;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_addr_u32(dst)),
-      "l"(tm), "r"(smem_addr_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
-          smem_addr_u32(dst)),
-      "l"(tm), "r"(smem_addr_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
-__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
-}
-// One lane of a CONVERGED warp.  The single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) are issued under this predicate
-// from warp-uniform loops: issued from a divergent `lane == 0` branch instead, every one of them compiles into an
-// ELECT / BRA.U.ANY retry loop around the uniform-datapath instruction (first ncu capture: 2400 cycles per k-block in the MMA warp).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 operands, fp32 accumulate; `acc` = 0 overwrites D
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-        "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-
-// shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes (32 tf32), SWIZZLE_128B: 8-row groups 1024 B apart
-// (stride byte offset 64 x 16 B), descriptor version 1 (sm_100), layout type 2; advancing k by 8 elements adds 32 B to the start
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
 
 // The work of one CTA as a sequence of segments (tile, first k-block, end k-block): whole tiles of the data-parallel waves, then
 // its range of the stream-K remainder.  Every warp role walks the same sequence.
@@ -443,35 +348,6 @@ __global__ void __launch_bounds__(256) umma_fixup_kernel(float* __restrict__ C, 
   if (col >= N * n_mat || m >= M) return;
   const float add = umma_side_sum(pl, slots, m, col, N);
   if (add != 0.f) C[(size_t)m * ldc + col] += add;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// matrix (rows x K, row-major, optionally `planes` of it; fp32 or bf16) as a TMA tensor; box = {128 bytes, box_rows, planes}, SWIZZLE_128B, zero fill
-bool make_tmap(CUtensorMap* tm, const void* ptr, int K, long long rows, int planes, int box_rows, bool weights, bool bf16 = false) {
-  EncodeTiledFn fn = encode_fn();
-  if (fn == nullptr) return false;
-  const cuuint64_t es_bytes = bf16 ? 2 : 4;
-  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)planes};
-  cuuint64_t strides[2] = {(cuuint64_t)K * es_bytes, (cuuint64_t)K * es_bytes * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / es_bytes), (cuuint32_t)box_rows, (cuuint32_t)planes};
-  cuuint32_t es[3] = {1, 1, 1};
-  const int rank = planes > 1 ? 3 : 2;
-  return fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int g_sm_count = 0;
