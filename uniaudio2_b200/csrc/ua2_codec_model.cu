@@ -216,7 +216,9 @@ int conv(ua2_codec* h, const std::string& key, const float* x, const float* res,
 // SEANetResnetBlock (modules/seanet.py:21-94): y = x + conv_k1(ELU(conv_k3(ELU(x)))); `tmp` holds the hidden activation of the
 // two-launch form.  Option "resblock_fused": one kernel for the 64 -> 32 -> 64 blocks (ua2_resblock.cu).
 int resblock(ua2_codec* h, const std::string& p, const float* x, float* tmp, float* y, int B, int T, void* st) {
-  if (get_resblock_fused()) {
+  // the fused fp32 kernel serves builds / options without the tensor-core convolution (two conv_umma launches: 3.1 ms against 4.1 ms
+  // for the 64-channel block at batch 16 x 10 s)
+  if (get_resblock_fused() && !get_conv_umma()) {
     const ConvW *c1 = find_conv(h, p + "1.conv.conv"), *c3 = find_conv(h, p + "3.conv.conv");
     if (c1 && c3 && c1->w_src && c3->w_src && c1->k == 3 && c3->k == 1 && c1->cout == c3->cin && c1->cin == c3->cout) {
       LaunchCtx lc;

@@ -39,15 +39,27 @@ struct ConvUmmaParams {
   const float* res;
   float* y;
   int B, Cin, Cout, T_in, T_out, Ktaps, stride, pad_left, pre_elu;
+  int tap_step;     // +1 convolution (tap k reads t * stride + k - pad_left), -1 transposed convolution (tap k reads j - k)
+  int T_pos;        // positions (GEMM rows) per batch element: T_out, or the input grid Tj of a transposed convolution
+  int tr_stride;    // 0 = convolution; s = transposed convolution: GEMM column n0 + c = phase * Cout + channel -> y[b, ch, j * s + phase - crop]
+  int tr_crop;
+  int n0;           // first GEMM column (weight row) of this launch; n_cols of them are valid
+  int n_cols;
   int KB;           // k-blocks of 32: Ktaps * Cin / 32
   int cb_per_tap;   // Cin / 32
-  int tiles_per_b;  // ceil(T_out / 128)
+  int tiles_per_b;  // ceil(T_pos / 128)
   int n_tiles;
   int n_stages;     // weight ring stages
   int resident;     // KB <= n_stages: every k-block is loaded once and stays
 };
 
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// ELU with the SFU exponential: exp(v) - 1 = ex2(v * log2 e) - 1 for v <= 0.  Absolute error ~1e-7 (the library expm1f of the fp32
+// kernels is exact to an ulp); two orders below the tensor-core accumulation error of this path, codec indices stay bit-equal.
+__device__ __forceinline__ float elu_fast(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+  return v > 0.f ? v : e - 1.f;
+}
 
 template <int NO>
 __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmW, const ConvUmmaParams p) {
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
       if (!p.resident) smem_bar_wait(&w_empty[sw], pw ^ 1);
       if (elect_one()) {
         smem_bar_arrive_expect_tx(&w_full[sw], STAGE_BYTES);
-        tma_load_3d(w_ring + (size_t)sw * STAGE_BYTES, &tmW, kb * 32, 0, 0, &w_full[sw], POLICY_EVICT_LAST);
+        tma_load_3d(w_ring + (size_t)sw * STAGE_BYTES, &tmW, kb * 32, p.n0, 0, &w_full[sw], POLICY_EVICT_LAST);
       }
       __syncwarp();
     }
@@ -150,66 +162,163 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
     const int r = q * 32 + lane;
     const uint32_t n_it = (uint32_t)my_tiles * (uint32_t)p.KB;
     pdl_wait();  // x comes from the preceding kernel
-    for (uint32_t it = (uint32_t)grp; it < n_it; it += 2) {
-      const int j = (int)(it / (uint32_t)p.KB), kb = (int)(it - (uint32_t)j * (uint32_t)p.KB);
-      const int tile = cta + j * G;
-      const int b = tile / p.tiles_per_b, t_out = (tile - b * p.tiles_per_b) * CU_BM + r;
-      const int tap = kb / p.cb_per_tap, c0 = (kb - tap * p.cb_per_tap) * 32;
-      const int t_in = t_out * p.stride + tap - p.pad_left;
-      const bool ok = t_out < p.T_out && t_in >= 0 && t_in < p.T_in;
-      const float* src = p.x + ((size_t)b * p.Cin + c0) * p.T_in + (ok ? t_in : 0);
-      float v[32];
+    // the loads of k-block it + 2 (this group's next one) are issued before the split of k-block it: two k-blocks of a warp in flight.
+    // (tile, k-block) of the cursor advance incrementally - no integer division in the loop
+    struct Cur {
+      int kb, tap, cb;  // k-block, its tap and channel block
+      int b, t0;        // batch element and first position of the tile
+      int tile;
+    };
+    auto cur_init = [&](uint32_t it) -> Cur {
+      Cur c;
+      const int j = (int)(it / (uint32_t)p.KB);
+      c.kb = (int)(it - (uint32_t)j * (uint32_t)p.KB);
+      c.tap = c.kb / p.cb_per_tap;
+      c.cb = c.kb - c.tap * p.cb_per_tap;
+      c.tile = cta + j * G;
+      c.b = c.tile / p.tiles_per_b;
+      c.t0 = (c.tile - c.b * p.tiles_per_b) * CU_BM;
+      return c;
+    };
+    auto cur_step2 = [&](Cur& c) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        if (++c.cb == p.cb_per_tap) {
+          c.cb = 0;
+          ++c.tap;
+        }
+        if (++c.kb == p.KB) {
+          c.kb = 0;
+          c.tap = 0;
+          c.tile += G;
+          c.t0 += G * CU_BM;
+          while (c.t0 >= p.tiles_per_b * CU_BM) {
+            c.t0 -= p.tiles_per_b * CU_BM;
+            ++c.b;
+          }
+        }
+      }
+    };
+    auto gather = [&](const Cur& c, float (&v)[32]) {
+      const int t_pos = c.t0 + r;
+      const int t_in = t_pos * p.stride + c.tap * p.tap_step - p.pad_left;
+      const bool ok = t_pos < p.T_pos && t_in >= 0 && t_in < p.T_in;
+      const float* src = p.x + ((size_t)c.b * p.Cin + c.cb * 32) * p.T_in + (ok ? t_in : 0);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = ok ? __ldg(src + (size_t)i * p.T_in) : 0.f;
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float f = p.pre_elu ? elu_fast(v[i]) : v[i];
-        const uint32_t h = tf32_rna_bits(f);
-        hi[i] = h;
-        lo[i] = tf32_rna_bits(f - __uint_as_float(h));
+    };
+    float v[32], vn[32];
+    Cur cn = cur_init((uint32_t)grp);
+    if ((uint32_t)grp < n_it) gather(cn, v);
+    for (uint32_t it = (uint32_t)grp; it < n_it; it += 2) {
+      const bool more = it + 2 < n_it;
+      if (more) {
+        cur_step2(cn);
+        gather(cn, vn);
       }
       const uint32_t sa = it % CU_A_SLOTS, pa = (it / CU_A_SLOTS) & 1;
       smem_bar_wait(&a_empty[sa], pa ^ 1);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + sa * 64;
-      tmem_st32(taddr, hi);
-      tmem_st32(taddr + 32, lo);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {  // 16 channels at a time: hi / lo of a half live in 32 registers next to v / vn
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float f = p.pre_elu ? elu_fast(v[half * 16 + i]) : v[half * 16 + i];
+          const uint32_t h = tf32_rna_bits(f);
+          hi[i] = h;
+          lo[i] = tf32_rna_bits(f - __uint_as_float(h));
+        }
+        tmem_st16(taddr + half * 16, hi);
+        tmem_st16(taddr + 32 + half * 16, lo);
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(&a_full[sa]);
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = vn[i];
+      }
     }
   } else if (warp >= 12) {
     // ================= epilogue
     const int q = warp & 3;
     const int r = q * 32 + lane;
     pdl_wait();  // residual operand / output buffer ordering against the preceding kernels
+    // Per tile: row base of this thread's position; per column only a multiply-add (conv) or a phase / channel split (transposed).
+    struct Row {
+      size_t base;   // conv: &y[b, n0, t_pos]; transposed: &y[b, 0, 0]
+      int t_pos;
+      bool ok;
+    };
+    auto row_of = [&](int j) -> Row {
+      const int tile = cta + j * G;
+      const int b = tile / p.tiles_per_b, t_pos = (tile - b * p.tiles_per_b) * CU_BM + r;
+      Row rw;
+      rw.t_pos = t_pos;
+      rw.ok = t_pos < p.T_pos;
+      rw.base = p.tr_stride ? (size_t)b * p.Cout * p.T_out : ((size_t)b * p.Cout + p.n0) * p.T_out + t_pos;
+      return rw;
+    };
+    auto where = [&](const Row& rw, int col, size_t& idx, int& co) -> bool {
+      if (!p.tr_stride) {
+        co = p.n0 + col;
+        idx = rw.base + (size_t)col * p.T_out;
+        return rw.ok && col < p.n_cols;
+      }
+      // transposed convolution: column = phase * Cout + channel, output time j * s + phase - crop
+      const int c = p.n0 + col, ph = c / p.Cout;
+      co = c - ph * p.Cout;
+      const int t = rw.t_pos * p.tr_stride + ph - p.tr_crop;
+      idx = rw.base + (size_t)co * p.T_out + t;
+      return rw.ok && col < p.n_cols && t >= 0 && t < p.T_out;
+    };
+    // bias + residual of 32 columns: read-only loads that do not depend on the accumulator, so they are issued one chunk AHEAD
+    // (before the wait for the tile's MMAs / before the previous chunk's stores) and their latency hides behind the tensor cores.
+    auto load_add = [&](const Row& rw, int c0, float (&add)[32]) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        size_t idx;
+        int co;
+        const bool ok = where(rw, c0 + i, idx, co);
+        float a = (ok && p.bias) ? __ldg(p.bias + co) : 0.f;
+        if (ok && p.res) a += __ldg(p.res + idx);
+        add[i] = a;
+      }
+    };
+    float add_next[32];
+    Row row_next{};
+    if (my_tiles > 0) {
+      row_next = row_of(0);
+      load_add(row_next, 0, add_next);
+    }
     for (int j = 0; j < my_tiles; ++j) {
       const int ab = NACC == 2 ? (j & 1) : 0;
       const uint32_t use = NACC == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;
-      const int tile = cta + j * G;
-      const int b = tile / p.tiles_per_b, t_out = (tile - b * p.tiles_per_b) * CU_BM + r;
+      const Row rw = row_next;
+      if (j + 1 < my_tiles) row_next = row_of(j + 1);
       smem_bar_wait(&acc_full[ab], use & 1);
       tc_fence_after();
-      const size_t row = ((size_t)b * p.Cout) * p.T_out + t_out;
 #pragma unroll 1
       for (int c0 = 0; c0 < NO; c0 += 32) {
-        if (c0 >= p.Cout) break;
+        if (c0 >= p.n_cols) break;
+        float add[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) add[i] = add_next[i];
+        if (c0 + 32 < p.n_cols && c0 + 32 < NO)
+          load_add(rw, c0 + 32, add_next);
+        else if (j + 1 < my_tiles)
+          load_add(row_next, 0, add_next);
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * 128 + c0, v);
         tmem_wait_ld();
-        if (t_out < p.T_out) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int co = c0 + i;
-            if (co < p.Cout) {
-              float o = __uint_as_float(v[i]) + (p.bias ? p.bias[co] : 0.f);
-              const size_t idx = row + (size_t)co * p.T_out;
-              if (p.res) o += p.res[idx];
-              p.y[idx] = o;
-            }
-          }
+        for (int i = 0; i < 32; ++i) {
+          size_t idx;
+          int co;
+          if (where(rw, c0 + i, idx, co)) p.y[idx] = __uint_as_float(v[i]) + add[i];
         }
       }
       tc_fence_before();
@@ -240,6 +349,21 @@ __global__ void conv_umma_repack_kernel(const float* __restrict__ w, float* __re
     wp[n + i] = __uint_as_float(tf32_rna_bits(v - __uint_as_float(h)));
   }
 }
+// per-phase transposed-conv operand (s, Cout, Cin, 2) (repack_convtr_phase_kernel, ua2_codec.cu) -> [2][s * Cout][tap * Cin + ci] planes
+__global__ void convtr_umma_repack_kernel(const float* __restrict__ w_phase, float* __restrict__ wp, int rows, int Cin) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int KT = 2 * Cin;
+  const long long n = (long long)rows * KT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / KT), k = (int)(i - (long long)row * KT);
+    const int tap = k / Cin, ci = k - tap * Cin;
+    const float v = w_phase[((size_t)row * Cin + ci) * 2 + tap];
+    const uint32_t h = tf32_rna_bits(v);
+    wp[i] = __uint_as_float(h);
+    wp[n + i] = __uint_as_float(tf32_rna_bits(v - __uint_as_float(h)));
+  }
+}
 
 struct ConvUmmaScratch {
   float* wp = nullptr;
@@ -247,6 +371,25 @@ struct ConvUmmaScratch {
 };
 ConvUmmaScratch g_cu;
 int g_conv_umma = 1;
+
+cudaError_t reserve_wp(const LaunchCtx& lc, size_t need) {
+  if (need <= g_cu.floats) return cudaSuccess;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(lc.stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return cudaErrorNotSupported;  // the scratch would have to grow
+  if (g_cu.wp) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    cudaFree(g_cu.wp);
+    g_cu.wp = nullptr;
+    g_cu.floats = 0;
+  }
+  const size_t want = std::max(need, (size_t)1 << 21);
+  cudaError_t e = cudaMalloc((void**)&g_cu.wp, want * sizeof(float));
+  if (e != cudaSuccess) return e;
+  g_cu.floats = want;
+  return cudaSuccess;
+}
 
 template <int NO>
 cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, ConvUmmaParams p) {
@@ -261,16 +404,29 @@ cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, ConvUmmaParam
   }
   p.n_stages = stages;
   const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + (2 * CU_MAX_STAGES + 2 * CU_A_SLOTS + 4) * 8 + 16;
-  static size_t attr = 0;
-  if (smem > attr) {
+  static bool attr = false;
+  if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     if (e != cudaSuccess) return e;
-    attr = 220 * 1024;
+    attr = true;
   }
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(p.n_tiles, sms);
   return launch(lc, conv_umma_kernel<NO>, dim3(grid), dim3(CU_THREADS), smem, tmW, p);
+}
+
+// columns [n0, n0 + n_cols) of a GEMM whose weight planes hold `rows_total` rows
+cudaError_t launch_cols(const LaunchCtx& lc, ConvUmmaParams p, int KT, int rows_total) {
+  const int NO = p.n_cols <= 32 ? 32 : p.n_cols <= 64 ? 64 : p.n_cols <= 128 ? 128 : 256;
+  CUtensorMap tmW;
+  if (!make_tmap(&tmW, g_cu.wp, KT, rows_total, 2, NO, false)) return cudaErrorNotSupported;
+  switch (NO) {
+    case 32: return launch_no<32>(lc, tmW, p);
+    case 64: return launch_no<64>(lc, tmW, p);
+    case 128: return launch_no<128>(lc, tmW, p);
+    default: return launch_no<256>(lc, tmW, p);
+  }
 }
 
 }  // namespace
@@ -283,31 +439,16 @@ cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float*
                                int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
                                int replicate) {
   if (!g_conv_umma || dilation != 1 || replicate || (Cin & 31) || Cout < 16 || Cout > 256 || (long long)B * T_out < 4 * CU_BM) return cudaErrorNotSupported;
+  // pointwise convolutions with fewer than 4 k-blocks per tile are all epilogue (measured at batch 16 x 10 s: 32 -> 64 at 24 kHz 3.0 ms
+  // here against 1.6 ms on the fp32 register-tiled core, 64 -> 128 at 6 kHz 2.6 against 2.2): they stay on the SIMT core
+  if (Ktaps == 1 && Cin < 128) return cudaErrorNotSupported;
   const long long KT = (long long)Cin * Ktaps;
   if (KT > (1 << 20)) return cudaErrorNotSupported;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(lc.stream, &cs);
-  const size_t need = (size_t)2 * Cout * KT;
-  if (need > g_cu.floats) {
-    if (cs != cudaStreamCaptureStatusNone) return cudaErrorNotSupported;  // the scratch would have to grow
-    if (g_cu.wp) {
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) return e;
-      cudaFree(g_cu.wp);
-      g_cu.wp = nullptr;
-      g_cu.floats = 0;
-    }
-    const size_t want = std::max(need, (size_t)1 << 20);
-    cudaError_t e = cudaMalloc((void**)&g_cu.wp, want * sizeof(float));
-    if (e != cudaSuccess) return e;
-    g_cu.floats = want;
-  }
-  cudaError_t e = launch(lc, conv_umma_repack_kernel, dim3((unsigned)std::min<long long>((Cout * KT + 255) / 256, 148 * 8)), dim3(256), 0, w_torch,
-                         g_cu.wp, Cout, Cin, Ktaps);
+  cudaError_t e = reserve_wp(lc, (size_t)2 * Cout * KT);
   if (e != cudaSuccess) return e;
-  const int NO = Cout <= 32 ? 32 : Cout <= 64 ? 64 : Cout <= 128 ? 128 : 256;
-  CUtensorMap tmW;
-  if (!make_tmap(&tmW, g_cu.wp, (int)KT, Cout, 2, NO, false)) return cudaErrorNotSupported;
+  e = launch(lc, conv_umma_repack_kernel, dim3((unsigned)std::min<long long>((Cout * KT + 255) / 256, 148 * 8)), dim3(256), 0, w_torch, g_cu.wp, Cout,
+             Cin, Ktaps);
+  if (e != cudaSuccess) return e;
   ConvUmmaParams p{};
   p.x = x;
   p.bias = bias;
@@ -322,18 +463,65 @@ cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float*
   p.stride = stride;
   p.pad_left = pad_left;
   p.pre_elu = pre_elu;
+  p.tap_step = 1;
+  p.T_pos = T_out;
+  p.n0 = 0;
+  p.n_cols = Cout;
   p.KB = (int)(KT / 32);
   p.cb_per_tap = Cin / 32;
   p.tiles_per_b = (T_out + CU_BM - 1) / CU_BM;
   const long long n_tiles = (long long)B * p.tiles_per_b;
   if (n_tiles * p.KB >= (1LL << 31)) return cudaErrorNotSupported;
   p.n_tiles = (int)n_tiles;
-  switch (NO) {
-    case 32: return launch_no<32>(lc, tmW, p);
-    case 64: return launch_no<64>(lc, tmW, p);
-    case 128: return launch_no<128>(lc, tmW, p);
-    default: return launch_no<256>(lc, tmW, p);
+  return launch_cols(lc, p, (int)KT, Cout);
+}
+
+// Transposed convolution with kernel = 2 * stride (modules/conv.py:306-329) over the per-phase weights of launch_convtr1d_gemm:
+//   y[b, n, j * s + ph - crop_left] = bias[n] + sum_ci ( w[ph][n][ci][0] f(x[b, ci, j]) + w[ph][n][ci][1] f(x[b, ci, j - 1]) )
+// as ONE implicit GEMM over the input grid j with K = 2 Cin and the s * Cout (phase, channel) pairs as columns, 256 columns per launch.
+cudaError_t launch_convtr1d_umma(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin, int Cout,
+                                 int T_in, int stride, int pre_elu, int crop_left, int T_out) {
+  const int Tj = (crop_left + T_out > T_in * stride) ? T_in + 1 : T_in;
+  const int rows = stride * Cout, KT = 2 * Cin;
+  if (!g_conv_umma || (Cin & 31) || Cout < 16 || (long long)B * Tj < 4 * CU_BM || rows > 4096) return cudaErrorNotSupported;
+  cudaError_t e = reserve_wp(lc, (size_t)2 * rows * KT);
+  if (e != cudaSuccess) return e;
+  e = launch(lc, convtr_umma_repack_kernel, dim3((unsigned)std::min<long long>(((long long)rows * KT + 255) / 256, 148 * 8)), dim3(256), 0, w_phase,
+             g_cu.wp, rows, Cin);
+  if (e != cudaSuccess) return e;
+  ConvUmmaParams p{};
+  p.x = x;
+  p.bias = bias;
+  p.res = nullptr;
+  p.y = y;
+  p.B = B;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.T_in = T_in;
+  p.T_out = T_out;
+  p.Ktaps = 2;
+  p.stride = 1;
+  p.pad_left = 0;
+  p.pre_elu = pre_elu;
+  p.tap_step = -1;
+  p.T_pos = Tj;
+  p.tr_stride = stride;
+  p.tr_crop = crop_left;
+  p.KB = KT / 32;
+  p.cb_per_tap = Cin / 32;
+  p.tiles_per_b = (Tj + CU_BM - 1) / CU_BM;
+  const long long n_tiles = (long long)B * p.tiles_per_b;
+  if (n_tiles * p.KB >= (1LL << 31)) return cudaErrorNotSupported;
+  p.n_tiles = (int)n_tiles;
+  // whole phases per launch, at most 256 columns (Cout <= 256); a wider layer goes one phase at a time in chunks of 256 channels
+  const int ph_per = Cout <= 256 ? std::max(1, 256 / Cout) : 0;
+  if (ph_per == 0) return cudaErrorNotSupported;
+  for (int ph0 = 0; ph0 < stride; ph0 += ph_per) {
+    p.n0 = ph0 * Cout;
+    p.n_cols = std::min(ph_per, stride - ph0) * Cout;
+    if ((e = launch_cols(lc, p, KT, rows)) != cudaSuccess) return e;
   }
+  return cudaSuccess;
 }
 
 }  // namespace ua2

@@ -456,9 +456,119 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// The two thin ends of the SEANet stacks at the full 24 kHz rate (modules/seanet.py:147-150, :365-371): conv k7 1 -> 64 (encoder
+// input) and ELU + conv k7 64 -> 1 (decoder output).  One operand is a single channel, so both are pure streaming kernels (HBM
+// bound: 4 B x 64 channels per sample on the wide side); as implicit GEMMs they wasted 31 of 32 output columns (4.0 ms for the
+// decoder output at batch 16 x 10 s).  Causal zero padding, stride 1.
+constexpr int THIN_T = 1024;     // outputs per CTA (4 per thread)
+constexpr int THIN_MAX_K = 16;
+
+// Cout = 1:  y[b, 0, t] = bias + sum_{ci, k} w[0, ci, k] f(x[b, ci, t + k - pad])
+__global__ void __launch_bounds__(256) conv1d_cout1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ y, int Cin, int T, int K, int pad_left, int pre_elu) {
+  constexpr int CH = 8;  // channels per shared-memory pass
+  __shared__ __align__(16) float tile[CH][THIN_T + THIN_MAX_K];
+  __shared__ float ws[CH][THIN_MAX_K];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * THIN_T;
+  const int span = THIN_T + K - 1;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < Cin; c0 += CH) {
+    __syncthreads();
+    for (int i = tid; i < CH * span; i += 256) {
+      const int c = i / span, j = i - c * span;
+      const int t = t0 + j - pad_left;
+      float v = 0.f;
+      if (c0 + c < Cin && t >= 0 && t < T) {
+        v = x[((size_t)b * Cin + c0 + c) * T + t];
+        if (pre_elu) v = v > 0.f ? v : expm1f(v);
+      }
+      tile[c][j] = v;
+    }
+    for (int i = tid; i < CH * K; i += 256) {
+      const int c = i / K, k = i - c * K;
+      ws[c][k] = (c0 + c < Cin) ? w[(size_t)(c0 + c) * K + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float xv[4 + THIN_MAX_K - 1];
+#pragma unroll
+      for (int j = 0; j < 4 + THIN_MAX_K - 1; ++j) xv[j] = (j < 4 + K - 1) ? tile[c][4 * tid + j] : 0.f;
+#pragma unroll
+      for (int k = 0; k < THIN_MAX_K; ++k) {
+        if (k < K) {
+          const float wk = ws[c][k];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(wk, xv[o + k], acc[o]);
+        }
+      }
+    }
+  }
+  const float bv = bias ? bias[0] : 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int t = t0 + 4 * tid + o;
+    if (t < T) y[(size_t)b * T + t] = acc[o] + bv;
+  }
+}
+
+// Cin = 1:  y[b, co, t] = bias[co] + sum_k w[co, 0, k] f(x[b, 0, t + k - pad])
+__global__ void __launch_bounds__(256) conv1d_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          float* __restrict__ y, int Cout, int T, int K, int pad_left, int pre_elu) {
+  extern __shared__ float thin_ws[];  // [Cout][K] then bias [Cout]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * THIN_T + 4 * tid;
+  for (int i = tid; i < Cout * K; i += 256) thin_ws[i] = w[i];
+  for (int i = tid; i < Cout; i += 256) thin_ws[Cout * K + i] = bias ? bias[i] : 0.f;
+  float xv[4 + THIN_MAX_K - 1];
+#pragma unroll
+  for (int j = 0; j < 4 + THIN_MAX_K - 1; ++j) {
+    const int t = t0 + j - pad_left;
+    float v = (j < 4 + K - 1 && t >= 0 && t < T) ? x[(size_t)b * T + t] : 0.f;
+    if (pre_elu) v = v > 0.f ? v : expm1f(v);
+    xv[j] = v;
+  }
+  __syncthreads();
+  if (t0 >= T) return;
+  const bool vec = (T & 3) == 0 && t0 + 3 < T;
+  for (int co = 0; co < Cout; ++co) {
+    float a[4];
+    const float bv = thin_ws[Cout * K + co];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) a[o] = bv;
+#pragma unroll
+    for (int k = 0; k < THIN_MAX_K; ++k) {
+      if (k < K) {
+        const float wk = thin_ws[co * K + k];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a[o] = fmaf(wk, xv[o + k], a[o]);
+      }
+    }
+    float* dst = y + ((size_t)b * Cout + co) * T + t0;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (t0 + o < T) dst[o] = a[o];
+    }
+  }
+}
+
+
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
                                int pad_left, int pre_elu, int replicate, const float* prelu) {
+  if (prelu == nullptr && res == nullptr && stride == 1 && dilation == 1 && !replicate && Ktaps <= THIN_MAX_K && T_out == T_in && B <= 65535) {
+    const dim3 grid((T_out + THIN_T - 1) / THIN_T, B);
+    if (Cout == 1 && Cin > 1) return launch(lc, conv1d_cout1_kernel, grid, dim3(256), 0, x, w_torch, bias, y, Cin, T_in, Ktaps, pad_left, pre_elu);
+    if (Cin == 1 && Cout > 1 && (size_t)Cout * (Ktaps + 1) * 4 <= 40 * 1024)
+      return launch(lc, conv1d_cin1_kernel, grid, dim3(256), (size_t)Cout * (Ktaps + 1) * 4, x, w_torch, bias, y, Cout, T_in, Ktaps, pad_left, pre_elu);
+  }
   if (prelu == nullptr) {  // option "conv_umma" (default 1): implicit GEMM on tcgen05 straight from (B, C, T), ua2_convumma.cu
     const cudaError_t e = launch_conv1d_umma(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
                                              replicate);
@@ -486,7 +596,11 @@ cudaError_t launch_convtr1d_gemm(const LaunchCtx& lc, const float* x, const floa
                                  const float* prelu) {
   // as a conv over the input grid: 2 taps, tap 0 -> x[j], tap 1 -> x[j-1]  (dilation -1, no padding, input stride 1);
   // j runs to T_in inclusive when the right tail (x[T_in - 1] * w[ph + s]) survives the crop
-  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 0): all phases as one tensor-core GEMM, ua2_convtc.cu
+  if (prelu == nullptr && Cout <= 64) {  // the narrow 24 kHz layer (128 -> 64): implicit GEMM straight from (B, C, T), ua2_convumma.cu (option "conv_umma"); wider ones measured equal or better as im2col + GEMM
+    const cudaError_t e = launch_convtr1d_umma(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, pre_elu, crop_left, T_out);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 1): all phases as one tensor-core GEMM, ua2_convtc.cu
     const cudaError_t e = launch_convtr1d_tc(lc, x, w_phase, bias, y, B, Cin, Cout, T_in, stride, pre_elu, crop_left, T_out);
     if (e != cudaErrorNotSupported) return e;
   }
