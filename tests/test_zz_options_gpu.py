@@ -391,3 +391,81 @@ def test_attn_ring_option_keeps_llm_golden_ids():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_llm_gpu.py"), "-q", "-x", "-m", "gpu", "-k", "batch"],
                        capture_output=True, text=True, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+# ---- (6) option "conv_umma": causal convolutions as an implicit GEMM on tcgen05 straight from (B, C, T) (csrc/ua2_convumma.cu)
+@pytest.mark.parametrize("B,Cin,Cout,T,K,stride,elu,res", [
+    (2, 64, 32, 1500, 3, 1, 1, 0),      # residual block, first convolution (weights resident, two accumulators)
+    (1, 128, 256, 700, 1, 1, 1, 1),     # pointwise with residual, 256 output channels (single accumulator)
+    (2, 64, 128, 2051, 8, 4, 1, 0),     # strided down-sampling, ragged length
+    (1, 128, 256, 1285, 10, 5, 1, 0),   # 40 k-blocks: weights streamed through the ring
+    (3, 32, 48, 333, 7, 1, 0, 0),       # Cout not a multiple of 32, no activation
+    (1, 64, 16, 40, 3, 1, 1, 0),        # too few positions: stays on the SIMT core (the option must not change it)
+])
+def test_conv_umma_option_matches_oracle(B, Cin, Cout, T, K, stride, elu, res):
+    import math
+
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cin + Cout + T + K)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = CO.conv1d_causal(F.elu(x) if elu else x, w, b, stride=stride, dilation=1)
+    r = torch.randn_like(ref) if res else None
+    if res:
+        ref = r + ref
+    xd, wd, bd = x.cuda(), w.contiguous().cuda(), b.cuda()
+    rd = r.cuda() if res else None
+    outs = []
+    try:
+        for opt in (0, 1):
+            _lib.check(L.ua2_set_global_option(b"conv_umma", opt))
+            y = torch.full((B, Cout, ref.shape[-1]), float("nan"), device="cuda")
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(rd), _lib.ptr(y), B, Cin, Cout, T, K,
+                                                    stride, 1, elu, 0, None))
+            torch.cuda.synchronize()
+            outs.append(y.cpu())
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_umma", 1))
+    # fp32-class: 3xTF32 + the TMEM accumulator's round-toward-zero per k-step (see test_conv_tc_option_matches_oracle) + the SFU exponential
+    # of the fused ELU (abs 1e-7)
+    tol = max(2e-5, 1.5 * (3 * Cin * K / 8) * 2.0 ** -24)
+    for y in outs:
+        assert bool(torch.isfinite(y).all())
+        assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,stride", [(2, 128, 64, 1000, 4), (1, 64, 32, 777, 5), (1, 128, 64, 600, 8)])
+def test_convtr_umma_option_matches_oracle(B, Cin, Cout, T, stride):
+    """Transposed convolution (kernel = 2 x stride, causal trim) with all phases as columns of one implicit GEMM over the input grid."""
+    import math
+
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cin + T + stride)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, 2 * stride, generator=g) / math.sqrt(Cin * 2)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = CO.convtr1d_causal(F.elu(x), w, b, stride=stride)
+    xd, wd, bd = x.cuda(), w.contiguous().cuda(), b.cuda()
+    wp = torch.empty(stride, Cout, Cin, 2, device="cuda")
+    _lib.check(L.ua2_convtr1d_repack_phase_f32(_lib.ptr(wd), _lib.ptr(wp), Cin, Cout, stride, None))
+    outs = []
+    try:
+        for opt in (0, 1):
+            _lib.check(L.ua2_set_global_option(b"conv_umma", opt))
+            y = torch.full((B, Cout, T * stride), float("nan"), device="cuda")
+            _lib.check(L.ua2_convtr1d_causal_gemm_f32(_lib.ptr(xd), _lib.ptr(wp), _lib.ptr(bd), _lib.ptr(y), B, Cin, Cout, T, stride, 1, None))
+            torch.cuda.synchronize()
+            outs.append(y.cpu())
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_umma", 1))
+    tol = max(2e-5, 1.5 * (3 * 2 * Cin / 8) * 2.0 ** -24)
+    for y in outs:
+        assert y.shape == ref.shape and bool(torch.isfinite(y).all())
+        assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
