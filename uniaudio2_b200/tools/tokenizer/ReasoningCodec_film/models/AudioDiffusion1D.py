@@ -3,6 +3,8 @@
 guidance mix, Euler update) on the device through ua2_dit_solve_euler - no host synchronisation between steps."""
 import ctypes as C
 
+import math
+
 import torch
 import torch.nn as nn
 
@@ -54,6 +56,9 @@ class ResidualVQ(nn.Module):
     def __init__(self, dim, codebook_size, codebook_dim, num_quantizers, device=None, **unused_training_kwargs):
         super().__init__()
         self.dim, self.codebook_size, self.codebook_dim, self.num_quantizers = dim, codebook_size, codebook_dim, num_quantizers
+        self.project_in = nn.Module()  # dim -> codebook_dim (the package inserts it because dim != codebook_dim); encode side only
+        self.project_in.weight = nn.Parameter(torch.zeros(codebook_dim, dim, device=device), requires_grad=False)
+        self.project_in.bias = nn.Parameter(torch.zeros(codebook_dim, device=device), requires_grad=False)
         self.project_out = nn.Module()
         self.project_out.weight = nn.Parameter(torch.empty(dim, codebook_dim, device=device), requires_grad=False)
         self.project_out.bias = nn.Parameter(torch.zeros(dim, device=device), requires_grad=False)
@@ -64,15 +69,47 @@ class ResidualVQ(nn.Module):
             layer._codebook.embed = nn.Parameter(torch.empty(1, codebook_size, codebook_dim, device=device), requires_grad=False)
             self.layers.append(layer)
         self._emb = None
+        self._sqnorm = None
 
     def load_state_dict(self, sd, strict=True, **kw):
         keep = set(self.state_dict().keys())
-        self._emb = None
-        return super().load_state_dict({k: v for k, v in sd.items() if k in keep}, strict=strict, **kw)
+        self._emb = self._sqnorm = None
+        sd = {k: v for k, v in sd.items() if k in keep}
+        for k in ("project_in.weight", "project_in.bias"):  # decode-only checkpoints / fixtures carry no project_in
+            if k not in sd:
+                sd[k] = self.state_dict()[k]
+        return super().load_state_dict(sd, strict=strict, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._emb = None
+        self._emb = self._sqnorm = None
         return super()._apply(fn, *a, **kw)
+
+    @torch.inference_mode()
+    def encode(self, x, codes, q_off):
+        """Eval-mode forward of the package's ResidualVQ on x (B, T, dim): project_in, then per quantizer the nearest code vector
+        (Euclidean, lowest index on ties) of the running residual - ua2_rvq_encode_gemm_f32 - writing codes[b, q_off + q, t] of a
+        (B, n_q_total, T) tensor; returns project_out(sum of the chosen code vectors) (B, T, dim)."""
+        emb = self.codebooks()
+        if self._sqnorm is None:
+            self._sqnorm = (emb * emb).sum(-1).contiguous()
+        B, T, _ = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(emb.device):
+            h = torch.empty(B, T, self.codebook_dim, device=emb.device, dtype=torch.float32)
+            _lib.check(L.ua2_linear_bias_f32(_lib.ptr(x), _lib.ptr(self.project_in.weight.detach().float().contiguous()),
+                                             _lib.ptr(self.project_in.bias.detach().float().contiguous()), _lib.ptr(h), B * T, self.codebook_dim,
+                                             self.dim, _lib.current_stream()), "project_in")
+            r = h.clone()  # running residual, frame-major (B * T, codebook_dim), updated in place
+            S = torch.empty(B * T, self.codebook_size, device=emb.device, dtype=torch.float32)
+            _lib.check(L.ua2_rvq_encode_gemm_f32(_lib.ptr(r), _lib.ptr(emb), _lib.ptr(self._sqnorm), _lib.ptr(S), _lib.ptr(codes), B,
+                                                 self.codebook_dim, T, self.codebook_size, self.num_quantizers, codes.shape[1], q_off,
+                                                 _lib.current_stream()), "rvq_encode")
+            q = (h - r).contiguous()  # sum of the chosen code vectors = input minus the final residual
+            out = torch.empty(B, T, self.dim, device=emb.device, dtype=torch.float32)
+            _lib.check(L.ua2_linear_bias_f32(_lib.ptr(q), _lib.ptr(self.project_out.weight.detach().float().contiguous()),
+                                             _lib.ptr(self.project_out.bias.detach().float().contiguous()), _lib.ptr(out), B * T, self.dim,
+                                             self.codebook_dim, _lib.current_stream()), "project_out")
+        return out
 
     def codebooks(self):
         if self._emb is None:  # (q, K, d) contiguous, the layout ua2_rvq_decode_f32 reads
@@ -104,7 +141,7 @@ class AudioDiffusion1D(nn.Module):
     (ua2_dit_solve_euler); torch only moves data (concatenate, repeat frames x2, fill the masked tail)."""
 
     def __init__(self, estimator: Transformer1DModel, codec_dim=768, codebook_size=8192, codebook_dim=32, sq_codec_latent=136,
-                 device=None):
+                 device=None, whisper_dim=1024, wavlm_dim=768, bestrq_dim=1024):
         super().__init__()
         self.codec_dim, self.sq_codec_latent = codec_dim, sq_codec_latent
         self.max_t_len = 30 * 50
@@ -117,6 +154,28 @@ class AudioDiffusion1D(nn.Module):
         self.zero_cond_embedding1 = nn.Parameter(torch.zeros(codec_dim, device=device), requires_grad=False)
         self.cfm_wrapper = BASECFM(estimator)
         self._proj = None
+        # ---- encode side (fetch_codes_batch :515-551): strided down-samplers of the SSL features, fusion linears, FiLM heads
+        self.gamma = 0.1
+
+        def lin(out_f, in_f):
+            m = nn.Module()
+            m.weight = nn.Parameter(torch.zeros(out_f, in_f, device=device), requires_grad=False)
+            m.bias = nn.Parameter(torch.zeros(out_f, device=device), requires_grad=False)
+            return m
+
+        def conv(ch, k):
+            m = nn.Module()
+            m.weight = nn.Parameter(torch.zeros(ch, ch, k, device=device), requires_grad=False)
+            m.bias = nn.Parameter(torch.zeros(ch, device=device), requires_grad=False)
+            return m
+
+        self.d_conv_whisper, self.d_conv_wavlm = conv(whisper_dim, 4), conv(wavlm_dim, 4)
+        self.d_conv_embedding_semantic, self.d_conv_embedding_acoustic = conv(bestrq_dim, 2), conv(bestrq_dim, 2)
+        self.cond_fusion_layer_semantic = lin(codec_dim, bestrq_dim)
+        self.cond_fusion_layer_acoustic = lin(codec_dim, bestrq_dim + whisper_dim)
+        self.cond_fusion_layer_phone = lin(codec_dim, wavlm_dim)
+        self.time_film_phone, self.time_film_semantic, self.time_film_acoustic = (lin(2 * codec_dim, codec_dim) for _ in range(3))
+        self.reason_adaptor = lin(codec_dim, codec_dim)
 
     @property
     def device(self):
@@ -140,6 +199,73 @@ class AudioDiffusion1D(nn.Module):
             _lib.check(_lib.lib().ua2_linear_bias_f32(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), M, w.shape[0], K, _lib.current_stream()),
                        "linear_bias")
         return y
+
+    def _draw_zero_cond(self, B):
+        """The reference's per-call `torch.rand(B, 1, 1) < 0.2` zero-condition draw of time_film (:435 - yes, at inference too)."""
+        return (torch.rand(B, 1, 1, device=self.device) < 0.2).view(-1).to(torch.uint8)
+
+    @torch.inference_mode()
+    def fetch_codes_from_features(self, whisper_embeds, wavlm_embeds, bestrq_emb_acoustic, bestrq_emb_semantic, quantized_reasoning,
+                                  film_masks=None):
+        """Everything fetch_codes_batch (:492-551) does after the SSL front-ends (Whisper, WavLM, BEST-RQ) and the reasoning encoder
+        have produced their features - the own-code chain of the codec's encode direction:
+          d_conv_* (strided Conv1d k4 s4 / k2 s2) -> cond_fusion_layer_* -> time_film (FiLM from the up-sampled reasoning features)
+          -> ResidualVQ (1 + 1 + 6 quantizers of 8192 x 32) -> codes (B, T, 8) = [phone | semantic | 6 x acoustic] and
+          merge_features = cond_feature_emb(sum of the three quantized outputs).
+        whisper / wavlm (B, C, Tw), bestrq_* (B, 1024, Tw / 2), quantized_reasoning (B, Tq, 768) with Tw / 4 == 2.5 Tq.
+        film_masks: three (B,) uint8 tensors replacing the reference's random zero-condition draws (None = draw like the reference)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise _lib.Ua2Error("AudioDiffusion1D runs on a CUDA device only (no CPU fallback): call .to('cuda') first")
+        L = _lib.lib()
+        st = _lib.current_stream
+
+        def dconv(x, m, k):
+            x = x.to(device=dev, dtype=torch.float32).contiguous()
+            B, C, T = x.shape
+            T_out = (T - k) // k + 1
+            y = torch.empty(B, C, T_out, device=dev, dtype=torch.float32)
+            _lib.check(L.ua2_conv1d_f32(_lib.ptr(x), _lib.ptr(m.weight.detach().float().contiguous()), _lib.ptr(m.bias.detach().float().contiguous()),
+                                        None, None, _lib.ptr(y), B, C, C, T, k, k, 1, 0, 0, st()), "d_conv")
+            return y
+
+        def p32(m):
+            return m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous()
+
+        with torch.cuda.device(dev):
+            whisper_rec = dconv(whisper_embeds, self.d_conv_whisper, 4)
+            wavlm_feat = dconv(wavlm_embeds, self.d_conv_wavlm, 4)
+            sem_rec = dconv(bestrq_emb_semantic, self.d_conv_embedding_semantic, 2)
+            acoustic = dconv(bestrq_emb_acoustic, self.d_conv_embedding_acoustic, 2)
+            qr = quantized_reasoning.to(device=dev, dtype=torch.float32).contiguous()
+            B, Tq, D = qr.shape
+            ra = self._linear_bias(qr, *p32(self.reason_adaptor))                       # (B, Tq, D)
+            T = int(math.floor(Tq * 2.5))
+            ra_ct = ra.transpose(1, 2).contiguous()                                      # F.interpolate works on (B, C, T)
+            up = torch.empty(B, D, T, device=dev, dtype=torch.float32)
+            _lib.check(L.ua2_interp_nearest_f32(_lib.ptr(ra_ct), _lib.ptr(up), B, D, Tq, T, 2.5, st()), "interp")
+            reasoning = up.transpose(1, 2).contiguous()                                  # (B, T, D)
+            if film_masks is None:
+                film_masks = [self._draw_zero_cond(B) for _ in range(3)]
+            codes = torch.zeros(B, 8, T, dtype=torch.int64, device=dev)
+            total = None
+            n = min(acoustic.shape[-1], whisper_rec.shape[-1])
+            branches = ((wavlm_feat, self.cond_fusion_layer_phone, self.time_film_phone, self.vq_pronunciation_semantic, 0),
+                        (sem_rec, self.cond_fusion_layer_semantic, self.time_film_semantic, self.vq_structure_semantic, 1),
+                        (torch.cat([acoustic[:, :, :n], whisper_rec[:, :, :n]], dim=1), self.cond_fusion_layer_acoustic, self.time_film_acoustic,
+                         self.vq_acoustic, 2))
+            for (feat_bct, fusion, film, vq, q_off), mask in zip(branches, film_masks):
+                f = self._linear_bias(feat_bct.transpose(1, 2).contiguous(), *p32(fusion))   # (B, T, D)
+                if f.shape[1] != T:
+                    raise ValueError(f"feature frames {f.shape[1]} != reasoning frames {T} (the reference's time_film broadcasts)")
+                params = self._linear_bias(reasoning, *p32(film))                             # (B, T, 2D)
+                out = torch.empty_like(f)
+                _lib.check(L.ua2_film_f32(_lib.ptr(params), _lib.ptr(f), _lib.ptr(mask.to(device=dev, dtype=torch.uint8).contiguous()), _lib.ptr(out),
+                                          B, T, D, float(self.gamma), st()), "time_film")
+                q = vq.encode(out, codes, q_off)
+                total = q if total is None else total + q
+            merge = self._linear_bias(total.contiguous(), *p32(self.cond_feature_emb))
+        return codes.transpose(1, 2).contiguous(), merge
 
     def prepare_latents(self, batch_size, num_frames, dtype, device):
         return torch.randn((batch_size, num_frames, self.sq_codec_latent), device=device, dtype=dtype)  # randn_tensor, :652-655
