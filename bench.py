@@ -648,12 +648,12 @@ def main():
         e2e = None
         if not args.no_e2e:
             for _ in range(2):
-                gen.generate_tts(task_prompt, "TTS", text_token=text, temperature=TEMPERATURE, topk=TOPK, fixed_schedule=(N_REASON, N_SEMANTIC))
+                gen.generate_tts(task_prompt, "TTS", text_token=text, temperature=TEMPERATURE, topk=TOPK, fixed_schedule=(N_REASON, N_SEMANTIC), device_loop=True)
             barrier()
             e0.record()
             for _ in range(args.steps):
                 r, s = gen.generate_tts(task_prompt, "TTS", text_token=text, temperature=TEMPERATURE, topk=TOPK,
-                                        fixed_schedule=(N_REASON, N_SEMANTIC))
+                                        fixed_schedule=(N_REASON, N_SEMANTIC), device_loop=True)
                 if world > 1:
                     gather_variable([torch.cat([r, s], dim=1)], world)
             e1.record()

@@ -123,6 +123,20 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
                            float temperature, int topk, int forbid_prefix, float cfg_scale, const float* noise,
                            uint64_t seed, int32_t* out, void* stream);
 
+/* The hot loop of Generator.generate_tts (evaluation/tts_task.py:253-279, B = 1) with its phase / EOS state machine ON THE DEVICE:
+ * `n_frames` consecutive frames from input_pos, each fed the previous frame's sample (audio tokens -> columns 0..nq-1, text token ->
+ * column nq, audio mask), no host round trip in between.  tokens0 / mask0 (1,1,nq+1): the prompt's last row for the first frame of an
+ * utterance, NULL to continue from the previous sample.  After every frame the sampled row is tested like the reference does:
+ * all audio tokens == end_tok -> done (nothing recorded, later frames of the call are ignored); otherwise the row is appended to
+ * frames_out (frames_cap x (1+nq) int32, device); all == reason_eos (or, with fixed_switch >= 0, the fixed_switch-th recorded frame)
+ * -> the following frames run with forbid_prefix = reason_card.
+ * state (device int32[4], zero it before an utterance): [0] forbid_prefix of the next frame, [1] done, [2] frames recorded,
+ * [3] 1-based index of the frame that switched the phase.  noise: NULL (Philox) or n_frames blocks of noise_stride floats laid out as
+ * for ua2_llm_generate_frame. */
+int ua2_llm_tts_frames(ua2_llm* h, const int64_t* tokens0, const uint8_t* mask0, int64_t input_pos, int n_frames, float temperature, int topk,
+                       const float* noise, int64_t noise_stride, uint64_t seed, int reason_eos, int end_tok, int reason_card, int fixed_switch,
+                       int32_t* state, int32_t* frames_out, int frames_cap, void* stream);
+
 /* Introspection for parity tests: device pointers of internal buffers (valid until destroy).
  * which: 0 backbone, 1 decoder, 2 understanding, 3 generation. */
 int ua2_llm_get_kv(ua2_llm* h, int which, int layer, float** k, float** v);
@@ -149,6 +163,10 @@ int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float ep
  * (model_new.py:456-507) and batched frames use for M >= tc_min_rows.  Scratch is owned by the library. */
 int ua2_tc_linear_f32(const float* x, const float* W, const float* W2, const float* norm_w, float eps, const float* residual, float* y,
                       int M, int N, int K, void* stream);
+/* One application of the TTS loop's break / phase-switch rules (evaluation/tts_task.py:259-271) to a sampled row (1+nq int32, device):
+ * the state machine that ua2_llm_tts_frames runs after every frame. */
+int ua2_tts_state_step(const int32_t* sample, int nq, int32_t* state, int32_t* frames_out, int frames_cap, int reason_eos, int end_tok,
+                       int reason_card, int fixed_switch, void* stream);
 /* y[m, n] = silu(sum_k f(x) W1[n,k]) * (sum_k f(x) W2[n,k])   (LLaMAMLP fc_1/fc_2, lit_model.py:591-594) */
 int ua2_swiglu_f32(const float* x, const float* W1, const float* W2, const float* norm_w, float eps, float* y, int M,
                    int N, int K, void* stream);

@@ -211,6 +211,59 @@ def test_task_generators(models):
     assert ids == ref_ids and len(ids) == 6
 
 
+def test_device_side_tts_loop_matches_host_loop(models):
+    """Generator.generate_tts with the sample feedback and the phase / EOS state machine on the device (ua2_llm_tts_frames, one 16-byte
+    D2H per chunk of frames) returns the tokens of the per-frame host loop - fixed schedule (random weights never emit EOS), greedy and
+    sampled (torch noise and in-kernel Philox)."""
+    from uniaudio2_b200.evaluation.tts_task import Generator, default_train_args
+
+    cfg, sd, m = models["tiny"]
+    gen = Generator(m, default_train_args(REASON_CARD["tiny"], cfg.audio_vocab - REASON_CARD["tiny"]), is_cfg=False)
+    g = torch.Generator().manual_seed(3)
+    prompt, text = torch.randint(0, 100, (5,), generator=g), torch.randint(0, 100, (6,), generator=g)
+    for rng_mode, topk in (("torch", 1), ("torch", 20), ("philox", 20)):
+        m.rng_mode = rng_mode
+        outs = []
+        for dev_loop in (False, True):
+            torch.manual_seed(11)
+            m.seed = 888
+            m.reset_frame_counter() if hasattr(m, "reset_frame_counter") else None
+            r, s = gen.generate_tts(prompt, "TTS", text_token=text, temperature=0.9, topk=topk, fixed_schedule=(5, 9), device_loop=dev_loop,
+                                    sync_every=4)
+            outs.append((r.cpu(), s.cpu(), gen.n_frames))
+        if rng_mode == "torch":  # Philox draws are keyed by the library's frame counter, which keeps running between the two runs
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (rng_mode, topk)
+        assert outs[0][2] == outs[1][2] == 14
+        assert outs[1][0].shape == outs[0][0].shape == (8, 3) and outs[1][1].shape == outs[0][1].shape == (8, 8)
+    m.rng_mode = "torch"
+
+
+def test_device_side_tts_state_machine_follows_the_reference_rules(models):
+    """The EOS / phase rules of tts_task.py:253-279 on scripted rows: frames_out / state after every call of the device kernel equal a
+    restatement of the reference's loop body (break on all == end_tok before recording; all == reason_eos switches the phase)."""
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    nq, reason_eos, end_tok, card = 8, 5, 100 + 7, 100
+    script = [[1] * 9, [0] + [3] * 8, [0] + [reason_eos] * 8, [2] + [150] * 8, [9] + [end_tok] * 7 + [101], [4] + [end_tok] * 8, [1] + [120] * 8]
+    state = torch.zeros(4, dtype=torch.int32, device="cuda")
+    out = torch.zeros(16, nq + 1, dtype=torch.int32, device="cuda")
+    ref_rows, forbid, done, switch = [], 0, False, 0
+    for row in script:
+        smp = torch.tensor(row, dtype=torch.int32, device="cuda")
+        _lib.check(L.ua2_tts_state_step(_lib.ptr(smp), nq, _lib.ptr(state), _lib.ptr(out), 16, reason_eos, end_tok, card, -1, None))
+        if not done:
+            if all(v == end_tok for v in row[1:]):
+                done = True
+            else:
+                ref_rows.append(row)
+                if all(v == reason_eos for v in row[1:]):
+                    forbid, switch = card, len(ref_rows)
+        st = state.cpu().tolist()
+        assert st == [forbid, int(done), len(ref_rows), switch], (row, st)
+    assert out[: len(ref_rows)].cpu().tolist() == ref_rows and len(ref_rows) == 5 and done
+
+
 def test_batch32_caption_config():
     """SURVEY section 8(d) config 3 shape: 32 equal-length mixed prompts, batched prefill (B*S rows go through the tiled
     GEMM path) + greedy frames at B = 32 (four M tiles of 8 rows per linear), against the oracle run in-process.

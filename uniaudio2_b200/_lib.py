@@ -63,8 +63,11 @@ SYMBOLS = {
                                          C.c_uint64, _P, _P]),
     "ua2_llm_get_kv": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     "ua2_llm_get_buffer": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "ua2_llm_tts_frames": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_int, _P, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, _P, _P, C.c_int, _P]),
     "ua2_llm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ua2_llm_last_launch_count": (C.c_int, [_P]),
+    "ua2_tts_state_step": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_linear_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_tc_linear_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_swiglu_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, _P]),

@@ -201,6 +201,12 @@ enum : int { MIX_UND_TO_BACKBONE = 0, MIX_BACKBONE_TO_GEN = 1, MIX_FINAL = 2, MI
 cudaError_t launch_frame_begin(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, int n_tok,
                                int64_t* d_tokens, uint8_t* d_mask, int32_t* d_pos, int32_t* d_bidx, int B,
                                int32_t pos_value, FrameScalars* d_fs, FrameScalars fs);
+// device-side phase / EOS state machine of the TTS task loop (ua2_llm_tts_frames)
+cudaError_t launch_tts_begin(const LaunchCtx& lc, const int64_t* tokens0, const uint8_t* mask0, const int32_t* prev_sample, int nq,
+                             int64_t* d_tokens, uint8_t* d_mask, int32_t* d_pos, int32_t* d_bidx, int32_t pos_value, FrameScalars* d_fs,
+                             FrameScalars fs, const int32_t* state);
+cudaError_t launch_tts_state(const LaunchCtx& lc, const int32_t* sample, int nq, int32_t* state, int32_t* frames_out, int frames_cap,
+                             int reason_eos, int end_tok, int reason_card, int fixed_switch);
 cudaError_t launch_prefill_begin(const LaunchCtx& lc, const int64_t* pos64, int32_t* d_pos, int32_t* d_bidx, int M,
                                  int T, int row0);
 // audio_head (nq, d, V) -> (nq, V, d)

@@ -632,6 +632,72 @@ int ua2_llm_prefill(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, cons
   return UA2_OK;
 }
 
+}  // extern "C"
+
+// The kernels of one frame after frame_begin (global stacks, heads, local decoder, samplers): eager on the first use of a shape,
+// captured on the second, replayed as a CUDA graph from then on.  lc.launch_counter must be set.
+static int run_frame_body(ua2_llm* h, LaunchCtx lc, int B, int rows, int64_t input_pos, bool use_cfg) {
+  cudaStream_t stream = lc.stream;
+  const int n_splits = (int)(input_pos / ATTN_CHUNK) + 1;
+  lc.pdl = h->opt_pdl != 0;
+  const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |
+                                 (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull) | (h->opt_attn_direct ? 4ull : 0ull) |
+                                 ((get_tc_gemm() && B >= get_tc_min_rows()) ? 8ull : 0ull);
+  // the frame's sequence of linears: recorded by the first run of this shape, replayed (with tail prefetch specs of the
+  // following weights) by every later run / by the graph capture
+  GemvSeq& sq = h->seqs[key];
+  sq.pos = 0;
+  struct SeqDone {
+    GemvSeq& s;
+    ~SeqDone() { s.recorded = s.recorded || !s.ops.empty(); }
+  };
+  if (!h->opt_graph) {
+    lc.seq = &sq;
+    SeqDone done{sq};
+    UA2_CHECK_CUDA(run_global(h, lc, B, n_splits, true));
+    UA2_CHECK_CUDA(run_heads(h, lc, B, rows));
+  } else {
+    lc.seq = &sq;
+    SeqDone done{sq};
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      // first use of this shape: run eagerly (also sets the lazily-initialised kernel attributes)
+      UA2_CHECK_CUDA(run_global(h, lc, B, n_splits, true));
+      UA2_CHECK_CUDA(run_heads(h, lc, B, rows));
+      h->graphs.emplace(key, ua2_llm::GraphEntry());
+      return UA2_OK;
+    }
+    if (it->second.exec == nullptr) {
+      // second use: capture on a private stream so the caller's stream state is untouched
+      cudaStream_t cs;
+      UA2_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      LaunchCtx lcc = lc;
+      lcc.stream = cs;
+      int glaunches = 0;
+      lcc.launch_counter = &glaunches;
+      cudaGraph_t graph = nullptr;
+      UA2_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e1 = run_global(h, lcc, B, n_splits, true);
+      cudaError_t e2 = (e1 == cudaSuccess) ? run_heads(h, lcc, B, rows) : e1;
+      cudaError_t e3 = cudaStreamEndCapture(cs, &graph);
+      if (e2 != cudaSuccess || e3 != cudaSuccess) {
+        set_error(std::string("graph capture failed: ") + cudaGetErrorString(e2 != cudaSuccess ? e2 : e3));
+        cudaStreamDestroy(cs);
+        return UA2_ERR_CUDA;
+      }
+      UA2_CHECK_CUDA(cudaGraphInstantiate(&it->second.exec, graph, 0));
+      it->second.launches = glaunches;
+      cudaGraphDestroy(graph);
+      cudaStreamDestroy(cs);
+    }
+    UA2_CHECK_CUDA(cudaGraphLaunch(it->second.exec, stream));
+    *lc.launch_counter += it->second.launches;
+  }
+  return UA2_OK;
+}
+
+extern "C" {
+
 int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, int B, int64_t input_pos,
                            float temperature, int topk, int forbid_prefix, float cfg_scale, const float* noise,
                            uint64_t seed, int32_t* out, void* stream_v) {
@@ -676,64 +742,54 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
   h->rows_are_batch = true;
   UA2_CHECK_CUDA(launch_frame_begin(lc, tokens, mask, B * (nq + 1), h->d_tokens, h->d_mask, h->d_pos, h->d_bidx, B,
                                     (int32_t)input_pos, h->d_fs, fs));
-  const int n_splits = (int)(input_pos / ATTN_CHUNK) + 1;
   lc.pdl = h->opt_pdl != 0;
-  const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |
-                                 (use_cfg ? 2ull : 0ull) | (h->opt_pdl ? 1ull : 0ull) | (h->opt_attn_direct ? 4ull : 0ull) |
-                                 ((get_tc_gemm() && B >= get_tc_min_rows()) ? 8ull : 0ull);
-  // the frame's sequence of linears: recorded by the first run of this shape, replayed (with tail prefetch specs of the
-  // following weights) by every later run / by the graph capture
-  GemvSeq& sq = h->seqs[key];
-  sq.pos = 0;
-  struct SeqDone {
-    GemvSeq& s;
-    ~SeqDone() { s.recorded = s.recorded || !s.ops.empty(); }
-  };
-  if (!h->opt_graph) {
-    lc.seq = &sq;
-    SeqDone done{sq};
-    UA2_CHECK_CUDA(run_global(h, lc, B, n_splits, true));
-    UA2_CHECK_CUDA(run_heads(h, lc, B, rows));
-  } else {
-    lc.seq = &sq;
-    SeqDone done{sq};
-    auto it = h->graphs.find(key);
-    if (it == h->graphs.end()) {
-      // first use of this shape: run eagerly (also sets the lazily-initialised kernel attributes)
-      UA2_CHECK_CUDA(run_global(h, lc, B, n_splits, true));
-      UA2_CHECK_CUDA(run_heads(h, lc, B, rows));
-      h->graphs.emplace(key, ua2_llm::GraphEntry());
-      UA2_CHECK_CUDA(cudaMemcpyAsync(out, mirror, (size_t)B * (nq + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-      h->last_launches = launches;
-      return UA2_OK;
-    }
-    if (it->second.exec == nullptr) {
-      // second use: capture on a private stream so the caller's stream state is untouched
-      cudaStream_t cs;
-      UA2_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      LaunchCtx lcc = lc;
-      lcc.stream = cs;
-      int glaunches = 0;
-      lcc.launch_counter = &glaunches;
-      cudaGraph_t graph = nullptr;
-      UA2_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      cudaError_t e1 = run_global(h, lcc, B, n_splits, true);
-      cudaError_t e2 = (e1 == cudaSuccess) ? run_heads(h, lcc, B, rows) : e1;
-      cudaError_t e3 = cudaStreamEndCapture(cs, &graph);
-      if (e2 != cudaSuccess || e3 != cudaSuccess) {
-        set_error(std::string("graph capture failed: ") + cudaGetErrorString(e2 != cudaSuccess ? e2 : e3));
-        cudaStreamDestroy(cs);
-        return UA2_ERR_CUDA;
-      }
-      UA2_CHECK_CUDA(cudaGraphInstantiate(&it->second.exec, graph, 0));
-      it->second.launches = glaunches;
-      cudaGraphDestroy(graph);
-      cudaStreamDestroy(cs);
-    }
-    UA2_CHECK_CUDA(cudaGraphLaunch(it->second.exec, stream));
-    launches += it->second.launches;
-  }
+  if (int rc = run_frame_body(h, lc, B, rows, input_pos, use_cfg)) return rc;
   UA2_CHECK_CUDA(cudaMemcpyAsync(out, mirror, (size_t)B * (nq + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+  h->last_launches = launches;
+  return UA2_OK;
+}
+
+int ua2_llm_tts_frames(ua2_llm* h, const int64_t* tokens0, const uint8_t* mask0, int64_t input_pos, int n_frames, float temperature, int topk,
+                       const float* noise, int64_t noise_stride, uint64_t seed, int reason_eos, int end_tok, int reason_card, int fixed_switch,
+                       int32_t* state, int32_t* frames_out, int frames_cap, void* stream_v) {
+  UA2_REQUIRE(h && state && frames_out, "null argument");
+  if (!h->ready) {
+    set_error("You need to call setup_caches() first");
+    return UA2_ERR_STATE;
+  }
+  UA2_REQUIRE((tokens0 == nullptr) == (mask0 == nullptr), "tokens0 and mask0 go together");
+  UA2_REQUIRE(n_frames >= 1 && input_pos >= 0 && input_pos + n_frames <= h->cfg.max_seq_length, "Positions in 'input_pos' must be in [0,max_seq_length)");
+  UA2_REQUIRE(temperature > 0.f, "temperature must be > 0");
+  UA2_REQUIRE(reason_card >= 0 && reason_card < h->cfg.audio_vocab, "forbid_prefix must be smaller than vocab size");
+  UA2_REQUIRE(topk >= 1 && topk <= h->cfg.audio_vocab - reason_card && topk <= h->cfg.text_vocab, "topk must be in 1..effective_vocab given forbid_prefix");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const int nq = h->cfg.num_codebooks;
+  int32_t* mirror = reinterpret_cast<int32_t*>(h->audio_logits + h->audio_logits_numel);
+  int launches = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    FrameScalars fs;
+    fs.temperature = temperature;
+    fs.topk = topk;
+    fs.forbid_prefix = 0;  // overwritten on the device from state[0]
+    fs.cfg_scale = 1.f;
+    fs.seed = seed;
+    fs.offset = h->frame_counter++;
+    fs.noise = noise ? noise + (size_t)f * noise_stride : nullptr;
+    fs.out = mirror;
+    fs.rows = 1;
+    fs.B = 1;
+    LaunchCtx lc;
+    lc.stream = stream;
+    lc.launch_counter = &launches;
+    h->rows_are_batch = true;
+    const bool first = f == 0 && tokens0 != nullptr;
+    UA2_CHECK_CUDA(launch_tts_begin(lc, first ? tokens0 : nullptr, first ? mask0 : nullptr, mirror, nq, h->d_tokens, h->d_mask, h->d_pos, h->d_bidx,
+                                    (int32_t)(input_pos + f), h->d_fs, fs, state));
+    lc.pdl = h->opt_pdl != 0;
+    if (int rc = run_frame_body(h, lc, 1, 1, input_pos + f, false)) return rc;
+    lc.pdl = false;
+    UA2_CHECK_CUDA(launch_tts_state(lc, mirror, nq, state, frames_out, frames_cap, reason_eos, end_tok, reason_card, fixed_switch));
+  }
   h->last_launches = launches;
   return UA2_OK;
 }

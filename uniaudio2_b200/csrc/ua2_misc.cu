@@ -108,6 +108,58 @@ __global__ void frame_begin_kernel(const int64_t* __restrict__ tokens, const uin
   if (t == 0) *d_fs = fs;
 }
 
+// ---- device-side phase / EOS state machine of Generator.generate_tts (evaluation/tts_task.py:253-279, B = 1) ----
+// state[0] forbid_prefix of the next frame, [1] done, [2] frames recorded, [3] 1-based index of the frame that switched the phase (0: none)
+__global__ void tts_begin_kernel(const int64_t* __restrict__ tokens0, const uint8_t* __restrict__ mask0, const int32_t* __restrict__ prev_sample,
+                                 int nq, int64_t* __restrict__ d_tokens, uint8_t* __restrict__ d_mask, int32_t* __restrict__ d_pos,
+                                 int32_t* __restrict__ d_bidx, int32_t pos_value, FrameScalars* __restrict__ d_fs, FrameScalars fs,
+                                 const int32_t* __restrict__ state) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = threadIdx.x;
+  if (t <= nq) {
+    if (tokens0 != nullptr) {  // first frame of the utterance: the last row of the prompt
+      d_tokens[t] = tokens0[t];
+      d_mask[t] = mask0[t] ? 1 : 0;
+    } else {  // feedback (tts_task.py:276-279): audio tokens of the previous sample in columns 0..nq-1, its text token in column nq
+      d_tokens[t] = t < nq ? (int64_t)prev_sample[1 + t] : (int64_t)prev_sample[0];
+      d_mask[t] = t < nq ? 1 : 0;
+    }
+  }
+  if (t == 0) {
+    d_pos[0] = pos_value;
+    d_bidx[0] = 0;
+    fs.forbid_prefix = state[0];
+    *d_fs = fs;
+  }
+}
+
+// after the samplers of a frame: apply the reference's break / phase-switch tests to the sampled row and record it
+__global__ void tts_state_kernel(const int32_t* __restrict__ sample, int nq, int32_t* __restrict__ state, int32_t* __restrict__ frames_out,
+                                 int frames_cap, int reason_eos, int end_tok, int reason_card, int fixed_switch) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x != 0 || state[1]) return;
+  bool all_end = true, all_reason_eos = true;
+  for (int i = 1; i <= nq; ++i) {
+    all_end = all_end && sample[i] == end_tok;
+    all_reason_eos = all_reason_eos && sample[i] == reason_eos;
+  }
+  if (fixed_switch < 0 && all_end) {  // `break` before anything is recorded (tts_task.py:261-262)
+    state[1] = 1;
+    return;
+  }
+  const int n = state[2];
+  if (n < frames_cap)
+    for (int i = 0; i <= nq; ++i) frames_out[(size_t)n * (nq + 1) + i] = sample[i];
+  state[2] = n + 1;
+  const bool sw = fixed_switch >= 0 ? (n + 1 == fixed_switch) : all_reason_eos;
+  if (sw) {  // :263-266
+    state[0] = reason_card;
+    state[3] = n + 1;
+  }
+}
+
 __global__ void prefill_begin_kernel(const int64_t* __restrict__ pos64, int32_t* __restrict__ d_pos,
                                      int32_t* __restrict__ d_bidx, int M, int T, int row0) {
   pdl_launch_dependents();
@@ -170,6 +222,18 @@ cudaError_t launch_frame_begin(const LaunchCtx& lc, const int64_t* tokens, const
   misc_attrs_once();
   return launch(lc, frame_begin_kernel, dim3(1), dim3(128), 0, tokens, mask, n_tok, d_tokens, d_mask, d_pos, d_bidx, B,
                 pos_value, d_fs, fs);
+}
+
+cudaError_t launch_tts_begin(const LaunchCtx& lc, const int64_t* tokens0, const uint8_t* mask0, const int32_t* prev_sample, int nq,
+                             int64_t* d_tokens, uint8_t* d_mask, int32_t* d_pos, int32_t* d_bidx, int32_t pos_value, FrameScalars* d_fs,
+                             FrameScalars fs, const int32_t* state) {
+  return launch(lc, tts_begin_kernel, dim3(1), dim3(32), 0, tokens0, mask0, prev_sample, nq, d_tokens, d_mask, d_pos, d_bidx, pos_value, d_fs, fs,
+                state);
+}
+cudaError_t launch_tts_state(const LaunchCtx& lc, const int32_t* sample, int nq, int32_t* state, int32_t* frames_out, int frames_cap,
+                             int reason_eos, int end_tok, int reason_card, int fixed_switch) {
+  return launch(lc, tts_state_kernel, dim3(1), dim3(32), 0, sample, nq, state, frames_out, frames_cap, reason_eos, end_tok, reason_card,
+                fixed_switch);
 }
 
 cudaError_t launch_prefill_begin(const LaunchCtx& lc, const int64_t* pos64, int32_t* d_pos, int32_t* d_bidx, int M,

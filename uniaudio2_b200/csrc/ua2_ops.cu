@@ -158,6 +158,16 @@ int ua2_tc_linear_f32(const float* x, const float* W, const float* W2, const flo
   return UA2_OK;
 }
 
+// one application of the device-side TTS state machine to a sampled row (unit-parity surface of ua2_llm_tts_frames)
+int ua2_tts_state_step(const int32_t* sample, int nq, int32_t* state, int32_t* frames_out, int frames_cap, int reason_eos, int end_tok,
+                       int reason_card, int fixed_switch, void* stream) {
+  UA2_REQUIRE(sample && state && frames_out && nq >= 1 && frames_cap >= 1, "bad argument");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch_tts_state(lc, sample, nq, state, frames_out, frames_cap, reason_eos, end_tok, reason_card, fixed_switch));
+  return UA2_OK;
+}
+
 int ua2_swiglu_f32(const float* x, const float* W1, const float* W2, const float* norm_w, float eps, float* y, int M,
                    int N, int K, void* stream) {
   UA2_REQUIRE(x && W1 && W2 && y, "null argument");

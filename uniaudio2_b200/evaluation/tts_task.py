@@ -90,10 +90,14 @@ class Generator:
     @torch.inference_mode()
     def generate_tts(self, task_prompt, task_name=None, text_token=None, semantic_token=None, reason_token=None,
                      temperature: float = 0.9, topk: int = 200, cfg_scale=1.0, max_audio_frames: int = 500,
-                     fixed_schedule: Optional[Tuple[int, int]] = None, pinned_staging: bool = True, _packed=None):
+                     fixed_schedule: Optional[Tuple[int, int]] = None, pinned_staging: bool = True, _packed=None,
+                     device_loop: bool = False, sync_every: int = 16):
         """Returns (reason tokens (8, T_r), semantic tokens (8, T_s)) int64 on the model device.
         fixed_schedule=(n_reason, n_semantic): synthetic mode - switch phase after n_reason frames and stop after
-        n_reason + n_semantic frames regardless of EOS (random weights never emit EOS)."""
+        n_reason + n_semantic frames regardless of EOS (random weights never emit EOS).
+        device_loop=True (B = 1): the sample feedback and the phase / EOS tests of :253-279 run on the device (Model_stage3.tts_frames);
+        the host reads a 16-byte state record once per `sync_every` frames instead of the sampled row after every frame - at most
+        sync_every - 1 frames are computed past the end frame and discarded.  Same tokens as the host loop."""
         model, dev = self._model, self.device
         model.reset_caches()
         # _packed: (tokens, mask, cfg_tokens, cfg_mask) from another task's prompt packer (instruct TTS, speech-to-speech)
@@ -126,6 +130,32 @@ class Generator:
         audio_mask = audio_mask.to(dev)
         end_tok = self.semantic_eos + self.audio_reason_card
         n_frames = 0
+        if device_loop and not self.is_cfg:
+            state = torch.zeros(4, dtype=torch.int32, device=dev)
+            frames_buf = torch.zeros(max_audio_frames, nq + 1, dtype=torch.int32, device=dev)
+            total = max_audio_frames if fixed_schedule is None else min(max_audio_frames, fixed_schedule[0] + fixed_schedule[1])
+            total = min(total, getattr(model, "_max_seq_length", 1 << 30) - curr_pos)  # the KV caches end there
+            launched, st = 0, None
+            while launched < total:
+                n = min(int(sync_every), total - launched)
+                model.tts_frames(curr_tokens if launched == 0 else None, curr_mask if launched == 0 else None, curr_pos + launched, n, state,
+                                 frames_buf, temperature, topk, self.reason_eos, end_tok, self.audio_reason_card,
+                                 fixed_schedule[0] if fixed_schedule is not None else -1)
+                launched += n
+                st = state.cpu()  # ONE D2H of 16 bytes per chunk of frames
+                self.d2h_bytes += 16
+                if int(st[1]):
+                    break
+            n_rec, switch = int(st[2]), int(st[3])
+            rows = frames_buf[:n_rec].cpu().to(torch.int64)
+            self.d2h_bytes += rows.numel() * 4
+            self.n_frames = n_rec + (1 if int(st[1]) else 0)
+            # rows 1 .. switch - 1 are reason frames, row `switch` is the reason_eos frame (not kept, :263-271), the rest semantic
+            reason_rows = rows[: (switch - 1 if switch else n_rec), 1:]
+            sem_rows = rows[switch:, 1:] - self.audio_reason_card if switch else rows[:0, 1:]
+            de_reason = reason_rows[1:].t().contiguous() if reason_rows.shape[0] > 1 else torch.zeros(nq, 0, dtype=torch.int64)
+            de_sem = sem_rows[1:].t().contiguous() if sem_rows.shape[0] > 1 else torch.zeros(nq, 0, dtype=torch.int64)
+            return de_reason.to(dev), de_sem.to(dev)
         for _ in range(max_audio_frames):
             sample = model.generate_frame(curr_tokens, curr_mask, input_pos=curr_pos, input_pos_maxp1=maxp1,
                                           temperature=temperature, topk=topk, forbid_prefix=forbid_prefix)

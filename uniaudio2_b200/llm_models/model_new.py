@@ -250,6 +250,40 @@ class Model_stage3(nn.Module):
         return buf
 
     @torch.inference_mode()
+    def tts_frames(self, tokens, tokens_mask, input_pos: int, n_frames: int, state: torch.Tensor, frames_out: torch.Tensor,
+                   temperature: float, topk: int, reason_eos: int, end_tok: int, reason_card: int, fixed_switch: int = -1):
+        """`n_frames` consecutive frames of the TTS hot loop (evaluation/tts_task.py:253-279, B = 1) with the feedback of the sample and
+        the phase / EOS state machine on the device (ua2_llm_tts_frames): no host round trip between frames.  tokens / tokens_mask
+        (1, 1, nq+1): the prompt's last row for the first frame of an utterance, None to continue from the previous sample.  state: int32[4]
+        on the device (zero it per utterance); frames_out: int32 (cap, 1+nq) on the device."""
+        self._require_handle()
+        dev = self.audio_head.device
+        nq = self.config.audio_num_codebooks
+        tok = msk = None
+        if tokens is not None:
+            tok = tokens.to(device=dev, dtype=torch.int64).contiguous()
+            msk = tokens_mask.to(device=dev, dtype=torch.uint8).contiguous()
+            assert tok.numel() == nq + 1 and msk.numel() == nq + 1, "one row of nq + 1 streams (B = 1)"
+        noise, stride = None, 0
+        with torch.cuda.device(dev):
+            if self.rng_mode == "torch":  # the same draws, in the same order, as n_frames calls of generate_frame would take
+                Vt = self.backbone.config.padded_vocab_size
+                Va = self.config.audio_semantic_vocab_size + self.config.audio_reason_vocab_size
+                stride = Vt + nq * Va
+                if getattr(self, "_noise_frames", None) is None or self._noise_frames.numel() < n_frames * stride:
+                    self._noise_frames = torch.empty(n_frames * stride, dtype=torch.float32, device=dev)
+                noise = self._noise_frames
+                for f in range(n_frames):
+                    base = f * stride
+                    noise[base: base + Vt].view(1, Vt).exponential_(1)
+                    for i in range(nq):
+                        noise[base + Vt + i * Va: base + Vt + (i + 1) * Va].view(1, Va).exponential_(1)
+            _lib.check(_lib.lib().ua2_llm_tts_frames(self._h, _lib.ptr(tok), _lib.ptr(msk), int(input_pos), int(n_frames), float(temperature),
+                                                     int(topk), _lib.ptr(noise), int(stride), int(self.seed), int(reason_eos), int(end_tok),
+                                                     int(reason_card), int(fixed_switch), _lib.ptr(state), _lib.ptr(frames_out),
+                                                     int(frames_out.shape[0]), _lib.current_stream()), "tts_frames")
+
+    @torch.inference_mode()
     def generate_frame(self, tokens: torch.Tensor, tokens_mask: torch.Tensor, input_pos: torch.Tensor,
                        input_pos_maxp1=None, temperature: float = 1.0, topk: int = 1, forbid_prefix: int = 0,
                        cfg_scale: float = 1.0, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
