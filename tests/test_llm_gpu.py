@@ -215,10 +215,15 @@ def test_device_side_tts_loop_matches_host_loop(models):
     """Generator.generate_tts with the sample feedback and the phase / EOS state machine on the device (ua2_llm_tts_frames, one 16-byte
     D2H per chunk of frames) returns the tokens of the per-frame host loop - fixed schedule (random weights never emit EOS), greedy and
     sampled (torch noise and in-kernel Philox)."""
-    from uniaudio2_b200.evaluation.tts_task import Generator, default_train_args
+    from types import SimpleNamespace
+
+    from uniaudio2_b200.evaluation import tts_task
 
     cfg, sd, m = models["tiny"]
-    gen = Generator(m, default_train_args(REASON_CARD["tiny"], cfg.audio_vocab - REASON_CARD["tiny"]), is_cfg=False)
+    args = SimpleNamespace(text_pad_token=3, semantic_pad_token=80, semantic_eos=81, semantic_bos=82, reason_eos=37, reason_bos=38,
+                           reason_pad_token=36, parallel_number=9, audio_reason_card=REASON_CARD["tiny"], audio_semantic_card=90)
+    gen = tts_task.Generator(m, args)
+    gen.special_token_dict = {k: 1000 + i for i, k in enumerate(tts_task.SPECIAL_TOKENS)}  # ids inside the tiny vocab
     g = torch.Generator().manual_seed(3)
     prompt, text = torch.randint(0, 100, (5,), generator=g), torch.randint(0, 100, (6,), generator=g)
     for rng_mode, topk in (("torch", 1), ("torch", 20), ("philox", 20)):
@@ -227,7 +232,6 @@ def test_device_side_tts_loop_matches_host_loop(models):
         for dev_loop in (False, True):
             torch.manual_seed(11)
             m.seed = 888
-            m.reset_frame_counter() if hasattr(m, "reset_frame_counter") else None
             r, s = gen.generate_tts(prompt, "TTS", text_token=text, temperature=0.9, topk=topk, fixed_schedule=(5, 9), device_loop=dev_loop,
                                     sync_every=4)
             outs.append((r.cpu(), s.cpu(), gen.n_frames))
@@ -236,6 +240,27 @@ def test_device_side_tts_loop_matches_host_loop(models):
         assert outs[0][2] == outs[1][2] == 14
         assert outs[1][0].shape == outs[0][0].shape == (8, 3) and outs[1][1].shape == outs[0][1].shape == (8, 8)
     m.rng_mode = "torch"
+
+
+def test_out_of_range_token_id_is_reported():
+    """nn.Embedding raises IndexError for an id outside its table; the kernel reads row 0 instead of foreign memory and the NEXT call
+    of the handle raises ValueError (the flag travels through mapped host memory, no synchronisation on the hot path)."""
+    cfg = tiny_cfgs()["tiny"]
+    sd = O.random_state_dict(cfg, seed=5)
+    m = build_product_model(cfg, sd, "cuda", 1)
+    tok = torch.zeros(1, 1, 9, dtype=torch.long, device="cuda")
+    msk = torch.ones(1, 1, 9, dtype=torch.bool, device="cuda")
+    tok[0, 0, 2] = cfg.audio_vocab  # one past the last audio id
+    m.generate_frame(tok, msk, torch.tensor([0]), 1, temperature=1.0, topk=1)
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="out of range"):
+        m.reset_caches()
+    m.reset_caches()  # reported once, then cleared
+    tok[0, 0, 2], tok[0, 0, 8] = 0, cfg.backbone.padded_vocab_size + 5
+    m.generate_frame(tok, msk, torch.tensor([0]), 1, temperature=1.0, topk=1)
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="out of range"):
+        m.generate_frame(tok, msk, torch.tensor([1]), 2, temperature=1.0, topk=1)
 
 
 def test_device_side_tts_state_machine_follows_the_reference_rules(models):

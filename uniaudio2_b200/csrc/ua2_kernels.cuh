@@ -190,7 +190,7 @@ struct FrameScalars {  // per-call scalars living in device memory so captured g
 
 // embedding merge of model_new.py:598-604: audio_in[m] = sum_c mask[m,c] * E[tok[m,c] + c*V]; text_emb[m] = wte[tok[m,nq]]
 cudaError_t launch_embed(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, const float* audio_emb,
-                         const float* wte, float* audio_in, float* text_emb, int M, int nq, int V, int D);
+                         const float* wte, float* audio_in, float* text_emb, int M, int nq, int V, int D, int text_vocab, int* err_flag);
 // out[m] = RMSNorm(x[m]; w) * ma[m] + add[m] * mt[m]; optional normed copy kept in `keep`
 //   ma = mask[m*(nq+1)+0], mt = mask[m*(nq+1)+nq] (audio-step / text-step masks, model_new.py:594-595)
 cudaError_t launch_norm_mix(const LaunchCtx& lc, const float* x, const float* w, float eps, const uint8_t* mask,

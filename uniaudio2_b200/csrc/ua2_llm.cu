@@ -49,6 +49,8 @@ struct ua2_llm {
   uint8_t* d_mask = nullptr;
   int32_t *d_pos = nullptr, *d_bidx = nullptr, *d_pos_local = nullptr;
   FrameScalars* d_fs = nullptr;
+  int* err_flag = nullptr;      // pinned, device-mapped: set by embed_kernel when a token id is outside its embedding table
+  int* err_flag_dev = nullptr;  // the device alias of the same word
   float *x = nullptr, *audio_in = nullptr, *text_emb = nullptr, *hb = nullptr, *h_final = nullptr, *qbuf = nullptr,
         *hmlp = nullptr, *sg_ws = nullptr, *o_part = nullptr, *ml_part = nullptr, *dec_x = nullptr, *text_logits = nullptr,
         *audio_logits = nullptr;
@@ -230,7 +232,7 @@ cudaError_t run_global(ua2_llm* h, const LaunchCtx& lc, int M, int n_splits, boo
   const int D = h->cfg.backbone.n_embd, nq = h->cfg.num_codebooks;
   cudaError_t e;
   if ((e = launch_embed(lc, h->d_tokens, h->d_mask, h->audio_emb, h->wte, h->audio_in, h->text_emb, M, nq,
-                        h->cfg.audio_vocab, D)) != cudaSuccess)
+                        h->cfg.audio_vocab, D, h->cfg.text_vocab, h->err_flag_dev)) != cudaSuccess)
     return e;
   Stack& und = h->st[2];
   for (int l = 0; l < und.cfg.n_layer; ++l)
@@ -380,6 +382,7 @@ int ua2_llm_destroy(ua2_llm* h) {
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->owned) cudaFree(p);
+  if (h->err_flag) cudaFreeHost(h->err_flag);
   delete h;
   return UA2_OK;
 }
@@ -522,6 +525,11 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   if ((rc = alloc(h, (void**)&h->d_bidx, (size_t)Mc * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->d_pos_local, (size_t)nq * B * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->d_fs, sizeof(FrameScalars)))) return rc;
+  if (h->err_flag == nullptr) {
+    UA2_CHECK_CUDA(cudaHostAlloc((void**)&h->err_flag, sizeof(int), cudaHostAllocMapped));
+    *h->err_flag = 0;
+    UA2_CHECK_CUDA(cudaHostGetDevicePointer((void**)&h->err_flag_dev, h->err_flag, 0));
+  }
   if ((rc = alloc(h, (void**)&h->x, (size_t)Mc * D * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->audio_in, (size_t)Mc * D * 4))) return rc;
   if ((rc = alloc(h, (void**)&h->text_emb, (size_t)Mc * D * 4))) return rc;
@@ -572,8 +580,19 @@ int ua2_llm_setup_caches(ua2_llm* h, int max_batch_size, void* stream_v) {
   return UA2_OK;
 }
 
+// nn.Embedding's IndexError analogue: an earlier call gathered with an id outside [0, vocab); reported by the next call (the flag is
+// written by the device into mapped host memory - no synchronisation on the hot path) and cleared
+#define UA2_CHECK_IDS(h)                                                                                                   \
+  do {                                                                                                                     \
+    if ((h)->err_flag && *(volatile int*)(h)->err_flag) {                                                                  \
+      *(volatile int*)(h)->err_flag = 0;                                                                                   \
+      UA2_REQUIRE(false, "index out of range in self: a token id of an earlier call lies outside its embedding table");   \
+    }                                                                                                                      \
+  } while (0)
+
 int ua2_llm_reset_caches(ua2_llm* h, void* stream_v) {
   UA2_REQUIRE(h, "null handle");
+  UA2_CHECK_IDS(h);
   if (!h->ready) {
     set_error("You need to call setup_caches() first");  // lit_model.py:134-135 TypeError analogue
     return UA2_ERR_STATE;
@@ -596,6 +615,7 @@ int ua2_llm_prefill(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, cons
     set_error("You need to call setup_caches() first");
     return UA2_ERR_STATE;
   }
+  UA2_CHECK_IDS(h);
   UA2_REQUIRE(B >= 1 && B <= h->B_max, "batch size exceeds setup_caches(max_batch_size)");
   UA2_REQUIRE(T >= 1 && T <= h->cfg.max_seq_length,
               "Cannot forward sequence of length T, max seq length is only max_seq_length");  // lit_model.py:120-121
@@ -706,6 +726,7 @@ int ua2_llm_generate_frame(ua2_llm* h, const int64_t* tokens, const uint8_t* mas
     set_error("You need to call setup_caches() first");
     return UA2_ERR_STATE;
   }
+  UA2_CHECK_IDS(h);
   UA2_REQUIRE(B >= 1 && B <= h->B_max, "batch size exceeds setup_caches(max_batch_size)");
   UA2_REQUIRE(input_pos >= 0 && input_pos < h->cfg.max_seq_length, "Positions in 'input_pos' must be in [0,max_seq_length)");
   // model_new.py:165-180

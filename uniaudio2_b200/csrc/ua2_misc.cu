@@ -11,7 +11,8 @@ namespace {
 // the same order is kept here so the fp32 sum is reproduced exactly.
 __global__ void embed_kernel(const int64_t* __restrict__ tokens, const uint8_t* __restrict__ mask,
                              const float* __restrict__ audio_emb, const float* __restrict__ wte,
-                             float* __restrict__ audio_in, float* __restrict__ text_emb, int nq, int V, int D) {
+                             float* __restrict__ audio_in, float* __restrict__ text_emb, int nq, int V, int D, int text_vocab,
+                             int* __restrict__ err_flag) {
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.y;
@@ -20,8 +21,16 @@ __global__ void embed_kernel(const int64_t* __restrict__ tokens, const uint8_t* 
   const int64_t* tk = tokens + (size_t)m * (nq + 1);
   const uint8_t* mk = mask + (size_t)m * (nq + 1);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // nn.Embedding raises an index error for ids outside the table (also on masked streams: the reference gathers before it masks);
+  // here such an id reads row 0 instead of foreign memory and raises the handle's error flag, which the next C-ABI call reports
+  bool bad = false;
   for (int c = 0; c < nq; ++c) {
-    const float4 e = *reinterpret_cast<const float4*>(audio_emb + ((size_t)tk[c] + (size_t)c * V) * D + k);
+    long long id = tk[c];
+    if (id < 0 || id >= V) {
+      bad = true;
+      id = 0;
+    }
+    const float4 e = *reinterpret_cast<const float4*>(audio_emb + ((size_t)id + (size_t)c * V) * D + k);
     const float w = mk[c] ? 1.f : 0.f;
     acc.x += e.x * w;
     acc.y += e.y * w;
@@ -29,8 +38,13 @@ __global__ void embed_kernel(const int64_t* __restrict__ tokens, const uint8_t* 
     acc.w += e.w * w;
   }
   *reinterpret_cast<float4*>(audio_in + (size_t)m * D + k) = acc;
-  *reinterpret_cast<float4*>(text_emb + (size_t)m * D + k) =
-      *reinterpret_cast<const float4*>(wte + (size_t)tk[nq] * D + k);
+  long long tid_text = tk[nq];
+  if (tid_text < 0 || tid_text >= text_vocab) {
+    bad = true;
+    tid_text = 0;
+  }
+  *reinterpret_cast<float4*>(text_emb + (size_t)m * D + k) = *reinterpret_cast<const float4*>(wte + (size_t)tid_text * D + k);
+  if (bad && k == 0 && err_flag != nullptr) *err_flag = 1;
 }
 
 // ln_f of one stack fused with the mask-mix feeding the next one (model_new.py:607, :610, :613):
@@ -203,11 +217,11 @@ static void misc_attrs_once() {
 }
 
 cudaError_t launch_embed(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, const float* audio_emb,
-                         const float* wte, float* audio_in, float* text_emb, int M, int nq, int V, int D) {
+                         const float* wte, float* audio_in, float* text_emb, int M, int nq, int V, int D, int text_vocab, int* err_flag) {
   misc_attrs_once();
   const int threads = 128;
   const dim3 grid((D / 4 + threads - 1) / threads, M);
-  return launch(lc, embed_kernel, grid, dim3(threads), 0, tokens, mask, audio_emb, wte, audio_in, text_emb, nq, V, D);
+  return launch(lc, embed_kernel, grid, dim3(threads), 0, tokens, mask, audio_emb, wte, audio_in, text_emb, nq, V, D, text_vocab, err_flag);
 }
 
 cudaError_t launch_norm_mix(const LaunchCtx& lc, const float* x, const float* w, float eps, const uint8_t* mask,
