@@ -142,12 +142,15 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        _lib = l
         # UA2_OPTIONS="attn_ring=1,conv_tc=1": global options applied at load, for A/B runs of whole programs (bench.py, the test
-        # suite) without editing them; an unknown name or a refused value raises
+        # suite) without editing them; an unknown name or a refused value raises - and leaves the module unloaded, so that a caller
+        # that swallows the exception cannot go on with half of the options applied
         for item in filter(None, (x.strip() for x in os.environ.get("UA2_OPTIONS", "").split(","))):
             name, _, value = item.partition("=")
-            check(l.ua2_set_global_option(name.strip().encode(), int(value)), f"UA2_OPTIONS {item}")
+            rc = l.ua2_set_global_option(name.strip().encode(), int(value))
+            if rc != 0:
+                raise ValueError(f"UA2_OPTIONS {item}: " + l.ua2_last_error().decode("utf-8", "replace"))
+        _lib = l
     return _lib
 
 

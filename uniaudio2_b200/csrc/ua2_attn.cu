@@ -554,13 +554,12 @@ __global__ void attn_combine_kernel(const AttnParams p, float* y) {  // grid (M,
 template <int HS>
 cudaError_t launch_attn_hs(const LaunchCtx& lc, const AttnParams& p) {
   const size_t smem = (size_t)2 * ATTN_CHUNK * HS * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(attn_split_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = prefer_max_smem(attn_split_kernel<HS>);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const dim3 grid(p.n_splits_launch, p.n_groups, p.M), block(128);
   return launch(lc, attn_split_kernel<HS>, grid, block, smem, p);
@@ -569,16 +568,15 @@ cudaError_t launch_attn_hs(const LaunchCtx& lc, const AttnParams& p) {
 template <int HS>
 cudaError_t launch_attn_ring_hs(const LaunchCtx& lc, const AttnParams& p, int n_items) {
   const size_t smem = (size_t)RING_SLOTS * ATTN_CHUNK * HS * sizeof(float);
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   static int n_sm = 148;
-  if (!attr_set) {
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(attn_ring_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = prefer_max_smem(attn_ring_kernel<HS>);
     if (e != cudaSuccess) return e;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
   }
   const int per_sm = HS == 128 ? 2 : 4;  // 105 KB / 57 KB / 31 KB of shared memory per CTA
   const int grid = std::min(n_items, n_sm * per_sm);
@@ -587,10 +585,9 @@ cudaError_t launch_attn_ring_hs(const LaunchCtx& lc, const AttnParams& p, int n_
 
 template <int HS, int RPW>
 cudaError_t launch_attn_rows_hs(const LaunchCtx& lc, const AttnParams& p) {
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     prefer_max_smem(attn_rows_kernel<HS, RPW>);
-    once = true;
   }
   return launch(lc, attn_rows_kernel<HS, RPW>, dim3((p.M + 8 * RPW - 1) / (8 * RPW), p.n_head), dim3(256), 0, p);
 }
@@ -638,10 +635,9 @@ cudaError_t launch_attn(const LaunchCtx& lc, const AttnParams& p) {
 }
 
 cudaError_t launch_attn_combine(const LaunchCtx& lc, const AttnParams& p, float* y) {
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     prefer_max_smem(attn_combine_kernel);
-    once = true;
   }
   return launch(lc, attn_combine_kernel, dim3(p.M, p.n_head), dim3(std::min(128, p.hs)), 0, p, y);
 }

@@ -511,10 +511,9 @@ int ua2_conv1d_causal_f32(const float* x, const float* w_ckc, const float* bias,
   const int plen = (span + stride - 1) / stride + 1;
   const size_t smem = ((size_t)CI_T * stride * plen + (size_t)CI_T * K * CO_T) * sizeof(float);
   UA2_REQUIRE(smem <= 200 * 1024, "conv tile does not fit shared memory");
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     UA2_CHECK_CUDA(cudaFuncSetAttribute(conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    once = true;
   }
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
@@ -562,10 +561,9 @@ int ua2_convtr1d_causal_f32(const float* x, const float* w_ckc, const float* bia
   const int K = 2 * stride;
   ConvTrParams p{x, w_ckc, bias, y, B, Cin, Cout, T_in, K, stride, pre_elu};
   const size_t smem = ((size_t)CI_T * (J_T + 1) + (size_t)CI_T * K * CO_T) * sizeof(float);
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     UA2_CHECK_CUDA(cudaFuncSetAttribute(convtr1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    once = true;
   }
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
@@ -680,10 +678,9 @@ int ua2_rvq_encode_f32(const float* x, const float* emb, const float* emb_sqnorm
   RvqEncParams p{x, emb, emb_sqnorm, codes, B, D, T, K, n_q, n_q_total, q_off};
   const size_t smem = (size_t)(FT + CT) * (D + 4) * sizeof(float);
   UA2_REQUIRE(smem <= 200 * 1024, "codebook dimension too large for the shared-memory tile");
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     UA2_CHECK_CUDA(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    once = true;
   }
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
@@ -725,10 +722,9 @@ int ua2_rvq_decode_f32(const int64_t* codes, const float* emb, float* out, int B
   UA2_REQUIRE(B >= 1 && T >= 1 && K >= 1 && n_q >= 1 && D >= 1, "bad shape");
   UA2_REQUIRE(q_off >= 0 && q_off + n_q <= n_q_total, "quantizer range outside the codes tensor");
   const size_t smem = (size_t)32 * (D + 1) * sizeof(float);
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     UA2_CHECK_CUDA(cudaFuncSetAttribute(rvq_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    once = true;
   }
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;

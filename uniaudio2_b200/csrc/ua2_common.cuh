@@ -102,6 +102,19 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, u
 __device__ __forceinline__ void smem_bar_wait(uint64_t* bar, uint32_t parity) { shim::mbar_wait(bar, parity); }
 #endif
 
+// Function attributes (dynamic shared-memory opt-in, carveout preference) are PER DEVICE: a once-flag must be too, or a process that
+// runs handles on a second GPU never issues the opt-in there and its first large-shared-memory launch fails with invalid-argument.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool need() {  // true the first time it is asked on the current device
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Per-launch context shared by the host-side launchers.
 struct GemvSeq;
 struct LaunchCtx {

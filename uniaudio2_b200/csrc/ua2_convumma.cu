@@ -404,11 +404,10 @@ cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, ConvUmmaParam
   }
   p.n_stages = stages;
   const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + (2 * CU_MAX_STAGES + 2 * CU_A_SLOTS + 4) * 8 + 16;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -326,13 +326,12 @@ cudaError_t launch_one(const LaunchCtx& lc, const GemvParams& p) {
   const int m_tiles = (p.M + MT - 1) / MT;
   const size_t kMaxSmem = 220 * 1024;
   auto kern = gemv2_kernel<MT, PRO, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) return e;
     e = prefer_max_smem(kern);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const size_t smem = xbytes + (size_t)V2_WARPS * STAGES * 2 * KC * sizeof(float);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;

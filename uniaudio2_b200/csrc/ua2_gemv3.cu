@@ -347,13 +347,12 @@ int mt_of(int M, int K) {
 template <int MT, int PRO, int EPI>
 cudaError_t launch3_one(const LaunchCtx& lc, const GemvParams& p, int n_splits) {
   auto kern = gemv3_kernel<MT, PRO, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     e = prefer_max_smem(kern);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const V3Plan pl = plan_v3(MT, EPI, p.M, p.N, p.K, n_splits);
   if (!pl.ok) return cudaErrorInvalidValue;

@@ -32,6 +32,8 @@ struct PfSpec {
 constexpr int PF_MAX = 3;
 
 // scratch of the tensor-core path for many-row linears (ua2_tcgemm.cu / ua2_umma.cu): split activations, stream-K side slots, raw product
+void bump_option_epoch();          // process-wide options changed (ua2_set_global_option)
+unsigned long long option_epoch();
 void set_tc_min_rows(int v);
 int get_tc_min_rows();
 size_t tc_slots_max_floats();  // largest side-slot scratch a launch may need: 148 CTAs x 256 x 128 floats

@@ -65,6 +65,7 @@ struct ua2_llm {
   int opt_graph = 1, opt_pdl = 1;  // a persistent one-kernel "chain" form measured 18 % slower than graph + PDL (profiles/r1_chain_experiment.md) and was removed
   int last_launches = 0;
   unsigned long long frame_counter = 0;
+  unsigned long long opt_epoch = 0;  // option_epoch() the captured graphs / recorded sequences were made under
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
@@ -658,6 +659,13 @@ int ua2_llm_prefill(ua2_llm* h, const int64_t* tokens, const uint8_t* mask, cons
 // captured on the second, replayed as a CUDA graph from then on.  lc.launch_counter must be set.
 static int run_frame_body(ua2_llm* h, LaunchCtx lc, int B, int rows, int64_t input_pos, bool use_cfg) {
   cudaStream_t stream = lc.stream;
+  if (h->opt_epoch != option_epoch()) {  // a process-wide option changed: the captured frames were built from the old choice
+    for (auto& kv : h->graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+    h->seqs.clear();
+    h->opt_epoch = option_epoch();
+  }
   const int n_splits = (int)(input_pos / ATTN_CHUNK) + 1;
   lc.pdl = h->opt_pdl != 0;
   const unsigned long long key = ((unsigned long long)B << 32) | ((unsigned long long)n_splits << 8) |

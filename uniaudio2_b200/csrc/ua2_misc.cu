@@ -207,13 +207,12 @@ __global__ void transpose_head_kernel(const float* __restrict__ src, float* __re
 }  // namespace
 
 static void misc_attrs_once() {
-  static bool done = false;
-  if (done) return;
+  static DeviceOnce once;
+  if (!once.need()) return;
   prefer_max_smem(embed_kernel);
   prefer_max_smem(norm_mix_kernel);
   prefer_max_smem(frame_begin_kernel);
   prefer_max_smem(prefill_begin_kernel);
-  done = true;
 }
 
 cudaError_t launch_embed(const LaunchCtx& lc, const int64_t* tokens, const uint8_t* mask, const float* audio_emb,

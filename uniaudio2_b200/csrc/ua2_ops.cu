@@ -19,6 +19,7 @@ extern "C" {
 
 int ua2_set_global_option(const char* name, int value) {
   UA2_REQUIRE(name, "null name");
+  bump_option_epoch();  // handles drop their captured frame graphs: a replay would still run the kernels chosen under the old options
   if (std::string(name) == "gemv3_balance_grid") {
     set_gemv3_balance_grid(value);
     return UA2_OK;

@@ -133,11 +133,10 @@ cudaError_t launch_resblock_fused(const LaunchCtx& lc, const float* x, const flo
                                   float* y, int B, int C, int H, int T) {
   if (C != RB_C || H != RB_H || b1 == nullptr || b2 == nullptr || x == y || B > 65535) return cudaErrorNotSupported;
   const size_t smem = (size_t)(RB_C * RB_XS + RB_C * 3 * RB_H + RB_H * RB_C + RB_H * RB_T) * sizeof(float);
-  static bool once = false;
-  if (!once) {
+  static DeviceOnce once;
+  if (once.need()) {
     cudaError_t e = cudaFuncSetAttribute(resblock64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    once = true;
   }
   return launch(lc, resblock64_kernel, dim3((T + RB_T - 1) / RB_T, B), dim3(256), smem, x, w1, b1, w2, b2, y, T);
 }

@@ -512,15 +512,14 @@ cudaError_t launch_sampler(const LaunchCtx& lc, const float* logits, int V, cons
   while (csize < MAX_CLUSTER && (V + csize - 1) / csize > SLICE_CAP) csize <<= 1;
   const int per = (V + csize - 1) / csize;
   const size_t smem = (size_t)(per < SLICE_CAP ? per : SLICE_CAP) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_CAP * 4);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_CAP * 4);
     if (e != cudaSuccess) return e;
     prefer_max_smem(sample_kernel<true>);
     prefer_max_smem(sample_kernel<false>);
-    attr_set = true;
   }
   if (lc.launch_counter) ++*lc.launch_counter;
   cudaLaunchConfig_t cfg{};

@@ -151,6 +151,9 @@ int g_tc_min_rows = 32;  // measured at 32 rows: 61 ms per frame on the skinny k
 
 }  // namespace
 
+static unsigned long long g_option_epoch = 0;
+void bump_option_epoch() { ++g_option_epoch; }
+unsigned long long option_epoch() { return g_option_epoch; }
 void set_tc_min_rows(int v) { g_tc_min_rows = v < 1 ? 1 : v; }
 int get_tc_min_rows() { return g_tc_min_rows; }
 size_t tc_slots_max_floats() { return (size_t)148 * 256 * 128; }
