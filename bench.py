@@ -367,7 +367,73 @@ def make_codec(dev):
     return m
 
 
-def bench_codec(dev, batch=16, clip_s=10.0, reps=3, cpu=True):
+def codec_conv_roofline(dev, batch=16, clip_s=10.0, reps=5):
+    """Roofline of the dominant SEANet kernel of an encode + decode at this size: the strided down-sampling convolution 64 -> 128
+    (k 8, s 4) at the 24 kHz rate, conv_umma_kernel<128> (csrc/ua2_convumma.cu: implicit GEMM on tcgen05 straight from (B, C, T)).
+    HBM-bound by its arithmetic (algorithmic bytes = input + output activations, 4 B each; 85 FLOP/B against a 3xTF32 ridge of ~35)."""
+    from uniaudio2_b200 import _lib
+
+    L, P = _lib.lib(), _lib.ptr
+    T = int(clip_s * 24000)
+    x = torch.randn(batch, 64, T, device=dev)
+    w = torch.randn(128, 64, 8, device=dev) / (64 * 8) ** 0.5
+    b = torch.zeros(128, device=dev)
+    y = torch.empty(batch, 128, T // 4, device=dev)
+    st = _lib.current_stream()
+
+    def run():
+        _lib.check(L.ua2_conv1d_causal_gemm_f32(P(x), P(w), P(b), None, P(y), batch, 64, 128, T, 8, 4, 1, 1, 0, st))
+
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    by = 4.0 * (x.numel() + y.numel())
+    peak, src = load_peaks()
+    return {"bound": "hbm", "kernel": "conv_umma_kernel<128> + weight repack (encoder down-sampling conv 64 -> 128, k 8 s 4, 24 kHz)",
+            "achieved": round(by / ms / 1e6, 1), "peak": peak, "unit": "GB/s", "frac": round(by / ms / 1e6 / peak, 4), "traffic": None,
+            "launch_ms": round(ms, 3), "bytes_per_launch": by, "peak_source": src,
+            "note": "activations (983 MB in + 492 MB out) exceed L2; the kernel is bound by its A-producer warps, not by HBM yet (profiles/r2_kernel_rooflines.md)"}
+
+
+def codec_sweep(dev, rank, world, clips=(1.0, 5.0, 30.0), batches=(1, 4, 16, 64, 256), budget_samples=16 * 240000):
+    """BASELINE.json config 5: encode + decode RTF over clip length x batch.  The `batch` clips of a point are dealt to the ranks (clip i
+    -> rank i mod W, strong scaling); a rank runs its share in sub-batches of at most `budget_samples` samples.  Returns this rank's
+    milliseconds per point (the caller takes the max over ranks)."""
+    m = make_codec(dev)
+    out = []
+    for clip_s in clips:
+        T = int(clip_s * 24000)
+        for batch in batches:
+            mine = len(range(rank, batch, world))
+            sub = max(1, min(mine, budget_samples // T)) if mine else 0
+            wav = torch.randn(max(sub, 1), 1, T, device=dev) * 0.1
+            ms = 0.0
+            if mine:
+                m.decode(m.encode(wav[:sub]))  # warm-up of this shape
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                done = 0
+                while done < mine:
+                    n = min(sub, mine - done)
+                    m.decode(m.encode(wav[:n]))
+                    done += n
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+            out.append((clip_s, batch, ms))
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_codec(dev, batch=16, clip_s=10.0, reps=3, cpu=True, roofline=True):
     """Codec real-time factor (BASELINE.json 'codec RTF'): SEANet + 8-layer transformer + 32 x 2048 x 256 residual VQ
     (mimi_config.yaml geometry, the in-repo twin of llm_modules/{seanet,conv,resample,transformer}.py), encode + decode of
     `batch` synthetic clips of `clip_s` seconds at 24 kHz, fp32, random weights.  RTF = audio seconds / wall seconds."""
@@ -405,6 +471,8 @@ def bench_codec(dev, batch=16, clip_s=10.0, reps=3, cpu=True):
            "rtf_x_realtime": round(audio_s / ((enc_ms + dec_ms) * 1e-3), 1), "encode_x_realtime": round(audio_s / (enc_ms * 1e-3), 1),
            "decode_x_realtime": round(audio_s / (dec_ms * 1e-3), 1), "e2e_x_realtime": round(audio_s / e2e_s, 1),
            "codes_shape": list(codes.shape), "gflop_per_audio_s": 11.0}
+    if roofline:
+        res["roofline"] = codec_conv_roofline(dev, batch, clip_s)
     if cpu:
         from oracle import codec_oracle as CO  # the CPU-baseline leg: the oracle port runs the same weights on the host cores
 
@@ -514,6 +582,7 @@ def main():
     ap.add_argument("--parity-frames", type=int, default=8, help="greedy frames compared id-for-id with the CPU oracle at full size (N = 1)")
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--no-flow-decoder", action="store_true")
+    ap.add_argument("--codec-sweep", action="store_true", help="BASELINE.json config 5: codec RTF over 1/5/30 s clips x batch 1..256, clips dealt to the ranks")
     ap.add_argument("--v3-cps", type=int, default=0)
     ap.add_argument("--v3-stages", type=int, default=0)
     ap.add_argument("--v3-kcw", type=int, default=0)
@@ -702,12 +771,34 @@ def main():
                     flow = bench_flow_decoder(dev, cpu=not args.no_cpu_baseline)
                 except Exception as e:  # noqa: BLE001
                     flow = {"error": f"{type(e).__name__}: {e}"}
+    # ---- codec at N > 1: every rank encodes + decodes its own batch of 16 x 10 s clips (replicas, weak scaling), time = max over ranks;
+    #      --codec-sweep: the clip length x batch grid of BASELINE.json config 5 with the clips of a point dealt to the ranks
+    if world > 1 and not args.no_codec:
+        with torch.inference_mode():
+            try:
+                c = bench_codec(dev, cpu=False, roofline=False)
+                t = torch.tensor([c["encode_ms"] + c["decode_ms"]], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    codec = {"config": c["config"] + f" per GPU x {world} GPUs (replicas)", "ms_max_over_ranks": round(float(t.item()), 2),
+                             "rtf_x_realtime": round(world * 160.0 / (float(t.item()) * 1e-3), 1)}
+            except Exception as e:  # noqa: BLE001
+                codec = {"error": f"{type(e).__name__}: {e}"}
+    sweep = None
+    if args.codec_sweep:
+        with torch.inference_mode():
+            pts = codec_sweep(dev, rank, world)
+            t = torch.tensor([p[2] for p in pts], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sweep = [{"clip_s": c, "batch": b, "ms": round(float(ms), 2), "x_realtime": round(c * b / (float(ms) * 1e-3), 1) if float(ms) > 0 else None}
+                     for (c, b, _), ms in zip(pts, t.tolist())]
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
                           "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
-                          "codec": codec, "flow_decoder": flow}))
+                          "codec": codec, "codec_sweep": sweep, "flow_decoder": flow}))
     if world > 1:
         dist.destroy_process_group()
 
