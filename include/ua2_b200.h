@@ -163,6 +163,11 @@ int ua2_linear_f32(const float* x, const float* W, const float* norm_w, float ep
  * (model_new.py:456-507) and batched frames use for M >= tc_min_rows.  Scratch is owned by the library. */
 int ua2_tc_linear_f32(const float* x, const float* W, const float* W2, const float* norm_w, float eps, const float* residual, float* y,
                       int M, int N, int K, void* stream);
+/* Unmasked softmax(q k^T / sqrt(hs)) v on tensor cores, bf16 operands, fp32 scores / statistics / output: the attention of the
+ * flow-matching decoder's blocks (ReasoningCodec_film/models/attention.py:308-357 -> diffusers Attention -> SDPA, which the reference
+ * runs in bf16 under reason_tokenizer.py:265's autocast).  q16, k16, v16: (B, H, T, 64) bf16; out: (B, T, H * 64) fp32.
+ * csrc/ua2_flash.cu: tcgen05 kind::f16 for both contractions, P from tensor memory.  UA2_ERR_INVALID unless hs == 64. */
+int ua2_flash_attn_bf16(const void* q16, const void* k16, const void* v16, float* out, int B, int T, int H, int hs, void* stream);
 /* One application of the TTS loop's break / phase-switch rules (evaluation/tts_task.py:259-271) to a sampled row (1+nq int32, device):
  * the state machine that ua2_llm_tts_frames runs after every frame. */
 int ua2_tts_state_step(const int32_t* sample, int nq, int32_t* state, int32_t* frames_out, int frames_cap, int reason_eos, int end_tok,

@@ -70,6 +70,7 @@ inline __nv_bfloat16 shim_f2bf16_rn(float f) {  // round to nearest even (finite
   return {(uint16_t)(u >> 16)};
 }
 inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return {shim_f2bf16_rn(a), shim_f2bf16_rn(b)}; }
+inline __nv_bfloat16 __float2bfloat16_rn(float a) { return shim_f2bf16_rn(a); }
 
 #define __global__
 #define __device__

@@ -29,6 +29,17 @@ cudaError_t launch_tc_linear(const LaunchCtx&, int pro, int epi, const GemvParam
   }
   return cudaSuccess;
 }
+// the tcgen05 convolution path does not exist on the shim: the option reads 0 and the launchers decline, so the codec model
+// takes the fp32 SIMT / conv_tc kernels that the shim can run
+int get_conv_umma() { return 0; }
+void set_conv_umma(int) {}
+cudaError_t launch_conv1d_umma(const LaunchCtx&, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int,
+                               int, int, int, int) {
+  return cudaErrorNotSupported;
+}
+cudaError_t launch_convtr1d_umma(const LaunchCtx&, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int) {
+  return cudaErrorNotSupported;
+}
 }  // namespace ua2
 
 extern "C" {

@@ -17,6 +17,14 @@ inline float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = std::fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+struct DeviceOnce {  // one device on the shim
+  bool done = false;
+  bool need() {
+    const bool n = !done;
+    done = true;
+    return n;
+  }
+};
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   bool pdl = false;

@@ -3,6 +3,7 @@ oracle/make_golden_encode.py produced by executing the UNMODIFIED source of Audi
 (AudioDiffusion1D.py:428-438, :492-551) on stand-in SSL features - codes bit-equal, features bit-equal."""
 import os
 
+import pytest
 import torch
 
 from oracle import encode_oracle as EO
@@ -10,10 +11,18 @@ from oracle import encode_oracle as EO
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(autouse=True)
+def _generator_thread_count():
+    """Bit-exact comparisons run with the thread count oracle/make_golden_encode.py used (ATen partitions sums by it); restored after."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(4)
+    yield
+    torch.set_num_threads(n)
+
+
 def test_encode_chain_matches_reference_golden():
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "encode_golden.pt"), weights_only=False)
     p = EO.random_params(gold["param_seed"])
-    torch.set_num_threads(4)
     for c in gold["cases"]:
         feats = EO.stand_in_features(c["feat_seed"], *c["shape"])
         with torch.no_grad():

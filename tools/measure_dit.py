@@ -75,8 +75,12 @@ def main():
         m.set_option("bf16", 1)
         ms = timed(lambda: m(x, timestep=t), a.reps)
         got = m(x, timestep=t).sample
+        m.set_option("flash_attn", 0)
+        ms_simt = timed(lambda: m(x, timestep=t), a.reps)
+        m.set_option("flash_attn", 1)
         m.set_option("bf16", 0)
-        print(json.dumps(dict(what="estimator call, bf16 option", launches=m.last_launch_count(), ms=round(ms, 3),
+        print(json.dumps(dict(what="estimator call, bf16 option with the fp32 SIMT attention", ms=round(ms_simt, 3))))
+        print(json.dumps(dict(what="estimator call, bf16 option (tensor-core attention)", launches=m.last_launch_count(), ms=round(ms, 3),
                               bf16_mma_TFLOPs=round(fl / ms / 1e9, 1), max_abs_diff_vs_3xtf32=float((got - ref).abs().max()),
                               out_scale=float(ref.abs().max()))))
     cfm = BASECFM(m)

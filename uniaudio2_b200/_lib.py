@@ -70,6 +70,7 @@ SYMBOLS = {
     "ua2_tts_state_step": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_linear_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_tc_linear_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_flash_attn_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_swiglu_f32": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_qkv_rope_f32": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, _P]),

@@ -80,7 +80,8 @@ enum : int {
   DE_BIAS_SILU = 4,   // y = silu(y + bias)                      TimestepEmbedding.act
   DE_BIAS_KEEP_SILU = 5,  // y = y + bias, y2 = silu(y)          embedded_timestep and the input of adaln_single.linear
   DE_GATE_RES = 6,    // res = gate_b * (y + bias) + res         attention.py:350-353, :409-412
-  DE_QKV_SPLIT = 7    // q (M, D) = y[:, :D] + b; k, v -> (B, H, T, hs)
+  DE_QKV_SPLIT = 7,   // q (M, D) = y[:, :D] + b; k, v -> (B, H, T, hs)
+  DE_QKV_SPLIT_BF16 = 8  // q, k, v -> (B, H, T, hs) bf16: operands of the tensor-core attention (ua2_flash.cu)
 };
 
 struct DitEpi {
@@ -95,6 +96,7 @@ struct DitEpi {
   const float* t6;    // GATE_RES: timestep modulation (B, 6N)
   int gate_idx;
   float *q, *k, *v;   // QKV_SPLIT destinations
+  __nv_bfloat16 *q16, *k16, *v16;  // QKV_SPLIT_BF16 destinations
   int H, hs;
 };
 
@@ -131,6 +133,12 @@ __global__ void dit_epilogue_kernel(const DitEpi e) {
       const int b = (int)(m / e.T);
       const float gate = __fadd_rn(e.table[(size_t)e.gate_idx * e.N + c], e.t6[((size_t)b * 6 + e.gate_idx) * e.N + c]);
       e.y2[i] = __fadd_rn(__fmul_rn(gate, v), e.y2[i]);
+    } else if (MODE == DE_QKV_SPLIT_BF16) {
+      const int D = e.N / 3;
+      const int part = c / D, cc = c - part * D;
+      const int hh = cc / e.hs, d = cc - hh * e.hs;
+      const int b = (int)(m / e.T), t = (int)(m % e.T);
+      (part == 0 ? e.q16 : part == 1 ? e.k16 : e.v16)[(((size_t)b * e.H + hh) * e.T + t) * e.hs + d] = __float2bfloat16_rn(v);
     } else {  // DE_QKV_SPLIT: N = 3*D, columns ordered [q | k | v], each (h d)
       const int D = e.N / 3;
       const int part = c / D, cc = c - part * D;
@@ -419,6 +427,7 @@ struct ua2_dit {
   TcWorkspace tc;
   // option "bf16": linears of >= 32 rows on bf16 operands with fp32 accumulation (the reference's autocast arithmetic)
   int opt_bf16 = 0;
+  int opt_flash = 1;  // with bf16: tensor-core attention (0 = keep the fp32 SIMT attention; measurement switch)
   __nv_bfloat16* a16 = nullptr;  // (M, kmax) activations converted per call
   std::map<const float*, __nv_bfloat16*> w16;  // weights converted once, keyed by the fp32 tensor
   int last_launches = 0;
@@ -591,20 +600,27 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
   // ---- proj_in + positional embedding
   RUN(project_layer(h, lc, x, h->in1_w, h->in1, h->in2, h->n, h->h, B, T, c.in_channels, D, h->pe));
   // ---- blocks
+  const bool flash = h->opt_bf16 && h->opt_flash && hs == 64 && tc_gemm_available();
   for (const DitBlock& bl : h->blocks) {
     CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 0, 1,
               c.norm_eps, T, D));
     RUN(linear_raw(h, lc, h->n, bl.wqkv, h->qkv, M, 3 * D, D, &src));
-    {
-      DitEpi e = epi(src, h->qkv, bl.bqkv, M, 3 * D, T);
+    DitEpi e = epi(src, h->qkv, bl.bqkv, M, 3 * D, T);
+    e.H = H;
+    e.hs = hs;
+    if (flash) {  // bf16 mode: both contractions of the attention on tcgen05 (the reference runs SDPA in bf16 under its autocast)
+      e.q16 = reinterpret_cast<__nv_bfloat16*>(h->q);
+      e.k16 = reinterpret_cast<__nv_bfloat16*>(h->k);
+      e.v16 = reinterpret_cast<__nv_bfloat16*>(h->v);
+      CU(launch_epi<DE_QKV_SPLIT_BF16>(lc, e));
+      CU(launch_flash_bf16(lc, e.q16, e.k16, e.v16, h->att, B, T, H, hs));
+    } else {
       e.q = h->q;
       e.k = h->k;
       e.v = h->v;
-      e.H = H;
-      e.hs = hs;
       CU(launch_epi<DE_QKV_SPLIT>(lc, e));
+      CU(launch_dit_attn(lc, h->q, h->k, h->v, h->att, B, T, H, hs));
     }
-    CU(launch_dit_attn(lc, h->q, h->k, h->v, h->att, B, T, H, hs));
     RUN(linear_raw(h, lc, h->att, bl.o.w, h->n, M, D, D, &src));
     {
       DitEpi e = epi(src, h->n, bl.o.b, M, D, T);
@@ -864,6 +880,10 @@ int ua2_dit_set_option(ua2_dit* h, const char* name, int value) {
   const std::string n(name);
   if (n == "bf16") {
     h->opt_bf16 = value ? 1 : 0;
+    return UA2_OK;
+  }
+  if (n == "flash_attn") {
+    h->opt_flash = value ? 1 : 0;
     return UA2_OK;
   }
   UA2_REQUIRE(false, "unknown option " + n);

@@ -19,6 +19,7 @@
 
 #include "ua2_kernels.cuh"
 #include "ua2_tcgen05.cuh"
+#include "ua2_umma.cuh"
 
 namespace ua2 {
 namespace {
@@ -189,7 +190,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (j > 0) {
         smem_bar_wait(o_done, (uint32_t)(j - 1) & 1);
         tc_fence_after();
-        if (alpha != 1.f) {
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // warp-uniform: tcgen05.ld / st are .sync.aligned
 #pragma unroll 1
           for (int c0 = 0; c0 < FA_HS; c0 += 32) {
             uint32_t ov[32];

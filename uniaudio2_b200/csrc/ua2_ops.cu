@@ -1,6 +1,7 @@
 // Stand-alone operator entry points of the C ABI (unit-parity surface).  Same kernels as the handle path.
 #include "../../include/ua2_b200.h"
 #include "ua2_kernels.cuh"
+#include "ua2_umma.cuh"
 
 using namespace ua2;
 
@@ -128,6 +129,16 @@ static int tc_op_ws(size_t a, size_t c) {
   UA2_CHECK_CUDA(grow(&g_tc_op_ws.a, &g_tc_op_ws.a_floats, a));
   UA2_CHECK_CUDA(grow(&g_tc_op_ws.c, &g_tc_op_ws.c_floats, c));
   UA2_CHECK_CUDA(grow(&g_tc_op_ws.slots, &g_tc_op_ws.slots_floats, tc_slots_max_floats()));
+  return UA2_OK;
+}
+
+int ua2_flash_attn_bf16(const void* q16, const void* k16, const void* v16, float* out, int B, int T, int H, int hs, void* stream) {
+  UA2_REQUIRE(q16 && k16 && v16 && out, "null argument");
+  UA2_REQUIRE(hs == 64, "head size must be 64");
+  UA2_REQUIRE(B >= 1 && T >= 1 && H >= 1, "empty problem");
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  UA2_CHECK_CUDA(launch_flash_bf16(lc, q16, k16, v16, out, B, T, H, hs));
   return UA2_OK;
 }
 

@@ -27,6 +27,8 @@ int umma_pick_nt(int M);
 UmmaPlan umma_plan(int M, int N, int n_mat, int K, bool bf16 = false);
 cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W, const float* W2, float* C, int ldc, float* slots, int M, int N,
                             int K, const UmmaPlan& pl);
+// Tensor-core attention (ua2_flash.cu): q16 / k16 / v16 (B, H, T, 64) bf16 -> out (B, T, H * 64) fp32, unmasked softmax(q k^T / 8) v
+cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, int B, int T, int H, int hs);
 cudaError_t run_umma_bf16(const LaunchCtx& lc, const void* X16, const void* W16, float* C, int ldc, float* slots, int M, int N, int K,
                           const UmmaPlan& pl);
 cudaError_t run_umma_fixup(const LaunchCtx& lc, float* C, int ldc, const float* slots, int M, int N, int n_mat, const UmmaPlan& pl);
