@@ -39,7 +39,7 @@ int shim_dit_attn(const float* q, const float* k, const float* v, float* out, in
 }
 int shim_dit_ln_mod(const float* x, float* out, const float* table, const float* t, int t_row, int t_stride, int shift_idx, int scale_idx,
                     float eps, int M, int T, int D) {
-  return shim::run_grid(ua2::dit_ln_mod_kernel, dim3(M), dim3(256), x, out, table, t, t_row, t_stride, shift_idx, scale_idx, eps, T, D);
+  return shim::run_grid(ua2::dit_ln_mod_kernel, dim3(M), dim3(256), x, out, (__nv_bfloat16*)nullptr, table, t, t_row, t_stride, shift_idx, scale_idx, eps, T, D);
 }
 int shim_dit_im2col3(const float* x, float* out, int B, int T, int C) {
   return shim::run_grid(ua2::dit_im2col3_kernel, dim3(ua2::grid_for((long long)B * T * 3 * C)), dim3(256), x, out, B, T, C);

@@ -31,8 +31,19 @@ def _ref(q, k, v):
 
 
 @pytest.mark.parametrize("B,H,T", [(1, 1, 128), (1, 2, 1), (2, 3, 100), (1, 2, 129), (2, 24, 500), (1, 4, 1000), (3, 2, 257), (1, 1, 2048)])
-@pytest.mark.parametrize("scale", [1.0, 4.0])
-def test_flash_attention_matches_fp64_softmax(B, H, T, scale):
+@pytest.mark.parametrize("scale,sbuf", [(1.0, 0), (4.0, 1), (4.0, 2)])
+def test_flash_attention_matches_fp64_softmax(B, H, T, scale, sbuf):
+    """sbuf: 0 = the launcher's choice, 1 = single score buffer / two CTAs per SM, 2 = double-buffered scores / one CTA per SM."""
+    from uniaudio2_b200 import _lib
+
+    _lib.check(_lib.lib().ua2_set_global_option(b"flash_sbuf", sbuf))
+    try:
+        _check_case(B, H, T, scale)
+    finally:
+        _lib.check(_lib.lib().ua2_set_global_option(b"flash_sbuf", 0))
+
+
+def _check_case(B, H, T, scale):
     g = torch.Generator().manual_seed(B * 1000 + H * 10 + T)
     q = (torch.randn(B, H, T, 64, generator=g) * scale).bfloat16().cuda()
     k = (torch.randn(B, H, T, 64, generator=g) * scale).bfloat16().cuda()

@@ -59,6 +59,8 @@ def main():
     x = torch.randn(2, T, 1040, device=dev)
     t = torch.full((2,), 0.35, device=dev)
     if a.once:
+        if a.bf16:
+            m.set_option("bf16", 1)
         m(x, timestep=t)
         m(x, timestep=t)
         torch.cuda.synchronize()

@@ -98,6 +98,14 @@ struct DitEpi {
   float *q, *k, *v;   // QKV_SPLIT destinations
   __nv_bfloat16 *q16, *k16, *v16;  // QKV_SPLIT_BF16 destinations
   int H, hs;
+  // fused bf16 block path (dit_epi4_kernel): the GEMM's stream-K side slots are summed here (no separate fix-up pass), and the
+  // result goes out as bf16 when the only consumer is the next tensor-core linear
+#ifndef UA2_CPU_SHIM
+  const float* slots;
+  UmmaPlan pl;
+  int has_split;
+  __nv_bfloat16* y16;
+#endif
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {  // F.gelu(approximate='tanh')
@@ -133,12 +141,6 @@ __global__ void dit_epilogue_kernel(const DitEpi e) {
       const int b = (int)(m / e.T);
       const float gate = __fadd_rn(e.table[(size_t)e.gate_idx * e.N + c], e.t6[((size_t)b * 6 + e.gate_idx) * e.N + c]);
       e.y2[i] = __fadd_rn(__fmul_rn(gate, v), e.y2[i]);
-    } else if (MODE == DE_QKV_SPLIT_BF16) {
-      const int D = e.N / 3;
-      const int part = c / D, cc = c - part * D;
-      const int hh = cc / e.hs, d = cc - hh * e.hs;
-      const int b = (int)(m / e.T), t = (int)(m % e.T);
-      (part == 0 ? e.q16 : part == 1 ? e.k16 : e.v16)[(((size_t)b * e.H + hh) * e.T + t) * e.hs + d] = __float2bfloat16_rn(v);
     } else {  // DE_QKV_SPLIT: N = 3*D, columns ordered [q | k | v], each (h d)
       const int D = e.N / 3;
       const int part = c / D, cc = c - part * D;
@@ -160,11 +162,141 @@ cudaError_t launch_epi(const LaunchCtx& lc, const DitEpi& e) {
   return launch(lc, dit_epilogue_kernel<MODE>, dim3(grid), dim3(256), 0, e);
 }
 
+#ifndef UA2_CPU_SHIM  // (tensor-core path only: not part of the CPU shim's build)
+// The block's epilogues on the fused bf16 path, 4 columns per thread, one row per blockIdx.x: raw product (+ the continuation CTAs'
+// side slots) + bias, then  DE_QKV_SPLIT_BF16: q / k / v (B, H, T, hs) bf16 | DE_BIAS_GELU: gelu_tanh -> y16 (M, N) bf16 |
+// DE_GATE_RES: y2 = gate_b * v + y2 (fp32 residual stream).
+template <int MODE>
+__global__ void __launch_bounds__(256) dit_epi4_kernel(const DitEpi e) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
+  const int c = (blockIdx.y * 256 + threadIdx.x) * 4;
+  if (c >= e.N) return;
+  float4 v = *reinterpret_cast<const float4*>(e.src + (size_t)m * e.N + c);
+  if (e.has_split) {
+    const float4 sd = umma_side_sum4(e.pl, e.slots, m, c, e.N);
+    v.x += sd.x;
+    v.y += sd.y;
+    v.z += sd.z;
+    v.w += sd.w;
+  }
+  const float4 bs = *reinterpret_cast<const float4*>(e.bias + c);
+  v.x = __fadd_rn(v.x, bs.x);
+  v.y = __fadd_rn(v.y, bs.y);
+  v.z = __fadd_rn(v.z, bs.z);
+  v.w = __fadd_rn(v.w, bs.w);
+  if (MODE == DE_BIAS_GELU) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(gelu_tanh(v.x), gelu_tanh(v.y)), b2 = __floats2bfloat162_rn(gelu_tanh(v.z), gelu_tanh(v.w));
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b2);
+    *reinterpret_cast<uint2*>(e.y16 + (size_t)m * e.N + c) = o;
+  } else if (MODE == DE_GATE_RES) {
+    const int b = m / e.T;
+    const float4 tb = *reinterpret_cast<const float4*>(e.table + (size_t)e.gate_idx * e.N + c);
+    const float4 t6 = *reinterpret_cast<const float4*>(e.t6 + ((size_t)b * 6 + e.gate_idx) * e.N + c);
+    float4* rp = reinterpret_cast<float4*>(e.y2 + (size_t)m * e.N + c);
+    float4 r = *rp;
+    r.x = __fadd_rn(__fmul_rn(__fadd_rn(tb.x, t6.x), v.x), r.x);
+    r.y = __fadd_rn(__fmul_rn(__fadd_rn(tb.y, t6.y), v.y), r.y);
+    r.z = __fadd_rn(__fmul_rn(__fadd_rn(tb.z, t6.z), v.z), r.z);
+    r.w = __fadd_rn(__fmul_rn(__fadd_rn(tb.w, t6.w), v.w), r.w);
+    *rp = r;
+  } else {  // DE_QKV_SPLIT_BF16: the 4 columns lie inside one head (hs % 4 == 0)
+    const int D = e.N / 3;
+    const int part = c / D, cc = c - part * D;
+    const int hh = cc / e.hs, d = cc - hh * e.hs;
+    const int b = m / e.T, t = m - b * e.T;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b2 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b2);
+    *reinterpret_cast<uint2*>((part == 0 ? e.q16 : part == 1 ? e.k16 : e.v16) + (((size_t)b * e.H + hh) * e.T + t) * e.hs + d) = o;
+  }
+}
+
+// DE_GATE_RES of one full row per CTA (thread = 4 columns, blockDim = N / 4 rounded up to a warp) followed by the NEXT LayerNorm +
+// modulation of that row (attention.py:399-401 after :350-353, or the next block's :312-317 after :409-412): the residual stream is
+// updated in fp32, and the normalised, modulated row goes out as bf16, the next linear's operand.  Saves the dit_ln_mod launch and
+// its re-read of the row.  ln_table: the (6, N) table whose rows shift_idx / scale_idx modulate the LayerNorm output.
+__global__ void __launch_bounds__(1024) dit_gate_res_ln_kernel(const DitEpi e, const float* __restrict__ ln_table, int shift_idx, int scale_idx,
+                                                               float eps) {
+  __shared__ float red[32];
+  __shared__ float stat[2];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int c = tid * 4;
+  const bool on = c < e.N;
+  const int b = m / e.T;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) {
+    float4 v = *reinterpret_cast<const float4*>(e.src + (size_t)m * e.N + c);
+    if (e.has_split) {
+      const float4 sd = umma_side_sum4(e.pl, e.slots, m, c, e.N);
+      v.x += sd.x;
+      v.y += sd.y;
+      v.z += sd.z;
+      v.w += sd.w;
+    }
+    const float4 bs = *reinterpret_cast<const float4*>(e.bias + c);
+    const float4 tb = *reinterpret_cast<const float4*>(e.table + (size_t)e.gate_idx * e.N + c);
+    const float4 t6 = *reinterpret_cast<const float4*>(e.t6 + ((size_t)b * 6 + e.gate_idx) * e.N + c);
+    float4* rp = reinterpret_cast<float4*>(e.y2 + (size_t)m * e.N + c);
+    r = *rp;
+    r.x = __fadd_rn(__fmul_rn(__fadd_rn(tb.x, t6.x), __fadd_rn(v.x, bs.x)), r.x);
+    r.y = __fadd_rn(__fmul_rn(__fadd_rn(tb.y, t6.y), __fadd_rn(v.y, bs.y)), r.y);
+    r.z = __fadd_rn(__fmul_rn(__fadd_rn(tb.z, t6.z), __fadd_rn(v.z, bs.z)), r.z);
+    r.w = __fadd_rn(__fmul_rn(__fadd_rn(tb.w, t6.w), __fadd_rn(v.w, bs.w)), r.w);
+    *rp = r;
+  }
+  float s = warp_sum(on ? (r.x + r.y) + (r.z + r.w) : 0.f);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = warp_sum(lane < nw ? red[lane] : 0.f);
+    if (lane == 0) stat[0] = t / (float)e.N;
+  }
+  __syncthreads();
+  const float mean = stat[0];
+  const float dx = r.x - mean, dy = r.y - mean, dz = r.z - mean, dw = r.w - mean;
+  float q = warp_sum(on ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  if (warp == 0) {
+    float t = warp_sum(lane < nw ? red[lane] : 0.f);
+    if (lane == 0) stat[1] = rsqrtf(t / (float)e.N + eps);
+  }
+  __syncthreads();
+  if (!on) return;
+  const float rstd = stat[1];
+  const float4 sc_t = *reinterpret_cast<const float4*>(ln_table + (size_t)scale_idx * e.N + c);
+  const float4 sc_b = *reinterpret_cast<const float4*>(e.t6 + ((size_t)b * 6 + scale_idx) * e.N + c);
+  const float4 sh_t = *reinterpret_cast<const float4*>(ln_table + (size_t)shift_idx * e.N + c);
+  const float4 sh_b = *reinterpret_cast<const float4*>(e.t6 + ((size_t)b * 6 + shift_idx) * e.N + c);
+  const float o0 = __fadd_rn(__fmul_rn(dx * rstd, __fadd_rn(1.f, __fadd_rn(sc_t.x, sc_b.x))), __fadd_rn(sh_t.x, sh_b.x));
+  const float o1 = __fadd_rn(__fmul_rn(dy * rstd, __fadd_rn(1.f, __fadd_rn(sc_t.y, sc_b.y))), __fadd_rn(sh_t.y, sh_b.y));
+  const float o2 = __fadd_rn(__fmul_rn(dz * rstd, __fadd_rn(1.f, __fadd_rn(sc_t.z, sc_b.z))), __fadd_rn(sh_t.z, sh_b.z));
+  const float o3 = __fadd_rn(__fmul_rn(dw * rstd, __fadd_rn(1.f, __fadd_rn(sc_t.w, sc_b.w))), __fadd_rn(sh_t.w, sh_b.w));
+  const __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), b2 = __floats2bfloat162_rn(o2, o3);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a);
+  o.y = *reinterpret_cast<const uint32_t*>(&b2);
+  *reinterpret_cast<uint2*>(e.y16 + (size_t)m * e.N + c) = o;
+}
+
+template <int MODE>
+cudaError_t launch_epi4(const LaunchCtx& lc, const DitEpi& e) {
+  return launch(lc, dit_epi4_kernel<MODE>, dim3(e.M, (e.N + 1023) / 1024), dim3(256), 0, e);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------ LayerNorm + modulation
 // out[m] = LN(x[m]; eps, no affine) * (1 + scale_b) + shift_b,  scale_b = table[scale_idx] + t[b, scale_idx * t_stride ...]
 // (attention.py:312-317 / :399-401 with t = the 6*D rows of adaln_single; transformer_1d_flow.py:378-381 with t = the
 // embedded timestep, t_stride = 0: both rows of the (2, D) table get the same D-vector added)
-__global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ x, float* __restrict__ out,
+__global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
                                                          const float* __restrict__ table, const float* __restrict__ t, int t_row,
                                                          int t_stride, int shift_idx, int scale_idx, float eps, int T, int D) {
   __shared__ float red[8];
@@ -206,7 +338,12 @@ __global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict
     const float scale = __fadd_rn(table[(size_t)scale_idx * D + c], tb[(size_t)scale_idx * t_stride + c]);
     const float shift = __fadd_rn(table[(size_t)shift_idx * D + c], tb[(size_t)shift_idx * t_stride + c]);
     const float nrm = (xr[c] - mean) * rstd;
-    out[(size_t)m * D + c] = __fadd_rn(__fmul_rn(nrm, __fadd_rn(1.f, scale)), shift);
+    const float o = __fadd_rn(__fmul_rn(nrm, __fadd_rn(1.f, scale)), shift);
+    if (out16 != nullptr) {  // fused bf16 path: the only consumer is the next tensor-core linear
+      out16[(size_t)m * D + c] = __float2bfloat16_rn(o);
+    } else {
+      out[(size_t)m * D + c] = o;
+    }
   }
 }
 
@@ -504,23 +641,50 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
   return UA2_OK;
 }
 
+// the bf16 copy of a weight, made at first use (2 B / parameter)
+int weight16(ua2_dit* h, const LaunchCtx& lc, const float* W, int N, int K, const __nv_bfloat16** out) {
+  auto it = h->w16.find(W);
+  if (it == h->w16.end()) {
+    __nv_bfloat16* wb = nullptr;
+    UA2_CHECK_CUDA(cudaMalloc((void**)&wb, (size_t)N * K * sizeof(__nv_bfloat16)));
+    it = h->w16.emplace(W, wb).first;
+    const long long n4 = (long long)N * K / 4;
+    CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, W, wb, n4));
+  }
+  *out = it->second;
+  return UA2_OK;
+}
+
+// fused bf16 path: a16 (M, K) bf16 @ W^T on the tcgen05 kind::f16 mainloop -> raw product in the handle's buffer; the epilogue
+// description comes back with the product, the side slots and the plan filled in (dit_epi4_kernel sums the slots itself)
+int linear16(ua2_dit* h, const LaunchCtx& lc, const float* W, const float* bias, int M, int N, int K, int T, DitEpi* e) {
+  const __nv_bfloat16* w16 = nullptr;
+  RUN(weight16(h, lc, W, N, K, &w16));
+  const UmmaPlan pl = umma_plan(M, N, 1, K, true);
+  UA2_REQUIRE(pl.slot_floats <= h->tc.slots_floats && (size_t)M * N <= h->tc.c_floats && (K % 8) == 0 && (N % 4) == 0, "flow decoder linear outside the tensor-core path's shapes");
+  CU(run_umma_bf16(lc, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl));
+  e->src = h->tc.c;
+  e->bias = bias;
+  e->M = M;
+  e->N = N;
+  e->T = T;
+  e->slots = h->tc.slots;
+  e->pl = pl;
+  e->has_split = umma_has_split_tiles(pl) ? 1 : 0;
+  return UA2_OK;
+}
+
 // x (M, K, row stride K) @ W^T, raw (no bias): tensor cores for M >= tc_min_rows (the product then stays in the path's own
 // buffer, *src points at it and `y` is not written), skinny fp32 kernels below (product in y, *src = y)
 int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K, const float** src) {
   if (h->opt_bf16 && h->a16 != nullptr && M >= 32 && (K % 8) == 0 && (N % 4) == 0 && (size_t)M * N <= h->tc.c_floats) {
-    auto it = h->w16.find(W);
-    if (it == h->w16.end()) {  // first use of this weight: keep a bf16 copy (2 B / parameter)
-      __nv_bfloat16* wb = nullptr;
-      UA2_CHECK_CUDA(cudaMalloc((void**)&wb, (size_t)N * K * sizeof(__nv_bfloat16)));
-      it = h->w16.emplace(W, wb).first;
-      const long long n4 = (long long)N * K / 4;
-      CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, W, wb, n4));
-    }
+    const __nv_bfloat16* w16 = nullptr;
+    RUN(weight16(h, lc, W, N, K, &w16));
     const long long n4 = (long long)M * K / 4;
     CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, x, h->a16, n4));
     // hand-written tcgen05 kind::f16 mainloop (ua2_umma.cu, bf16 mode): fp32 accumulation in TMEM, product in the handle's buffer
     const UmmaPlan pl = umma_plan(M, N, 1, K, true);
-    cudaError_t e = pl.slot_floats <= h->tc.slots_floats ? run_umma_bf16(lc, h->a16, it->second, h->tc.c, N, h->tc.slots, M, N, K, pl) : cudaErrorNotSupported;
+    cudaError_t e = pl.slot_floats <= h->tc.slots_floats ? run_umma_bf16(lc, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl) : cudaErrorNotSupported;
     if (e == cudaSuccess) e = run_umma_fixup(lc, h->tc.c, N, h->tc.slots, M, N, 1, pl);
     if (e == cudaSuccess) {
       *src = h->tc.c;
@@ -600,27 +764,66 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
   // ---- proj_in + positional embedding
   RUN(project_layer(h, lc, x, h->in1_w, h->in1, h->in2, h->n, h->h, B, T, c.in_channels, D, h->pe));
   // ---- blocks
-  const bool flash = h->opt_bf16 && h->opt_flash && hs == 64 && tc_gemm_available();
-  for (const DitBlock& bl : h->blocks) {
-    CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 0, 1,
-              c.norm_eps, T, D));
-    RUN(linear_raw(h, lc, h->n, bl.wqkv, h->qkv, M, 3 * D, D, &src));
-    DitEpi e = epi(src, h->qkv, bl.bqkv, M, 3 * D, T);
-    e.H = H;
-    e.hs = hs;
-    if (flash) {  // bf16 mode: both contractions of the attention on tcgen05 (the reference runs SDPA in bf16 under its autocast)
+  const bool fused16 = h->opt_bf16 && h->opt_flash && hs == 64 && tc_gemm_available() && h->a16 != nullptr && M >= 32 && (D % 8) == 0;
+  const bool fuse_ln = fused16 && D <= 4096;  // residual update + the next LayerNorm in one kernel (one CTA per row, 4 columns per thread)
+  for (size_t li = 0; li < h->blocks.size(); ++li) {
+    const DitBlock& bl = h->blocks[li];
+    if (fused16) {
+      // bf16 mode (the reference's autocast arithmetic), 9 launches per block: every linear and both contractions of the attention on
+      // tcgen05; activations travel between them as bf16, written by the producing kernel; the residual stream h stays fp32
+      if (li == 0 || !fuse_ln)
+        CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, (float*)nullptr, h->a16, bl.table, (const float*)h->t6,
+                  6 * D, D, 0, 1, c.norm_eps, T, D));
+      DitEpi e{};
+      RUN(linear16(h, lc, bl.wqkv, bl.bqkv, M, 3 * D, D, T, &e));
       e.q16 = reinterpret_cast<__nv_bfloat16*>(h->q);
       e.k16 = reinterpret_cast<__nv_bfloat16*>(h->k);
       e.v16 = reinterpret_cast<__nv_bfloat16*>(h->v);
-      CU(launch_epi<DE_QKV_SPLIT_BF16>(lc, e));
-      CU(launch_flash_bf16(lc, e.q16, e.k16, e.v16, h->att, B, T, H, hs));
-    } else {
+      e.H = H;
+      e.hs = hs;
+      CU(launch_epi4<DE_QKV_SPLIT_BF16>(lc, e));
+      CU(launch_flash_bf16(lc, e.q16, e.k16, e.v16, nullptr, h->a16, B, T, H, hs));
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) {
+          if (!fuse_ln)
+            CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, (float*)nullptr, h->a16, bl.table,
+                      (const float*)h->t6, 6 * D, D, 3, 4, c.norm_eps, T, D));
+          DitEpi f{};
+          RUN(linear16(h, lc, bl.ff1.w, bl.ff1.b, M, 4 * D, D, T, &f));
+          f.y16 = h->a16;  // the product is in the handle's fp32 buffer: the operand buffer is free again
+          CU(launch_epi4<DE_BIAS_GELU>(lc, f));
+        }
+        DitEpi g{};
+        RUN(linear16(h, lc, half ? bl.ff2.w : bl.o.w, half ? bl.ff2.b : bl.o.b, M, D, half ? 4 * D : D, T, &g));
+        g.y2 = h->h;
+        g.table = bl.table;
+        g.t6 = h->t6;
+        g.gate_idx = half ? 5 : 2;
+        const bool last = half == 1 && li + 1 == h->blocks.size();  // norm_out follows: its own table, timestep vector and eps
+        if (fuse_ln && !last) {
+          g.y16 = h->a16;
+          const float* ln_table = half ? h->blocks[li + 1].table : bl.table;
+          CU(launch(lc, dit_gate_res_ln_kernel, dim3(M), dim3(((D / 4) + 31) / 32 * 32), 0, g, ln_table, half ? 0 : 3, half ? 1 : 4,
+                    c.norm_eps));
+        } else {
+          CU(launch_epi4<DE_GATE_RES>(lc, g));
+        }
+      }
+      continue;
+    }
+    CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, (__nv_bfloat16*)nullptr, bl.table, (const float*)h->t6, 6 * D, D, 0, 1,
+              c.norm_eps, T, D));
+    RUN(linear_raw(h, lc, h->n, bl.wqkv, h->qkv, M, 3 * D, D, &src));
+    {
+      DitEpi e = epi(src, h->qkv, bl.bqkv, M, 3 * D, T);
+      e.H = H;
+      e.hs = hs;
       e.q = h->q;
       e.k = h->k;
       e.v = h->v;
       CU(launch_epi<DE_QKV_SPLIT>(lc, e));
-      CU(launch_dit_attn(lc, h->q, h->k, h->v, h->att, B, T, H, hs));
     }
+    CU(launch_dit_attn(lc, h->q, h->k, h->v, h->att, B, T, H, hs));
     RUN(linear_raw(h, lc, h->att, bl.o.w, h->n, M, D, D, &src));
     {
       DitEpi e = epi(src, h->n, bl.o.b, M, D, T);
@@ -630,7 +833,7 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
       e.gate_idx = 2;
       CU(launch_epi<DE_GATE_RES>(lc, e));
     }
-    CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, bl.table, (const float*)h->t6, 6 * D, D, 3, 4,
+    CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, (__nv_bfloat16*)nullptr, bl.table, (const float*)h->t6, 6 * D, D, 3, 4,
               c.norm_eps, T, D));
     RUN(linear_raw(h, lc, h->n, bl.ff1.w, h->ff, M, 4 * D, D, &src));
     CU(launch_epi<DE_BIAS_GELU>(lc, epi(src, h->ff, bl.ff1.b, M, 4 * D, T)));
@@ -645,7 +848,7 @@ int dit_forward(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* t_
     }
   }
   // ---- norm_out + modulation with (scale_shift_table + embedded_timestep) (eps 1e-6 hard-wired, :234), proj_out
-  CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, h->table, (const float*)h->temb, D, 0, 0, 1, 1e-6f,
+  CU(launch(lc, dit_ln_mod_kernel, dim3(M), dim3(256), 0, (const float*)h->h, h->n, (__nv_bfloat16*)nullptr, h->table, (const float*)h->temb, D, 0, 0, 1, 1e-6f,
             T, D));
   RUN(project_layer(h, lc, h->n, h->out1_w, h->out1, h->out2, h->att, out, B, T, D, c.out_channels, nullptr));
   return UA2_OK;

@@ -27,10 +27,9 @@ namespace {
 using namespace tc;
 
 constexpr int FA_BM = 128, FA_BN = 128, FA_HS = 64;
-constexpr int FA_STAGES = 3;                       // K / V ring
 constexpr int FA_TILE_BYTES = FA_BN * FA_HS * 2;   // 16 KB
 constexpr int FA_THREADS = 256;
-constexpr int FA_S_COL = 0, FA_P_COL = 256, FA_O_COL = 320;
+
 
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
@@ -58,9 +57,15 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+// SBUF = 2: scores double-buffered (S_{j+1} accumulates while the softmax warps work on S_j), 512 TMEM columns, one CTA per SM.
+// SBUF = 1: one score buffer, 256 columns and 80 KB of shared memory: two CTAs per SM overlap each other instead.
+template <int SBUF>
+__global__ void __launch_bounds__(FA_THREADS, SBUF == 1 ? 2 : 1)
 flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                  float* __restrict__ out, int T, int H, float scale_log2e) {
+                  float* __restrict__ out, __nv_bfloat16* __restrict__ out16, int T, int H, float scale_log2e) {
+  constexpr int FA_S_COL = 0, FA_P_COL = SBUF * 128, FA_O_COL = SBUF * 128 + 64;
+  constexpr uint32_t FA_TMEM_COLS = SBUF == 2 ? 512u : 256u;
+  constexpr int FA_STAGES = SBUF == 2 ? 3 : 2;  // K / V ring
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* q_s = base;                                   // 16 KB
@@ -99,7 +104,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     smem_bar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(tmem_base_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(tmem_base_smem)), "r"(FA_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -138,19 +143,19 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     auto issue_s = [&](int j) {  // S_j into buffer j & 1
       const int s = j % FA_STAGES;
       smem_bar_wait(&kv_full[s], (uint32_t)(j / FA_STAGES) & 1);
-      smem_bar_wait(&s_empty[j & 1], ((uint32_t)(j >> 1) & 1) ^ 1);
+      smem_bar_wait(&s_empty[j % SBUF], ((uint32_t)(j / SBUF) & 1) ^ 1);
       tc_fence_after();
       const uint64_t kd = smem_desc_sw128(smem_addr_u32(k_ring + s * FA_TILE_BYTES));
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < FA_HS / 16; ++ks) mma_bf16_ss(tmem + FA_S_COL + (j & 1) * 128, qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_s, ks ? 1u : 0u);
-        tc_commit(&s_full[j & 1]);
+        for (int ks = 0; ks < FA_HS / 16; ++ks) mma_bf16_ss(tmem + FA_S_COL + (j % SBUF) * 128, qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_s, ks ? 1u : 0u);
+        tc_commit(&s_full[j % SBUF]);
       }
       __syncwarp();
     };
     issue_s(0);
     for (int j = 0; j < n_kb; ++j) {
-      if (j + 1 < n_kb) issue_s(j + 1);  // the next block's scores accumulate while the softmax warps work on this one
+      if (SBUF == 2 && j + 1 < n_kb) issue_s(j + 1);  // the next block's scores accumulate while the softmax warps work on this one
       const int s = j % FA_STAGES;
       smem_bar_wait(p_full, (uint32_t)j & 1);
       tc_fence_after();
@@ -163,6 +168,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_commit(o_done);
       }
       __syncwarp();
+      if (SBUF == 1 && j + 1 < n_kb) issue_s(j + 1);  // the score buffer is free once P_j has been written
     }
   } else if (warp >= 4) {
     // ================= softmax + epilogue: thread = query row
@@ -171,7 +177,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kb; ++j) {
-      smem_bar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1);
+      smem_bar_wait(&s_full[j % SBUF], (uint32_t)(j / SBUF) & 1);
       tc_fence_after();
       // ---- row maximum of this block (keys past T are masked)
       const int n_valid = min(FA_BN, T - j * FA_BN);
@@ -179,7 +185,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       uint32_t sv[32];
 #pragma unroll 1
       for (int c0 = 0; c0 < FA_BN; c0 += 32) {
-        tmem_ld32(tmem + lane_addr + FA_S_COL + (j & 1) * 128 + c0, sv);
+        tmem_ld32(tmem + lane_addr + FA_S_COL + (j % SBUF) * 128 + c0, sv);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -206,7 +212,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       float sum = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < FA_BN; c0 += 32) {
-        tmem_ld32(tmem + lane_addr + FA_S_COL + (j & 1) * 128 + c0, sv);
+        tmem_ld32(tmem + lane_addr + FA_S_COL + (j % SBUF) * 128 + c0, sv);
         tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
@@ -225,7 +231,7 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        bar_arrive(&s_empty[j & 1]);
+        bar_arrive(&s_empty[j % SBUF]);
         bar_arrive(p_full);
       }
     }
@@ -239,7 +245,15 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       uint32_t ov[32];
       tmem_ld32(tmem + lane_addr + FA_O_COL + c0, ov);
       tmem_wait_ld();
-      if (t < T) {
+      if (t < T && out16 != nullptr) {
+        __nv_bfloat16* dst = out16 + ((size_t)b * T + t) * (size_t)(H * FA_HS) + h * FA_HS + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv),
+                                                          pack_bf16(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv),
+                                                          pack_bf16(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv),
+                                                          pack_bf16(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv));
+      } else if (t < T) {
         float* dst = out + ((size_t)b * T + t) * (size_t)(H * FA_HS) + h * FA_HS + c0;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
@@ -252,28 +266,57 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(FA_TMEM_COLS) : "memory");
   }
+}
+
+int g_flash_sbuf = 0;  // 0 = by grid size; 1 / 2 force a variant (option "flash_sbuf", measurement switch)
+int flash_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 }  // namespace
 
-// q16 / k16 / v16: (B, H, T, 64) bf16; out: (B, T, H * 64) fp32.  cudaErrorNotSupported unless head size 64.
-cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, int B, int T, int H, int hs) {
+void set_flash_sbuf(int v) { g_flash_sbuf = v == 1 || v == 2 ? v : 0; }
+
+// q16 / k16 / v16: (B, H, T, 64) bf16; out: (B, T, H * 64) fp32, or out16 (same shape, bf16) when not NULL.
+// cudaErrorNotSupported unless head size 64.
+cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
+                              int hs) {
   if (hs != FA_HS || T < 1 || B < 1 || H < 1 || B > 65535 || H > 65535) return cudaErrorNotSupported;
   const long long rows = (long long)B * H * T;
   CUtensorMap tmQ, tmK, tmV;
   if (!make_tmap(&tmQ, q16, FA_HS, rows, 1, FA_BM, false, true) || !make_tmap(&tmK, k16, FA_HS, rows, 1, FA_BN, false, true) ||
       !make_tmap(&tmV, v16, FA_HS, rows, 1, FA_BN, false, true))
     return cudaErrorNotSupported;
-  const size_t smem = 1024 + (size_t)(1 + 2 * FA_STAGES) * FA_TILE_BYTES + 32 * 8 + 16;
+  const int ctas = ((T + FA_BM - 1) / FA_BM) * H * B;
+  int sbuf = g_flash_sbuf;
+  if (sbuf == 0) sbuf = (ctas > flash_sm_count() ? 1 : 2);  // more tiles than SMs: co-resident CTA pairs instead of a second wave
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)hs);
+  const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
+  if (sbuf == 1) {
+    const size_t smem = 1024 + (size_t)(1 + 2 * 2) * FA_TILE_BYTES + 32 * 8 + 16;
+    static DeviceOnce once;
+    if (once.need()) {
+      cudaError_t e = cudaFuncSetAttribute(flash_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    return launch(lc, flash_bf16_kernel<1>, grid, dim3(FA_THREADS), smem, tmQ, tmK, tmV, out, static_cast<__nv_bfloat16*>(out16), T, H, scale_log2e);
+  }
+  const size_t smem = 1024 + (size_t)(1 + 2 * 3) * FA_TILE_BYTES + 32 * 8 + 16;
   static DeviceOnce once;
   if (once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(flash_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(flash_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const float scale_log2e = 1.4426950408889634f / sqrtf((float)hs);
-  return launch(lc, flash_bf16_kernel, dim3((T + FA_BM - 1) / FA_BM, H, B), dim3(FA_THREADS), smem, tmQ, tmK, tmV, out, T, H, scale_log2e);
+  return launch(lc, flash_bf16_kernel<2>, grid, dim3(FA_THREADS), smem, tmQ, tmK, tmV, out, static_cast<__nv_bfloat16*>(out16), T, H, scale_log2e);
 }
 
 }  // namespace ua2

@@ -50,6 +50,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_attn_ring(value);
     return UA2_OK;
   }
+  if (std::string(name) == "flash_sbuf") {
+    set_flash_sbuf(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "conv_umma") {
     set_conv_umma(value);
     return UA2_OK;
@@ -138,7 +142,7 @@ int ua2_flash_attn_bf16(const void* q16, const void* k16, const void* v16, float
   UA2_REQUIRE(B >= 1 && T >= 1 && H >= 1, "empty problem");
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
-  UA2_CHECK_CUDA(launch_flash_bf16(lc, q16, k16, v16, out, B, T, H, hs));
+  UA2_CHECK_CUDA(launch_flash_bf16(lc, q16, k16, v16, out, nullptr, B, T, H, hs));
   return UA2_OK;
 }
 

@@ -28,7 +28,10 @@ UmmaPlan umma_plan(int M, int N, int n_mat, int K, bool bf16 = false);
 cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W, const float* W2, float* C, int ldc, float* slots, int M, int N,
                             int K, const UmmaPlan& pl);
 // Tensor-core attention (ua2_flash.cu): q16 / k16 / v16 (B, H, T, 64) bf16 -> out (B, T, H * 64) fp32, unmasked softmax(q k^T / 8) v
-cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, int B, int T, int H, int hs);
+// (out16 != NULL: the result as bf16 instead, the next linear's operand)
+void set_flash_sbuf(int v);
+cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
+                              int hs);
 cudaError_t run_umma_bf16(const LaunchCtx& lc, const void* X16, const void* W16, float* C, int ldc, float* slots, int M, int N, int K,
                           const UmmaPlan& pl);
 cudaError_t run_umma_fixup(const LaunchCtx& lc, float* C, int ldc, const float* slots, int M, int N, int n_mat, const UmmaPlan& pl);
@@ -48,6 +51,26 @@ __device__ __forceinline__ float umma_side_sum(const UmmaPlan& pl, const float* 
   const int c_first = u0 / pl.Lr, c_last = u1 / pl.Lr;
   float s = 0.f;
   for (int c = c_first + 1; c <= c_last; ++c) s += slots[((size_t)c * pl.NT + (m - mt * pl.NT)) * 128 + (cn & 127)];
+  return s;
+}
+// the same for 4 consecutive columns (col % 4 == 0: one tile, one slot row)
+__device__ __forceinline__ float4 umma_side_sum4(const UmmaPlan& pl, const float* __restrict__ slots, int m, int col, int N) {
+  const int mat = col / N, cn = col - mat * N;
+  const int mt = m / pl.NT, nt = mat * pl.nt_per_mat + (cn >> 7);
+  const int g = mt / pl.GM;
+  const int gmg = pl.n_mt - g * pl.GM < pl.GM ? pl.n_mt - g * pl.GM : pl.GM;
+  const int tile = g * pl.GM * pl.n_nt + nt * gmg + (mt - g * pl.GM);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tile < pl.dp_tiles) return s;
+  const int u0 = (tile - pl.dp_tiles) * pl.KB, u1 = u0 + pl.KB - 1;
+  const int c_first = u0 / pl.Lr, c_last = u1 / pl.Lr;
+  for (int c = c_first + 1; c <= c_last; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(slots + ((size_t)c * pl.NT + (m - mt * pl.NT)) * 128 + (cn & 127));
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
+  }
   return s;
 }
 #endif
