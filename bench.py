@@ -394,11 +394,22 @@ def codec_conv_roofline(dev, batch=16, clip_s=10.0, reps=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     by = 4.0 * (x.numel() + y.numel())
-    peak, src = load_peaks()
-    return {"bound": "hbm", "kernel": "conv_umma_kernel<128> + weight repack (encoder down-sampling conv 64 -> 128, k 8 s 4, 24 kHz)",
-            "achieved": round(by / ms / 1e6, 1), "peak": peak, "unit": "GB/s", "frac": round(by / ms / 1e6 / peak, 4), "traffic": None,
-            "launch_ms": round(ms, 3), "bytes_per_launch": by, "peak_source": src,
-            "note": "activations (983 MB in + 492 MB out) exceed L2; the kernel is bound by its A-producer warps, not by HBM yet (profiles/r2_kernel_rooflines.md)"}
+    flop = 2.0 * 64 * 8 * 128 * batch * (T // 4)
+    hbm_peak, hbm_src = load_peaks()
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf32_peak = float(pk.get("bf16_tflops_sustained", 0.0)) / 2.0  # tf32 runs at half the bf16 rate
+    if tf32_peak <= 0.0:
+        tf32_peak = 1125.0  # nominal dense tf32, B200_PROFILING.md
+    mma = 3.0 * flop / ms / 1e9  # tf32 tensor-core TFLOP/s issued: 3 MMAs per fp32 product (operand splitting keeps fp32-class accuracy)
+    # report max(bytes / BW, flops / peak).  85 FLOP per byte: 3 * flop / tf32 peak = 0.55 ms against bytes / HBM peak =
+    # 0.23 ms, so the arithmetic binds - on the fp32 SIMT pipe (74 TFLOP/s measured) the same layer cannot run below 1.69 ms.
+    return {"bound": "tensor", "kernel": "conv_umma_kernel<128> + weight repack (encoder down-sampling conv 64 -> 128, k 8 s 4, 24 kHz)",
+            "achieved": round(mma, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(mma / tf32_peak, 4), "traffic": None,
+            "launch_ms": round(ms, 3), "flop_per_launch": flop, "fp32_equivalent_tflops": round(flop / ms / 1e9, 1),
+            "bytes_per_launch": by, "hbm_gbs": round(by / ms / 1e6, 1), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4),
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32); HBM: " + hbm_src,
+            "note": "tf32 MMAs issued (3 per fp32 product); the layer moves 983 MB in + 492 MB out per launch; limited by the producer warps "
+                    "that gather, activate and split the activations into tensor memory (profiles/r2_kernel_rooflines.md)"}
 
 
 def codec_sweep(dev, rank, world, clips=(1.0, 5.0, 30.0), batches=(1, 4, 16, 64, 256), budget_samples=16 * 240000):

@@ -438,6 +438,41 @@ def test_conv_umma_option_matches_oracle(B, Cin, Cout, T, K, stride, elu, res):
         assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
 
 
+# ---- (6b) the k = 1 streaming kernel of the narrow residual blocks (csrc/ua2_sgemm.cu: conv1d_pointwise_kernel), option "conv_pointwise"
+@pytest.mark.parametrize("B,Cin,Cout,T,elu,res", [(2, 32, 64, 3001, 1, 1), (1, 64, 128, 700, 1, 1), (3, 96, 64, 255, 0, 0), (1, 32, 128, 1, 1, 1)])
+def test_conv_pointwise_matches_oracle(B, Cin, Cout, T, elu, res):
+    import math
+
+    from oracle import codec_oracle as CO
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cin + Cout + T)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, 1, generator=g) / math.sqrt(Cin)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = CO.conv1d_causal(F.elu(x) if elu else x, w, b, stride=1, dilation=1)
+    r = torch.randn_like(ref) if res else None
+    if res:
+        ref = r + ref
+    xd, wd, bd = x.cuda(), w.contiguous().cuda(), b.cuda()
+    rd = r.cuda() if res else None
+    outs = []
+    try:
+        for opt in (1, 0):
+            _lib.check(L.ua2_set_global_option(b"conv_pointwise", opt))
+            y = torch.full((B, Cout, T), float("nan"), device="cuda")
+            _lib.check(L.ua2_conv1d_causal_gemm_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(rd), _lib.ptr(y), B, Cin, Cout, T, 1, 1, 1, elu,
+                                                    0, None))
+            torch.cuda.synchronize()
+            outs.append(y.cpu())
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_pointwise", 1))
+    for y in outs:  # fp32 FMA chain over <= 96 terms: 2e-5 of the output scale (the bar of tests/test_codec_gpu.py)
+        assert bool(torch.isfinite(y).all())
+        assert float((y - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("B,Cin,Cout,T,stride", [(2, 128, 64, 1000, 4), (1, 64, 32, 777, 5), (1, 128, 64, 600, 8)])
 def test_convtr_umma_option_matches_oracle(B, Cin, Cout, T, stride):
     """Transposed convolution (kernel = 2 x stride, causal trim) with all phases as columns of one implicit GEMM over the input grid."""

@@ -90,6 +90,8 @@ def main():
         ("enc res k3 64->32", 64, 32, 3, 1, T0),
         ("enc res k1 32->64", 32, 64, 1, 1, T0),
         ("enc down k8 s4 64->128", 64, 128, 8, 4, T0),
+        ("enc res k3 128->64 @6k", 128, 64, 3, 1, T0 // 4),
+        ("enc res k1 64->128 @6k", 64, 128, 1, 1, T0 // 4),
         ("enc down k10 s5 128->256", 128, 256, 10, 5, T0 // 4),
         ("enc down k12 s6 256->512", 256, 512, 12, 6, T0 // 20),
         ("enc down k16 s8 512->1024", 512, 1024, 16, 8, T0 // 120),

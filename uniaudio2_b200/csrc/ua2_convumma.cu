@@ -288,11 +288,17 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
         add[i] = a;
       }
     };
+    // Transposed convolution with stride 4 and no left crop (the 24 kHz up-sampling layer, modules/seanet.py:330-340): the four phases
+    // of a channel are the four consecutive output samples 4 j .. 4 j + 3 of this thread's position j - one 128-bit store per channel,
+    // a warp writes 512 contiguous bytes (the generic path below stores one float per column with an integer division in front of it:
+    // 4.46 ms for 128 -> 64 at batch 16 x 10 s, 88 us per tile, all of it in these four warps).
+    const bool fast_tr = p.tr_stride == 4 && p.tr_crop == 0 && p.res == nullptr && p.n0 == 0 && p.n_cols == 4 * p.Cout && (p.Cout % 16) == 0 &&
+                         (p.T_out % 4) == 0 && 4 * p.Cout <= NO;
     float add_next[32];
     Row row_next{};
     if (my_tiles > 0) {
       row_next = row_of(0);
-      load_add(row_next, 0, add_next);
+      if (!fast_tr) load_add(row_next, 0, add_next);
     }
     for (int j = 0; j < my_tiles; ++j) {
       const int ab = NACC == 2 ? (j & 1) : 0;
@@ -301,6 +307,33 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
       if (j + 1 < my_tiles) row_next = row_of(j + 1);
       smem_bar_wait(&acc_full[ab], use & 1);
       tc_fence_after();
+      if (fast_tr) {
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * 128;
+        const int t4 = rw.t_pos * 4;
+        const bool ok = rw.ok && t4 + 3 < p.T_out;
+#pragma unroll 1
+        for (int ch0 = 0; ch0 < p.Cout; ch0 += 8) {
+          uint32_t v0[8], v1[8], v2[8], v3[8];
+          tmem_ld8(tbase + ch0, v0);
+          tmem_ld8(tbase + p.Cout + ch0, v1);
+          tmem_ld8(tbase + 2 * p.Cout + ch0, v2);
+          tmem_ld8(tbase + 3 * p.Cout + ch0, v3);
+          tmem_wait_ld();
+          if (ok) {
+            float* dst = p.y + rw.base + (size_t)ch0 * p.T_out + t4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float bv = p.bias ? __ldg(p.bias + ch0 + i) : 0.f;
+              *reinterpret_cast<float4*>(dst + (size_t)i * p.T_out) = make_float4(__uint_as_float(v0[i]) + bv, __uint_as_float(v1[i]) + bv,
+                                                                                 __uint_as_float(v2[i]) + bv, __uint_as_float(v3[i]) + bv);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&acc_empty[ab]);
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < NO; c0 += 32) {
         if (c0 >= p.n_cols) break;

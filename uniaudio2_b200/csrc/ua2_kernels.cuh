@@ -138,6 +138,8 @@ cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float*
                                int replicate);
 cudaError_t launch_convtr1d_umma(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin, int Cout,
                                  int T_in, int stride, int pre_elu, int crop_left, int T_out);
+void set_conv_pointwise(int v);
+int get_conv_pointwise();
 void set_conv_umma(int v);
 int get_conv_umma();
 // fused SEANet residual block for the 64-channel / 24 kHz stages (ua2_resblock.cu; option "resblock_fused", default 0)

@@ -456,6 +456,12 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_conv_kernel(const ConvGem
 
 }  // namespace
 
+namespace {
+int g_conv_pointwise = 1;  // option "conv_pointwise": measurement switch for the k = 1 streaming kernel below
+}
+void set_conv_pointwise(int v) { g_conv_pointwise = v ? 1 : 0; }
+int get_conv_pointwise() { return g_conv_pointwise; }
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // The two thin ends of the SEANet stacks at the full 24 kHz rate (modules/seanet.py:147-150, :365-371): conv k7 1 -> 64 (encoder
 // input) and ELU + conv k7 64 -> 1 (decoder output).  One operand is a single channel, so both are pure streaming kernels (HBM
@@ -559,6 +565,56 @@ __global__ void __launch_bounds__(256) conv1d_cin1_kernel(const float* __restric
   }
 }
 
+// Pointwise convolution of a narrow SEANet residual block (k = 1, Cin in {32, 64, 96, 128}: modules/seanet.py:53-58, the second conv of the
+// block, 32 -> 64 at 24 kHz, 64 -> 128 at 6 kHz, 128 -> 256 at 1.2 kHz) with the block's skip add:  y[b, co, t] = bias[co] + sum_ci w[co, ci] f(x[b, ci, t]) + res.
+// 16-32 FLOP per byte of activations: a streaming kernel.  Thread = one position (all loads and stores coalesced along t), 64 output
+// channels in registers, the (Cin x 64) weight slice in shared memory read as broadcast float4.  As an implicit GEMM with K = 32 the
+// tiled core spent its time on tile overhead (2.98 ms for 32 -> 64 at batch 16 x 10 s; 2.46 GB of traffic = 0.38 ms at the HBM peak).
+constexpr int PW_CO = 64;
+__global__ void __launch_bounds__(256, 2) conv1d_pointwise_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                               const float* __restrict__ res, float* __restrict__ y, int Cin, int Cout, int T,
+                                                               int pre_elu) {
+  extern __shared__ __align__(16) float pw_ws[];  // [Cin][PW_CO]
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.y * PW_CO, t = blockIdx.x * 256 + tid;
+  for (int i = tid; i < Cin * PW_CO; i += 256) {  // weights do not depend on the previous kernel: staged before the wait
+    const int co = i / Cin, ci = i - co * Cin;
+    pw_ws[ci * PW_CO + co] = w[(size_t)(co0 + co) * Cin + ci];
+  }
+  pdl_wait();
+  __syncthreads();
+  if (t >= T) return;
+  float acc[PW_CO];
+#pragma unroll
+  for (int c = 0; c < PW_CO; ++c) acc[c] = bias ? bias[co0 + c] : 0.f;
+  const float* xp = x + (size_t)b * Cin * T + t;
+  for (int c0 = 0; c0 < Cin; c0 += 16) {  // Cin % 32 == 0 (launcher): 16 independent loads in flight per thread (2 KB per warp, 32 KB per SM)
+    float xv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xv[i] = __ldg(xp + (size_t)(c0 + i) * T);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float v = xv[i];
+      if (pre_elu) v = v > 0.f ? v : expm1f(v);
+      const float4* wr = reinterpret_cast<const float4*>(pw_ws + (c0 + i) * PW_CO);
+#pragma unroll
+      for (int c4 = 0; c4 < PW_CO / 4; ++c4) {
+        const float4 w4 = wr[c4];
+        acc[4 * c4 + 0] = fmaf(w4.x, v, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(w4.y, v, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(w4.z, v, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(w4.w, v, acc[4 * c4 + 3]);
+      }
+    }
+  }
+  const size_t o = ((size_t)b * Cout + co0) * T + t;
+#pragma unroll
+  for (int c = 0; c < PW_CO; ++c) {
+    float r = acc[c];
+    if (res) r += res[o + (size_t)c * T];
+    y[o + (size_t)c * T] = r;
+  }
+}
 
 cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res,
                                float* y, int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation,
@@ -569,6 +625,10 @@ cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float*
     if (Cin == 1 && Cout > 1 && (size_t)Cout * (Ktaps + 1) * 4 <= 40 * 1024)
       return launch(lc, conv1d_cin1_kernel, grid, dim3(256), (size_t)Cout * (Ktaps + 1) * 4, x, w_torch, bias, y, Cout, T_in, Ktaps, pad_left, pre_elu);
   }
+  if (prelu == nullptr && Ktaps == 1 && stride == 1 && !replicate && T_out == T_in && Cin <= 128 && (Cin % 32) == 0 && (Cout % PW_CO) == 0 && B <= 65535 &&
+      Cout / PW_CO <= 65535 && get_conv_pointwise())
+    return launch(lc, conv1d_pointwise_kernel, dim3((T_out + 255) / 256, Cout / PW_CO, B), dim3(256), (size_t)Cin * PW_CO * 4, x, w_torch, bias, res, y,
+                  Cin, Cout, T_in, pre_elu);
   if (prelu == nullptr) {  // option "conv_umma" (default 1): implicit GEMM on tcgen05 straight from (B, C, T), ua2_convumma.cu
     const cudaError_t e = launch_conv1d_umma(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
                                              replicate);
