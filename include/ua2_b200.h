@@ -418,6 +418,37 @@ int ua2_dit_solve_euler(ua2_dit* h, float* x, const float* incontext_x, int inco
 int ua2_dit_set_option(ua2_dit* h, const char* name, int value);
 int ua2_dit_last_launch_count(ua2_dit* h);
 
+/* ----------------------------------------------------------------------------------------------
+ * Whisper encoder: the first SSL front-end of ReasoningCodec_film's tokenize.  Replaces
+ * `WhisperModel.from_pretrained(path).encoder(mels, return_dict=True).last_hidden_state` as called from
+ * models/AudioDiffusion1D.py:223, :334-343 - the reference's own copy of the model code is
+ * models/modeling_whisper.py: WhisperEncoder.forward :766-867, WhisperEncoderLayer.forward :394-443, WhisperAttention.forward :255-374.
+ * csrc/ua2_enc.cu.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ua2_whisper_cfg {     /* WhisperConfig fields the encoder reads (whisper-medium: 1024 / 16 / 4096 / 24 / 1500 / 80) */
+  int32_t d_model;                   /* multiple of 8, <= 4096; d_model / heads in {32, 64, 128} (64 for the bf16 mode) */
+  int32_t encoder_attention_heads;
+  int32_t encoder_ffn_dim;
+  int32_t encoder_layers;
+  int32_t max_source_positions;      /* output frames per clip; the input has exactly twice as many mel frames (:808-811) */
+  int32_t num_mel_bins;
+} ua2_whisper_cfg;
+typedef struct ua2_whisper ua2_whisper;
+
+int ua2_whisper_create(const ua2_whisper_cfg* cfg, ua2_whisper** out);
+int ua2_whisper_destroy(ua2_whisper* h);
+/* one fp32 parameter by its state-dict key relative to the encoder ("conv1.weight", "embed_positions.weight",
+ * "layers.3.self_attn.k_proj.weight", "layers.3.final_layer_norm.bias", "layer_norm.weight", ...); tensors must outlive the handle */
+int ua2_whisper_load_weight(ua2_whisper* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+/* validates the parameter set; repacks the two k = 3 convolutions to GEMM form and concatenates q / k / v projections */
+int ua2_whisper_finalize(ua2_whisper* h, void* stream);
+/* input_features (B, num_mel_bins, 2 * max_source_positions) fp32 -> last_hidden_state (B, max_source_positions, d_model) fp32 */
+int ua2_whisper_forward(ua2_whisper* h, const float* input_features, float* out, int B, void* stream);
+/* "bf16" (0/1, default 0): the reference's autocast arithmetic (reason_tokenizer.py:114-118) - linears on bf16 operands with fp32
+ * accumulation (tcgen05 kind::f16), attention on tensor cores (csrc/ua2_flash.cu); default: fp32 class (3xTF32 linears, fp32 attention) */
+int ua2_whisper_set_option(ua2_whisper* h, const char* name, int value);
+int ua2_whisper_last_launch_count(ua2_whisper* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,11 @@ class DitCfg(C.Structure):
                 ("flow_t_size", C.c_int32), ("norm_eps", C.c_float)]
 
 
+class WhisperCfg(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("encoder_attention_heads", C.c_int32), ("encoder_ffn_dim", C.c_int32),
+                ("encoder_layers", C.c_int32), ("max_source_positions", C.c_int32), ("num_mel_bins", C.c_int32)]
+
+
 # every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -117,6 +122,13 @@ SYMBOLS = {
     "ua2_dit_solve_euler": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.c_int, _P, C.c_int, C.c_float, C.c_float, _P]),
     "ua2_dit_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ua2_dit_last_launch_count": (C.c_int, [_P]),
+    "ua2_whisper_create": (C.c_int, [C.POINTER(WhisperCfg), C.POINTER(_P)]),
+    "ua2_whisper_destroy": (C.c_int, [_P]),
+    "ua2_whisper_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_whisper_finalize": (C.c_int, [_P, _P]),
+    "ua2_whisper_forward": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "ua2_whisper_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "ua2_whisper_last_launch_count": (C.c_int, [_P]),
     "ua2_stx_create": (C.c_int, [C.POINTER(StxCfg), C.POINTER(_P)]),
     "ua2_stx_destroy": (C.c_int, [_P]),
     "ua2_stx_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),

@@ -541,6 +541,11 @@ struct DitBlock {
 };
 
 }  // namespace
+
+// unmasked softmax(q k^T / sqrt(hs)) v in fp32 for other handles of the library (ua2_enc.cu): q (B * T, H * hs), k / v (B, H, T, hs)
+cudaError_t launch_dense_attn_f32(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H, int hs) {
+  return launch_dit_attn(lc, q, kc, vc, out, B, T, H, hs);
+}
 }  // namespace ua2
 
 using namespace ua2;

@@ -29,6 +29,8 @@ cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W
                             int K, const UmmaPlan& pl);
 // Tensor-core attention (ua2_flash.cu): q16 / k16 / v16 (B, H, T, 64) bf16 -> out (B, T, H * 64) fp32, unmasked softmax(q k^T / 8) v
 // (out16 != NULL: the result as bf16 instead, the next linear's operand)
+// fp32 SIMT attention of ua2_dit.cu (head size 32 / 64 / 128): q (B * T, H * hs), k / v (B, H, T, hs) -> out (B * T, H * hs)
+cudaError_t launch_dense_attn_f32(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H, int hs);
 void set_flash_sbuf(int v);
 cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
                               int hs);
