@@ -85,3 +85,28 @@ def test_whisper_encoder_interface_errors():
         m.load_state_dict(bad, strict=True)
     with pytest.raises(_lib.Ua2Error):
         type(m)(m.config)(torch.zeros(1, 80, 80))  # CPU parameters: no fallback
+
+
+def test_get_whisper_feature_mirrors_the_reference_cut():
+    """AudioDiffusion1D.get_whisper_feature (:334-343): frames = max(int(n / 24000 * 50), 2 * len_semantic), result (B, D, T)."""
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.AudioDiffusion1D import AudioDiffusion1D
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.transformer_1d_flow import Transformer1DModel
+
+    cfg = WO.WhisperCfg(d_model=128, encoder_attention_heads=2, encoder_ffn_dim=256, encoder_layers=1, max_source_positions=100)
+    sd = WO.random_state_dict(cfg, seed=3)
+    enc = _model(cfg, sd)
+    est = Transformer1DModel(num_attention_heads=1, attention_head_dim=64, in_channels=56, out_channels=12, num_layers=1, norm_type="ada_norm_single",
+                             activation_fn="gelu-approximate", attention_bias=True, norm_elementwise_affine=False, num_positional_embeddings=64)
+    m = AudioDiffusion1D(est, codec_dim=32, codebook_size=16, codebook_dim=8, sq_codec_latent=12, whisper_dim=128, wavlm_dim=32, bestrq_dim=32)
+    import pytest as _pt
+    with _pt.raises(Exception):
+        m.get_whisper_feature(torch.zeros(1, 80, 200), 24000, 10)
+    m.attach_whisper_encoder(enc)
+    g = torch.Generator().manual_seed(9)
+    mel = torch.randn(2, 80, 200, generator=g)
+    with torch.no_grad():
+        ref = WO.WhisperEncoderOracle(cfg, sd).forward(mel)
+    for n_samples, len_sem, want in ((24000, 10, 50), (24000, 40, 80), (12345, 1, 25)):
+        y = m.get_whisper_feature(mel.cuda(), n_samples, len_sem)
+        assert y.shape == (2, 128, want)
+        assert _rel(y.cpu(), ref[:, :want].transpose(1, 2)) < 1e-4

@@ -176,6 +176,25 @@ class AudioDiffusion1D(nn.Module):
         self.cond_fusion_layer_phone = lin(codec_dim, wavlm_dim)
         self.time_film_phone, self.time_film_semantic, self.time_film_acoustic = (lin(2 * codec_dim, codec_dim) for _ in range(3))
         self.reason_adaptor = lin(codec_dim, codec_dim)
+        # SSL front-ends (AudioDiffusion1D.py:222-236).  Only the Whisper encoder exists in this package so far (modeling_whisper.py);
+        # it is attached by the caller because its size comes from the checkpoint's config, not from this class's arguments.
+        self.whisper_encoder = None
+
+    def attach_whisper_encoder(self, encoder):
+        """`self.whisper_encoder = WhisperModel.from_pretrained(whisper_path).encoder` (AudioDiffusion1D.py:223): the caller builds the
+        drop-in WhisperEncoder (models/modeling_whisper.py), loads the checkpoint's encoder.* tensors into it and hands it over."""
+        self.whisper_encoder = encoder
+        return encoder
+
+    @torch.inference_mode()
+    def get_whisper_feature(self, mels, n_len, len_semantic):
+        """AudioDiffusion1D.py:334-343: encoder output cut to the clip's frames (50 Hz), at least twice the BEST-RQ frames, as (B, D, T)."""
+        if self.whisper_encoder is None:
+            raise _lib.Ua2Error("no Whisper encoder attached (attach_whisper_encoder)")
+        n_len = int((n_len / 24000) * 50)
+        n_len = max(n_len, len_semantic * 2)
+        whisper_embeds = self.whisper_encoder(mels, return_dict=True).last_hidden_state
+        return whisper_embeds[:, :n_len, :].transpose(1, 2)
 
     @property
     def device(self):
