@@ -577,6 +577,66 @@ def bench_flow_decoder(dev, frames=500, steps=10, reps=3, cpu=True):
     return res
 
 
+def bench_whisper_encoder(dev, batch=6, reps=3, cpu=True):
+    """First SSL front-end of ReasoningCodec_film's tokenize: the Whisper-medium encoder on `batch`
+    windows of 30 s (reason_tokenizer.py:86 batch_size=6), random weights, bf16 mode = the reference's autocast arithmetic
+    (reason_tokenizer.py:114-118) and fp32 class.  1.14 TFLOP per window."""
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.modeling_whisper import WhisperConfig, WhisperModel
+
+    torch.manual_seed(0)
+    m = WhisperModel(WhisperConfig(), device=dev).encoder
+    P, D, F, L = 1500, 1024, 4096, 24
+    flop = batch * (2.0 * 3000 * 240 * D + 2.0 * P * 3 * D * D + L * (2.0 * P * (4 * D * D + 2 * D * F) + 4.0 * P * P * D))
+    g = torch.Generator().manual_seed(2)
+    mel_h = torch.randn(batch, 80, 3000, generator=g).pin_memory()
+    mel = mel_h.to(dev)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 0.0))
+    modes = {}
+    for mode, bf16 in (("bf16", 1), ("fp32_class", 0)):
+        m.set_option("bf16", bf16)
+        for _ in range(2):
+            y = m(mel).last_hidden_state
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            y = m(mel).last_hidden_state
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):  # end to end with host buffers: H2D of the log-mel windows, D2H of the features
+            y_h = m(mel_h.to(dev, non_blocking=True)).last_hidden_state.cpu()
+        e2e_s = (time.perf_counter() - t0) / reps
+        mma = (1 if bf16 else 3) * flop / ms / 1e9
+        peak = bf16_peak / (1 if bf16 else 2)
+        modes[mode] = {"ms": round(ms, 2), "x_realtime": round(batch * 30.0 / (ms * 1e-3), 1), "e2e_x_realtime": round(batch * 30.0 / e2e_s, 1),
+                       "mma_tflops": round(mma, 1),
+                       "roofline": {"bound": "tensor", "achieved": round(mma, 1), "peak": round(peak, 1) if peak else None, "unit": "TFLOP/s",
+                                    "frac": round(mma / peak, 4) if peak else None,
+                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" + ("" if bf16 else " / 2 (tf32)")}}
+    res = {"config": f"Whisper-medium encoder (24 x (16 x 64), d 1024), {batch} x 30 s windows, random weights",
+           "tflop_per_call": round(flop / 1e12, 3), "default_mode": "bf16 (the reference's autocast)", **modes["bf16"],
+           "fp32_class": modes["fp32_class"], "out_shape": list(y_h.shape)}
+    if cpu:
+        from oracle import whisper_oracle as WO  # the CPU-baseline leg: the oracle port encodes one window on the host cores
+
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        orc = WO.WhisperEncoderOracle(WO.WhisperCfg(), sd)
+        with torch.inference_mode():
+            t0 = time.perf_counter()
+            ref = orc.forward(mel_h[:1])
+            dt = time.perf_counter() - t0
+        m.set_option("bf16", 0)
+        got = m(mel[:1]).last_hidden_state.cpu()
+        res["cpu_baseline"] = {"kind": "port", "cores": torch.get_num_threads(), "sample": "1 window of 30 s", "s": round(dt, 2),
+                               "x_realtime": round(30.0 / dt, 1)}
+        res["parity"] = {"fp32_class_vs_cpu_oracle_max_abs": float((got - ref).abs().max()), "out_scale": float(ref.abs().max())}
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def state_dict_to_cpu(model):
     return {k: v.detach().to("cpu") for k, v in model.state_dict().items()}
 
@@ -749,7 +809,7 @@ def main():
                    "ms_per_step": round(ems / args.steps, 2)}
 
         hbm_peak, peak_src = load_peaks()
-        roofline = cpu_base = codec = flow = parity = None
+        roofline = cpu_base = codec = flow = parity = whisper = None
         if rank == 0:
             roofline = time_dominant_kernel(model, hbm_peak)
             roofline["peak_source"] = peak_src
@@ -782,6 +842,10 @@ def main():
                     flow = bench_flow_decoder(dev, cpu=not args.no_cpu_baseline)
                 except Exception as e:  # noqa: BLE001
                     flow = {"error": f"{type(e).__name__}: {e}"}
+                try:  # secondary metric (first SSL front-end of tokenize), same rule
+                    whisper = bench_whisper_encoder(dev, cpu=not args.no_cpu_baseline)
+                except Exception as e:  # noqa: BLE001
+                    whisper = {"error": f"{type(e).__name__}: {e}"}
     # ---- codec at N > 1: every rank encodes + decodes its own batch of 16 x 10 s clips (replicas, weak scaling), time = max over ranks;
     #      --codec-sweep: the clip length x batch grid of BASELINE.json config 5 with the clips of a point dealt to the ranks
     if world > 1 and not args.no_codec:
@@ -809,7 +873,7 @@ def main():
                           "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
                           "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
-                          "codec": codec, "codec_sweep": sweep, "flow_decoder": flow}))
+                          "codec": codec, "codec_sweep": sweep, "flow_decoder": flow, "whisper_encoder": whisper}))
     if world > 1:
         dist.destroy_process_group()
 

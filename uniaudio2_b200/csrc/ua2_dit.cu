@@ -647,8 +647,11 @@ int reserve(ua2_dit* h, size_t M, size_t B) {
 }
 
 // the bf16 copy of a weight, made at first use (2 B / parameter)
-int weight16(ua2_dit* h, const LaunchCtx& lc, const float* W, int N, int K, const __nv_bfloat16** out) {
+// *fresh: the copy was made by a kernel just launched on this stream.  The GEMM's weight producer starts its TMA loads BEFORE
+// griddepcontrol.wait (weights are normally static), so the launch that follows must not be a programmatic dependent launch.
+int weight16(ua2_dit* h, const LaunchCtx& lc, const float* W, int N, int K, const __nv_bfloat16** out, bool* fresh) {
   auto it = h->w16.find(W);
+  *fresh = it == h->w16.end();
   if (it == h->w16.end()) {
     __nv_bfloat16* wb = nullptr;
     UA2_CHECK_CUDA(cudaMalloc((void**)&wb, (size_t)N * K * sizeof(__nv_bfloat16)));
@@ -664,10 +667,13 @@ int weight16(ua2_dit* h, const LaunchCtx& lc, const float* W, int N, int K, cons
 // description comes back with the product, the side slots and the plan filled in (dit_epi4_kernel sums the slots itself)
 int linear16(ua2_dit* h, const LaunchCtx& lc, const float* W, const float* bias, int M, int N, int K, int T, DitEpi* e) {
   const __nv_bfloat16* w16 = nullptr;
-  RUN(weight16(h, lc, W, N, K, &w16));
+  bool fresh = false;
+  RUN(weight16(h, lc, W, N, K, &w16, &fresh));
   const UmmaPlan pl = umma_plan(M, N, 1, K, true);
   UA2_REQUIRE(pl.slot_floats <= h->tc.slots_floats && (size_t)M * N <= h->tc.c_floats && (K % 8) == 0 && (N % 4) == 0, "flow decoder linear outside the tensor-core path's shapes");
-  CU(run_umma_bf16(lc, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl));
+  LaunchCtx lg = lc;
+  if (fresh) lg.pdl = false;  // full stream order behind the conversion kernel (see weight16)
+  CU(run_umma_bf16(lg, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl));
   e->src = h->tc.c;
   e->bias = bias;
   e->M = M;
@@ -684,9 +690,12 @@ int linear16(ua2_dit* h, const LaunchCtx& lc, const float* W, const float* bias,
 int linear_raw(ua2_dit* h, const LaunchCtx& lc, const float* x, const float* W, float* y, int M, int N, int K, const float** src) {
   if (h->opt_bf16 && h->a16 != nullptr && M >= 32 && (K % 8) == 0 && (N % 4) == 0 && (size_t)M * N <= h->tc.c_floats) {
     const __nv_bfloat16* w16 = nullptr;
-    RUN(weight16(h, lc, W, N, K, &w16));
+    bool fresh = false;
+    RUN(weight16(h, lc, W, N, K, &w16, &fresh));
     const long long n4 = (long long)M * K / 4;
-    CU(launch(lc, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, x, h->a16, n4));
+    LaunchCtx lg = lc;
+    if (fresh) lg.pdl = false;  // full stream order behind the weight conversion (see weight16); the GEMM then follows this kernel
+    CU(launch(lg, dit_to_bf16_kernel, dim3(grid_for(n4)), dim3(256), 0, x, h->a16, n4));
     // hand-written tcgen05 kind::f16 mainloop (ua2_umma.cu, bf16 mode): fp32 accumulation in TMEM, product in the handle's buffer
     const UmmaPlan pl = umma_plan(M, N, 1, K, true);
     cudaError_t e = pl.slot_floats <= h->tc.slots_floats ? run_umma_bf16(lc, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl) : cudaErrorNotSupported;

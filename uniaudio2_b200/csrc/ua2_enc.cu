@@ -340,8 +340,11 @@ int reserve(ua2_whisper* h, int B) {
   return UA2_OK;
 }
 
-int weight16(ua2_whisper* h, const LaunchCtx& lc, const float* W, int N, int K, const __nv_bfloat16** out) {
+// *fresh: the copy was made by a kernel just launched on this stream.  The GEMM's weight producer starts its TMA loads BEFORE
+// griddepcontrol.wait (weights are normally static), so the launch that follows must not be a programmatic dependent launch.
+int weight16(ua2_whisper* h, const LaunchCtx& lc, const float* W, int N, int K, const __nv_bfloat16** out, bool* fresh) {
   auto it = h->w16.find(W);
+  *fresh = it == h->w16.end();
   if (it == h->w16.end()) {
     __nv_bfloat16* wb = nullptr;
     UA2_CHECK_CUDA(cudaMalloc((void**)&wb, (size_t)N * K * sizeof(__nv_bfloat16)));
@@ -365,11 +368,14 @@ int enc_linear(ua2_whisper* h, const LaunchCtx& lc, const float* x32, const floa
   e->eps = 1e-5f;
   if (h->opt_bf16) {
     const __nv_bfloat16* w16 = nullptr;
-    RUN(weight16(h, lc, W, N, K, &w16));
+    bool fresh = false;
+    RUN(weight16(h, lc, W, N, K, &w16, &fresh));
     const UmmaPlan pl = umma_plan(M, N, 1, K, true);
     UA2_REQUIRE(pl.slot_floats <= h->tc.slots_floats && (size_t)M * N <= h->tc.c_floats && (K % 8) == 0 && (N % 4) == 0,
                 "encoder linear outside the tensor-core path's shapes");
-    CU(run_umma_bf16(lc, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl));
+    LaunchCtx lg = lc;
+    if (fresh) lg.pdl = false;  // full stream order behind the conversion kernel (see weight16)
+    CU(run_umma_bf16(lg, h->a16, w16, h->tc.c, N, h->tc.slots, M, N, K, pl));
     e->src = h->tc.c;
     e->slots = h->tc.slots;
     e->pl = pl;
