@@ -54,6 +54,7 @@ inline T shim_exchange(T v, int src_lane) {
   return out;
 }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return shim_exchange(v, (t_linear_tid & 31) ^ lane_mask); }
+template <typename T> inline T __ldg(const T* p) { return *p; }  // read-only data path: a plain load here
 template <typename T> inline T __shfl_sync(unsigned, T v, int src_lane) { return shim_exchange(v, src_lane); }
 inline void __syncwarp() { (*g_warps)[t_linear_tid >> 5]->bar.arrive_and_wait(); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -34,7 +34,7 @@ cudaError_t launch_tc_linear(const LaunchCtx&, int pro, int epi, const GemvParam
 int get_conv_umma() { return 0; }
 void set_conv_umma(int) {}
 cudaError_t launch_conv1d_umma(const LaunchCtx&, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int,
-                               int, int, int, int) {
+                               int, int, int, int, const float*) {
   return cudaErrorNotSupported;
 }
 cudaError_t launch_convtr1d_umma(const LaunchCtx&, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int) {

@@ -78,7 +78,7 @@ inline cudaError_t launch_gemv(const LaunchCtx&, int, int, const GemvParams& p) 
 }
 cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y,
                              int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
-                             int replicate);
+                             int replicate, const float* prelu = nullptr);
 cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin,
                                int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out);
 cudaError_t launch_resblock_fused(const LaunchCtx& lc, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -504,3 +504,48 @@ def test_convtr_umma_option_matches_oracle(B, Cin, Cout, T, stride):
     for y in outs:
         assert y.shape == ref.shape and bool(torch.isfinite(y).all())
         assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+
+
+# ---- (7) ScalarModel convolutions on the tensor cores: scalar nn.PReLU after the bias (activation(conv(x)), scalar24k.py:139-150; the skip
+#      add comes after it), dilation, symmetric padding, channel counts that
+#      are multiples of 16 (48, 96: zero-padded k-blocks), more than 256 output channels (column chunks / im2col GEMM), k = 1 + skip
+@pytest.mark.parametrize("B,Cin,Cout,T,K,dil,causal,res", [
+    (1, 96, 96, 3000, 7, 9, 1, 0),     # conv_umma, dilation 9, 96 -> 128-column tile
+    (1, 96, 96, 3000, 1, 1, 1, 1),     # pointwise<48> with PReLU + skip
+    (2, 48, 48, 2500, 7, 3, 1, 0),     # Cin 48: the second channel block of every tap is half zero padding
+    (1, 48, 48, 5000, 1, 1, 1, 1),     # pointwise<48>, Cin % 32 != 0
+    (2, 192, 192, 700, 7, 5, 0, 0),    # symmetric padding (non-causal configuration)
+    (1, 384, 384, 9600, 7, 7, 1, 0),   # 384 output channels: two column chunks of the implicit GEMM
+    (1, 768, 768, 300, 7, 1, 1, 0),    # few positions, long reduction: materialised im2col + stream-K GEMM
+    (1, 384, 384, 3000, 1, 1, 1, 1),   # pointwise with 384 channels + skip
+    (1, 136, 1536, 500, 5, 1, 0, 0),   # the delay convolution of the decoder (Cin 136: not a multiple of 16 -> fp32 SIMT core)
+])
+def test_scalar_model_convs_on_tensor_cores(B, Cin, Cout, T, K, dil, causal, res):
+    import math
+
+    from uniaudio2_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cin + Cout + T + K + dil)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g) * 0.1
+    slope = torch.tensor([0.25])
+    if causal:  # scalar24k.py:47-50: left pad dilation * (k - 1)
+        pl, pr = dil * (K - 1), 0
+    else:       # get_padding, scalar24k.py:18-19
+        pl = pr = (K * dil - dil) // 2
+    ref = F.prelu(F.conv1d(F.pad(x, (pl, pr)), w, b, dilation=dil), slope)
+    r = torch.randn_like(ref) if res else None
+    if res:
+        ref = ref + r
+    xd, wd, bd, sd = x.cuda(), w.contiguous().cuda(), b.cuda(), slope.cuda()
+    rd = r.cuda() if res else None
+    y = torch.full(tuple(ref.shape), float("nan"), device="cuda")
+    _lib.check(L.ua2_conv1d_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(sd), _lib.ptr(rd), _lib.ptr(y), B, Cin, Cout, T, K, 1, dil, pl, pr,
+                                None))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(y).all())
+    tol = max(2e-5, 1.5 * (3 * Cin * K / 8) * 2.0 ** -24)  # fp32 class: 3xTF32 + the TMEM accumulator's round-toward-zero per k-step
+    err, scale = float((y.cpu() - ref).abs().max()), max(1.0, float(ref.abs().max()))
+    assert err < tol * scale, (err, tol, scale)

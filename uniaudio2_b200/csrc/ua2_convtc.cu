@@ -48,12 +48,14 @@ __global__ void conv_im2col_kernel(const float* __restrict__ x, float* __restric
   }
 }
 
-// y[b, co, t] = C[r][co] + bias[co] (+ res[b, co, t]) for rows r of the chunk; 32 x 32 tiles through shared memory
+// y[b, co, t] = act(C[r][co] + bias[co]) (+ res[b, co, t]) for rows r of the chunk, act = identity or a scalar nn.PReLU (ScalarModel);
+// 32 x 32 tiles through shared memory
 __global__ void conv_tc_epilogue_kernel(const float* __restrict__ C, const float* __restrict__ bias, const float* __restrict__ res,
-                                        float* __restrict__ y, int Cout, int T_out, long long m0, int rows) {
+                                        float* __restrict__ y, int Cout, int T_out, long long m0, int rows, const float* __restrict__ prelu) {
   __shared__ float tile[32][33];
   pdl_launch_dependents();
   pdl_wait();
+  const float slope = prelu ? prelu[0] : 1.f;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // read: threadIdx.x walks channels
     const int r = r0 + i, co = c0 + threadIdx.x;
@@ -67,6 +69,7 @@ __global__ void conv_tc_epilogue_kernel(const float* __restrict__ C, const float
       const int b = (int)(m / T_out), t = (int)(m - (long long)b * T_out);
       const size_t o = ((size_t)b * Cout + co) * T_out + t;
       float v = tile[threadIdx.x][i] + (bias ? bias[co] : 0.f);
+      if (v < 0.f) v *= slope;
       if (res) v += res[o];
       y[o] = v;
     }
@@ -172,10 +175,12 @@ int get_conv_tc() { return g_conv_tc; }
 // returns cudaErrorNotSupported when the layer is not served here (the caller continues on the SIMT core)
 cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y,
                              int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
-                             int replicate) {
+                             int replicate, const float* prelu) {
   const int KT = Cin * Ktaps;
   const long long M = (long long)B * T_out;
-  if (!tc_gemm_available() || !get_tc_gemm() || KT < 1024 || (KT & 3) || (Cout & 3) || M < 128) return cudaErrorNotSupported;
+  // reduction length: >= 1024, or a pointwise convolution of >= 256 channels (the "im2col" is then just the transpose to rows)
+  const bool long_k = KT >= 1024 || (Ktaps == 1 && KT >= 256 && M >= 1024);
+  if (!tc_gemm_available() || !get_tc_gemm() || !long_k || (KT & 3) || (Cout & 3) || M < 128 || (pre_elu && prelu)) return cudaErrorNotSupported;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(lc.stream, &cs);
   if (cs != cudaStreamCaptureStatusNone) return cudaErrorNotSupported;  // the scratch may have to grow
@@ -220,7 +225,7 @@ cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w
     if (e != cudaSuccess) return e;
     const float* src = raw ? raw : g_ws.c;
     if ((e = launch(lc, conv_tc_epilogue_kernel, dim3((rows + 31) / 32, (Cout + 31) / 32), dim3(32, 8), 0, src, bias, res, y, Cout, T_out, m0,
-                    rows)) != cudaSuccess)
+                    rows, prelu)) != cudaSuccess)
       return e;
   }
   return cudaSuccess;

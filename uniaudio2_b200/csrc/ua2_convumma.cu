@@ -38,15 +38,16 @@ struct ConvUmmaParams {
   const float* bias;
   const float* res;
   float* y;
+  const float* prelu;  // scalar nn.PReLU slope applied after the bias and before the residual add (ScalarModel: activation(conv(x)), scalar24k.py:139-150) or nullptr
   int B, Cin, Cout, T_in, T_out, Ktaps, stride, pad_left, pre_elu;
-  int tap_step;     // +1 convolution (tap k reads t * stride + k - pad_left), -1 transposed convolution (tap k reads j - k)
+  int tap_step;     // dilation d of a convolution (tap k reads t * stride + k * d - pad_left), -1 transposed convolution (tap k reads j - k)
   int T_pos;        // positions (GEMM rows) per batch element: T_out, or the input grid Tj of a transposed convolution
   int tr_stride;    // 0 = convolution; s = transposed convolution: GEMM column n0 + c = phase * Cout + channel -> y[b, ch, j * s + phase - crop]
   int tr_crop;
   int n0;           // first GEMM column (weight row) of this launch; n_cols of them are valid
   int n_cols;
-  int KB;           // k-blocks of 32: Ktaps * Cin / 32
-  int cb_per_tap;   // Cin / 32
+  int KB;           // k-blocks of 32: Ktaps * cb_per_tap
+  int cb_per_tap;   // ceil(Cin / 32): the last channel block of a tap is zero-padded when Cin % 32 != 0 (weights and activations)
   int tiles_per_b;  // ceil(T_pos / 128)
   int n_tiles;
   int n_stages;     // weight ring stages
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
       const int t_in = t_pos * p.stride + c.tap * p.tap_step - p.pad_left;
       const bool ok = t_pos < p.T_pos && t_in >= 0 && t_in < p.T_in;
       const float* src = p.x + ((size_t)c.b * p.Cin + c.cb * 32) * p.T_in + (ok ? t_in : 0);
+      const int nch = p.Cin - c.cb * 32;  // valid channels of this block (>= 32 except in a padded last block)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = ok ? __ldg(src + (size_t)i * p.T_in) : 0.f;
+      for (int i = 0; i < 32; ++i) v[i] = (ok && i < nch) ? __ldg(src + (size_t)i * p.T_in) : 0.f;
     };
     float v[32], vn[32];
     Cur cn = cur_init((uint32_t)grp);
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
         int co;
         const bool ok = where(rw, c0 + i, idx, co);
         float a = (ok && p.bias) ? __ldg(p.bias + co) : 0.f;
-        if (ok && p.res) a += __ldg(p.res + idx);
+        if (ok && p.res && !p.prelu) a += __ldg(p.res + idx);  // with a PReLU the residual is added after the activation (below)
         add[i] = a;
       }
     };
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
     // 4.46 ms for 128 -> 64 at batch 16 x 10 s, 88 us per tile, all of it in these four warps).
     const bool fast_tr = p.tr_stride == 4 && p.tr_crop == 0 && p.res == nullptr && p.n0 == 0 && p.n_cols == 4 * p.Cout && (p.Cout % 16) == 0 &&
                          (p.T_out % 4) == 0 && 4 * p.Cout <= NO;
+    const float slope = p.prelu ? __ldg(p.prelu) : 1.f;
     float add_next[32];
     Row row_next{};
     if (my_tiles > 0) {
@@ -351,7 +354,14 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
         for (int i = 0; i < 32; ++i) {
           size_t idx;
           int co;
-          if (where(rw, c0 + i, idx, co)) p.y[idx] = __uint_as_float(v[i]) + add[i];
+          if (where(rw, c0 + i, idx, co)) {
+            float o = __uint_as_float(v[i]) + add[i];
+            if (p.prelu) {
+              o = o > 0.f ? o : o * slope;
+              if (p.res) o += __ldg(p.res + idx);
+            }
+            p.y[idx] = o;
+          }
         }
       }
       tc_fence_before();
@@ -367,16 +377,16 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
   }
 }
 
-// torch Conv1d weight (Cout, Cin, Ktaps) -> [2][Cout][tap * Cin + ci] hi / lo tf32 planes
-__global__ void conv_umma_repack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int Ktaps) {
+// torch Conv1d weight (Cout, Cin, Ktaps) -> [2][Cout][tap * CinP + ci] hi / lo tf32 planes, CinP = Cin rounded up to 32 (zero columns)
+__global__ void conv_umma_repack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int CinP, int Ktaps) {
   pdl_launch_dependents();
   pdl_wait();
-  const int KT = Cin * Ktaps;
+  const int KT = CinP * Ktaps;
   const long long n = (long long)Cout * KT;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i / KT), k = (int)(i - (long long)co * KT);
-    const int tap = k / Cin, ci = k - tap * Cin;
-    const float v = w[((size_t)co * Cin + ci) * Ktaps + tap];
+    const int tap = k / CinP, ci = k - tap * CinP;
+    const float v = ci < Cin ? w[((size_t)co * Cin + ci) * Ktaps + tap] : 0.f;
     const uint32_t h = tf32_rna_bits(v);
     wp[i] = __uint_as_float(h);
     wp[n + i] = __uint_as_float(tf32_rna_bits(v - __uint_as_float(h)));
@@ -469,23 +479,34 @@ int get_conv_umma() { return g_conv_umma; }
 // cudaErrorNotSupported when the layer is not served here (the caller continues on its other paths)
 cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y, int B,
                                int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
-                               int replicate) {
-  if (!g_conv_umma || dilation != 1 || replicate || (Cin & 31) || Cout < 16 || Cout > 256 || (long long)B * T_out < 4 * CU_BM) return cudaErrorNotSupported;
+                               int replicate, const float* prelu) {
+  if (!g_conv_umma || dilation < 1 || replicate || (Cin & 15) || Cin < 32 || Cout < 16 || (long long)B * T_out < 4 * CU_BM) return cudaErrorNotSupported;
+  if (pre_elu && prelu) return cudaErrorNotSupported;
   // pointwise convolutions with fewer than 4 k-blocks per tile are all epilogue (measured at batch 16 x 10 s: 32 -> 64 at 24 kHz 3.0 ms
   // here against 1.6 ms on the fp32 register-tiled core, 64 -> 128 at 6 kHz 2.6 against 2.2): they stay on the SIMT core
   if (Ktaps == 1 && Cin < 128) return cudaErrorNotSupported;
-  const long long KT = (long long)Cin * Ktaps;
+  const int CinP = (Cin + 31) / 32 * 32;
+  const long long KT = (long long)CinP * Ktaps;
   if (KT > (1 << 20)) return cudaErrorNotSupported;
+  const int tiles_per_b = (T_out + CU_BM - 1) / CU_BM;
+  const long long n_tiles = (long long)B * tiles_per_b;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // few positions and a long reduction (the low-rate stages): one tile per SM leaves most SMs idle and every column chunk gathers the
+  // activations again - the materialised-im2col GEMM (ua2_convtc.cu) spreads the same work over all SMs by stream-K
+  if (Cout > 256 && n_tiles * 2 < sms && KT >= 256) return cudaErrorNotSupported;
+  if (Ktaps == 1 && Cin >= 256 && Cout > 256) return cudaErrorNotSupported;  // a plain GEMM: transpose to rows + the linears' kernel (ua2_convtc.cu)
   cudaError_t e = reserve_wp(lc, (size_t)2 * Cout * KT);
   if (e != cudaSuccess) return e;
   e = launch(lc, conv_umma_repack_kernel, dim3((unsigned)std::min<long long>((Cout * KT + 255) / 256, 148 * 8)), dim3(256), 0, w_torch, g_cu.wp, Cout,
-             Cin, Ktaps);
+             Cin, CinP, Ktaps);
   if (e != cudaSuccess) return e;
   ConvUmmaParams p{};
   p.x = x;
   p.bias = bias;
   p.res = res;
   p.y = y;
+  p.prelu = prelu;
   p.B = B;
   p.Cin = Cin;
   p.Cout = Cout;
@@ -495,17 +516,19 @@ cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float*
   p.stride = stride;
   p.pad_left = pad_left;
   p.pre_elu = pre_elu;
-  p.tap_step = 1;
+  p.tap_step = dilation;
   p.T_pos = T_out;
-  p.n0 = 0;
-  p.n_cols = Cout;
   p.KB = (int)(KT / 32);
-  p.cb_per_tap = Cin / 32;
-  p.tiles_per_b = (T_out + CU_BM - 1) / CU_BM;
-  const long long n_tiles = (long long)B * p.tiles_per_b;
+  p.cb_per_tap = CinP / 32;
+  p.tiles_per_b = tiles_per_b;
   if (n_tiles * p.KB >= (1LL << 31)) return cudaErrorNotSupported;
   p.n_tiles = (int)n_tiles;
-  return launch_cols(lc, p, (int)KT, Cout);
+  for (int n0 = 0; n0 < Cout; n0 += 256) {  // 256 output channels per launch (a wider layer gathers its activations once per chunk)
+    p.n0 = n0;
+    p.n_cols = std::min(256, Cout - n0);
+    if ((e = launch_cols(lc, p, (int)KT, Cout)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 // Transposed convolution with kernel = 2 * stride (modules/conv.py:306-329) over the per-phase weights of launch_convtr1d_gemm:

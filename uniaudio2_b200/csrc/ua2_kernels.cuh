@@ -128,14 +128,14 @@ cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float*
 // wide convolutions (Cin * Ktaps >= 1024) as im2col + tcgen05 3xTF32 GEMM (ua2_convtc.cu; option "conv_tc", default 0)
 cudaError_t launch_conv1d_tc(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y,
                              int B, int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
-                             int replicate);
+                             int replicate, const float* prelu = nullptr);
 cudaError_t launch_convtr1d_tc(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin,
                                int Cout, int T_in, int stride, int pre_elu, int crop_left, int T_out);
 // narrow / strided causal convolutions (Cin % 32 == 0, 16 <= Cout <= 256) as an implicit GEMM on tcgen05 with the activations going
 // global -> registers -> tensor memory (ua2_convumma.cu; option "conv_umma", default 1)
 cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float* w_torch, const float* bias, const float* res, float* y, int B,
                                int Cin, int Cout, int T_in, int T_out, int Ktaps, int stride, int dilation, int pad_left, int pre_elu,
-                               int replicate);
+                               int replicate, const float* prelu = nullptr);
 cudaError_t launch_convtr1d_umma(const LaunchCtx& lc, const float* x, const float* w_phase, const float* bias, float* y, int B, int Cin, int Cout,
                                  int T_in, int stride, int pre_elu, int crop_left, int T_out);
 void set_conv_pointwise(int v);

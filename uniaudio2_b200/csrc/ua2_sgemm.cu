@@ -570,10 +570,10 @@ __global__ void __launch_bounds__(256) conv1d_cin1_kernel(const float* __restric
 // 16-32 FLOP per byte of activations: a streaming kernel.  Thread = one position (all loads and stores coalesced along t), 64 output
 // channels in registers, the (Cin x 64) weight slice in shared memory read as broadcast float4.  As an implicit GEMM with K = 32 the
 // tiled core spent its time on tile overhead (2.98 ms for 32 -> 64 at batch 16 x 10 s; 2.46 GB of traffic = 0.38 ms at the HBM peak).
-constexpr int PW_CO = 64;
+template <int PW_CO>  // output channels per CTA: 64, 48 (the 48 / 96-channel stages of ScalarModel) or 32
 __global__ void __launch_bounds__(256, 2) conv1d_pointwise_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                                const float* __restrict__ res, float* __restrict__ y, int Cin, int Cout, int T,
-                                                               int pre_elu) {
+                                                               int pre_elu, const float* __restrict__ prelu) {
   extern __shared__ __align__(16) float pw_ws[];  // [Cin][PW_CO]
   pdl_launch_dependents();
   const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.y * PW_CO, t = blockIdx.x * 256 + tid;
@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(256, 2) conv1d_pointwise_kernel(const float* _
   pdl_wait();
   __syncthreads();
   if (t >= T) return;
+  const float slope = prelu ? __ldg(prelu) : 1.f;  // scalar nn.PReLU after the bias, before the skip add (ScalarModel: activation2(conv2(.)) + x, scalar24k.py:139-150)
   float acc[PW_CO];
 #pragma unroll
   for (int c = 0; c < PW_CO; ++c) acc[c] = bias ? bias[co0 + c] : 0.f;
@@ -611,6 +612,7 @@ __global__ void __launch_bounds__(256, 2) conv1d_pointwise_kernel(const float* _
 #pragma unroll
   for (int c = 0; c < PW_CO; ++c) {
     float r = acc[c];
+    if (r < 0.f) r *= slope;
     if (res) r += res[o + (size_t)c * T];
     y[o + (size_t)c * T] = r;
   }
@@ -625,18 +627,28 @@ cudaError_t launch_conv1d_gemm(const LaunchCtx& lc, const float* x, const float*
     if (Cin == 1 && Cout > 1 && (size_t)Cout * (Ktaps + 1) * 4 <= 40 * 1024)
       return launch(lc, conv1d_cin1_kernel, grid, dim3(256), (size_t)Cout * (Ktaps + 1) * 4, x, w_torch, bias, y, Cout, T_in, Ktaps, pad_left, pre_elu);
   }
-  if (prelu == nullptr && Ktaps == 1 && stride == 1 && !replicate && T_out == T_in && Cin <= 128 && (Cin % 32) == 0 && (Cout % PW_CO) == 0 && B <= 65535 &&
-      Cout / PW_CO <= 65535 && get_conv_pointwise())
-    return launch(lc, conv1d_pointwise_kernel, dim3((T_out + 255) / 256, Cout / PW_CO, B), dim3(256), (size_t)Cin * PW_CO * 4, x, w_torch, bias, res, y,
-                  Cin, Cout, T_in, pre_elu);
-  if (prelu == nullptr) {  // option "conv_umma" (default 1): implicit GEMM on tcgen05 straight from (B, C, T), ua2_convumma.cu
+  if (!(pre_elu && prelu) && Ktaps == 1 && stride == 1 && !replicate && T_out == T_in && pad_left == 0 && Cin <= 128 && (Cin % 16) == 0 && B <= 65535 &&
+      get_conv_pointwise()) {
+    const dim3 blk(256);
+    const unsigned gx = (unsigned)((T_out + 255) / 256);
+    if ((Cout % 64) == 0)
+      return launch(lc, conv1d_pointwise_kernel<64>, dim3(gx, Cout / 64, B), blk, (size_t)Cin * 64 * 4, x, w_torch, bias, res, y, Cin, Cout, T_in, pre_elu,
+                    prelu);
+    if ((Cout % 48) == 0)
+      return launch(lc, conv1d_pointwise_kernel<48>, dim3(gx, Cout / 48, B), blk, (size_t)Cin * 48 * 4, x, w_torch, bias, res, y, Cin, Cout, T_in, pre_elu,
+                    prelu);
+    if ((Cout % 32) == 0)
+      return launch(lc, conv1d_pointwise_kernel<32>, dim3(gx, Cout / 32, B), blk, (size_t)Cin * 32 * 4, x, w_torch, bias, res, y, Cin, Cout, T_in, pre_elu,
+                    prelu);
+  }
+  {  // option "conv_umma" (default 1): implicit GEMM on tcgen05 straight from (B, C, T), ua2_convumma.cu
     const cudaError_t e = launch_conv1d_umma(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
-                                             replicate);
+                                             replicate, prelu);
     if (e != cudaErrorNotSupported) return e;
   }
-  if (get_conv_tc() && prelu == nullptr) {  // option "conv_tc" (default 1): wide layers as im2col + tensor-core GEMM, ua2_convtc.cu
+  if (get_conv_tc()) {  // option "conv_tc" (default 1): wide layers as im2col + tensor-core GEMM, ua2_convtc.cu
     const cudaError_t e = launch_conv1d_tc(lc, x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu,
-                                           replicate);
+                                           replicate, prelu);
     if (e != cudaErrorNotSupported) return e;
   }
   ConvGemmParams p{x, w_torch, bias, res, y, B, Cin, Cout, T_in, T_out, Ktaps, stride, dilation, pad_left, pre_elu, replicate, 1, 0, T_out,
