@@ -33,6 +33,7 @@ cudaError_t launch_tc_linear(const LaunchCtx&, int pro, int epi, const GemvParam
 // takes the fp32 SIMT / conv_tc kernels that the shim can run
 int get_conv_umma() { return 0; }
 void set_conv_umma(int) {}
+void set_conv_umma_staged(int) {}
 cudaError_t launch_conv1d_umma(const LaunchCtx&, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int,
                                int, int, int, int, const float*) {
   return cudaErrorNotSupported;

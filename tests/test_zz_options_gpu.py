@@ -519,6 +519,9 @@ def test_convtr_umma_option_matches_oracle(B, Cin, Cout, T, stride):
     (1, 768, 768, 300, 7, 1, 1, 0),    # few positions, long reduction: materialised im2col + stream-K GEMM
     (1, 384, 384, 3000, 1, 1, 1, 1),   # pointwise with 384 channels + skip
     (1, 136, 1536, 500, 5, 1, 0, 0),   # the delay convolution of the decoder (Cin 136: not a multiple of 16 -> fp32 SIMT core)
+    (3, 64, 32, 1000, 3, 1, 1, 1),     # several batch elements, tile tails (1000 = 7 x 128 + 104), residual
+    (1, 32, 64, 516, 7, 9, 0, 0),      # widest halo (54 samples) on both sides of a short sequence
+    (2, 64, 64, 1028, 2, 1, 1, 0),     # two taps: every splitter group owns exactly one tap per stage
 ])
 def test_scalar_model_convs_on_tensor_cores(B, Cin, Cout, T, K, dil, causal, res):
     import math
@@ -541,11 +544,16 @@ def test_scalar_model_convs_on_tensor_cores(B, Cin, Cout, T, K, dil, causal, res
         ref = ref + r
     xd, wd, bd, sd = x.cuda(), w.contiguous().cuda(), b.cuda(), slope.cuda()
     rd = r.cuda() if res else None
-    y = torch.full(tuple(ref.shape), float("nan"), device="cuda")
-    _lib.check(L.ua2_conv1d_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(sd), _lib.ptr(rd), _lib.ptr(y), B, Cin, Cout, T, K, 1, dil, pl, pr,
-                                None))
-    torch.cuda.synchronize()
-    assert bool(torch.isfinite(y).all())
     tol = max(2e-5, 1.5 * (3 * Cin * K / 8) * 2.0 ** -24)  # fp32 class: 3xTF32 + the TMEM accumulator's round-toward-zero per k-step
-    err, scale = float((y.cpu() - ref).abs().max()), max(1.0, float(ref.abs().max()))
-    assert err < tol * scale, (err, tol, scale)
+    try:
+        for staged in (1, 0):  # activations through the TMA-staged shared-memory ring (default) / gathered into registers
+            _lib.check(L.ua2_set_global_option(b"conv_umma_staged", staged))
+            y = torch.full(tuple(ref.shape), float("nan"), device="cuda")
+            _lib.check(L.ua2_conv1d_f32(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(sd), _lib.ptr(rd), _lib.ptr(y), B, Cin, Cout, T, K, 1, dil, pl,
+                                        pr, None))
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(y).all())
+            err, scale = float((y.cpu() - ref).abs().max()), max(1.0, float(ref.abs().max()))
+            assert err < tol * scale, (staged, err, tol, scale)
+    finally:
+        _lib.check(L.ua2_set_global_option(b"conv_umma_staged", 1))

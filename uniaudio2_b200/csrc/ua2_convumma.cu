@@ -28,8 +28,10 @@ namespace {
 using namespace tc;
 
 constexpr int CU_BM = 128;       // output positions per tile
-constexpr int CU_A_SLOTS = 4;    // TMEM A ring (64 columns per slot)
-constexpr int CU_ACC_COL = 256;  // accumulators: columns [256, 256 + NO) and, double-buffered, [384, 384 + NO)
+constexpr int CU_A_SLOTS = 6;    // capacity of the TMEM A ring's barrier arrays (64 columns per slot); a kernel uses A_SLOTS of them:
+                                 // NO <= 64: 6 slots, accumulators at columns 384 (+ 64); NO >= 128: 4 slots, accumulators at 256 (+ 128).
+                                 // (ncu, 64 -> 32 k 3 at 24 kHz: with 4 slots the splitter warps spent half their time waiting for a free
+                                 // slot while the MMA warp spun on `slot full` - two slots per splitter group do not absorb the jitter)
 constexpr int CU_MAX_STAGES = 24;
 constexpr int CU_THREADS = 512;
 
@@ -52,6 +54,14 @@ struct ConvUmmaParams {
   int n_tiles;
   int n_stages;     // weight ring stages
   int resident;     // KB <= n_stages: every k-block is loaded once and stays
+  // stride-1 convolutions with T_in % 4 == 0: the 128 + (Ktaps - 1) * dilation samples x 32 channels that a (tile, channel block)
+  // needs come by TMA (boxes of 32 samples x 32 channels, SWIZZLE_128B) into a shared-memory ring and serve all taps from there
+  // (k-block order: channel block, then tap; the weight planes are repacked in that order); 0 = the register gather (strided /
+  // transposed / odd lengths)
+  int staged;
+  int xw;           // 32-sample boxes per activation stage (4 KB each)
+  int x_shift;      // 0..3: a stage starts x_shift samples LEFT of t0 - pad_left, so that every box starts on a 16-byte boundary of the row
+  int n_xstages;
 };
 
 // ELU with the SFU exponential: exp(v) - 1 = ex2(v * log2 e) - 1 for v <= 0.  Absolute error ~1e-7 (the library expm1f of the fp32
@@ -62,21 +72,31 @@ __device__ __forceinline__ float elu_fast(float v) {
   return v > 0.f ? v : e - 1.f;
 }
 
+constexpr int CU_X_STAGES = 4;
+
 template <int NO>
-__global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmW, const ConvUmmaParams p) {
+__global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                                                                 const ConvUmmaParams p) {
   constexpr int STAGE_BYTES = 2 * NO * 128;  // hi tile then lo tile, NO rows of 128 bytes each
   constexpr int NACC = NO <= 128 ? 2 : 1;
+  constexpr int A_SLOTS = NO <= 64 ? 6 : 4;
+  constexpr int CU_ACC_COL = A_SLOTS * 64;
+  constexpr int ACC_STRIDE = NO <= 64 ? 64 : 128;
   extern __shared__ uint8_t cu_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(cu_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* w_ring = base;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + (size_t)p.n_stages * STAGE_BYTES);
+  uint8_t* x_ring = w_ring + (size_t)p.n_stages * STAGE_BYTES;  // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
+  const uint32_t x_bytes = (uint32_t)p.xw * 4096u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + (size_t)p.n_xstages * x_bytes);
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + CU_MAX_STAGES;
   uint64_t* a_full = w_empty + CU_MAX_STAGES;
   uint64_t* a_empty = a_full + CU_A_SLOTS;
   uint64_t* acc_full = a_empty + CU_A_SLOTS;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* x_full = acc_empty + 2;
+  uint64_t* x_empty = x_full + CU_X_STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_empty + CU_X_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -95,6 +115,11 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
       smem_bar_init(&acc_full[i], 1);
       smem_bar_init(&acc_empty[i], 4);
     }
+    for (int i = 0; i < CU_X_STAGES; ++i) {
+      smem_bar_init(&x_full[i], 1);
+      smem_bar_init(&x_empty[i], 8);  // every splitter warp is done with the stage
+    }
+    if (p.staged) tma_prefetch_desc(&tmX);
     smem_bar_fence_init();
   }
   if (warp == 1) {
@@ -131,11 +156,11 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
       const uint32_t use = NACC == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;  // how often this accumulator has been used before
       smem_bar_wait(&acc_empty[ab], (use & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem + CU_ACC_COL + ab * 128;
+      const uint32_t d_tmem = tmem + CU_ACC_COL + ab * ACC_STRIDE;
       for (int kb = 0; kb < p.KB; ++kb, ++it) {
         const uint32_t sw = p.resident ? (uint32_t)kb : it % (uint32_t)p.n_stages;
         const uint32_t pw = p.resident ? 0u : (it / (uint32_t)p.n_stages) & 1;
-        const uint32_t sa = it % CU_A_SLOTS, pa = (it / CU_A_SLOTS) & 1;
+        const uint32_t sa = it % A_SLOTS, pa = (it / A_SLOTS) & 1;
         smem_bar_wait(&w_full[sw], pw);
         smem_bar_wait(&a_full[sa], pa);
         tc_fence_after();
@@ -154,6 +179,84 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
           if (kb + 1 == p.KB) tc_commit(&acc_full[ab]);
         }
         __syncwarp();
+      }
+    }
+  } else if (warp == 2 && p.staged) {
+    // ================= activation producer (staged mode): 32 channels x (128 + halo) samples per (tile, channel block) as boxes of 32
+    // samples; samples left of 0 / right of T_in arrive as zeros = the convolution's zero padding
+    pdl_wait();  // x comes from the preceding kernel
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.cb_per_tap;
+    int j = 0, cb = 0;
+    for (uint32_t n = 0; n < total; ++n) {
+      const uint32_t xs = n % (uint32_t)p.n_xstages, ph = (n / (uint32_t)p.n_xstages) & 1;
+      smem_bar_wait(&x_empty[xs], ph ^ 1);
+      const int tile = cta + j * G;
+      const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * CU_BM;
+      if (elect_one()) {
+        smem_bar_arrive_expect_tx(&x_full[xs], x_bytes);
+        for (int k = 0; k < p.xw; ++k)
+          tma_load_2d(x_ring + (size_t)xs * x_bytes + (size_t)k * 4096, &tmX, t0 - p.pad_left - p.x_shift + 32 * k, b * p.Cin + cb * 32,
+                      &x_full[xs], POLICY_EVICT_FIRST);
+      }
+      __syncwarp();
+      if (++cb == p.cb_per_tap) {
+        cb = 0;
+        ++j;
+      }
+    }
+  } else if (warp >= 4 && warp < 12 && p.staged) {
+    // ================= splitters (staged mode): thread = output position; tap k of a channel block reads column r + k * dilation of
+    // the block's shared-memory stage (consecutive lanes, consecutive words: conflict-free), activates, splits hi / lo -> TMEM
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t n_it = (uint32_t)my_tiles * (uint32_t)p.KB;
+    uint32_t it = (uint32_t)grp;
+    int jt = (int)(it / (uint32_t)p.KB);
+    int kb0 = (int)(it - (uint32_t)jt * (uint32_t)p.KB);
+    int cb = kb0 / p.Ktaps, tap = kb0 - cb * p.Ktaps;
+    for (; it < n_it; it += 2) {
+      const uint32_t n = (uint32_t)jt * (uint32_t)p.cb_per_tap + (uint32_t)cb;
+      const uint32_t xs = n % (uint32_t)p.n_xstages, xph = (n / (uint32_t)p.n_xstages) & 1;
+      smem_bar_wait(&x_full[xs], xph);
+      // sample c = r + tap * dilation of the stage: box c / 32, row = channel i (128 bytes), 16-byte chunk ((c % 32) / 4) ^ (i % 8)
+      const int c = r + tap * p.tap_step + p.x_shift;
+      const uint8_t* xb = x_ring + (size_t)xs * x_bytes + (size_t)(c >> 5) * 4096 + (c & 3) * 4;
+      const int cq = (c & 31) >> 2;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = *reinterpret_cast<const float*>(xb + i * 128 + ((cq ^ (i & 7)) << 4));
+      const uint32_t sa = it % A_SLOTS, pa = (it / A_SLOTS) & 1;
+      smem_bar_wait(&a_empty[sa], pa ^ 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + sa * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float f = p.pre_elu ? elu_fast(v[half * 16 + i]) : v[half * 16 + i];
+          const uint32_t h = tf32_rna_bits(f);
+          hi[i] = h;
+          lo[i] = tf32_rna_bits(f - __uint_as_float(h));
+        }
+        tmem_st16(taddr + half * 16, hi);
+        tmem_st16(taddr + 32 + half * 16, lo);
+      }
+      tmem_wait_st();  // the stores carry the loaded values: the stage has been read when they are done
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        bar_arrive(&a_full[sa]);
+        if (tap + 2 >= p.Ktaps) bar_arrive(&x_empty[xs]);  // this warp's last tap of the stage (Ktaps >= 2: both groups have one)
+      }
+      tap += 2;
+      while (tap >= p.Ktaps) {
+        tap -= p.Ktaps;
+        if (++cb == p.cb_per_tap) {
+          cb = 0;
+          ++jt;
+        }
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -218,7 +321,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
         cur_step2(cn);
         gather(cn, vn);
       }
-      const uint32_t sa = it % CU_A_SLOTS, pa = (it / CU_A_SLOTS) & 1;
+      const uint32_t sa = it % A_SLOTS, pa = (it / A_SLOTS) & 1;
       smem_bar_wait(&a_empty[sa], pa ^ 1);
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + sa * 64;
@@ -311,7 +414,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
       smem_bar_wait(&acc_full[ab], use & 1);
       tc_fence_after();
       if (fast_tr) {
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * 128;
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * ACC_STRIDE;
         const int t4 = rw.t_pos * 4;
         const bool ok = rw.ok && t4 + 3 < p.T_out;
 #pragma unroll 1
@@ -348,7 +451,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
         else if (j + 1 < my_tiles)
           load_add(row_next, 0, add_next);
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * 128 + c0, v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * ACC_STRIDE + c0, v);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -377,15 +480,25 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
   }
 }
 
-// torch Conv1d weight (Cout, Cin, Ktaps) -> [2][Cout][tap * CinP + ci] hi / lo tf32 planes, CinP = Cin rounded up to 32 (zero columns)
-__global__ void conv_umma_repack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int CinP, int Ktaps) {
+// torch Conv1d weight (Cout, Cin, Ktaps) -> [2][Cout][KT] hi / lo tf32 planes, CinP = Cin rounded up to 32 (zero columns); column
+// order tap * CinP + ci (register-gather mode) or, cb_major, (ci / 32 * Ktaps + tap) * 32 + ci % 32 (staged mode: all taps of a
+// 32-channel block are consecutive k-blocks)
+__global__ void conv_umma_repack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int CinP, int Ktaps, int cb_major) {
   pdl_launch_dependents();
   pdl_wait();
   const int KT = CinP * Ktaps;
   const long long n = (long long)Cout * KT;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i / KT), k = (int)(i - (long long)co * KT);
-    const int tap = k / CinP, ci = k - tap * CinP;
+    int tap, ci;
+    if (cb_major) {
+      const int blk = k >> 5, cbk = blk / Ktaps;
+      tap = blk - cbk * Ktaps;
+      ci = cbk * 32 + (k & 31);
+    } else {
+      tap = k / CinP;
+      ci = k - tap * CinP;
+    }
     const float v = ci < Cin ? w[((size_t)co * Cin + ci) * Ktaps + tap] : 0.f;
     const uint32_t h = tf32_rna_bits(v);
     wp[i] = __uint_as_float(h);
@@ -414,6 +527,7 @@ struct ConvUmmaScratch {
 };
 ConvUmmaScratch g_cu;
 int g_conv_umma = 1;
+int g_conv_umma_staged = 1;  // option "conv_umma_staged": measurement switch of the TMA-staged activation path
 
 cudaError_t reserve_wp(const LaunchCtx& lc, size_t need) {
   if (need <= g_cu.floats) return cudaSuccess;
@@ -435,9 +549,16 @@ cudaError_t reserve_wp(const LaunchCtx& lc, size_t need) {
 }
 
 template <int NO>
-cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, ConvUmmaParams p) {
+cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, const CUtensorMap& tmX, ConvUmmaParams p) {
   constexpr int STAGE_BYTES = 2 * NO * 128;
-  int stages = std::min(CU_MAX_STAGES, (int)((200 * 1024) / STAGE_BYTES));
+  size_t x_ring = 0;
+  if (p.staged) {  // activation ring first (2-4 stages), the weights get the rest
+    const size_t xb = (size_t)p.xw * 4096;
+    p.n_xstages = (int)std::min<size_t>(CU_X_STAGES, std::max<size_t>(2, (72 * 1024) / xb));
+    x_ring = p.n_xstages * xb;
+    if (x_ring + 2 * STAGE_BYTES > 200 * 1024) return cudaErrorNotSupported;
+  }
+  int stages = std::min(CU_MAX_STAGES, (int)((200 * 1024 - x_ring) / STAGE_BYTES));
   if (p.KB <= stages) {
     stages = p.KB;
     p.resident = 1;
@@ -446,7 +567,7 @@ cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, ConvUmmaParam
     p.resident = 0;
   }
   p.n_stages = stages;
-  const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + (2 * CU_MAX_STAGES + 2 * CU_A_SLOTS + 4) * 8 + 16;
+  const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + x_ring + (2 * CU_MAX_STAGES + 2 * CU_A_SLOTS + 4 + 2 * CU_X_STAGES) * 8 + 16;
   static DeviceOnce attr;
   if (attr.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
@@ -455,25 +576,28 @@ cudaError_t launch_no(const LaunchCtx& lc, const CUtensorMap& tmW, ConvUmmaParam
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(p.n_tiles, sms);
-  return launch(lc, conv_umma_kernel<NO>, dim3(grid), dim3(CU_THREADS), smem, tmW, p);
+  return launch(lc, conv_umma_kernel<NO>, dim3(grid), dim3(CU_THREADS), smem, tmW, tmX, p);
 }
 
 // columns [n0, n0 + n_cols) of a GEMM whose weight planes hold `rows_total` rows
 cudaError_t launch_cols(const LaunchCtx& lc, ConvUmmaParams p, int KT, int rows_total) {
   const int NO = p.n_cols <= 32 ? 32 : p.n_cols <= 64 ? 64 : p.n_cols <= 128 ? 128 : 256;
-  CUtensorMap tmW;
+  CUtensorMap tmW, tmX;
   if (!make_tmap(&tmW, g_cu.wp, KT, rows_total, 2, NO, false)) return cudaErrorNotSupported;
+  tmX = tmW;  // unused unless staged
+  if (p.staged && !make_tmap(&tmX, p.x, p.T_in, (long long)p.B * p.Cin, 1, 32, false)) return cudaErrorNotSupported;
   switch (NO) {
-    case 32: return launch_no<32>(lc, tmW, p);
-    case 64: return launch_no<64>(lc, tmW, p);
-    case 128: return launch_no<128>(lc, tmW, p);
-    default: return launch_no<256>(lc, tmW, p);
+    case 32: return launch_no<32>(lc, tmW, tmX, p);
+    case 64: return launch_no<64>(lc, tmW, tmX, p);
+    case 128: return launch_no<128>(lc, tmW, tmX, p);
+    default: return launch_no<256>(lc, tmW, tmX, p);
   }
 }
 
 }  // namespace
 
 void set_conv_umma(int v) { g_conv_umma = v ? 1 : 0; }
+void set_conv_umma_staged(int v) { g_conv_umma_staged = v ? 1 : 0; }
 int get_conv_umma() { return g_conv_umma; }
 
 // cudaErrorNotSupported when the layer is not served here (the caller continues on its other paths)
@@ -496,10 +620,16 @@ cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float*
   // activations again - the materialised-im2col GEMM (ua2_convtc.cu) spreads the same work over all SMs by stream-K
   if (Cout > 256 && n_tiles * 2 < sms && KT >= 256) return cudaErrorNotSupported;
   if (Ktaps == 1 && Cin >= 256 && Cout > 256) return cudaErrorNotSupported;  // a plain GEMM: transpose to rows + the linears' kernel (ua2_convtc.cu)
+  // stride 1 and a row pitch TMA can address: activations staged in shared memory once per (tile, channel block) for all taps
+  const int halo = (Ktaps - 1) * dilation;
+  const int x_shift = (4 - (pad_left & 3)) & 3;  // TMA needs the first sample of a box on a 16-byte boundary: t0 - pad_left - x_shift is a multiple of 4
+  const int xw = (CU_BM + halo + x_shift + 31) / 32;  // boxes of 32 samples
+  const bool staged = g_conv_umma_staged && stride == 1 && Ktaps >= 2 && (T_in & 3) == 0 && xw <= 8 &&
+                      (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   cudaError_t e = reserve_wp(lc, (size_t)2 * Cout * KT);
   if (e != cudaSuccess) return e;
   e = launch(lc, conv_umma_repack_kernel, dim3((unsigned)std::min<long long>((Cout * KT + 255) / 256, 148 * 8)), dim3(256), 0, w_torch, g_cu.wp, Cout,
-             Cin, CinP, Ktaps);
+             Cin, CinP, Ktaps, staged ? 1 : 0);
   if (e != cudaSuccess) return e;
   ConvUmmaParams p{};
   p.x = x;
@@ -517,6 +647,9 @@ cudaError_t launch_conv1d_umma(const LaunchCtx& lc, const float* x, const float*
   p.pad_left = pad_left;
   p.pre_elu = pre_elu;
   p.tap_step = dilation;
+  p.staged = staged ? 1 : 0;
+  p.xw = xw;
+  p.x_shift = x_shift;
   p.T_pos = T_out;
   p.KB = (int)(KT / 32);
   p.cb_per_tap = CinP / 32;

@@ -141,6 +141,7 @@ cudaError_t launch_convtr1d_umma(const LaunchCtx& lc, const float* x, const floa
 void set_conv_pointwise(int v);
 int get_conv_pointwise();
 void set_conv_umma(int v);
+void set_conv_umma_staged(int v);
 int get_conv_umma();
 // fused SEANet residual block for the 64-channel / 24 kHz stages (ua2_resblock.cu; option "resblock_fused", default 0)
 cudaError_t launch_resblock_fused(const LaunchCtx& lc, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -50,6 +50,10 @@ int ua2_set_global_option(const char* name, int value) {
     set_attn_ring(value);
     return UA2_OK;
   }
+  if (std::string(name) == "conv_umma_staged") {
+    set_conv_umma_staged(value);
+    return UA2_OK;
+  }
   if (std::string(name) == "conv_pointwise") {
     set_conv_pointwise(value);
     return UA2_OK;
