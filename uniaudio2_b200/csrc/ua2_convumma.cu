@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
     Row row_next{};
     if (my_tiles > 0) {
       row_next = row_of(0);
-      if (!fast_tr) load_add(row_next, 0, add_next);
+      if (!fast_tr && p.tr_stride) load_add(row_next, 0, add_next);
     }
     for (int j = 0; j < my_tiles; ++j) {
       const int ab = NACC == 2 ? (j & 1) : 0;
@@ -432,6 +432,49 @@ __global__ void __launch_bounds__(CU_THREADS, 1) conv_umma_kernel(const __grid_c
               const float bv = p.bias ? __ldg(p.bias + ch0 + i) : 0.f;
               *reinterpret_cast<float4*>(dst + (size_t)i * p.T_out) = make_float4(__uint_as_float(v0[i]) + bv, __uint_as_float(v1[i]) + bv,
                                                                                  __uint_as_float(v2[i]) + bv, __uint_as_float(v3[i]) + bv);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&acc_empty[ab]);
+        continue;
+      }
+      if (!p.tr_stride) {
+        // convolution: column c of the tile is output channel n0 + c at this thread's position - one pointer per row, one multiply-add
+        // of the channel stride per column.  (The generic path below re-derives (channel, time, validity) per element: ncu counted
+        // 1 300 instructions per tile in each epilogue warp for 32 columns, 96 % of the warps' time, and the MMA warp waiting on
+        // `accumulator free` half of its time: the kernel was epilogue-bound on the narrow layers.)
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + CU_ACC_COL + ab * ACC_STRIDE;
+        float* yp = p.y + rw.base;
+        const float* rp = p.res ? p.res + rw.base : nullptr;
+        const float* bp = p.bias ? p.bias + p.n0 : nullptr;
+        const size_t ts = (size_t)p.T_out;
+        const bool row_ok = rw.ok;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
+          const int nc = min(32, p.n_cols - c0);  // warp-uniform
+          float add[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = (bp && i < nc) ? __ldg(bp + c0 + i) : 0.f;
+            if (rp && !p.prelu && row_ok && i < nc) a += __ldg(rp + (size_t)(c0 + i) * ts);
+            add[i] = a;
+          }
+          uint32_t v[32];
+          tmem_ld32(tb + c0, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nc) {
+                float o = __uint_as_float(v[i]) + add[i];
+                if (p.prelu) {
+                  o = o > 0.f ? o : o * slope;
+                  if (rp) o += __ldg(rp + (size_t)(c0 + i) * ts);
+                }
+                yp[(size_t)(c0 + i) * ts] = o;
+              }
             }
           }
         }
