@@ -40,10 +40,19 @@ const char* ua2_version(void);
  * "sgemm_min_rows" (rows from which linears use the fp32 register-tiled GEMM core when the tensor-core path is off, default 128);
  * "tc_gemm" (0/1, default 1: linears with >= "tc_min_rows" (default 32) rows run on the hand-written tcgen05 mainloop - 3xTF32,
  * fp32-class accuracy, fp32 weights read once and split on chip: csrc/ua2_umma.cu, csrc/ua2_tcgemm.cu);
- * "resblock_fused" (0/1, default 1: the 64-channel SEANet residual blocks of the codec handle run as one kernel, csrc/ua2_resblock.cu);
- * "conv_tc" (0/1, default 1: causal convolutions with Cin * K >= 1024 and transposed convolutions with Cin >= 128 run as im2col +
- * the tcgen05 GEMM instead of the fp32 register-tiled core - csrc/ua2_convtc.cu);
- * "attn_ring" (0/1: KV-cache attention launches with >= 592 (row, group, 64-key split) items run on persistent CTAs that stream the
+ * "resblock_fused" (0/1, default 0: the 64-channel SEANet residual blocks of the codec handle as one SIMT kernel, csrc/ua2_resblock.cu -
+ * measured slower than the pair of launches it replaces, profiles/r2_kernel_rooflines.md);
+ * "conv_umma" (0/1, default 1: convolutions with Cin % 16 == 0 and >= 512 output positions run as implicit GEMMs on tcgen05 straight
+ * from the (B, C, T) layout - dilation, ELU prologue, PReLU epilogue, residual - and transposed convolutions of <= 64 channels as one
+ * GEMM over all phases: csrc/ua2_convumma.cu); "conv_umma_staged" (0/1, default 1: its stride-1 layers stage the activations in
+ * shared memory by TMA instead of gathering them into registers);
+ * "conv_pointwise" (0/1, default 1: k = 1 convolutions of <= 128 input channels on the streaming SIMT kernel of csrc/ua2_sgemm.cu);
+ * "conv_tc" (0/1, default 1: causal convolutions with Cin * K >= 1024 (or k = 1 with >= 256 channels) and transposed convolutions with
+ * Cin >= 128 that the kernels above do not take run as im2col + the tcgen05 GEMM instead of the fp32 register-tiled core -
+ * csrc/ua2_convtc.cu);
+ * "attn_rows" (0/1, default 1: causal attention of many-row passes on the row-tile kernel); "flash_sbuf" (0 = by grid size, 1 / 2:
+ * variant of the bf16 tensor-core attention, csrc/ua2_flash.cu);
+ * "attn_ring" (0/1, default 1: KV-cache attention launches with >= 592 (row, group, 64-key split) items run on persistent CTAs that stream the
  * K / V chunks through a 3-slot bulk-copy ring instead of one fetch-compute-exit CTA per item - csrc/ua2_attn.cu);
  * "gemv3_prefetch_mb" / "gemv3_prefetch_idle_mb" (tail L2 prefetch budgets, default 0; only effective in builds with
  * -DUA2_GEMV3_TAIL_PREFETCH=1 - measured slower, see profiles/r1_l2_prefetch_experiment.md) */
@@ -213,8 +222,8 @@ int ua2_conv1d_causal_gemm_f32(const float* x, const float* w_torch, const float
                                void* stream);
 /* SEANetResnetBlock.forward (modules/seanet.py:21-94, dilation 1, true_skip) as ONE kernel that keeps the hidden activation on
  * chip: y = x + conv_k1(ELU(conv_k3(ELU(x)))).  w1 (H, C, 3), w2 (C, H, 1) in torch's Conv1d layout; served for C = 64, H = 32
- * (the blocks that run at 24 kHz).  The codec handle uses it when the global option "resblock_fused" is 1 (default 0: written at
- * the end of round 1, not yet run on a B200). */
+ * (the blocks that run at 24 kHz).  The codec handle uses it when the global option "resblock_fused" is 1 (default 0:
+ * measured on a B200 at 4.1 ms for batch 16 x 10 s against 0.88 + 0.83 ms for the two launches it replaces). */
 int ua2_resblock_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int B, int C, int H,
                      int T, void* stream);
 /* StreamingConvTranspose1d.forward, causal, trim_right_ratio = 1 (modules/conv.py:306-329): kernel = 2*stride,
