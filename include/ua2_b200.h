@@ -40,8 +40,8 @@ const char* ua2_version(void);
  * "sgemm_min_rows" (rows from which linears use the fp32 register-tiled GEMM core when the tensor-core path is off, default 128);
  * "tc_gemm" (0/1, default 1: linears with >= "tc_min_rows" (default 32) rows run on the hand-written tcgen05 mainloop - 3xTF32,
  * fp32-class accuracy, fp32 weights read once and split on chip: csrc/ua2_umma.cu, csrc/ua2_tcgemm.cu);
- * "resblock_fused" (0/1, default 0: the 64-channel SEANet residual blocks of the codec handle as one SIMT kernel, csrc/ua2_resblock.cu -
- * measured slower than the pair of launches it replaces, profiles/r2_kernel_rooflines.md);
+ * "resblock_fused" (0/1, default 1, but the codec handle takes it only while "conv_umma" is 0: the 64-channel SEANet residual blocks as
+ * one SIMT kernel, csrc/ua2_resblock.cu - measured slower than the pair of tensor-core / streaming launches, profiles/r2_kernel_rooflines.md);
  * "conv_umma" (0/1, default 1: convolutions with Cin % 16 == 0 and >= 512 output positions run as implicit GEMMs on tcgen05 straight
  * from the (B, C, T) layout - dilation, ELU prologue, PReLU epilogue, residual - and transposed convolutions of <= 64 channels as one
  * GEMM over all phases: csrc/ua2_convumma.cu); "conv_umma_staged" (0/1, default 1: its stride-1 layers stage the activations in
@@ -222,8 +222,8 @@ int ua2_conv1d_causal_gemm_f32(const float* x, const float* w_torch, const float
                                void* stream);
 /* SEANetResnetBlock.forward (modules/seanet.py:21-94, dilation 1, true_skip) as ONE kernel that keeps the hidden activation on
  * chip: y = x + conv_k1(ELU(conv_k3(ELU(x)))).  w1 (H, C, 3), w2 (C, H, 1) in torch's Conv1d layout; served for C = 64, H = 32
- * (the blocks that run at 24 kHz).  The codec handle uses it when the global option "resblock_fused" is 1 (default 0:
- * measured on a B200 at 4.1 ms for batch 16 x 10 s against 0.88 + 0.83 ms for the two launches it replaces). */
+ * (the blocks that run at 24 kHz).  The codec handle uses it when the global option "resblock_fused" is 1 and "conv_umma"
+ * is 0 (measured on a B200 at 4.1 ms for batch 16 x 10 s against 0.88 + 0.83 ms for the two default launches it would replace). */
 int ua2_resblock_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int B, int C, int H,
                      int T, void* stream);
 /* StreamingConvTranspose1d.forward, causal, trim_right_ratio = 1 (modules/conv.py:306-329): kernel = 2*stride,
