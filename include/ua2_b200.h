@@ -458,6 +458,74 @@ int ua2_whisper_forward(ua2_whisper* h, const float* input_features, float* out,
 int ua2_whisper_set_option(ua2_whisper* h, const char* name, int value);
 int ua2_whisper_last_launch_count(ua2_whisper* h);
 
+/* ----------------------------------------------------------------------------------------------
+ * Waveform front-end of ReasoningCodec_film's tokenize (csrc/ua2_frontend.cu).  The reference leaves the
+ * device here: reason_tokenizer.py:67-72 get_whisper_features = torchaudio Resample(24000, 16000) -> .cpu().numpy() ->
+ * transformers WhisperFeatureExtractor (torch.stft on the host) -> .to(device); AudioDiffusion1D.py:363-365 resamples again for WavLM.
+ * ---------------------------------------------------------------------------------------------- */
+/* torchaudio.transforms.Resample (sinc_interp_hann): y[b, new * m + p] = sum_k kernel[p, k] * x[b, orig * m + k - width], zero outside
+ * the clip; kernel (newf, 2 * width + orig) fp32 as torchaudio builds it, orig / newf already divided by their gcd.  Positions
+ * [n_valid, n_store) of every output row are written as zeros (padding to 30 s; the 160 zeros appended for WavLM).
+ * n_valid <= ceil(newf * L / orig). */
+int ua2_resample_f32(const float* x, long long ldx, const float* kernel, float* y, long long ldy, int B, int L, int n_valid, int n_store, int orig,
+                     int newf, int width, void* stream);
+/* WhisperFeatureExtractor._torch_extract_fbank_features: wav16 (B, L) fp32 (already padded / cut to 30 s) -> out (B, n_mels, n_frames)
+ * = (max(log10(max(mel_filters^T |stft|^2, 1e-10)), clip max - 8) + 4) / 4 with stft = torch.stft(n_fft, hop, window, center, reflect);
+ * window (n_fft), mel_filters (n_fft / 2 + 1, n_mels) fp32 device arrays.  n_fft <= 512 and even; n_frames <= 1 + L / hop (the
+ * reference drops the last of those frames: pass L / hop). */
+int ua2_whisper_logmel_f32(const float* wav16, long long ld, const float* window, const float* mel_filters, float* out, int B, int L, int n_fft,
+                           int hop, int n_mels, int n_frames, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * WavLM encoder: the second SSL front-end of tokenize.  Replaces `AutoModel.from_pretrained(wav_lm_path)(wav_16k,
+ * output_hidden_states=True).hidden_states` + the [6:10] mean of models/AudioDiffusion1D.py:226, :359-370 (transformers WavLMModel:
+ * modeling_wavlm.py WavLMFeatureEncoder / WavLMFeatureProjection / WavLMPositionalConvEmbedding / WavLMEncoder / WavLMAttention).
+ * Served: feat_extract_norm "group", do_stable_layer_norm false (wavlm-base, wavlm-base-plus), no attention mask, eval.
+ * csrc/ua2_wavlm.cu.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ua2_wavlm_cfg {       /* WavLMConfig fields (base-plus: 768 / 12 / 3072 / 12 / 7 / 512.. / 10,3,3,3,3,2,2 / 5,2,2,2,2,2,2 / 0 / 128 / 16 / 320 / 800 / 1e-5) */
+  int32_t hidden_size;               /* multiple of 8, <= 4096; hidden_size / heads in {32, 64, 128} */
+  int32_t num_attention_heads;
+  int32_t intermediate_size;
+  int32_t num_hidden_layers;
+  int32_t num_feat_extract_layers;   /* 2 .. 8 */
+  int32_t conv_dim[8];               /* multiples of 8 */
+  int32_t conv_kernel[8];            /* conv_kernel[0] <= 16 */
+  int32_t conv_stride[8];            /* conv_stride[0] <= 8 */
+  int32_t conv_bias;
+  int32_t num_conv_pos_embeddings;   /* even, <= 128 */
+  int32_t num_conv_pos_embedding_groups; /* hidden_size / groups <= 48 */
+  int32_t num_buckets;
+  int32_t max_bucket_distance;
+  float layer_norm_eps;
+} ua2_wavlm_cfg;
+typedef struct ua2_wavlm ua2_wavlm;
+
+int ua2_wavlm_create(const ua2_wavlm_cfg* cfg, ua2_wavlm** out);
+int ua2_wavlm_destroy(ua2_wavlm* h);
+/* one fp32 parameter by its WavLMModel state-dict key ("feature_extractor.conv_layers.2.conv.weight", "feature_projection.projection.bias",
+ * "encoder.layers.0.attention.rel_attn_embed.weight", "encoder.layers.4.attention.gru_rel_pos_const", ...).  The positional convolution
+ * is given with its weight normalisation applied: "encoder.pos_conv_embed.conv.weight" (hidden, hidden / groups, kernel) =
+ * g * v / ||v|| over dims (0, 1) of ...parametrizations.weight.original0 / original1.  Tensors must outlive the handle. */
+int ua2_wavlm_load_weight(ua2_wavlm* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+/* validates the parameter set; repacks the strided convolutions to GEMM form, the positional convolution to per-tap slabs, and
+ * concatenates q / k / v projections */
+int ua2_wavlm_finalize(ua2_wavlm* h, void* stream);
+/* encoder frames for a clip of L samples (0: shorter than the receptive field) */
+long long ua2_wavlm_frames(ua2_wavlm* h, long long L);
+/* wav16 (B, L) fp32, row stride ld -> out (B, T, hidden) = mean of hidden_states[hs_lo:hs_hi] (hidden_states[0] = the encoder's input
+ * after its LayerNorm, [i] = output of layer i - 1; only the first hs_hi - 1 layers run).  all_hidden (optional): every hidden state
+ * [0, hs_hi) as (hs_hi, B, T, hidden). */
+int ua2_wavlm_forward(ua2_wavlm* h, const float* wav16, long long ld, int B, int L, int hs_lo, int hs_hi, float* out, float* all_hidden,
+                      void* stream);
+int ua2_wavlm_last_launch_count(ua2_wavlm* h);
+/* host-only: WavLMAttention._relative_positions_bucket for relative positions -(T - 1) .. T - 1 -> out_host[2 T - 1] */
+int ua2_wavlm_rel_bucket_table(int T, int num_buckets, int max_distance, int32_t* out_host);
+/* the encoder's own kernels one at a time, for operator-level parity tests (op 0 positional convolution, 1 gate, 2 biased attention;
+ * argument meaning per op in csrc/ua2_wavlm.cu) */
+int ua2_wavlm_ops_f32(int op, const float* a, const float* b, const float* c, const float* d, float* y, int i0, int i1, int i2, int i3, int i4,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,10 @@ int shim_dit_attn(const float* q, const float* k, const float* v, float* out, in
   ua2::LaunchCtx lc;
   return ua2::launch_dit_attn(lc, q, k, v, out, B, T, H, hs);
 }
+int shim_dit_attn_bias(const float* q, const float* k, const float* v, float* out, int B, int T, int H, int hs, const float* gate, const float* tab) {
+  ua2::LaunchCtx lc;
+  return ua2::launch_dit_attn_bias(lc, q, k, v, out, B, T, H, hs, gate, tab);
+}
 int shim_dit_ln_mod(const float* x, float* out, const float* table, const float* t, int t_row, int t_stride, int shift_idx, int scale_idx,
                     float eps, int M, int T, int D) {
   return shim::run_grid(ua2::dit_ln_mod_kernel, dim3(M), dim3(256), x, out, (__nv_bfloat16*)nullptr, table, t, t_row, t_stride, shift_idx, scale_idx, eps, T, D);

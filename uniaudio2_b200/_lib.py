@@ -51,6 +51,14 @@ class WhisperCfg(C.Structure):
                 ("encoder_layers", C.c_int32), ("max_source_positions", C.c_int32), ("num_mel_bins", C.c_int32)]
 
 
+class WavLMCfg(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_attention_heads", C.c_int32), ("intermediate_size", C.c_int32),
+                ("num_hidden_layers", C.c_int32), ("num_feat_extract_layers", C.c_int32), ("conv_dim", C.c_int32 * 8),
+                ("conv_kernel", C.c_int32 * 8), ("conv_stride", C.c_int32 * 8), ("conv_bias", C.c_int32),
+                ("num_conv_pos_embeddings", C.c_int32), ("num_conv_pos_embedding_groups", C.c_int32), ("num_buckets", C.c_int32),
+                ("max_bucket_distance", C.c_int32), ("layer_norm_eps", C.c_float)]
+
+
 # every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -129,6 +137,17 @@ SYMBOLS = {
     "ua2_whisper_forward": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ua2_whisper_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ua2_whisper_last_launch_count": (C.c_int, [_P]),
+    "ua2_resample_f32": (C.c_int, [_P, C.c_longlong, _P, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_whisper_logmel_f32": (C.c_int, [_P, C.c_longlong, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_wavlm_create": (C.c_int, [C.POINTER(WavLMCfg), C.POINTER(_P)]),
+    "ua2_wavlm_destroy": (C.c_int, [_P]),
+    "ua2_wavlm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_wavlm_finalize": (C.c_int, [_P, _P]),
+    "ua2_wavlm_frames": (C.c_longlong, [_P, C.c_longlong]),
+    "ua2_wavlm_forward": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "ua2_wavlm_last_launch_count": (C.c_int, [_P]),
+    "ua2_wavlm_rel_bucket_table": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_wavlm_ops_f32": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ua2_stx_create": (C.c_int, [C.POINTER(StxCfg), C.POINTER(_P)]),
     "ua2_stx_destroy": (C.c_int, [_P]),
     "ua2_stx_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),

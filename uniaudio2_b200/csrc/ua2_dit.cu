@@ -354,9 +354,13 @@ constexpr int DA_KEYS = 32;  // keys per shared-memory tile (one per lane in the
 // all rows.  Score phase: lane = key, K row read with 128-bit loads (row stride HS + 4 keeps them conflict-free), the RPW
 // query rows of the warp are broadcast reads - (1 + RPW) loads per 4 * RPW FMAs.  Online softmax per row; the probabilities
 // go through a per-warp shared tile so that the P @ V phase (lane = output dim) reads them as broadcast float4.
-template <int HS, int RPW>
+// BIAS (WavLM's gated relative position bias, transformers modeling_wavlm.py WavLMAttention.forward): the score of (query i, key j)
+// gets gate[b, h, i] * tab[h, j - i + T - 1] added after the 1 / sqrt(hs) scaling - the (B H, T, T) additive attn_mask of
+// F.multi_head_attention_forward, never materialised.
+template <int HS, int RPW, bool BIAS>
 __global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__ q, const float* __restrict__ kc,
-                                                       const float* __restrict__ vc, float* __restrict__ out, int T, int H) {
+                                                       const float* __restrict__ vc, float* __restrict__ out, int T, int H,
+                                                       const float* __restrict__ gate, const float* __restrict__ tab) {
   constexpr int DPL = HS / 32;  // output dims per lane
   constexpr int ROWS = 8 * RPW;
   constexpr int KST = HS + 4;
@@ -379,8 +383,19 @@ __global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__
   const float* Vb = vc + ((size_t)b * H + h) * (size_t)T * HS;
   const float scale = rsqrtf((float)HS);
   float mx[RPW], l[RPW], acc[RPW][DPL];
+  float gt[RPW];                 // BIAS: the row's gate
+  const float* tb[RPW];          // BIAS: tab[h] shifted so that tb[r][j] is the entry of key j for this row
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
+    gt[r] = 0.f;
+    tb[r] = nullptr;
+    if (BIAS) {
+      const int t = t0 + warp * RPW + r;
+      if (t < T) {
+        gt[r] = gate[((size_t)b * H + h) * T + t];
+        tb[r] = tab + (size_t)h * (2 * T - 1) + (T - 1 - t);
+      }
+    }
     mx[r] = -INFINITY;
     l[r] = 0.f;
 #pragma unroll
@@ -418,7 +433,10 @@ __global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__
     const bool valid = j0 + lane < T;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      const float sv = valid ? s[r] * scale : -INFINITY;
+      float sv = valid ? s[r] * scale : -INFINITY;
+      if (BIAS) {
+        if (valid && tb[r] != nullptr) sv = fmaf(gt[r], tb[r][j0 + lane], sv);
+      }
       const float mn = fmaxf(mx[r], warp_max(sv));  // every tile holds at least one valid key, so mn is finite
       const float corr = expf(mx[r] - mn);
       const float p = valid ? expf(sv - mn) : 0.f;
@@ -463,10 +481,24 @@ __global__ void __launch_bounds__(256) dit_attn_kernel(const float* __restrict__
 cudaError_t launch_dit_attn(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H,
                             int hs) {
   const dim3 block(256);
+  const float* none = nullptr;
   switch (hs) {  // 4 rows per warp (32 per CTA); 2 at head size 128 to stay inside 48 KB of static shared memory
-    case 32: return launch(lc, dit_attn_kernel<32, 4>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H);
-    case 64: return launch(lc, dit_attn_kernel<64, 4>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H);
-    case 128: return launch(lc, dit_attn_kernel<128, 2>, dim3((T + 15) / 16, H, B), block, 0, q, kc, vc, out, T, H);
+    case 32: return launch(lc, dit_attn_kernel<32, 4, false>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H, none, none);
+    case 64: return launch(lc, dit_attn_kernel<64, 4, false>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H, none, none);
+    case 128: return launch(lc, dit_attn_kernel<128, 2, false>, dim3((T + 15) / 16, H, B), block, 0, q, kc, vc, out, T, H, none, none);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// the same attention with gate[b, h, i] * tab[h, j - i + T - 1] added to the scaled scores; gate (B, H, T), tab (H, 2 T - 1)
+cudaError_t launch_dit_attn_bias(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H,
+                                 int hs, const float* gate, const float* tab) {
+  const dim3 block(256);
+  if (gate == nullptr || tab == nullptr) return cudaErrorInvalidValue;
+  switch (hs) {
+    case 32: return launch(lc, dit_attn_kernel<32, 4, true>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H, gate, tab);
+    case 64: return launch(lc, dit_attn_kernel<64, 4, true>, dim3((T + 31) / 32, H, B), block, 0, q, kc, vc, out, T, H, gate, tab);
+    case 128: return launch(lc, dit_attn_kernel<128, 2, true>, dim3((T + 15) / 16, H, B), block, 0, q, kc, vc, out, T, H, gate, tab);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -545,6 +577,11 @@ struct DitBlock {
 // unmasked softmax(q k^T / sqrt(hs)) v in fp32 for other handles of the library (ua2_enc.cu): q (B * T, H * hs), k / v (B, H, T, hs)
 cudaError_t launch_dense_attn_f32(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H, int hs) {
   return launch_dit_attn(lc, q, kc, vc, out, B, T, H, hs);
+}
+// the same with the additive bias gate[b, h, i] * tab[h, j - i + T - 1] (ua2_wavlm.cu): gate (B, H, T), tab (H, 2 T - 1)
+cudaError_t launch_dense_attn_bias_f32(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H, int hs,
+                                       const float* gate, const float* tab) {
+  return launch_dit_attn_bias(lc, q, kc, vc, out, B, T, H, hs, gate, tab);
 }
 }  // namespace ua2
 

@@ -31,6 +31,9 @@ cudaError_t run_umma_tf32x3(const LaunchCtx& lc, const float* X2, const float* W
 // (out16 != NULL: the result as bf16 instead, the next linear's operand)
 // fp32 SIMT attention of ua2_dit.cu (head size 32 / 64 / 128): q (B * T, H * hs), k / v (B, H, T, hs) -> out (B * T, H * hs)
 cudaError_t launch_dense_attn_f32(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H, int hs);
+// + gate[b, h, i] * tab[h, j - i + T - 1] on the scaled scores (WavLM's gated relative position bias): gate (B, H, T), tab (H, 2 T - 1)
+cudaError_t launch_dense_attn_bias_f32(const LaunchCtx& lc, const float* q, const float* kc, const float* vc, float* out, int B, int T, int H, int hs,
+                                       const float* gate, const float* tab);
 void set_flash_sbuf(int v);
 cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
                               int hs);
