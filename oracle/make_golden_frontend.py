@@ -14,7 +14,7 @@ import warnings
 
 import torch
 
-SMALL = dict(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_hidden_layers=3, conv_dim=(32, 32, 32), conv_kernel=(10, 3, 2),
+SMALL = dict(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_hidden_layers=3, conv_dim=(64, 64, 64), conv_kernel=(10, 3, 2),
              conv_stride=(5, 2, 2), conv_bias=False, num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4, num_buckets=320,
              max_bucket_distance=800, layer_norm_eps=1e-5)
 # head size 64 and 48 channels per positional-convolution group like the checkpoints, k = 128 taps, two strided k = 3 convolutions, conv biases

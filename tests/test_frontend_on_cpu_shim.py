@@ -196,3 +196,86 @@ def test_biased_attention_source_on_cpu(dit, hs, T, B):
     out = torch.full((B * T, H * hs), float("nan"))
     assert dit.shim_dit_attn_bias(_p(q.reshape(B * T, H * hs).contiguous()), _p(k), _p(v), _p(out), B, T, H, hs, _p(gate), _p(tab)) == 0
     assert _rel(out, ref) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def wavlm_handle_lib(tmp_path_factory):
+    """Whole translation units with the real headers (-DUA2_CPU_SHIM), like the third build of tests/test_kernels_on_cpu_shim.py:
+    csrc/ua2_wavlm.cu (kernels AND the ua2_wavlm_* handle) over the real linear launchers (ua2_gemv.cu, ua2_gemv3.cu, ua2_sgemm.cu,
+    ua2_attn.cu, ua2_misc.cu); the tcgen05 GEMM is a CPU GEMM (stubs_real_headers.cpp), the attention comes from ua2_dit.cu's kernels."""
+    d = str(tmp_path_factory.mktemp("shim_wavlm"))
+    hdr = os.path.join(ROOT, "include", "ua2_b200.h")
+    srcs = []
+    for name in ("ua2_codec", "ua2_sgemm", "ua2_convtc", "ua2_resblock", "ua2_attn", "ua2_gemv3", "ua2_gemv", "ua2_misc", "ua2_codec_model", "ua2_wavlm"):
+        src = open(os.path.join(CSRC, name + ".cu")).read()
+        src = re.sub(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(shim::g_dyn_smem);", src)
+        src = src.replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
+        open(os.path.join(d, name + ".cpp"), "w").write(src)
+        srcs.append(os.path.join(d, name + ".cpp"))
+    _kernel_part("ua2_dit", d)
+    for stub in ("stubs_real_headers.cpp", "stubs_wavlm.cpp"):
+        text = open(os.path.join(SHIM, stub)).read().replace('#include "../../include/ua2_b200.h"', f'#include "{hdr}"')
+        open(os.path.join(d, stub), "w").write(text)
+        srcs.append(os.path.join(d, stub))
+    so = os.path.join(d, "libshim_wavlm.so")
+    r = subprocess.run(GXX + ["-DUA2_CPU_SHIM", "-DUA2_ATTN_RING_MIN_ITEMS=64", "-I", d, "-I", CSRC, "-I", os.path.join(SHIM, "rt"), "-Wl,--no-undefined"] + srcs +
+                       ["-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-6000:]
+    lib = C.CDLL(so)
+    lib.ua2_last_error.restype = C.c_char_p
+    lib.ua2_wavlm_frames.restype = C.c_longlong
+    lib.ua2_wavlm_frames.argtypes = [C.c_void_p, C.c_longlong]
+    lib.ua2_wavlm_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ua2_wavlm_load_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+    return lib
+
+
+def test_whole_wavlm_handle_on_cpu_against_transformers_golden(wavlm_handle_lib):
+    """csrc/ua2_wavlm.cu as shipped - parameter loading, weight repacks, workspace sizing, the feature encoder, feature projection,
+    positional convolution, post-LayerNorm layers with the gated relative position bias, hidden-state outputs and their mean - on CPU
+    tensors through the shim, against the hidden states of the real transformers.WavLMModel (tests/golden/frontend_golden.pt)."""
+    from uniaudio2_b200 import _lib
+
+    lib = wavlm_handle_lib
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "frontend_golden.pt"), weights_only=False)
+    c = gold["wavlm_small"]
+    cfg = c["cfg"]
+    sd = WO.random_state_dict(cfg, c["seed"])
+    n = len(cfg["conv_dim"])
+    arr = lambda v: (C.c_int32 * 8)(*(list(v) + [0] * (8 - n)))
+    ccfg = _lib.WavLMCfg(cfg["hidden_size"], cfg["num_attention_heads"], cfg["intermediate_size"], cfg["num_hidden_layers"], n, arr(cfg["conv_dim"]),
+                         arr(cfg["conv_kernel"]), arr(cfg["conv_stride"]), 1 if cfg["conv_bias"] else 0, cfg["num_conv_pos_embeddings"],
+                         cfg["num_conv_pos_embedding_groups"], cfg["num_buckets"], cfg["max_bucket_distance"], cfg["layer_norm_eps"])
+    h = C.c_void_p()
+    assert lib.ua2_wavlm_create(C.byref(ccfg), C.byref(h)) == 0, lib.ua2_last_error()
+    sd = dict(sd)
+    pre = "encoder.pos_conv_embed.conv."
+    g, v = sd.pop(pre + "parametrizations.weight.original0"), sd.pop(pre + "parametrizations.weight.original1")
+    sd[pre + "weight"] = (g * (v / v.norm(dim=(0, 1), keepdim=True))).contiguous()
+    sd.pop("masked_spec_embed")
+    keep = []
+    for key, t in sd.items():
+        t = t.contiguous()
+        keep.append(t)
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        assert lib.ua2_wavlm_load_weight(h, key.encode(), _p(t), shape, t.dim()) == 0, (key, lib.ua2_last_error())
+    assert lib.ua2_wavlm_finalize(h, None) == 0, lib.ua2_last_error()
+    wav = c["wav16"][:, :1300].contiguous()  # a shorter clip keeps the OS-thread emulation to seconds; reference below from the oracle
+    with torch.no_grad():
+        ref = WO.hidden_states(sd | {}, cfg, wav)
+    B, L = wav.shape
+    T = int(lib.ua2_wavlm_frames(h, L))
+    assert T == ref[0].shape[1]
+    nl = cfg["num_hidden_layers"]
+    out = torch.full((B, T, cfg["hidden_size"]), float("nan"))
+    allh = torch.full((nl + 1, B, T, cfg["hidden_size"]), float("nan"))
+    assert lib.ua2_wavlm_forward(h, _p(wav), L, B, L, 1, nl + 1, _p(out), _p(allh), None) == 0, lib.ua2_last_error()
+    for i in range(nl + 1):
+        assert _rel(allh[i], ref[i]) < 2e-5, (i, _rel(allh[i], ref[i]))
+    assert _rel(out, torch.stack(ref, 1)[:, 1:nl + 1].mean(1)) < 2e-5
+    # only the needed layers run, and a second call (cached bias table, reused workspace) gives the same result
+    out2 = torch.full_like(out, float("nan"))
+    assert lib.ua2_wavlm_forward(h, _p(wav), L, B, L, 0, 2, _p(out2), None, None) == 0, lib.ua2_last_error()
+    assert _rel(out2, (ref[0] + ref[1]) / 2) < 2e-5
+    assert lib.ua2_wavlm_forward(h, _p(wav), L, B, L, 0, nl + 2, _p(out2), None, None) != 0  # range beyond the layers is refused
+    assert lib.ua2_wavlm_destroy(h) == 0

@@ -4,7 +4,9 @@
 #pragma once
 #include <algorithm>
 
+#ifndef UA2_CPU_SHIM
 #include <cuda_bf16.h>
+#endif
 
 #include "ua2_kernels.cuh"
 #include "ua2_umma.cuh"
@@ -52,6 +54,7 @@ struct EncEpi {
 
 __device__ __forceinline__ float4 enc_load4(const EncEpi& e, int m, int c) {
   float4 v = *reinterpret_cast<const float4*>(e.src + (size_t)m * e.N + c);
+#ifndef UA2_CPU_SHIM  // (the stream-K side slots belong to the tcgen05 GEMM, which the CPU shim of tests/ replaces by a plain GEMM)
   if (e.has_split) {
     const float4 sd = umma_side_sum4(e.pl, e.slots, m, c, e.N);
     v.x += sd.x;
@@ -59,6 +62,7 @@ __device__ __forceinline__ float4 enc_load4(const EncEpi& e, int m, int c) {
     v.z += sd.z;
     v.w += sd.w;
   }
+#endif
   const float4 bs = *reinterpret_cast<const float4*>(e.bias + c);
   v.x += bs.x;
   v.y += bs.y;

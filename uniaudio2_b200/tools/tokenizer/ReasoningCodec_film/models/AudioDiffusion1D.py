@@ -176,9 +176,12 @@ class AudioDiffusion1D(nn.Module):
         self.cond_fusion_layer_phone = lin(codec_dim, wavlm_dim)
         self.time_film_phone, self.time_film_semantic, self.time_film_acoustic = (lin(2 * codec_dim, codec_dim) for _ in range(3))
         self.reason_adaptor = lin(codec_dim, codec_dim)
-        # SSL front-ends (AudioDiffusion1D.py:222-236).  Only the Whisper encoder exists in this package so far (modeling_whisper.py);
-        # it is attached by the caller because its size comes from the checkpoint's config, not from this class's arguments.
+        # SSL front-ends (AudioDiffusion1D.py:222-236).  The Whisper encoder (modeling_whisper.py) and the WavLM encoder
+        # (modeling_wavlm.py) exist in this package; they are attached by the caller because their sizes come from the checkpoints'
+        # configs, not from this class's arguments.  The BEST-RQ conformer is not built.
         self.whisper_encoder = None
+        self.wavlm_encoder = None
+        self.wavlm_transfer = None
 
     def attach_whisper_encoder(self, encoder):
         """`self.whisper_encoder = WhisperModel.from_pretrained(whisper_path).encoder` (AudioDiffusion1D.py:223): the caller builds the
@@ -195,6 +198,29 @@ class AudioDiffusion1D(nn.Module):
         n_len = max(n_len, len_semantic * 2)
         whisper_embeds = self.whisper_encoder(mels, return_dict=True).last_hidden_state
         return whisper_embeds[:, :n_len, :].transpose(1, 2)
+
+    def attach_wavlm_encoder(self, encoder):
+        """`self.wavlm_encoder = AutoModel.from_pretrained(wav_lm_path)` + `self.wavlm_transfer = Resample(24000, 16000)`
+        (AudioDiffusion1D.py:226-227): the caller builds the drop-in WavLMModel (models/modeling_wavlm.py), loads the checkpoint into it
+        and hands it over; the resampler is the device kernel of ../frontend.py."""
+        from ..frontend import Resample
+
+        self.wavlm_encoder = encoder
+        self.wavlm_transfer = Resample(24000, 16000)
+        return encoder
+
+    @torch.inference_mode()
+    def get_wavlm_feature(self, wav_24k, len_semantic):
+        """AudioDiffusion1D.py:359-370: wav_24k (B, 1, T) -> (B, wavlm_dim, frames) = mean of hidden states 6..9 of the WavLM encoder on the
+        16 kHz waveform with 160 zero samples appended, cut to twice the BEST-RQ frames.  Resampling and the zero tail are one launch; the
+        stack / slice / mean of the reference is fused into the encoder call, which stops after the ninth layer."""
+        if self.wavlm_encoder is None:
+            raise _lib.Ua2Error("no WavLM encoder attached (attach_wavlm_encoder)")
+        wav = wav_24k.squeeze(1)
+        wav_16k = self.wavlm_transfer(wav, pad_to=self.wavlm_transfer.out_length(wav.shape[-1]) + 160)
+        target = self.wavlm_encoder.hidden_states_mean(wav_16k, 6, 10).transpose(1, 2)
+        n_len = min(target.shape[-1], len_semantic * 2)
+        return target[:, :, :n_len]
 
     @property
     def device(self):

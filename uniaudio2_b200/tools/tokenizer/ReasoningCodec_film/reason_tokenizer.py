@@ -9,7 +9,8 @@ one AudioDiffusion1D.inference_codes call (a flow-matching solve) whose first la
 window's latents; each window's latents go through the SQ-codec decoder, and consecutive waveforms are joined by a linear
 cross-fade over the shared quarter (on the host, in float64, like the reference).  tests/test_detok_oracle.py checks this host
 logic bit-exactly against fixtures produced by the unmodified reference source; `model` and `SQCodec` are the uniaudio2_b200
-drop-ins (GPU only).  The tokenize direction (Whisper / WavLM / BEST-RQ front-ends) is not on this path.
+drop-ins (GPU only).  Of the tokenize direction this class carries `get_whisper_features` (:67-72); the SSL
+encoders hang off AudioDiffusion1D (Whisper, WavLM; the BEST-RQ conformer and AudioThinking are not built).
 """
 import math
 from dataclasses import dataclass
@@ -78,6 +79,23 @@ class ReasoningTokenizer:
         # hand-written tcgen05 kind::f16 mainloop); False keeps the fp32-class 3xTF32 arithmetic that the 1e-4 parity tests compare
         # with the fp32 CPU oracle.
         self.autocast_bf16 = True
+
+    @torch.inference_mode()
+    def get_whisper_features(self, audio, sr):
+        """reason_tokenizer.py:67-72: audio (B, samples) -> Whisper input features (B, 80, 3000).  The reference resamples on the device,
+        copies the batch to the host for WhisperFeatureExtractor and copies the features back; here the resampler (with the 30 s pad /
+        cut), the STFT, the mel projection and the normalisation are three launches of csrc/ua2_frontend.cu and nothing leaves the device."""
+        from .frontend import Resample, WhisperLogMel
+
+        if getattr(self, "wav_processor", None) is None:
+            self.wav_processor = WhisperLogMel()
+            self.transfer16k = Resample(24000, 16000)
+        audio = audio.to(self.device)
+        if sr != 16000:
+            if sr != 24000:
+                raise ValueError(f"sample rate {sr}: the reference's transfer16k resamples from 24000 Hz only")
+            audio = self.transfer16k(audio, pad_to=self.wav_processor.n_samples)
+        return self.wav_processor(audio, sampling_rate=16000, return_tensors="pt")["input_features"]
 
     def _randn(self, *shape):
         """Noise the reference draws on the CPU generator and then moves to the device (reason_tokenizer.py:234, :279)."""
