@@ -518,10 +518,15 @@ long long ua2_wavlm_frames(ua2_wavlm* h, long long L);
  * [0, hs_hi) as (hs_hi, B, T, hidden). */
 int ua2_wavlm_forward(ua2_wavlm* h, const float* wav16, long long ld, int B, int L, int hs_lo, int hs_hi, float* out, float* all_hidden,
                       void* stream);
+/* "bf16" (0/1, default 0): the reference's autocast arithmetic (reason_tokenizer.py:114-118) - GEMMs on bf16 operands with fp32
+ * accumulation (tcgen05 kind::f16), attention on tensor cores with the position bias added in the softmax (csrc/ua2_flash.cu, head
+ * size 64); default: fp32 class (3xTF32 GEMMs, fp32 attention) */
+int ua2_wavlm_set_option(ua2_wavlm* h, const char* name, int value);
 int ua2_wavlm_last_launch_count(ua2_wavlm* h);
 /* host-only: WavLMAttention._relative_positions_bucket for relative positions -(T - 1) .. T - 1 -> out_host[2 T - 1] */
 int ua2_wavlm_rel_bucket_table(int T, int num_buckets, int max_distance, int32_t* out_host);
-/* the encoder's own kernels one at a time, for operator-level parity tests (op 0 positional convolution, 1 gate, 2 biased attention;
+/* the encoder's own kernels one at a time, for operator-level parity tests (op 0 positional convolution, 1 gate, 2 biased attention,
+ * 3 biased attention on tensor cores from bf16 q / k / v;
  * argument meaning per op in csrc/ua2_wavlm.cu) */
 int ua2_wavlm_ops_f32(int op, const float* a, const float* b, const float* c, const float* d, float* y, int i0, int i1, int i2, int i3, int i4,
                       void* stream);

@@ -3,6 +3,19 @@
 // kernels (first convolution + GroupNorm, im2col, weight repacks, positional convolution, gate, bias table, hidden-state mean).
 #include "ua2_kernels.cuh"
 
+namespace ua2 {
+namespace {
+// csrc/ua2_enc_dev.cuh (not part of this build: its epilogue kernels need the tensor-core GEMM's headers) defines this helper
+inline uint2 pack4_bf16(float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o;
+  std::memcpy(&o.x, &lo, 4);
+  std::memcpy(&o.y, &hi, 4);
+  return o;
+}
+}  // namespace
+}  // namespace ua2
+
 #include "ua2_frontend_kernels.inc"
 #include "ua2_wavlm_kernels.inc"
 
@@ -26,7 +39,7 @@ int shim_wl_conv0(const float* x, long long ld, const float* w0, const float* b0
 }
 int shim_wl_im2col(const float* in, float* col, int B, int Tin, int Tout, int C, int k, int s) {
   ua2::LaunchCtx lc;
-  return ua2::launch_wl_im2col(lc, in, col, B, Tin, Tout, C, k, s);
+  return ua2::launch_wl_im2col<float>(lc, in, col, B, Tin, Tout, C, k, s);
 }
 int shim_wl_repack_conv(const float* w, float* out, int Cout, int Cin, int k) {
   return shim::run_grid(ua2::wl_repack_conv_kernel, dim3(ua2::wl_grid((long long)Cout * Cin * k)), dim3(256), w, out, Cout, Cin, k);

@@ -3,7 +3,9 @@ hidden states of the real transformers.WavLMModel (tests/golden/frontend_golden.
 tests/test_wavlm_oracle.py) on fresh inputs, up to the checkpoint geometry (wavlm-base-plus, random weights).
 
 Bar (floating point, fp32 class: 3xTF32 GEMMs, fp32 attention / convolution kernels): 2e-4 of the output scale for every hidden
-state; the encoder's own kernels one at a time: 1e-5."""
+state; the encoder's own kernels one at a time: 1e-5.  bf16 mode (the reference's autocast arithmetic: bf16 operands, fp32
+accumulation, tensor-core attention with the bias added in the softmax): 5e-2 of the output scale and really different; the
+tensor-core attention alone: 1e-2 against fp64 softmax of the same bf16 operands (the bar of tests/test_flash_gpu.py)."""
 import ctypes as C
 import math
 import os
@@ -160,3 +162,60 @@ def test_wavlm_interface_errors():
         m.hidden_states_mean(torch.zeros(1, 4000, device="cuda"), 2, 9)   # range beyond the model's layers
     with pytest.raises((ValueError, _lib.Ua2Error)):
         m(torch.zeros(1, 200, device="cuda"))               # fewer than 32 frames in the batch
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 3, 150), (1, 2, 128), (1, 2, 300), (2, 12, 1500), (1, 1, 1)])
+@pytest.mark.parametrize("sbuf", [0, 1, 2])
+def test_biased_flash_attention_operator(B, H, T, sbuf):
+    """flash_bf16_kernel<.., BIAS>: q / k / v as bf16 (B, H, T, 64), bias gate[b, h, i] * tab[h, j - i + T - 1] added in the softmax warps."""
+    from uniaudio2_b200 import _lib
+
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + T)
+    q = (torch.randn(B, H, T, 64, generator=g) * 2).bfloat16()
+    k = (torch.randn(B, H, T, 64, generator=g) * 2).bfloat16()
+    v = torch.randn(B, H, T, 64, generator=g).bfloat16()
+    gate = 1 + torch.rand(B, H, T, generator=g)
+    tab = torch.randn(H, 2 * T - 1, generator=g) * 2
+    i = torch.arange(T)[:, None]
+    j = torch.arange(T)[None, :]
+    bias = (gate[..., None] * tab[:, (j - i + T - 1)][None]).double()
+    s_ = q.double() @ k.double().transpose(-1, -2) / 8.0 + bias
+    ref = (torch.softmax(s_, dim=-1) @ v.double()).permute(0, 2, 1, 3).reshape(B, T, H * 64)
+    d = torch.cat([gate.reshape(-1), tab.reshape(-1)]).cuda()
+    _lib.check(_lib.lib().ua2_set_global_option(b"flash_sbuf", sbuf))
+    try:
+        y = _ops(3, q.cuda(), k.cuda(), v.cuda(), d, torch.full((B, T, H * 64), float("nan"), device="cuda"), B, T, H, 64)
+    finally:
+        _lib.check(_lib.lib().ua2_set_global_option(b"flash_sbuf", 0))
+    assert bool(torch.isfinite(y).all())
+    err = float((y.double() - ref).abs().max())
+    assert err <= 1e-2 * max(1.0, float(ref.abs().max())), err
+
+
+def test_wavlm_bf16_mode(gold):
+    """The option that mirrors the reference's autocast: every hidden state close to the fp32 reference, not equal to the fp32-class
+    result, and switching it off gives the fp32-class result back bit for bit.  `mid` fixture (head size 64) and checkpoint geometry."""
+    c = gold["wavlm_mid"]
+    cases = [(c["cfg"], WO.random_state_dict(c["cfg"], c["seed"]), c["wav16"], c["hidden_states"])]
+    cfg = dict(WO.BASE_PLUS, num_hidden_layers=9)
+    sd = WO.random_state_dict(cfg, 5)
+    wav16 = torch.randn(2, 48160, generator=torch.Generator().manual_seed(8)) * 0.2
+    with torch.no_grad():
+        cases.append((cfg, sd, wav16, WO.hidden_states(sd, cfg, wav16)))
+    for cfg, sd, wav, ref in cases:
+        m = _model(cfg, sd)
+        y32 = m(wav.cuda(), output_hidden_states=True).hidden_states
+        m.set_option("bf16", 1)
+        y16 = m(wav.cuda(), output_hidden_states=True).hidden_states
+        m.set_option("bf16", 0)
+        y32b = m(wav.cuda(), output_hidden_states=True).hidden_states
+        for i, (a, b, r) in enumerate(zip(y16, y32, ref)):
+            assert bool(torch.isfinite(a).all())
+            err = _rel(a.cpu(), r)
+            assert 1e-6 < err < 5e-2, (i, err)
+            assert torch.equal(b, y32b[i])
+    small = gold["wavlm_small"]  # head size 32: the tensor-core attention does not serve it
+    m = _model(small["cfg"], WO.random_state_dict(small["cfg"], small["seed"]))
+    m.set_option("bf16", 1)
+    with pytest.raises(Exception):
+        m(small["wav16"].cuda())

@@ -76,7 +76,12 @@ def main():
         x = w16(audio, pad_to=w16.out_length(audio.shape[-1]) + 160)
         return m.hidden_states_mean(x, 6, 10)
 
-    ms, out = timed(wavlm, n=3, warm=2)
+    res = {}
+    for mode, bf in (("bf16", 1), ("fp32 class", 0)):
+        m.set_option("bf16", bf)
+        ms, out = timed(wavlm, n=3, warm=2)
+        res[mode] = (ms, out, m.last_launch_count())
+    ms16, out16, n16 = res["bf16"]
     T = out.shape[1]
     t = 480160
     conv = 0.0
@@ -90,6 +95,9 @@ def main():
     pos = 2.0 * T * D * (D // c.num_conv_pos_embedding_groups) * c.num_conv_pos_embeddings
     layers = 9 * (2.0 * T * (4 * D * D + 2 * D * Fi) + 4.0 * T * T * D)
     flop = B * (conv + pos + 2.0 * T * D * c.conv_dim[-1] + layers)
+    print(json.dumps({"what": "WavLM base-plus, %d x 30 s, hidden states 6..9 (9 layers), bf16 mode" % B, "ms": round(ms16, 3), "launches": n16,
+                      "TFLOPs": round(flop / ms16 / 1e9, 1), "x_realtime": round(B * 30.0 / (ms16 * 1e-3), 1), "finite": bool(torch.isfinite(out16).all()),
+                      "max_abs_vs_fp32_class": float((out16 - out).abs().max())}))
     print(json.dumps({"what": "WavLM base-plus, %d x 30 s, hidden states 6..9 (9 layers), fp32 class" % B, "ms": round(ms, 3), "frames": T,
                       "launches": m.last_launch_count(), "algorithmic_TFLOP": round(flop / 1e12, 3), "TFLOPs_fp32_equivalent": round(flop / ms / 1e9, 1),
                       "x_realtime": round(B * 30.0 / (ms * 1e-3), 1), "finite": bool(torch.isfinite(out).all()), "out_scale": float(out.abs().max())}))

@@ -145,6 +145,7 @@ SYMBOLS = {
     "ua2_wavlm_finalize": (C.c_int, [_P, _P]),
     "ua2_wavlm_frames": (C.c_longlong, [_P, C.c_longlong]),
     "ua2_wavlm_forward": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "ua2_wavlm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "ua2_wavlm_last_launch_count": (C.c_int, [_P]),
     "ua2_wavlm_rel_bucket_table": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
     "ua2_wavlm_ops_f32": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -28,15 +28,6 @@
 namespace ua2 {
 namespace {
 
-__global__ void enc_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
-  pdl_launch_dependents();
-  pdl_wait();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
-    reinterpret_cast<uint2*>(y)[i] = pack4_bf16(v.x, v.y, v.z, v.w);
-  }
-}
-
 // torch Conv1d weight (Cout, Cin, 3) -> (Cout, 3 * Cin) with column k * Cin + c
 __global__ void enc_repack_conv3_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
   const long long n = (long long)Cout * Cin * 3;

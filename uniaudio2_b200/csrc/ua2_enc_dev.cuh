@@ -23,6 +23,18 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
   return o;
 }
 
+#ifndef UA2_CPU_SHIM
+// fp32 -> bf16 copy of a weight matrix (bf16 modes: made at first use, 2 B per parameter); n4 = elements / 4
+__global__ void enc_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = pack4_bf16(v.x, v.y, v.z, v.w);
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------- epilogues
 enum EncMode : int {
   EE_GELU = 0,      // y = gelu(v + bias)                        conv1; fc1
@@ -50,6 +62,8 @@ struct EncEpi {
   // residual + LayerNorm kernel
   const float *ln_g, *ln_b;
   float eps;
+  __nv_bfloat16* y16_also;  // residual + LayerNorm kernel: with y32, a bf16 copy of the normalised row (post-LayerNorm encoders: the row is both
+                            // the residual stream and the next tensor-core linear's operand)
 };
 
 __device__ __forceinline__ float4 enc_load4(const EncEpi& e, int m, int c) {
@@ -174,6 +188,7 @@ __global__ void __launch_bounds__(1024) enc_res_ln_kernel(const EncEpi e) {
     *reinterpret_cast<uint2*>(e.y16 + (size_t)m * e.N + c) = pack4_bf16(o0, o1, o2, o3);
   } else {
     *reinterpret_cast<float4*>(e.y32 + (size_t)m * e.N + c) = make_float4(o0, o1, o2, o3);
+    if (e.y16_also != nullptr) *reinterpret_cast<uint2*>(e.y16_also + (size_t)m * e.N + c) = pack4_bf16(o0, o1, o2, o3);
   }
 }
 

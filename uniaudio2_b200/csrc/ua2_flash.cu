@@ -59,10 +59,14 @@ __device__ __forceinline__ float ex2(float x) {
 
 // SBUF = 2: scores double-buffered (S_{j+1} accumulates while the softmax warps work on S_j), 512 TMEM columns, one CTA per SM.
 // SBUF = 1: one score buffer, 256 columns and 80 KB of shared memory: two CTAs per SM overlap each other instead.
-template <int SBUF>
+// BIAS (WavLM's gated relative position bias, csrc/ua2_wavlm.cu): logit(i, j) = q_i k_j / sqrt(hs) + gate[b, h, i] * tab[h, j - i + T - 1];
+// the softmax warps work on z = s * scale * log2 e + gate * log2 e * tab in the exp2 domain, so the running maximum, the rescale
+// factor and the probabilities all refer to z.  tab (H, 2 T - 1) is 12 KB per head: the two passes read it through L1.
+template <int SBUF, bool BIAS>
 __global__ void __launch_bounds__(FA_THREADS, SBUF == 1 ? 2 : 1)
 flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                  float* __restrict__ out, __nv_bfloat16* __restrict__ out16, int T, int H, float scale_log2e) {
+                  float* __restrict__ out, __nv_bfloat16* __restrict__ out16, int T, int H, float scale_log2e, const float* __restrict__ gate,
+                  const float* __restrict__ tab) {
   constexpr int FA_S_COL = 0, FA_P_COL = SBUF * 128, FA_O_COL = SBUF * 128 + 64;
   constexpr uint32_t FA_TMEM_COLS = SBUF == 2 ? 512u : 256u;
   constexpr int FA_STAGES = SBUF == 2 ? 3 : 2;  // K / V ring
@@ -176,6 +180,13 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
+    float gl = 0.f;              // BIAS: gate[b, h, row] * log2 e
+    const float* tb = nullptr;   // BIAS: tab[h] shifted so that tb[key] is this row's entry; rows past T read row T - 1's (never stored)
+    if (BIAS) {
+      const int tq = min(qt * FA_BM + r, T - 1);
+      gl = gate[((size_t)b * H + h) * T + tq] * 1.4426950408889634f;
+      tb = tab + (size_t)h * (2 * T - 1) + (T - 1 - tq);
+    }
     for (int j = 0; j < n_kb; ++j) {
       smem_bar_wait(&s_full[j % SBUF], (uint32_t)(j / SBUF) & 1);
       tc_fence_after();
@@ -189,9 +200,15 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+          if (c0 + i < n_valid) {
+            if (BIAS) {
+              mx = fmaxf(mx, fmaf(__uint_as_float(sv[i]), scale_log2e, gl * tb[j * FA_BN + c0 + i]));
+            } else {
+              mx = fmaxf(mx, __uint_as_float(sv[i]));
+            }
+          }
       }
-      const float alpha = ex2((m_run - mx) * scale_log2e);  // 0 for the first block (m_run = -inf)
+      const float alpha = BIAS ? ex2(m_run - mx) : ex2((m_run - mx) * scale_log2e);  // 0 for the first block (m_run = -inf)
       // ---- the previous block's P V must have completed before P is overwritten and O rescaled
       if (j > 0) {
         smem_bar_wait(o_done, (uint32_t)(j - 1) & 1);
@@ -217,8 +234,15 @@ flash_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = (c0 + 2 * i < n_valid) ? ex2((__uint_as_float(sv[2 * i]) - mx) * scale_log2e) : 0.f;
-          const float p1 = (c0 + 2 * i + 1 < n_valid) ? ex2((__uint_as_float(sv[2 * i + 1]) - mx) * scale_log2e) : 0.f;
+          float p0 = 0.f, p1 = 0.f;
+          if (BIAS) {
+            const int kj = j * FA_BN + c0 + 2 * i;
+            if (c0 + 2 * i < n_valid) p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), scale_log2e, gl * tb[kj]) - mx);
+            if (c0 + 2 * i + 1 < n_valid) p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2e, gl * tb[kj + 1]) - mx);
+          } else {
+            if (c0 + 2 * i < n_valid) p0 = ex2((__uint_as_float(sv[2 * i]) - mx) * scale_log2e);
+            if (c0 + 2 * i + 1 < n_valid) p1 = ex2((__uint_as_float(sv[2 * i + 1]) - mx) * scale_log2e);
+          }
           pk[i] = pack_bf16(p0, p1);
           const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&pk[i]);
           sum += __bfloat162float(rb.x) + __bfloat162float(rb.y);
@@ -287,10 +311,25 @@ int flash_sm_count() {
 void set_flash_sbuf(int v) { g_flash_sbuf = v == 1 || v == 2 ? v : 0; }
 
 // q16 / k16 / v16: (B, H, T, 64) bf16; out: (B, T, H * 64) fp32, or out16 (same shape, bf16) when not NULL.
+// gate (B, H, T) + tab (H, 2 T - 1), both or neither: the additive bias gate[b, h, i] * tab[h, j - i + T - 1] on the scaled scores.
 // cudaErrorNotSupported unless head size 64.
-cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
-                              int hs) {
-  if (hs != FA_HS || T < 1 || B < 1 || H < 1 || B > 65535 || H > 65535) return cudaErrorNotSupported;
+template <int SBUF, bool BIAS>
+cudaError_t launch_flash_variant(const LaunchCtx& lc, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, float* out, void* out16,
+                                 int B, int T, int H, float scale_log2e, const float* gate, const float* tab) {
+  const size_t smem = 1024 + (size_t)(1 + 2 * (SBUF == 1 ? 2 : 3)) * FA_TILE_BYTES + 32 * 8 + 16;
+  static DeviceOnce once;
+  if (once.need()) {
+    cudaError_t e = cudaFuncSetAttribute(flash_bf16_kernel<SBUF, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
+  return launch(lc, flash_bf16_kernel<SBUF, BIAS>, grid, dim3(FA_THREADS), smem, tmQ, tmK, tmV, out, static_cast<__nv_bfloat16*>(out16), T, H,
+                scale_log2e, gate, tab);
+}
+
+cudaError_t launch_flash_bf16_bias(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
+                                   int hs, const float* gate, const float* tab) {
+  if (hs != FA_HS || T < 1 || B < 1 || H < 1 || B > 65535 || H > 65535 || (gate == nullptr) != (tab == nullptr)) return cudaErrorNotSupported;
   const long long rows = (long long)B * H * T;
   CUtensorMap tmQ, tmK, tmV;
   if (!make_tmap(&tmQ, q16, FA_HS, rows, 1, FA_BM, false, true) || !make_tmap(&tmK, k16, FA_HS, rows, 1, FA_BN, false, true) ||
@@ -300,23 +339,17 @@ cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* 
   int sbuf = g_flash_sbuf;
   if (sbuf == 0) sbuf = (ctas > flash_sm_count() ? 1 : 2);  // more tiles than SMs: co-resident CTA pairs instead of a second wave
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)hs);
-  const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
-  if (sbuf == 1) {
-    const size_t smem = 1024 + (size_t)(1 + 2 * 2) * FA_TILE_BYTES + 32 * 8 + 16;
-    static DeviceOnce once;
-    if (once.need()) {
-      cudaError_t e = cudaFuncSetAttribute(flash_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-    }
-    return launch(lc, flash_bf16_kernel<1>, grid, dim3(FA_THREADS), smem, tmQ, tmK, tmV, out, static_cast<__nv_bfloat16*>(out16), T, H, scale_log2e);
+  if (gate != nullptr) {
+    if (sbuf == 1) return launch_flash_variant<1, true>(lc, tmQ, tmK, tmV, out, out16, B, T, H, scale_log2e, gate, tab);
+    return launch_flash_variant<2, true>(lc, tmQ, tmK, tmV, out, out16, B, T, H, scale_log2e, gate, tab);
   }
-  const size_t smem = 1024 + (size_t)(1 + 2 * 3) * FA_TILE_BYTES + 32 * 8 + 16;
-  static DeviceOnce once;
-  if (once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(flash_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  return launch(lc, flash_bf16_kernel<2>, grid, dim3(FA_THREADS), smem, tmQ, tmK, tmV, out, static_cast<__nv_bfloat16*>(out16), T, H, scale_log2e);
+  if (sbuf == 1) return launch_flash_variant<1, false>(lc, tmQ, tmK, tmV, out, out16, B, T, H, scale_log2e, gate, tab);
+  return launch_flash_variant<2, false>(lc, tmQ, tmK, tmV, out, out16, B, T, H, scale_log2e, gate, tab);
+}
+
+cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
+                              int hs) {
+  return launch_flash_bf16_bias(lc, q16, k16, v16, out, out16, B, T, H, hs, nullptr, nullptr);
 }
 
 }  // namespace ua2

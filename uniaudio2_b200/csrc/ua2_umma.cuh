@@ -37,6 +37,9 @@ cudaError_t launch_dense_attn_bias_f32(const LaunchCtx& lc, const float* q, cons
 void set_flash_sbuf(int v);
 cudaError_t launch_flash_bf16(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
                               int hs);
+// + gate[b, h, i] * tab[h, j - i + T - 1] on the scaled scores (gate (B, H, T), tab (H, 2 T - 1) fp32; both NULL = no bias)
+cudaError_t launch_flash_bf16_bias(const LaunchCtx& lc, const void* q16, const void* k16, const void* v16, float* out, void* out16, int B, int T, int H,
+                                   int hs, const float* gate, const float* tab);
 cudaError_t run_umma_bf16(const LaunchCtx& lc, const void* X16, const void* W16, float* C, int ldc, float* slots, int M, int N, int K,
                           const UmmaPlan& pl);
 cudaError_t run_umma_fixup(const LaunchCtx& lc, float* C, int ldc, const float* slots, int M, int N, int n_mat, const UmmaPlan& pl);

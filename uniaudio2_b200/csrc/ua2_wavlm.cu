@@ -10,7 +10,13 @@
 // oracle/wavlm_oracle.py restates it and is pinned against the installed class.
 //
 // Served configuration: feat_extract_norm "group", do_stable_layer_norm false (base / base-plus), erf GELU, no attention mask,
-// eval mode; fp32 class (the linears and the strided convolutions as GEMMs on the tcgen05 3xTF32 kernel of ua2_umma.cu).
+// eval mode.  Two arithmetic modes, like the Whisper encoder (ua2_enc.cu):
+//   fp32 class (default; what the 2e-4 parity tests run): linears and strided convolutions as GEMMs on the tcgen05 3xTF32 kernel
+//       (ua2_umma.cu), attention on the fp32 SIMT kernel of ua2_dit.cu with the bias added to its scores
+//   bf16 (option "bf16" = the reference's arithmetic: fetch_codes_batch runs under torch.autocast(bfloat16), reason_tokenizer.py:114-118):
+//       GEMMs on tcgen05 kind::f16 with fp32 accumulation, both attention contractions on tcgen05 with the bias added in the softmax
+//       warps (ua2_flash.cu, head size 64), operands handed from kernel to kernel as bf16; residual stream, LayerNorm / GroupNorm
+//       statistics, the first convolution, the positional convolution and the gate stay fp32
 // Activations are channels-last (B, T, C) from the first convolution on, so every later convolution is a GEMM over im2col rows and
 // the transformer consumes the stem's output as it lies.
 //
@@ -20,7 +26,7 @@
 //                          order), pass 2 recomputes, applies GroupNorm(C0 groups) + GELU and writes (B, T0, C0)
 //   wl_im2col_kernel       rows [x[s t] | ... | x[s t + k - 1]] of a channels-last tensor (float4 along channels)
 //   wl_posconv_kernel      grouped convolution (k 128, 16 groups of 48 channels, padding 64, last output dropped) + bias + GELU, fp32 FMA:
-//                          CTA = 32 positions of one (clip, group), the (32 + k - 1) x 48 input tile in shared memory (row stride 49:
+//                          CTA = 64 positions of one (clip, group), the (64 + k - 1) x 48 input tile in shared memory (row stride 49:
 //                          conflict-free along positions), one tap's 48 x 48 weight slab staged per step and read as broadcasts
 //   wl_gate_kernel         gate[b, h, t] = a (b' c_h - 1) + 2 with a, b' = sigmoid of the two 4-sums of gru_rel_pos_linear(x[b, t, head h])
 //   wl_bias_table_kernel   tab[h, j - i + T - 1] = rel_attn_embed[bucket(j - i), h]; the (B H, T, T) bias itself is never formed: the
@@ -28,6 +34,7 @@
 //   wl_axpy_kernel         running mean of the selected hidden states
 #include <algorithm>
 #include <cmath>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -42,7 +49,7 @@ namespace {
 constexpr int WL_TT = 256;     // conv0: output frames per CTA
 constexpr int WL_MAXK0 = 16;   // conv0: kernel bound
 constexpr int WL_MAXS0 = 8;    // conv0: stride bound
-constexpr int PC_TT = 32;      // pos conv: positions per CTA
+constexpr int PC_TT = 64;      // pos conv: positions per CTA
 constexpr int PC_MAXK = 128;   // pos conv: kernel bound
 constexpr int PC_MAXCG = 48;   // pos conv: channels per group bound
 
@@ -137,7 +144,8 @@ __global__ void __launch_bounds__(256) wl_conv0_apply_kernel(const float* __rest
 }
 
 // col[(b, t)][j * C + c] = in[b, s * t + j, c], in channels-last (B, Tin, C); C % 4 == 0
-__global__ void wl_im2col_kernel(const float* __restrict__ in, float* __restrict__ col, int B, int Tin, int Tout, int C, int k, int s) {
+template <typename OUT>
+__global__ void wl_im2col_kernel(const float* __restrict__ in, OUT* __restrict__ col, int B, int Tin, int Tout, int C, int k, int s) {
   pdl_launch_dependents();
   pdl_wait();
   const int C4 = C / 4;
@@ -149,7 +157,12 @@ __global__ void wl_im2col_kernel(const float* __restrict__ in, float* __restrict
     r /= k;
     const int t = (int)(r % Tout), b = (int)(r / Tout);
     const float4 v = *reinterpret_cast<const float4*>(in + ((size_t)b * Tin + (size_t)s * t + j) * C + 4 * c4);
-    *reinterpret_cast<float4*>(col + ((size_t)b * Tout + t) * ((size_t)k * C) + (size_t)j * C + 4 * c4) = v;
+    OUT* dst = col + ((size_t)b * Tout + t) * ((size_t)k * C) + (size_t)j * C + 4 * c4;
+    if (sizeof(OUT) == 2) {
+      *reinterpret_cast<uint2*>(dst) = pack4_bf16(v.x, v.y, v.z, v.w);
+    } else {
+      *reinterpret_cast<float4*>(dst) = v;
+    }
   }
 }
 
@@ -178,43 +191,65 @@ __global__ void wl_repack_posconv_kernel(const float* __restrict__ w, float* __r
 }
 
 // p[b, t, g cg + co] = gelu(bias + sum_j sum_ci w[g cg + co, ci, j] * h[b, t + j - K / 2, g cg + ci]),  t in [0, T)
+// thread = two positions (t0 + tl, t0 + tl + 32) x up to 6 output channels (cq + 8 i): per input channel 2 conflict-free loads of the
+// input tile and up to 6 broadcast loads of the tap's weight slab feed 12 FMAs; the next tap's slab is fetched into registers while
+// this tap is computed (ncu on the first version - one position per thread, slab fetched between the barriers: 6.2 ms at 6 x 1500
+// frames, shared-memory-load bound).
 __global__ void __launch_bounds__(256) wl_posconv_kernel(const float* __restrict__ h, const float* __restrict__ wr, const float* __restrict__ bias,
                                                          float* __restrict__ p, int T, int D, int cg, int K) {
   __shared__ float Xs[(PC_TT + PC_MAXK - 1) * (PC_MAXCG + 1)];
   __shared__ float Ws[PC_MAXCG * PC_MAXCG];
+  constexpr int WPT = (PC_MAXCG * PC_MAXCG + 255) / 256;  // slab elements per thread
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x, tl = tid & 31, cq = tid >> 5;
   const int t0 = blockIdx.x * PC_TT, g = blockIdx.y, b = blockIdx.z;
-  const int pad = K / 2, xst = cg + 1, rows = PC_TT + K - 1;
+  const int pad = K / 2, xst = cg + 1, rows = PC_TT + K - 1, slab = cg * cg;
   for (int i = tid; i < rows * cg; i += 256) {
     const int r = i / cg, ci = i - r * cg;
     const int ts = t0 + r - pad;
     Xs[r * xst + ci] = (ts >= 0 && ts < T) ? h[((size_t)b * T + ts) * D + g * cg + ci] : 0.f;
   }
-  float acc[PC_MAXCG / 8];
+  float acc0[PC_MAXCG / 8], acc1[PC_MAXCG / 8], wreg[WPT];
 #pragma unroll
-  for (int i = 0; i < PC_MAXCG / 8; ++i) acc[i] = 0.f;
-  const float* wg = wr + (size_t)g * K * cg * cg;
+  for (int i = 0; i < PC_MAXCG / 8; ++i) acc0[i] = acc1[i] = 0.f;
+  const float* wg = wr + (size_t)g * K * slab;
+#pragma unroll
+  for (int q = 0; q < WPT; ++q) wreg[q] = (tid + 256 * q < slab) ? wg[tid + 256 * q] : 0.f;
   for (int j = 0; j < K; ++j) {
     __syncthreads();  // the input tile is complete (first step) / the previous tap's slab is consumed
-    for (int i = tid; i < cg * cg; i += 256) Ws[i] = wg[(size_t)j * cg * cg + i];
+#pragma unroll
+    for (int q = 0; q < WPT; ++q)
+      if (tid + 256 * q < slab) Ws[tid + 256 * q] = wreg[q];
     __syncthreads();
-    const float* xr = Xs + (tl + j) * xst;
+    if (j + 1 < K) {
+      const float* wn = wg + (size_t)(j + 1) * slab;
+#pragma unroll
+      for (int q = 0; q < WPT; ++q) wreg[q] = (tid + 256 * q < slab) ? wn[tid + 256 * q] : 0.f;
+    }
+    const float* xr0 = Xs + (tl + j) * xst;
+    const float* xr1 = xr0 + 32 * xst;
     for (int ci = 0; ci < cg; ++ci) {
-      const float xv = xr[ci];
+      const float x0 = xr0[ci], x1 = xr1[ci];
       const float* wrow = Ws + ci * cg + cq;
 #pragma unroll
       for (int i = 0; i < PC_MAXCG / 8; ++i)
-        if (cq + 8 * i < cg) acc[i] = fmaf(xv, wrow[8 * i], acc[i]);
+        if (cq + 8 * i < cg) {
+          const float w = wrow[8 * i];
+          acc0[i] = fmaf(x0, w, acc0[i]);
+          acc1[i] = fmaf(x1, w, acc1[i]);
+        }
     }
   }
-  const int t = t0 + tl;
-  if (t < T) {
 #pragma unroll
-    for (int i = 0; i < PC_MAXCG / 8; ++i) {
-      const int co = cq + 8 * i;
-      if (co < cg) p[((size_t)b * T + t) * D + g * cg + co] = wl_gelu(acc[i] + bias[g * cg + co]);
+  for (int half = 0; half < 2; ++half) {
+    const int t = t0 + tl + 32 * half;
+    if (t < T) {
+#pragma unroll
+      for (int i = 0; i < PC_MAXCG / 8; ++i) {
+        const int co = cq + 8 * i;
+        if (co < cg) p[((size_t)b * T + t) * D + g * cg + co] = wl_gelu((half ? acc1[i] : acc0[i]) + bias[g * cg + co]);
+      }
     }
   }
 }
@@ -286,8 +321,9 @@ cudaError_t launch_wl_conv0(const LaunchCtx& lc, const float* x, long long ld, c
   return launch(lc, wl_conv0_apply_kernel, grid, dim3(256), 0, x, ld, w0, b0, (const float*)stat, gamma, beta, out, L, T0, C0, k0, s0);
 }
 
-cudaError_t launch_wl_im2col(const LaunchCtx& lc, const float* in, float* col, int B, int Tin, int Tout, int C, int k, int s) {
-  return launch(lc, wl_im2col_kernel, dim3(wl_grid((long long)B * Tout * k * (C / 4))), dim3(256), 0, in, col, B, Tin, Tout, C, k, s);
+template <typename OUT>
+cudaError_t launch_wl_im2col(const LaunchCtx& lc, const float* in, OUT* col, int B, int Tin, int Tout, int C, int k, int s) {
+  return launch(lc, wl_im2col_kernel<OUT>, dim3(wl_grid((long long)B * Tout * k * (C / 4))), dim3(256), 0, in, col, B, Tin, Tout, C, k, s);
 }
 
 cudaError_t launch_wl_posconv(const LaunchCtx& lc, const float* h, const float* wr, const float* bias, float* p, int B, int T, int D, int cg,
@@ -357,6 +393,9 @@ struct ua2_wavlm {
   int tab_T = 0;  // the T the device table was built for (0 = none; reset when weights change)
   size_t stats_floats = 0;
   TcWorkspace tc;
+  int opt_bf16 = 0;
+  __nv_bfloat16* a16 = nullptr;                   // bf16 operand rows of the next tensor-core linear
+  std::map<const float*, __nv_bfloat16*> w16;     // bf16 copies of the weights, made at first use
   int last_launches = 0;
 };
 
@@ -397,6 +436,8 @@ void wl_free_ws(ua2_wavlm* h) {
   h->part = nullptr;
   if (h->bucket_dev) cudaFree(h->bucket_dev);
   h->bucket_dev = nullptr;
+  if (h->a16) cudaFree(h->a16);
+  h->a16 = nullptr;
   h->tab_T = 0;
 }
 
@@ -453,6 +494,7 @@ int wl_reserve(ua2_wavlm* h, int B, int L) {
   RUN(wl_dmalloc(&h->tc.a, h->tc.a_floats));
   RUN(wl_dmalloc(&h->tc.slots, h->tc.slots_floats));
   RUN(wl_dmalloc(&h->tc.c, h->tc.c_floats));
+  UA2_CHECK_CUDA(cudaMalloc((void**)&h->a16, col * sizeof(__nv_bfloat16)));
   h->max_B = B;
   h->max_L = L;
   return UA2_OK;
@@ -466,6 +508,30 @@ int wl_linear(ua2_wavlm* h, const LaunchCtx& lc, const float* x, const float* W,
   e->N = N;
   e->T = T;
   e->eps = h->cfg.layer_norm_eps;
+#ifndef UA2_CPU_SHIM
+  if (h->opt_bf16) {  // operand rows are already bf16 in h->a16; the stream-K side slots are left for the epilogue to sum
+    auto it = h->w16.find(W);
+    const bool fresh = it == h->w16.end();
+    if (fresh) {
+      __nv_bfloat16* wb = nullptr;
+      UA2_CHECK_CUDA(cudaMalloc((void**)&wb, (size_t)N * K * sizeof(__nv_bfloat16)));
+      it = h->w16.emplace(W, wb).first;
+      const long long n4 = (long long)N * K / 4;
+      CU(launch(lc, enc_to_bf16_kernel, dim3(wl_grid(n4)), dim3(256), 0, W, wb, n4));
+    }
+    const UmmaPlan pl = umma_plan(M, N, 1, K, true);
+    UA2_REQUIRE(pl.grid >= 1 && pl.slot_floats <= h->tc.slots_floats && (size_t)M * N <= h->tc.c_floats && (K % 8) == 0 && (N % 4) == 0,
+                "encoder linear outside the tensor-core path's shapes");
+    LaunchCtx lg = lc;
+    if (fresh) lg.pdl = false;  // the GEMM prefetches weights before griddepcontrol.wait: full stream order behind the conversion kernel
+    CU(run_umma_bf16(lg, h->a16, it->second, h->tc.c, N, h->tc.slots, M, N, K, pl));
+    e->src = h->tc.c;
+    e->slots = h->tc.slots;
+    e->pl = pl;
+    e->has_split = umma_has_split_tiles(pl) ? 1 : 0;
+    return UA2_OK;
+  }
+#endif
   GemvParams p;
   p.W = W;
   p.N = N;
@@ -492,6 +558,7 @@ int wl_forward(ua2_wavlm* h, const LaunchCtx& lc, const float* wav, long long ld
   UA2_REQUIRE(wl_frames(c, L, Ts), "clip shorter than the feature encoder's receptive field");
   const int T = (int)Ts[nc - 1], M = B * T;
   UA2_REQUIRE(M >= 32, "fewer than 32 frames in the batch");
+  const bool bf = h->opt_bf16 != 0;
   EncEpi e;
   // ---- feature encoder: conv0 + GroupNorm + GELU, then GEMM convolutions + GELU, ping-pong between x0 / x1
   CU(launch_wl_conv0(lc, wav, ld, h->conv[0].w, h->conv[0].b, h->gn_g, h->gn_b, h->part, h->gnstat, h->x0, B, L, (int)Ts[0], c.conv_dim[0],
@@ -500,7 +567,11 @@ int wl_forward(ua2_wavlm* h, const LaunchCtx& lc, const float* wav, long long ld
   for (int i = 1; i < nc; ++i) {
     float* nxt = (i % 2) ? h->x1 : h->x0;
     const int Tin = (int)Ts[i - 1], Tout = (int)Ts[i], Cin = c.conv_dim[i - 1], Cout = c.conv_dim[i], k = c.conv_kernel[i], s = c.conv_stride[i];
-    CU(launch_wl_im2col(lc, cur, h->col, B, Tin, Tout, Cin, k, s));
+    if (bf) {
+      CU(launch_wl_im2col(lc, cur, h->a16, B, Tin, Tout, Cin, k, s));
+    } else {
+      CU(launch_wl_im2col(lc, cur, h->col, B, Tin, Tout, Cin, k, s));
+    }
     RUN(wl_linear(h, lc, h->col, h->conv_wr[i], h->conv[i].b ? h->conv[i].b : h->zeros, B * Tout, Cout, k * Cin, Tout, &e));
     e.y32 = nxt;
     CU(launch_enc_epi<EE_GELU>(lc, e));
@@ -517,6 +588,7 @@ int wl_forward(ua2_wavlm* h, const LaunchCtx& lc, const float* wav, long long ld
     l.ln_b = h->fp_ln_b;
     l.eps = c.layer_norm_eps;
     l.y32 = h->n;
+    l.y16 = bf ? h->a16 : nullptr;
     CU(launch(lc, enc_res_ln_kernel<false>, dim3(M), dim3((unsigned)(((CL / 4) + 31) / 32 * 32)), 0, l));
   }
   RUN(wl_linear(h, lc, h->n, h->fp.w, h->fp.b, M, D, CL, T, &e));
@@ -537,6 +609,7 @@ int wl_forward(ua2_wavlm* h, const LaunchCtx& lc, const float* wav, long long ld
     l.ln_b = h->enc_ln_b;
     l.eps = c.layer_norm_eps;
     l.y32 = h->h;  // the normalised row replaces the residual stream (post-LayerNorm encoder)
+    l.y16_also = bf ? h->a16 : nullptr;
     CU(launch(lc, enc_res_ln_kernel<true>, dim3(M), dim3(ln_threads), 0, l));
   }
   const long long n4 = (long long)M * D / 4;
@@ -565,27 +638,41 @@ int wl_forward(ua2_wavlm* h, const LaunchCtx& lc, const float* wav, long long ld
     RUN(wl_linear(h, lc, h->h, Ly.wqkv, Ly.bqkv, M, 3 * D, D, T, &e));
     e.H = H;
     e.hs = hs;
-    e.q = h->q;
-    e.k = h->k;
-    e.v = h->v;
-    CU(launch_enc_epi<EE_QKV>(lc, e));
-    CU(launch_dense_attn_bias_f32(lc, h->q, h->k, h->v, h->att, B, T, H, hs, h->gate, h->tab));
+#ifndef UA2_CPU_SHIM
+    if (bf) {
+      e.q16 = reinterpret_cast<__nv_bfloat16*>(h->q);
+      e.k16 = reinterpret_cast<__nv_bfloat16*>(h->k);
+      e.v16 = reinterpret_cast<__nv_bfloat16*>(h->v);
+      CU(launch_enc_epi<EE_QKV16>(lc, e));
+      CU(launch_flash_bf16_bias(lc, e.q16, e.k16, e.v16, nullptr, h->a16, B, T, H, hs, h->gate, h->tab));
+    } else
+#endif
+    {
+      e.q = h->q;
+      e.k = h->k;
+      e.v = h->v;
+      CU(launch_enc_epi<EE_QKV>(lc, e));
+      CU(launch_dense_attn_bias_f32(lc, h->q, h->k, h->v, h->att, B, T, H, hs, h->gate, h->tab));
+    }
     // h = layer_norm(h + out_proj(att))
     RUN(wl_linear(h, lc, h->att, Ly.o.w, Ly.o.b, M, D, D, T, &e));
     e.res = h->h;
     e.ln_g = Ly.ln1_g;
     e.ln_b = Ly.ln1_b;
     e.y32 = h->h;
+    e.y16_also = bf ? h->a16 : nullptr;
     CU(launch(lc, enc_res_ln_kernel<true>, dim3(M), dim3(ln_threads), 0, e));
     // h = final_layer_norm(h + output_dense(gelu(intermediate_dense(h))))
     RUN(wl_linear(h, lc, h->h, Ly.ff1.w, Ly.ff1.b, M, F, D, T, &e));
     e.y32 = h->ff;
+    e.y16 = bf ? h->a16 : nullptr;
     CU(launch_enc_epi<EE_GELU>(lc, e));
     RUN(wl_linear(h, lc, h->ff, Ly.ff2.w, Ly.ff2.b, M, D, F, T, &e));
     e.res = h->h;
     e.ln_g = Ly.ln2_g;
     e.ln_b = Ly.ln2_b;
     e.y32 = h->h;
+    e.y16_also = bf ? h->a16 : nullptr;
     CU(launch(lc, enc_res_ln_kernel<true>, dim3(M), dim3(ln_threads), 0, e));
     RUN(emit(li + 1));
   }
@@ -638,6 +725,7 @@ int ua2_wavlm_destroy(ua2_wavlm* h) {
   cudaDeviceSynchronize();
   wl_free_ws(h);
   for (void* p : h->owned) cudaFree(p);
+  for (auto& kv : h->w16) cudaFree(kv.second);
   delete h;
   return UA2_OK;
 }
@@ -780,6 +868,8 @@ int ua2_wavlm_finalize(ua2_wavlm* h, void* stream) {
     UA2_CHECK_CUDA(cudaMemcpyAsync(L.bqkv + D, L.k.b, bb, cudaMemcpyDeviceToDevice, st));
     UA2_CHECK_CUDA(cudaMemcpyAsync(L.bqkv + 2 * D, L.v.b, bb, cudaMemcpyDeviceToDevice, st));
   }
+  for (auto& kv : h->w16) cudaFree(kv.second);  // weights may have changed: bf16 copies are rebuilt at next use
+  h->w16.clear();
   h->tab_T = 0;
   h->ready = true;
   return UA2_OK;
@@ -797,6 +887,7 @@ int ua2_wavlm_forward(ua2_wavlm* h, const float* wav16, long long ld, int B, int
   UA2_REQUIRE(h->ready, "ua2_wavlm_finalize has not run");
   UA2_REQUIRE(B >= 1 && B <= 65535 && L >= 1 && ld >= L, "bad batch / clip length / row stride");
   UA2_REQUIRE(hs_lo >= 0 && hs_hi > hs_lo && hs_hi <= h->cfg.num_hidden_layers + 1, "hidden-state range outside [0, num_hidden_layers]");
+  UA2_REQUIRE(!h->opt_bf16 || h->cfg.hidden_size / h->cfg.num_attention_heads == 64, "bf16 mode serves head size 64");
   RUN(wl_reserve(h, B, L));
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
@@ -806,6 +897,19 @@ int ua2_wavlm_forward(ua2_wavlm* h, const float* wav16, long long ld, int B, int
   const int rc = wl_forward(h, lc, wav16, ld, B, L, hs_lo, hs_hi, out, all_hidden);
   h->last_launches = launches;
   return rc;
+}
+
+int ua2_wavlm_set_option(ua2_wavlm* h, const char* name, int value) {
+  UA2_REQUIRE(h && name, "null argument");
+  const std::string n(name);
+  if (n == "bf16") {
+#ifdef UA2_CPU_SHIM
+    UA2_REQUIRE(!value, "bf16 mode needs the tensor cores");
+#endif
+    h->opt_bf16 = value ? 1 : 0;
+    return UA2_OK;
+  }
+  UA2_REQUIRE(false, "unknown option " + n);
 }
 
 int ua2_wavlm_last_launch_count(ua2_wavlm* h) { return h ? h->last_launches : 0; }
@@ -847,6 +951,13 @@ int ua2_wavlm_ops_f32(int op, const float* a, const float* b, const float* c, co
     UA2_CHECK_CUDA(launch_dense_attn_bias_f32(lc, a, b, c, y, i0, i1, i2, i3, d, d + (size_t)i0 * i2 * i1));
     return UA2_OK;
   }
+#ifndef UA2_CPU_SHIM
+  if (op == 3) {  // op 2 on the tensor cores: a / b / c = q / k / v as (B, H, T, 64) BF16 (device pointers passed as float*), d as in op 2
+    UA2_REQUIRE(d != nullptr && i0 >= 1 && i1 >= 1 && i2 >= 1 && i3 == 64, "bad attention geometry (head size 64)");
+    UA2_CHECK_CUDA(launch_flash_bf16_bias(lc, a, b, c, y, nullptr, i0, i1, i2, i3, d, d + (size_t)i0 * i2 * i1));
+    return UA2_OK;
+  }
+#endif
   UA2_REQUIRE(false, "unknown op");
 }
 

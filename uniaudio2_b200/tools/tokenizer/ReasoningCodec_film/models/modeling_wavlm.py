@@ -15,7 +15,8 @@ same call: `model(wav_16k, output_hidden_states=True).hidden_states` is the tupl
 and no per-layer tensor is materialised.
 
 Served configuration: feat_extract_norm='group', do_stable_layer_norm=False, 'gelu' activations (wavlm-base, wavlm-base-plus - the
-768-wide models the reference's `wavlm_fea_dim = 768` implies), inference, no attention mask.  fp32 class arithmetic.
+768-wide models the reference's `wavlm_fea_dim = 768` implies), inference, no attention mask.  fp32 class arithmetic by default;
+`set_option('bf16', 1)` switches to the reference's autocast arithmetic (bf16 operands, fp32 accumulation, tensor-core attention).
 All arithmetic runs in libua2_b200.so (csrc/ua2_wavlm.cu).  No torch / CPU fallback."""
 import ctypes as C
 import math
@@ -114,6 +115,7 @@ class WavLMModel(nn.Module):
         self.encoder = enc
         self._h = None
         self._keep = []
+        self._bf16 = 0
 
     # ------------------------------------------------------------------ native handle
     def _destroy(self):
@@ -173,11 +175,20 @@ class WavLMModel(nn.Module):
                     shape = (C.c_int64 * t.dim())(*t.shape)
                     _lib.check(L.ua2_wavlm_load_weight(h, key.encode(), _lib.ptr(t), shape, t.dim()), f"load_weight({key})")
                 _lib.check(L.ua2_wavlm_finalize(h, _lib.current_stream()), "ua2_wavlm_finalize")
+                _lib.check(L.ua2_wavlm_set_option(h, b"bf16", self._bf16), "set_option(bf16)")
             except Exception:
                 L.ua2_wavlm_destroy(h)
                 raise
         self._h, self._keep = h, keep
         return h
+
+    def set_option(self, name: str, value: int):
+        """'bf16' (0/1, default 0): the reference's arithmetic for this call (torch.autocast(bfloat16) around fetch_codes_batch,
+        reason_tokenizer.py:114-118): bf16 operands with fp32 accumulation on tensor cores, attention included (head size 64); the default
+        is fp32 class (3xTF32 GEMMs, fp32 attention)."""
+        if name == "bf16":
+            self._bf16 = 1 if value else 0
+        _lib.check(_lib.lib().ua2_wavlm_set_option(self._ensure(), name.encode(), int(value)), f"set_option({name})")
 
     def last_launch_count(self) -> int:
         return int(_lib.lib().ua2_wavlm_last_launch_count(self._h)) if self._h is not None else 0
