@@ -21,6 +21,8 @@ audio = (torch.randn(B, 720240) * 0.1).to(dev)
 rs, lm = FE.Resample(24000, 16000), FE.WhisperLogMel()
 m = WavLMModel(WavLMConfig(), device=dev)
 m.MAX_BATCH = B
+if len(sys.argv) > 2 and sys.argv[2] == "bf16":
+    m.set_option("bf16", 1)
 
 
 def step():
