@@ -637,6 +637,98 @@ def bench_whisper_encoder(dev, batch=6, reps=3, cpu=True):
     return res
 
 
+def bench_tokenize_frontends(dev, batch=6, reps=3, cpu=True):
+    """The waveform side of ReasoningCodec_film's tokenize at the reference's batch of `batch` windows of
+    30 s + 240 samples (reason_tokenizer.py:86-110): get_whisper_features (resampler + log-mel, :67-72) on the device next to the
+    reference's own route for that step (device resample -> host WhisperFeatureExtractor -> device), and the WavLM base-plus encoder
+    up to hidden state 9 (AudioDiffusion1D.get_wavlm_feature :359-370, resampling and the 160 appended zeros included) in bf16 mode
+    (the reference's autocast) and fp32 class.  Random weights."""
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film import frontend as FE
+    from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.modeling_wavlm import WavLMConfig, WavLMModel
+
+    def timed(fn, n):
+        for _ in range(2):
+            out = fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out
+
+    g = torch.Generator().manual_seed(3)
+    audio_h = (torch.randn(batch, 720240, generator=g) * 0.1).pin_memory()
+    audio = audio_h.to(dev)
+    rs, lm = FE.Resample(24000, 16000), FE.WhisperLogMel()
+    ms_fe, feats = timed(lambda: lm(rs(audio, pad_to=lm.n_samples))["input_features"], reps)
+    res = {"config": f"{batch} windows of 30 s + 240 samples at 24 kHz, random weights",
+           "whisper_features": {"ms": round(ms_fe, 3), "x_realtime": round(batch * 30.0 / (ms_fe * 1e-3), 1), "launches": 3, "dtype": "f64 accumulation"}}
+    if cpu:
+        try:  # the reference's route for this step: third-party classes, present in this image
+            import torchaudio
+            from transformers import WhisperFeatureExtractor
+
+            t16, fe = torchaudio.transforms.Resample(24000, 16000).to(dev), WhisperFeatureExtractor()
+
+            def ref_route():
+                return fe(t16(audio).detach().cpu().numpy(), sampling_rate=16000, return_tensors="pt")["input_features"].to(dev)
+
+            ref = ref_route()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ref = ref_route()
+            torch.cuda.synchronize()
+            res["whisper_features"]["reference_route"] = {"kind": "reference", "ms": round((time.perf_counter() - t0) / reps * 1e3, 2),
+                                                          "what": "torchaudio Resample on the device, D2H, transformers WhisperFeatureExtractor on the host, H2D"}
+            res["whisper_features"]["parity_max_abs"] = float((ref - feats).abs().max())
+        except Exception as e:  # noqa: BLE001
+            res["whisper_features"]["reference_route"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.manual_seed(0)
+    m = WavLMModel(WavLMConfig(), device=dev)
+    m.MAX_BATCH = batch
+    c = m.config
+    t, ts = 480160, []
+    for k, st in zip(c.conv_kernel, c.conv_stride):
+        t = (t - k) // st + 1
+        ts.append(t)
+    T, D, Fi = ts[-1], c.hidden_size, c.intermediate_size
+    flop = sum(2.0 * ts[i] * c.conv_dim[i] * c.conv_kernel[i] * c.conv_dim[i - 1] for i in range(1, len(ts)))
+    flop += 2.0 * T * D * (D // c.num_conv_pos_embedding_groups) * c.num_conv_pos_embeddings + 2.0 * T * D * c.conv_dim[-1]
+    flop = batch * (flop + 9 * (2.0 * T * (4 * D * D + 2 * D * Fi) + 4.0 * T * T * D))
+
+    def wavlm():
+        return m.hidden_states_mean(rs(audio, pad_to=rs.out_length(audio.shape[-1]) + 160), 6, 10)
+
+    modes = {}
+    for mode, bf16 in (("bf16", 1), ("fp32_class", 0)):
+        m.set_option("bf16", bf16)
+        ms, out = timed(wavlm, reps)
+        modes[mode] = {"ms": round(ms, 2), "x_realtime": round(batch * 30.0 / (ms * 1e-3), 1), "tflops": round(flop / ms / 1e9, 1), "launches": m.last_launch_count()}
+    res["wavlm"] = {"config": "WavLM base-plus geometry (12 x 64 heads, d 768, 7 convolutions), hidden states 6..9 = 9 layers", "frames": T,
+                    "tflop_per_call": round(flop / 1e12, 3), "default_mode": "fp32 class (bf16 = the reference's autocast, option)", **modes["bf16"],
+                    "fp32_class": modes["fp32_class"]}
+    if cpu:
+        from oracle import wavlm_oracle as WO  # CPU-baseline leg: the oracle port (pinned to transformers.WavLMModel) on one 10 s clip
+
+        cfg = dict(WO.BASE_PLUS, num_hidden_layers=9)
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        clip = rs(audio[:1, :240000], pad_to=160160)
+        with torch.inference_mode():
+            t0 = time.perf_counter()
+            hs = WO.hidden_states(sd, cfg, clip.cpu())
+            dt = time.perf_counter() - t0
+        got = m.hidden_states_mean(clip, 6, 10).cpu()
+        ref = torch.stack(hs, 1)[:, 6:10].mean(1)
+        res["wavlm"]["cpu_baseline"] = {"kind": "port", "cores": torch.get_num_threads(), "sample": "1 clip of 10 s", "s": round(dt, 2),
+                                        "x_realtime": round(10.0 / dt, 1)}
+        res["wavlm"]["parity"] = {"fp32_class_vs_cpu_oracle_max_abs": float((got - ref).abs().max()), "out_scale": float(ref.abs().max())}
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def state_dict_to_cpu(model):
     return {k: v.detach().to("cpu") for k, v in model.state_dict().items()}
 
@@ -809,7 +901,7 @@ def main():
                    "ms_per_step": round(ems / args.steps, 2)}
 
         hbm_peak, peak_src = load_peaks()
-        roofline = cpu_base = codec = flow = parity = whisper = None
+        roofline = cpu_base = codec = flow = parity = whisper = frontends = None
         if rank == 0:
             roofline = time_dominant_kernel(model, hbm_peak)
             roofline["peak_source"] = peak_src
@@ -846,6 +938,10 @@ def main():
                     whisper = bench_whisper_encoder(dev, cpu=not args.no_cpu_baseline)
                 except Exception as e:  # noqa: BLE001
                     whisper = {"error": f"{type(e).__name__}: {e}"}
+                try:  # secondary metric (waveform front-end + second SSL encoder of tokenize), same rule
+                    frontends = bench_tokenize_frontends(dev, cpu=not args.no_cpu_baseline)
+                except Exception as e:  # noqa: BLE001
+                    frontends = {"error": f"{type(e).__name__}: {e}"}
     # ---- codec at N > 1: every rank encodes + decodes its own batch of 16 x 10 s clips (replicas, weak scaling), time = max over ranks;
     #      --codec-sweep: the clip length x batch grid of BASELINE.json config 5 with the clips of a point dealt to the ranks
     if world > 1 and not args.no_codec:
@@ -873,7 +969,7 @@ def main():
                           "warmup": warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config, "e2e": e2e,
                           "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
-                          "codec": codec, "codec_sweep": sweep, "flow_decoder": flow, "whisper_encoder": whisper}))
+                          "codec": codec, "codec_sweep": sweep, "flow_decoder": flow, "whisper_encoder": whisper, "tokenize_frontends": frontends}))
     if world > 1:
         dist.destroy_process_group()
 
