@@ -531,6 +531,39 @@ int ua2_wavlm_rel_bucket_table(int T, int num_buckets, int max_distance, int32_t
 int ua2_wavlm_ops_f32(int op, const float* a, const float* b, const float* c, const float* d, float* y, int i0, int i1, int i2, int i3, int i4,
                       void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Reasoning encoder (`AudioThinking`) of tokenize, up to the query tokens that go into reasoning_vq.  Replaces
+ * AudioDiffusion1D.encode_reasoning_part (models/AudioDiffusion1D.py:372-390: down_sampling_layer_whisper, concatenation with the
+ * BEST-RQ features, semantic_merge_proj, set_masking :458-477, 5 x modules/transformer.py TransformerBlock :645-783 with
+ * power-normalised linears, per-head LayerNorm of q / k, partial rotary embedding, sigmoid GLU and LayerScale) before
+ * extract_mask_positions (:479-486, a strided slice) and the residual VQ (ua2_rvq_*).  csrc/ua2_thinking.cu.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ua2_thinking_cfg {    /* the reference's values: 768 / 128 / 5 / 5 / 1024 / 1024 / 4 */
+  int32_t dim;                       /* multiple of dim_heads */
+  int32_t dim_heads;                 /* 128 */
+  int32_t depth;
+  int32_t interval;                  /* frames per query token */
+  int32_t whisper_dim;
+  int32_t mu_dim;                    /* BEST-RQ feature width */
+  int32_t ff_mult;
+} ua2_thinking_cfg;
+typedef struct ua2_thinking ua2_thinking;
+
+int ua2_thinking_create(const ua2_thinking_cfg* cfg, ua2_thinking** out);
+int ua2_thinking_destroy(ua2_thinking* h);
+/* one fp32 parameter by its AudioThinking state-dict key ("cls_token", "down_sampling_layer_whisper.weight", "semantic_merge_proj.bias",
+ * "encoder_transformers.2.self_attn.q_norm.weight", "encoder_transformers.2.rope.inv_freq", ...).  Weight-normed linears are given
+ * with the normalisation applied: "...self_attn.to_qkv.weight", "...self_attn.to_out.weight", "...ff.ff.0.proj.weight",
+ * "...ff.ff.2.weight" = g * v / ||v||_row of the parametrizations.weight.original0 / original1 pair. */
+int ua2_thinking_load_weight(ua2_thinking* h, const char* key, const float* dptr, const int64_t* shape, int ndim);
+int ua2_thinking_finalize(ua2_thinking* h, void* stream);
+/* rows per clip of the encoder's sequence, T + T / interval with T = min(Tw / 2, Tb); 0 when T is not a positive multiple of interval */
+long long ua2_thinking_rows(ua2_thinking* h, int Tw, int Tb);
+/* whisper (B, whisper_dim, Tw), mu (B, mu_dim, Tb) fp32 channels-first -> out (B, rows, dim): the encoder's output sequence; the query
+ * tokens are its rows interval, 2 interval + 1, ... (out[:, interval :: interval + 1]) */
+int ua2_thinking_encode(ua2_thinking* h, const float* whisper, const float* mu, int B, int Tw, int Tb, float* out, void* stream);
+int ua2_thinking_last_launch_count(ua2_thinking* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,11 @@ class WavLMCfg(C.Structure):
                 ("max_bucket_distance", C.c_int32), ("layer_norm_eps", C.c_float)]
 
 
+class ThinkingCfg(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("dim_heads", C.c_int32), ("depth", C.c_int32), ("interval", C.c_int32), ("whisper_dim", C.c_int32),
+                ("mu_dim", C.c_int32), ("ff_mult", C.c_int32)]
+
+
 # every symbol include/ua2_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -149,6 +154,13 @@ SYMBOLS = {
     "ua2_wavlm_last_launch_count": (C.c_int, [_P]),
     "ua2_wavlm_rel_bucket_table": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
     "ua2_wavlm_ops_f32": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ua2_thinking_create": (C.c_int, [C.POINTER(ThinkingCfg), C.POINTER(_P)]),
+    "ua2_thinking_destroy": (C.c_int, [_P]),
+    "ua2_thinking_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ua2_thinking_finalize": (C.c_int, [_P, _P]),
+    "ua2_thinking_rows": (C.c_longlong, [_P, C.c_int, C.c_int]),
+    "ua2_thinking_encode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "ua2_thinking_last_launch_count": (C.c_int, [_P]),
     "ua2_stx_create": (C.c_int, [C.POINTER(StxCfg), C.POINTER(_P)]),
     "ua2_stx_destroy": (C.c_int, [_P]),
     "ua2_stx_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),

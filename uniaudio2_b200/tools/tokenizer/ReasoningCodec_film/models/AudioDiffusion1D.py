@@ -178,10 +178,11 @@ class AudioDiffusion1D(nn.Module):
         self.reason_adaptor = lin(codec_dim, codec_dim)
         # SSL front-ends (AudioDiffusion1D.py:222-236).  The Whisper encoder (modeling_whisper.py) and the WavLM encoder
         # (modeling_wavlm.py) exist in this package; they are attached by the caller because their sizes come from the checkpoints'
-        # configs, not from this class's arguments.  The BEST-RQ conformer is not built.
+        # configs, not from this class's arguments.  The BEST-RQ conformer is not built (its features are inputs).
         self.whisper_encoder = None
         self.wavlm_encoder = None
         self.wavlm_transfer = None
+        self.audio_thinking = None  # the reasoning encoder (models/audio_thinking.py), attached like the SSL encoders
 
     def attach_whisper_encoder(self, encoder):
         """`self.whisper_encoder = WhisperModel.from_pretrained(whisper_path).encoder` (AudioDiffusion1D.py:223): the caller builds the
@@ -198,6 +199,19 @@ class AudioDiffusion1D(nn.Module):
         n_len = max(n_len, len_semantic * 2)
         whisper_embeds = self.whisper_encoder(mels, return_dict=True).last_hidden_state
         return whisper_embeds[:, :n_len, :].transpose(1, 2)
+
+    def attach_audio_thinking(self, audio_thinking):
+        """`self.audio_thinking = AudioThinking(dim=self.codec_dim, interval=5, encoder_depth=5, ...)` (AudioDiffusion1D.py:303)."""
+        self.audio_thinking = audio_thinking
+        return audio_thinking
+
+    @torch.inference_mode()
+    def encode_reasoning_part(self, whisper_embeds, muencoder_embeds):
+        """AudioDiffusion1D.py:372-390: (B, 1024, Tw) Whisper features + (B, 1024, Tb) BEST-RQ features -> (quantized reasoning features
+        (B, T / 5, codec_dim), reasoning codes (B, T / 5, 8), None)."""
+        if self.audio_thinking is None:
+            raise _lib.Ua2Error("no reasoning encoder attached (attach_audio_thinking)")
+        return self.audio_thinking.encode_reasoning_part(whisper_embeds, muencoder_embeds)
 
     def attach_wavlm_encoder(self, encoder):
         """`self.wavlm_encoder = AutoModel.from_pretrained(wav_lm_path)` + `self.wavlm_transfer = Resample(24000, 16000)`
