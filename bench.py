@@ -726,6 +726,36 @@ def bench_tokenize_frontends(dev, batch=6, reps=3, cpu=True):
         res["wavlm"]["parity"] = {"fp32_class_vs_cpu_oracle_max_abs": float((got - ref).abs().max()), "out_scale": float(ref.abs().max())}
     del m
     torch.cuda.empty_cache()
+    try:  # reasoning encoder (AudioThinking, AudioDiffusion1D.py:169-188, :372-390): 1500 Whisper + 750 BEST-RQ frames per window -> 150 query tokens
+        from uniaudio2_b200.tools.tokenizer.ReasoningCodec_film.models.audio_thinking import AudioThinking
+
+        at = AudioThinking(device=dev)
+        with torch.no_grad():
+            for prm in at.reasoning_vq.parameters():
+                prm.normal_()
+        wh, mu = torch.randn(batch, 1024, 1500, device=dev), torch.randn(batch, 1024, 750, device=dev)
+        ms_at, q = timed(lambda: at.encode_reasoning_part(wh, mu)[0], reps)
+        Tn, Dm, Ff = 900, 768, 3072
+        fl = batch * (2.0 * 750 * 1024 * 2048 + 2.0 * 750 * 2048 * Dm + 5 * (2.0 * Tn * (4 * Dm * Dm + 3 * Dm * Ff) + 4.0 * Tn * Tn * Dm))
+        res["audio_thinking"] = {"config": "AudioThinking (dim 768, 6 x 128 heads, 5 blocks) + 8-level residual VQ, fp32 class", "ms": round(ms_at, 2),
+                                 "x_realtime": round(batch * 30.0 / (ms_at * 1e-3), 1), "tflops_fp32_equivalent": round(fl / ms_at / 1e9, 1),
+                                 "launches": at.last_launch_count(), "out_shape": list(q.shape)}
+        if cpu:
+            from oracle import thinking_oracle as TO  # CPU-baseline leg: the oracle port (bit-equal to the reference source) on one window
+
+            sd = {k: v.detach().cpu() for k, v in at.state_dict().items() if not k.startswith("reasoning_vq.")}
+            with torch.inference_mode():
+                t0 = time.perf_counter()
+                ref = TO.encode(sd, TO.CFG, wh[:1].cpu(), mu[:1].cpu())
+                dt = time.perf_counter() - t0
+            got = at.query_tokens(wh[:1], mu[:1]).cpu()
+            res["audio_thinking"]["cpu_baseline"] = {"kind": "port", "cores": torch.get_num_threads(), "sample": "1 window of 30 s", "s": round(dt, 2),
+                                                     "x_realtime": round(30.0 / dt, 1)}
+            res["audio_thinking"]["parity"] = {"query_tokens_vs_cpu_oracle_max_abs": float((got - ref).abs().max()), "out_scale": float(ref.abs().max())}
+        del at
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        res["audio_thinking"] = {"error": f"{type(e).__name__}: {e}"}
     return res
 
 

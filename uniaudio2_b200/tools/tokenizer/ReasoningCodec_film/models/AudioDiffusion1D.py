@@ -183,6 +183,7 @@ class AudioDiffusion1D(nn.Module):
         self.wavlm_encoder = None
         self.wavlm_transfer = None
         self.audio_thinking = None  # the reasoning encoder (models/audio_thinking.py), attached like the SSL encoders
+        self.pretrained_model = None  # BEST-RQ feature provider (attach_bestrq); the conformer itself is not built here
 
     def attach_whisper_encoder(self, encoder):
         """`self.whisper_encoder = WhisperModel.from_pretrained(whisper_path).encoder` (AudioDiffusion1D.py:223): the caller builds the
@@ -199,6 +200,31 @@ class AudioDiffusion1D(nn.Module):
         n_len = max(n_len, len_semantic * 2)
         whisper_embeds = self.whisper_encoder(mels, return_dict=True).last_hidden_state
         return whisper_embeds[:, :n_len, :].transpose(1, 2)
+
+    def attach_bestrq(self, pretrained_model):
+        """`self.pretrained_model = BESTRQ_Model(...)` (AudioDiffusion1D.py:228-229): any object with
+        `extract_continous_embeds_multiple(input_audios (B, 1, samples)) -> (acoustic (B, 1024, Tb), semantic (B, 1024, Tb))`.  The BEST-RQ
+        MusicFM conformer itself is not built in this package: the caller supplies it."""
+        self.pretrained_model = pretrained_model
+        return pretrained_model
+
+    @torch.inference_mode()
+    def fetch_codes_batch(self, input_audios, spectrograms, additional_feats=None, return_reasoning_text=False, film_masks=None):
+        """AudioDiffusion1D.py:492-551: input_audios (B, 1, samples) at 24 kHz + Whisper input features (B, 80, 3000) ->
+        ([reasoning codes (B, Tq, 8)], [reconstruction codes (B, T, 8)], [merge features (B, T, codec_dim)]) - the BEST-RQ provider,
+        the Whisper encoder, the WavLM encoder, the reasoning encoder and the own-code chain of this class in the reference's order."""
+        if return_reasoning_text:
+            raise NotImplementedError("the reasoning-text head (llama tokenizer + LoRA LLM) is not on this path")
+        if getattr(self, "pretrained_model", None) is None:
+            raise _lib.Ua2Error("no BEST-RQ feature provider attached (attach_bestrq)")
+        bestrq_emb_acoustic, bestrq_emb_semantic = self.pretrained_model.extract_continous_embeds_multiple(input_audios.clone())
+        len_semantic = bestrq_emb_semantic.shape[2]
+        whisper_embeds = self.get_whisper_feature(spectrograms, input_audios.shape[-1], len_semantic)
+        wavlm_embeds = self.get_wavlm_feature(input_audios, len_semantic)
+        quantized_reasoning, reasoning_codes, _ = self.encode_reasoning_part(whisper_embeds, bestrq_emb_semantic)
+        merge_codes, merge_features = self.fetch_codes_from_features(whisper_embeds, wavlm_embeds, bestrq_emb_acoustic, bestrq_emb_semantic,
+                                                                     quantized_reasoning, film_masks=film_masks)
+        return [reasoning_codes], [merge_codes], [merge_features]
 
     def attach_audio_thinking(self, audio_thinking):
         """`self.audio_thinking = AudioThinking(dim=self.codec_dim, interval=5, encoder_depth=5, ...)` (AudioDiffusion1D.py:303)."""

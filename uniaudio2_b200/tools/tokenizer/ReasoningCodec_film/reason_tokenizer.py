@@ -9,8 +9,9 @@ one AudioDiffusion1D.inference_codes call (a flow-matching solve) whose first la
 window's latents; each window's latents go through the SQ-codec decoder, and consecutive waveforms are joined by a linear
 cross-fade over the shared quarter (on the host, in float64, like the reference).  tests/test_detok_oracle.py checks this host
 logic bit-exactly against fixtures produced by the unmodified reference source; `model` and `SQCodec` are the uniaudio2_b200
-drop-ins (GPU only).  Of the tokenize direction this class carries `get_whisper_features` (:67-72); the SSL
-encoders hang off AudioDiffusion1D (Whisper, WavLM; the BEST-RQ conformer and AudioThinking are not built).
+drop-ins (GPU only).  Of the tokenize direction this class carries `get_whisper_features` (:67-72), `audio2token`
+(:85-129) and `tokenize` (:377-391); the encoders hang off AudioDiffusion1D (Whisper, WavLM, AudioThinking; BEST-RQ features come from a
+provider the caller attaches).  tests/test_tokenize_host_cpu.py checks the windowing bit-exactly against the unmodified reference source.
 """
 import math
 from dataclasses import dataclass
@@ -96,6 +97,58 @@ class ReasoningTokenizer:
                 raise ValueError(f"sample rate {sr}: the reference's transfer16k resamples from 24000 Hz only")
             audio = self.transfer16k(audio, pad_to=self.wav_processor.n_samples)
         return self.wav_processor(audio, sampling_rate=16000, return_tensors="pt")["input_features"]
+
+    @torch.no_grad()
+    def audio2token(self, orig_samples, sr, return_reasoning_text=False, task_name="speech_reasoning", min_duration=30, batch_size=6):
+        """reason_tokenizer.py:85-129: (channels, samples) at 24 kHz -> (reason codes (1, 8, Tr), reconstruction codes (1, 8, Ts)).
+        The clip is made periodic (doubled until it covers one window, then once more), cut into windows of min_duration s + 240 samples
+        and encoded `batch_size` windows at a time by AudioDiffusion1D.fetch_codes_batch; the code sequences are cut back to the clip's
+        own length (12.5 and 5 frames per second, plus one)."""
+        if return_reasoning_text:
+            raise NotImplementedError("the reasoning-text head is not on this path")
+        if orig_samples.ndim == 2:
+            audios = orig_samples.unsqueeze(0).to(self.device)
+        elif orig_samples.ndim == 3:
+            audios = orig_samples.to(self.device)
+        else:
+            raise AssertionError(tuple(orig_samples.shape))  # the reference asserts ndim in (2, 3)
+        audios = audios.squeeze(0)
+        n_orig = audios.shape[-1]
+        window = int(min_duration * self.sample_rate) + 240  # 240 extra samples so that the last frame of a window is complete
+        n_rec = int(n_orig / float(self.sample_rate) * self.rec_frame_rate) + 1
+        n_reason = int(n_orig / float(self.sample_rate) * self.reason_frame_rate) + 1
+        while audios.shape[-1] < window:
+            audios = torch.cat([audios, audios], -1)
+        n_windows = audios.shape[-1] // (window - 240) + 1
+        audios = torch.cat([audios, audios], -1)[:, :int(n_windows * window)]
+        windows = audios.reshape(1, -1, window).permute(1, 0, 2).reshape(-1, 1, window)
+        reason, rec = [], []
+        for i in range(0, windows.shape[0], batch_size):
+            chunk = windows[i:i + batch_size]
+            mels = self.get_whisper_features(chunk[:, 0, :], 24000).to(self.device)
+            reasoning_codes, rec_codes, _ = self.model.fetch_codes_batch(chunk, mels, additional_feats=[], return_reasoning_text=False)
+            reason.append(torch.cat(reasoning_codes, 1))
+            rec.append(torch.cat(rec_codes, 1))
+        reason = torch.cat(reason, 0).reshape(-1, 8).unsqueeze(0)[:, :n_reason, :].transpose(1, 2)
+        rec = torch.cat(rec, 0).reshape(-1, 8).unsqueeze(0)[:, :n_rec, :].transpose(1, 2)
+        return reason, rec
+
+    def tokenize(self, wav, return_reasoning_text=False, task_name="asr", min_duration=30):
+        """reason_tokenizer.py:377-391: a path -> (reason codes (8, Tr), reconstruction codes (8, Ts)); a tensor is returned as it is."""
+        if isinstance(wav, str):
+            import torchaudio  # file decoding only
+
+            prompt_audio, fs = torchaudio.load(wav)
+            if prompt_audio.shape[0] == 2:
+                prompt_audio = prompt_audio.mean(0, keepdim=True)
+            if fs != self.sample_rate:
+                prompt_audio = torchaudio.functional.resample(prompt_audio, fs, self.sample_rate)
+                fs = self.sample_rate
+            reason_codec, rec_codec = self.audio2token(prompt_audio, fs, return_reasoning_text, task_name=task_name)
+            return reason_codec.squeeze(0), rec_codec.squeeze(0)
+        if isinstance(wav, torch.Tensor):
+            return wav
+        raise NotImplementedError
 
     def _randn(self, *shape):
         """Noise the reference draws on the CPU generator and then moves to the device (reason_tokenizer.py:234, :279)."""
