@@ -76,6 +76,55 @@ def test_create_validates_config(L):
     assert b"head_size" in L.ua2_last_error()
 
 
+def test_tokenize_handles_validate_config_and_keys_without_gpu(L):
+    """ua2_wavlm_* / ua2_thinking_* / the front-end operators: configuration, key, shape and size errors are rejected before any CUDA call."""
+    from uniaudio2_b200 import _lib
+
+    arr = lambda v: (C.c_int32 * 8)(*(list(v) + [0] * (8 - len(v))))
+    dims, ker, strd = arr([512] * 7), arr([10, 3, 3, 3, 3, 2, 2]), arr([5, 2, 2, 2, 2, 2, 2])
+    h = C.c_void_p()
+    good = _lib.WavLMCfg(768, 12, 3072, 12, 7, dims, ker, strd, 0, 128, 16, 320, 800, 1e-5)
+    assert L.ua2_wavlm_create(C.byref(good), C.byref(h)) == 0
+    assert L.ua2_wavlm_frames(h, 480160) == 1500 and L.ua2_wavlm_frames(h, 300) == 0  # 30 s + 160 zeros -> 1500 frames; too short -> 0
+    with pytest.raises(ValueError):  # forward before finalize
+        _lib.check(L.ua2_wavlm_forward(h, C.c_void_p(16), 480160, 1, 480160, 6, 10, C.c_void_p(16), None, None))
+    shape3 = (C.c_int64 * 3)(512, 1, 10)
+    assert L.ua2_wavlm_load_weight(h, b"feature_extractor.conv_layers.0.conv.weight", C.c_void_p(16), shape3, 3) == 0
+    with pytest.raises(ValueError):  # conv_bias = False in this configuration
+        _lib.check(L.ua2_wavlm_load_weight(h, b"feature_extractor.conv_layers.0.conv.bias", C.c_void_p(16), (C.c_int64 * 1)(512), 1))
+    with pytest.raises(ValueError):  # wrong shape
+        _lib.check(L.ua2_wavlm_load_weight(h, b"encoder.layers.0.attention.rel_attn_embed.weight", C.c_void_p(16), (C.c_int64 * 2)(320, 8), 2))
+    with pytest.raises(ValueError):  # only layer 0 carries the bucket embedding
+        _lib.check(L.ua2_wavlm_load_weight(h, b"encoder.layers.1.attention.rel_attn_embed.weight", C.c_void_p(16), (C.c_int64 * 2)(320, 12), 2))
+    with pytest.raises(ValueError):  # missing parameters
+        _lib.check(L.ua2_wavlm_finalize(h, None))
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_wavlm_set_option(h, b"no_such_option", 1))
+    assert L.ua2_wavlm_destroy(h) == 0
+    for bad in (_lib.WavLMCfg(768, 12, 3072, 12, 7, dims, ker, strd, 0, 128, 8, 320, 800, 1e-5),     # 96 channels per positional-convolution group
+                _lib.WavLMCfg(768, 10, 3072, 12, 7, dims, ker, strd, 0, 128, 16, 320, 800, 1e-5),    # hidden / heads not an integer
+                _lib.WavLMCfg(768, 12, 3072, 12, 7, dims, arr([20, 3, 3, 3, 3, 2, 2]), strd, 0, 128, 16, 320, 800, 1e-5)):  # first kernel > 16
+        with pytest.raises(ValueError):
+            _lib.check(L.ua2_wavlm_create(C.byref(bad), C.byref(h)))
+    tc = _lib.ThinkingCfg(768, 128, 5, 5, 1024, 1024, 4)
+    assert L.ua2_thinking_create(C.byref(tc), C.byref(h)) == 0
+    assert L.ua2_thinking_rows(h, 1500, 750) == 900 and L.ua2_thinking_rows(h, 1500, 751) == 900 and L.ua2_thinking_rows(h, 1500, 748) == 0
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_thinking_load_weight(h, b"encoder_transformers.5.ff_scale.scale", C.c_void_p(16), (C.c_int64 * 1)(768), 1))  # 5 blocks: 0..4
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_thinking_encode(h, C.c_void_p(16), C.c_void_p(16), 1, 1500, 750, C.c_void_p(16), None))  # before finalize
+    assert L.ua2_thinking_destroy(h) == 0
+    with pytest.raises(ValueError):
+        _lib.check(L.ua2_thinking_create(C.byref(_lib.ThinkingCfg(768, 64, 5, 5, 1024, 1024, 4)), C.byref(h)))  # dim_heads is 128 in the reference
+    p = C.c_void_p(16)
+    with pytest.raises(ValueError):  # n_valid beyond ceil(new * L / orig)
+        _lib.check(L.ua2_resample_f32(p, 300, p, p, 400, 1, 300, 300, 400, 3, 2, 10, None))
+    with pytest.raises(ValueError):  # more frames than 1 + L / hop
+        _lib.check(L.ua2_whisper_logmel_f32(p, 16000, p, p, p, 1, 16000, 400, 160, 80, 102, None))
+    with pytest.raises(ValueError):  # odd n_fft
+        _lib.check(L.ua2_whisper_logmel_f32(p, 16000, p, p, p, 1, 16000, 401, 160, 80, 100, None))
+
+
 def test_sampler_argument_errors_without_gpu(L):
     """model_new.py:165-180 error cases are rejected before any CUDA call."""
     from uniaudio2_b200 import _lib
