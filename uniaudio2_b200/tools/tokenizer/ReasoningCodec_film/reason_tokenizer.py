@@ -122,6 +122,11 @@ class ReasoningTokenizer:
         n_windows = audios.shape[-1] // (window - 240) + 1
         audios = torch.cat([audios, audios], -1)[:, :int(n_windows * window)]
         windows = audios.reshape(1, -1, window).permute(1, 0, 2).reshape(-1, 1, window)
+        # the reference encodes under torch.autocast(device_type='cuda', dtype=torch.bfloat16) (:114-118): the two big encoders follow it
+        # through their "bf16" option (bf16 operands, fp32 accumulation, tensor-core attention) when autocast_bf16 is set
+        for enc in (getattr(self.model, "whisper_encoder", None), getattr(self.model, "wavlm_encoder", None)):
+            if enc is not None and hasattr(enc, "set_option"):
+                enc.set_option("bf16", 1 if self.autocast_bf16 else 0)
         reason, rec = [], []
         for i in range(0, windows.shape[0], batch_size):
             chunk = windows[i:i + batch_size]
